@@ -1,0 +1,225 @@
+/*
+ * mcp.h -- C ABI of libmcp.so, the B200-native replacement for the one hot path of
+ * mapr-demos/monte-carlo-portfolios:
+ *
+ *   portfolio x scenario valuation -> per-portfolio loss/tail statistics ->
+ *   sorted breach-trial index lists -> JavaFastPFOR-format encoding (and decoding)
+ *
+ * The reference is pure Java with NO native seam (no JNI, no `native` methods).  The
+ * Java-side interfaces this ABI sits behind are
+ *
+ *   IntegerCODEC.compress / uncompress
+ *       JavaFastPFOR/src/main/java/me/lemire/integercompression/IntegerCODEC.java:36-58
+ *   SkippableIntegerCODEC.headlessCompress / headlessUncompress
+ *       .../SkippableIntegerCODEC.java:43-66
+ *   LoadPortfolios.getCompressedInstruments / getDecompressedInstruments
+ *       maprdb-portfolio/src/main/java/com/mapr/db/data/LoadPortfolios.java:608-623, 625-662
+ *   the codec instance chosen at LoadPortfolios.java:725-726
+ *
+ * INTEGRATION.md shows the JNI / Panama-FFM stubs a maintainer would add.  Everything
+ * here is plain pointers and sizes: JNI `GetPrimitiveArrayCritical` / FFM
+ * `MemorySegment` friendly, no callbacks, no ownership transfer, never throws.
+ *
+ * There is NO CPU fallback: every entry point that computes runs sm_100a kernels and
+ * fails with MCP_E_CUDA if no usable GPU is present.
+ *
+ * Threading: an mcp_ctx is bound to one GPU and one CUDA stream and must be used by
+ * one thread at a time (the same rule the reference states for FastPFOR instances,
+ * FastPFOR.java:36-37).  Use one ctx per thread / per GPU.
+ */
+#ifndef MCP_H
+#define MCP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCP_VERSION 100 /* 0.1.0 */
+
+/* ------------------------------------------------------------------ errors */
+enum {
+    MCP_OK            = 0,
+    MCP_E_ARG         = -1, /* null pointer, negative size, unknown codec id ...            */
+    MCP_E_CAP         = -2, /* caller's output buffer too small (Java: ArrayIndexOutOfBounds) */
+    MCP_E_CUDA        = -3, /* CUDA runtime error / no device                               */
+    MCP_E_NOMEM       = -4, /* device or host allocation failed                             */
+    MCP_E_FORMAT      = -5, /* malformed compressed stream                                  */
+    MCP_E_STATE       = -6, /* call sequence error (run before upload, ...)                 */
+    MCP_E_UNSUPPORTED = -7, /* valid request this build does not implement  */
+    MCP_E_NCCL        = -8
+};
+typedef struct mcp_ctx mcp_ctx;
+
+const char *mcp_strerror(int err);
+/* detail of the last error on this ctx (CUDA error string etc.); never NULL */
+const char *mcp_last_error(const mcp_ctx *ctx);
+
+/* ------------------------------------------------------------------ codecs */
+/* codec_id = one of MCP_CODEC_* optionally OR-ed with MCP_FLAG_DELTA */
+enum {
+    MCP_CODEC_BP32_VB        = 0, /* new Composition(new BinaryPacking(), new VariableByte())   LoadPortfolios.java:725 ("bpacking+variablebyte") */
+    MCP_CODEC_FASTPFOR256_VB = 1, /* new Composition(new FastPFOR(), new VariableByte())        FastPFOR.java:22         */
+    MCP_CODEC_FASTPFOR128_VB = 2, /* new Composition(new FastPFOR128(), new VariableByte())     FastPFOR128.java:33      */
+    MCP_CODEC_IBP32_IVB      = 3, /* new IntegratedComposition(new IntegratedBinaryPacking(), new IntegratedVariableByte()) */
+    MCP_CODEC_SK_IBP32_IVB   = 4, /* new IntegratedIntCompressor()  (n, then headless stream)   IntegratedIntCompressor.java:38-62 */
+    MCP_CODEC_VB             = 5, /* new VariableByte()                                         VariableByte.java:32     */
+    MCP_CODEC_SK_BP32_VB     = 6, /* new IntCompressor()            (n, then headless stream)   IntCompressor.java:38-61 */
+    MCP_CODEC_COUNT          = 7,
+    MCP_CODEC_MASK           = 0xff,
+    MCP_FLAG_DELTA           = 0x100 /* Delta.delta(int[]) before compress, inverse after uncompress (Delta.java:24-28,84-88) */
+};
+
+/* byte framing of a compressed list */
+enum {
+    MCP_FRAME_WORDS = 0, /* the codec's int[] output, native (little-endian) 32-bit words = Java int[0..outpos) */
+    MCP_FRAME_APP   = 1  /* LoadPortfolios framing: big-endian bytes of outpos+1 ints (one trailing zero int)
+                            LoadPortfolios.java:622, BitManipulationHelper.java:29-66 */
+};
+
+/* ------------------------------------------------------------------ context */
+int  mcp_create(int device, mcp_ctx **out);
+void mcp_destroy(mcp_ctx *ctx);
+int  mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
+int  mcp_sync(mcp_ctx *ctx);
+
+/* Upper bound on the encoded size in BYTES of one list of n ints under `framing`
+ * (the analogue of the reference's `new int[4*n + 1024]`, LoadPortfolios.java:611). */
+int64_t mcp_codec_max_bytes(int codec_id, int framing, int64_t n);
+
+/* ----------------------------------------------- single-list drop-in calls
+ * IntegerCODEC.compress(in, inpos, inlength, out, outpos) with a fresh codec:
+ *   in/out are the Java arrays already offset by inpos/outpos; *out_words receives the
+ *   number of ints written (what Java adds to outpos); out_cap is out.length - outpos.
+ *   All inlength ints are consumed (Java adds inlength to inpos).
+ * These run the same kernels as the batched calls with nlists = 1: correct, but a GPU
+ * round trip per list -- use the batched calls for throughput.
+ */
+int mcp_codec_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
+                       int32_t *out, int32_t out_cap, int32_t *out_words);
+/* IntegerCODEC.uncompress(in, inpos, inlength, out, outpos): *out_count = ints produced */
+int mcp_codec_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
+                         int32_t *out, int32_t out_cap, int32_t *out_count);
+/* LoadPortfolios.getCompressedInstruments(ArrayList<Integer>) -> byte[] (MCP_FRAME_APP) */
+int mcp_get_compressed_instruments(mcp_ctx *ctx, int codec_id, const int32_t *instruments, int32_t n,
+                                   uint8_t *bytes, int64_t cap, int64_t *nbytes);
+/* LoadPortfolios.getDecompressedInstruments(byte[], numberOfIntegers) -> int[] */
+int mcp_get_decompressed_instruments(mcp_ctx *ctx, int codec_id, const uint8_t *bytes, int64_t nbytes,
+                                     int32_t number_of_integers, int32_t *out);
+
+/* ------------------------------------------------------- batched codec, host
+ * CSR in, CSR out.  vals[list_off[i] .. list_off[i+1]) is list i.  On return
+ * out_off[0..nlists] are byte offsets into out (out_off[0] = 0) and *out_len the total.
+ * Copies host->device, runs the kernels, copies back.  MCP_E_CAP if cap is too small
+ * (then *out_len holds the required size).
+ */
+int mcp_codec_encode(mcp_ctx *ctx, int codec_id, int framing,
+                     const int32_t *vals, const int64_t *list_off, int64_t nlists,
+                     int64_t *out_off, uint8_t *out, int64_t cap, int64_t *out_len);
+/* in[in_off[i] .. in_off[i+1]) is the compressed list i; out_off gives where its
+ * decoded ints go (out_off[i+1]-out_off[i] = the list's length, which the reference
+ * stores beside the blob as "uncompressedIntegerSize", LoadPortfolios.java:600). */
+int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing,
+                     const uint8_t *in, const int64_t *in_off, int64_t nlists,
+                     int32_t *out, const int64_t *out_off);
+
+/* ----------------------------------------------------- batched codec, device
+ * Same, but every pointer is a DEVICE pointer on ctx's GPU (for callers whose lists
+ * are already in HBM).  total_out is a HOST pointer.  d_out_off is written.
+ */
+int mcp_codec_encode_dev(mcp_ctx *ctx, int codec_id, int framing,
+                         const int32_t *d_vals, const int64_t *d_list_off, int64_t nlists, int64_t total_vals,
+                         int64_t *d_out_off, uint8_t *d_out, int64_t cap, int64_t *total_out);
+int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing,
+                         const uint8_t *d_in, const int64_t *d_in_off, int64_t nlists,
+                         int32_t *d_out, const int64_t *d_out_off);
+
+/* -------------------------------------------------------- risk path: inputs
+ * Exposure matrix E: row-major P x F doubles.  Scenario matrix S: row-major N x F
+ * doubles, row n = trial n.  (The reference defines neither: portfolios.json holds
+ * (instrument, weight) lists, macro.json holds 10 factor rows, and no Java code joins
+ * them -- SURVEY.md section 0; DESIGN.md section 3 is the specification.)
+ */
+int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F);
+int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F);
+/* Counter-based on-device generation (Philox4x32-10, Irwin-Hall(12) variates;
+ * value = fma(x, scale, shift); bit-identical to oracle/risk_oracle.c orc_gen_normal).
+ * row0 = global index of the first row (for sharded generation). */
+int mcp_generate_exposures(mcp_ctx *ctx, int64_t P, int32_t F, uint64_t seed, double scale, double shift, int64_t row0);
+int mcp_generate_scenarios(mcp_ctx *ctx, int64_t N, int32_t F, uint64_t seed, double scale, double shift, int64_t row0);
+int mcp_download_exposures(mcp_ctx *ctx, double *E);
+int mcp_download_scenarios(mcp_ctx *ctx, double *S);
+
+/* V[p0..p1) x [0..N) -> host, row-major (debug / parity: bit-identical to the oracle) */
+int mcp_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *V);
+
+/* tail size t = N - ceil(alpha*N - 1e-7) + 1 */
+int64_t mcp_tail_size(int64_t N, double alpha);
+
+/* ----------------------------------------------------------- risk path: run
+ * Values every uploaded portfolio under every uploaded scenario, reduces, selects,
+ * compacts and encodes ON THE DEVICE; results stay in HBM until fetched.
+ *   trial_base: global index of scenario row 0 (trial-sharded runs), else 0.
+ */
+int mcp_run(mcp_ctx *ctx, double alpha, int codec_id, int framing);
+
+/* sizes of the last run */
+int mcp_run_sizes(mcp_ctx *ctx, int64_t *P, int64_t *N, int64_t *tail, int64_t *enc_bytes);
+
+/* Fetch results of the last mcp_run (any pointer may be NULL):
+ *   mean, variance (population), var_loss, cvar : double[P];  var_trial : int32[P]
+ *   breach_idx : int32[P * tail] ascending trial indices per portfolio
+ *   enc_off : int64[P+1] byte offsets;  enc : uint8[enc_cap]
+ */
+int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
+              int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap);
+
+/* One-call host-buffer version (upload + run + fetch): the end-to-end path */
+int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int64_t N, int32_t F,
+                 double alpha, int codec_id, int framing,
+                 double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
+                 int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len);
+
+/* ------------------------------------------------------------- measurement
+ * Kernel timing with CUDA events on ctx's own stream.  Classes: */
+enum {
+    MCP_K_VALUE = 0,   /* valuation (+ fused moments / threshold filter) */
+    MCP_K_SELECT = 1,  /* radix-select / prune / finalize               */
+    MCP_K_ENCODE = 2,  /* codec encode (size + emit)                    */
+    MCP_K_DECODE = 3,  /* codec decode                                  */
+    MCP_K_SCAN = 4,    /* prefix sums / bookkeeping                     */
+    MCP_K_GEN = 5,     /* generators, FP64 peak probe                   */
+    MCP_K_COUNT = 6
+};
+int mcp_profile_enable(mcp_ctx *ctx, int on);
+int mcp_profile_reset(mcp_ctx *ctx);
+/* per class: number of launches and summed device ms since the last reset (syncs the stream) */
+int mcp_profile_get(mcp_ctx *ctx, int64_t launches[MCP_K_COUNT], double ms[MCP_K_COUNT]);
+/* whole-region timing on ctx's stream */
+int mcp_timer_start(mcp_ctx *ctx);
+int mcp_timer_stop(mcp_ctx *ctx, double *ms);
+/* dependent-free DFMA issue-rate probe: returns achieved FP64 TFLOP/s (2 flop per FMA) */
+int mcp_fp64_peak(mcp_ctx *ctx, double *tflops);
+/* write `bytes` of zeros to a scratch buffer (> L2) to flush the L2 between timed steps */
+int mcp_flush_l2(mcp_ctx *ctx);
+
+/* Synthetic breach lists on device (Bernoulli(rate) mask over n_trials per list; Philox;
+ * bit-identical to oracle orc_gen_breach_list).  Returns device pointers owned by ctx
+ * (valid until the next call / destroy).  first_list = global id of list 0. */
+int mcp_generate_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed,
+                              int64_t first_list, const int32_t **d_vals, const int64_t **d_list_off, int64_t *total_vals);
+
+/* raw device memory helpers for callers without a CUDA runtime of their own */
+int mcp_dev_alloc(mcp_ctx *ctx, size_t bytes, void **dptr);
+int mcp_dev_free(mcp_ctx *ctx, void *dptr);
+int mcp_memcpy_h2d(mcp_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+int mcp_memcpy_d2h(mcp_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+int mcp_host_alloc_pinned(size_t bytes, void **hptr);
+int mcp_host_free_pinned(void *hptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCP_H */

@@ -1,0 +1,180 @@
+// common.cuh -- context, error plumbing and device-buffer helpers shared by the
+// translation units of libmcp.so.  Plain CUDA runtime; no torch types anywhere.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mcp.h"
+
+namespace mcp {
+
+constexpr int kWarp = 32;
+
+// A grow-only device buffer (cudaMalloc is slow; steps reuse their scratch).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Profile {
+    bool on = false;
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;          // recorded, not yet resolved
+    std::vector<cudaEvent_t> pool;  // free events
+    int64_t launches[MCP_K_COUNT] = {0};
+    double ms[MCP_K_COUNT] = {0};
+};
+
+} // namespace mcp
+
+struct mcp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string last_error;
+
+    // ---- risk path state
+    mcp::DevBuf dE, dS;            // exposures P x F, scenarios N x F (doubles)
+    int64_t P = 0, N = 0;
+    int32_t F = 0;
+    bool haveE = false, haveS = false;
+
+    // results of the last run (device)
+    mcp::DevBuf dMean, dVar, dVarLoss, dVarTrial, dCvar, dBreach, dEncOff, dEnc;
+    int64_t runP = 0, runN = 0, runTail = 0, runEncBytes = 0;
+    bool haveRun = false;
+
+    // scratch
+    mcp::DevBuf dLoss;             // dense loss tile
+    mcp::DevBuf dPart;             // moment partials
+    mcp::DevBuf dShift;            // per-portfolio shift c_p
+    mcp::DevBuf dSizes, dScanTmp;  // codec size/scan scratch
+    mcp::DevBuf dIo0, dIo1, dIo2, dIo3; // host-API staging (vals, offsets, out, out offsets)
+    mcp::DevBuf dErr;              // int error flag
+    mcp::DevBuf dFlush;            // L2 flush buffer
+    mcp::DevBuf dGenVals, dGenOff; // synthetic breach lists
+    mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
+    void *hPinned = nullptr;       // small pinned staging (scalars)
+
+    mcp::Profile prof;
+    cudaEvent_t tA = nullptr, tB = nullptr;
+};
+
+namespace mcp {
+
+inline int fail(mcp_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        ctx->last_error = buf;
+    }
+    return code;
+}
+
+#define MCP_CUDA(ctx, expr)                                                          \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            cudaGetLastError();                                                      \
+            return ::mcp::fail((ctx), _e == cudaErrorMemoryAllocation ? MCP_E_NOMEM : MCP_E_CUDA, #expr, _e); \
+        }                                                                            \
+    } while (0)
+
+#define MCP_TRY(expr)                 \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != MCP_OK) return _rc; \
+    } while (0)
+
+// RAII-ish scope that brackets kernel launches of one class with CUDA events on the
+// ctx stream when profiling is enabled.
+struct KScope {
+    mcp_ctx *ctx;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KScope(mcp_ctx *c, int k, int nlaunch = 1) : ctx(c), cls(k)
+    {
+        ctx->prof.launches[cls] += nlaunch;
+        if (!ctx->prof.on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->prof.pool.empty()) { e = ctx->prof.pool.back(); ctx->prof.pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~KScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof.recs.push_back({cls, a, b});
+    }
+};
+
+inline int check_launch(mcp_ctx *ctx, const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, MCP_E_CUDA, what, e);
+    return MCP_OK;
+}
+
+// ---- launch-side entry points implemented in the .cu files ----
+
+// codec_kernels.cu
+int codec_encode_plan(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
+                      int64_t uniform_len, int64_t nlists, int64_t *d_out_off, int64_t *total_out);
+int codec_encode_emit(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
+                      int64_t uniform_len, int64_t nlists, const int64_t *d_out_off, uint8_t *d_out);
+int codec_decode_counts(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off,
+                        int64_t nlists, int64_t *d_counts);
+int codec_decode_device(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off,
+                        int64_t nlists, int32_t *d_out, const int64_t *d_out_off);
+int exclusive_scan_i64(mcp_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out /* n+1 */);
+int64_t codec_max_words(int codec, int64_t n);
+
+// risk_kernels.cu
+int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing);
+int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V);
+int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t seed, uint32_t tensor_id, double scale,
+               double shift, int64_t row0);
+int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
+                     int64_t *total);
+int fp64_peak(mcp_ctx *ctx, double *tflops);
+
+} // namespace mcp

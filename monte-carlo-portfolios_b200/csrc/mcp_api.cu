@@ -1,0 +1,575 @@
+// mcp_api.cu -- the extern "C" surface declared in include/mcp.h.
+// Host-side argument checking, host<->device staging, and nothing else: all compute is
+// in codec_kernels.cu / risk_kernels.cu.  There is no CPU implementation of any stage.
+#include <math.h>
+
+#include <new>
+
+#include "common.cuh"
+
+using namespace mcp;
+
+namespace {
+
+int set_dev(mcp_ctx *ctx)
+{
+    if (!ctx) return MCP_E_ARG;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, MCP_E_CUDA, "cudaSetDevice", e);
+    return MCP_OK;
+}
+
+int h2d(mcp_ctx *ctx, void *d, const void *h, size_t bytes)
+{
+    if (bytes == 0) return MCP_OK;
+    MCP_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MCP_OK;
+}
+
+int d2h(mcp_ctx *ctx, void *h, const void *d, size_t bytes)
+{
+    if (bytes == 0) return MCP_OK;
+    MCP_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MCP_OK;
+}
+
+int sync(mcp_ctx *ctx)
+{
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MCP_OK;
+}
+
+bool codec_ok(int codec_id)
+{
+    const int c = codec_id & MCP_CODEC_MASK;
+    return c >= 0 && c < MCP_CODEC_COUNT && !(codec_id & ~(MCP_CODEC_MASK | MCP_FLAG_DELTA));
+}
+
+void resolve_profile(mcp_ctx *ctx)
+{
+    for (auto &r : ctx->prof.recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->prof.ms[r.cls] += ms;
+        ctx->prof.pool.push_back(r.a);
+        ctx->prof.pool.push_back(r.b);
+    }
+    ctx->prof.recs.clear();
+}
+
+} // namespace
+
+extern "C" {
+
+const char *mcp_strerror(int err)
+{
+    switch (err) {
+    case MCP_OK: return "ok";
+    case MCP_E_ARG: return "invalid argument";
+    case MCP_E_CAP: return "output buffer too small";
+    case MCP_E_CUDA: return "CUDA error";
+    case MCP_E_NOMEM: return "out of memory";
+    case MCP_E_FORMAT: return "malformed compressed stream";
+    case MCP_E_STATE: return "call sequence error";
+    case MCP_E_UNSUPPORTED: return "not supported by this build";
+    case MCP_E_NCCL: return "NCCL error";
+    }
+    return "unknown error";
+}
+
+const char *mcp_last_error(const mcp_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int mcp_create(int device, mcp_ctx **out)
+{
+    if (!out) return MCP_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return MCP_E_CUDA; // no GPU: there is deliberately no CPU fallback
+    }
+    if (device < 0 || device >= ndev) return MCP_E_ARG;
+    mcp_ctx *ctx = new (std::nothrow) mcp_ctx();
+    if (!ctx) return MCP_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->hPinned, 4096) != cudaSuccess || cudaEventCreate(&ctx->tA) != cudaSuccess ||
+        cudaEventCreate(&ctx->tB) != cudaSuccess) {
+        cudaGetLastError();
+        mcp_destroy(ctx);
+        return MCP_E_CUDA;
+    }
+    *out = ctx;
+    return MCP_OK;
+}
+
+void mcp_destroy(mcp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    resolve_profile(ctx);
+    for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+    mcp::DevBuf *bufs[] = {&ctx->dE, &ctx->dS, &ctx->dMean, &ctx->dVar, &ctx->dVarLoss, &ctx->dVarTrial, &ctx->dCvar,
+                           &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dShift, &ctx->dSizes,
+                           &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
+                           &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
+                           &ctx->dKeptKey, &ctx->dKeptIdx};
+    for (auto b : bufs) b->release();
+    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+    if (ctx->tA) cudaEventDestroy(ctx->tA);
+    if (ctx->tB) cudaEventDestroy(ctx->tB);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes)
+{
+    if (!ctx) return MCP_E_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (hbm_bytes) *hbm_bytes = ctx->prop.totalGlobalMem;
+    return MCP_OK;
+}
+
+int mcp_sync(mcp_ctx *ctx)
+{
+    MCP_TRY(set_dev(ctx));
+    return sync(ctx);
+}
+
+int64_t mcp_codec_max_bytes(int codec_id, int framing, int64_t n)
+{
+    if (!codec_ok(codec_id) || n < 0) return -1;
+    return 4 * (codec_max_words(codec_id & MCP_CODEC_MASK, n) + (framing == MCP_FRAME_APP ? 1 : 0));
+}
+
+int64_t mcp_tail_size(int64_t N, double alpha)
+{
+    if (N <= 0) return 0;
+    int64_t k = (int64_t)ceil(alpha * (double)N - 1e-7);
+    if (k < 1) k = 1;
+    if (k > N) k = N;
+    return N - k + 1;
+}
+
+// ------------------------------------------------------------ batched codec
+int mcp_codec_encode_dev(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
+                         int64_t nlists, int64_t total_vals, int64_t *d_out_off, uint8_t *d_out, int64_t cap,
+                         int64_t *total_out)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || total_vals < 0 || !d_out_off || (nlists > 0 && !d_list_off)) return fail(ctx, MCP_E_ARG, "encode_dev: bad argument");
+    int64_t total = 0;
+    MCP_TRY(codec_encode_plan(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, d_out_off, &total));
+    if (total_out) *total_out = total;
+    if (total > cap || (total > 0 && !d_out)) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+    return codec_encode_emit(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, d_out_off, d_out);
+}
+
+int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off,
+                         int64_t nlists, int32_t *d_out, const int64_t *d_out_off)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || (nlists > 0 && (!d_in_off || !d_out_off))) return fail(ctx, MCP_E_ARG, "decode_dev: bad argument");
+    return codec_decode_device(ctx, codec_id, framing, d_in, d_in_off, nlists, d_out, d_out_off);
+}
+
+int mcp_codec_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *vals, const int64_t *list_off, int64_t nlists,
+                     int64_t *out_off, uint8_t *out, int64_t cap, int64_t *out_len)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || !list_off || !out_off || cap < 0) return fail(ctx, MCP_E_ARG, "encode: bad argument");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    const int64_t total_vals = list_off[nlists] - list_off[0];
+    if (total_vals < 0 || (total_vals > 0 && !vals)) return fail(ctx, MCP_E_ARG, "encode: bad list offsets");
+    for (int64_t i = 0; i < nlists; ++i)
+        if (list_off[i + 1] < list_off[i]) return fail(ctx, MCP_E_ARG, "encode: list offsets not monotone");
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)(total_vals + 1) * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dIo1.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, vals + list_off[0], (size_t)total_vals * sizeof(int32_t)));
+    // offsets are rebased to the first list on the device side
+    if (list_off[0] == 0) {
+        MCP_TRY(h2d(ctx, ctx->dIo1.p, list_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    } else {
+        std::vector<int64_t> rb((size_t)nlists + 1);
+        for (int64_t i = 0; i <= nlists; ++i) rb[i] = list_off[i] - list_off[0];
+        MCP_TRY(h2d(ctx, ctx->dIo1.p, rb.data(), rb.size() * sizeof(int64_t)));
+        MCP_TRY(sync(ctx));
+    }
+    int64_t total = 0;
+    MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists,
+                              ctx->dIo3.as<int64_t>(), &total));
+    if (out_len) *out_len = total;
+    MCP_TRY(d2h(ctx, out_off, ctx->dIo3.p, (size_t)(nlists + 1) * sizeof(int64_t)));
+    if (total > cap || (total > 0 && !out)) {
+        sync(ctx);
+        return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+    }
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)total + 16));
+    MCP_TRY(codec_encode_emit(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists,
+                              ctx->dIo3.as<int64_t>(), ctx->dIo2.as<uint8_t>()));
+    MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)total));
+    return sync(ctx);
+}
+
+int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *in, const int64_t *in_off, int64_t nlists,
+                     int32_t *out, const int64_t *out_off)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || !in_off || !out_off) return fail(ctx, MCP_E_ARG, "decode: bad argument");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (nlists == 0) return MCP_OK;
+    if (in_off[0] != 0 || out_off[0] != 0) return fail(ctx, MCP_E_ARG, "decode: offsets must start at 0");
+    const int64_t in_bytes = in_off[nlists], out_n = out_off[nlists];
+    if (in_bytes < 0 || out_n < 0 || (in_bytes > 0 && !in) || (out_n > 0 && !out)) return fail(ctx, MCP_E_ARG, "decode: bad sizes");
+    for (int64_t i = 0; i < nlists; ++i) {
+        if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) return fail(ctx, MCP_E_ARG, "decode: offsets not monotone");
+        if ((in_off[i] & 3) != 0) return fail(ctx, MCP_E_FORMAT, "decode: byte offsets must be multiples of 4");
+    }
+    if (in_bytes & 3) return fail(ctx, MCP_E_FORMAT, "decode: byte length not a multiple of 4");
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)in_bytes + 16));
+    MCP_CUDA(ctx, ctx->dIo1.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)(out_n + 1) * sizeof(int32_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, in, (size_t)in_bytes));
+    MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists,
+                                ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
+    MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)out_n * sizeof(int32_t)));
+    return sync(ctx);
+}
+
+// ------------------------------------------------------- single-list drop-ins
+int mcp_codec_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength, int32_t *out, int32_t out_cap,
+                       int32_t *out_words)
+{
+    if (!ctx || inlength < 0 || out_cap < 0 || !out_words) return ctx ? fail(ctx, MCP_E_ARG, "compress: bad argument") : MCP_E_ARG;
+    const int64_t lo[2] = {0, inlength};
+    int64_t oo[2] = {0, 0}, len = 0;
+    const int rc = mcp_codec_encode(ctx, codec_id, MCP_FRAME_WORDS, in, lo, 1, oo, reinterpret_cast<uint8_t *>(out),
+                                    (int64_t)out_cap * 4, &len);
+    *out_words = (int32_t)(len / 4);
+    return rc;
+}
+
+static int decode_single(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *bytes, int64_t nbytes, int32_t *out,
+                         int64_t out_cap, int64_t *out_count)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nbytes < 0 || out_cap < 0 || (nbytes > 0 && !bytes)) return fail(ctx, MCP_E_ARG, "uncompress: bad argument");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (nbytes & 3) return fail(ctx, MCP_E_FORMAT, "uncompress: byte length not a multiple of 4");
+    *out_count = 0;
+    const int64_t in_off[2] = {0, nbytes};
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)nbytes + 16));
+    MCP_CUDA(ctx, ctx->dIo1.reserve(2 * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve(2 * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, bytes, (size_t)nbytes));
+    MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, sizeof in_off));
+    // length of the list, from the stream's own headers
+    MCP_TRY(codec_decode_counts(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), 1,
+                                ctx->dIo3.as<int64_t>() + 1));
+    int64_t n = 0;
+    MCP_TRY(d2h(ctx, &n, ctx->dIo3.as<int64_t>() + 1, sizeof n));
+    MCP_TRY(sync(ctx));
+    if (n > out_cap) return fail(ctx, MCP_E_CAP, "uncompress: output array too small");
+    const int64_t out_off[2] = {0, n};
+    MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, sizeof out_off));
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)(n + 1) * sizeof(int32_t)));
+    MCP_TRY(codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), 1,
+                                ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
+    MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)n * sizeof(int32_t)));
+    MCP_TRY(sync(ctx));
+    *out_count = n;
+    return MCP_OK;
+}
+
+int mcp_codec_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength, int32_t *out, int32_t out_cap,
+                         int32_t *out_count)
+{
+    if (!ctx || inlength < 0 || !out_count) return ctx ? fail(ctx, MCP_E_ARG, "uncompress: bad argument") : MCP_E_ARG;
+    int64_t n = 0;
+    const int rc = decode_single(ctx, codec_id, MCP_FRAME_WORDS, reinterpret_cast<const uint8_t *>(in), (int64_t)inlength * 4,
+                                 out, out_cap, &n);
+    *out_count = (int32_t)n;
+    return rc;
+}
+
+int mcp_get_compressed_instruments(mcp_ctx *ctx, int codec_id, const int32_t *instruments, int32_t n, uint8_t *bytes,
+                                   int64_t cap, int64_t *nbytes)
+{
+    if (!ctx || n < 0 || !nbytes) return ctx ? fail(ctx, MCP_E_ARG, "getCompressedInstruments: bad argument") : MCP_E_ARG;
+    const int64_t lo[2] = {0, n};
+    int64_t oo[2] = {0, 0};
+    return mcp_codec_encode(ctx, codec_id, MCP_FRAME_APP, instruments, lo, 1, oo, bytes, cap, nbytes);
+}
+
+int mcp_get_decompressed_instruments(mcp_ctx *ctx, int codec_id, const uint8_t *bytes, int64_t nbytes,
+                                     int32_t number_of_integers, int32_t *out)
+{
+    if (!ctx || number_of_integers < 0) return ctx ? fail(ctx, MCP_E_ARG, "getDecompressedInstruments: bad argument") : MCP_E_ARG;
+    int64_t n = 0;
+    MCP_TRY(decode_single(ctx, codec_id, MCP_FRAME_APP, bytes, nbytes, out, number_of_integers, &n));
+    for (int64_t i = n; i < number_of_integers; ++i) out[i] = 0; // Java: new int[numberOfIntegers] is zero-filled
+    return MCP_OK;
+}
+
+// ------------------------------------------------------------------ risk path
+static int upload_matrix(mcp_ctx *ctx, mcp::DevBuf &buf, const double *h, int64_t rows, int32_t F)
+{
+    if (rows < 0 || F <= 0 || (rows > 0 && !h)) return fail(ctx, MCP_E_ARG, "upload: bad argument");
+    MCP_CUDA(ctx, buf.reserve((size_t)rows * F * sizeof(double) + 16));
+    MCP_TRY(h2d(ctx, buf.p, h, (size_t)rows * F * sizeof(double)));
+    return sync(ctx);
+}
+
+int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F)
+{
+    MCP_TRY(set_dev(ctx));
+    if (ctx->haveS && ctx->F != F) return fail(ctx, MCP_E_ARG, "upload_exposures: F differs from the scenario matrix");
+    MCP_TRY(upload_matrix(ctx, ctx->dE, E, P, F));
+    ctx->P = P; ctx->F = F; ctx->haveE = true; ctx->haveRun = false;
+    return MCP_OK;
+}
+
+int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F)
+{
+    MCP_TRY(set_dev(ctx));
+    if (ctx->haveE && ctx->F != F) return fail(ctx, MCP_E_ARG, "upload_scenarios: F differs from the exposure matrix");
+    MCP_TRY(upload_matrix(ctx, ctx->dS, S, N, F));
+    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;
+    return MCP_OK;
+}
+
+int mcp_generate_exposures(mcp_ctx *ctx, int64_t P, int32_t F, uint64_t seed, double scale, double shift, int64_t row0)
+{
+    MCP_TRY(set_dev(ctx));
+    if (P < 0 || F <= 0) return fail(ctx, MCP_E_ARG, "generate_exposures: bad size");
+    if (ctx->haveS && ctx->F != F) return fail(ctx, MCP_E_ARG, "generate_exposures: F differs from the scenario matrix");
+    MCP_CUDA(ctx, ctx->dE.reserve((size_t)P * F * sizeof(double) + 16));
+    MCP_TRY(gen_matrix(ctx, ctx->dE.as<double>(), P, F, seed, 1u, scale, shift, row0));
+    ctx->P = P; ctx->F = F; ctx->haveE = true; ctx->haveRun = false;
+    return MCP_OK;
+}
+
+int mcp_generate_scenarios(mcp_ctx *ctx, int64_t N, int32_t F, uint64_t seed, double scale, double shift, int64_t row0)
+{
+    MCP_TRY(set_dev(ctx));
+    if (N < 0 || F <= 0) return fail(ctx, MCP_E_ARG, "generate_scenarios: bad size");
+    if (ctx->haveE && ctx->F != F) return fail(ctx, MCP_E_ARG, "generate_scenarios: F differs from the exposure matrix");
+    MCP_CUDA(ctx, ctx->dS.reserve((size_t)N * F * sizeof(double) + 16));
+    MCP_TRY(gen_matrix(ctx, ctx->dS.as<double>(), N, F, seed, 2u, scale, shift, row0));
+    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;
+    return MCP_OK;
+}
+
+int mcp_download_exposures(mcp_ctx *ctx, double *E)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!ctx->haveE || !E) return fail(ctx, MCP_E_STATE, "download_exposures: nothing uploaded");
+    MCP_TRY(d2h(ctx, E, ctx->dE.p, (size_t)ctx->P * ctx->F * sizeof(double)));
+    return sync(ctx);
+}
+
+int mcp_download_scenarios(mcp_ctx *ctx, double *S)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!ctx->haveS || !S) return fail(ctx, MCP_E_STATE, "download_scenarios: nothing uploaded");
+    MCP_TRY(d2h(ctx, S, ctx->dS.p, (size_t)ctx->N * ctx->F * sizeof(double)));
+    return sync(ctx);
+}
+
+int mcp_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *V)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!ctx->haveE || !ctx->haveS) return fail(ctx, MCP_E_STATE, "value: upload exposures and scenarios first");
+    if (p0 < 0 || p1 > ctx->P || p1 < p0 || !V) return fail(ctx, MCP_E_ARG, "value: bad range");
+    const size_t bytes = (size_t)(p1 - p0) * ctx->N * sizeof(double);
+    MCP_CUDA(ctx, ctx->dLoss.reserve(bytes + 16));
+    MCP_TRY(risk_value(ctx, p0, p1, ctx->dLoss.as<double>()));
+    MCP_TRY(d2h(ctx, V, ctx->dLoss.p, bytes));
+    return sync(ctx);
+}
+
+int mcp_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!ctx->haveE || !ctx->haveS) return fail(ctx, MCP_E_STATE, "run: upload exposures and scenarios first");
+    if (!(alpha > 0.0 && alpha <= 1.0)) return fail(ctx, MCP_E_ARG, "run: alpha must be in (0,1]");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
+    return risk_run(ctx, alpha, codec_id, framing);
+}
+
+int mcp_run_sizes(mcp_ctx *ctx, int64_t *P, int64_t *N, int64_t *tail, int64_t *enc_bytes)
+{
+    if (!ctx) return MCP_E_ARG;
+    if (!ctx->haveRun) return fail(ctx, MCP_E_STATE, "run_sizes: no completed run");
+    if (P) *P = ctx->runP;
+    if (N) *N = ctx->runN;
+    if (tail) *tail = ctx->runTail;
+    if (enc_bytes) *enc_bytes = ctx->runEncBytes;
+    return MCP_OK;
+}
+
+int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
+              int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!ctx->haveRun) return fail(ctx, MCP_E_STATE, "fetch: no completed run");
+    const size_t P = (size_t)ctx->runP;
+    if (enc && enc_cap < ctx->runEncBytes) return fail(ctx, MCP_E_CAP, "fetch: encoded buffer too small");
+    if (mean) MCP_TRY(d2h(ctx, mean, ctx->dMean.p, P * sizeof(double)));
+    if (variance) MCP_TRY(d2h(ctx, variance, ctx->dVar.p, P * sizeof(double)));
+    if (var_loss) MCP_TRY(d2h(ctx, var_loss, ctx->dVarLoss.p, P * sizeof(double)));
+    if (var_trial) MCP_TRY(d2h(ctx, var_trial, ctx->dVarTrial.p, P * sizeof(int32_t)));
+    if (cvar) MCP_TRY(d2h(ctx, cvar, ctx->dCvar.p, P * sizeof(double)));
+    if (breach_idx) MCP_TRY(d2h(ctx, breach_idx, ctx->dBreach.p, P * (size_t)ctx->runTail * sizeof(int32_t)));
+    if (enc_off) MCP_TRY(d2h(ctx, enc_off, ctx->dEncOff.p, (P + 1) * sizeof(int64_t)));
+    if (enc) MCP_TRY(d2h(ctx, enc, ctx->dEnc.p, (size_t)ctx->runEncBytes));
+    return sync(ctx);
+}
+
+int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int64_t N, int32_t F, double alpha,
+                 int codec_id, int framing, double *mean, double *variance, double *var_loss, int32_t *var_trial,
+                 double *cvar, int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len)
+{
+    MCP_TRY(set_dev(ctx));
+    ctx->haveE = ctx->haveS = false;
+    MCP_TRY(mcp_upload_exposures(ctx, E, P, F));
+    MCP_TRY(mcp_upload_scenarios(ctx, S, N, F));
+    MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+    if (enc_len) *enc_len = ctx->runEncBytes;
+    return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
+}
+
+// ---------------------------------------------------------------- measurement
+int mcp_profile_enable(mcp_ctx *ctx, int on)
+{
+    if (!ctx) return MCP_E_ARG;
+    ctx->prof.on = on != 0;
+    return MCP_OK;
+}
+
+int mcp_profile_reset(mcp_ctx *ctx)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(sync(ctx));
+    resolve_profile(ctx);
+    for (int i = 0; i < MCP_K_COUNT; ++i) { ctx->prof.launches[i] = 0; ctx->prof.ms[i] = 0; }
+    return MCP_OK;
+}
+
+int mcp_profile_get(mcp_ctx *ctx, int64_t launches[MCP_K_COUNT], double ms[MCP_K_COUNT])
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(sync(ctx));
+    resolve_profile(ctx);
+    for (int i = 0; i < MCP_K_COUNT; ++i) {
+        if (launches) launches[i] = ctx->prof.launches[i];
+        if (ms) ms[i] = ctx->prof.ms[i];
+    }
+    return MCP_OK;
+}
+
+int mcp_timer_start(mcp_ctx *ctx)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_CUDA(ctx, cudaEventRecord(ctx->tA, ctx->stream));
+    return MCP_OK;
+}
+
+int mcp_timer_stop(mcp_ctx *ctx, double *ms)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_CUDA(ctx, cudaEventRecord(ctx->tB, ctx->stream));
+    MCP_CUDA(ctx, cudaEventSynchronize(ctx->tB));
+    float f = 0;
+    MCP_CUDA(ctx, cudaEventElapsedTime(&f, ctx->tA, ctx->tB));
+    if (ms) *ms = f;
+    return MCP_OK;
+}
+
+int mcp_fp64_peak(mcp_ctx *ctx, double *tflops)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!tflops) return fail(ctx, MCP_E_ARG, "fp64_peak: null");
+    return fp64_peak(ctx, tflops);
+}
+
+int mcp_flush_l2(mcp_ctx *ctx)
+{
+    MCP_TRY(set_dev(ctx));
+    const size_t bytes = (size_t)256 << 20; // 2x the 126 MB L2
+    MCP_CUDA(ctx, ctx->dFlush.reserve(bytes));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dFlush.p, 0, bytes, ctx->stream));
+    return MCP_OK;
+}
+
+int mcp_generate_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed,
+                              int64_t first_list, const int32_t **d_vals, const int64_t **d_list_off, int64_t *total_vals)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || n_trials < 0 || !(rate >= 0.0 && rate < 1.0) || !d_vals || !d_list_off || !total_vals)
+        return fail(ctx, MCP_E_ARG, "generate_breach_lists: bad argument");
+    int64_t total = 0;
+    MCP_TRY(gen_breach_lists(ctx, nlists, n_trials, rate, seed, first_list, &total));
+    *d_vals = ctx->dGenVals.as<int32_t>();
+    *d_list_off = ctx->dGenOff.as<int64_t>();
+    *total_vals = total;
+    return MCP_OK;
+}
+
+int mcp_dev_alloc(mcp_ctx *ctx, size_t bytes, void **dptr)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!dptr) return fail(ctx, MCP_E_ARG, "dev_alloc: null");
+    MCP_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 16));
+    return MCP_OK;
+}
+
+int mcp_dev_free(mcp_ctx *ctx, void *dptr)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_CUDA(ctx, cudaFree(dptr));
+    return MCP_OK;
+}
+
+int mcp_memcpy_h2d(mcp_ctx *ctx, void *dptr, const void *hptr, size_t bytes)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(h2d(ctx, dptr, hptr, bytes));
+    return sync(ctx);
+}
+
+int mcp_memcpy_d2h(mcp_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(d2h(ctx, hptr, dptr, bytes));
+    return sync(ctx);
+}
+
+int mcp_host_alloc_pinned(size_t bytes, void **hptr)
+{
+    if (!hptr) return MCP_E_ARG;
+    if (cudaMallocHost(hptr, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return MCP_E_NOMEM;
+    }
+    return MCP_OK;
+}
+
+int mcp_host_free_pinned(void *hptr)
+{
+    if (cudaFreeHost(hptr) != cudaSuccess) {
+        cudaGetLastError();
+        return MCP_E_CUDA;
+    }
+    return MCP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,67 @@
+"""Mirror of the reference loader's codec call sites
+(maprdb-portfolio/src/main/java/com/mapr/db/data/LoadPortfolios.java:251-260, 597-623, 625-662),
+batched: the reference compresses one portfolio per loop iteration, here all portfolios
+of a file go to the GPU in one call.
+"""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+from . import _native as N
+from .engine import Context
+
+INTEGER_CODEC_NAME = "bpacking+variablebyte"  # LoadPortfolios.java:726
+
+
+class LoadPortfolios:
+    """The subset of LoadPortfolios that touches the codec (the drop-in boundary)."""
+
+    def __init__(self, ctx: Context | None = None, codec_id: int = N.CODEC_BP32_VB):
+        from .codec import default_context
+        self.ctx = ctx or default_context()
+        self.codec_id = codec_id  # LoadPortfolios.java:725: new Composition(new BinaryPacking(), new VariableByte())
+
+    # -- single list, same signatures as the Java methods
+    def getCompressedInstruments(self, instruments) -> bytes:  # :608-623
+        return self.ctx.get_compressed_instruments(self.codec_id, instruments)
+
+    def getDecompressedInstruments(self, compressedInstruments: bytes, numberOfIntegers: int) -> np.ndarray:  # :625-662
+        return self.ctx.get_decompressed_instruments(self.codec_id, compressedInstruments, numberOfIntegers)
+
+    # -- batched
+    def compress_all(self, lists) -> list[bytes]:
+        lens = np.array([len(x) for x in lists], np.int64)
+        off = np.zeros(len(lists) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        vals = np.concatenate([np.asarray(x, np.int64) for x in lists]) if len(lists) and off[-1] else np.zeros(0, np.int64)
+        out_off, out = self.ctx.codec_encode(self.codec_id, N.FRAME_APP, vals, off)
+        return [bytes(out[out_off[i]: out_off[i + 1]]) for i in range(len(lists))]
+
+    @staticmethod
+    def integersToBytes(instruments) -> bytes:  # BitManipulationHelper.java:17-27 (the "none" fallback; pure byte order)
+        return np.asarray(instruments, np.int64).astype(np.uint32).astype(">u4").tobytes()
+
+    def getInstrumentDocument(self, instruments, compressed: bytes | None = None) -> dict:
+        """LoadPortfolios.java:254-260 + 597-606: store compressed iff smaller than 4n bytes, else raw big-endian."""
+        n = len(instruments)
+        blob = self.getCompressedInstruments(instruments) if compressed is None else compressed
+        algo = INTEGER_CODEC_NAME
+        if not (len(blob) < 4 * n):
+            blob, algo = self.integersToBytes(instruments), "none"
+        return {"uncompressedIntegerSize": n, "compressed": blob, "compressedByteSize": len(blob), "algo": algo}
+
+    def documents_from_json(self, path: str) -> list[dict]:
+        """One document per JSON line of a portfolios.json-style file (schema: SURVEY.md A.8), instruments only."""
+        rows = [json.loads(line) for line in open(path) if line.strip()]
+        lists = [[int(p["instrument"]) for p in r["instruments"]] for r in rows]
+        blobs = self.compress_all(lists)
+        docs = []
+        for r, ins, blob in zip(rows, lists, blobs):
+            w = [float(p["weight"]) for p in r["instruments"]]
+            docs.append({"_id": str(r.get("id", len(docs))),
+                         "metadata": {"min_instrument": min(ins), "max_instrument": max(ins),
+                                      "min_weight": min(w), "max_weight": max(w)},
+                         "instruments": self.getInstrumentDocument(ins, blob)})
+        return docs

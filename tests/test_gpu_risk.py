@@ -1,0 +1,149 @@
+"""GPU parity for kernels (1)-(3) + the fused encode: CUDA path through the C ABI against the oracle.
+Bars (BASELINE.json north_star): breach lists and encoded byte streams bit-exact, VaR trial index bit-exact,
+portfolio values bit-identical (single fma chain on both sides), moments / CVaR within 1e-9 relative."""
+import numpy as np
+import pytest
+
+import cases
+import riskcases
+from mcp_b200 import native as N
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9  # north_star tolerance for FP64 moments
+
+
+def check_against_oracle(ctx, E, S, alpha, cid=N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, framing=N.FRAME_APP, rows=None):
+    ctx.upload_exposures(E)
+    ctx.upload_scenarios(S)
+    ctx.run(alpha, cid, framing)
+    r = ctx.fetch()
+    P = E.shape[0]
+    rows = range(P) if rows is None else rows
+    o = cref.risk(E, S, alpha)
+    assert r["tail"] == o["tail"]
+    for p in rows:
+        assert r["var_trial"][p] == o["var_trial"][p], p
+        assert r["var_loss"][p] == o["var_loss"][p], p
+        assert np.array_equal(r["breach"][p], o["breach"][p]), p
+        blob = bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]])
+        ref = cref.get_compressed_instruments(cid, o["breach"][p]) if framing == N.FRAME_APP else cref.compress(cid, o["breach"][p]).tobytes()
+        assert blob == ref, p
+    rr = list(rows)
+    np.testing.assert_allclose(r["mean"][rr], o["mean"][rr], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(r["variance"][rr], o["variance"][rr], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(r["cvar"][rr], o["cvar"][rr], rtol=RTOL, atol=0)
+    return r
+
+
+@pytest.mark.parametrize("shape", [(10, 10, 10), (70, 1000, 32), (65, 999, 64), (33, 257, 5), (3, 4097, 33), (129, 130, 96)])
+def test_value_bit_identical(ctx, shape):
+    P, Nn, F = shape
+    E, S = riskcases.synthetic(P, Nn, F, 7)
+    ctx.upload_exposures(E)
+    ctx.upload_scenarios(S)
+    V = ctx.value(0, P, Nn)
+    assert np.array_equal(V.view(np.uint64), cref.value(E, S).view(np.uint64))
+    V2 = ctx.value(P // 2, P, Nn)
+    assert np.array_equal(V2, V[P // 2:])
+
+
+@pytest.mark.parametrize("shape", [(10, 10, 10, 0.9), (40, 1000, 32, 0.99), (30, 999, 64, 0.95), (9, 257, 5, 0.5),
+                                   (5, 64, 3, 1.0), (12, 20000, 32, 0.99), (3, 100000, 32, 0.99), (2, 50000, 7, 0.6)])
+def test_run_matches_oracle(ctx, shape):
+    P, Nn, F, alpha = shape
+    E, S = riskcases.synthetic(P, Nn, F, 1234 + P)
+    check_against_oracle(ctx, E, S, alpha)
+
+
+def test_ties_break_by_trial_index(ctx):
+    E, S = riskcases.with_ties(20, 3000, 4, 9)
+    check_against_oracle(ctx, E, S, 0.9)
+    E, S = riskcases.with_ties(4, 40000, 3, 10)   # thousands of identical losses: deep radix passes
+    check_against_oracle(ctx, E, S, 0.75)
+
+
+def test_degenerate_rows(ctx):
+    E, S = riskcases.synthetic(6, 500, 8, 5)
+    E[0] = 0.0            # all losses +0.0: the tail is the last t trials
+    E[1] = -E[2]          # mirrored
+    S[100] = S[200]       # identical scenarios -> identical losses
+    check_against_oracle(ctx, E, S, 0.97)
+
+
+def test_adversarial_trial_order(ctx):
+    """Losses that increase with the trial index (the worst case for any streaming threshold filter)."""
+    F = 4
+    Nn = 30000
+    S = np.zeros((Nn, F))
+    S[:, 0] = -np.linspace(0.0, 1.0, Nn)
+    S[:, 1] = 1e-3 * np.cos(np.arange(Nn))
+    E = np.abs(riskcases.synthetic(8, 1, F, 3)[0]) + 1.0
+    check_against_oracle(ctx, E, S, 0.99)
+    check_against_oracle(ctx, E, S[::-1].copy(), 0.99)
+
+
+def test_c1_shipped_sample(ctx):
+    """BASELINE config C1: portfolios.json x macro.json (fixture tests/golden/c1_sample.json)."""
+    d, E, S = riskcases.c1_inputs()
+    for cid in (N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_BP32_VB):
+        check_against_oracle(ctx, E, S, 0.9, cid)
+
+
+@pytest.mark.parametrize("cid", [N.CODEC_BP32_VB, N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA,
+                                 N.CODEC_IBP32_IVB, N.CODEC_SK_IBP32_IVB])
+def test_every_breach_codec(ctx, cid):
+    E, S = riskcases.synthetic(16, 30000, 32, 77)
+    check_against_oracle(ctx, E, S, 0.99, cid, N.FRAME_APP)
+    check_against_oracle(ctx, E, S, 0.99, cid, N.FRAME_WORDS, rows=[0, 15])
+
+
+def test_simulate_one_call(ctx):
+    E, S = riskcases.synthetic(25, 5000, 32, 8)
+    r = ctx.simulate(E, S, 0.99)
+    o = cref.risk(E, S, 0.99)
+    assert np.array_equal(r["breach"], o["breach"]) and np.array_equal(r["var_trial"], o["var_trial"])
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    for p in (0, 24):
+        assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
+
+
+def test_device_generators_match_the_oracle(ctx):
+    ctx.generate_exposures(100, 32, 0x5EED0002, 100.0, 0.0)
+    ctx.generate_scenarios(1000, 32, 0x5EED0002, 1.0, 0.05)
+    assert np.array_equal(ctx.download_exposures(100, 32), cref.gen_normal(100, 32, 0x5EED0002, 1, 100.0, 0.0))
+    assert np.array_equal(ctx.download_scenarios(1000, 32), cref.gen_normal(1000, 32, 0x5EED0002, 2, 1.0, 0.05))
+    ctx.generate_scenarios(10, 32, 0x5EED0002, 1.0, 0.05, row0=500)
+    assert np.array_equal(ctx.download_scenarios(10, 32), cref.gen_normal(10, 32, 0x5EED0002, 2, 1.0, 0.05, row0=500))
+
+
+def test_full_size_c2_properties(ctx):
+    """BASELINE config C2 at full size (10 000 x 100 000 x 32) on device-generated inputs: spot rows against the
+    oracle plus size-independent properties on every row."""
+    P, Nn, F, alpha = 10000, 100000, 32, 0.99
+    ctx.generate_exposures(P, F, 0x5EED0002, 100.0, 0.0)
+    ctx.generate_scenarios(Nn, F, 0x5EED0002, 1.0, 0.05)
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    ctx.run(alpha, cid, N.FRAME_APP)
+    r = ctx.fetch()
+    t = r["tail"]
+    assert t == 1001
+    b = r["breach"]
+    assert np.all(np.diff(b, axis=1) > 0) and b.min() >= 0 and b.max() < Nn          # sorted, distinct, in range
+    assert np.all((b == r["var_trial"][:, None]).sum(axis=1) == 1)                     # the VaR trial is in its list
+    assert np.all(r["cvar"] >= r["var_loss"]) and np.all(r["variance"] > 0)
+    # decode the encoded lists back on the GPU: encode -> decode round trip over all 10 000 lists
+    off = np.arange(P + 1, dtype=np.int64) * t
+    back = ctx.codec_decode(cid, N.FRAME_APP, r["enc"], r["enc_off"], off)
+    assert np.array_equal(back.reshape(P, t), b)
+    # oracle on a handful of rows (host-generated inputs are bit-identical to the device generator)
+    rows = [0, 1, 4999, 9999]
+    E = cref.gen_normal(P, F, 0x5EED0002, 1, 100.0, 0.0)
+    S = cref.gen_normal(Nn, F, 0x5EED0002, 2, 1.0, 0.05)
+    for p in rows:
+        o = cref.risk(E, S, alpha, p, p + 1)
+        assert r["var_trial"][p] == o["var_trial"][0] and r["var_loss"][p] == o["var_loss"][0]
+        assert np.array_equal(b[p], o["breach"][0])
+        assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][0])
+        np.testing.assert_allclose([r["mean"][p], r["variance"][p], r["cvar"][p]],
+                                   [o["mean"][0], o["variance"][0], o["cvar"][0]], rtol=RTOL, atol=0)

