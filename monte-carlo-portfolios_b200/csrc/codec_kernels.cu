@@ -61,8 +61,10 @@ struct EncArgs {
     const int64_t *out_off;  // bytes (WRITE)
     uint8_t *out;
     int64_t *sizes;          // bytes (!WRITE)
-    int *err;
+    int *flags;              // [0] error, [1] number of multi-page FastPFOR lists (size pass), [2] shadow ticket (emit)
+    uint32_t *shadow;        // emit: per multi-page list, 33 x 65536 words emulating FastPFOR.dataTobePacked
 };
+constexpr int64_t kShadowWords = 33 * (int64_t)kFpPage;
 
 // x(i): the value sequence the codec sees (after the optional Delta.delta pre-pass)
 struct ValSeq {
@@ -212,7 +214,7 @@ __device__ __forceinline__ FpBlockPlan warp_fp_plan(const uint32_t (&v)[ROUNDS],
 // zero, so the padding of the last packed group of every exception stream is zero.
 template <bool WRITE, int ROUNDS>
 __device__ int64_t warp_fp_encode_page(const ValSeq &x, int64_t base, int n, uint32_t *outw, int *freq, int *cnt_k,
-                                       int lane)
+                                       uint32_t *shadow, int lane)
 {
     constexpr int B = ROUNDS * 32;
     const int nblocks = n / B;
@@ -285,6 +287,7 @@ __device__ int64_t warp_fp_encode_page(const ValSeq &x, int64_t base, int n, uin
                 if (hi != 0) {
                     const int rank = e0 + __popc(em & ((1u << lane) - 1u));
                     meta[mpos + 3 + rank] = (uint8_t)(32 * r + lane); // :166
+                    if (shadow) shadow[(int64_t)k * kFpPage + spos + rank] = hi; // dataTobePacked[k][dataPointers[k]++] (:169-170)
                     if (k >= 2) { // stream 1 is implicit (decoder ORs 1<<b, :291-295)
                         const int64_t bit = (int64_t)(spos + rank) * k;
                         const int w = (int)(bit >> 5), sh = (int)(bit & 31);
@@ -309,17 +312,35 @@ __device__ int64_t warp_fp_encode_page(const ValSeq &x, int64_t base, int n, uin
         }
         __syncwarp();
     }
+    if (shadow && mycnt) {
+        // FastPFOR never clears dataTobePacked (only the fill pointers, :143): the last packed group of stream k is
+        // padded with whatever earlier pages of this codec instance left at positions [cnt, roundup32(cnt)), and the
+        // words that survive the trim (:207-208) keep those bits.  Lane l replays that for stream k = l+1.
+        const int nwords = (int)(((int64_t)mycnt * myk + 31) >> 5);
+        uint32_t *sw = outw + s_stream_base[wib][myk] + 1;
+        const int cend = (mycnt + 31) & ~31;
+        for (int i = mycnt; i < cend; ++i) {
+            uint32_t v = shadow[(int64_t)myk * kFpPage + i];
+            if (myk < 32) v &= (1u << myk) - 1u;
+            const int64_t bit = (int64_t)i * myk;
+            const int w = (int)(bit >> 5), sh = (int)(bit & 31);
+            if (w < nwords) sw[w] |= v << sh;
+            if (sh + myk > 32 && w + 1 < nwords) sw[w + 1] |= v >> (32 - sh);
+        }
+    }
+    __syncwarp();
     return total;
 }
 
 template <bool WRITE, int ROUNDS>
-__device__ int64_t warp_fastpfor_encode(const ValSeq &x, int64_t m, uint32_t *outw, int *freq, int *cnt_k, int lane)
+__device__ int64_t warp_fastpfor_encode(const ValSeq &x, int64_t m, uint32_t *outw, int *freq, int *cnt_k,
+                                        uint32_t *shadow, int lane)
 {
     // FastPFOR.headlessCompress (:92-105): pages of at most 65536 ints
     int64_t pos = 0;
     for (int64_t s = 0; s < m; s += kFpPage) {
         const int sz = (int)((m - s < kFpPage) ? m - s : kFpPage);
-        pos += warp_fp_encode_page<WRITE, ROUNDS>(x, s, sz, WRITE ? outw + pos : nullptr, freq, cnt_k, lane);
+        pos += warp_fp_encode_page<WRITE, ROUNDS>(x, s, sz, WRITE ? outw + pos : nullptr, freq, cnt_k, shadow, lane);
     }
     return pos;
 }
@@ -437,10 +458,20 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
                 if (m > 0) {
                     // FastPFOR writes native words (byte-granular metadata); APP framing swaps afterwards
                     int64_t w;
+                    uint32_t *shadow = nullptr;
+                    if (m > kFpPage) { // multi-page list: needs the stale-buffer emulation
+                        if (WRITE) {
+                            int slot = 0;
+                            if (lane == 0) slot = atomicAdd(a.flags + 2, 1);
+                            slot = __shfl_sync(kFull, slot, 0);
+                            shadow = a.shadow + (int64_t)slot * kShadowWords;
+                        } else if (lane == 0)
+                            atomicAdd(a.flags + 1, 1);
+                    }
                     if (tr.fp_block == 256)
-                        w = warp_fastpfor_encode<WRITE, 8>(x, m, WRITE ? outw + pos : nullptr, s_freq[wib], s_cnt[wib], lane);
+                        w = warp_fastpfor_encode<WRITE, 8>(x, m, WRITE ? outw + pos : nullptr, s_freq[wib], s_cnt[wib], shadow, lane);
                     else
-                        w = warp_fastpfor_encode<WRITE, 4>(x, m, WRITE ? outw + pos : nullptr, s_freq[wib], s_cnt[wib], lane);
+                        w = warp_fastpfor_encode<WRITE, 4>(x, m, WRITE ? outw + pos : nullptr, s_freq[wib], s_cnt[wib], shadow, lane);
                     if (WRITE && a.app) {
                         __syncwarp();
                         for (int64_t j = pos + lane; j < pos + w; j += 32) outw[j] = bswap32(outw[j]);
@@ -766,7 +797,10 @@ int codec_encode_plan(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         return MCP_OK;
     }
     MCP_CUDA(ctx, ctx->dSizes.reserve((size_t)nlists * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dErr.reserve(64));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, 16, ctx->stream));
     a.sizes = ctx->dSizes.as<int64_t>();
+    a.flags = ctx->dErr.as<int>();
     {
         KScope ks(ctx, MCP_K_ENCODE);
         k_encode<false><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
@@ -774,8 +808,11 @@ int codec_encode_plan(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     }
     MCP_TRY(exclusive_scan_i64(ctx, a.sizes, nlists, d_out_off));
     MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, d_out_off + nlists, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hPinned) + 8, ctx->dErr.as<int>() + 1, sizeof(int),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);
+    ctx->planMultiPage = *reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8);
     return MCP_OK;
 }
 
@@ -787,6 +824,15 @@ int codec_encode_emit(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     if (nlists == 0) return MCP_OK;
     a.out_off = d_out_off;
     a.out = d_out;
+    MCP_CUDA(ctx, ctx->dErr.reserve(64));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, 16, ctx->stream));
+    a.flags = ctx->dErr.as<int>();
+    if (codec_traits(a.codec).fastpfor && ctx->planMultiPage > 0) {
+        const size_t bytes = (size_t)ctx->planMultiPage * kShadowWords * sizeof(uint32_t);
+        MCP_CUDA(ctx, ctx->dShadow.reserve(bytes));
+        MCP_CUDA(ctx, cudaMemsetAsync(ctx->dShadow.p, 0, bytes, ctx->stream));
+        a.shadow = ctx->dShadow.as<uint32_t>();
+    }
     KScope ks(ctx, MCP_K_ENCODE);
     k_encode<true><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
     return check_launch(ctx, "k_encode<emit>");

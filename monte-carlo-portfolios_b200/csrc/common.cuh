@@ -79,7 +79,9 @@ struct mcp_ctx {
     mcp::DevBuf dShift;            // per-portfolio shift c_p
     mcp::DevBuf dSizes, dScanTmp;  // codec size/scan scratch
     mcp::DevBuf dIo0, dIo1, dIo2, dIo3; // host-API staging (vals, offsets, out, out offsets)
-    mcp::DevBuf dErr;              // int error flag
+    mcp::DevBuf dErr;              // int flags (error, multi-page count, shadow ticket)
+    mcp::DevBuf dShadow;           // FastPFOR stale-buffer emulation for multi-page lists
+    int planMultiPage = 0;
     mcp::DevBuf dFlush;            // L2 flush buffer
     mcp::DevBuf dGenVals, dGenOff; // synthetic breach lists
     mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter

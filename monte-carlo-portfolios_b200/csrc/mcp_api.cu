@@ -114,7 +114,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dShift, &ctx->dSizes,
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
-                           &ctx->dKeptKey, &ctx->dKeptIdx};
+                           &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -330,7 +330,7 @@ static int upload_matrix(mcp_ctx *ctx, mcp::DevBuf &buf, const double *h, int64_
 int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F)
 {
     MCP_TRY(set_dev(ctx));
-    if (ctx->haveS && ctx->F != F) return fail(ctx, MCP_E_ARG, "upload_exposures: F differs from the scenario matrix");
+    if (ctx->haveS && ctx->F != F) ctx->haveS = false; // a new factor count invalidates the other matrix
     MCP_TRY(upload_matrix(ctx, ctx->dE, E, P, F));
     ctx->P = P; ctx->F = F; ctx->haveE = true; ctx->haveRun = false;
     return MCP_OK;
@@ -339,7 +339,7 @@ int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F)
 int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F)
 {
     MCP_TRY(set_dev(ctx));
-    if (ctx->haveE && ctx->F != F) return fail(ctx, MCP_E_ARG, "upload_scenarios: F differs from the exposure matrix");
+    if (ctx->haveE && ctx->F != F) ctx->haveE = false;
     MCP_TRY(upload_matrix(ctx, ctx->dS, S, N, F));
     ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;
     return MCP_OK;
@@ -349,7 +349,7 @@ int mcp_generate_exposures(mcp_ctx *ctx, int64_t P, int32_t F, uint64_t seed, do
 {
     MCP_TRY(set_dev(ctx));
     if (P < 0 || F <= 0) return fail(ctx, MCP_E_ARG, "generate_exposures: bad size");
-    if (ctx->haveS && ctx->F != F) return fail(ctx, MCP_E_ARG, "generate_exposures: F differs from the scenario matrix");
+    if (ctx->haveS && ctx->F != F) ctx->haveS = false;
     MCP_CUDA(ctx, ctx->dE.reserve((size_t)P * F * sizeof(double) + 16));
     MCP_TRY(gen_matrix(ctx, ctx->dE.as<double>(), P, F, seed, 1u, scale, shift, row0));
     ctx->P = P; ctx->F = F; ctx->haveE = true; ctx->haveRun = false;
@@ -360,7 +360,7 @@ int mcp_generate_scenarios(mcp_ctx *ctx, int64_t N, int32_t F, uint64_t seed, do
 {
     MCP_TRY(set_dev(ctx));
     if (N < 0 || F <= 0) return fail(ctx, MCP_E_ARG, "generate_scenarios: bad size");
-    if (ctx->haveE && ctx->F != F) return fail(ctx, MCP_E_ARG, "generate_scenarios: F differs from the exposure matrix");
+    if (ctx->haveE && ctx->F != F) ctx->haveE = false;
     MCP_CUDA(ctx, ctx->dS.reserve((size_t)N * F * sizeof(double) + 16));
     MCP_TRY(gen_matrix(ctx, ctx->dS.as<double>(), N, F, seed, 2u, scale, shift, row0));
     ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;

@@ -100,9 +100,8 @@ def test_breach_like_batch_all_codecs(ctx):
 
 
 def test_multipage_fastpfor(ctx):
-    """> 65 536 ints: FastPFOR pages (FastPFOR.java:98-102).  Decode of the oracle's stream is exact; the GPU
-    encoder's stream round-trips through the oracle's decoder (padding bits of multi-page exception streams may
-    differ from a Java instance that carried stale buffers across pages -- DESIGN.md 6, decoders ignore them)."""
+    """> 65 536 ints: FastPFOR pages (FastPFOR.java:98-102), including the stale exception-buffer padding that a
+    Java instance carries from page to page (FastPFOR.java:143): bytes identical to the oracle's emulation."""
     label, v = cases.reference_matrix(big=True)[-2]
     assert len(v) == 1333333
     vi = cases.to_i32(v)
@@ -112,7 +111,7 @@ def test_multipage_fastpfor(ctx):
         dec = ctx.codec_decode(cid, N.FRAME_WORDS, w.view(np.uint8), np.array([0, w.size * 4], np.int64), off)
         assert np.array_equal(dec, vi)
         out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vi, off)
-        assert out.size == w.size * 4
+        assert bytes(out) == w.tobytes()
         assert np.array_equal(cref.uncompress(cid, out.view(np.int32), len(v)), vi)
     label, s = cases.reference_matrix(big=True)[-1]
     si = cases.to_i32(s)
