@@ -84,6 +84,10 @@ int  mcp_create(int device, mcp_ctx **out);
 void mcp_destroy(mcp_ctx *ctx);
 int  mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
 int  mcp_sync(mcp_ctx *ctx);
+/* Tuning / test switches.  Keys: "force_dense" (1 = value every trial into a dense tile and select once, the
+ * path used for factor counts without a streaming kernel), "force_sort_finalize" (1 = breach list by bitonic
+ * sort instead of the trial bitmap).  Results are identical either way; only the kernels differ. */
+int  mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value);
 
 /* Upper bound on the encoded size in BYTES of one list of n ints under `framing`
  * (the analogue of the reference's `new int[4*n + 1024]`, LoadPortfolios.java:611). */

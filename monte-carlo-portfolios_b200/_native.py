@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
         "mcp_destroy": (None, [vp]),
         "mcp_device_info": (C.c_int, [vp, P(C.c_int), P(C.c_int), P(C.c_int), P(sz)]),
         "mcp_sync": (C.c_int, [vp]),
+        "mcp_set_option": (C.c_int, [vp, C.c_char_p, i64]),
         "mcp_codec_max_bytes": (i64, [C.c_int, C.c_int, i64]),
         "mcp_codec_compress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
         "mcp_codec_uncompress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),

@@ -85,6 +85,9 @@ struct mcp_ctx {
     mcp::DevBuf dFlush;            // L2 flush buffer
     mcp::DevBuf dGenVals, dGenOff; // synthetic breach lists
     mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
+    mcp::DevBuf dKept2Key, dKept2Idx, dFinKey, dFinIdx;
+    bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
+    bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)
 
     mcp::Profile prof;

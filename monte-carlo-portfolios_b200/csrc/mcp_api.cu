@@ -114,7 +114,8 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dShift, &ctx->dSizes,
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
-                           &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow};
+                           &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
+                           &ctx->dFinKey, &ctx->dFinIdx};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -130,6 +131,15 @@ int mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, s
     if (cc_major) *cc_major = ctx->prop.major;
     if (cc_minor) *cc_minor = ctx->prop.minor;
     if (hbm_bytes) *hbm_bytes = ctx->prop.totalGlobalMem;
+    return MCP_OK;
+}
+
+int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
+{
+    if (!ctx || !key) return MCP_E_ARG;
+    if (!strcmp(key, "force_dense")) ctx->forceDense = value != 0;
+    else if (!strcmp(key, "force_sort_finalize")) ctx->forceSortFinalize = value != 0;
+    else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
 }
 

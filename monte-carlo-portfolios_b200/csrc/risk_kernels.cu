@@ -6,6 +6,8 @@
 // Bit-exactness contract: V[p][n] is ONE fma chain over k ascending starting from +0.0,
 // on both sides, so every loss is bit-identical to the oracle's and the selected trial
 // indices are exact.
+#include <vector>
+
 #include "common.cuh"
 
 namespace mcp {
@@ -172,10 +174,10 @@ int fp64_peak(mcp_ctx *ctx, double *tflops)
 // ============================================================ valuation (generic F)
 // V tile = 64 portfolios x 64 trials per CTA, 4x4 register micro-tile per thread, k staged
 // through shared memory in slabs of 32.  Every (p,n) accumulator is a single fma chain in
-// ascending k.  Writes either V or loss = 0.0 - V, row-major [p][n].
+// ascending k.  Writes V row-major [p - p0][N].  Used for factor counts
+// without a specialised streaming kernel and for mcp_value().
 constexpr int VT = 64, VK = 32;
 
-template <bool LOSS>
 __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict__ E, const double *__restrict__ S,
                                                        int64_t p0, int64_t P1, int64_t N, int32_t F,
                                                        double *__restrict__ out /* [(P1-p0)][N] */)
@@ -217,8 +219,251 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int64_t n = nb + tx + 16 * j;
-            if (n < N) out[(p - p0) * N + n] = LOSS ? 0.0 - acc[i][j] : acc[i][j];
+            if (n < N) out[(p - p0) * N + n] = acc[i][j];
         }
+    }
+}
+
+// ============================================================ valuation, F = 32, streaming
+// Kernel (1)+(2a)+(3a) fused for the headline shape.  "E-stationary": every lane keeps the
+// exposure rows of TWO portfolios in registers (2 x 32 doubles) and streams trials past them;
+// a warp therefore owns 64 portfolios, a CTA (8 consumer warps) 512.  The scenario rows of a
+// trial sub-chunk are staged into shared memory by ONE elected producer thread with
+// cp.async.bulk (TMA bulk copy, mbarrier complete_tx), 4 stages of 32 trials (8 KB each), and
+// read back as warp-broadcast LDS.128 (one load feeds 4 DFMAs).  Per (portfolio, trial) the
+// accumulator is a single fma chain over k ascending -> bit-identical to the oracle.
+// Fused on the value while it is still in a register:
+//   * moments: d = V - c_p (c_p = V[p][trial 0]), s1 += d, s2 = fma(d,d,s2)
+//   * tail filter: DENSE steps store every V; SPARSE steps append (V, trial) only when
+//     V <= ntau_p, i.e. loss >= the current lower bound of the portfolio's VaR, pre-screened
+//     with an integer compare on the order-preserving image of the high word.
+// Each lane appends to its own private segment (portfolio, sub-chunk): no atomics.
+constexpr int VS_CWARPS = 8;                 // consumer warps
+constexpr int VS_THREADS = VS_CWARPS * 32;
+constexpr int VS_PG = VS_CWARPS * 64;        // portfolios per CTA
+constexpr int VS_ST = 32;                    // trials per stage
+constexpr int VS_NSTAGE = 4;
+constexpr int VS_F = 32;
+
+struct StreamArgs {
+    const double *E, *S;
+    int64_t p0, p1;          // portfolio tile
+    int64_t n_begin, n_end;  // trial range of this step
+    int nsub;                // sub-chunks (gridDim.x)
+    int sub_len;             // trials per sub-chunk (multiple of 8)
+    const double *ntau;      // [P] candidate iff V <= ntau (SPARSE)
+    const uint32_t *thr_hi;  // [P] order-preserving image of ntau's high word
+    double *candV;           // [p - p0][stride]
+    int32_t *candI;          // [p - p0][stride]   (SPARSE)
+    int64_t stride;
+    int32_t *cnt;            // [p - p0][nsub]     (SPARSE)
+    double *part;            // [P][part_stride][2]
+    int part_stride, part_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t hi_image(double x)
+{
+    const int hi = __double2hiint(x);
+    return (uint32_t)hi ^ ((uint32_t)(hi >> 31) | 0x80000000u);
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamArgs a)
+{
+    __shared__ __align__(128) double s_S[VS_NSTAGE][VS_ST * VS_F];
+    __shared__ __align__(8) uint64_t s_full[VS_NSTAGE], s_empty[VS_NSTAGE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = blockIdx.x;
+    const int64_t nb = a.n_begin + (int64_t)sub * a.sub_len;
+    const int64_t ne = min(a.n_end, nb + a.sub_len);
+    const int ntr = (int)(ne - nb);
+    const int nst = (ntr + VS_ST - 1) / VS_ST;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VS_NSTAGE; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], VS_CWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // Producer duty: lane 0 of warp 0 keeps the stage ring full (prefetch distance NSTAGE-1 stages).  A 9th,
+    // dedicated producer warp would put three warps on one SM sub-partition and cap every thread at 168
+    // registers (spills); eight warps leave 255.
+    auto produce = [&](int it) {
+        const int st = it % VS_NSTAGE;
+        if (it >= VS_NSTAGE) mbar_wait(&s_empty[st], ((it / VS_NSTAGE) - 1) & 1);
+        const int rows = min(VS_ST, ntr - it * VS_ST);
+        const uint32_t bytes = (uint32_t)rows * VS_F * sizeof(double);
+        mbar_expect_tx(&s_full[st], bytes);
+        bulk_g2s(&s_S[st][0], a.S + (nb + (int64_t)it * VS_ST) * VS_F, bytes, &s_full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int it = 0; it < VS_NSTAGE - 1 && it < nst; ++it) produce(it);
+    // ===== consumers
+    const int64_t pA = a.p0 + (int64_t)blockIdx.y * VS_PG + warp * 64 + lane, pB = pA + 32;
+    const bool okA = pA < a.p1, okB = pB < a.p1;
+    double e0[VS_F], e1[VS_F];
+    {
+        const double2 *ra = reinterpret_cast<const double2 *>(a.E + (okA ? pA : a.p0) * VS_F);
+        const double2 *rb = reinterpret_cast<const double2 *>(a.E + (okB ? pB : a.p0) * VS_F);
+#pragma unroll
+        for (int k = 0; k < VS_F; k += 2) {
+            const double2 x = __ldg(ra + (k >> 1)), y = __ldg(rb + (k >> 1));
+            e0[k] = x.x; e0[k + 1] = x.y; e1[k] = y.x; e1[k + 1] = y.y;
+        }
+    }
+    // shift c_p = V[p][0]  (same fma chain as any other valuation)
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < VS_F; ++k) {
+        const double s = __ldg(a.S + k);
+        c0 = fma(e0[k], s, c0);
+        c1 = fma(e1[k], s, c1);
+    }
+    double ntau0 = 0.0, ntau1 = 0.0;
+    uint32_t thr0 = 0, thr1 = 0;
+    if (!DENSE) {
+        if (okA) { ntau0 = a.ntau[pA]; thr0 = a.thr_hi[pA]; }
+        if (okB) { ntau1 = a.ntau[pB]; thr1 = a.thr_hi[pB]; }
+    }
+    const int64_t rowA = (pA - a.p0) * a.stride + (int64_t)sub * a.sub_len;
+    const int64_t rowB = (pB - a.p0) * a.stride + (int64_t)sub * a.sub_len;
+    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
+    int cntA = 0, cntB = 0;
+
+    for (int it = 0; it < nst; ++it) {
+        const int st = it % VS_NSTAGE;
+        if (threadIdx.x == 0 && it + VS_NSTAGE - 1 < nst) produce(it + VS_NSTAGE - 1);
+        __syncwarp();
+        mbar_wait(&s_full[st], (it / VS_NSTAGE) & 1);
+        const int rows = min(VS_ST, ntr - it * VS_ST);
+        const double *sbase = &s_S[st][0];
+        for (int tg = 0; tg * 4 < rows; ++tg) {
+            const double *srow = sbase + tg * 4 * VS_F;
+            double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < VS_F; k += 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 s = *reinterpret_cast<const double2 *>(srow + j * VS_F + k); // warp-broadcast LDS.128
+                    a0[j] = fma(e0[k], s.x, a0[j]);
+                    a1[j] = fma(e1[k], s.x, a1[j]);
+                    a0[j] = fma(e0[k + 1], s.y, a0[j]);
+                    a1[j] = fma(e1[k + 1], s.y, a1[j]);
+                }
+            }
+            const int tl = it * VS_ST + tg * 4; // trial offset inside the sub-chunk
+            const int valid = min(4, rows - tg * 4);
+            if (DENSE) {
+                if (valid == 4) {
+                    if (okA) {
+                        double2 *d = reinterpret_cast<double2 *>(a.candV + rowA + tl);
+                        d[0] = make_double2(a0[0], a0[1]);
+                        d[1] = make_double2(a0[2], a0[3]);
+                    }
+                    if (okB) {
+                        double2 *d = reinterpret_cast<double2 *>(a.candV + rowB + tl);
+                        d[0] = make_double2(a1[0], a1[1]);
+                        d[1] = make_double2(a1[2], a1[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < valid) {
+                            if (okA) a.candV[rowA + tl + j] = a0[j];
+                            if (okB) a.candV[rowB + tl + j] = a1[j];
+                        }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < valid) {
+                    const double da = a0[j] - c0, db = a1[j] - c1;
+                    s1a += da; s2a = fma(da, da, s2a);
+                    s1b += db; s2b = fma(db, db, s2b);
+                    if (!DENSE) {
+                        if (hi_image(a0[j]) <= thr0 && okA && a0[j] <= ntau0) {
+                            a.candV[rowA + cntA] = a0[j];
+                            a.candI[rowA + cntA] = (int32_t)(nb + tl + j);
+                            ++cntA;
+                        }
+                        if (hi_image(a1[j]) <= thr1 && okB && a1[j] <= ntau1) {
+                            a.candV[rowB + cntB] = a1[j];
+                            a.candI[rowB + cntB] = (int32_t)(nb + tl + j);
+                            ++cntB;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+    }
+    const int slot = a.part_base + sub;
+    if (okA) {
+        double *q = a.part + ((int64_t)pA * a.part_stride + slot) * 2;
+        q[0] = s1a; q[1] = s2a;
+        if (!DENSE) a.cnt[(pA - a.p0) * a.nsub + sub] = cntA;
+    }
+    if (okB) {
+        double *q = a.part + ((int64_t)pB * a.part_stride + slot) * 2;
+        q[0] = s1b; q[1] = s2b;
+        if (!DENSE) a.cnt[(pB - a.p0) * a.nsub + sub] = cntB;
+    }
+}
+
+// mean / population variance from the per-sub-chunk partial sums: one warp per portfolio, lane-strided
+// partials then a fixed shuffle tree, so the result does not depend on scheduling (deterministic)
+__global__ void __launch_bounds__(256) k_moments_finalize(const double *E, const double *S, int64_t P, int32_t F, int64_t N,
+                                                          const double *part, int part_stride, int nparts, double *mean,
+                                                          double *variance)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    double s1 = 0.0, s2 = 0.0;
+    const double2 *q = reinterpret_cast<const double2 *>(part) + p * part_stride;
+    for (int j = lane; j < nparts; j += 32) {
+        const double2 v = q[j];
+        s1 += v.x;
+        s2 += v.y;
+    }
+    for (int d = 16; d; d >>= 1) {
+        s1 += __shfl_down_sync(kFullMask, s1, d);
+        s2 += __shfl_down_sync(kFullMask, s2, d);
+    }
+    if (lane == 0) {
+        double c = 0.0;
+        for (int k = 0; k < F; ++k) c = fma(E[p * F + k], S[k], c);
+        const double invn = 1.0 / (double)N, m1 = s1 * invn;
+        mean[p] = c + m1;
+        variance[p] = fma(-m1, m1, s2 * invn);
     }
 }
 
@@ -240,22 +485,33 @@ __device__ __forceinline__ u128 comp_of(uint64_t key, uint32_t idx) { return ((u
 
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_BINS = 4096;   // 12-bit digits over the 96-bit composite (key64, trial32)
-constexpr int SEL_CAP = 8192;    // candidates resolved in shared memory
+constexpr int SEL_CAP = 8192;    // shared-memory candidate capacity
+constexpr int SEL_SORT = 256;    // keep refining digits until the boundary bucket is at most this big
 constexpr size_t SEL_SMEM = (size_t)SEL_CAP * 12 + (size_t)SEL_BINS * 4;
 
+// Candidates of one portfolio row = the previously kept tail (key, trial) plus this step's
+// segments of raw values V (loss = 0.0 - V), one segment per trial sub-chunk.
 struct SelArgs {
-    const double *loss;      // dense: [rows][row_stride]; candidate i of row r = loss[r*row_stride + i]
-    const int32_t *idx;      // null -> trial = idx_base + i
-    int64_t row_stride;
-    const int32_t *count;    // null -> `n` candidates per row
-    int64_t n;
-    int32_t idx_base;
-    int64_t tail;            // t
-    int64_t moments_n;       // N for the moments (dense rows only; 0 = skip)
-    uint64_t *kept_key;      // [rows][tail]
-    int32_t *kept_idx;       // [rows][tail]
-    double *mean, *variance, *var_loss;
+    const double *candV;       // [rows][stride]
+    const int32_t *candI;      // null -> dense: trial = n_begin + seg*sub_len + i
+    int64_t stride;
+    const int32_t *cnt;        // [rows][nsub]; null -> dense (segment full)
+    int nsub;
+    int64_t sub_len;
+    int64_t step_len;          // dense: number of valid trials in the step
+    int64_t n_begin;
+    const uint64_t *kept_key_in;
+    const int32_t *kept_idx_in;
+    int64_t kept_n;            // 0 or tail
+    uint64_t *kept_key_out;    // [rows][tail]
+    int32_t *kept_idx_out;
+    int64_t tail;              // t
+    int64_t moments_n;         // > 0: also compute mean/variance from the dense row (generic path)
+    double *mean, *variance;   // [rows] (moments_n > 0)
+    double *var_loss;          // [rows]
     int32_t *var_trial;
+    double *ntau;              // [rows] 0.0 - var_loss, for the next step's filter
+    uint32_t *thr_hi;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
@@ -277,6 +533,25 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
     return t;
 }
 
+template <class Fn>
+__device__ __forceinline__ void for_each_candidate(const SelArgs &a, int64_t row, Fn f)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.tail + i], (uint32_t)a.kept_idx_in[row * a.tail + i]);
+    const double *V = a.candV + row * a.stride;
+    const int32_t *I = a.candI ? a.candI + row * a.stride : nullptr;
+    for (int seg = warp; seg < a.nsub; seg += SEL_THREADS / 32) {
+        const int64_t base = (int64_t)seg * a.sub_len;
+        int64_t c;
+        if (a.cnt) c = a.cnt[row * a.nsub + seg];
+        else { c = a.step_len - base; c = c < 0 ? 0 : (c > a.sub_len ? a.sub_len : c); }
+        for (int64_t i = lane; i < c; i += 32) {
+            const uint32_t id = I ? (uint32_t)I[base + i] : (uint32_t)(a.n_begin + base + i);
+            f(fkey(0.0 - V[base + i]), id);
+        }
+    }
+}
+
 // One CTA per portfolio row: exact top-`tail` of (loss, trial) by MSB-first radix select.
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
 {
@@ -287,20 +562,18 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     __shared__ double red[32];
     __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept;
     const int64_t row = blockIdx.x;
-    const double *L = a.loss + row * a.row_stride;
-    const int32_t *I = a.idx ? a.idx + row * a.row_stride : nullptr;
-    const int64_t n = a.count ? a.count[row] : a.n;
     const int64_t t = a.tail;
-    uint64_t *kk = a.kept_key + row * t;
-    int32_t *ki = a.kept_idx + row * t;
+    uint64_t *kk = a.kept_key_out + row * t;
+    int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x;
 
-    // ---- moments of V = -loss with shift c = V[0]
+    // ---- moments of the dense row with shift c = V[0] (generic path only)
     if (a.moments_n > 0) {
-        const double c = -L[0];
+        const double *V = a.candV + row * a.stride;
+        const double c = V[0];
         double s1 = 0.0, s2 = 0.0;
-        for (int64_t i = tid; i < n; i += SEL_THREADS) {
-            const double d = -L[i] - c;
+        for (int64_t i = tid; i < a.step_len; i += SEL_THREADS) {
+            const double d = V[i] - c;
             s1 += d;
             s2 = fma(d, d, s2);
         }
@@ -323,10 +596,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         shift -= 12;
         for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
         __syncthreads();
-        for (int64_t i = tid; i < n; i += SEL_THREADS) {
-            const u128 c = comp_of(fkey(L[i]), (uint32_t)(I ? I[i] : a.idx_base + (int32_t)i));
+        for_each_candidate(a, row, [&](uint64_t key, uint32_t id) {
+            const u128 c = comp_of(key, id);
             if (pass == 0 || (c >> (shift + 12)) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (SEL_BINS - 1)], 1);
-        }
+        });
         __syncthreads();
         // warp 0: find the digit where the count from the top reaches `need`
         if (tid < 32) {
@@ -354,14 +627,12 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         need -= s_above;
         bucket = s_bucket;
         __syncthreads();
-        if (bucket <= SEL_CAP) break;
+        if (bucket <= SEL_SORT) break;
     }
     // ---- gather: strictly-above-prefix -> kept; equal-prefix -> shared candidates
     if (tid == 0) s_ncand = 0;
     __syncthreads();
-    for (int64_t i = tid; i < n; i += SEL_THREADS) {
-        const uint64_t key = fkey(L[i]);
-        const uint32_t id = (uint32_t)(I ? I[i] : a.idx_base + (int32_t)i);
+    for_each_candidate(a, row, [&](uint64_t key, uint32_t id) {
         const u128 hp = comp_of(key, id) >> shift;
         if (hp > prefix) {
             const int o = atomicAdd(&s_nkept, 1);
@@ -372,7 +643,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             ckey[o] = key;
             cidx[o] = id;
         }
-    }
+    });
     __syncthreads();
     // ---- bitonic sort of the candidates, descending composite; pads (0,0) sink to the end
     int m = 1;
@@ -400,15 +671,72 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         kk[base + i] = ckey[i];
         ki[base + i] = (int32_t)cidx[i];
     }
-    if (tid == 0) { // the need-th largest candidate is the VaR order statistic
-        a.var_loss[row] = fkey_inv(ckey[need - 1]);
+    if (tid == 0) { // the need-th largest candidate is the VaR order statistic (so far)
+        const double vl = fkey_inv(ckey[need - 1]);
+        a.var_loss[row] = vl;
         a.var_trial[row] = (int32_t)cidx[need - 1];
+        if (a.ntau) {
+            const double nt = 0.0 - vl; // canonical +0.0 for a zero loss
+            a.ntau[row] = nt;
+            a.thr_hi[row] = hi_image(nt);
+        }
     }
 }
 
 // ============================================================ finalize
-// Sort the kept tail by trial index (ascending) -> breach list; CVaR = mean tail loss.
+// Kernel (3): the kept tail -> ascending breach-trial list, and CVaR = mean tail loss.
+// Stream compaction over a per-portfolio trial bitmap in shared memory: set one bit per kept
+// trial, prefix-sum the word popcounts, then every set bit knows its rank.  (Falls back to a
+// bitonic sort by trial index when the trial range does not fit the bitmap.)
 constexpr int FIN_THREADS = 256;
+constexpr int64_t FIN_BITMAP_MAX_TRIALS = 1400000; // 175 KB of bitmap + scan scratch
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
+                                                                 int64_t n_trials, int32_t trial_base, int32_t *breach,
+                                                                 double *cvar)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int s_wsum[FIN_THREADS / 32];
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smem_raw);
+    const int nwords = (int)((n_trials + 31) >> 5);
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < nwords; i += FIN_THREADS) bm[i] = 0;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = tid; i < t; i += FIN_THREADS) {
+        const int32_t id = kept_idx[row * t + i] - trial_base;
+        atomicOr(&bm[id >> 5], 1u << (id & 31));
+        s += fkey_inv(kept_key[row * t + i]);
+    }
+    s = block_sum(s, red);
+    if (tid == 0) cvar[row] = s / (double)t;
+    __syncthreads();
+    // each thread owns a contiguous run of words
+    const int per = (nwords + FIN_THREADS - 1) / FIN_THREADS;
+    const int w0 = tid * per, w1 = min(nwords, w0 + per);
+    int c = 0;
+    for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
+    int incl = c;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int off = incl - c;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    int32_t *dst = breach + row * t;
+    for (int w = w0; w < w1; ++w) {
+        uint32_t m = bm[w];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            dst[off++] = trial_base + (w << 5) + b;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
                                                           int m /* pow2 >= t */, int32_t *breach, double *cvar,
@@ -458,9 +786,210 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
     if (p1 <= p0) return MCP_OK;
     dim3 grid((unsigned)((ctx->N + VT - 1) / VT), (unsigned)((p1 - p0 + VT - 1) / VT));
     KScope ks(ctx, MCP_K_VALUE);
-    k_value_generic<false><<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), p0, p1, ctx->N,
-                                                         ctx->F, d_V);
+    k_value_generic<<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), p0, p1, ctx->N, ctx->F, d_V);
     return check_launch(ctx, "k_value_generic");
+}
+
+struct Step { int64_t begin, end; int nsub; int sub_len; };
+
+// Trial schedule of the streaming path: a dense first step of ~4 tail sizes establishes each
+// portfolio's threshold, then steps double in length; every later step inserts ~tail candidates.
+static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sms)
+{
+    std::vector<Step> steps;
+    int64_t c0 = 4 * t;
+    if (c0 < 2048) c0 = 2048;
+    int64_t b = 0, len = c0;
+    while (b < N) {
+        int64_t e = b + len;
+        if (e > N || N - e < len / 4) e = N; // fold a short remainder into the last step
+        const int64_t L = e - b;
+        int64_t waves = (L * nsg + (int64_t)sms * 64) / ((int64_t)sms * 128);
+        if (waves < 1) waves = 1;
+        int64_t nsub = (sms * waves) / nsg;
+        if (nsub < 1) nsub = 1;
+        if (nsub > L / 8) nsub = L / 8 > 0 ? L / 8 : 1;
+        int64_t sl = (L + nsub - 1) / nsub;
+        sl = (sl + 7) & ~(int64_t)7;
+        nsub = (L + sl - 1) / sl;
+        steps.push_back({b, e, (int)nsub, (int)sl});
+        b = e;
+        len = e; // doubling: the next step is as long as everything seen so far
+    }
+    return steps;
+}
+
+static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *kk, const int32_t *ki, int32_t *breach, double *cvar)
+{
+    if (ctx->N <= FIN_BITMAP_MAX_TRIALS && !ctx->forceSortFinalize) {
+        const size_t bm_smem = (size_t)((ctx->N + 31) / 32) * 4;
+        if (bm_smem > 48 * 1024)
+            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        KScope ks(ctx, MCP_K_SELECT);
+        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, ctx->stream>>>(kk, ki, t, ctx->N, 0, breach, cvar);
+        return check_launch(ctx, "k_finalize_bitmap");
+    }
+    int m = 1;
+    while (m < t) m <<= 1;
+    const size_t fin_smem = (size_t)m * 12;
+    const bool fin_global = fin_smem > 200 * 1024;
+    if (fin_global) {
+        MCP_CUDA(ctx, ctx->dFinKey.reserve((size_t)rows * m * sizeof(uint64_t)));
+        MCP_CUDA(ctx, ctx->dFinIdx.reserve((size_t)rows * m * sizeof(int32_t)));
+    } else if (fin_smem > 48 * 1024) {
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    }
+    KScope ks(ctx, MCP_K_SELECT);
+    k_finalize<<<(unsigned)rows, FIN_THREADS, fin_global ? 0 : fin_smem, ctx->stream>>>(
+        kk, ki, t, m, breach, cvar, fin_global ? ctx->dFinKey.as<uint64_t>() : nullptr, fin_global ? ctx->dFinIdx.as<int32_t>() : nullptr);
+    return check_launch(ctx, "k_finalize");
+}
+
+// generic factor count: dense V tile + one selection pass per portfolio
+static int risk_run_dense(mcp_ctx *ctx, int64_t t)
+{
+    const int64_t P = ctx->P, N = ctx->N;
+    size_t budget = ctx->prop.totalGlobalMem / 4;
+    if (budget > ((size_t)32 << 30)) budget = (size_t)32 << 30;
+    int64_t Pt = (int64_t)(budget / ((size_t)N * sizeof(double)));
+    if (Pt < 1) return fail(ctx, MCP_E_NOMEM, "run: one loss row does not fit the tile budget");
+    if (Pt > P) Pt = P;
+    if (Pt > 65535 * (int64_t)VT) Pt = 65535 * (int64_t)VT;
+    MCP_CUDA(ctx, ctx->dLoss.reserve((size_t)Pt * N * sizeof(double)));
+    for (int64_t p0 = 0; p0 < P; p0 += Pt) {
+        const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
+        MCP_TRY(risk_value(ctx, p0, p1, ctx->dLoss.as<double>()));
+        SelArgs a{};
+        a.candV = ctx->dLoss.as<double>();
+        a.stride = N;
+        a.nsub = 1;
+        a.sub_len = N;
+        a.step_len = N;
+        a.n_begin = 0;
+        a.kept_n = 0;
+        a.kept_key_out = ctx->dKeptKey.as<uint64_t>() + p0 * t;
+        a.kept_idx_out = ctx->dKeptIdx.as<int32_t>() + p0 * t;
+        a.tail = t;
+        a.moments_n = N;
+        a.mean = ctx->dMean.as<double>() + p0;
+        a.variance = ctx->dVar.as<double>() + p0;
+        a.var_loss = ctx->dVarLoss.as<double>() + p0;
+        a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
+        {
+            KScope ks(ctx, MCP_K_SELECT);
+            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, SEL_SMEM, ctx->stream>>>(a);
+            MCP_TRY(check_launch(ctx, "k_select"));
+        }
+        MCP_TRY(run_finalize(ctx, p1 - p0, t, a.kept_key_out, a.kept_idx_out, ctx->dBreach.as<int32_t>() + p0 * t,
+                             ctx->dCvar.as<double>() + p0));
+    }
+    return MCP_OK;
+}
+
+// F = 32: streaming valuation + threshold filter + incremental radix-select
+static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
+{
+    const int64_t P = ctx->P, N = ctx->N;
+    const int sms = ctx->prop.multiProcessorCount;
+    // portfolio tile: candidate buffers are Pt x (longest step) x 12 bytes; keep them under 1/4 of HBM
+    size_t budget = ctx->prop.totalGlobalMem / 4;
+    if (budget > ((size_t)40 << 30)) budget = (size_t)40 << 30;
+    int64_t Pt = P;
+    std::vector<Step> steps;
+    int64_t stride = 0;
+    int max_nsub = 0, nparts = 0;
+    for (;;) {
+        const int64_t nsg = (Pt + VS_PG - 1) / VS_PG;
+        steps = make_schedule(N, t, nsg, sms);
+        stride = 0; max_nsub = 0; nparts = 0;
+        for (auto &s : steps) {
+            const int64_t w = (int64_t)s.nsub * s.sub_len;
+            if (w > stride) stride = w;
+            if (s.nsub > max_nsub) max_nsub = s.nsub;
+            nparts += s.nsub;
+        }
+        stride = (stride + 3) & ~(int64_t)3;
+        if ((size_t)Pt * stride * 12 <= budget || Pt <= VS_PG) break;
+        Pt = ((Pt / 2 + VS_PG - 1) / VS_PG) * VS_PG;
+    }
+    if (Pt > 65535 * (int64_t)VS_PG) Pt = 65535 * (int64_t)VS_PG;
+    MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dCandIdx.reserve((size_t)Pt * stride * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * (sizeof(double) + sizeof(uint32_t))));
+    MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
+    double *ntau = ctx->dTau.as<double>();
+    uint32_t *thr = reinterpret_cast<uint32_t *>(ntau + P);
+
+    for (int64_t p0 = 0; p0 < P; p0 += Pt) {
+        const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
+        const int64_t rows = p1 - p0;
+        uint64_t *kkey[2] = {ctx->dKeptKey.as<uint64_t>() + p0 * t, ctx->dKept2Key.as<uint64_t>() + p0 * t};
+        int32_t *kidx[2] = {ctx->dKeptIdx.as<int32_t>() + p0 * t, ctx->dKept2Idx.as<int32_t>() + p0 * t};
+        int cur = 0, part_base = 0;
+        for (size_t si = 0; si < steps.size(); ++si) {
+            const Step &s = steps[si];
+            const bool dense = si == 0;
+            StreamArgs v{};
+            v.E = ctx->dE.as<double>();
+            v.S = ctx->dS.as<double>();
+            v.p0 = p0; v.p1 = p1;
+            v.n_begin = s.begin; v.n_end = s.end;
+            v.nsub = s.nsub; v.sub_len = s.sub_len;
+            v.ntau = ntau; v.thr_hi = thr;
+            v.candV = ctx->dCandKey.as<double>();
+            v.candI = ctx->dCandIdx.as<int32_t>();
+            v.stride = stride;
+            v.cnt = ctx->dCandCnt.as<int32_t>();
+            v.part = ctx->dPart.as<double>();
+            v.part_stride = nparts; v.part_base = part_base;
+            dim3 grid((unsigned)s.nsub, (unsigned)((rows + VS_PG - 1) / VS_PG));
+            {
+                KScope ks(ctx, MCP_K_VALUE);
+                if (dense) k_value_stream32<true><<<grid, VS_THREADS, 0, ctx->stream>>>(v);
+                else k_value_stream32<false><<<grid, VS_THREADS, 0, ctx->stream>>>(v);
+                MCP_TRY(check_launch(ctx, "k_value_stream32"));
+            }
+            SelArgs a{};
+            a.candV = v.candV;
+            a.candI = dense ? nullptr : v.candI;
+            a.stride = stride;
+            a.cnt = dense ? nullptr : v.cnt;
+            a.nsub = s.nsub;
+            a.sub_len = s.sub_len;
+            a.step_len = s.end - s.begin;
+            a.n_begin = s.begin;
+            a.kept_key_in = kkey[cur];
+            a.kept_idx_in = kidx[cur];
+            a.kept_n = dense ? 0 : t;
+            a.kept_key_out = kkey[cur ^ 1];
+            a.kept_idx_out = kidx[cur ^ 1];
+            a.tail = t;
+            a.moments_n = 0;
+            a.var_loss = ctx->dVarLoss.as<double>() + p0;
+            a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
+            a.ntau = ntau + p0;
+            a.thr_hi = thr + p0;
+            {
+                KScope ks(ctx, MCP_K_SELECT);
+                k_select<<<(unsigned)rows, SEL_THREADS, SEL_SMEM, ctx->stream>>>(a);
+                MCP_TRY(check_launch(ctx, "k_select"));
+            }
+            cur ^= 1;
+            part_base += s.nsub;
+        }
+        MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], ctx->dBreach.as<int32_t>() + p0 * t, ctx->dCvar.as<double>() + p0));
+    }
+    {
+        KScope ks(ctx, MCP_K_SELECT);
+        k_moments_finalize<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), P, ctx->F, N,
+                                                                                ctx->dPart.as<double>(), nparts, nparts,
+                                                                                ctx->dMean.as<double>(), ctx->dVar.as<double>());
+        MCP_TRY(check_launch(ctx, "k_moments_finalize"));
+    }
+    return MCP_OK;
 }
 
 int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
@@ -478,66 +1007,11 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     MCP_CUDA(ctx, ctx->dBreach.reserve((size_t)P * t * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dKeptKey.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * t * sizeof(int32_t)));
-
-    // dense loss tile budget: a quarter of HBM, at most 32 GiB
-    size_t budget = ctx->prop.totalGlobalMem / 4;
-    if (budget > ((size_t)32 << 30)) budget = (size_t)32 << 30;
-    int64_t Pt = (int64_t)(budget / ((size_t)N * sizeof(double)));
-    if (Pt < 1) return fail(ctx, MCP_E_NOMEM, "run: one loss row does not fit the tile budget");
-    if (Pt > P) Pt = P;
-    if (Pt > 65535 * (int64_t)VT) Pt = 65535 * (int64_t)VT;
-    MCP_CUDA(ctx, ctx->dLoss.reserve((size_t)Pt * N * sizeof(double)));
-
-    int m = 1;
-    while (m < t) m <<= 1;
-    const size_t fin_smem = (size_t)m * 12;
-    const bool fin_global = fin_smem > 200 * 1024;
-    if (fin_global) {
-        MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * m * sizeof(uint64_t)));
-        MCP_CUDA(ctx, ctx->dCandIdx.reserve((size_t)Pt * m * sizeof(int32_t)));
-    } else if (fin_smem > 48 * 1024) {
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    }
-
     MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
 
-    for (int64_t p0 = 0; p0 < P; p0 += Pt) {
-        const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
-        {
-            dim3 grid((unsigned)((N + VT - 1) / VT), (unsigned)((p1 - p0 + VT - 1) / VT));
-            KScope ks(ctx, MCP_K_VALUE);
-            k_value_generic<true><<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), p0, p1, N,
-                                                                ctx->F, ctx->dLoss.as<double>());
-            MCP_TRY(check_launch(ctx, "k_value_generic"));
-        }
-        SelArgs a{};
-        a.loss = ctx->dLoss.as<double>();
-        a.idx = nullptr;
-        a.row_stride = N;
-        a.count = nullptr;
-        a.n = N;
-        a.idx_base = 0;
-        a.tail = t;
-        a.moments_n = N;
-        a.kept_key = ctx->dKeptKey.as<uint64_t>() + p0 * t;
-        a.kept_idx = ctx->dKeptIdx.as<int32_t>() + p0 * t;
-        a.mean = ctx->dMean.as<double>() + p0;
-        a.variance = ctx->dVar.as<double>() + p0;
-        a.var_loss = ctx->dVarLoss.as<double>() + p0;
-        a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
-        {
-            KScope ks(ctx, MCP_K_SELECT);
-            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, SEL_SMEM, ctx->stream>>>(a);
-            MCP_TRY(check_launch(ctx, "k_select"));
-        }
-        {
-            KScope ks(ctx, MCP_K_SELECT);
-            k_finalize<<<(unsigned)(p1 - p0), FIN_THREADS, fin_global ? 0 : fin_smem, ctx->stream>>>(
-                a.kept_key, a.kept_idx, t, m, ctx->dBreach.as<int32_t>() + p0 * t, ctx->dCvar.as<double>() + p0,
-                fin_global ? ctx->dCandKey.as<uint64_t>() : nullptr, fin_global ? ctx->dCandIdx.as<int32_t>() : nullptr);
-            MCP_TRY(check_launch(ctx, "k_finalize"));
-        }
-    }
+    if (ctx->F == VS_F && !ctx->forceDense) MCP_TRY(risk_run_stream32(ctx, t));
+    else MCP_TRY(risk_run_dense(ctx, t));
+
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));
     int64_t total = 0;

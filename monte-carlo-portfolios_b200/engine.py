@@ -74,6 +74,9 @@ class Context:
     def sync(self):
         self._check(self._L.mcp_sync(self._h), "sync")
 
+    def set_option(self, key: str, value: int):
+        self._check(self._L.mcp_set_option(self._h, key.encode(), value), "set_option")
+
     # -- batched codec (host buffers)
     def codec_encode(self, codec_id: int, framing: int, vals, list_off, cap: int | None = None):
         """-> (out_off int64[nlists+1], out uint8[total])"""

@@ -56,11 +56,34 @@ def test_run_matches_oracle(ctx, shape):
     check_against_oracle(ctx, E, S, alpha)
 
 
+@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize"])
+def test_alternate_kernel_paths_agree(ctx, opt):
+    """F = 32 normally takes the streaming kernels + bitmap compaction; the dense tile + single selection and
+    the sort-based breach list must give identical results."""
+    ctx.set_option(opt, 1)
+    try:
+        E, S = riskcases.synthetic(40, 9000, 32, 21)
+        check_against_oracle(ctx, E, S, 0.99)
+        E, S = riskcases.with_ties(8, 5000, 32, 22)
+        check_against_oracle(ctx, E, S, 0.9)
+    finally:
+        ctx.set_option(opt, 0)
+
+
+def test_streaming_path_many_portfolios_ragged(ctx):
+    """F = 32 streaming path with a ragged last portfolio group and trial counts that are not multiples of 4/8/32."""
+    for P, Nn, alpha in ((513, 4099, 0.99), (1030, 2049, 0.9), (70, 33333, 0.999), (3, 7, 0.5), (600, 12345, 0.95)):
+        E, S = riskcases.synthetic(P, Nn, 32, 100 + P)
+        check_against_oracle(ctx, E, S, alpha, rows=list(range(0, P, max(1, P // 37))) + [P - 1])
+
+
 def test_ties_break_by_trial_index(ctx):
     E, S = riskcases.with_ties(20, 3000, 4, 9)
     check_against_oracle(ctx, E, S, 0.9)
     E, S = riskcases.with_ties(4, 40000, 3, 10)   # thousands of identical losses: deep radix passes
     check_against_oracle(ctx, E, S, 0.75)
+    E, S = riskcases.with_ties(70, 40000, 32, 11)  # same through the F = 32 streaming path
+    check_against_oracle(ctx, E, S, 0.75, rows=[0, 1, 35, 69])
 
 
 def test_degenerate_rows(ctx):
@@ -73,7 +96,11 @@ def test_degenerate_rows(ctx):
 
 def test_adversarial_trial_order(ctx):
     """Losses that increase with the trial index (the worst case for any streaming threshold filter)."""
-    F = 4
+    for F in (4, 32):
+        _adversarial(ctx, F)
+
+
+def _adversarial(ctx, F):
     Nn = 30000
     S = np.zeros((Nn, F))
     S[:, 0] = -np.linspace(0.0, 1.0, Nn)
