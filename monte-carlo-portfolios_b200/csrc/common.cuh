@@ -87,6 +87,7 @@ struct mcp_ctx {
     mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
     mcp::DevBuf dKept2Key, dKept2Idx, dFinKey, dFinIdx;
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
+    int selCap = 2304;
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)
 

@@ -483,11 +483,11 @@ __device__ __forceinline__ double fkey_inv(uint64_t k)
 typedef unsigned __int128 u128;
 __device__ __forceinline__ u128 comp_of(uint64_t key, uint32_t idx) { return ((u128)key << 32) | idx; }
 
-constexpr int SEL_THREADS = 512;
-constexpr int SEL_BINS = 4096;   // 12-bit digits over the 96-bit composite (key64, trial32)
-constexpr int SEL_CAP = 8192;    // shared-memory candidate capacity
-constexpr int SEL_SORT = 256;    // keep refining digits until the boundary bucket is at most this big
-constexpr size_t SEL_SMEM = (size_t)SEL_CAP * 12 + (size_t)SEL_BINS * 4;
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_BITS = 11;
+constexpr int SEL_BINS = 1 << SEL_BITS; // 11-bit digits over the 96-bit composite (key64, trial32), MSB first
+constexpr int SEL_SORT = 256;           // keep refining digits until the boundary bucket is at most this big
+constexpr int SEL_NPASS = (96 + SEL_BITS - 1) / SEL_BITS;
 
 // Candidates of one portfolio row = the previously kept tail (key, trial) plus this step's
 // segments of raw values V (loss = 0.0 - V), one segment per trial sub-chunk.
@@ -512,6 +512,7 @@ struct SelArgs {
     int32_t *var_trial;
     double *ntau;              // [rows] 0.0 - var_loss, for the next step's filter
     uint32_t *thr_hi;
+    int cap;                   // shared-memory candidate capacity (entries)
 };
 
 __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
@@ -533,8 +534,9 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
     return t;
 }
 
+// visit every candidate of the row straight from global memory
 template <class Fn>
-__device__ __forceinline__ void for_each_candidate(const SelArgs &a, int64_t row, Fn f)
+__device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, Fn f)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.tail + i], (uint32_t)a.kept_idx_in[row * a.tail + i]);
@@ -552,20 +554,27 @@ __device__ __forceinline__ void for_each_candidate(const SelArgs &a, int64_t row
     }
 }
 
-// One CTA per portfolio row: exact top-`tail` of (loss, trial) by MSB-first radix select.
+// One CTA per portfolio row: exact top-`tail` of (loss, trial) by MSB-first radix select
+// (kernel (2b)).  The row's candidates are staged ONCE into shared memory when they fit
+// (the normal case: a few tail sizes), so the digit passes never go back to HBM; rows with
+// more candidates than `cap` (adversarial trial orders, very large tails) run the same
+// passes straight from global memory.
 __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
 {
     extern __shared__ __align__(16) unsigned char sel_smem[];
-    uint64_t *ckey = reinterpret_cast<uint64_t *>(sel_smem);
-    uint32_t *cidx = reinterpret_cast<uint32_t *>(ckey + SEL_CAP);
-    int *hist = reinterpret_cast<int *>(cidx + SEL_CAP);
+    uint64_t *skey = reinterpret_cast<uint64_t *>(sel_smem);
+    uint32_t *sidx = reinterpret_cast<uint32_t *>(skey + a.cap);
+    int *hist = reinterpret_cast<int *>(sidx + a.cap);
+    __shared__ uint64_t ckey[SEL_SORT];
+    __shared__ uint32_t cidx[SEL_SORT];
     __shared__ double red[32];
-    __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept;
+    __shared__ int s_wsum[SEL_THREADS / 32];
+    __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept, s_total;
     const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
     uint64_t *kk = a.kept_key_out + row * t;
     int32_t *ki = a.kept_idx_out + row * t;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- moments of the dense row with shift c = V[0] (generic path only)
     if (a.moments_n > 0) {
@@ -587,31 +596,74 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         }
     }
 
+    // ---- how many candidates does this row have?  stage them if they fit
+    int64_t M;
+    if (a.cnt) {
+        int c = 0;
+        for (int sgi = tid; sgi < a.nsub; sgi += SEL_THREADS) c += a.cnt[row * a.nsub + sgi];
+        for (int d = 16; d; d >>= 1) c += __shfl_down_sync(kFullMask, c, d);
+        if (lane == 0) s_wsum[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < SEL_THREADS / 32; ++w) tot += s_wsum[w];
+            s_total = tot;
+        }
+        __syncthreads();
+        M = a.kept_n + s_total;
+    } else
+        M = a.kept_n + a.step_len;
+    const bool staged = M <= a.cap;
+    if (tid == 0) { s_ncand = 0; s_nkept = 0; }
+    __syncthreads();
+    if (staged) {
+        for_each_global(a, row, [&](uint64_t key, uint32_t id) {
+            const int o = atomicAdd(&s_ncand, 1);
+            skey[o] = key;
+            sidx[o] = id;
+        });
+        __syncthreads();
+    }
+    const int Ms = (int)M;
+    auto for_each = [&](auto f) {
+        if (staged) {
+            for (int i = tid; i < Ms; i += SEL_THREADS) f(skey[i], sidx[i]);
+        } else
+            for_each_global(a, row, f);
+    };
+
     u128 prefix = 0;     // selected high digits
     int shift = 96;      // bits below the prefix
     int64_t need = t;    // rank from the top still to resolve inside the prefix bucket
-    if (tid == 0) s_nkept = 0;
     int bucket = 0;
-    for (int pass = 0; pass < 8; ++pass) {
-        shift -= 12;
+    for (int pass = 0; pass < SEL_NPASS; ++pass) {
+        const int width = shift >= SEL_BITS ? SEL_BITS : shift;
+        shift -= width;
+        const uint32_t dmask = (1u << width) - 1u;
         for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
         __syncthreads();
-        for_each_candidate(a, row, [&](uint64_t key, uint32_t id) {
+        for_each([&](uint64_t key, uint32_t id) {
             const u128 c = comp_of(key, id);
-            if (pass == 0 || (c >> (shift + 12)) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (SEL_BINS - 1)], 1);
+            if (pass == 0 || (c >> (shift + width)) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & dmask], 1);
         });
         __syncthreads();
-        // warp 0: find the digit where the count from the top reaches `need`
-        if (tid < 32) {
-            constexpr int PER = SEL_BINS / 32;
-            const int hi = SEL_BINS - 1 - tid * PER; // lane 0 owns the highest bins
+        // find the digit where the count from the top reaches `need`: thread 0 owns the highest bins
+        {
+            constexpr int PER = SEL_BINS / SEL_THREADS;
+            const int hi = SEL_BINS - 1 - tid * PER;
             int sum = 0;
+#pragma unroll
             for (int j = 0; j < PER; ++j) sum += hist[hi - j];
             int incl = sum;
             for (int d = 1; d < 32; d <<= 1) {
                 const int v = __shfl_up_sync(kFullMask, incl, d);
-                if (tid >= d) incl += v;
+                if (lane >= d) incl += v;
             }
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+            incl += woff;
             const int excl = incl - sum;
             if ((int64_t)excl < need && need <= (int64_t)incl) {
                 int above = excl;
@@ -623,16 +675,16 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             }
         }
         __syncthreads();
-        prefix = (prefix << 12) | (u128)(uint32_t)s_sel;
+        prefix = (prefix << width) | (u128)(uint32_t)s_sel;
         need -= s_above;
         bucket = s_bucket;
         __syncthreads();
         if (bucket <= SEL_SORT) break;
     }
-    // ---- gather: strictly-above-prefix -> kept; equal-prefix -> shared candidates
+    // ---- gather: strictly-above-prefix -> kept; equal-prefix -> the small boundary bucket
     if (tid == 0) s_ncand = 0;
     __syncthreads();
-    for_each_candidate(a, row, [&](uint64_t key, uint32_t id) {
+    for_each([&](uint64_t key, uint32_t id) {
         const u128 hp = comp_of(key, id) >> shift;
         if (hp > prefix) {
             const int o = atomicAdd(&s_nkept, 1);
@@ -645,7 +697,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         }
     });
     __syncthreads();
-    // ---- bitonic sort of the candidates, descending composite; pads (0,0) sink to the end
+    // ---- bitonic sort of the boundary bucket, descending composite; pads (0,0) sink to the end
     int m = 1;
     while (m < bucket) m <<= 1;
     for (int i = bucket + tid; i < m; i += SEL_THREADS) { ckey[i] = 0; cidx[i] = 0; }
@@ -682,6 +734,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         }
     }
 }
+
+static size_t sel_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4; }
 
 // ============================================================ finalize
 // Kernel (3): the kept tail -> ascending breach-trial list, and CVaR = mean tail loss.
@@ -802,7 +856,7 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
     int64_t b = 0, len = c0;
     while (b < N) {
         int64_t e = b + len;
-        if (e > N || N - e < len / 4) e = N; // fold a short remainder into the last step
+        if (e > N || (b > 0 && N - e < len / 4)) e = N; // fold a short remainder into the last (sparse) step
         const int64_t L = e - b;
         int64_t waves = (L * nsg + (int64_t)sms * 64) / ((int64_t)sms * 128);
         if (waves < 1) waves = 1;
@@ -877,7 +931,8 @@ static int risk_run_dense(mcp_ctx *ctx, int64_t t)
         a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
         {
             KScope ks(ctx, MCP_K_SELECT);
-            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, SEL_SMEM, ctx->stream>>>(a);
+            a.cap = ctx->selCap;
+            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, sel_smem_bytes(a.cap), ctx->stream>>>(a);
             MCP_TRY(check_launch(ctx, "k_select"));
         }
         MCP_TRY(run_finalize(ctx, p1 - p0, t, a.kept_key_out, a.kept_idx_out, ctx->dBreach.as<int32_t>() + p0 * t,
@@ -974,7 +1029,8 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             a.thr_hi = thr + p0;
             {
                 KScope ks(ctx, MCP_K_SELECT);
-                k_select<<<(unsigned)rows, SEL_THREADS, SEL_SMEM, ctx->stream>>>(a);
+                a.cap = ctx->selCap;
+                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap), ctx->stream>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
             cur ^= 1;
@@ -1007,7 +1063,14 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     MCP_CUDA(ctx, ctx->dBreach.reserve((size_t)P * t * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dKeptKey.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * t * sizeof(int32_t)));
-    MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEL_SMEM));
+    {
+        // shared-memory staging capacity of the selection kernel: the dense first step has max(2048, 4t) candidates
+        int64_t cap = 4 * t + 256;
+        if (cap < 2304) cap = 2304;
+        if (cap > 16384) cap = 16384; // 200 KB; larger rows select straight from global memory
+        ctx->selCap = (int)cap;
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap)));
+    }
 
     if (ctx->F == VS_F && !ctx->forceDense) MCP_TRY(risk_run_stream32(ctx, t));
     else MCP_TRY(risk_run_dense(ctx, t));
