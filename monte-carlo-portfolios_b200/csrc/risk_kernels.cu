@@ -244,6 +244,8 @@ constexpr int VS_PG = VS_CWARPS * 64;        // portfolios per CTA
 constexpr int VS_ST = 32;                    // trials per stage
 constexpr int VS_NSTAGE = 4;
 constexpr int VS_F = 32;
+constexpr int VS_EROW = 272;             // padded exposure row in shared memory (bytes)
+constexpr size_t VS_SMEM = sizeof(double) * VS_NSTAGE * VS_ST * VS_F + (size_t)VS_CWARPS * 64 * VS_EROW;
 
 struct StreamArgs {
     const double *E, *S;
@@ -251,8 +253,7 @@ struct StreamArgs {
     int64_t n_begin, n_end;  // trial range of this step
     int nsub;                // sub-chunks (gridDim.x)
     int sub_len;             // trials per sub-chunk (multiple of 8)
-    const double *ntau;      // [P] candidate iff V <= ntau (SPARSE)
-    const uint32_t *thr_hi;  // [P] order-preserving image of ntau's high word
+    const uint64_t *tkey;    // [P] candidate iff fkey(V) <= tkey, i.e. V <= -(current VaR lower bound)  (SPARSE)
     double *candV;           // [p - p0][stride]
     int32_t *candI;          // [p - p0][stride]   (SPARSE)
     int64_t stride;
@@ -290,16 +291,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ uint32_t hi_image(double x)
+// order-preserving image of a double (larger value -> larger key)
+__device__ __forceinline__ uint64_t fkey(double x)
 {
-    const int hi = __double2hiint(x);
-    return (uint32_t)hi ^ ((uint32_t)(hi >> 31) | 0x80000000u);
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double fkey_inv(uint64_t k)
+{
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// branch-free conditional append of one candidate (value, trial) to a lane-private segment
+__device__ __forceinline__ void append_if(uint32_t hit, double *pv, double v, int32_t *pi, int32_t n)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.f64 [%1], %2;\n\t@p st.global.s32 [%3], %4;\n\t}" ::"r"(hit),
+                 "l"(pv), "d"(v), "l"(pi), "r"(n) : "memory");
 }
 
 template <bool DENSE>
 __global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamArgs a)
 {
-    __shared__ __align__(128) double s_S[VS_NSTAGE][VS_ST * VS_F];
+    extern __shared__ __align__(128) unsigned char vs_smem[];
+    double (*s_S)[VS_ST * VS_F] = reinterpret_cast<double (*)[VS_ST * VS_F]>(vs_smem);
+    unsigned char *s_E = vs_smem + sizeof(double) * VS_NSTAGE * VS_ST * VS_F; // per-warp exposure staging, padded rows
     __shared__ __align__(8) uint64_t s_full[VS_NSTAGE], s_empty[VS_NSTAGE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = blockIdx.x;
@@ -330,11 +346,25 @@ __global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamAr
     const bool okA = pA < a.p1, okB = pB < a.p1;
     double e0[VS_F], e1[VS_F];
     {
-        const double2 *ra = reinterpret_cast<const double2 *>(a.E + (okA ? pA : a.p0) * VS_F);
-        const double2 *rb = reinterpret_cast<const double2 *>(a.E + (okB ? pB : a.p0) * VS_F);
+        // The warp's 64 exposure rows are contiguous in global memory (16 KB): load them coalesced, park them in
+        // shared memory with 272-byte rows (conflict-free for the per-lane row reads below), then each lane pulls
+        // its two rows into registers.
+        unsigned char *we = s_E + warp * (64 * VS_EROW);
+        const int64_t prow0 = a.p0 + (int64_t)blockIdx.y * VS_PG + warp * 64;
+        const double2 *g = reinterpret_cast<const double2 *>(a.E + prow0 * VS_F);
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int chunk = i * 32 + lane, r = chunk >> 4, c = chunk & 15;
+            double2 v = make_double2(0.0, 0.0);
+            if (prow0 + r < a.p1) v = __ldg(g + chunk);
+            *reinterpret_cast<double2 *>(we + r * VS_EROW + c * 16) = v;
+        }
+        __syncwarp();
+        const double2 *ra = reinterpret_cast<const double2 *>(we + lane * VS_EROW);
+        const double2 *rb = reinterpret_cast<const double2 *>(we + (lane + 32) * VS_EROW);
 #pragma unroll
         for (int k = 0; k < VS_F; k += 2) {
-            const double2 x = __ldg(ra + (k >> 1)), y = __ldg(rb + (k >> 1));
+            const double2 x = ra[k >> 1], y = rb[k >> 1];
             e0[k] = x.x; e0[k + 1] = x.y; e1[k] = y.x; e1[k + 1] = y.y;
         }
     }
@@ -346,11 +376,10 @@ __global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamAr
         c0 = fma(e0[k], s, c0);
         c1 = fma(e1[k], s, c1);
     }
-    double ntau0 = 0.0, ntau1 = 0.0;
-    uint32_t thr0 = 0, thr1 = 0;
+    uint64_t tk0 = 0, tk1 = 0; // fkey(x) <= 0 never holds for a finite x: inactive lanes never append
     if (!DENSE) {
-        if (okA) { ntau0 = a.ntau[pA]; thr0 = a.thr_hi[pA]; }
-        if (okB) { ntau1 = a.ntau[pB]; thr1 = a.thr_hi[pB]; }
+        if (okA) tk0 = a.tkey[pA];
+        if (okB) tk1 = a.tkey[pB];
     }
     const int64_t rowA = (pA - a.p0) * a.stride + (int64_t)sub * a.sub_len;
     const int64_t rowB = (pB - a.p0) * a.stride + (int64_t)sub * a.sub_len;
@@ -408,16 +437,14 @@ __global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamAr
                     s1a += da; s2a = fma(da, da, s2a);
                     s1b += db; s2b = fma(db, db, s2b);
                     if (!DENSE) {
-                        if (hi_image(a0[j]) <= thr0 && okA && a0[j] <= ntau0) {
-                            a.candV[rowA + cntA] = a0[j];
-                            a.candI[rowA + cntA] = (int32_t)(nb + tl + j);
-                            ++cntA;
-                        }
-                        if (hi_image(a1[j]) <= thr1 && okB && a1[j] <= ntau1) {
-                            a.candV[rowB + cntB] = a1[j];
-                            a.candI[rowB + cntB] = (int32_t)(nb + tl + j);
-                            ++cntB;
-                        }
+                        // integer compare on the order-preserving images (keeps the FP64 pipe for the fma chains);
+                        // predicated stores, no divergence
+                        const uint32_t ha = fkey(a0[j]) <= tk0, hb = fkey(a1[j]) <= tk1;
+                        const int32_t n = (int32_t)(nb + tl + j);
+                        append_if(ha, a.candV + rowA + cntA, a0[j], a.candI + rowA + cntA, n);
+                        append_if(hb, a.candV + rowB + cntB, a1[j], a.candI + rowB + cntB, n);
+                        cntA += ha;
+                        cntB += hb;
                     }
                 }
             }
@@ -468,18 +495,6 @@ __global__ void __launch_bounds__(256) k_moments_finalize(const double *E, const
 }
 
 // ============================================================ selection
-// order-preserving image of a double (larger value -> larger key)
-__device__ __forceinline__ uint64_t fkey(double x)
-{
-    const uint64_t b = (uint64_t)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double fkey_inv(uint64_t k)
-{
-    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
-
 typedef unsigned __int128 u128;
 __device__ __forceinline__ u128 comp_of(uint64_t key, uint32_t idx) { return ((u128)key << 32) | idx; }
 
@@ -510,8 +525,7 @@ struct SelArgs {
     double *mean, *variance;   // [rows] (moments_n > 0)
     double *var_loss;          // [rows]
     int32_t *var_trial;
-    double *ntau;              // [rows] 0.0 - var_loss, for the next step's filter
-    uint32_t *thr_hi;
+    uint64_t *tkey;            // [rows] fkey(0.0 - var_loss): the next step's filter bound on V
     int cap;                   // shared-memory candidate capacity (entries)
 };
 
@@ -727,11 +741,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         const double vl = fkey_inv(ckey[need - 1]);
         a.var_loss[row] = vl;
         a.var_trial[row] = (int32_t)cidx[need - 1];
-        if (a.ntau) {
-            const double nt = 0.0 - vl; // canonical +0.0 for a zero loss
-            a.ntau[row] = nt;
-            a.thr_hi[row] = hi_image(nt);
-        }
+        if (a.tkey) a.tkey[row] = fkey(0.0 - vl); // canonical +0.0 for a zero loss, so V = -0.0 and +0.0 both pass
     }
 }
 
@@ -845,6 +855,7 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
 }
 
 struct Step { int64_t begin, end; int nsub; int sub_len; };
+constexpr int64_t kItemTrials = 512; // target trials per CTA work item (amortises the exposure-tile prologue)
 
 // Trial schedule of the streaming path: a dense first step of ~4 tail sizes establishes each
 // portfolio's threshold, then steps double in length; every later step inserts ~tail candidates.
@@ -858,7 +869,7 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
         int64_t e = b + len;
         if (e > N || (b > 0 && N - e < len / 4)) e = N; // fold a short remainder into the last (sparse) step
         const int64_t L = e - b;
-        int64_t waves = (L * nsg + (int64_t)sms * 64) / ((int64_t)sms * 128);
+        int64_t waves = (L * nsg + (int64_t)sms * kItemTrials / 2) / ((int64_t)sms * kItemTrials);
         if (waves < 1) waves = 1;
         int64_t nsub = (sms * waves) / nsg;
         if (nsub < 1) nsub = 1;
@@ -971,12 +982,13 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
     MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * sizeof(double)));
     MCP_CUDA(ctx, ctx->dCandIdx.reserve((size_t)Pt * stride * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * sizeof(int32_t)));
-    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * (sizeof(double) + sizeof(uint32_t))));
+    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * sizeof(uint64_t)));
+    MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_stream32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM));
+    MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_stream32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM));
     MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
     MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
-    double *ntau = ctx->dTau.as<double>();
-    uint32_t *thr = reinterpret_cast<uint32_t *>(ntau + P);
+    uint64_t *tkey = ctx->dTau.as<uint64_t>();
 
     for (int64_t p0 = 0; p0 < P; p0 += Pt) {
         const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
@@ -993,7 +1005,7 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             v.p0 = p0; v.p1 = p1;
             v.n_begin = s.begin; v.n_end = s.end;
             v.nsub = s.nsub; v.sub_len = s.sub_len;
-            v.ntau = ntau; v.thr_hi = thr;
+            v.tkey = tkey;
             v.candV = ctx->dCandKey.as<double>();
             v.candI = ctx->dCandIdx.as<int32_t>();
             v.stride = stride;
@@ -1003,8 +1015,8 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VS_PG - 1) / VS_PG));
             {
                 KScope ks(ctx, MCP_K_VALUE);
-                if (dense) k_value_stream32<true><<<grid, VS_THREADS, 0, ctx->stream>>>(v);
-                else k_value_stream32<false><<<grid, VS_THREADS, 0, ctx->stream>>>(v);
+                if (dense) k_value_stream32<true><<<grid, VS_THREADS, VS_SMEM, ctx->stream>>>(v);
+                else k_value_stream32<false><<<grid, VS_THREADS, VS_SMEM, ctx->stream>>>(v);
                 MCP_TRY(check_launch(ctx, "k_value_stream32"));
             }
             SelArgs a{};
@@ -1025,8 +1037,7 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             a.moments_n = 0;
             a.var_loss = ctx->dVarLoss.as<double>() + p0;
             a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
-            a.ntau = ntau + p0;
-            a.thr_hi = thr + p0;
+            a.tkey = tkey + p0;
             {
                 KScope ks(ctx, MCP_K_SELECT);
                 a.cap = ctx->selCap;
