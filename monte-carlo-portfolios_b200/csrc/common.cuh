@@ -88,6 +88,8 @@ struct mcp_ctx {
     mcp::DevBuf dKept2Key, dKept2Idx, dFinKey, dFinIdx;
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
     int selCap = 2304;
+    uint32_t mmaConfigured = 0;
+    bool valueMma = true;          // mcp_value through the tensor-core kernel when F allows (else scalar fma)
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)
 

@@ -139,6 +139,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     if (!ctx || !key) return MCP_E_ARG;
     if (!strcmp(key, "force_dense")) ctx->forceDense = value != 0;
     else if (!strcmp(key, "force_sort_finalize")) ctx->forceSortFinalize = value != 0;
+    else if (!strcmp(key, "value_mma")) ctx->valueMma = value != 0;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
 }

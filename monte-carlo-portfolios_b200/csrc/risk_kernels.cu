@@ -224,28 +224,33 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
     }
 }
 
-// ============================================================ valuation, F = 32, streaming
-// Kernel (1)+(2a)+(3a) fused for the headline shape.  "E-stationary": every lane keeps the
-// exposure rows of TWO portfolios in registers (2 x 32 doubles) and streams trials past them;
-// a warp therefore owns 64 portfolios, a CTA (8 consumer warps) 512.  The scenario rows of a
-// trial sub-chunk are staged into shared memory by ONE elected producer thread with
-// cp.async.bulk (TMA bulk copy, mbarrier complete_tx), 4 stages of 32 trials (8 KB each), and
-// read back as warp-broadcast LDS.128 (one load feeds 4 DFMAs).  Per (portfolio, trial) the
-// accumulator is a single fma chain over k ascending -> bit-identical to the oracle.
-// Fused on the value while it is still in a register:
+// ============================================================ valuation, streaming, FP64 tensor cores
+// Kernels (1)+(2a)+(3a) fused, for factor counts F = 4*NK in {16, 32, 48, 64}.
+//
+// The contraction V = E x S^T runs on the FP64 tensor-core path: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4),
+// 8 portfolios x 8 trials x 4 factors per instruction.  On B200 its result is BIT-IDENTICAL to the
+// k-ascending chain of IEEE fma that DESIGN.md 3.1 specifies (profiles/microbench/dmma_probe.cu: 0
+// mismatches in 128 000 outputs on inputs spanning 2^-20..2^20; the parity tests re-check it on every run),
+// it peaks at 37.1 TFLOP/s here against 34.0 for scalar DFMA, and -- the reason it wins -- it needs one
+// shared-memory operand fetch per 256 fma instead of one per 64: the scalar DFMA version of this kernel
+// (git history) was shared-memory-bandwidth bound at 48 % of the FP64 peak.  (tcgen05 has no FP64 kind.)
+//
+// "E-stationary": a warp keeps the A fragments of 4 portfolio groups (32 portfolios x all F factors) in
+// registers and streams trials past them; a CTA = 8 warps = 256 portfolios.  The scenario rows of the
+// CTA's trial sub-chunk are staged into shared memory by one elected thread with cp.async.bulk (TMA bulk
+// copy, SASS UBLKCP) completing on mbarriers, 4 stages x 32 trials, rows padded by 32 B so that the B-fragment
+// loads are bank-conflict free.  Fused on each value while it is still in a register:
 //   * moments: d = V - c_p (c_p = V[p][trial 0]), s1 += d, s2 = fma(d,d,s2)
 //   * tail filter: DENSE steps store every V; SPARSE steps append (V, trial) only when
-//     V <= ntau_p, i.e. loss >= the current lower bound of the portfolio's VaR, pre-screened
-//     with an integer compare on the order-preserving image of the high word.
-// Each lane appends to its own private segment (portfolio, sub-chunk): no atomics.
-constexpr int VS_CWARPS = 8;                 // consumer warps
-constexpr int VS_THREADS = VS_CWARPS * 32;
-constexpr int VS_PG = VS_CWARPS * 64;        // portfolios per CTA
-constexpr int VS_ST = 32;                    // trials per stage
-constexpr int VS_NSTAGE = 4;
-constexpr int VS_F = 32;
-constexpr int VS_EROW = 272;             // padded exposure row in shared memory (bytes)
-constexpr size_t VS_SMEM = sizeof(double) * VS_NSTAGE * VS_ST * VS_F + (size_t)VS_CWARPS * 64 * VS_EROW;
+//     fkey(V) <= tkey_p, i.e. loss >= the current lower bound of the portfolio's VaR: a 64-bit integer
+//     compare on the order-preserving image, and predicated stores -- no divergence, no FP64-pipe slots.
+// Each lane appends to its own private segment (portfolio, sub-chunk, lane%4): no atomics.
+constexpr int VM_WARPS = 8;
+constexpr int VM_THREADS = VM_WARPS * 32;
+constexpr int VM_G = 4;                      // portfolio groups (of 8) per warp
+constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 256
+constexpr int VM_ST = 32;                    // trials per stage
+constexpr int VM_NSTAGE = 4;
 
 struct StreamArgs {
     const double *E, *S;
@@ -257,8 +262,8 @@ struct StreamArgs {
     double *candV;           // [p - p0][stride]
     int32_t *candI;          // [p - p0][stride]   (SPARSE)
     int64_t stride;
-    int32_t *cnt;            // [p - p0][nsub]     (SPARSE)
-    double *part;            // [P][part_stride][2]
+    int32_t *cnt;            // [p - p0][4*nsub]   (SPARSE)
+    double *part;            // [P][part_stride][2]; null = no moments (mcp_value)
     int part_stride, part_base;
 };
 
@@ -291,6 +296,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// D(8x8) += A(8x4) * B(4x8), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // order-preserving image of a double (larger value -> larger key)
 __device__ __forceinline__ uint64_t fkey(double x)
 {
@@ -310,158 +321,156 @@ __device__ __forceinline__ void append_if(uint32_t hit, double *pv, double v, in
                  "l"(pv), "d"(v), "l"(pi), "r"(n) : "memory");
 }
 
-template <bool DENSE>
-__global__ void __launch_bounds__(VS_THREADS, 1) k_value_stream32(const StreamArgs a)
+template <int NK>
+constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * VM_ST * (NK * 4 + 4); }
+
+template <int NK, bool DENSE>
+__global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 {
-    extern __shared__ __align__(128) unsigned char vs_smem[];
-    double (*s_S)[VS_ST * VS_F] = reinterpret_cast<double (*)[VS_ST * VS_F]>(vs_smem);
-    unsigned char *s_E = vs_smem + sizeof(double) * VS_NSTAGE * VS_ST * VS_F; // per-warp exposure staging, padded rows
-    __shared__ __align__(8) uint64_t s_full[VS_NSTAGE], s_empty[VS_NSTAGE];
+    constexpr int F = NK * 4;
+    constexpr int RS = F + 4; // padded row (doubles): stride = 8 banks mod 32 for F % 16 == 0 -> conflict-free fragments
+    extern __shared__ __align__(128) unsigned char vm_smem[];
+    double *s_S = reinterpret_cast<double *>(vm_smem); // [NSTAGE][ST][RS]
+    __shared__ __align__(8) uint64_t s_full[VM_NSTAGE], s_empty[VM_NSTAGE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane >> 2, c = lane & 3;
     const int sub = blockIdx.x;
     const int64_t nb = a.n_begin + (int64_t)sub * a.sub_len;
     const int64_t ne = min(a.n_end, nb + a.sub_len);
     const int ntr = (int)(ne - nb);
-    const int nst = (ntr + VS_ST - 1) / VS_ST;
+    const int nst = (ntr + VM_ST - 1) / VM_ST;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < VS_NSTAGE; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], VS_CWARPS); }
+        for (int s = 0; s < VM_NSTAGE; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], VM_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // Producer duty: lane 0 of warp 0 keeps the stage ring full (prefetch distance NSTAGE-1 stages).  A 9th,
-    // dedicated producer warp would put three warps on one SM sub-partition and cap every thread at 168
-    // registers (spills); eight warps leave 255.
+    // Producer duty: thread 0 keeps the stage ring full (prefetch distance NSTAGE-1 stages); one bulk copy per
+    // scenario row because the rows are padded in shared memory.
     auto produce = [&](int it) {
-        const int st = it % VS_NSTAGE;
-        if (it >= VS_NSTAGE) mbar_wait(&s_empty[st], ((it / VS_NSTAGE) - 1) & 1);
-        const int rows = min(VS_ST, ntr - it * VS_ST);
-        const uint32_t bytes = (uint32_t)rows * VS_F * sizeof(double);
-        mbar_expect_tx(&s_full[st], bytes);
-        bulk_g2s(&s_S[st][0], a.S + (nb + (int64_t)it * VS_ST) * VS_F, bytes, &s_full[st]);
+        const int st = it % VM_NSTAGE;
+        if (it >= VM_NSTAGE) mbar_wait(&s_empty[st], ((it / VM_NSTAGE) - 1) & 1);
+        const int rows = min(VM_ST, ntr - it * VM_ST);
+        mbar_expect_tx(&s_full[st], (uint32_t)rows * F * sizeof(double));
+        const double *src = a.S + (nb + (int64_t)it * VM_ST) * F;
+        double *dst = s_S + (size_t)st * VM_ST * RS;
+        for (int q = 0; q < rows; ++q) bulk_g2s(dst + q * RS, src + (size_t)q * F, F * sizeof(double), &s_full[st]);
     };
     if (threadIdx.x == 0)
-        for (int it = 0; it < VS_NSTAGE - 1 && it < nst; ++it) produce(it);
-    // ===== consumers
-    const int64_t pA = a.p0 + (int64_t)blockIdx.y * VS_PG + warp * 64 + lane, pB = pA + 32;
-    const bool okA = pA < a.p1, okB = pB < a.p1;
-    double e0[VS_F], e1[VS_F];
-    {
-        // The warp's 64 exposure rows are contiguous in global memory (16 KB): load them coalesced, park them in
-        // shared memory with 272-byte rows (conflict-free for the per-lane row reads below), then each lane pulls
-        // its two rows into registers.
-        unsigned char *we = s_E + warp * (64 * VS_EROW);
-        const int64_t prow0 = a.p0 + (int64_t)blockIdx.y * VS_PG + warp * 64;
-        const double2 *g = reinterpret_cast<const double2 *>(a.E + prow0 * VS_F);
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const int chunk = i * 32 + lane, r = chunk >> 4, c = chunk & 15;
-            double2 v = make_double2(0.0, 0.0);
-            if (prow0 + r < a.p1) v = __ldg(g + chunk);
-            *reinterpret_cast<double2 *>(we + r * VS_EROW + c * 16) = v;
-        }
-        __syncwarp();
-        const double2 *ra = reinterpret_cast<const double2 *>(we + lane * VS_EROW);
-        const double2 *rb = reinterpret_cast<const double2 *>(we + (lane + 32) * VS_EROW);
+        for (int it = 0; it < VM_NSTAGE - 1 && it < nst; ++it) produce(it);
+
+    // ---- A fragments: this warp's 4 groups x 8 portfolios, all factors, resident in registers
+    const int64_t pw = a.p0 + (int64_t)blockIdx.y * VM_PG + warp * (VM_G * 8);
+    double ef[VM_G][NK];
+    bool ok[VM_G];
+    int64_t prow[VM_G];
 #pragma unroll
-        for (int k = 0; k < VS_F; k += 2) {
-            const double2 x = ra[k >> 1], y = rb[k >> 1];
-            e0[k] = x.x; e0[k + 1] = x.y; e1[k] = y.x; e1[k + 1] = y.y;
-        }
-    }
-    // shift c_p = V[p][0]  (same fma chain as any other valuation)
-    double c0 = 0.0, c1 = 0.0;
+    for (int g = 0; g < VM_G; ++g) {
+        const int64_t p = pw + g * 8 + r;
+        ok[g] = p < a.p1;
+        prow[g] = p;
+        const double *er = a.E + (ok[g] ? p : a.p0) * F + c;
 #pragma unroll
-    for (int k = 0; k < VS_F; ++k) {
-        const double s = __ldg(a.S + k);
-        c0 = fma(e0[k], s, c0);
-        c1 = fma(e1[k], s, c1);
+        for (int s = 0; s < NK; ++s) ef[g][s] = __ldg(er + 4 * s);
     }
-    uint64_t tk0 = 0, tk1 = 0; // fkey(x) <= 0 never holds for a finite x: inactive lanes never append
-    if (!DENSE) {
-        if (okA) tk0 = a.tkey[pA];
-        if (okB) tk1 = a.tkey[pB];
+    // ---- shift c_p = V[p][trial 0]: one DMMA pass over scenario rows 0..7, column 0 broadcast to the row's 4 lanes
+    double cs[VM_G];
+    if (a.part) {
+        double z0[VM_G], z1[VM_G];
+#pragma unroll
+        for (int g = 0; g < VM_G; ++g) { z0[g] = 0.0; z1[g] = 0.0; }
+        const int64_t Ntot = a.n_end; // rows 0..7 exist whenever N >= 8; clamp otherwise
+#pragma unroll
+        for (int s = 0; s < NK; ++s) {
+            const double b = __ldg(a.S + (int64_t)min((int64_t)r, Ntot - 1) * F + 4 * s + c);
+#pragma unroll
+            for (int g = 0; g < VM_G; ++g) dmma884(z0[g], z1[g], ef[g][s], b);
+        }
+#pragma unroll
+        for (int g = 0; g < VM_G; ++g) cs[g] = __shfl_sync(0xffffffffu, z0[g], lane & ~3);
+    } else {
+#pragma unroll
+        for (int g = 0; g < VM_G; ++g) cs[g] = 0.0;
     }
-    const int64_t rowA = (pA - a.p0) * a.stride + (int64_t)sub * a.sub_len;
-    const int64_t rowB = (pB - a.p0) * a.stride + (int64_t)sub * a.sub_len;
-    double s1a = 0.0, s2a = 0.0, s1b = 0.0, s2b = 0.0;
-    int cntA = 0, cntB = 0;
+    uint64_t tk[VM_G];
+    int cnt[VM_G];
+    double s1[VM_G], s2[VM_G];
+    int64_t seg[VM_G]; // this lane's private segment (SPARSE) or the row base (DENSE)
+#pragma unroll
+    for (int g = 0; g < VM_G; ++g) {
+        tk[g] = 0; // fkey(x) <= 0 never holds for a finite x: inactive rows never append
+        if (!DENSE && ok[g]) tk[g] = a.tkey[prow[g]];
+        cnt[g] = 0;
+        s1[g] = 0.0;
+        s2[g] = 0.0;
+        const int64_t rowbase = (prow[g] - a.p0) * a.stride + (int64_t)sub * a.sub_len;
+        seg[g] = DENSE ? rowbase : rowbase + (int64_t)c * (a.sub_len >> 2);
+    }
+    const bool vec_ok = (a.stride & 1) == 0 && (a.sub_len & 1) == 0;
 
     for (int it = 0; it < nst; ++it) {
-        const int st = it % VS_NSTAGE;
-        if (threadIdx.x == 0 && it + VS_NSTAGE - 1 < nst) produce(it + VS_NSTAGE - 1);
+        const int st = it % VM_NSTAGE;
+        if (threadIdx.x == 0 && it + VM_NSTAGE - 1 < nst) produce(it + VM_NSTAGE - 1);
         __syncwarp();
-        mbar_wait(&s_full[st], (it / VS_NSTAGE) & 1);
-        const int rows = min(VS_ST, ntr - it * VS_ST);
-        const double *sbase = &s_S[st][0];
-        for (int tg = 0; tg * 4 < rows; ++tg) {
-            const double *srow = sbase + tg * 4 * VS_F;
-            double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+        mbar_wait(&s_full[st], (it / VM_NSTAGE) & 1);
+        const int rows = min(VM_ST, ntr - it * VM_ST);
+        const double *sbase = s_S + (size_t)st * VM_ST * RS;
+#pragma unroll 1
+        for (int blk = 0; blk * 8 < rows; ++blk) {
+            const double *bp = sbase + (blk * 8 + r) * RS + c;
+            double sf[NK];
 #pragma unroll
-            for (int k = 0; k < VS_F; k += 2) {
+            for (int s = 0; s < NK; ++s) sf[s] = bp[4 * s];
+            double d0[VM_G], d1[VM_G];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 s = *reinterpret_cast<const double2 *>(srow + j * VS_F + k); // warp-broadcast LDS.128
-                    a0[j] = fma(e0[k], s.x, a0[j]);
-                    a1[j] = fma(e1[k], s.x, a1[j]);
-                    a0[j] = fma(e0[k + 1], s.y, a0[j]);
-                    a1[j] = fma(e1[k + 1], s.y, a1[j]);
+            for (int g = 0; g < VM_G; ++g) { d0[g] = 0.0; d1[g] = 0.0; }
+#pragma unroll
+            for (int s = 0; s < NK; ++s)
+#pragma unroll
+                for (int g = 0; g < VM_G; ++g) dmma884(d0[g], d1[g], ef[g][s], sf[s]);
+            const int tl = it * VM_ST + blk * 8 + 2 * c; // offset of this lane's first trial inside the sub-chunk
+            const bool v0 = tl < ntr, v1 = tl + 1 < ntr;
+            const int32_t n0 = (int32_t)(nb + tl);
+#pragma unroll
+            for (int g = 0; g < VM_G; ++g) {
+                if (a.part) {
+                    const double da = d0[g] - cs[g], db = d1[g] - cs[g];
+                    if (v0) { s1[g] += da; s2[g] = fma(da, da, s2[g]); }
+                    if (v1) { s1[g] += db; s2[g] = fma(db, db, s2[g]); }
                 }
-            }
-            const int tl = it * VS_ST + tg * 4; // trial offset inside the sub-chunk
-            const int valid = min(4, rows - tg * 4);
-            if (DENSE) {
-                if (valid == 4) {
-                    if (okA) {
-                        double2 *d = reinterpret_cast<double2 *>(a.candV + rowA + tl);
-                        d[0] = make_double2(a0[0], a0[1]);
-                        d[1] = make_double2(a0[2], a0[3]);
-                    }
-                    if (okB) {
-                        double2 *d = reinterpret_cast<double2 *>(a.candV + rowB + tl);
-                        d[0] = make_double2(a1[0], a1[1]);
-                        d[1] = make_double2(a1[2], a1[3]);
+                if (DENSE) {
+                    if (ok[g]) {
+                        double *dst = a.candV + seg[g] + tl;
+                        if (v1 && vec_ok) *reinterpret_cast<double2 *>(dst) = make_double2(d0[g], d1[g]);
+                        else {
+                            if (v0) dst[0] = d0[g];
+                            if (v1) dst[1] = d1[g];
+                        }
                     }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (j < valid) {
-                            if (okA) a.candV[rowA + tl + j] = a0[j];
-                            if (okB) a.candV[rowB + tl + j] = a1[j];
-                        }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < valid) {
-                    const double da = a0[j] - c0, db = a1[j] - c1;
-                    s1a += da; s2a = fma(da, da, s2a);
-                    s1b += db; s2b = fma(db, db, s2b);
-                    if (!DENSE) {
-                        // integer compare on the order-preserving images (keeps the FP64 pipe for the fma chains);
-                        // predicated stores, no divergence
-                        const uint32_t ha = fkey(a0[j]) <= tk0, hb = fkey(a1[j]) <= tk1;
-                        const int32_t n = (int32_t)(nb + tl + j);
-                        append_if(ha, a.candV + rowA + cntA, a0[j], a.candI + rowA + cntA, n);
-                        append_if(hb, a.candV + rowB + cntB, a1[j], a.candI + rowB + cntB, n);
-                        cntA += ha;
-                        cntB += hb;
-                    }
+                    const uint32_t h0 = (fkey(d0[g]) <= tk[g]) && v0, h1 = (fkey(d1[g]) <= tk[g]) && v1;
+                    append_if(h0, a.candV + seg[g] + cnt[g], d0[g], a.candI + seg[g] + cnt[g], n0);
+                    cnt[g] += h0;
+                    append_if(h1, a.candV + seg[g] + cnt[g], d1[g], a.candI + seg[g] + cnt[g], n0 + 1);
+                    cnt[g] += h1;
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
     }
-    const int slot = a.part_base + sub;
-    if (okA) {
-        double *q = a.part + ((int64_t)pA * a.part_stride + slot) * 2;
-        q[0] = s1a; q[1] = s2a;
-        if (!DENSE) a.cnt[(pA - a.p0) * a.nsub + sub] = cntA;
-    }
-    if (okB) {
-        double *q = a.part + ((int64_t)pB * a.part_stride + slot) * 2;
-        q[0] = s1b; q[1] = s2b;
-        if (!DENSE) a.cnt[(pB - a.p0) * a.nsub + sub] = cntB;
+    // ---- epilogue: per-portfolio partial moments (fixed 4-lane tree: deterministic) and segment counts
+#pragma unroll
+    for (int g = 0; g < VM_G; ++g) {
+        if (a.part) {
+            double x = s1[g], y = s2[g];
+            x += __shfl_xor_sync(0xffffffffu, x, 1); y += __shfl_xor_sync(0xffffffffu, y, 1);
+            x += __shfl_xor_sync(0xffffffffu, x, 2); y += __shfl_xor_sync(0xffffffffu, y, 2);
+            if (c == 0 && ok[g]) {
+                double *q = a.part + ((int64_t)prow[g] * a.part_stride + a.part_base + sub) * 2;
+                q[0] = x; q[1] = y;
+            }
+        }
+        if (!DENSE && ok[g]) a.cnt[(prow[g] - a.p0) * (4 * (int64_t)a.nsub) + 4 * sub + c] = cnt[g];
     }
 }
 
@@ -845,15 +854,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
 }
 
 // ============================================================ host orchestration
-int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
-{
-    if (p1 <= p0) return MCP_OK;
-    dim3 grid((unsigned)((ctx->N + VT - 1) / VT), (unsigned)((p1 - p0 + VT - 1) / VT));
-    KScope ks(ctx, MCP_K_VALUE);
-    k_value_generic<<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), p0, p1, ctx->N, ctx->F, d_V);
-    return check_launch(ctx, "k_value_generic");
-}
-
 struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kItemTrials = 512; // target trials per CTA work item (amortises the exposure-tile prologue)
 
@@ -910,6 +910,8 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
     return check_launch(ctx, "k_finalize");
 }
 
+int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V);
+
 // generic factor count: dense V tile + one selection pass per portfolio
 static int risk_run_dense(mcp_ctx *ctx, int64_t t)
 {
@@ -952,8 +954,58 @@ static int risk_run_dense(mcp_ctx *ctx, int64_t t)
     return MCP_OK;
 }
 
-// F = 32: streaming valuation + threshold filter + incremental radix-select
-static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
+template <int NK>
+static int launch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 grid)
+{
+    const bool configured = (ctx->mmaConfigured >> NK) & 1u; // per context: the attribute is per device
+    if (!configured) {
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<NK>()));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<NK>()));
+        ctx->mmaConfigured |= 1u << NK;
+    }
+    KScope ks(ctx, MCP_K_VALUE);
+    if (dense) k_value_mma<NK, true><<<grid, VM_THREADS, vm_smem_bytes<NK>(), ctx->stream>>>(v);
+    else k_value_mma<NK, false><<<grid, VM_THREADS, vm_smem_bytes<NK>(), ctx->stream>>>(v);
+    return check_launch(ctx, "k_value_mma");
+}
+
+static bool mma_supported(int32_t F) { return F == 16 || F == 32 || F == 48 || F == 64; }
+
+static int dispatch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 grid)
+{
+    switch (ctx->F) {
+    case 16: return launch_value_mma<4>(ctx, v, dense, grid);
+    case 32: return launch_value_mma<8>(ctx, v, dense, grid);
+    case 48: return launch_value_mma<12>(ctx, v, dense, grid);
+    case 64: return launch_value_mma<16>(ctx, v, dense, grid);
+    }
+    return fail(ctx, MCP_E_UNSUPPORTED, "no tensor-core valuation kernel for this factor count");
+}
+
+int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
+{
+    if (p1 <= p0) return MCP_OK;
+    if (ctx->valueMma && mma_supported(ctx->F)) {
+        // the streaming kernel in DENSE mode writes V itself: [p - p0][N]
+        const int64_t nsg = (p1 - p0 + VM_PG - 1) / VM_PG;
+        std::vector<Step> st = make_schedule(ctx->N, ctx->N, nsg, ctx->prop.multiProcessorCount); // one step: [0, N)
+        StreamArgs v{};
+        v.E = ctx->dE.as<double>(); v.S = ctx->dS.as<double>();
+        v.p0 = p0; v.p1 = p1;
+        v.n_begin = 0; v.n_end = ctx->N;
+        v.nsub = st[0].nsub; v.sub_len = st[0].sub_len;
+        v.candV = d_V; v.stride = ctx->N;
+        dim3 grid((unsigned)v.nsub, (unsigned)nsg);
+        return dispatch_value_mma(ctx, v, true, grid);
+    }
+    dim3 grid((unsigned)((ctx->N + VT - 1) / VT), (unsigned)((p1 - p0 + VT - 1) / VT));
+    KScope ks(ctx, MCP_K_VALUE);
+    k_value_generic<<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), p0, p1, ctx->N, ctx->F, d_V);
+    return check_launch(ctx, "k_value_generic");
+}
+
+// streaming valuation (FP64 tensor cores) + threshold filter + incremental radix-select
+static int risk_run_stream(mcp_ctx *ctx, int64_t t)
 {
     const int64_t P = ctx->P, N = ctx->N;
     const int sms = ctx->prop.multiProcessorCount;
@@ -965,7 +1017,7 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
     int64_t stride = 0;
     int max_nsub = 0, nparts = 0;
     for (;;) {
-        const int64_t nsg = (Pt + VS_PG - 1) / VS_PG;
+        const int64_t nsg = (Pt + VM_PG - 1) / VM_PG;
         steps = make_schedule(N, t, nsg, sms);
         stride = 0; max_nsub = 0; nparts = 0;
         for (auto &s : steps) {
@@ -975,16 +1027,14 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             nparts += s.nsub;
         }
         stride = (stride + 3) & ~(int64_t)3;
-        if ((size_t)Pt * stride * 12 <= budget || Pt <= VS_PG) break;
-        Pt = ((Pt / 2 + VS_PG - 1) / VS_PG) * VS_PG;
+        if ((size_t)Pt * stride * 12 <= budget || Pt <= VM_PG) break;
+        Pt = ((Pt / 2 + VM_PG - 1) / VM_PG) * VM_PG;
     }
-    if (Pt > 65535 * (int64_t)VS_PG) Pt = 65535 * (int64_t)VS_PG;
+    if (Pt > 65535 * (int64_t)VM_PG) Pt = 65535 * (int64_t)VM_PG;
     MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * sizeof(double)));
     MCP_CUDA(ctx, ctx->dCandIdx.reserve((size_t)Pt * stride * sizeof(int32_t)));
-    MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * sizeof(uint64_t)));
-    MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_stream32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM));
-    MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_stream32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM));
     MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
     MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
@@ -1012,20 +1062,16 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
             v.cnt = ctx->dCandCnt.as<int32_t>();
             v.part = ctx->dPart.as<double>();
             v.part_stride = nparts; v.part_base = part_base;
-            dim3 grid((unsigned)s.nsub, (unsigned)((rows + VS_PG - 1) / VS_PG));
-            {
-                KScope ks(ctx, MCP_K_VALUE);
-                if (dense) k_value_stream32<true><<<grid, VS_THREADS, VS_SMEM, ctx->stream>>>(v);
-                else k_value_stream32<false><<<grid, VS_THREADS, VS_SMEM, ctx->stream>>>(v);
-                MCP_TRY(check_launch(ctx, "k_value_stream32"));
-            }
+            dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
+            MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
             SelArgs a{};
             a.candV = v.candV;
             a.candI = dense ? nullptr : v.candI;
             a.stride = stride;
             a.cnt = dense ? nullptr : v.cnt;
-            a.nsub = s.nsub;
-            a.sub_len = s.sub_len;
+            // sparse steps: every sub-chunk holds four lane-private segments of sub_len/4 slots
+            a.nsub = dense ? s.nsub : 4 * s.nsub;
+            a.sub_len = dense ? s.sub_len : s.sub_len / 4;
             a.step_len = s.end - s.begin;
             a.n_begin = s.begin;
             a.kept_key_in = kkey[cur];
@@ -1052,8 +1098,8 @@ static int risk_run_stream32(mcp_ctx *ctx, int64_t t)
     {
         KScope ks(ctx, MCP_K_SELECT);
         k_moments_finalize<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), P, ctx->F, N,
-                                                                                ctx->dPart.as<double>(), nparts, nparts,
-                                                                                ctx->dMean.as<double>(), ctx->dVar.as<double>());
+                                                                            ctx->dPart.as<double>(), nparts, nparts,
+                                                                            ctx->dMean.as<double>(), ctx->dVar.as<double>());
         MCP_TRY(check_launch(ctx, "k_moments_finalize"));
     }
     return MCP_OK;
@@ -1083,7 +1129,7 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
         MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap)));
     }
 
-    if (ctx->F == VS_F && !ctx->forceDense) MCP_TRY(risk_run_stream32(ctx, t));
+    if (mma_supported(ctx->F) && !ctx->forceDense) MCP_TRY(risk_run_stream(ctx, t));
     else MCP_TRY(risk_run_dense(ctx, t));
 
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format

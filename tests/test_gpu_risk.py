@@ -48,6 +48,28 @@ def test_value_bit_identical(ctx, shape):
     assert np.array_equal(V2, V[P // 2:])
 
 
+@pytest.mark.parametrize("F", [16, 32, 48, 64])
+def test_tensor_core_valuation_is_the_fma_chain(ctx, F):
+    """The FP64 tensor-core kernel (mma.sync m8n8k4 / DMMA) must reproduce the k-ascending fma chain bit for bit.
+    Inputs span 40 binades so that any other accumulation order or an unfused multiply would show up."""
+    rng = np.random.default_rng(F)
+    P, Nn = 300, 1203
+    E = (rng.random((P, F)) - 0.5) * np.exp2(rng.integers(-20, 20, (P, F)).astype(np.float64))
+    S = (rng.random((Nn, F)) - 0.5) * np.exp2(rng.integers(-20, 20, (Nn, F)).astype(np.float64))
+    ctx.upload_exposures(E)
+    ctx.upload_scenarios(S)
+    ref = cref.value(E, S).view(np.uint64)
+    ctx.set_option("value_mma", 1)
+    assert np.array_equal(ctx.value(0, P, Nn).view(np.uint64), ref)
+    assert np.array_equal(ctx.value(7, 270, Nn).view(np.uint64), ref[7:270])
+    ctx.set_option("value_mma", 0)
+    try:
+        assert np.array_equal(ctx.value(0, P, Nn).view(np.uint64), ref)   # scalar-fma kernel
+    finally:
+        ctx.set_option("value_mma", 1)
+    check_against_oracle(ctx, E, S, 0.97, rows=[0, 1, 150, 299])
+
+
 @pytest.mark.parametrize("shape", [(10, 10, 10, 0.9), (40, 1000, 32, 0.99), (30, 999, 64, 0.95), (9, 257, 5, 0.5),
                                    (5, 64, 3, 1.0), (12, 20000, 32, 0.99), (3, 100000, 32, 0.99), (2, 50000, 7, 0.6)])
 def test_run_matches_oracle(ctx, shape):
@@ -72,8 +94,9 @@ def test_alternate_kernel_paths_agree(ctx, opt):
 
 def test_streaming_path_many_portfolios_ragged(ctx):
     """F = 32 streaming path with a ragged last portfolio group and trial counts that are not multiples of 4/8/32."""
-    for P, Nn, alpha in ((513, 4099, 0.99), (1030, 2049, 0.9), (70, 33333, 0.999), (3, 7, 0.5), (600, 12345, 0.95)):
-        E, S = riskcases.synthetic(P, Nn, 32, 100 + P)
+    for P, Nn, alpha, F in ((513, 4099, 0.99, 32), (1030, 2049, 0.9, 32), (70, 33333, 0.999, 32), (3, 7, 0.5, 32),
+                            (600, 12345, 0.95, 32), (300, 9001, 0.99, 64), (257, 5003, 0.98, 16), (100, 20011, 0.995, 48)):
+        E, S = riskcases.synthetic(P, Nn, F, 100 + P)
         check_against_oracle(ctx, E, S, alpha, rows=list(range(0, P, max(1, P // 37))) + [P - 1])
 
 
