@@ -64,6 +64,8 @@ struct mcp_ctx {
 
     // ---- risk path state
     mcp::DevBuf dE, dS;            // exposures P x F, scenarios N x F (doubles)
+    mcp::DevBuf dSfrag;            // scenarios in tensor-core B-fragment order (built lazily from dS)
+    bool sfragValid = false;
     int64_t P = 0, N = 0;
     int32_t F = 0;
     bool haveE = false, haveS = false;

@@ -115,7 +115,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
-                           &ctx->dFinKey, &ctx->dFinIdx};
+                           &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -352,7 +352,7 @@ int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F)
     MCP_TRY(set_dev(ctx));
     if (ctx->haveE && ctx->F != F) ctx->haveE = false;
     MCP_TRY(upload_matrix(ctx, ctx->dS, S, N, F));
-    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;
+    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false; ctx->sfragValid = false;
     return MCP_OK;
 }
 
@@ -374,7 +374,7 @@ int mcp_generate_scenarios(mcp_ctx *ctx, int64_t N, int32_t F, uint64_t seed, do
     if (ctx->haveE && ctx->F != F) ctx->haveE = false;
     MCP_CUDA(ctx, ctx->dS.reserve((size_t)N * F * sizeof(double) + 16));
     MCP_TRY(gen_matrix(ctx, ctx->dS.as<double>(), N, F, seed, 2u, scale, shift, row0));
-    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false;
+    ctx->N = N; ctx->F = F; ctx->haveS = true; ctx->haveRun = false; ctx->sfragValid = false;
     return MCP_OK;
 }
 

@@ -254,6 +254,7 @@ constexpr int VM_NSTAGE = 4;
 
 struct StreamArgs {
     const double *E, *S;
+    const double *Sfrag;     // scenarios repacked in B-fragment order: [trial block of 8][k-step][lane] (k_repack_scenarios)
     int64_t p0, p1;          // portfolio tile
     int64_t n_begin, n_end;  // trial range of this step
     int nsub;                // sub-chunks (gridDim.x)
@@ -322,15 +323,34 @@ __device__ __forceinline__ void append_if(uint32_t hit, double *pv, double v, in
 }
 
 template <int NK>
-constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * VM_ST * (NK * 4 + 4); }
+constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * VM_ST * (NK * 4); }
+
+// S[N][F] -> Sfrag[ceil(N/8)][NK][32]: element (b, s, lane) = S[8b + lane/4][4s + lane%4] (0 past the last trial).
+// In this order a stage of 32 trials is one contiguous block (a single TMA bulk copy) and every B-fragment load is
+// 32 consecutive doubles: bank-conflict free without padding.
+__global__ void k_repack_scenarios(const double *__restrict__ S, int64_t N, int NK, double *__restrict__ Sfrag)
+{
+    const int64_t nblk = (N + 7) >> 3;
+    const int64_t total = nblk * NK * 32;
+    const int F = NK * 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int lane = (int)(i & 31);
+        const int64_t bs = i >> 5;
+        const int sidx = (int)(bs % NK);
+        const int64_t b = bs / NK;
+        const int64_t n = 8 * b + (lane >> 2);
+        Sfrag[i] = n < N ? S[n * F + 4 * sidx + (lane & 3)] : 0.0;
+    }
+}
 
 template <int NK, bool DENSE>
 __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 {
     constexpr int F = NK * 4;
-    constexpr int RS = F + 4; // padded row (doubles): stride = 8 banks mod 32 for F % 16 == 0 -> conflict-free fragments
+    constexpr int BLK = NK * 32;            // doubles per 8-trial block in fragment order
+    constexpr int STG = (VM_ST / 8) * BLK;  // doubles per stage
     extern __shared__ __align__(128) unsigned char vm_smem[];
-    double *s_S = reinterpret_cast<double *>(vm_smem); // [NSTAGE][ST][RS]
+    double *s_S = reinterpret_cast<double *>(vm_smem); // [NSTAGE][ST/8][NK][32]
     __shared__ __align__(8) uint64_t s_full[VM_NSTAGE], s_empty[VM_NSTAGE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
@@ -344,16 +364,15 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // Producer duty: thread 0 keeps the stage ring full (prefetch distance NSTAGE-1 stages); one bulk copy per
-    // scenario row because the rows are padded in shared memory.
+    // Producer duty: thread 0 keeps the stage ring full (prefetch distance NSTAGE-1 stages) with ONE bulk copy per
+    // stage: in fragment order the stage's trial blocks are contiguous (nb is a multiple of 8).
     auto produce = [&](int it) {
         const int st = it % VM_NSTAGE;
         if (it >= VM_NSTAGE) mbar_wait(&s_empty[st], ((it / VM_NSTAGE) - 1) & 1);
         const int rows = min(VM_ST, ntr - it * VM_ST);
-        mbar_expect_tx(&s_full[st], (uint32_t)rows * F * sizeof(double));
-        const double *src = a.S + (nb + (int64_t)it * VM_ST) * F;
-        double *dst = s_S + (size_t)st * VM_ST * RS;
-        for (int q = 0; q < rows; ++q) bulk_g2s(dst + q * RS, src + (size_t)q * F, F * sizeof(double), &s_full[st]);
+        const uint32_t bytes = (uint32_t)((rows + 7) >> 3) * BLK * sizeof(double);
+        mbar_expect_tx(&s_full[st], bytes);
+        bulk_g2s(s_S + (size_t)st * STG, a.Sfrag + ((nb >> 3) + (int64_t)it * (VM_ST / 8)) * BLK, bytes, &s_full[st]);
     };
     if (threadIdx.x == 0)
         for (int it = 0; it < VM_NSTAGE - 1 && it < nst; ++it) produce(it);
@@ -413,13 +432,13 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
         __syncwarp();
         mbar_wait(&s_full[st], (it / VM_NSTAGE) & 1);
         const int rows = min(VM_ST, ntr - it * VM_ST);
-        const double *sbase = s_S + (size_t)st * VM_ST * RS;
+        const double *sbase = s_S + (size_t)st * STG;
 #pragma unroll 1
         for (int blk = 0; blk * 8 < rows; ++blk) {
-            const double *bp = sbase + (blk * 8 + r) * RS + c;
+            const double *bp = sbase + blk * BLK + lane;
             double sf[NK];
 #pragma unroll
-            for (int s = 0; s < NK; ++s) sf[s] = bp[4 * s];
+            for (int s = 0; s < NK; ++s) sf[s] = bp[32 * s];
             double d0[VM_G], d1[VM_G];
 #pragma unroll
             for (int g = 0; g < VM_G; ++g) { d0[g] = 0.0; d1[g] = 0.0; }
@@ -565,6 +584,15 @@ __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, F
     for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.tail + i], (uint32_t)a.kept_idx_in[row * a.tail + i]);
     const double *V = a.candV + row * a.stride;
     const int32_t *I = a.candI ? a.candI + row * a.stride : nullptr;
+    if (a.cnt && a.nsub >= 64) {
+        // sparse step: many short lane-private segments -> one thread per segment keeps all their loads in flight
+        for (int seg = tid; seg < a.nsub; seg += SEL_THREADS) {
+            const int64_t base = (int64_t)seg * a.sub_len;
+            const int c = a.cnt[row * a.nsub + seg];
+            for (int i = 0; i < c; ++i) f(fkey(0.0 - V[base + i]), (uint32_t)I[base + i]);
+        }
+        return;
+    }
     for (int seg = warp; seg < a.nsub; seg += SEL_THREADS / 32) {
         const int64_t base = (int64_t)seg * a.sub_len;
         int64_t c;
@@ -864,6 +892,7 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
     std::vector<Step> steps;
     int64_t c0 = 4 * t;
     if (c0 < 2048) c0 = 2048;
+    c0 = (c0 + 7) & ~(int64_t)7; // step boundaries stay multiples of 8 (tensor-core trial blocks)
     int64_t b = 0, len = c0;
     while (b < N) {
         int64_t e = b + len;
@@ -971,6 +1000,20 @@ static int launch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 
 
 static bool mma_supported(int32_t F) { return F == 16 || F == 32 || F == 48 || F == 64; }
 
+// (re)build the fragment-order copy of the scenario matrix when it is stale
+static int ensure_sfrag(mcp_ctx *ctx)
+{
+    if (ctx->sfragValid) return MCP_OK;
+    const int NK = ctx->F / 4;
+    const int64_t nblk = (ctx->N + 7) / 8;
+    MCP_CUDA(ctx, ctx->dSfrag.reserve((size_t)nblk * NK * 32 * sizeof(double) + 16));
+    KScope ks(ctx, MCP_K_GEN);
+    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, NK, ctx->dSfrag.as<double>());
+    MCP_TRY(check_launch(ctx, "k_repack_scenarios"));
+    ctx->sfragValid = true;
+    return MCP_OK;
+}
+
 static int dispatch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 grid)
 {
     switch (ctx->F) {
@@ -989,8 +1032,9 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
         // the streaming kernel in DENSE mode writes V itself: [p - p0][N]
         const int64_t nsg = (p1 - p0 + VM_PG - 1) / VM_PG;
         std::vector<Step> st = make_schedule(ctx->N, ctx->N, nsg, ctx->prop.multiProcessorCount); // one step: [0, N)
+        MCP_TRY(ensure_sfrag(ctx));
         StreamArgs v{};
-        v.E = ctx->dE.as<double>(); v.S = ctx->dS.as<double>();
+        v.E = ctx->dE.as<double>(); v.S = ctx->dS.as<double>(); v.Sfrag = ctx->dSfrag.as<double>();
         v.p0 = p0; v.p1 = p1;
         v.n_begin = 0; v.n_end = ctx->N;
         v.nsub = st[0].nsub; v.sub_len = st[0].sub_len;
@@ -1039,6 +1083,7 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
     MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
     uint64_t *tkey = ctx->dTau.as<uint64_t>();
+    MCP_TRY(ensure_sfrag(ctx));
 
     for (int64_t p0 = 0; p0 < P; p0 += Pt) {
         const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
@@ -1052,6 +1097,7 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             StreamArgs v{};
             v.E = ctx->dE.as<double>();
             v.S = ctx->dS.as<double>();
+            v.Sfrag = ctx->dSfrag.as<double>();
             v.p0 = p0; v.p1 = p1;
             v.n_begin = s.begin; v.n_end = s.end;
             v.nsub = s.nsub; v.sub_len = s.sub_len;
