@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcp.so")
+LIB_PATH = os.environ.get("MCP_LIB_PATH") or os.path.join(_HERE, "libmcp.so")  # override: experiments only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mcp.h")
 
 MCP_OK, MCP_E_ARG, MCP_E_CAP, MCP_E_CUDA, MCP_E_NOMEM, MCP_E_FORMAT, MCP_E_STATE, MCP_E_UNSUPPORTED, MCP_E_NCCL = (

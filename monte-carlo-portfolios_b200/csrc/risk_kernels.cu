@@ -297,6 +297,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// named barriers between the two warps that share an SM sub-partition (ids 1..8; 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -425,6 +429,56 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
         seg[g] = DENSE ? rowbase : rowbase + (int64_t)c * (a.sub_len >> 2);
     }
     const bool vec_ok = (a.stride & 1) == 0 && (a.sub_len & 1) == 0;
+    const bool moments = a.part != nullptr;
+    // Scheduling.  The FP64 tensor pipe is the bound resource and scalar FP64 ops (the moments) share it, while
+    // integer work from the partner warp co-issues with DMMA (profiles/microbench/dmma_coissue.cu).  So:
+    //  * warps w and w+4 (same SM sub-partition) ping-pong through two named barriers: one owns the pipe
+    //    (DMMAs + the moment updates), the other runs its integer epilogue (filter, address math, stores);
+    //  * the epilogue is software-pipelined by one block: the moments of block i-1 are interleaved between the
+    //    k-steps of block i's DMMAs (no dependency bubble), its filter runs after the hand-off.
+    const bool first = warp < 4;
+    const int bar_a = 1 + 2 * (warp & 3), bar_b = bar_a + 1;
+    double pd0[VM_G], pd1[VM_G]; // previous block's values; initialised to the shift so that they add exactly 0
+#pragma unroll
+    for (int g = 0; g < VM_G; ++g) { pd0[g] = cs[g]; pd1[g] = cs[g]; }
+    int ptl = 0;          // previous block: offset of this lane's first trial inside the sub-chunk
+    uint32_t pv = 0;      // previous block: bit0 / bit1 = first / second trial is real
+
+    // integer half of the epilogue for the block held in pd0/pd1
+    auto int_epilogue = [&]() {
+        const uint32_t v0 = pv & 1u, v1 = pv >> 1;
+        const int32_t n0 = (int32_t)(nb + ptl);
+#pragma unroll
+        for (int g = 0; g < VM_G; ++g) {
+            if (DENSE) {
+                if (ok[g]) {
+                    double *dst = a.candV + seg[g] + ptl;
+                    if (v1 && vec_ok) *reinterpret_cast<double2 *>(dst) = make_double2(pd0[g], pd1[g]);
+                    else {
+                        if (v0) dst[0] = pd0[g];
+                        if (v1) dst[1] = pd1[g];
+                    }
+                }
+            } else {
+#ifndef MCP_EXP_NO_FILTER
+                const uint32_t h0 = (fkey(pd0[g]) <= tk[g]) & v0, h1 = (fkey(pd1[g]) <= tk[g]) & v1;
+                append_if(h0, a.candV + seg[g] + cnt[g], pd0[g], a.candI + seg[g] + cnt[g], n0);
+                cnt[g] += h0;
+                append_if(h1, a.candV + seg[g] + cnt[g], pd1[g], a.candI + seg[g] + cnt[g], n0 + 1);
+                cnt[g] += h1;
+#endif
+            }
+        }
+    };
+    // FP64 half for value v (0..7) of the block held in pd0/pd1
+    auto moment_of = [&](int v) {
+#ifndef MCP_EXP_NO_MOMENTS
+        const int g = v >> 1;
+        const double d = ((v & 1) ? pd1[g] : pd0[g]) - cs[g];
+        s1[g] += d;
+        s2[g] = fma(d, d, s2[g]);
+#endif
+    };
 
     for (int it = 0; it < nst; ++it) {
         const int st = it % VM_NSTAGE;
@@ -442,41 +496,38 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
             double d0[VM_G], d1[VM_G];
 #pragma unroll
             for (int g = 0; g < VM_G; ++g) { d0[g] = 0.0; d1[g] = 0.0; }
+            if (!first) pair_sync(bar_a); // wait until the partner warp has released the pipe
 #pragma unroll
-            for (int s = 0; s < NK; ++s)
+            for (int s = 0; s < NK; ++s) {
 #pragma unroll
                 for (int g = 0; g < VM_G; ++g) dmma884(d0[g], d1[g], ef[g][s], sf[s]);
-            const int tl = it * VM_ST + blk * 8 + 2 * c; // offset of this lane's first trial inside the sub-chunk
-            const bool v0 = tl < ntr, v1 = tl + 1 < ntr;
-            const int32_t n0 = (int32_t)(nb + tl);
+                if (moments) {
 #pragma unroll
-            for (int g = 0; g < VM_G; ++g) {
-                if (a.part) {
-                    const double da = d0[g] - cs[g], db = d1[g] - cs[g];
-                    if (v0) { s1[g] += da; s2[g] = fma(da, da, s2[g]); }
-                    if (v1) { s1[g] += db; s2[g] = fma(db, db, s2[g]); }
-                }
-                if (DENSE) {
-                    if (ok[g]) {
-                        double *dst = a.candV + seg[g] + tl;
-                        if (v1 && vec_ok) *reinterpret_cast<double2 *>(dst) = make_double2(d0[g], d1[g]);
-                        else {
-                            if (v0) dst[0] = d0[g];
-                            if (v1) dst[1] = d1[g];
-                        }
-                    }
-                } else {
-                    const uint32_t h0 = (fkey(d0[g]) <= tk[g]) && v0, h1 = (fkey(d1[g]) <= tk[g]) && v1;
-                    append_if(h0, a.candV + seg[g] + cnt[g], d0[g], a.candI + seg[g] + cnt[g], n0);
-                    cnt[g] += h0;
-                    append_if(h1, a.candV + seg[g] + cnt[g], d1[g], a.candI + seg[g] + cnt[g], n0 + 1);
-                    cnt[g] += h1;
+                    for (int v = 0; v < 8; ++v)
+                        if ((v * NK) / 8 == s) moment_of(v);
                 }
             }
+            pair_arrive(first ? bar_a : bar_b); // hand the tensor pipe to the partner
+            int_epilogue();                    // previous block, integer pipe only
+            // rotate: this block becomes "previous"
+            ptl = it * VM_ST + blk * 8 + 2 * c;
+            pv = (ptl < ntr ? 1u : 0u) | (ptl + 1 < ntr ? 2u : 0u);
+#pragma unroll
+            for (int g = 0; g < VM_G; ++g) {
+                pd0[g] = (pv & 1u) ? d0[g] : cs[g]; // trials past the end of the sub-chunk contribute exactly 0
+                pd1[g] = (pv & 2u) ? d1[g] : cs[g];
+            }
+            if (first) pair_sync(bar_b); // the partner has issued its DMMAs: the pipe is ours again
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
     }
+    // drain the software pipeline: the last block
+    if (moments) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) moment_of(v);
+    }
+    int_epilogue();
     // ---- epilogue: per-portfolio partial moments (fixed 4-lane tree: deterministic) and segment counts
 #pragma unroll
     for (int g = 0; g < VM_G; ++g) {
