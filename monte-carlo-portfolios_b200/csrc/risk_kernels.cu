@@ -260,9 +260,9 @@ struct StreamArgs {
     int nsub;                // sub-chunks (gridDim.x)
     int sub_len;             // trials per sub-chunk (multiple of 8)
     const uint64_t *tkey;    // [P] candidate iff fkey(V) <= tkey, i.e. V <= -(current VaR lower bound)  (SPARSE)
-    double *candV;           // [p - p0][stride]
-    int32_t *candI;          // [p - p0][stride]   (SPARSE)
-    int64_t stride;
+    void *cand;              // candidate buffer, one row of `pitch` bytes per portfolio.  DENSE steps use the row as a
+                             // plain double array (slot = trial - n_begin); SPARSE steps append 16-byte records {V, trial}
+    int64_t pitch;
     int32_t *cnt;            // [p - p0][4*nsub]   (SPARSE)
     double *part;            // [P][part_stride][2]; null = no moments (mcp_value)
     int part_stride, part_base;
@@ -319,11 +319,14 @@ __device__ __forceinline__ double fkey_inv(uint64_t k)
     return __longlong_as_double((long long)b);
 }
 
-// branch-free conditional append of one candidate (value, trial) to a lane-private segment
-__device__ __forceinline__ void append_if(uint32_t hit, double *pv, double v, int32_t *pi, int32_t n)
+// candidate record of a sparse step: 16 bytes so that one predicated STG.128 appends it
+struct __align__(16) CandRec { double v; int32_t trial; int32_t pad; };
+
+// branch-free conditional append of one candidate record to a lane-private segment
+__device__ __forceinline__ void append_if(uint32_t hit, CandRec *dst, double v, int32_t n)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.global.f64 [%1], %2;\n\t@p st.global.s32 [%3], %4;\n\t}" ::"r"(hit),
-                 "l"(pv), "d"(v), "l"(pi), "r"(n) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 t;\n\tsetp.ne.u32 p, %0, 0;\n\tcvt.u64.u32 t, %3;\n\t@p st.global.v2.b64 [%1], {%2, t};\n\t}" ::"r"(hit),
+                 "l"(dst), "l"(__double_as_longlong(v)), "r"(n) : "memory");
 }
 
 template <int NK>
@@ -414,21 +417,33 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 #pragma unroll
         for (int g = 0; g < VM_G; ++g) cs[g] = 0.0;
     }
-    uint64_t tk[VM_G];
+    uint64_t tk[VM_G];   // generic compare: candidate iff fkey(V) <= tk
+    uint64_t traw[VM_G]; // fast compare (negative bound, the normal case): candidate iff bits(V) >= traw, unsigned
     int cnt[VM_G];
     double s1[VM_G], s2[VM_G];
-    int64_t seg[VM_G]; // this lane's private segment (SPARSE) or the row base (DENSE)
+    double *drow[VM_G];   // DENSE: the portfolio's row as doubles, at this sub-chunk
+    CandRec *srec[VM_G];  // SPARSE: this lane's private segment of records
+    bool neg = true;
 #pragma unroll
     for (int g = 0; g < VM_G; ++g) {
         tk[g] = 0; // fkey(x) <= 0 never holds for a finite x: inactive rows never append
-        if (!DENSE && ok[g]) tk[g] = a.tkey[prow[g]];
+        traw[g] = ~0ull;
+        if (!DENSE && ok[g]) {
+            tk[g] = a.tkey[prow[g]];
+            const double bound = fkey_inv(tk[g]);
+            traw[g] = (uint64_t)__double_as_longlong(bound);
+            neg = neg && (bound < 0.0);
+        }
         cnt[g] = 0;
         s1[g] = 0.0;
         s2[g] = 0.0;
-        const int64_t rowbase = (prow[g] - a.p0) * a.stride + (int64_t)sub * a.sub_len;
-        seg[g] = DENSE ? rowbase : rowbase + (int64_t)c * (a.sub_len >> 2);
+        unsigned char *rowp = reinterpret_cast<unsigned char *>(a.cand) + (prow[g] - a.p0) * a.pitch;
+        drow[g] = reinterpret_cast<double *>(rowp) + (int64_t)sub * a.sub_len;
+        srec[g] = reinterpret_cast<CandRec *>(rowp) + (int64_t)sub * a.sub_len + (int64_t)c * (a.sub_len >> 2);
     }
-    const bool vec_ok = (a.stride & 1) == 0 && (a.sub_len & 1) == 0;
+    // all 32 portfolios of the warp have a negative bound on V (a positive VaR): one unsigned compare per value
+    const bool fastcmp = __all_sync(0xffffffffu, neg);
+    const bool vec_ok = (a.sub_len & 1) == 0 && (a.pitch & 15) == 0;
     const bool moments = a.part != nullptr;
     // Scheduling.  The FP64 tensor pipe is the bound resource and scalar FP64 ops (the moments) share it, while
     // integer work from the partner warp co-issues with DMMA (profiles/microbench/dmma_coissue.cu).  So:
@@ -452,7 +467,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
         for (int g = 0; g < VM_G; ++g) {
             if (DENSE) {
                 if (ok[g]) {
-                    double *dst = a.candV + seg[g] + ptl;
+                    double *dst = drow[g] + ptl;
                     if (v1 && vec_ok) *reinterpret_cast<double2 *>(dst) = make_double2(pd0[g], pd1[g]);
                     else {
                         if (v0) dst[0] = pd0[g];
@@ -461,10 +476,17 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                 }
             } else {
 #ifndef MCP_EXP_NO_FILTER
-                const uint32_t h0 = (fkey(pd0[g]) <= tk[g]) & v0, h1 = (fkey(pd1[g]) <= tk[g]) & v1;
-                append_if(h0, a.candV + seg[g] + cnt[g], pd0[g], a.candI + seg[g] + cnt[g], n0);
+                uint32_t h0, h1;
+                if (fastcmp) {
+                    h0 = ((uint64_t)__double_as_longlong(pd0[g]) >= traw[g]) & v0;
+                    h1 = ((uint64_t)__double_as_longlong(pd1[g]) >= traw[g]) & v1;
+                } else {
+                    h0 = (fkey(pd0[g]) <= tk[g]) & v0;
+                    h1 = (fkey(pd1[g]) <= tk[g]) & v1;
+                }
+                append_if(h0, srec[g] + cnt[g], pd0[g], n0);
                 cnt[g] += h0;
-                append_if(h1, a.candV + seg[g] + cnt[g], pd1[g], a.candI + seg[g] + cnt[g], n0 + 1);
+                append_if(h1, srec[g] + cnt[g], pd1[g], n0 + 1);
                 cnt[g] += h1;
 #endif
             }
@@ -511,11 +533,17 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
             int_epilogue();                    // previous block, integer pipe only
             // rotate: this block becomes "previous"
             ptl = it * VM_ST + blk * 8 + 2 * c;
-            pv = (ptl < ntr ? 1u : 0u) | (ptl + 1 < ntr ? 2u : 0u);
+            if (it * VM_ST + blk * 8 + 8 <= ntr) { // whole block is real (warp-uniform)
+                pv = 3u;
 #pragma unroll
-            for (int g = 0; g < VM_G; ++g) {
-                pd0[g] = (pv & 1u) ? d0[g] : cs[g]; // trials past the end of the sub-chunk contribute exactly 0
-                pd1[g] = (pv & 2u) ? d1[g] : cs[g];
+                for (int g = 0; g < VM_G; ++g) { pd0[g] = d0[g]; pd1[g] = d1[g]; }
+            } else {
+                pv = (ptl < ntr ? 1u : 0u) | (ptl + 1 < ntr ? 2u : 0u);
+#pragma unroll
+                for (int g = 0; g < VM_G; ++g) {
+                    pd0[g] = (pv & 1u) ? d0[g] : cs[g]; // trials past the end of the sub-chunk contribute exactly 0
+                    pd1[g] = (pv & 2u) ? d1[g] : cs[g];
+                }
             }
             if (first) pair_sync(bar_b); // the partner has issued its DMMAs: the pipe is ours again
         }
@@ -582,13 +610,14 @@ constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS; // 11-bit digits over the 96-bit composite (key64, trial32), MSB first
 constexpr int SEL_SORT = 256;           // keep refining digits until the boundary bucket is at most this big
 constexpr int SEL_NPASS = (96 + SEL_BITS - 1) / SEL_BITS;
+constexpr int kSelMaxSeg = 4096;         // most segments (4 per sub-chunk) a sparse step may have
 
 // Candidates of one portfolio row = the previously kept tail (key, trial) plus this step's
 // segments of raw values V (loss = 0.0 - V), one segment per trial sub-chunk.
 struct SelArgs {
-    const double *candV;       // [rows][stride]
-    const int32_t *candI;      // null -> dense: trial = n_begin + seg*sub_len + i
-    int64_t stride;
+    const void *cand;          // one row of `pitch` bytes per portfolio: dense rows are double arrays (trial = n_begin +
+                               // seg*sub_len + i), sparse rows are CandRec arrays in lane-private segments
+    int64_t pitch;
     const int32_t *cnt;        // [rows][nsub]; null -> dense (segment full)
     int nsub;
     int64_t sub_len;
@@ -629,30 +658,34 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
 
 // visit every candidate of the row straight from global memory
 template <class Fn>
-__device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, Fn f)
+__device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, const int *segoff, Fn f)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.tail + i], (uint32_t)a.kept_idx_in[row * a.tail + i]);
-    const double *V = a.candV + row * a.stride;
-    const int32_t *I = a.candI ? a.candI + row * a.stride : nullptr;
-    if (a.cnt && a.nsub >= 64) {
-        // sparse step: many short lane-private segments -> one thread per segment keeps all their loads in flight
-        for (int seg = tid; seg < a.nsub; seg += SEL_THREADS) {
-            const int64_t base = (int64_t)seg * a.sub_len;
-            const int c = a.cnt[row * a.nsub + seg];
-            for (int i = 0; i < c; ++i) f(fkey(0.0 - V[base + i]), (uint32_t)I[base + i]);
+    const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
+    if (a.cnt) {
+        // sparse step: many short lane-private segments of 16-byte records.  Flat index over all their entries
+        // (segoff = exclusive prefix of the segment counts, in shared memory): independent loads in flight.
+        const int4 *R = reinterpret_cast<const int4 *>(rowp);
+        const int total = segoff[a.nsub];
+        for (int i = tid; i < total; i += SEL_THREADS) {
+            int lo = 0, hi = a.nsub; // largest seg with segoff[seg] <= i
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (segoff[mid] <= i) lo = mid; else hi = mid;
+            }
+            const int4 rec = R[(int64_t)lo * a.sub_len + (i - segoff[lo])];
+            const double v = __hiloint2double(rec.y, rec.x);
+            f(fkey(0.0 - v), (uint32_t)rec.z);
         }
         return;
     }
+    const double *V = reinterpret_cast<const double *>(rowp);
     for (int seg = warp; seg < a.nsub; seg += SEL_THREADS / 32) {
         const int64_t base = (int64_t)seg * a.sub_len;
-        int64_t c;
-        if (a.cnt) c = a.cnt[row * a.nsub + seg];
-        else { c = a.step_len - base; c = c < 0 ? 0 : (c > a.sub_len ? a.sub_len : c); }
-        for (int64_t i = lane; i < c; i += 32) {
-            const uint32_t id = I ? (uint32_t)I[base + i] : (uint32_t)(a.n_begin + base + i);
-            f(fkey(0.0 - V[base + i]), id);
-        }
+        int64_t c = a.step_len - base;
+        c = c < 0 ? 0 : (c > a.sub_len ? a.sub_len : c);
+        for (int64_t i = lane; i < c; i += 32) f(fkey(0.0 - V[base + i]), (uint32_t)(a.n_begin + base + i));
     }
 }
 
@@ -667,6 +700,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     uint64_t *skey = reinterpret_cast<uint64_t *>(sel_smem);
     uint32_t *sidx = reinterpret_cast<uint32_t *>(skey + a.cap);
     int *hist = reinterpret_cast<int *>(sidx + a.cap);
+    int *segoff = hist + SEL_BINS; // [nsub + 1] exclusive prefix of the segment counts (sparse steps)
     __shared__ uint64_t ckey[SEL_SORT];
     __shared__ uint32_t cidx[SEL_SORT];
     __shared__ double red[32];
@@ -680,7 +714,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
 
     // ---- moments of the dense row with shift c = V[0] (generic path only)
     if (a.moments_n > 0) {
-        const double *V = a.candV + row * a.stride;
+        const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
         const double c = V[0];
         double s1 = 0.0, s2 = 0.0;
         for (int64_t i = tid; i < a.step_len; i += SEL_THREADS) {
@@ -701,25 +735,32 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     // ---- how many candidates does this row have?  stage them if they fit
     int64_t M;
     if (a.cnt) {
-        int c = 0;
-        for (int sgi = tid; sgi < a.nsub; sgi += SEL_THREADS) c += a.cnt[row * a.nsub + sgi];
-        for (int d = 16; d; d >>= 1) c += __shfl_down_sync(kFullMask, c, d);
-        if (lane == 0) s_wsum[warp] = c;
+        for (int sgi = tid; sgi < a.nsub; sgi += SEL_THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
+        if (tid == 0) segoff[0] = 0;
         __syncthreads();
-        if (tid == 0) {
-            int tot = 0;
-            for (int w = 0; w < SEL_THREADS / 32; ++w) tot += s_wsum[w];
-            s_total = tot;
+        if (warp == 0) { // inclusive scan, 32 segments per round
+            int run = 0;
+            for (int base = 0; base < a.nsub; base += 32) {
+                const int i = base + lane;
+                const int v = i < a.nsub ? segoff[i + 1] : 0;
+                int incl = v;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(kFullMask, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                if (i < a.nsub) segoff[i + 1] = run + incl;
+                run += __shfl_sync(kFullMask, incl, 31);
+            }
         }
         __syncthreads();
-        M = a.kept_n + s_total;
+        M = a.kept_n + segoff[a.nsub];
     } else
         M = a.kept_n + a.step_len;
     const bool staged = M <= a.cap;
     if (tid == 0) { s_ncand = 0; s_nkept = 0; }
     __syncthreads();
     if (staged) {
-        for_each_global(a, row, [&](uint64_t key, uint32_t id) {
+        for_each_global(a, row, segoff, [&](uint64_t key, uint32_t id) {
             const int o = atomicAdd(&s_ncand, 1);
             skey[o] = key;
             sidx[o] = id;
@@ -731,22 +772,32 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         if (staged) {
             for (int i = tid; i < Ms; i += SEL_THREADS) f(skey[i], sidx[i]);
         } else
-            for_each_global(a, row, f);
+            for_each_global(a, row, segoff, f);
     };
 
-    u128 prefix = 0;     // selected high digits
-    int shift = 96;      // bits below the prefix
+    // Radix select on the 64-bit loss key first (cheap 64-bit digit extraction); the trial index only breaks ties,
+    // so its digits are visited only if more than SEL_SORT candidates share one exact loss value.
+    // `kpre`/`ipre` = selected high bits of key / trial; `kshift`/`ishift` = bits not yet resolved.
+    uint64_t kpre = 0;
+    uint32_t ipre = 0;
+    int kshift = 64, ishift = 32;
     int64_t need = t;    // rank from the top still to resolve inside the prefix bucket
     int bucket = 0;
-    for (int pass = 0; pass < SEL_NPASS; ++pass) {
-        const int width = shift >= SEL_BITS ? SEL_BITS : shift;
-        shift -= width;
+    auto in_prefix = [&](uint64_t key, uint32_t id) -> bool {
+        if (kshift < 64 && (key >> kshift) != kpre) return false;
+        if (kshift == 0 && ishift < 32 && (id >> ishift) != ipre) return false;
+        return true;
+    };
+    for (int pass = 0; pass < 12; ++pass) {
+        const bool on_key = kshift > 0;
+        const int rem = on_key ? kshift : ishift;
+        const int width = rem >= SEL_BITS ? SEL_BITS : rem;
+        const int sh = rem - width;
         const uint32_t dmask = (1u << width) - 1u;
         for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
         __syncthreads();
         for_each([&](uint64_t key, uint32_t id) {
-            const u128 c = comp_of(key, id);
-            if (pass == 0 || (c >> (shift + width)) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & dmask], 1);
+            if (in_prefix(key, id)) atomicAdd(&hist[on_key ? (uint32_t)(key >> sh) & dmask : (id >> sh) & dmask], 1);
         });
         __syncthreads();
         // find the digit where the count from the top reaches `need`: thread 0 owns the highest bins
@@ -777,7 +828,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             }
         }
         __syncthreads();
-        prefix = (prefix << width) | (u128)(uint32_t)s_sel;
+        if (on_key) { kpre = (width == 64 ? 0 : (kpre << width)) | (uint64_t)(uint32_t)s_sel; kshift = sh; }
+        else { ipre = (ipre << width) | (uint32_t)s_sel; ishift = sh; }
         need -= s_above;
         bucket = s_bucket;
         __syncthreads();
@@ -787,12 +839,19 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     if (tid == 0) s_ncand = 0;
     __syncthreads();
     for_each([&](uint64_t key, uint32_t id) {
-        const u128 hp = comp_of(key, id) >> shift;
-        if (hp > prefix) {
+        // compare the resolved prefix of the composite (key, trial)
+        int rel; // +1 above, 0 inside, -1 below
+        const uint64_t kp = kshift < 64 ? (key >> kshift) : 0;
+        if (kp != kpre) rel = kp > kpre ? 1 : -1;
+        else if (kshift == 0 && ishift < 32) {
+            const uint32_t ip = id >> ishift;
+            rel = ip == ipre ? 0 : (ip > ipre ? 1 : -1);
+        } else rel = 0;
+        if (rel > 0) {
             const int o = atomicAdd(&s_nkept, 1);
             kk[o] = key;
             ki[o] = (int32_t)id;
-        } else if (hp == prefix) {
+        } else if (rel == 0) {
             const int o = atomicAdd(&s_ncand, 1);
             ckey[o] = key;
             cidx[o] = id;
@@ -833,7 +892,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     }
 }
 
-static size_t sel_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4; }
+static size_t sel_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4 + (size_t)(kSelMaxSeg + 1) * 4; }
 
 // ============================================================ finalize
 // Kernel (3): the kept tail -> ascending breach-trial list, and CVaR = mean tail loss.
@@ -954,6 +1013,7 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
         int64_t nsub = (sms * waves) / nsg;
         if (nsub < 1) nsub = 1;
         if (nsub > L / 8) nsub = L / 8 > 0 ? L / 8 : 1;
+        if (nsub > kSelMaxSeg / 4) nsub = kSelMaxSeg / 4;
         int64_t sl = (L + nsub - 1) / nsub;
         sl = (sl + 7) & ~(int64_t)7;
         nsub = (L + sl - 1) / sl;
@@ -1007,8 +1067,8 @@ static int risk_run_dense(mcp_ctx *ctx, int64_t t)
         const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
         MCP_TRY(risk_value(ctx, p0, p1, ctx->dLoss.as<double>()));
         SelArgs a{};
-        a.candV = ctx->dLoss.as<double>();
-        a.stride = N;
+        a.cand = ctx->dLoss.as<double>();
+        a.pitch = N * (int64_t)sizeof(double);
         a.nsub = 1;
         a.sub_len = N;
         a.step_len = N;
@@ -1089,7 +1149,7 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
         v.p0 = p0; v.p1 = p1;
         v.n_begin = 0; v.n_end = ctx->N;
         v.nsub = st[0].nsub; v.sub_len = st[0].sub_len;
-        v.candV = d_V; v.stride = ctx->N;
+        v.cand = d_V; v.pitch = ctx->N * (int64_t)sizeof(double);
         dim3 grid((unsigned)v.nsub, (unsigned)nsg);
         return dispatch_value_mma(ctx, v, true, grid);
     }
@@ -1122,12 +1182,11 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             nparts += s.nsub;
         }
         stride = (stride + 3) & ~(int64_t)3;
-        if ((size_t)Pt * stride * 12 <= budget || Pt <= VM_PG) break;
+        if ((size_t)Pt * stride * 16 <= budget || Pt <= VM_PG) break;
         Pt = ((Pt / 2 + VM_PG - 1) / VM_PG) * VM_PG;
     }
     if (Pt > 65535 * (int64_t)VM_PG) Pt = 65535 * (int64_t)VM_PG;
-    MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * sizeof(double)));
-    MCP_CUDA(ctx, ctx->dCandIdx.reserve((size_t)Pt * stride * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * 16));
     MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
@@ -1153,18 +1212,16 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             v.n_begin = s.begin; v.n_end = s.end;
             v.nsub = s.nsub; v.sub_len = s.sub_len;
             v.tkey = tkey;
-            v.candV = ctx->dCandKey.as<double>();
-            v.candI = ctx->dCandIdx.as<int32_t>();
-            v.stride = stride;
+            v.cand = ctx->dCandKey.p;
+            v.pitch = stride * 16;
             v.cnt = ctx->dCandCnt.as<int32_t>();
             v.part = ctx->dPart.as<double>();
             v.part_stride = nparts; v.part_base = part_base;
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
             MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
             SelArgs a{};
-            a.candV = v.candV;
-            a.candI = dense ? nullptr : v.candI;
-            a.stride = stride;
+            a.cand = v.cand;
+            a.pitch = v.pitch;
             a.cnt = dense ? nullptr : v.cnt;
             // sparse steps: every sub-chunk holds four lane-private segments of sub_len/4 slots
             a.nsub = dense ? s.nsub : 4 * s.nsub;
