@@ -86,7 +86,10 @@ int  mcp_device_info(mcp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, 
 int  mcp_sync(mcp_ctx *ctx);
 /* Tuning / test switches.  Keys: "force_dense" (1 = value every trial into a dense tile and select once, the
  * path used for factor counts without a streaming kernel), "force_sort_finalize" (1 = breach list by bitonic
- * sort instead of the trial bitmap).  Results are identical either way; only the kernels differ. */
+ * sort instead of the trial bitmap), "value_mma" (0 = mcp_value through the scalar-fma kernel instead of the FP64
+ * tensor-core kernel), "fused_moments" (1 = mean/variance by a per-trial reduction fused into the valuation kernel
+ * instead of by linearity, mean = E.mean(S), var = E^T Cov(S) E).  Trial indices, breach lists and byte streams are
+ * identical either way, moments agree to 1e-9; only the kernels differ. */
 int  mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value);
 
 /* Upper bound on the encoded size in BYTES of one list of n ints under `framing`

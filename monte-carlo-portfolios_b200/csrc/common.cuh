@@ -92,6 +92,8 @@ struct mcp_ctx {
     int selCap = 2304;
     uint32_t mmaConfigured = 0;
     bool valueMma = true;          // mcp_value through the tensor-core kernel when F allows (else scalar fma)
+    bool fusedMoments = false;     // true: per-trial moment reduction fused in the valuation kernel (scalar FP64)
+    mcp::DevBuf dGram;
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)
 

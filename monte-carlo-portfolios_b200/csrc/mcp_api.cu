@@ -115,7 +115,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
-                           &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag};
+                           &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -140,6 +140,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     if (!strcmp(key, "force_dense")) ctx->forceDense = value != 0;
     else if (!strcmp(key, "force_sort_finalize")) ctx->forceSortFinalize = value != 0;
     else if (!strcmp(key, "value_mma")) ctx->valueMma = value != 0;
+    else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
 }

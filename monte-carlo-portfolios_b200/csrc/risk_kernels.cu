@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 //     fkey(V) <= tkey_p, i.e. loss >= the current lower bound of the portfolio's VaR: a 64-bit integer
 //     compare on the order-preserving image, and predicated stores -- no divergence, no FP64-pipe slots.
 // Each lane appends to its own private segment (portfolio, sub-chunk, lane%4): no atomics.
-constexpr int VM_WARPS = 8;
+constexpr int VM_WARPS = 16;
 constexpr int VM_THREADS = VM_WARPS * 32;
-constexpr int VM_G = 4;                      // portfolio groups (of 8) per warp
+constexpr int VM_G = 2;                      // portfolio groups (of 8) per warp
 constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 256
 constexpr int VM_ST = 32;                    // trials per stage
 constexpr int VM_NSTAGE = 4;
@@ -298,8 +298,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // named barriers between the two warps that share an SM sub-partition (ids 1..8; 0 is __syncthreads)
+#ifndef MCP_EXP_NO_PINGPONG
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+#else
+__device__ __forceinline__ void pair_sync(int) {}
+__device__ __forceinline__ void pair_arrive(int) {}
+#endif
 
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -451,8 +456,6 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     //    (DMMAs + the moment updates), the other runs its integer epilogue (filter, address math, stores);
     //  * the epilogue is software-pipelined by one block: the moments of block i-1 are interleaved between the
     //    k-steps of block i's DMMAs (no dependency bubble), its filter runs after the hand-off.
-    const bool first = warp < 4;
-    const int bar_a = 1 + 2 * (warp & 3), bar_b = bar_a + 1;
     double pd0[VM_G], pd1[VM_G]; // previous block's values; initialised to the shift so that they add exactly 0
 #pragma unroll
     for (int g = 0; g < VM_G; ++g) { pd0[g] = cs[g]; pd1[g] = cs[g]; }
@@ -518,7 +521,6 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
             double d0[VM_G], d1[VM_G];
 #pragma unroll
             for (int g = 0; g < VM_G; ++g) { d0[g] = 0.0; d1[g] = 0.0; }
-            if (!first) pair_sync(bar_a); // wait until the partner warp has released the pipe
 #pragma unroll
             for (int s = 0; s < NK; ++s) {
 #pragma unroll
@@ -529,7 +531,6 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                         if ((v * NK) / 8 == s) moment_of(v);
                 }
             }
-            pair_arrive(first ? bar_a : bar_b); // hand the tensor pipe to the partner
             int_epilogue();                    // previous block, integer pipe only
             // rotate: this block becomes "previous"
             ptl = it * VM_ST + blk * 8 + 2 * c;
@@ -545,7 +546,6 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                     pd1[g] = (pv & 2u) ? d1[g] : cs[g];
                 }
             }
-            if (first) pair_sync(bar_b); // the partner has issued its DMMAs: the pipe is ours again
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
@@ -599,6 +599,104 @@ __global__ void __launch_bounds__(256) k_moments_finalize(const double *E, const
         mean[p] = c + m1;
         variance[p] = fma(-m1, m1, s2 * invn);
     }
+}
+
+// ============================================================ moments by linearity
+// mean_p = E_p . mean(S) and var_p = E_p^T Cov(S) E_p are algebraically the mean and population variance of the
+// portfolio's N valuations (V = E S^T is linear), and cost one Gram-matrix pass over S plus F^2 fma per portfolio
+// instead of 3 scalar FP64 instructions per valuation.  That matters here because scalar FP64 instructions share
+// the DMMA pipe and cost a full tensor-op slot each when interleaved with DMMAs (ncu: the fused per-value moment
+// updates took 30 % of the valuation kernel).  The fused per-trial reduction stays available (option
+// "fused_moments") and both are held to 1e-9 against the oracle's long-double per-trial reduction.
+constexpr int GM_THREADS = 256;
+constexpr int GM_ROWS = 256; // scenario rows per CTA
+
+// column sums of S over this CTA's rows -> partial[b][F]
+__global__ void __launch_bounds__(GM_THREADS) k_col_sums(const double *__restrict__ S, int64_t N, int F, double *__restrict__ partial)
+{
+    const int64_t r0 = (int64_t)blockIdx.x * GM_ROWS, r1 = min(N, r0 + GM_ROWS);
+    for (int k = threadIdx.x; k < F; k += GM_THREADS) {
+        double acc = 0.0;
+        for (int64_t r = r0; r < r1; ++r) acc += S[r * F + k];
+        partial[(int64_t)blockIdx.x * F + k] = acc;
+    }
+}
+
+// mu[k] = sum of partials / N (fixed order)
+__global__ void k_col_mean(const double *partial, int nb, int F, int64_t N, double *mu)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    double acc = 0.0;
+    for (int b = 0; b < nb; ++b) acc += partial[(int64_t)b * F + k];
+    mu[k] = acc / (double)N;
+}
+
+// centered Gram matrix of this CTA's rows: partial[b][F][F] = sum_r (S_r - mu)(S_r - mu)^T
+__global__ void __launch_bounds__(GM_THREADS) k_gram_centered(const double *__restrict__ S, int64_t N, int F, const double *__restrict__ mu,
+                                                              double *__restrict__ partial)
+{
+    extern __shared__ double gm_s[]; // [32][F] rows being processed
+    const int64_t r0 = (int64_t)blockIdx.x * GM_ROWS, r1 = min(N, r0 + GM_ROWS);
+    const int FF = F * F;
+    // each thread owns entries e = tid, tid + 256, ... (at most 16 for F = 64)
+    double acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+    for (int64_t rb = r0; rb < r1; rb += 32) {
+        const int nr = (int)min((int64_t)32, r1 - rb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * F; i += GM_THREADS) gm_s[i] = S[rb * F + i] - mu[i % F];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int e = threadIdx.x + q * GM_THREADS;
+            if (e < FF) {
+                const int k = e / F, l = e % F;
+                double a = acc[q];
+                for (int r = 0; r < nr; ++r) a = fma(gm_s[r * F + k], gm_s[r * F + l], a);
+                acc[q] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int e = threadIdx.x + q * GM_THREADS;
+        if (e < FF) partial[(int64_t)blockIdx.x * FF + e] = acc[q];
+    }
+}
+
+// cov[e] = sum of partials / N (fixed order)
+__global__ void k_gram_reduce(const double *partial, int nb, int FF, int64_t N, double *cov)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= FF) return;
+    double acc = 0.0;
+    for (int b = 0; b < nb; ++b) acc += partial[(int64_t)b * FF + e];
+    cov[e] = acc / (double)N;
+}
+
+// one warp per portfolio: mean = E.mu, variance = E^T Cov E
+__global__ void __launch_bounds__(256) k_moments_linear(const double *__restrict__ E, int64_t P, int F, const double *__restrict__ mu,
+                                                        const double *__restrict__ cov, double *mean, double *variance)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const double *e = E + p * F;
+    double m = 0.0, v = 0.0;
+    for (int k = lane; k < F; k += 32) {
+        const double ek = e[k];
+        m = fma(ek, mu[k], m);
+        double row = 0.0;
+        for (int l = 0; l < F; ++l) row = fma(cov[k * F + l], e[l], row);
+        v = fma(ek, row, v);
+    }
+    for (int d = 16; d; d >>= 1) {
+        m += __shfl_down_sync(kFullMask, m, d);
+        v += __shfl_down_sync(kFullMask, v, d);
+    }
+    if (lane == 0) { mean[p] = m; variance[p] = v; }
 }
 
 // ============================================================ selection
@@ -1159,6 +1257,25 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
     return check_launch(ctx, "k_value_generic");
 }
 
+// mean / variance of every portfolio by linearity (see "moments by linearity" above)
+static int run_moments_linear(mcp_ctx *ctx)
+{
+    const int64_t N = ctx->N, P = ctx->P;
+    const int F = ctx->F;
+    if (F > 64) return fail(ctx, MCP_E_UNSUPPORTED, "linear moments: more than 64 factors");
+    const int nb = (int)((N + GM_ROWS - 1) / GM_ROWS);
+    MCP_CUDA(ctx, ctx->dGram.reserve(((size_t)nb * F * F + (size_t)nb * F + (size_t)F * F + F) * sizeof(double)));
+    double *pg = ctx->dGram.as<double>(), *ps = pg + (size_t)nb * F * F, *cov = ps + (size_t)nb * F, *mu = cov + (size_t)F * F;
+    KScope ks(ctx, MCP_K_SELECT, 5);
+    k_col_sums<<<nb, GM_THREADS, 0, ctx->stream>>>(ctx->dS.as<double>(), N, F, ps);
+    k_col_mean<<<(F + 63) / 64, 64, 0, ctx->stream>>>(ps, nb, F, N, mu);
+    k_gram_centered<<<nb, GM_THREADS, 32 * F * sizeof(double), ctx->stream>>>(ctx->dS.as<double>(), N, F, mu, pg);
+    k_gram_reduce<<<(F * F + 255) / 256, 256, 0, ctx->stream>>>(pg, nb, F * F, N, cov);
+    k_moments_linear<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), P, F, mu, cov, ctx->dMean.as<double>(),
+                                                                        ctx->dVar.as<double>());
+    return check_launch(ctx, "moments_linear");
+}
+
 // streaming valuation (FP64 tensor cores) + threshold filter + incremental radix-select
 static int risk_run_stream(mcp_ctx *ctx, int64_t t)
 {
@@ -1215,7 +1332,7 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             v.cand = ctx->dCandKey.p;
             v.pitch = stride * 16;
             v.cnt = ctx->dCandCnt.as<int32_t>();
-            v.part = ctx->dPart.as<double>();
+            v.part = ctx->fusedMoments ? ctx->dPart.as<double>() : nullptr;
             v.part_stride = nparts; v.part_base = part_base;
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
             MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
@@ -1249,13 +1366,14 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
         }
         MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], ctx->dBreach.as<int32_t>() + p0 * t, ctx->dCvar.as<double>() + p0));
     }
-    {
+    if (ctx->fusedMoments) {
         KScope ks(ctx, MCP_K_SELECT);
         k_moments_finalize<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), P, ctx->F, N,
                                                                             ctx->dPart.as<double>(), nparts, nparts,
                                                                             ctx->dMean.as<double>(), ctx->dVar.as<double>());
         MCP_TRY(check_launch(ctx, "k_moments_finalize"));
-    }
+    } else
+        MCP_TRY(run_moments_linear(ctx));
     return MCP_OK;
 }
 

@@ -78,7 +78,7 @@ def test_run_matches_oracle(ctx, shape):
     check_against_oracle(ctx, E, S, alpha)
 
 
-@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize"])
+@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments"])
 def test_alternate_kernel_paths_agree(ctx, opt):
     """F = 32 normally takes the streaming kernels + bitmap compaction; the dense tile + single selection and
     the sort-based breach list must give identical results."""
