@@ -609,16 +609,24 @@ __global__ void __launch_bounds__(256) k_moments_finalize(const double *E, const
 // updates took 30 % of the valuation kernel).  The fused per-trial reduction stays available (option
 // "fused_moments") and both are held to 1e-9 against the oracle's long-double per-trial reduction.
 constexpr int GM_THREADS = 256;
-constexpr int GM_ROWS = 256; // scenario rows per CTA
+constexpr int GM_ROWS = 1024; // scenario rows per CTA
 
-// column sums of S over this CTA's rows -> partial[b][F]
+// column sums of S over this CTA's rows -> partial[b][F]; row-major reads stay coalesced
 __global__ void __launch_bounds__(GM_THREADS) k_col_sums(const double *__restrict__ S, int64_t N, int F, double *__restrict__ partial)
 {
+    __shared__ double red[GM_THREADS];
     const int64_t r0 = (int64_t)blockIdx.x * GM_ROWS, r1 = min(N, r0 + GM_ROWS);
-    for (int k = threadIdx.x; k < F; k += GM_THREADS) {
-        double acc = 0.0;
-        for (int64_t r = r0; r < r1; ++r) acc += S[r * F + k];
-        partial[(int64_t)blockIdx.x * F + k] = acc;
+    const int per = GM_THREADS / F;      // row lanes
+    const int k = threadIdx.x % F, j = threadIdx.x / F;
+    double acc = 0.0;
+    if (j < per)
+        for (int64_t r = r0 + j; r < r1; r += per) acc += S[r * F + k];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < F) {
+        double t = 0.0;
+        for (int q = 0; q < per; ++q) t += red[q * F + threadIdx.x];
+        partial[(int64_t)blockIdx.x * F + threadIdx.x] = t;
     }
 }
 
@@ -676,27 +684,31 @@ __global__ void k_gram_reduce(const double *partial, int nb, int FF, int64_t N, 
     cov[e] = acc / (double)N;
 }
 
-// one warp per portfolio: mean = E.mu, variance = E^T Cov E
+// one warp per portfolio: mean = E.mu, variance = E^T Cov E  (Cov and mu staged in shared memory)
 __global__ void __launch_bounds__(256) k_moments_linear(const double *__restrict__ E, int64_t P, int F, const double *__restrict__ mu,
                                                         const double *__restrict__ cov, double *mean, double *variance)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (p >= P) return;
-    const double *e = E + p * F;
-    double m = 0.0, v = 0.0;
-    for (int k = lane; k < F; k += 32) {
-        const double ek = e[k];
-        m = fma(ek, mu[k], m);
-        double row = 0.0;
-        for (int l = 0; l < F; ++l) row = fma(cov[k * F + l], e[l], row);
-        v = fma(ek, row, v);
+    extern __shared__ double ml_s[]; // [F*F + F]
+    for (int i = threadIdx.x; i < F * F; i += 256) ml_s[i] = cov[i];
+    for (int i = threadIdx.x; i < F; i += 256) ml_s[F * F + i] = mu[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < P; p += (int64_t)gridDim.x * 8) {
+        const double *e = E + p * F;
+        double m = 0.0, v = 0.0;
+        for (int k = lane; k < F; k += 32) {
+            const double ek = e[k];
+            m = fma(ek, ml_s[F * F + k], m);
+            double row = 0.0;
+            for (int l = 0; l < F; ++l) row = fma(ml_s[l * F + k], e[l], row); // Cov is symmetric: column read = conflict-free
+            v = fma(ek, row, v);
+        }
+        for (int d = 16; d; d >>= 1) {
+            m += __shfl_down_sync(kFullMask, m, d);
+            v += __shfl_down_sync(kFullMask, v, d);
+        }
+        if (lane == 0) { mean[p] = m; variance[p] = v; }
     }
-    for (int d = 16; d; d >>= 1) {
-        m += __shfl_down_sync(kFullMask, m, d);
-        v += __shfl_down_sync(kFullMask, v, d);
-    }
-    if (lane == 0) { mean[p] = m; variance[p] = v; }
 }
 
 // ============================================================ selection
@@ -866,12 +878,128 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         __syncthreads();
     }
     const int Ms = (int)M;
-    auto for_each = [&](auto f) {
-        if (staged) {
-            for (int i = tid; i < Ms; i += SEL_THREADS) f(skey[i], sidx[i]);
-        } else
-            for_each_global(a, row, segoff, f);
-    };
+    if (staged) {
+        // ===== fast path: the row's candidates sit in shared memory.  Range-adaptive radix select: histogram the
+        // keys on 2048 equal-width bins of the CURRENT [lo, hi] range (not on raw bit fields), so one pass usually
+        // isolates a boundary bin of a handful of elements; repeat on that bin's range until it holds <= SEL_SORT.
+        __shared__ uint64_t s_lo, s_hi;
+        __shared__ uint64_t s_red[2 * (SEL_THREADS / 32)];
+        // --- min / max key
+        uint64_t mn = ~0ull, mx = 0;
+        for (int i = tid; i < Ms; i += SEL_THREADS) { const uint64_t k = skey[i]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+        for (int d = 16; d; d >>= 1) {
+            const uint64_t a1 = __shfl_xor_sync(kFullMask, mn, d), b1 = __shfl_xor_sync(kFullMask, mx, d);
+            mn = a1 < mn ? a1 : mn; mx = b1 > mx ? b1 : mx;
+        }
+        if (lane == 0) { s_red[warp] = mn; s_red[SEL_THREADS / 32 + warp] = mx; }
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t lo = ~0ull, hi = 0;
+            for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = s_red[w] < lo ? s_red[w] : lo; hi = s_red[SEL_THREADS / 32 + w] > hi ? s_red[SEL_THREADS / 32 + w] : hi; }
+            s_lo = lo; s_hi = hi;
+        }
+        __syncthreads();
+        int64_t need = t;
+        int bucket = 0;
+        bool on_idx = false;      // ties: more than SEL_SORT candidates share one loss value -> continue on the trial index
+        uint64_t kstar = 0;       // that loss key
+        uint64_t lo = s_lo, hi = s_hi; // current range (of keys, or of trial indices when on_idx)
+        uint64_t blo = lo, bhi = hi;   // boundary bin
+        for (int pass = 0; pass < 16; ++pass) {
+            const uint64_t width = hi - lo;
+            const int shift = width < (uint64_t)SEL_BINS ? 0 : (64 - __clzll((long long)width)) - SEL_BITS;
+            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
+            __syncthreads();
+            for (int i = tid; i < Ms; i += SEL_THREADS) {
+                const uint64_t k = skey[i];
+                if (on_idx) { if (k == kstar) { const uint64_t v = sidx[i]; if (v >= lo && v <= hi) atomicAdd(&hist[(int)((v - lo) >> shift)], 1); } }
+                else if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+            }
+            __syncthreads();
+            {
+                constexpr int PER = SEL_BINS / SEL_THREADS;
+                const int hb = SEL_BINS - 1 - tid * PER; // thread 0 owns the highest bins
+                int sum = 0;
+#pragma unroll
+                for (int j = 0; j < PER; ++j) sum += hist[hb - j];
+                int incl = sum;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(kFullMask, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (lane == 31) s_wsum[warp] = incl;
+                __syncthreads();
+                int woff = 0;
+                for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+                incl += woff;
+                const int excl = incl - sum;
+                if ((int64_t)excl < need && need <= (int64_t)incl) {
+                    int above = excl;
+                    for (int j = 0; j < PER; ++j) {
+                        const int h = hist[hb - j];
+                        if (need <= (int64_t)above + h) { s_sel = hb - j; s_above = above; s_bucket = h; break; }
+                        above += h;
+                    }
+                }
+            }
+            __syncthreads();
+            need -= s_above;
+            bucket = s_bucket;
+            blo = lo + ((uint64_t)s_sel << shift);
+            bhi = shift == 0 ? blo : blo + ((1ull << shift) - 1);
+            if (bhi > hi) bhi = hi;
+            __syncthreads();
+            if (bucket <= SEL_SORT) break;
+            if (shift == 0) {
+                // a single value holds more than SEL_SORT candidates
+                if (on_idx) break; // cannot happen: trial indices are distinct
+                on_idx = true;
+                kstar = blo;
+                lo = 0; hi = 0xffffffffull;
+            } else { lo = blo; hi = bhi; }
+        }
+        // --- gather: above the boundary bin -> kept; inside it -> the small bucket
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+        for (int i = tid; i < Ms; i += SEL_THREADS) {
+            const uint64_t k = skey[i];
+            const uint32_t id = sidx[i];
+            int rel; // +1 above, 0 inside, -1 below
+            if (!on_idx) rel = k > bhi ? 1 : (k >= blo ? 0 : -1);
+            else if (k != kstar) rel = k > kstar ? 1 : -1;
+            else rel = (uint64_t)id > bhi ? 1 : ((uint64_t)id >= blo ? 0 : -1);
+            if (rel > 0) {
+                const int o = atomicAdd(&s_nkept, 1);
+                kk[o] = k;
+                ki[o] = (int32_t)id;
+            } else if (rel == 0) {
+                const int o = atomicAdd(&s_ncand, 1);
+                ckey[o] = k;
+                cidx[o] = id;
+            }
+        }
+        __syncthreads();
+        // --- rank the bucket by (key, trial) descending: rank = number of larger elements (no barriers in the loop)
+        const int base = s_nkept; // == t - need
+        if (tid < bucket) {
+            const u128 me = comp_of(ckey[tid], cidx[tid]);
+            int rank = 0;
+            for (int j = 0; j < bucket; ++j) rank += comp_of(ckey[j], cidx[j]) > me;
+            if (rank < (int)need) {
+                kk[base + rank] = ckey[tid];
+                ki[base + rank] = (int32_t)cidx[tid];
+            }
+            if (rank == (int)need - 1) { // the need-th largest candidate is the VaR order statistic (so far)
+                const double vl = fkey_inv(ckey[tid]);
+                a.var_loss[row] = vl;
+                a.var_trial[row] = (int32_t)cidx[tid];
+                if (a.tkey) a.tkey[row] = fkey(0.0 - vl);
+            }
+        }
+        return;
+    }
+    // ===== general path: more candidates than shared memory holds; digit passes straight from global memory
+    auto for_each = [&](auto f) { for_each_global(a, row, segoff, f); };
 
     // Radix select on the 64-bit loss key first (cheap 64-bit digit extraction); the trial index only breaks ties,
     // so its digits are visited only if more than SEL_SORT candidates share one exact loss value.
@@ -1091,6 +1219,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
 
 // ============================================================ host orchestration
 struct Step { int64_t begin, end; int nsub; int sub_len; };
+constexpr int64_t kStepRatio = 4;   // trials seen grow 4x per step: fewer selection passes, ~3 tail sizes of candidates per step
 constexpr int64_t kItemTrials = 512; // target trials per CTA work item (amortises the exposure-tile prologue)
 
 // Trial schedule of the streaming path: a dense first step of ~4 tail sizes establishes each
@@ -1117,7 +1246,7 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
         nsub = (L + sl - 1) / sl;
         steps.push_back({b, e, (int)nsub, (int)sl});
         b = e;
-        len = e; // doubling: the next step is as long as everything seen so far
+        len = (kStepRatio - 1) * e; // geometric: after this step the trials seen grow by kStepRatio
     }
     return steps;
 }
@@ -1271,8 +1400,14 @@ static int run_moments_linear(mcp_ctx *ctx)
     k_col_mean<<<(F + 63) / 64, 64, 0, ctx->stream>>>(ps, nb, F, N, mu);
     k_gram_centered<<<nb, GM_THREADS, 32 * F * sizeof(double), ctx->stream>>>(ctx->dS.as<double>(), N, F, mu, pg);
     k_gram_reduce<<<(F * F + 255) / 256, 256, 0, ctx->stream>>>(pg, nb, F * F, N, cov);
-    k_moments_linear<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), P, F, mu, cov, ctx->dMean.as<double>(),
-                                                                        ctx->dVar.as<double>());
+    {
+        int64_t g = (P + 7) / 8;
+        const int64_t gmax = (int64_t)ctx->prop.multiProcessorCount * 4;
+        if (g > gmax) g = gmax;
+        const size_t sm = ((size_t)F * F + F) * sizeof(double);
+        k_moments_linear<<<(unsigned)g, 256, sm, ctx->stream>>>(ctx->dE.as<double>(), P, F, mu, cov, ctx->dMean.as<double>(),
+                                                                ctx->dVar.as<double>());
+    }
     return check_launch(ctx, "moments_linear");
 }
 
