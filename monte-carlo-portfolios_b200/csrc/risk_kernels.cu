@@ -870,11 +870,37 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     if (tid == 0) { s_ncand = 0; s_nkept = 0; }
     __syncthreads();
     if (staged) {
-        for_each_global(a, row, segoff, [&](uint64_t key, uint32_t id) {
-            const int o = atomicAdd(&s_ncand, 1);
-            skey[o] = key;
-            sidx[o] = id;
-        });
+        // deterministic slots (no atomics) so that the loads of different candidates are independent and the
+        // compiler can keep several in flight per thread
+        const int kn = (int)a.kept_n;
+        for (int i = tid; i < kn; i += SEL_THREADS) {
+            skey[i] = a.kept_key_in[row * a.tail + i];
+            sidx[i] = (uint32_t)a.kept_idx_in[row * a.tail + i];
+        }
+        const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
+        if (a.cnt) {
+            const int4 *R = reinterpret_cast<const int4 *>(rowp);
+            const int total = segoff[a.nsub];
+#pragma unroll 4
+            for (int i = tid; i < total; i += SEL_THREADS) {
+                int lo = 0, hi = a.nsub; // largest seg with segoff[seg] <= i
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (segoff[mid] <= i) lo = mid; else hi = mid;
+                }
+                const int4 rec = __ldg(R + (int64_t)lo * a.sub_len + (i - segoff[lo]));
+                skey[kn + i] = fkey(0.0 - __hiloint2double(rec.y, rec.x));
+                sidx[kn + i] = (uint32_t)rec.z;
+            }
+        } else {
+            const double *V = reinterpret_cast<const double *>(rowp);
+            const int total = (int)a.step_len; // dense rows are contiguous: slot = trial - n_begin
+#pragma unroll 4
+            for (int i = tid; i < total; i += SEL_THREADS) {
+                skey[kn + i] = fkey(0.0 - __ldg(V + i));
+                sidx[kn + i] = (uint32_t)(a.n_begin + i);
+            }
+        }
         __syncthreads();
     }
     const int Ms = (int)M;
@@ -1118,7 +1144,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     }
 }
 
-static size_t sel_smem_bytes(int cap) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4 + (size_t)(kSelMaxSeg + 1) * 4; }
+static size_t sel_smem_bytes(int cap, int nseg) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4 + (size_t)(nseg + 2) * 4; }
 
 // ============================================================ finalize
 // Kernel (3): the kept tail -> ascending breach-trial list, and CVaR = mean tail loss.
@@ -1219,7 +1245,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
 
 // ============================================================ host orchestration
 struct Step { int64_t begin, end; int nsub; int sub_len; };
-constexpr int64_t kStepRatio = 4;   // trials seen grow 4x per step: fewer selection passes, ~3 tail sizes of candidates per step
+constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
 constexpr int64_t kItemTrials = 512; // target trials per CTA work item (amortises the exposure-tile prologue)
 
 // Trial schedule of the streaming path: a dense first step of ~4 tail sizes establishes each
@@ -1312,7 +1338,7 @@ static int risk_run_dense(mcp_ctx *ctx, int64_t t)
         {
             KScope ks(ctx, MCP_K_SELECT);
             a.cap = ctx->selCap;
-            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, sel_smem_bytes(a.cap), ctx->stream>>>(a);
+            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
             MCP_TRY(check_launch(ctx, "k_select"));
         }
         MCP_TRY(run_finalize(ctx, p1 - p0, t, a.kept_key_out, a.kept_idx_out, ctx->dBreach.as<int32_t>() + p0 * t,
@@ -1493,7 +1519,7 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             {
                 KScope ks(ctx, MCP_K_SELECT);
                 a.cap = ctx->selCap;
-                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap), ctx->stream>>>(a);
+                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
             cur ^= 1;
@@ -1529,11 +1555,11 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * t * sizeof(int32_t)));
     {
         // shared-memory staging capacity of the selection kernel: the dense first step has max(2048, 4t) candidates
-        int64_t cap = 4 * t + 256;
+        int64_t cap = 4 * t + 264; // dense first step: max(2048, 4t) rounded up to 8; later steps: t kept + ~2t new
         if (cap < 2304) cap = 2304;
         if (cap > 16384) cap = 16384; // 200 KB; larger rows select straight from global memory
         ctx->selCap = (int)cap;
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap)));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap, kSelMaxSeg)));
     }
 
     if (mma_supported(ctx->F) && !ctx->forceDense) MCP_TRY(risk_run_stream(ctx, t));
