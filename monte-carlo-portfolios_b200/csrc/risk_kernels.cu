@@ -355,7 +355,7 @@ __global__ void k_repack_scenarios(const double *__restrict__ S, int64_t N, int 
     }
 }
 
-template <int NK, bool DENSE>
+template <int NK, bool DENSE, bool MOMENTS>
 __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 {
     constexpr int F = NK * 4;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     }
     // ---- shift c_p = V[p][trial 0]: one DMMA pass over scenario rows 0..7, column 0 broadcast to the row's 4 lanes
     double cs[VM_G];
-    if (a.part) {
+    if (MOMENTS) {
         double z0[VM_G], z1[VM_G];
 #pragma unroll
         for (int g = 0; g < VM_G; ++g) { z0[g] = 0.0; z1[g] = 0.0; }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     // all 32 portfolios of the warp have a negative bound on V (a positive VaR): one unsigned compare per value
     const bool fastcmp = __all_sync(0xffffffffu, neg);
     const bool vec_ok = (a.sub_len & 1) == 0 && (a.pitch & 15) == 0;
-    const bool moments = a.part != nullptr;
+    constexpr bool moments = MOMENTS; // compile-time: even predicated-off scalar FP64 instructions cost DMMA-pipe slots
     // Scheduling.  The FP64 tensor pipe is the bound resource and scalar FP64 ops (the moments) share it, while
     // integer work from the partner warp co-issues with DMMA (profiles/microbench/dmma_coissue.cu).  So:
     //  * warps w and w+4 (same SM sub-partition) ping-pong through two named barriers: one owns the pipe
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     // ---- epilogue: per-portfolio partial moments (fixed 4-lane tree: deterministic) and segment counts
 #pragma unroll
     for (int g = 0; g < VM_G; ++g) {
-        if (a.part) {
+        if (MOMENTS) {
             double x = s1[g], y = s2[g];
             x += __shfl_xor_sync(0xffffffffu, x, 1); y += __shfl_xor_sync(0xffffffffu, y, 1);
             x += __shfl_xor_sync(0xffffffffu, x, 2); y += __shfl_xor_sync(0xffffffffu, y, 2);
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(256) k_moments_finalize(const double *E, const
 // updates took 30 % of the valuation kernel).  The fused per-trial reduction stays available (option
 // "fused_moments") and both are held to 1e-9 against the oracle's long-double per-trial reduction.
 constexpr int GM_THREADS = 256;
-constexpr int GM_ROWS = 1024; // scenario rows per CTA
+constexpr int GM_ROWS = 256;  // scenario rows per CTA
 
 // column sums of S over this CTA's rows -> partial[b][F]; row-major reads stay coalesced
 __global__ void __launch_bounds__(GM_THREADS) k_col_sums(const double *__restrict__ S, int64_t N, int F, double *__restrict__ partial)
@@ -1352,13 +1352,20 @@ static int launch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 
 {
     const bool configured = (ctx->mmaConfigured >> NK) & 1u; // per context: the attribute is per device
     if (!configured) {
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<NK>()));
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vm_smem_bytes<NK>()));
+        const int sm = (int)vm_smem_bytes<NK>();
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_value_mma<NK, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         ctx->mmaConfigured |= 1u << NK;
     }
     KScope ks(ctx, MCP_K_VALUE);
-    if (dense) k_value_mma<NK, true><<<grid, VM_THREADS, vm_smem_bytes<NK>(), ctx->stream>>>(v);
-    else k_value_mma<NK, false><<<grid, VM_THREADS, vm_smem_bytes<NK>(), ctx->stream>>>(v);
+    const size_t sm = vm_smem_bytes<NK>();
+    const bool mom = v.part != nullptr;
+    if (dense && mom) k_value_mma<NK, true, true><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
+    else if (dense) k_value_mma<NK, true, false><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
+    else if (mom) k_value_mma<NK, false, true><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
+    else k_value_mma<NK, false, false><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
     return check_launch(ctx, "k_value_mma");
 }
 
