@@ -12,5 +12,6 @@ from .codec import (BinaryPacking, Composition, FastPFOR, FastPFOR128, IntCompre
                     VariableByteCodec, default_context)
 from .engine import Context
 from .portfolio import LoadPortfolios
+from . import sharding
 
 __all__ = [n for n in dir() if not n.startswith("_")]

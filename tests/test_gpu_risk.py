@@ -197,3 +197,22 @@ def test_full_size_c2_properties(ctx):
         assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][0])
         np.testing.assert_allclose([r["mean"][p], r["variance"][p], r["cvar"][p]],
                                    [o["mean"][0], o["variance"][0], o["cvar"][0]], rtol=RTOL, atol=0)
+
+
+def test_sharded_assembly_on_gpu(ctx):
+    """The portfolio-sharding host logic with the real CUDA compute (one process; two simulated shards)."""
+    from mcp_b200 import sharding
+    E, S = riskcases.synthetic(70, 6000, 32, 31)
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    parts = []
+    for rank in range(2):
+        p0, p1 = sharding.portfolio_shard(70, rank, 2)
+        r = ctx.simulate(E[p0:p1], S, 0.99, cid, N.FRAME_APP)
+        r["range"] = (p0, p1)
+        parts.append(r)
+    whole = sharding.assemble(parts, 70)
+    one = ctx.simulate(E, S, 0.99, cid, N.FRAME_APP)
+    for k in ("var_loss", "var_trial", "breach", "enc_off", "enc", "cvar"):
+        assert np.array_equal(whole[k], one[k]), k
+    o = cref.risk(E, S, 0.99)
+    assert np.array_equal(whole["breach"], o["breach"])
