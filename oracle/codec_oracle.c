@@ -16,6 +16,16 @@
 #include <omp.h>
 #endif
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; an explicit request must win over the environment */
+static void orc_use_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) { omp_set_dynamic(0); omp_set_num_threads(n); }
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ Util */
 
 /* Util.java:101-103  bits(i) = 32 - numberOfLeadingZeros(i) */
@@ -652,6 +662,7 @@ int orc_batch_compress(int codec, int framing, const int32_t *vals, const int64_
 {
     int bad = 0;
     (void)nthreads;
+orc_use_threads(nthreads);
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1) reduction(| : bad)
     for (int64_t i = 0; i < nlists; ++i) {
         const int64_t n = list_off[i + 1] - list_off[i];
@@ -682,6 +693,7 @@ int orc_batch_uncompress(int codec, int framing, const uint8_t *in, int64_t stri
 {
     int bad = 0;
     (void)nthreads;
+orc_use_threads(nthreads);
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1) reduction(| : bad)
     for (int64_t i = 0; i < nlists; ++i) {
         const int64_t cap = out_off[i + 1] - out_off[i];

@@ -20,6 +20,16 @@
 #include <omp.h>
 #endif
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; an explicit request must win over the environment */
+static void orc_use_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) { omp_set_dynamic(0); omp_set_num_threads(n); }
+#else
+    (void)n;
+#endif
+}
+
 /* DESIGN.md 3.1:  acc = +0.0; for k ascending: acc = fma(E[p][k], S[n][k], acc) */
 static inline double value_one(const double *e, const double *s, int32_t F)
 {
@@ -30,6 +40,7 @@ static inline double value_one(const double *e, const double *s, int32_t F)
 
 void orc_value(const double *E, const double *S, int64_t P, int64_t N, int32_t F, double *V, int nthreads)
 {
+orc_use_threads(nthreads);
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
     for (int64_t p = 0; p < P; ++p)
         for (int64_t n = 0; n < N; ++n) V[p * N + n] = value_one(E + p * F, S + n * F, F);
@@ -89,6 +100,7 @@ int64_t orc_risk(const double *E, const double *S, int64_t P, int64_t N, int32_t
     (void)P;
     const int64_t t = orc_tail_size(N, alpha);
     const int64_t k = N - t + 1; /* 1-based rank of the VaR order statistic */
+orc_use_threads(nthreads);
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
     {
         double *V = (double *)malloc((size_t)N * sizeof(double));
@@ -155,6 +167,7 @@ void orc_gen_normal(double *out, int64_t rows, int32_t cols, uint64_t seed, uint
                     double scale, double shift, int64_t row0, int nthreads)
 {
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+orc_use_threads(nthreads);
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
     for (int64_t r = 0; r < rows; ++r) {
         const uint64_t gr = (uint64_t)(row0 + r);
