@@ -88,8 +88,10 @@ int  mcp_sync(mcp_ctx *ctx);
  * path used for factor counts without a streaming kernel), "force_sort_finalize" (1 = breach list by bitonic
  * sort instead of the trial bitmap), "value_mma" (0 = mcp_value through the scalar-fma kernel instead of the FP64
  * tensor-core kernel), "fused_moments" (1 = mean/variance by a per-trial reduction fused into the valuation kernel
- * instead of by linearity, mean = E.mean(S), var = E^T Cov(S) E).  Trial indices, breach lists and byte streams are
- * identical either way, moments agree to 1e-9; only the kernels differ. */
+ * instead of by linearity, mean = E.mean(S), var = E^T Cov(S) E), "optimistic" (0 = always use the guaranteed
+ * geometric trial schedule; 1 (default) = two-step schedule with an optimistic filter bound and an exact fallback
+ * for the rows where the bet fails).  Trial indices, breach lists and byte streams are identical either way, moments
+ * agree to 1e-9; only the kernels differ. */
 int  mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value);
 
 /* Upper bound on the encoded size in BYTES of one list of n ints under `framing`
@@ -174,6 +176,9 @@ int mcp_run(mcp_ctx *ctx, double alpha, int codec_id, int framing);
 
 /* sizes of the last run */
 int mcp_run_sizes(mcp_ctx *ctx, int64_t *P, int64_t *N, int64_t *tail, int64_t *enc_bytes);
+/* diagnostics of the last run: *fallback_rows = portfolios whose optimistic filter bound was too tight and that
+ * were redone with the guaranteed schedule (0 for exchangeable trial orders; results are exact either way) */
+int mcp_run_stats(mcp_ctx *ctx, int64_t *fallback_rows);
 
 /* Fetch results of the last mcp_run (any pointer may be NULL):
  *   mean, variance (population), var_loss, cvar : double[P];  var_trial : int32[P]
@@ -198,7 +203,8 @@ enum {
     MCP_K_DECODE = 3,  /* codec decode                                  */
     MCP_K_SCAN = 4,    /* prefix sums / bookkeeping                     */
     MCP_K_GEN = 5,     /* generators, FP64 peak probe                   */
-    MCP_K_COUNT = 6
+    MCP_K_MOMENTS = 6, /* mean / variance (on a side stream: overlaps the valuation) */
+    MCP_K_COUNT = 7
 };
 int mcp_profile_enable(mcp_ctx *ctx, int on);
 int mcp_profile_reset(mcp_ctx *ctx);

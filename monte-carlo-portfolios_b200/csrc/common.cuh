@@ -88,6 +88,13 @@ struct mcp_ctx {
     mcp::DevBuf dGenVals, dGenOff; // synthetic breach lists
     mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
     mcp::DevBuf dKept2Key, dKept2Idx, dFinKey, dFinIdx;
+    mcp::DevBuf dFail;             // [0] = number of rows that failed the optimistic bound, [4..] = their indices
+    mcp::DevBuf dFbE, dFbOut, dFbKey, dFbIdx; // fallback problem (failed rows, guaranteed schedule)
+    bool optimistic = true;        // two-step schedule with the optimistic filter bound (risk_kernels.cu)
+    int64_t itemTrials = 2048;     // target trials per valuation CTA work item (amortises the exposure-tile prologue)
+    int64_t runFallbackRows = 0;   // rows the last run had to redo with the guaranteed schedule
+    cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
     int selCap = 2304;
     uint32_t mmaConfigured = 0;
@@ -137,7 +144,8 @@ struct KScope {
     mcp_ctx *ctx;
     int cls;
     cudaEvent_t a = nullptr, b = nullptr;
-    KScope(mcp_ctx *c, int k, int nlaunch = 1) : ctx(c), cls(k)
+    cudaStream_t st;
+    KScope(mcp_ctx *c, int k, int nlaunch = 1, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream)
     {
         ctx->prof.launches[cls] += nlaunch;
         if (!ctx->prof.on) return;
@@ -149,12 +157,12 @@ struct KScope {
         };
         a = get();
         b = get();
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, st);
     }
     ~KScope()
     {
         if (!a) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, st);
         ctx->prof.recs.push_back({cls, a, b});
     }
 };

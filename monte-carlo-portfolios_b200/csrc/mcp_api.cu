@@ -93,6 +93,9 @@ int mcp_create(int device, mcp_ctx **out)
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost(&ctx->hPinned, 4096) != cudaSuccess || cudaEventCreate(&ctx->tA) != cudaSuccess ||
         cudaEventCreate(&ctx->tB) != cudaSuccess) {
         cudaGetLastError();
@@ -108,6 +111,7 @@ void mcp_destroy(mcp_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     resolve_profile(ctx);
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
     mcp::DevBuf *bufs[] = {&ctx->dE, &ctx->dS, &ctx->dMean, &ctx->dVar, &ctx->dVarLoss, &ctx->dVarTrial, &ctx->dCvar,
@@ -115,11 +119,15 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
-                           &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram};
+                           &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
+                           &ctx->dFbKey, &ctx->dFbIdx};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
     if (ctx->tB) cudaEventDestroy(ctx->tB);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -141,6 +149,8 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "force_sort_finalize")) ctx->forceSortFinalize = value != 0;
     else if (!strcmp(key, "value_mma")) ctx->valueMma = value != 0;
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
+    else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
+    else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
 }
@@ -425,6 +435,14 @@ int mcp_run_sizes(mcp_ctx *ctx, int64_t *P, int64_t *N, int64_t *tail, int64_t *
     if (N) *N = ctx->runN;
     if (tail) *tail = ctx->runTail;
     if (enc_bytes) *enc_bytes = ctx->runEncBytes;
+    return MCP_OK;
+}
+
+int mcp_run_stats(mcp_ctx *ctx, int64_t *fallback_rows)
+{
+    if (!ctx) return MCP_E_ARG;
+    if (!ctx->haveRun) return fail(ctx, MCP_E_STATE, "run_stats: no completed run");
+    if (fallback_rows) *fallback_rows = ctx->runFallbackRows;
     return MCP_OK;
 }
 

@@ -6,6 +6,7 @@
 // Bit-exactness contract: V[p][n] is ONE fma chain over k ascending starting from +0.0,
 // on both sides, so every loss is bit-identical to the oracle's and the selected trial
 // indices are exact.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -719,7 +720,8 @@ constexpr int SEL_THREADS = 256;
 constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS; // 11-bit digits over the 96-bit composite (key64, trial32), MSB first
 constexpr int SEL_SORT = 256;           // keep refining digits until the boundary bucket is at most this big
-constexpr int SEL_NPASS = (96 + SEL_BITS - 1) / SEL_BITS;
+constexpr int FS_BITS = 10, FS_BINS = 1 << FS_BITS; // staged fast path: bins per range-adaptive pass
+constexpr int FS_SORT = 96;                        // ... and the bucket size its rank sort takes
 constexpr int kSelMaxSeg = 4096;         // most segments (4 per sub-chunk) a sparse step may have
 
 // Candidates of one portfolio row = the previously kept tail (key, trial) plus this step's
@@ -735,7 +737,7 @@ struct SelArgs {
     int64_t n_begin;
     const uint64_t *kept_key_in;
     const int32_t *kept_idx_in;
-    int64_t kept_n;            // 0 or tail
+    int64_t kept_n;            // entries (= row stride) of the kept_*_in rows; 0 on the first step
     uint64_t *kept_key_out;    // [rows][tail]
     int32_t *kept_idx_out;
     int64_t tail;              // t
@@ -745,6 +747,9 @@ struct SelArgs {
     int32_t *var_trial;
     uint64_t *tkey;            // [rows] fkey(0.0 - var_loss): the next step's filter bound on V
     int cap;                   // shared-memory candidate capacity (entries)
+    int *fail_cnt;             // optimistic bound (see risk_run_stream): rows with fewer than `tail` candidates are
+    int32_t *fail_rows;        // appended here (row index) and redone by the guaranteed schedule; null otherwise
+    int64_t row_base;          // global index of row 0 (for fail_rows)
 };
 
 __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
@@ -771,7 +776,7 @@ template <class Fn>
 __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, const int *segoff, Fn f)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.tail + i], (uint32_t)a.kept_idx_in[row * a.tail + i]);
+    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.kept_n + i], (uint32_t)a.kept_idx_in[row * a.kept_n + i]);
     const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
     if (a.cnt) {
         // sparse step: many short lane-private segments of 16-byte records.  Flat index over all their entries
@@ -815,7 +820,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     __shared__ uint32_t cidx[SEL_SORT];
     __shared__ double red[32];
     __shared__ int s_wsum[SEL_THREADS / 32];
-    __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept, s_total;
+    __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept;
     const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
     uint64_t *kk = a.kept_key_out + row * t;
@@ -845,74 +850,77 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     // ---- how many candidates does this row have?  stage them if they fit
     int64_t M;
     if (a.cnt) {
+        // exclusive prefix of the segment counts: coalesced load, every thread scans a contiguous run, block scan
         for (int sgi = tid; sgi < a.nsub; sgi += SEL_THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
         if (tid == 0) segoff[0] = 0;
         __syncthreads();
-        if (warp == 0) { // inclusive scan, 32 segments per round
-            int run = 0;
-            for (int base = 0; base < a.nsub; base += 32) {
-                const int i = base + lane;
-                const int v = i < a.nsub ? segoff[i + 1] : 0;
-                int incl = v;
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int u = __shfl_up_sync(kFullMask, incl, d);
-                    if (lane >= d) incl += u;
-                }
-                if (i < a.nsub) segoff[i + 1] = run + incl;
-                run += __shfl_sync(kFullMask, incl, 31);
-            }
+        const int per = (a.nsub + SEL_THREADS - 1) / SEL_THREADS;
+        const int g0 = min(a.nsub, tid * per), g1 = min(a.nsub, g0 + per);
+        int c = 0;
+        for (int g = g0; g < g1; ++g) c += segoff[g + 1];
+        int incl = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= d) incl += u;
         }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int run = incl - c;
+        for (int w = 0; w < warp; ++w) run += s_wsum[w];
+        for (int g = g0; g < g1; ++g) { run += segoff[g + 1]; segoff[g + 1] = run; } // inclusive at g+1 == exclusive of g+1
         __syncthreads();
         M = a.kept_n + segoff[a.nsub];
     } else
         M = a.kept_n + a.step_len;
+    if (M < t) {
+        // Only possible under an optimistic filter bound that turned out too tight for this row: report the row
+        // (it is redone with the guaranteed schedule) and mark its kept list so that the finalize kernel skips it.
+        if (tid == 0) {
+            ki[0] = -1;
+            if (a.fail_cnt) a.fail_rows[atomicAdd(a.fail_cnt, 1)] = (int32_t)(a.row_base + row);
+        }
+        return;
+    }
     const bool staged = M <= a.cap;
     if (tid == 0) { s_ncand = 0; s_nkept = 0; }
     __syncthreads();
+    const int Ms = (int)M;
     if (staged) {
-        // deterministic slots (no atomics) so that the loads of different candidates are independent and the
-        // compiler can keep several in flight per thread
+        // ===== fast path: stage the row's candidates ONCE in shared memory (deterministic slots, independent
+        // loads), tracking the key range on the way.
+        __shared__ uint64_t s_lo, s_hi;
+        __shared__ uint64_t s_red[2 * (SEL_THREADS / 32)];
+        uint64_t mn = ~0ull, mx = 0;
+        auto put = [&](int slot, uint64_t k, uint32_t id) {
+            skey[slot] = k; sidx[slot] = id;
+            mn = k < mn ? k : mn; mx = k > mx ? k : mx;
+        };
         const int kn = (int)a.kept_n;
-        for (int i = tid; i < kn; i += SEL_THREADS) {
-            skey[i] = a.kept_key_in[row * a.tail + i];
-            sidx[i] = (uint32_t)a.kept_idx_in[row * a.tail + i];
-        }
+        for (int i = tid; i < kn; i += SEL_THREADS) put(i, a.kept_key_in[row * a.kept_n + i], (uint32_t)a.kept_idx_in[row * a.kept_n + i]);
         const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
         if (a.cnt) {
+            // sparse step: ~3 records in each of several hundred lane-private segments.  Phase 1: every thread labels
+            // the slots of its own segments with the segment id (shared memory only); phase 2: a flat, unrolled loop
+            // over the slots issues the 16-byte record loads independently of one another.
+            const int per = (a.nsub + SEL_THREADS - 1) / SEL_THREADS;
+            const int g0 = min(a.nsub, tid * per), g1 = min(a.nsub, g0 + per);
+            for (int g = g0; g < g1; ++g)
+                for (int j = segoff[g]; j < segoff[g + 1]; ++j) sidx[kn + j] = (uint32_t)g;
+            __syncthreads();
             const int4 *R = reinterpret_cast<const int4 *>(rowp);
             const int total = segoff[a.nsub];
 #pragma unroll 4
             for (int i = tid; i < total; i += SEL_THREADS) {
-                int lo = 0, hi = a.nsub; // largest seg with segoff[seg] <= i
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (segoff[mid] <= i) lo = mid; else hi = mid;
-                }
-                const int4 rec = __ldg(R + (int64_t)lo * a.sub_len + (i - segoff[lo]));
-                skey[kn + i] = fkey(0.0 - __hiloint2double(rec.y, rec.x));
-                sidx[kn + i] = (uint32_t)rec.z;
+                const int g = (int)sidx[kn + i];
+                const int4 rec = __ldg(R + (int64_t)g * a.sub_len + (i - segoff[g]));
+                put(kn + i, fkey(0.0 - __hiloint2double(rec.y, rec.x)), (uint32_t)rec.z);
             }
         } else {
             const double *V = reinterpret_cast<const double *>(rowp);
             const int total = (int)a.step_len; // dense rows are contiguous: slot = trial - n_begin
 #pragma unroll 4
-            for (int i = tid; i < total; i += SEL_THREADS) {
-                skey[kn + i] = fkey(0.0 - __ldg(V + i));
-                sidx[kn + i] = (uint32_t)(a.n_begin + i);
-            }
+            for (int i = tid; i < total; i += SEL_THREADS) put(kn + i, fkey(0.0 - __ldg(V + i)), (uint32_t)(a.n_begin + i));
         }
-        __syncthreads();
-    }
-    const int Ms = (int)M;
-    if (staged) {
-        // ===== fast path: the row's candidates sit in shared memory.  Range-adaptive radix select: histogram the
-        // keys on 2048 equal-width bins of the CURRENT [lo, hi] range (not on raw bit fields), so one pass usually
-        // isolates a boundary bin of a handful of elements; repeat on that bin's range until it holds <= SEL_SORT.
-        __shared__ uint64_t s_lo, s_hi;
-        __shared__ uint64_t s_red[2 * (SEL_THREADS / 32)];
-        // --- min / max key
-        uint64_t mn = ~0ull, mx = 0;
-        for (int i = tid; i < Ms; i += SEL_THREADS) { const uint64_t k = skey[i]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
         for (int d = 16; d; d >>= 1) {
             const uint64_t a1 = __shfl_xor_sync(kFullMask, mn, d), b1 = __shfl_xor_sync(kFullMask, mx, d);
             mn = a1 < mn ? a1 : mn; mx = b1 > mx ? b1 : mx;
@@ -925,16 +933,19 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             s_lo = lo; s_hi = hi;
         }
         __syncthreads();
+        // Range-adaptive radix select: histogram the keys on FS_BINS equal-width bins of the CURRENT [lo, hi] range
+        // (not on raw bit fields), so one pass usually isolates a boundary bin of a handful of elements; repeat on
+        // that bin's range until it holds <= FS_SORT.
         int64_t need = t;
         int bucket = 0;
-        bool on_idx = false;      // ties: more than SEL_SORT candidates share one loss value -> continue on the trial index
+        bool on_idx = false;      // ties: more than FS_SORT candidates share one loss value -> continue on the trial index
         uint64_t kstar = 0;       // that loss key
         uint64_t lo = s_lo, hi = s_hi; // current range (of keys, or of trial indices when on_idx)
         uint64_t blo = lo, bhi = hi;   // boundary bin
         for (int pass = 0; pass < 16; ++pass) {
             const uint64_t width = hi - lo;
-            const int shift = width < (uint64_t)SEL_BINS ? 0 : (64 - __clzll((long long)width)) - SEL_BITS;
-            for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
+            const int shift = width < (uint64_t)FS_BINS ? 0 : (64 - __clzll((long long)width)) - FS_BITS;
+            for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
             __syncthreads();
             for (int i = tid; i < Ms; i += SEL_THREADS) {
                 const uint64_t k = skey[i];
@@ -943,8 +954,8 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             }
             __syncthreads();
             {
-                constexpr int PER = SEL_BINS / SEL_THREADS;
-                const int hb = SEL_BINS - 1 - tid * PER; // thread 0 owns the highest bins
+                constexpr int PER = FS_BINS / SEL_THREADS;
+                const int hb = FS_BINS - 1 - tid * PER; // thread 0 owns the highest bins
                 int sum = 0;
 #pragma unroll
                 for (int j = 0; j < PER; ++j) sum += hist[hb - j];
@@ -975,31 +986,44 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             bhi = shift == 0 ? blo : blo + ((1ull << shift) - 1);
             if (bhi > hi) bhi = hi;
             __syncthreads();
-            if (bucket <= SEL_SORT) break;
+            if (bucket <= FS_SORT) break;
             if (shift == 0) {
-                // a single value holds more than SEL_SORT candidates
+                // a single value holds more than FS_SORT candidates
                 if (on_idx) break; // cannot happen: trial indices are distinct
                 on_idx = true;
                 kstar = blo;
                 lo = 0; hi = 0xffffffffull;
             } else { lo = blo; hi = bhi; }
         }
-        // --- gather: above the boundary bin -> kept; inside it -> the small bucket
-        if (tid == 0) s_ncand = 0;
-        __syncthreads();
-        for (int i = tid; i < Ms; i += SEL_THREADS) {
-            const uint64_t k = skey[i];
-            const uint32_t id = sidx[i];
-            int rel; // +1 above, 0 inside, -1 below
-            if (!on_idx) rel = k > bhi ? 1 : (k >= blo ? 0 : -1);
-            else if (k != kstar) rel = k > kstar ? 1 : -1;
-            else rel = (uint64_t)id > bhi ? 1 : ((uint64_t)id >= blo ? 0 : -1);
+        // --- gather: above the boundary bin -> kept; inside it -> the small bucket.  Warp-aggregated slot claims
+        // (one shared-memory atomic per warp and round, not one per element)
+        for (int base = 0; base < Ms; base += SEL_THREADS) {
+            const int i = base + tid;
+            int rel = -1; // +1 above, 0 inside, -1 below / out of range
+            uint64_t k = 0;
+            uint32_t id = 0;
+            if (i < Ms) {
+                k = skey[i];
+                id = sidx[i];
+                if (!on_idx) rel = k > bhi ? 1 : (k >= blo ? 0 : -1);
+                else if (k != kstar) rel = k > kstar ? 1 : -1;
+                else rel = (uint64_t)id > bhi ? 1 : ((uint64_t)id >= blo ? 0 : -1);
+            }
+            const unsigned mk = __ballot_sync(kFullMask, rel > 0), mc = __ballot_sync(kFullMask, rel == 0);
+            int bk = 0, bc = 0;
+            if (lane == 0) {
+                if (mk) bk = atomicAdd(&s_nkept, __popc(mk));
+                if (mc) bc = atomicAdd(&s_ncand, __popc(mc));
+            }
+            bk = __shfl_sync(kFullMask, bk, 0);
+            bc = __shfl_sync(kFullMask, bc, 0);
+            const unsigned lt = (1u << lane) - 1u;
             if (rel > 0) {
-                const int o = atomicAdd(&s_nkept, 1);
+                const int o = bk + __popc(mk & lt);
                 kk[o] = k;
                 ki[o] = (int32_t)id;
             } else if (rel == 0) {
-                const int o = atomicAdd(&s_ncand, 1);
+                const int o = bc + __popc(mc & lt);
                 ckey[o] = k;
                 cidx[o] = id;
             }
@@ -1152,7 +1176,9 @@ static size_t sel_smem_bytes(int cap, int nseg) { return (size_t)cap * 12 + (siz
 // trial, prefix-sum the word popcounts, then every set bit knows its rank.  (Falls back to a
 // bitonic sort by trial index when the trial range does not fit the bitmap.)
 constexpr int FIN_THREADS = 256;
-constexpr int64_t FIN_BITMAP_MAX_TRIALS = 1400000; // 175 KB of bitmap + scan scratch
+// shared memory of k_finalize_bitmap: bitmap + per-word prefix (N/4 bytes) + the tail's losses in list order (8 t bytes)
+static size_t fin_bitmap_smem(int64_t n_trials, int64_t t) { return (size_t)((n_trials + 31) / 32) * 8 + (size_t)t * 8; }
+constexpr size_t FIN_BITMAP_MAX_SMEM = 200 * 1024;
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
                                                                  int64_t n_trials, int32_t trial_base, int32_t *breach,
@@ -1161,24 +1187,23 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap(const uint64_t 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ int s_wsum[FIN_THREADS / 32];
-    uint32_t *bm = reinterpret_cast<uint32_t *>(smem_raw);
     const int nwords = (int)((n_trials + 31) >> 5);
+    double *sl = reinterpret_cast<double *>(smem_raw);               // [t] losses in ascending-trial order
+    uint32_t *bm = reinterpret_cast<uint32_t *>(sl + t);             // [nwords] one bit per kept trial
+    int *pre = reinterpret_cast<int *>(bm + nwords);                 // [nwords] kept trials before this word
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (kept_idx[row * t] < 0) return; // row failed its optimistic bound: redone separately (k_select)
     for (int i = tid; i < nwords; i += FIN_THREADS) bm[i] = 0;
     __syncthreads();
-    double s = 0.0;
     for (int i = tid; i < t; i += FIN_THREADS) {
         const int32_t id = kept_idx[row * t + i] - trial_base;
         atomicOr(&bm[id >> 5], 1u << (id & 31));
-        s += fkey_inv(kept_key[row * t + i]);
     }
-    s = block_sum(s, red);
-    if (tid == 0) cvar[row] = s / (double)t;
     __syncthreads();
-    // each thread owns a contiguous run of words
+    // exclusive prefix of the word popcounts: each thread owns a contiguous run of words
     const int per = (nwords + FIN_THREADS - 1) / FIN_THREADS;
-    const int w0 = tid * per, w1 = min(nwords, w0 + per);
+    const int w0 = min(nwords, tid * per), w1 = min(nwords, w0 + per);
     int c = 0;
     for (int w = w0; w < w1; ++w) c += __popc(bm[w]);
     int incl = c;
@@ -1190,15 +1215,24 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap(const uint64_t 
     __syncthreads();
     int off = incl - c;
     for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    for (int w = w0; w < w1; ++w) { pre[w] = off; off += __popc(bm[w]); }
+    __syncthreads();
+    // every kept trial knows its rank in the ascending list: emit the trial and park its loss at that rank
     int32_t *dst = breach + row * t;
-    for (int w = w0; w < w1; ++w) {
-        uint32_t m = bm[w];
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            dst[off++] = trial_base + (w << 5) + b;
-        }
+    for (int i = tid; i < t; i += FIN_THREADS) {
+        const int32_t gid = kept_idx[row * t + i];
+        const int32_t id = gid - trial_base;
+        const int rank = pre[id >> 5] + __popc(bm[id >> 5] & ((1u << (id & 31)) - 1u));
+        dst[rank] = gid;
+        sl[rank] = fkey_inv(kept_key[row * t + i]);
     }
+    __syncthreads();
+    // CVaR = mean tail loss, summed in list order with a fixed tree: bit-reproducible whatever order the
+    // selection kernel's atomics left the kept tail in
+    double s = 0.0;
+    for (int i = tid; i < t; i += FIN_THREADS) s += sl[i];
+    s = block_sum(s, red);
+    if (tid == 0) cvar[row] = s / (double)t;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
@@ -1208,6 +1242,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
     const int64_t row = blockIdx.x;
+    if (kept_idx[row * t] < 0) return; // row failed its optimistic bound: redone separately (k_select)
     uint64_t *sk;
     int32_t *si;
     if (gkey) { sk = gkey + row * m; si = gidx + row * m; }
@@ -1246,20 +1281,27 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
 // ============================================================ host orchestration
 struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
-constexpr int64_t kItemTrials = 512; // target trials per CTA work item (amortises the exposure-tile prologue)
 
-// Trial schedule of the streaming path: a dense first step of ~4 tail sizes establishes each
-// portfolio's threshold, then steps double in length; every later step inserts ~tail candidates.
-static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sms)
+// length of the dense first step: ~4 tail sizes, at least 2048 trials, a multiple of 8 (tensor-core trial blocks)
+static int64_t first_step_len(int64_t N, int64_t t)
 {
-    std::vector<Step> steps;
     int64_t c0 = 4 * t;
     if (c0 < 2048) c0 = 2048;
-    c0 = (c0 + 7) & ~(int64_t)7; // step boundaries stay multiples of 8 (tensor-core trial blocks)
+    c0 = (c0 + 7) & ~(int64_t)7;
+    return c0 < N ? c0 : N;
+}
+
+// Trial schedule of the streaming path.  Guaranteed: a dense first step of ~4 tail sizes establishes each
+// portfolio's threshold, then steps grow 3x; every later step inserts ~2 tail sizes of candidates.  Optimistic
+// (`two_step`): the dense first step, then ONE sparse step over all remaining trials (see optimistic_rank).
+static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sms, bool two_step = false, int64_t kItemTrials = 2048)
+{
+    std::vector<Step> steps;
+    const int64_t c0 = first_step_len(N, t);
     int64_t b = 0, len = c0;
     while (b < N) {
         int64_t e = b + len;
-        if (e > N || (b > 0 && N - e < len / 4)) e = N; // fold a short remainder into the last (sparse) step
+        if (e > N || (b > 0 && (two_step || N - e < len / 4))) e = N; // fold a short remainder into the last (sparse) step
         const int64_t L = e - b;
         int64_t waves = (L * nsg + (int64_t)sms * kItemTrials / 2) / ((int64_t)sms * kItemTrials);
         if (waves < 1) waves = 1;
@@ -1279,8 +1321,8 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
 
 static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *kk, const int32_t *ki, int32_t *breach, double *cvar)
 {
-    if (ctx->N <= FIN_BITMAP_MAX_TRIALS && !ctx->forceSortFinalize) {
-        const size_t bm_smem = (size_t)((ctx->N + 31) / 32) * 4;
+    if (fin_bitmap_smem(ctx->N, t) <= FIN_BITMAP_MAX_SMEM && !ctx->forceSortFinalize) {
+        const size_t bm_smem = fin_bitmap_smem(ctx->N, t);
         if (bm_smem > 48 * 1024)
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
         KScope ks(ctx, MCP_K_SELECT);
@@ -1428,37 +1470,83 @@ static int run_moments_linear(mcp_ctx *ctx)
     const int nb = (int)((N + GM_ROWS - 1) / GM_ROWS);
     MCP_CUDA(ctx, ctx->dGram.reserve(((size_t)nb * F * F + (size_t)nb * F + (size_t)F * F + F) * sizeof(double)));
     double *pg = ctx->dGram.as<double>(), *ps = pg + (size_t)nb * F * F, *cov = ps + (size_t)nb * F, *mu = cov + (size_t)F * F;
-    KScope ks(ctx, MCP_K_SELECT, 5);
-    k_col_sums<<<nb, GM_THREADS, 0, ctx->stream>>>(ctx->dS.as<double>(), N, F, ps);
-    k_col_mean<<<(F + 63) / 64, 64, 0, ctx->stream>>>(ps, nb, F, N, mu);
-    k_gram_centered<<<nb, GM_THREADS, 32 * F * sizeof(double), ctx->stream>>>(ctx->dS.as<double>(), N, F, mu, pg);
-    k_gram_reduce<<<(F * F + 255) / 256, 256, 0, ctx->stream>>>(pg, nb, F * F, N, cov);
+    cudaStream_t st = ctx->stream2; // forked from / joined to ctx->stream by risk_run
+    KScope ks(ctx, MCP_K_MOMENTS, 5, st);
+    k_col_sums<<<nb, GM_THREADS, 0, st>>>(ctx->dS.as<double>(), N, F, ps);
+    k_col_mean<<<(F + 63) / 64, 64, 0, st>>>(ps, nb, F, N, mu);
+    k_gram_centered<<<nb, GM_THREADS, 32 * F * sizeof(double), st>>>(ctx->dS.as<double>(), N, F, mu, pg);
+    k_gram_reduce<<<(F * F + 255) / 256, 256, 0, st>>>(pg, nb, F * F, N, cov);
     {
         int64_t g = (P + 7) / 8;
         const int64_t gmax = (int64_t)ctx->prop.multiProcessorCount * 4;
         if (g > gmax) g = gmax;
         const size_t sm = ((size_t)F * F + F) * sizeof(double);
-        k_moments_linear<<<(unsigned)g, 256, sm, ctx->stream>>>(ctx->dE.as<double>(), P, F, mu, cov, ctx->dMean.as<double>(),
+        k_moments_linear<<<(unsigned)g, 256, sm, st>>>(ctx->dE.as<double>(), P, F, mu, cov, ctx->dMean.as<double>(),
                                                                 ctx->dVar.as<double>());
     }
     return check_launch(ctx, "moments_linear");
 }
 
-// streaming valuation (FP64 tensor cores) + threshold filter + incremental radix-select
-static int risk_run_stream(mcp_ctx *ctx, int64_t t)
+// ---- optimistic filter bound
+// The guaranteed schedule (make_schedule) filters step i+1 with the exact t-th largest loss of the trials seen so
+// far: always sound, but it needs log_3(N / 4t) valuation launches and as many selection passes.  For trials in an
+// exchangeable order (Monte Carlo draws are) a far better bound is available after the dense first step alone: the
+// r-th largest loss of the n0-trial sample, r = ts + 7 sqrt(ts) + 2 with ts = t n0 / N the sample's expected share of
+// the tail.  The number of the other N - n0 trials above it is negative-hypergeometric; fewer than t - r of them --
+// the only way the bound can be too tight -- has probability < 1e-10 per portfolio for the configurations of
+// BASELINE.json (C2: r = 87 of 4 004, about 2.2 t candidates).  The bound is a bet, never a correctness assumption:
+// k_select counts every row's candidates, rows with fewer than t are collected (`fail_rows`), re-run through the
+// guaranteed schedule on a gathered copy of their exposures and scattered back, so the result is exact for ANY trial
+// order (descending-loss order makes every row fail; the tests do exactly that).
+static int64_t optimistic_rank(int64_t N, int64_t n0, int64_t t)
 {
-    const int64_t P = ctx->P, N = ctx->N;
+    const double ts = (double)t * (double)n0 / (double)N;
+    return (int64_t)ceil(ts + 7.0 * sqrt(ts) + 2.0);
+}
+
+// rows of E selected by `rows` -> a compact matrix (fallback of the optimistic bound)
+__global__ void k_gather_rows(const double *__restrict__ E, const int32_t *__restrict__ rows, int64_t n, int F, double *__restrict__ out)
+{
+    const int64_t total = n * F;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = E[(int64_t)rows[i / F] * F + i % F];
+}
+
+// results of the compact fallback problem -> their rows in the full result arrays (one CTA per row)
+__global__ void k_scatter_rows(const int32_t *__restrict__ rows, int64_t t, const double *vl, const int32_t *vt, const double *cv,
+                               const int32_t *br, double *var_loss, int32_t *var_trial, double *cvar, int32_t *breach)
+{
+    const int64_t i = blockIdx.x, r = rows[i];
+    if (threadIdx.x == 0) { var_loss[r] = vl[i]; var_trial[r] = vt[i]; cvar[r] = cv[i]; }
+    for (int64_t j = threadIdx.x; j < t; j += blockDim.x) breach[r * t + j] = br[i * t + j];
+}
+
+// One streaming problem: exposures E[P][F] (device) against the context's scenarios, results into `o`.
+struct StreamIO {
+    const double *E;
+    int64_t P;
+    double *var_loss; int32_t *var_trial; double *cvar; int32_t *breach; // [P], [P], [P], [P][t]
+    uint64_t *kkey[2]; int32_t *kidx[2];                                 // kept-tail ping-pong, [P][t] each
+    uint64_t *tkey;                                                      // [P]
+    bool moments;                                                        // fused per-trial moments into ctx->dPart
+    int *fail_cnt; int32_t *fail_rows;                                   // non-null: optimistic schedule
+};
+
+// streaming valuation (FP64 tensor cores) + threshold filter + radix-select; `optimistic` picks the schedule
+static int risk_stream_core(mcp_ctx *ctx, const StreamIO &io, int64_t t, bool optimistic, int *nparts_out)
+{
+    const int64_t P = io.P, N = ctx->N;
     const int sms = ctx->prop.multiProcessorCount;
-    // portfolio tile: candidate buffers are Pt x (longest step) x 12 bytes; keep them under 1/4 of HBM
+    // portfolio tile: candidate buffers are Pt x (longest step) x 16 bytes; keep them under 1/4 of HBM
     size_t budget = ctx->prop.totalGlobalMem / 4;
     if (budget > ((size_t)40 << 30)) budget = (size_t)40 << 30;
     int64_t Pt = P;
     std::vector<Step> steps;
-    int64_t stride = 0;
+    int64_t stride = 0, rank0 = t;
     int max_nsub = 0, nparts = 0;
     for (;;) {
         const int64_t nsg = (Pt + VM_PG - 1) / VM_PG;
-        steps = make_schedule(N, t, nsg, sms);
+        steps = make_schedule(N, t, nsg, sms, optimistic, ctx->itemTrials);
         stride = 0; max_nsub = 0; nparts = 0;
         for (auto &s : steps) {
             const int64_t w = (int64_t)s.nsub * s.sub_len;
@@ -1470,37 +1558,36 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
         if ((size_t)Pt * stride * 16 <= budget || Pt <= VM_PG) break;
         Pt = ((Pt / 2 + VM_PG - 1) / VM_PG) * VM_PG;
     }
+    if (optimistic) rank0 = optimistic_rank(N, steps[0].end, t);
+    if (nparts_out) *nparts_out = nparts;
     if (Pt > 65535 * (int64_t)VM_PG) Pt = 65535 * (int64_t)VM_PG;
     MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * 16));
     MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
-    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * sizeof(uint64_t)));
-    MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
-    MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
-    MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
-    uint64_t *tkey = ctx->dTau.as<uint64_t>();
+    if (io.moments) MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
     MCP_TRY(ensure_sfrag(ctx));
 
     for (int64_t p0 = 0; p0 < P; p0 += Pt) {
         const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
         const int64_t rows = p1 - p0;
-        uint64_t *kkey[2] = {ctx->dKeptKey.as<uint64_t>() + p0 * t, ctx->dKept2Key.as<uint64_t>() + p0 * t};
-        int32_t *kidx[2] = {ctx->dKeptIdx.as<int32_t>() + p0 * t, ctx->dKept2Idx.as<int32_t>() + p0 * t};
+        uint64_t *kkey[2] = {io.kkey[0] + p0 * t, io.kkey[1] + p0 * t};
+        int32_t *kidx[2] = {io.kidx[0] + p0 * t, io.kidx[1] + p0 * t};
         int cur = 0, part_base = 0;
+        int64_t kept = 0; // entries per row of the kept tail so far
         for (size_t si = 0; si < steps.size(); ++si) {
             const Step &s = steps[si];
             const bool dense = si == 0;
             StreamArgs v{};
-            v.E = ctx->dE.as<double>();
+            v.E = io.E;
             v.S = ctx->dS.as<double>();
             v.Sfrag = ctx->dSfrag.as<double>();
             v.p0 = p0; v.p1 = p1;
             v.n_begin = s.begin; v.n_end = s.end;
             v.nsub = s.nsub; v.sub_len = s.sub_len;
-            v.tkey = tkey;
+            v.tkey = io.tkey;
             v.cand = ctx->dCandKey.p;
             v.pitch = stride * 16;
             v.cnt = ctx->dCandCnt.as<int32_t>();
-            v.part = ctx->fusedMoments ? ctx->dPart.as<double>() : nullptr;
+            v.part = io.moments ? ctx->dPart.as<double>() : nullptr;
             v.part_stride = nparts; v.part_base = part_base;
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
             MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
@@ -1515,33 +1602,103 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
             a.n_begin = s.begin;
             a.kept_key_in = kkey[cur];
             a.kept_idx_in = kidx[cur];
-            a.kept_n = dense ? 0 : t;
+            a.kept_n = kept;
             a.kept_key_out = kkey[cur ^ 1];
             a.kept_idx_out = kidx[cur ^ 1];
-            a.tail = t;
+            // optimistic schedule: the dense step keeps only the top `rank0` of the sample (its rank0-th largest loss
+            // is the bound of the one sparse step); every other selection keeps the full tail
+            a.tail = (optimistic && dense && steps.size() > 1) ? rank0 : t;
             a.moments_n = 0;
-            a.var_loss = ctx->dVarLoss.as<double>() + p0;
-            a.var_trial = ctx->dVarTrial.as<int32_t>() + p0;
-            a.tkey = tkey + p0;
+            a.var_loss = io.var_loss + p0;
+            a.var_trial = io.var_trial + p0;
+            a.tkey = io.tkey + p0;
+            a.fail_cnt = io.fail_cnt;
+            a.fail_rows = io.fail_rows;
+            a.row_base = p0;
             {
                 KScope ks(ctx, MCP_K_SELECT);
-                a.cap = ctx->selCap;
+                // sparse steps stage kept + ~2.2 t candidates (optimistic) or ~2 t (guaranteed): a smaller staging area
+                // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
+                a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
                 k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
+            kept = a.tail;
             cur ^= 1;
             part_base += s.nsub;
         }
-        MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], ctx->dBreach.as<int32_t>() + p0 * t, ctx->dCvar.as<double>() + p0));
+        MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], io.breach + p0 * t, io.cvar + p0));
     }
+    return MCP_OK;
+}
+
+static int risk_run_stream(mcp_ctx *ctx, int64_t t)
+{
+    const int64_t P = ctx->P, N = ctx->N;
+    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)P * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * t * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * t * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dFail.reserve((size_t)(P + 4) * sizeof(int32_t)));
+    int *fail_cnt = ctx->dFail.as<int>();
+    int32_t *fail_rows = ctx->dFail.as<int32_t>() + 4;
+    // the optimistic bound needs a sample that is a small part of the trials and a rank below the tail size
+    const int64_t n0 = first_step_len(N, t);
+    const bool optimistic = ctx->optimistic && N >= 2 * n0 && optimistic_rank(N, n0, t) < t;
+    StreamIO io{};
+    io.E = ctx->dE.as<double>(); io.P = P;
+    io.var_loss = ctx->dVarLoss.as<double>(); io.var_trial = ctx->dVarTrial.as<int32_t>();
+    io.cvar = ctx->dCvar.as<double>(); io.breach = ctx->dBreach.as<int32_t>();
+    io.kkey[0] = ctx->dKeptKey.as<uint64_t>(); io.kkey[1] = ctx->dKept2Key.as<uint64_t>();
+    io.kidx[0] = ctx->dKeptIdx.as<int32_t>(); io.kidx[1] = ctx->dKept2Idx.as<int32_t>();
+    io.tkey = ctx->dTau.as<uint64_t>();
+    io.moments = ctx->fusedMoments;
+    if (optimistic) {
+        MCP_CUDA(ctx, cudaMemsetAsync(fail_cnt, 0, sizeof(int), ctx->stream));
+        io.fail_cnt = fail_cnt; io.fail_rows = fail_rows;
+    }
+    int nparts = 0;
+    MCP_TRY(risk_stream_core(ctx, io, t, optimistic, &nparts));
     if (ctx->fusedMoments) {
-        KScope ks(ctx, MCP_K_SELECT);
+        KScope ks(ctx, MCP_K_MOMENTS);
         k_moments_finalize<<<(unsigned)((P + 7) / 8), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dS.as<double>(), P, ctx->F, N,
                                                                             ctx->dPart.as<double>(), nparts, nparts,
                                                                             ctx->dMean.as<double>(), ctx->dVar.as<double>());
         MCP_TRY(check_launch(ctx, "k_moments_finalize"));
-    } else
-        MCP_TRY(run_moments_linear(ctx));
+    }
+    ctx->runFallbackRows = 0;
+    if (optimistic) {
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, fail_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int64_t nf = *reinterpret_cast<int *>(ctx->hPinned);
+        ctx->runFallbackRows = nf;
+        if (nf > 0) {
+            // redo the failed rows with the guaranteed schedule on a compact copy of their exposures
+            const int F = ctx->F;
+            MCP_CUDA(ctx, ctx->dFbE.reserve((size_t)nf * F * sizeof(double)));
+            MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)nf * (3 * sizeof(double) + (size_t)(t + 1) * sizeof(int32_t)) + 64));
+            MCP_CUDA(ctx, ctx->dFbKey.reserve((size_t)nf * t * 2 * sizeof(uint64_t)));
+            MCP_CUDA(ctx, ctx->dFbIdx.reserve((size_t)nf * t * 2 * sizeof(int32_t)));
+            {
+                KScope ks(ctx, MCP_K_SELECT);
+                k_gather_rows<<<(unsigned)std::min<int64_t>((nf * F + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), fail_rows, nf, F,
+                                                                                                              ctx->dFbE.as<double>());
+                MCP_TRY(check_launch(ctx, "k_gather_rows"));
+            }
+            StreamIO fb{};
+            fb.E = ctx->dFbE.as<double>(); fb.P = nf;
+            // dFbOut: [var_loss nf f64][cvar nf f64][tkey nf u64][breach nf*t i32][var_trial nf i32]
+            double *o = ctx->dFbOut.as<double>();
+            fb.var_loss = o; fb.cvar = o + nf; fb.tkey = reinterpret_cast<uint64_t *>(o + 2 * nf);
+            fb.breach = reinterpret_cast<int32_t *>(o + 3 * nf); fb.var_trial = fb.breach + nf * t;
+            fb.kkey[0] = ctx->dFbKey.as<uint64_t>(); fb.kkey[1] = fb.kkey[0] + nf * t;
+            fb.kidx[0] = ctx->dFbIdx.as<int32_t>(); fb.kidx[1] = fb.kidx[0] + nf * t;
+            MCP_TRY(risk_stream_core(ctx, fb, t, false, nullptr));
+            KScope ks(ctx, MCP_K_SELECT);
+            k_scatter_rows<<<(unsigned)nf, 128, 0, ctx->stream>>>(fail_rows, t, fb.var_loss, fb.var_trial, fb.cvar, fb.breach, io.var_loss,
+                                                                 io.var_trial, io.cvar, io.breach);
+            MCP_TRY(check_launch(ctx, "k_scatter_rows"));
+        }
+    }
     return MCP_OK;
 }
 
@@ -1569,8 +1726,18 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
         MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap, kSelMaxSeg)));
     }
 
-    if (mma_supported(ctx->F) && !ctx->forceDense) MCP_TRY(risk_run_stream(ctx, t));
+    const bool stream_path = mma_supported(ctx->F) && !ctx->forceDense;
+    const bool side_moments = stream_path && !ctx->fusedMoments;
+    if (side_moments) {
+        // mean / variance by linearity depend on E and S only: run them on the side stream, under the valuation
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+        MCP_TRY(run_moments_linear(ctx));
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+    }
+    if (stream_path) MCP_TRY(risk_run_stream(ctx, t));
     else MCP_TRY(risk_run_dense(ctx, t));
+    if (side_moments) MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));

@@ -180,6 +180,11 @@ class Context:
         self._check(self._L.mcp_run_sizes(self._h, C.byref(P), C.byref(Nn), C.byref(t), C.byref(eb)), "run_sizes")
         return {"P": P.value, "N": Nn.value, "tail": t.value, "enc_bytes": eb.value}
 
+    def run_stats(self) -> dict:
+        fb = C.c_int64()
+        self._check(self._L.mcp_run_stats(self._h, C.byref(fb)), "run_stats")
+        return {"fallback_rows": fb.value}
+
     def fetch(self, breach: bool = True, encoded: bool = True) -> dict:
         sz = self.run_sizes()
         P, t, eb = sz["P"], sz["tail"], sz["enc_bytes"]

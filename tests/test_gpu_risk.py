@@ -133,6 +133,35 @@ def _adversarial(ctx, F):
     check_against_oracle(ctx, E, S[::-1].copy(), 0.99)
 
 
+def test_optimistic_bound_falls_back_exactly(ctx):
+    """The two-step schedule bets on an optimistic filter bound (r-th largest loss of the first ~4t trials).  Trial
+    orders that break the bet must be detected per row and redone exactly: losses DEscending in the trial index make
+    the bound too tight for every row with positive exposure, ascending ones make it uselessly loose (every trial a
+    candidate); rows with mirrored exposure see the opposite order in the same run."""
+    F, Nn, P = 32, 60000, 300
+    S = np.zeros((Nn, F))
+    S[:, 0] = np.linspace(0.0, 1.0, Nn)           # V grows with the trial index for E[:,0] > 0: losses descend
+    S[:, 1] = 1e-3 * np.cos(np.arange(Nn))
+    E = np.abs(riskcases.synthetic(P, 1, F, 3)[0]) + 1.0
+    E[::3] *= -1.0                                 # every third row: losses ascend instead
+    rows = list(range(0, P, 7)) + [P - 1]
+    check_against_oracle(ctx, E, S, 0.99, rows=rows)
+    fb = ctx.run_stats()["fallback_rows"]
+    assert fb == P - len(range(0, P, 3)), fb       # exactly the descending-loss rows were redone
+    # exchangeable order: the bet holds, nothing is redone, and the guaranteed schedule gives the same bytes
+    E2, S2 = riskcases.synthetic(P, Nn, F, 41)
+    r1 = check_against_oracle(ctx, E2, S2, 0.99, rows=rows)
+    assert ctx.run_stats()["fallback_rows"] == 0
+    ctx.set_option("optimistic", 0)
+    try:
+        r0 = check_against_oracle(ctx, E2, S2, 0.99, rows=rows)
+        assert ctx.run_stats()["fallback_rows"] == 0
+    finally:
+        ctx.set_option("optimistic", 1)
+    for k in ("var_loss", "var_trial", "breach", "enc_off", "enc", "cvar"):
+        assert np.array_equal(r0[k], r1[k]), k
+
+
 def test_c1_shipped_sample(ctx):
     """BASELINE config C1: portfolios.json x macro.json (fixture tests/golden/c1_sample.json)."""
     d, E, S = riskcases.c1_inputs()
@@ -178,6 +207,7 @@ def test_full_size_c2_properties(ctx):
     r = ctx.fetch()
     t = r["tail"]
     assert t == 1001
+    assert ctx.run_stats()["fallback_rows"] == 0  # the optimistic bound held for every portfolio
     b = r["breach"]
     assert np.all(np.diff(b, axis=1) > 0) and b.min() >= 0 and b.max() < Nn          # sorted, distinct, in range
     assert np.all((b == r["var_trial"][:, None]).sum(axis=1) == 1)                     # the VaR trial is in its list
