@@ -164,6 +164,82 @@ __device__ __forceinline__ int64_t warp_bp32_decode(const WordSrc &src, int64_t 
     return p - p0;
 }
 
+// One list through a codec of the BinaryPacking family (Composition / IntCompressor framing around
+// BinaryPacking or IntegratedBinaryPacking + a VariableByte tail), by one warp.  Returns the words produced,
+// including the loader's trailing zero int when `app`.
+template <bool WRITE>
+__device__ __forceinline__ int64_t warp_bp_list_encode(const CodecTraits tr, const ValSeq x, int64_t n, const WordSink sink, bool app,
+                                                       uint32_t *stage, int lane)
+{
+    int64_t pos = 0;
+    if (tr.sk) { // IntCompressor / IntegratedIntCompressor: compressed[0] = input.length
+        if (WRITE && lane == 0) sink.put(0, (uint32_t)n);
+        pos = 1;
+    }
+    if (n > 0) {
+        const int64_t m = n & ~(int64_t)31;
+        if (!tr.sk) { // Composition: F1 header, or the 0 marker when F1 wrote nothing (Composition.java:45-48)
+            if (WRITE && lane == 0) sink.put(pos, (uint32_t)m);
+            ++pos;
+        }
+        pos += warp_bp32_encode<WRITE>(x, m, tr.integrated, sink, pos, lane);
+        const int64_t r = n - m;
+        if (r > 0) {
+            if (tr.integrated) {
+                // IntegratedVariableByte: gaps; the non-skippable composition restarts at 0
+                // (IntegratedVariableByte.java:40), the skippable one chains (:188-189)
+                const bool chain = tr.chain_tail;
+                auto getv = [&](int64_t i) -> uint32_t {
+                    const int64_t g = m + i;
+                    const uint32_t prev = (i > 0 || (chain && g > 0)) ? x(g - 1) : 0u;
+                    return x(g) - prev;
+                };
+                pos += warp_vb_encode<WRITE>(getv, r, sink, pos, stage, lane);
+            } else {
+                auto getv = [&](int64_t i) -> uint32_t { return x(m + i); };
+                pos += warp_vb_encode<WRITE>(getv, r, sink, pos, stage, lane);
+            }
+        }
+    }
+    if (app) {
+        if (WRITE && lane == 0) sink.put(pos, 0u); // LoadPortfolios.java:622: outpos + 1 ints
+        ++pos;
+    }
+    return pos;
+}
+
+// Inverse of warp_bp_list_encode: `avail` words at src decode to exactly n ints at out.  False on a malformed stream.
+__device__ __forceinline__ bool warp_bp_list_decode(const CodecTraits tr, const WordSrc src, int64_t avail, int64_t n, uint32_t *out,
+                                                    bool delta, int lane)
+{
+    int64_t p = 0, m = n & ~(int64_t)31;
+    uint32_t carry = 0;
+    if (tr.sk) {
+        if (avail < 1 || (int64_t)src.get(0) != n) return false;
+        p = 1;
+    }
+    if (n == 0) return true;
+    if (!tr.sk) {
+        if (p >= avail) return false;
+        if ((int64_t)src.get(p++) != m) return false;
+    }
+    if (m > 0) {
+        const int64_t used = warp_bp32_decode(src, p, avail, m, tr.integrated, out, carry, lane);
+        if (used < 0) return false;
+        p += used;
+    }
+    if (n > m) {
+        const bool ok = tr.integrated ? warp_vb_decode<true>(src, p, avail, n - m, out + m, tr.chain_tail ? carry : 0u, lane)
+                                      : warp_vb_decode<false>(src, p, avail, n - m, out + m, 0u, lane);
+        if (!ok) return false;
+    }
+    if (delta) {
+        __syncwarp();
+        warp_inverse_delta(out, n, lane);
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------- FastPFOR
 struct FpBlockPlan { int b, c, maxb; };
 
@@ -668,6 +744,482 @@ __global__ void k_bswap_copy(const uint32_t *in, uint32_t *out, int64_t n)
         out[i] = bswap32(in[i]);
 }
 
+// ============================================================ batched fast path (BinaryPacking family)
+// The kernels above give one warp to one list, which for the ~100-int breach lists of BASELINE config C4 leaves the
+// SMs latency- and instruction-bound (4 % of the HBM roofline).  The fast path turns the work around:
+//   * a CTA owns a BATCH of consecutive lists whose values (<= FE_VCAP ints) it stages in shared memory with
+//     coalesced loads;
+//   * ONE THREAD packs (or unpacks) ONE 32-int block from shared memory with a 64-bit shift register -- ~5 thread
+//     instructions per integer instead of ~5 WARP instructions per integer;
+//   * one thread per list writes the list header and the VariableByte tail (< 32 values);
+//   * the batch's output is assembled in shared memory and leaves with coalesced stores (byte-swapped on the way
+//     for the loader's big-endian framing);
+//   * encode is SINGLE PASS: the CSR output offsets come from a decoupled look-back over per-batch totals (batches
+//     take dynamic tickets, so a batch only ever waits on batches that are already running) instead of a size pass,
+//     a scan and an emit pass -- the input is read once.
+// Batches that do not fit the staging areas (very long lists, incompressible data) are handled inside the same kernel
+// by the per-warp routines above, so any input is accepted.  Codecs: BP32_VB, SK_BP32_VB (with or without the Delta
+// pre-pass) and IBP32_IVB, SK_IBP32_IVB (without).
+constexpr int FE_THREADS = 128;
+constexpr int FE_VCAP = 4096;   // staged values per batch: one 32-int block per thread
+constexpr int FE_MAXL = 128;    // lists per batch
+constexpr int FE_OCAP = 3328;   // staged compressed words per batch
+constexpr int FE_VPAD = FE_VCAP + FE_VCAP / 32 + 2;
+
+__host__ __device__ inline bool fast_codec_ok(int codec, bool delta)
+{
+    const CodecTraits t = codec_traits(codec);
+    return t.blocks && !t.fastpfor && !(t.integrated && delta);
+}
+
+__device__ __forceinline__ int sw33(int i) { return i + (i >> 5); } // 33-word stride per 32 values: conflict-free block reads
+
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// exclusive scan of one int per thread over the CTA (FE_THREADS = 4 warps); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ int cta_excl_scan(int v, int *s_w /* [5] */, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    __syncthreads(); // s_w may still be read from a previous call
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < FE_THREADS / 32; ++w) {
+        const int x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    *total = tot;
+    return off + incl - v;
+}
+
+struct FastEncArgs {
+    int codec;
+    bool delta, app;
+    const uint32_t *vals;
+    const int64_t *list_off; // null -> uniform_len
+    int64_t uniform_len;
+    int64_t nlists;
+    int lists_per_batch;
+    int64_t nbatches;
+    int64_t *out_off;        // [nlists + 1] bytes (written)
+    uint8_t *out;
+    int64_t cap;             // bytes
+    uint64_t *state;         // [nbatches] look-back state, zeroed; top 2 bits: 1 = aggregate, 2 = inclusive prefix
+    unsigned long long *ticket; // zeroed
+    int64_t *total;          // bytes (written by the last batch)
+    int *err;                // set to 1 when the output would exceed cap
+};
+
+// header words in front of block k of a list with nb blocks (BinaryPacking.java:54-89): one per group of four
+// blocks while full groups last, then one per block
+__device__ __forceinline__ int bp_hdrs_before(int k, int nb)
+{
+    const int ng = nb >> 2;
+    return k < 4 * ng ? (k >> 2) + 1 : ng + (k - 4 * ng) + 1;
+}
+
+__global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs a)
+{
+    __shared__ uint32_t s_val[FE_VPAD];
+    __shared__ uint32_t s_out[FE_OCAP];
+    __shared__ int s_in[FE_MAXL + 1];   // value offset of each list inside the batch
+    __shared__ int s_ib[FE_MAXL + 1];   // first block item of each list
+    __shared__ long long s_lo[FE_MAXL + 1]; // word offset of each list's output inside the batch
+    __shared__ int s_bsum[FE_THREADS + 1]; // exclusive prefix of the block widths over the items
+    __shared__ uint8_t s_w[FE_THREADS];    // width of each block item
+    __shared__ uint8_t s_il[FE_THREADS];   // list of each block item
+    __shared__ uint32_t s_stage[FE_THREADS / 32][48];
+    __shared__ int s_scan[8];
+    __shared__ long long s_base;
+    __shared__ long long s_vbase;
+    __shared__ unsigned long long s_batch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    const bool diff = a.delta || tr.integrated;
+    if (tid == 0) s_batch = atomicAdd(a.ticket, 1ull);
+    __syncthreads();
+    const int64_t batch = (int64_t)s_batch;
+    const int64_t l0 = batch * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    // ---- list extents
+    {
+        const int64_t vb = a.list_off ? a.list_off[l0] : l0 * a.uniform_len;
+        if (tid == 0) s_vbase = vb;
+        for (int j = tid; j <= nl; j += FE_THREADS) {
+            const int64_t o = (a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len) - vb;
+            s_in[j] = (int)(o > 0x7fffffff ? 0x7fffffff : o);
+        }
+    }
+    __syncthreads();
+    const int64_t vbase = s_vbase;
+    const int nv = s_in[nl];
+    bool fit = nv <= FE_VCAP;
+    long long T = 0; // words this batch produces
+    int my_pos = 0, my_b = 0, my_list = 0, my_k = 0, my_start = 0;
+    bool have_item = false;
+    if (fit) {
+        // ---- stage the values (coalesced), 33-word stride per 32 values
+        for (int i = tid; i < nv; i += FE_THREADS) s_val[sw33(i)] = __ldg(a.vals + vbase + i);
+        // ---- block items: list j owns items [s_ib[j], s_ib[j+1])
+        int ni = 0;
+        {
+            const int nbj = tid < nl ? (s_in[tid + 1] - s_in[tid]) >> 5 : 0;
+            const int ex = cta_excl_scan(nbj, s_scan, &ni);
+            if (tid < nl) s_ib[tid] = ex;
+            if (tid == 0) s_ib[nl] = ni;
+            __syncthreads();
+            if (tid < nl)
+                for (int k = 0; k < nbj; ++k) s_il[ex + k] = (uint8_t)tid;
+        }
+        __syncthreads();
+        // ---- width of my block (Util.maxbits / maxdiffbits)
+        uint32_t v[32];
+        have_item = tid < ni;
+        if (have_item) {
+            my_list = s_il[tid];
+            my_k = tid - s_ib[my_list];
+            my_start = s_in[my_list] + 32 * my_k;
+            uint32_t prev = (diff && my_k > 0) ? s_val[sw33(my_start - 1)] : 0u;
+            uint32_t orv = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t x = s_val[sw33(my_start + i)];
+                v[i] = diff ? x - prev : x;
+                if (diff) prev = x;
+                orv |= v[i];
+            }
+            my_b = bits32(orv);
+            s_w[tid] = (uint8_t)my_b;
+        }
+        int tb = 0;
+        const int bex = cta_excl_scan(have_item ? my_b : 0, s_scan, &tb);
+        s_bsum[tid] = bex;
+        if (tid == 0) s_bsum[FE_THREADS] = tb;
+        __syncthreads();
+        // ---- per list: words of the VariableByte tail and of the whole list
+        int lw = 0, tail_words = 0;
+        if (tid < nl) {
+            const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5, r = n & 31;
+            const int i0 = s_ib[tid];
+            const int bw = s_bsum[i0 + nb] - s_bsum[i0]; // i0 + nb <= ni <= FE_THREADS
+            int bytes = 0;
+            const int g0 = s_in[tid] + 32 * nb;
+            for (int i = 0; i < r; ++i) {
+                const int g = g0 + i;
+                const uint32_t x = s_val[sw33(g)];
+                uint32_t d = x;
+                if (tr.integrated) { if (i > 0 || (tr.chain_tail && nb > 0)) d = x - s_val[sw33(g - 1)]; }
+                else if (a.delta && (i > 0 || nb > 0)) d = x - s_val[sw33(g - 1)];
+                bytes += vb_len(d);
+            }
+            tail_words = (bytes + 3) >> 2;
+            const int hdrs = (nb >> 2) + (nb & 3);
+            lw = (n > 0 ? 1 + bw + hdrs + tail_words : (tr.sk ? 1 : 0)) + (a.app ? 1 : 0);
+        }
+        int Tw = 0;
+        const int lex = cta_excl_scan(lw, s_scan, &Tw);
+        T = Tw;
+        if (tid < nl) s_lo[tid] = lex;
+        if (tid == 0) s_lo[nl] = Tw;
+        __syncthreads();
+        fit = T <= FE_OCAP;
+        if (fit) {
+            // ---- pack my block into the staged output (BitPacking.fastpackwithoutmask; IntegratedBitPacking
+            // stores the raw values at width 32)
+            if (have_item) {
+                const int nb = (s_in[my_list + 1] - s_in[my_list]) >> 5;
+                my_pos = (int)s_lo[my_list] + 1 + (s_bsum[tid] - s_bsum[s_ib[my_list]]) + bp_hdrs_before(my_k, nb); // word 0 = list header
+                uint32_t *o = s_out + my_pos;
+                if (my_b == 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = tr.integrated ? s_val[sw33(my_start + i)] : v[i];
+                } else if (my_b > 0) {
+                    uint64_t acc = 0;
+                    int fill = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        acc |= (uint64_t)v[i] << fill;
+                        fill += my_b;
+                        if (fill >= 32) { *o++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
+                    }
+                }
+                const int ng4 = 4 * (nb >> 2);
+                if (my_k >= ng4) s_out[my_pos - 1] = (uint32_t)my_b;
+                else if ((my_k & 3) == 0)
+                    s_out[my_pos - 1] = ((uint32_t)my_b << 24) | ((uint32_t)s_w[tid + 1] << 16) | ((uint32_t)s_w[tid + 2] << 8) | (uint32_t)s_w[tid + 3];
+            }
+            // ---- per list: header word, VariableByte tail, trailing zero int of the loader's framing
+            if (tid < nl) {
+                const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5, r = n & 31;
+                uint32_t *o = s_out + s_lo[tid];
+                if (n > 0 || tr.sk) o[0] = tr.sk ? (uint32_t)n : (uint32_t)(32 * nb); // IntCompressor: n; Composition: F1 header / 0 marker
+                if (r > 0) {
+                    uint32_t *tw = s_out + s_lo[tid + 1] - (a.app ? 1 : 0) - tail_words;
+                    const int g0 = s_in[tid] + 32 * nb;
+                    uint64_t acc = 0;
+                    int fill = 0;
+                    for (int i = 0; i < r; ++i) {
+                        const int g = g0 + i;
+                        const uint32_t x = s_val[sw33(g)];
+                        uint32_t d = x;
+                        if (tr.integrated) { if (i > 0 || (tr.chain_tail && nb > 0)) d = x - s_val[sw33(g - 1)]; }
+                        else if (a.delta && (i > 0 || nb > 0)) d = x - s_val[sw33(g - 1)];
+                        while (d >= 128u) { acc |= (uint64_t)(d & 127u) << fill; fill += 8; d >>= 7; if (fill >= 32) { *tw++ = (uint32_t)acc; acc >>= 32; fill -= 32; } }
+                        acc |= (uint64_t)(d | 128u) << fill; fill += 8;
+                        if (fill >= 32) { *tw++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
+                    }
+                    if (fill > 0) *tw = (uint32_t)acc; // zero-padded to a word (VariableByte.java:62-66)
+                }
+                if (a.app) s_out[s_lo[tid + 1] - 1] = 0u; // LoadPortfolios.java:622: outpos + 1 ints
+            }
+        }
+    }
+    // ---- batches that do not fit the staging areas: sizes by the per-warp routines (one list per warp at a time)
+    if (!fit) {
+        __syncthreads();
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int64_t beg = a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len;
+            const int64_t n = (a.list_off ? a.list_off[l0 + j + 1] : (l0 + j + 1) * a.uniform_len) - beg;
+            const int64_t w = warp_bp_list_encode<false>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp], lane);
+            if (lane == 0) s_lo[j] = w;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            long long run = 0;
+            for (int j = 0; j < nl; ++j) { const long long w = s_lo[j]; s_lo[j] = run; run += w; }
+            s_lo[nl] = run;
+        }
+        __syncthreads();
+        T = s_lo[nl];
+    }
+    // ---- decoupled look-back: word offset of this batch in the output
+    if (tid == 0) {
+        constexpr uint64_t AGG = 1ull << 62, INC = 2ull << 62, MASK = (1ull << 62) - 1;
+        long long base = 0;
+        if (batch == 0) st_release_u64(a.state, INC | (uint64_t)T);
+        else {
+            st_release_u64(a.state + batch, AGG | (uint64_t)T);
+            for (int64_t j = batch - 1;; --j) {
+                uint64_t s;
+                do { s = ld_acquire_u64(a.state + j); } while ((s >> 62) == 0);
+                base += (long long)(s & MASK);
+                if ((s >> 62) == 2) break;
+            }
+            st_release_u64(a.state + batch, INC | (uint64_t)(base + T));
+        }
+        s_base = base;
+        if (batch == a.nbatches - 1) {
+            *a.total = 4 * (base + T);
+            a.out_off[a.nlists] = 4 * (base + T);
+        }
+        if (4 * (base + T) > a.cap) *a.err = 1;
+    }
+    __syncthreads();
+    const int64_t base = s_base;
+    for (int j = tid; j < nl; j += FE_THREADS) a.out_off[l0 + j] = 4 * (base + s_lo[j]);
+    if (4 * (base + T) > a.cap) return; // caller's buffer too small: report, write nothing
+    uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + base;
+    if (fit) {
+        for (int i = tid; i < (int)T; i += FE_THREADS) gout[i] = a.app ? bswap32(s_out[i]) : s_out[i];
+    } else {
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int64_t beg = a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len;
+            const int64_t n = (a.list_off ? a.list_off[l0 + j + 1] : (l0 + j + 1) * a.uniform_len) - beg;
+            warp_bp_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_lo[j], a.app}, a.app, s_stage[warp], lane);
+        }
+    }
+}
+
+
+struct FastDecArgs {
+    int codec;
+    bool delta, app;
+    const uint8_t *in;
+    const int64_t *in_off;
+    int64_t nlists;
+    int lists_per_batch;
+    uint32_t *out;
+    const int64_t *out_off;
+    int *err;
+};
+
+__global__ void __launch_bounds__(FE_THREADS) k_bp_decode_fast(const FastDecArgs a)
+{
+    __shared__ uint32_t s_val[FE_VPAD];   // decoded values of the batch (33-word stride per 32)
+    __shared__ uint32_t s_wd[FE_OCAP];    // compressed words of the batch, native order
+    __shared__ int s_in[FE_MAXL + 1];     // word offset of each list's stream inside the batch
+    __shared__ int s_oo[FE_MAXL + 1];     // value offset of each list inside the batch
+    __shared__ int s_ib[FE_MAXL + 1];     // first block item of each list
+    __shared__ int s_ipos[FE_THREADS];    // word position (in s_wd) of each block item
+    __shared__ uint32_t s_tot[FE_THREADS]; // sum of the block's differences / its last value
+    __shared__ uint32_t s_carry[FE_THREADS];
+    __shared__ uint8_t s_iw[FE_THREADS];
+    __shared__ uint8_t s_il[FE_THREADS];
+    __shared__ int s_scan[8];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    const bool diff = a.delta || tr.integrated;
+    const int64_t l0 = (int64_t)blockIdx.x * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    const int64_t ibase = a.in_off[l0], obase = a.out_off[l0];
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int j = tid; j <= nl; j += FE_THREADS) {
+        const int64_t ib = a.in_off[l0 + j] - ibase, ob = a.out_off[l0 + j] - obase;
+        if ((a.in_off[l0 + j] & 3) != 0) s_bad = 1;
+        s_in[j] = (int)((ib >> 2) > 0x7fffffff ? 0x7fffffff : (ib >> 2));
+        s_oo[j] = (int)(ob > 0x7fffffff ? 0x7fffffff : ob);
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) atomicExch(a.err, 1); return; }
+    const uint32_t *gin = reinterpret_cast<const uint32_t *>(a.in + ibase);
+    const int nw = s_in[nl], nv = s_oo[nl];
+    if (nw > FE_OCAP || nv > FE_VCAP) {
+        // batch does not fit the staging areas: per-warp routines straight from / to global memory
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int64_t ib = a.in_off[l0 + j], ie = a.in_off[l0 + j + 1];
+            const int64_t n = a.out_off[l0 + j + 1] - a.out_off[l0 + j];
+            const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + ib), a.app};
+            const bool ok = ((ie - ib) & 3) == 0 && warp_bp_list_decode(tr, src, (ie - ib) >> 2, n, a.out + a.out_off[l0 + j], a.delta, lane);
+            if (!ok && lane == 0) atomicExch(a.err, 1);
+            __syncwarp();
+        }
+        return;
+    }
+    for (int i = tid; i < nw; i += FE_THREADS) { const uint32_t x = __ldg(gin + i); s_wd[i] = a.app ? bswap32(x) : x; }
+    int ni = 0;
+    {
+        const int nbj = tid < nl ? (s_oo[tid + 1] - s_oo[tid]) >> 5 : 0;
+        const int ex = cta_excl_scan(nbj, s_scan, &ni);
+        if (tid < nl) s_ib[tid] = ex;
+        if (tid == 0) s_ib[nl] = ni;
+    }
+    __syncthreads();
+    // ---- one thread per list: walk the headers (the position of a header depends on the widths before it), note
+    // every block's position and width, decode the VariableByte tail (differences are summed below)
+    if (tid < nl) {
+        const int n = s_oo[tid + 1] - s_oo[tid], nb = n >> 5, r = n & 31;
+        const int avail = s_in[tid + 1] - s_in[tid];
+        const uint32_t *w = s_wd + s_in[tid];
+        int p = 0, item = s_ib[tid];
+        bool ok = true;
+        if (tr.sk) { ok = avail >= 1 && w[0] == (uint32_t)n; p = 1; }
+        if (ok && n > 0) {
+            if (!tr.sk) { ok = p < avail && w[p] == (uint32_t)(32 * nb); ++p; }
+            int k = 0;
+            for (; ok && k + 4 <= nb; k += 4) { // BinaryPacking.java:102-123
+                if (p >= avail) { ok = false; break; }
+                const uint32_t h = w[p++];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = (int)((h >> (24 - 8 * q)) & 255u);
+                    if (b > 32 || p + b > avail) { ok = false; break; }
+                    s_il[item] = (uint8_t)tid; s_ipos[item] = s_in[tid] + p; s_iw[item] = (uint8_t)b;
+                    ++item; p += b;
+                }
+            }
+            for (; ok && k < nb; ++k) {         // :124-131
+                if (p >= avail) { ok = false; break; }
+                const uint32_t h = w[p++];
+                if (h > 32u || p + (int)h > avail) { ok = false; break; }
+                s_il[item] = (uint8_t)tid; s_ipos[item] = s_in[tid] + p; s_iw[item] = (uint8_t)h;
+                ++item; p += (int)h;
+            }
+            // VariableByte.headlessUncompress (VariableByte.java:180-203)
+            if (ok && r > 0) {
+                const int o0 = s_oo[tid] + 32 * nb;
+                int got = 0, s = 0, shift = 0;
+                uint32_t v = 0;
+                while (got < r) {
+                    if (p >= avail) { ok = false; break; }
+                    const uint32_t c = (w[p] >> s) & 0xffu;
+                    s += 8; p += s >> 5; s &= 31;
+                    v += (c & 127u) << (shift & 31);
+                    if (c & 128u) { s_val[sw33(o0 + got)] = v; ++got; v = 0; shift = 0; }
+                    else shift += 7;
+                }
+            }
+        }
+        if (!ok) s_bad = 1;
+        for (; item < s_ib[tid + 1]; ++item) { s_il[item] = (uint8_t)tid; s_ipos[item] = 0; s_iw[item] = 0; } // malformed: keep the tables defined
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) atomicExch(a.err, 1); return; }
+    // ---- one thread per block: unpack 32 values (BitPacking.fastunpack), running sum inside the block when the
+    // stream holds differences
+    uint32_t v[32];
+    const bool have_item = tid < ni;
+    int my_start = 0, my_b = 0;
+    if (have_item) {
+        const int j = s_il[tid], k = tid - s_ib[j];
+        my_start = s_oo[j] + 32 * k;
+        my_b = s_iw[tid];
+        const uint32_t *ptr = s_wd + s_ipos[tid];
+        if (my_b == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ptr[i];
+        } else {
+            const uint32_t mask = (1u << my_b) - 1u;
+            uint64_t acc = 0;
+            int fill = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (fill < my_b) { acc |= (uint64_t)(*ptr++) << fill; fill += 32; }
+                v[i] = (uint32_t)acc & mask;
+                acc >>= my_b;
+                fill -= my_b;
+            }
+        }
+        const bool raw = tr.integrated && my_b == 32; // IntegratedBitPacking stores raw values at width 32
+        if (diff && !raw) {
+#pragma unroll
+            for (int i = 1; i < 32; ++i) v[i] += v[i - 1];
+        }
+        s_tot[tid] = v[31];
+    }
+    __syncthreads();
+    // ---- one thread per list: carry of every block (sum of everything before it), and the tail's running sum
+    if (diff && tid < nl) {
+        const int n = s_oo[tid + 1] - s_oo[tid], nb = n >> 5, r = n & 31;
+        uint32_t carry = 0;
+        for (int it = s_ib[tid]; it < s_ib[tid] + nb; ++it) {
+            const bool raw = tr.integrated && s_iw[it] == 32;
+            s_carry[it] = raw ? 0u : carry;
+            carry = raw ? s_tot[it] : carry + s_tot[it];
+        }
+        if (tr.integrated && !tr.chain_tail) carry = 0; // IntegratedVariableByte.java:40 restarts; the skippable form chains
+        const int o0 = s_oo[tid] + 32 * nb;
+        for (int i = 0; i < r; ++i) { carry += s_val[sw33(o0 + i)]; s_val[sw33(o0 + i)] = carry; }
+    }
+    __syncthreads();
+    if (have_item) {
+        const uint32_t c = diff ? s_carry[tid] : 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s_val[sw33(my_start + i)] = v[i] + c;
+    }
+    __syncthreads();
+    uint32_t *gout = a.out + obase;
+    for (int i = tid; i < nv; i += FE_THREADS) gout[i] = s_val[sw33(i)];
+}
+
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
 // block, then a second sweep.  Sizes here are "number of lists": bookkeeping, not hot.
@@ -760,6 +1312,105 @@ int exclusive_scan_i64(mcp_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_
 }
 
 // ------------------------------------------------------------------ launchers
+
+// ---- fast-path launchers -------------------------------------------------------------------------------------
+// lists per batch: fill ~92 % of the value staging area on average (a batch that overflows is still handled, by the
+// per-warp routines); 0 = the fast path is not worth it (long lists: the per-warp kernels are the better fit)
+static int fast_lists_per_batch(int64_t total_vals, int64_t nlists)
+{
+    if (nlists <= 0) return 0;
+    const double avg = (double)total_vals / (double)nlists;
+    if (avg > 1024.0) return 0;
+    int64_t g = (int64_t)(0.92 * FE_VCAP / (avg > 1.0 ? avg : 1.0));
+    if (g < 1) g = 1;
+    if (g > FE_MAXL) g = FE_MAXL;
+    return (int)g;
+}
+
+bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists)
+{
+    return fast_codec_ok(codec_id & MCP_CODEC_MASK, (codec_id & MCP_FLAG_DELTA) != 0) && fast_lists_per_batch(total_vals, nlists) > 0;
+}
+
+// upper bound of the encoded size in bytes for the fast-path codecs: 33 words per 32-int block worst case, a 31-value
+// VariableByte tail of 5 bytes each, count / header / trailing-zero words
+int64_t codec_fast_max_bytes(int64_t total_vals, int64_t nlists) { return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64); }
+
+// Single-pass encode of nlists lists; writes d_out_off[0..nlists] (bytes) and the stream.  *total_out = bytes needed;
+// MCP_E_CAP when that exceeds cap (nothing useful is written then).
+int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
+                      int64_t uniform_len, int64_t nlists, int64_t total_vals, int64_t *d_out_off, uint8_t *d_out, int64_t cap,
+                      int64_t *total_out)
+{
+    if (nlists == 0) {
+        MCP_CUDA(ctx, cudaMemsetAsync(d_out_off, 0, sizeof(int64_t), ctx->stream));
+        *total_out = 0;
+        return MCP_OK;
+    }
+    FastEncArgs a{};
+    a.codec = codec_id & MCP_CODEC_MASK;
+    a.delta = (codec_id & MCP_FLAG_DELTA) != 0;
+    a.app = framing == MCP_FRAME_APP;
+    a.vals = reinterpret_cast<const uint32_t *>(d_vals);
+    a.list_off = d_list_off;
+    a.uniform_len = uniform_len;
+    a.nlists = nlists;
+    a.lists_per_batch = fast_lists_per_batch(total_vals, nlists);
+    a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
+    if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
+    // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
+    const size_t sbytes = 32 + (size_t)a.nbatches * sizeof(uint64_t);
+    MCP_CUDA(ctx, ctx->dScanTmp.reserve(sbytes));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dScanTmp.p, 0, sbytes, ctx->stream));
+    unsigned char *sp = ctx->dScanTmp.as<unsigned char>();
+    a.ticket = reinterpret_cast<unsigned long long *>(sp);
+    a.total = reinterpret_cast<int64_t *>(sp + 8);
+    a.err = reinterpret_cast<int *>(sp + 16);
+    a.state = reinterpret_cast<uint64_t *>(sp + 32);
+    a.out_off = d_out_off;
+    a.out = d_out;
+    a.cap = d_out ? cap : 0;
+    {
+        KScope ks(ctx, MCP_K_ENCODE);
+        k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        MCP_TRY(check_launch(ctx, "k_bp_encode_fast"));
+    }
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, sp + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);
+    if (*reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8) != 0) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+    return MCP_OK;
+}
+
+int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off, int64_t nlists,
+                      int64_t total_out_vals, int32_t *d_out, const int64_t *d_out_off)
+{
+    if (nlists == 0) return MCP_OK;
+    FastDecArgs a{};
+    a.codec = codec_id & MCP_CODEC_MASK;
+    a.delta = (codec_id & MCP_FLAG_DELTA) != 0;
+    a.app = framing == MCP_FRAME_APP;
+    a.in = d_in;
+    a.in_off = d_in_off;
+    a.nlists = nlists;
+    a.lists_per_batch = fast_lists_per_batch(total_out_vals, nlists);
+    a.out = reinterpret_cast<uint32_t *>(d_out);
+    a.out_off = d_out_off;
+    MCP_CUDA(ctx, ctx->dErr.reserve(64));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
+    a.err = ctx->dErr.as<int>();
+    const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
+    {
+        KScope ks(ctx, MCP_K_DECODE);
+        k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        MCP_TRY(check_launch(ctx, "k_bp_decode_fast"));
+    }
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dErr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*reinterpret_cast<int *>(ctx->hPinned) != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
+    return MCP_OK;
+}
+
 static int grid_for_lists(mcp_ctx *ctx, int64_t nlists)
 {
     const int64_t want = (nlists + kEncWarps - 1) / kEncWarps;

@@ -150,6 +150,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "value_mma")) ctx->valueMma = value != 0;
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
+    else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
@@ -183,7 +184,14 @@ int mcp_codec_encode_dev(mcp_ctx *ctx, int codec_id, int framing, const int32_t 
 {
     MCP_TRY(set_dev(ctx));
     if (nlists < 0 || total_vals < 0 || !d_out_off || (nlists > 0 && !d_list_off)) return fail(ctx, MCP_E_ARG, "encode_dev: bad argument");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
     int64_t total = 0;
+    if (ctx->fastCodec && codec_fast_applicable(codec_id, total_vals, nlists)) {
+        const int rc = codec_fast_encode(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, total_vals, d_out_off, d_out, cap, &total);
+        if (total_out) *total_out = total;
+        return rc;
+    }
     MCP_TRY(codec_encode_plan(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, d_out_off, &total));
     if (total_out) *total_out = total;
     if (total > cap || (total > 0 && !d_out)) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
@@ -195,6 +203,17 @@ int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing, const uint8_t 
 {
     MCP_TRY(set_dev(ctx));
     if (nlists < 0 || (nlists > 0 && (!d_in_off || !d_out_off))) return fail(ctx, MCP_E_ARG, "decode_dev: bad argument");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
+    if (ctx->fastCodec && nlists > 0 && codec_fast_applicable(codec_id, 0, nlists)) {
+        // the batch size follows the average list length: two offsets from the device
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, d_out_off, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hPinned) + 8, d_out_off + nlists, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int64_t tv = reinterpret_cast<int64_t *>(ctx->hPinned)[1] - reinterpret_cast<int64_t *>(ctx->hPinned)[0];
+        if (tv >= 0 && codec_fast_applicable(codec_id, tv, nlists))
+            return codec_fast_decode(ctx, codec_id, framing, d_in, d_in_off, nlists, tv, d_out, d_out_off);
+    }
     return codec_decode_device(ctx, codec_id, framing, d_in, d_in_off, nlists, d_out, d_out_off);
 }
 
@@ -222,6 +241,23 @@ int mcp_codec_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *val
         MCP_TRY(sync(ctx));
     }
     int64_t total = 0;
+    if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, total_vals, nlists)) {
+        // single pass: encode into a worst-case device buffer, then copy back what was produced
+        const int64_t bound = codec_fast_max_bytes(total_vals, nlists);
+        MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)bound + 16));
+        const bool sizing = !out || cap <= 0; // size query: nothing is written
+        const int rc = codec_fast_encode(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists, total_vals,
+                                         ctx->dIo3.as<int64_t>(), sizing ? nullptr : ctx->dIo2.as<uint8_t>(), sizing ? 0 : (cap < bound ? cap : bound), &total);
+        if (out_len) *out_len = total;
+        if (rc != MCP_OK && rc != MCP_E_CAP) return rc;
+        MCP_TRY(d2h(ctx, out_off, ctx->dIo3.p, (size_t)(nlists + 1) * sizeof(int64_t)));
+        if (rc == MCP_E_CAP || (total > 0 && sizing)) {
+            sync(ctx);
+            return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+        }
+        MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)total));
+        return sync(ctx);
+    }
     MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists,
                               ctx->dIo3.as<int64_t>(), &total));
     if (out_len) *out_len = total;
@@ -259,8 +295,12 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *in,
     MCP_TRY(h2d(ctx, ctx->dIo0.p, in, (size_t)in_bytes));
     MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, (size_t)(nlists + 1) * sizeof(int64_t)));
     MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, (size_t)(nlists + 1) * sizeof(int64_t)));
-    MCP_TRY(codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists,
-                                ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
+    if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, out_n, nlists))
+        MCP_TRY(codec_fast_decode(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists, out_n,
+                                  ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
+    else
+        MCP_TRY(codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists,
+                                    ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
     MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)out_n * sizeof(int32_t)));
     return sync(ctx);
 }

@@ -35,10 +35,20 @@ def test_kat_through_the_c_abi(ctx):
     assert doc["algo"] == "bpacking+variablebyte" and doc["compressedByteSize"] == 36 and doc["uncompressedIntegerSize"] == 17
 
 
+@pytest.fixture(params=[1, 0], ids=["fastpath", "warp-per-list"])
+def codec_ctx(ctx, request):
+    """Both kernel families behind the codec ABI: the batched single-pass fast path (BinaryPacking family, short
+    lists) and the warp-per-list size/scan/emit kernels that handle everything else."""
+    ctx.set_option("fast_codec", request.param)
+    yield ctx
+    ctx.set_option("fast_codec", 1)
+
+
 @pytest.mark.parametrize("codec", cases.ALL_CODECS, ids=cases.NAMES)
 @pytest.mark.parametrize("delta", [0, cases.DELTA], ids=["plain", "delta"])
 @pytest.mark.parametrize("framing", [N.FRAME_WORDS, N.FRAME_APP], ids=["words", "app"])
-def test_encode_bit_exact_and_decode_roundtrip(ctx, codec, delta, framing):
+def test_encode_bit_exact_and_decode_roundtrip(codec_ctx, codec, delta, framing):
+    ctx = codec_ctx
     matrix = cases.reference_matrix(big=False)
     vals, off = batch_of(matrix)
     cid = codec | delta
@@ -82,7 +92,8 @@ def test_golden_bitpacking_through_gpu(ctx):
         assert list(dec[32 * i: 32 * i + 32]) == c["out"], c["b"]
 
 
-def test_breach_like_batch_all_codecs(ctx):
+def test_breach_like_batch_all_codecs(codec_ctx):
+    ctx = codec_ctx
     rng = np.random.default_rng(11)
     vals, off = cases.breach_like_lists(rng, 3000, 10000, 0.01)       # config C4 shape: ~100 ints per list
     vals2, off2 = cases.breach_like_lists(rng, 300, 100000, 0.01)     # ~1000 ints per list: exercises FastPFOR blocks
@@ -97,6 +108,54 @@ def test_breach_like_batch_all_codecs(ctx):
             for i in range(nl):
                 assert bytes(out[out_off[i]: out_off[i + 1]]) == bytes(ref[i * stride: i * stride + lens[i]]), (cid, i)
             assert np.array_equal(ctx.codec_decode(cid, N.FRAME_APP, out, out_off, o), v)
+
+
+@pytest.mark.parametrize("cid", [N.CODEC_BP32_VB, N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_SK_BP32_VB | N.FLAG_DELTA, N.CODEC_IBP32_IVB,
+                                 N.CODEC_SK_IBP32_IVB], ids=["bp", "bp+delta", "skbp+delta", "ibp", "skibp"])
+@pytest.mark.parametrize("framing", [N.FRAME_WORDS, N.FRAME_APP], ids=["words", "app"])
+def test_fast_path_batch_edges(ctx, cid, framing):
+    """Shapes that stress the batching of the fast path: batches whose values or compressed words overflow the
+    shared-memory staging (long lists among short ones, incompressible 32-bit data), empty lists, lists that are all
+    tail, exact multiples of 32 and 128, and negative (top-bit) values."""
+    rng = np.random.default_rng(cid * 7 + framing)
+    lists = []
+    for _ in range(400):
+        kind = rng.integers(0, 8)
+        n = int(rng.choice([0, 1, 5, 31, 32, 33, 64, 96, 100, 127, 128, 129, 160, 255, 256, 300, 512, 640, 1000]))
+        if kind == 0:
+            v = rng.integers(-2**31, 2**31 - 1, n)                              # incompressible: width 32
+        elif kind == 1:
+            v = np.sort(rng.integers(0, 2**31 - 1, n))                          # sorted, big gaps
+        elif kind == 2:
+            v = np.cumsum(rng.geometric(0.01, n))                               # breach-like
+        elif kind == 3:
+            v = np.full(n, int(rng.integers(0, 1000)))                          # constant: width 0 under delta
+        elif kind == 4:
+            v = rng.integers(0, 2 ** int(rng.integers(1, 31)), n)               # uniform width
+        elif kind == 5:
+            v = np.cumsum(rng.integers(0, 3, n)) + 2**31 - 50                   # crosses the sign bit
+        else:
+            v = rng.integers(0, 200, n)
+        lists.append(np.asarray(v, np.int64))
+    for j in (17, 211):
+        lists[j] = np.cumsum(rng.geometric(0.02, 6000))                         # longer than the value staging area
+    vals = np.concatenate([cases.to_i32(v) for v in lists])
+    off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum([len(v) for v in lists], out=off[1:])
+    out_off, out = ctx.codec_encode(cid, framing, vals, off)
+    assert out_off[0] == 0 and out_off[-1] == out.size
+    for i, v in enumerate(lists):
+        ref = cref.get_compressed_instruments(cid, v) if framing == N.FRAME_APP else cref.compress(cid, v).tobytes()
+        assert bytes(out[out_off[i]: out_off[i + 1]]) == ref, (i, len(v))
+    assert np.array_equal(ctx.codec_decode(cid, framing, out, out_off, off), vals)
+    # a malformed width anywhere in the batch is reported, not decoded
+    if framing == N.FRAME_WORDS and cid == N.CODEC_BP32_VB:
+        bad = out.copy()
+        i = next(k for k, v in enumerate(lists) if 32 <= len(v) < 128)
+        bad.view(np.uint32)[out_off[i] // 4 + 1] = 99
+        with pytest.raises(mcp_b200.McpError) as e:
+            ctx.codec_decode(cid, framing, bad, out_off, off)
+        assert e.value.code == N.MCP_E_FORMAT
 
 
 def test_multipage_fastpfor(ctx):
