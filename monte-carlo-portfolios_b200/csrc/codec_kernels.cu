@@ -772,6 +772,8 @@ __host__ __device__ inline bool fast_codec_ok(int codec, bool delta)
     return t.blocks && !t.fastpfor && !(t.integrated && delta);
 }
 
+constexpr uint64_t kLbAgg = 1ull << 62, kLbInc = 2ull << 62, kLbMask = (1ull << 62) - 1; // look-back state: flag | words
+
 __device__ __forceinline__ int sw33(int i) { return i + (i >> 5); } // 33-word stride per 32 values: conflict-free block reads
 
 __device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p)
@@ -835,8 +837,19 @@ __device__ __forceinline__ int bp_hdrs_before(int k, int nb)
     return k < 4 * ng ? (k >> 2) + 1 : ng + (k - 4 * ng) + 1;
 }
 
+// value i of a list's VariableByte tail as the codec sees it (g = its index in the staged batch, nb = blocks before it):
+// Delta pre-pass / IntegratedVariableByte gaps; the non-skippable integrated composition restarts the chain at 0
+// (IntegratedVariableByte.java:40), the skippable one continues it (:188-189)
+__device__ __forceinline__ uint32_t tail_value(const uint32_t *s_val, int g, int i, int nb, const CodecTraits tr, bool delta)
+{
+    const uint32_t x = s_val[sw33(g)];
+    if (tr.integrated) return (i > 0 || (tr.chain_tail && nb > 0)) ? x - s_val[sw33(g - 1)] : x;
+    return (delta && (i > 0 || nb > 0)) ? x - s_val[sw33(g - 1)] : x;
+}
+
 __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs a)
 {
+    __shared__ int s_tw[FE_MAXL];       // words of each list's VariableByte tail
     __shared__ uint32_t s_val[FE_VPAD];
     __shared__ uint32_t s_out[FE_OCAP];
     __shared__ int s_in[FE_MAXL + 1];   // value offset of each list inside the batch
@@ -870,11 +883,12 @@ __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs
     __syncthreads();
     const int64_t vbase = s_vbase;
     const int nv = s_in[nl];
-    bool fit = nv <= FE_VCAP;
+    const bool staged = nv <= FE_VCAP;
+    bool fit = false;
     long long T = 0; // words this batch produces
     int my_pos = 0, my_b = 0, my_list = 0, my_k = 0, my_start = 0;
     bool have_item = false;
-    if (fit) {
+    if (staged) {
         // ---- stage the values (coalesced), 33-word stride per 32 values
         for (int i = tid; i < nv; i += FE_THREADS) s_val[sw33(i)] = __ldg(a.vals + vbase + i);
         // ---- block items: list j owns items [s_ib[j], s_ib[j+1])
@@ -913,25 +927,24 @@ __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs
         s_bsum[tid] = bex;
         if (tid == 0) s_bsum[FE_THREADS] = tb;
         __syncthreads();
-        // ---- per list: words of the VariableByte tail and of the whole list
-        int lw = 0, tail_words = 0;
+        // ---- VariableByte tails (n mod 32 values per list): a warp per list, a lane per value
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int n = s_in[j + 1] - s_in[j], nb = n >> 5, r = n & 31;
+            int len = 0;
+            if (lane < r) len = vb_len(tail_value(s_val, s_in[j] + 32 * nb + lane, lane, nb, tr, a.delta));
+#pragma unroll
+            for (int d = 16; d; d >>= 1) len += __shfl_xor_sync(kFull, len, d);
+            if (lane == 0) s_tw[j] = (len + 3) >> 2;
+        }
+        __syncthreads();
+        // ---- per list: words of the whole list
+        int lw = 0;
         if (tid < nl) {
-            const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5, r = n & 31;
+            const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5;
             const int i0 = s_ib[tid];
             const int bw = s_bsum[i0 + nb] - s_bsum[i0]; // i0 + nb <= ni <= FE_THREADS
-            int bytes = 0;
-            const int g0 = s_in[tid] + 32 * nb;
-            for (int i = 0; i < r; ++i) {
-                const int g = g0 + i;
-                const uint32_t x = s_val[sw33(g)];
-                uint32_t d = x;
-                if (tr.integrated) { if (i > 0 || (tr.chain_tail && nb > 0)) d = x - s_val[sw33(g - 1)]; }
-                else if (a.delta && (i > 0 || nb > 0)) d = x - s_val[sw33(g - 1)];
-                bytes += vb_len(d);
-            }
-            tail_words = (bytes + 3) >> 2;
             const int hdrs = (nb >> 2) + (nb & 3);
-            lw = (n > 0 ? 1 + bw + hdrs + tail_words : (tr.sk ? 1 : 0)) + (a.app ? 1 : 0);
+            lw = (n > 0 ? 1 + bw + hdrs + s_tw[tid] : (tr.sk ? 1 : 0)) + (a.app ? 1 : 0);
         }
         int Tw = 0;
         const int lex = cta_excl_scan(lw, s_scan, &Tw);
@@ -940,6 +953,9 @@ __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs
         if (tid == 0) s_lo[nl] = Tw;
         __syncthreads();
         fit = T <= FE_OCAP;
+        // the batch's total is known: publish it NOW, so that by the time this batch has packed its blocks its
+        // predecessors' totals (and usually their prefixes) are already there
+        if (tid == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
         if (fit) {
             // ---- pack my block into the staged output (BitPacking.fastpackwithoutmask; IntegratedBitPacking
             // stores the raw values at width 32)
@@ -965,35 +981,31 @@ __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs
                 else if ((my_k & 3) == 0)
                     s_out[my_pos - 1] = ((uint32_t)my_b << 24) | ((uint32_t)s_w[tid + 1] << 16) | ((uint32_t)s_w[tid + 2] << 8) | (uint32_t)s_w[tid + 3];
             }
-            // ---- per list: header word, VariableByte tail, trailing zero int of the loader's framing
+            // ---- per list: header word and the trailing zero int of the loader's framing
             if (tid < nl) {
-                const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5, r = n & 31;
-                uint32_t *o = s_out + s_lo[tid];
-                if (n > 0 || tr.sk) o[0] = tr.sk ? (uint32_t)n : (uint32_t)(32 * nb); // IntCompressor: n; Composition: F1 header / 0 marker
-                if (r > 0) {
-                    uint32_t *tw = s_out + s_lo[tid + 1] - (a.app ? 1 : 0) - tail_words;
-                    const int g0 = s_in[tid] + 32 * nb;
-                    uint64_t acc = 0;
-                    int fill = 0;
-                    for (int i = 0; i < r; ++i) {
-                        const int g = g0 + i;
-                        const uint32_t x = s_val[sw33(g)];
-                        uint32_t d = x;
-                        if (tr.integrated) { if (i > 0 || (tr.chain_tail && nb > 0)) d = x - s_val[sw33(g - 1)]; }
-                        else if (a.delta && (i > 0 || nb > 0)) d = x - s_val[sw33(g - 1)];
-                        while (d >= 128u) { acc |= (uint64_t)(d & 127u) << fill; fill += 8; d >>= 7; if (fill >= 32) { *tw++ = (uint32_t)acc; acc >>= 32; fill -= 32; } }
-                        acc |= (uint64_t)(d | 128u) << fill; fill += 8;
-                        if (fill >= 32) { *tw++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
-                    }
-                    if (fill > 0) *tw = (uint32_t)acc; // zero-padded to a word (VariableByte.java:62-66)
-                }
+                const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5;
+                if (n > 0 || tr.sk) s_out[s_lo[tid]] = tr.sk ? (uint32_t)n : (uint32_t)(32 * nb); // IntCompressor: n; Composition: F1 header / 0 marker
                 if (a.app) s_out[s_lo[tid + 1] - 1] = 0u; // LoadPortfolios.java:622: outpos + 1 ints
+            }
+            // ---- VariableByte tails: lane i writes the bytes of tail value i at the warp-prefix of the byte lengths
+            for (int j = warp; j < nl; j += FE_THREADS / 32) {
+                const int n = s_in[j + 1] - s_in[j], nb = n >> 5, r = n & 31;
+                if (r == 0) continue;
+                uint32_t d = 0;
+                int len = 0;
+                if (lane < r) { d = tail_value(s_val, s_in[j] + 32 * nb + lane, lane, nb, tr, a.delta); len = vb_len(d); }
+                const int incl = (int)warp_incl_scan((uint32_t)len, lane);
+                const int total = __shfl_sync(kFull, incl, 31);
+                uint8_t *tb = reinterpret_cast<uint8_t *>(s_out + s_lo[j + 1] - (a.app ? 1 : 0) - s_tw[j]);
+                int o = incl - len;
+                for (int q = 0; q < len - 1; ++q) { tb[o++] = (uint8_t)(d & 127u); d >>= 7; }
+                if (len) tb[o] = (uint8_t)(d | 128u);
+                if (lane < ((4 - (total & 3)) & 3)) tb[total + lane] = 0; // zero-padded to a word (VariableByte.java:62-66)
             }
         }
     }
-    // ---- batches that do not fit the staging areas: sizes by the per-warp routines (one list per warp at a time)
-    if (!fit) {
-        __syncthreads();
+    // ---- batches whose values do not fit the staging area: sizes by the per-warp routines (one list per warp at a time)
+    if (!staged) {
         for (int j = warp; j < nl; j += FE_THREADS / 32) {
             const int64_t beg = a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len;
             const int64_t n = (a.list_off ? a.list_off[l0 + j + 1] : (l0 + j + 1) * a.uniform_len) - beg;
@@ -1005,31 +1017,40 @@ __global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs
             long long run = 0;
             for (int j = 0; j < nl; ++j) { const long long w = s_lo[j]; s_lo[j] = run; run += w; }
             s_lo[nl] = run;
+            st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)run);
         }
         __syncthreads();
         T = s_lo[nl];
     }
-    // ---- decoupled look-back: word offset of this batch in the output
-    if (tid == 0) {
-        constexpr uint64_t AGG = 1ull << 62, INC = 2ull << 62, MASK = (1ull << 62) - 1;
+    __syncthreads();
+    // ---- decoupled look-back by warp 0, 32 predecessors per round: word offset of this batch in the output.
+    // Batches take tickets in launch order, so every predecessor is already running and publishes its aggregate
+    // without waiting on anyone: the spin below is bounded.
+    if (warp == 0) {
         long long base = 0;
-        if (batch == 0) st_release_u64(a.state, INC | (uint64_t)T);
-        else {
-            st_release_u64(a.state + batch, AGG | (uint64_t)T);
-            for (int64_t j = batch - 1;; --j) {
-                uint64_t s;
-                do { s = ld_acquire_u64(a.state + j); } while ((s >> 62) == 0);
-                base += (long long)(s & MASK);
-                if ((s >> 62) == 2) break;
+        if (batch > 0) {
+            for (int64_t j = batch - 1;; j -= 32) {
+                const int64_t idx = j - lane;
+                uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
+                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
+                const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
+                long long v = lane <= first ? (long long)(st & kLbMask) : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+                base += v;
+                if (inc) break;
             }
-            st_release_u64(a.state + batch, INC | (uint64_t)(base + T));
+            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
         }
-        s_base = base;
-        if (batch == a.nbatches - 1) {
-            *a.total = 4 * (base + T);
-            a.out_off[a.nlists] = 4 * (base + T);
+        if (lane == 0) {
+            s_base = base;
+            if (batch == a.nbatches - 1) {
+                *a.total = 4 * (base + T);
+                a.out_off[a.nlists] = 4 * (base + T);
+            }
+            if (4 * (base + T) > a.cap) *a.err = 1;
         }
-        if (4 * (base + T) > a.cap) *a.err = 1;
     }
     __syncthreads();
     const int64_t base = s_base;
