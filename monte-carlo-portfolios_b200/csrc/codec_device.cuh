@@ -84,7 +84,9 @@ __device__ __forceinline__ uint32_t warp_unpack_val(uint32_t word, int b, int la
 // of a value; stream zero-padded to 4 bytes and stored as little-endian words.
 __device__ __forceinline__ int vb_len(uint32_t v)
 {
-    return v < (1u << 7) ? 1 : v < (1u << 14) ? 2 : v < (1u << 21) ? 3 : v < (1u << 28) ? 4 : 5;
+    // ceil(bits(v) / 7), at least 1: (bits + 6) / 7 with the division as a multiply-shift (exact for 6..38)
+    const int l = ((38 - __clz((int)v)) * 37) >> 8;
+    return l > 0 ? l : 1;
 }
 
 // Encodes `count` values produced by getv(i), i in [0,count).  `stage` is this warp's
@@ -139,9 +141,14 @@ __device__ __forceinline__ int64_t warp_vb_encode(GetV getv, int64_t count, cons
 // Decodes exactly `count` values from src words [p0, avail) (VariableByte.java:115-138
 // / :180-203).  With INTEGRATED the values are running sums starting at `init`
 // (IntegratedVariableByte.java:114-141, 227-254).  Returns false on a truncated stream.
-template <bool INTEGRATED>
-__device__ __forceinline__ bool warp_vb_decode(const WordSrc &src, int64_t p0, int64_t avail, int64_t count,
-                                               uint32_t *out, uint32_t init, int lane)
+struct PlainOut {
+    uint32_t *out;
+    __device__ __forceinline__ void operator()(int64_t i, uint32_t v) const { out[i] = v; }
+};
+
+template <bool INTEGRATED, class Src, class Out>
+__device__ __forceinline__ bool warp_vb_decode_to(const Src &src, int64_t p0, int64_t avail, int64_t count, const Out &put,
+                                                  uint32_t init, int lane)
 {
     int64_t decoded = 0;
     uint32_t carry_w = 0x80808080u; // "previous word ends on terminators": a value cannot start before the stream
@@ -188,7 +195,7 @@ __device__ __forceinline__ bool warp_vb_decode(const WordSrc &src, int64_t p0, i
             if (r < nv) {
                 uint32_t v = vals[r];
                 if (INTEGRATED) { basev += v; v = basev; }
-                if (idx < count) out[idx] = v;
+                if (idx < count) put(idx, v);
                 ++idx;
             }
         }
@@ -197,6 +204,13 @@ __device__ __forceinline__ bool warp_vb_decode(const WordSrc &src, int64_t p0, i
         p += 32;
     }
     return true;
+}
+
+template <bool INTEGRATED>
+__device__ __forceinline__ bool warp_vb_decode(const WordSrc &src, int64_t p0, int64_t avail, int64_t count,
+                                               uint32_t *out, uint32_t init, int lane)
+{
+    return warp_vb_decode_to<INTEGRATED>(src, p0, avail, count, PlainOut{out}, init, lane);
 }
 
 // In-place inclusive prefix sum over out[0..n) by one warp (Delta.inverseDelta, Delta.java:84-88)

@@ -763,7 +763,8 @@ __global__ void k_bswap_copy(const uint32_t *in, uint32_t *out, int64_t n)
 constexpr int FE_THREADS = 128;
 constexpr int FE_VCAP = 4096;   // staged values per batch: one 32-int block per thread
 constexpr int FE_MAXL = 128;    // lists per batch
-constexpr int FE_OCAP = 3328;   // staged compressed words per batch
+constexpr int FE_MINB = 7;      // resident CTAs per SM the kernels are compiled for (<= 72 registers, <= 31 KB shared memory)
+constexpr int FE_OCAP = 2304;   // staged compressed words per batch
 constexpr int FE_VPAD = FE_VCAP + FE_VCAP / 32 + 2;
 
 __host__ __device__ inline bool fast_codec_ok(int codec, bool delta)
@@ -847,7 +848,7 @@ __device__ __forceinline__ uint32_t tail_value(const uint32_t *s_val, int g, int
     return (delta && (i > 0 || nb > 0)) ? x - s_val[sw33(g - 1)] : x;
 }
 
-__global__ void __launch_bounds__(FE_THREADS) k_bp_encode_fast(const FastEncArgs a)
+__global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const FastEncArgs a)
 {
     __shared__ int s_tw[FE_MAXL];       // words of each list's VariableByte tail
     __shared__ uint32_t s_val[FE_VPAD];
@@ -1081,7 +1082,7 @@ struct FastDecArgs {
     int *err;
 };
 
-__global__ void __launch_bounds__(FE_THREADS) k_bp_decode_fast(const FastDecArgs a)
+__global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_decode_fast(const FastDecArgs a)
 {
     __shared__ uint32_t s_val[FE_VPAD];   // decoded values of the batch (33-word stride per 32)
     __shared__ uint32_t s_wd[FE_OCAP];    // compressed words of the batch, native order
