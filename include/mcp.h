@@ -174,7 +174,8 @@ int64_t mcp_tail_size(int64_t N, double alpha);
  */
 int mcp_run(mcp_ctx *ctx, double alpha, int codec_id, int framing);
 
-/* sizes of the last run */
+/* sizes of the last run (P = portfolios whose results the context holds: all of them, or the rank's slice after a
+ * trial-sharded run; N = trials the tail was taken over) */
 int mcp_run_sizes(mcp_ctx *ctx, int64_t *P, int64_t *N, int64_t *tail, int64_t *enc_bytes);
 /* diagnostics of the last run: *fallback_rows = portfolios whose optimistic filter bound was too tight and that
  * were redone with the guaranteed schedule (0 for exchangeable trial orders; results are exact either way) */
@@ -194,6 +195,38 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
                  double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
                  int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len);
 
+/* ------------------------------------------------- trial-sharded mode (optional)
+ * BASELINE config C5: every rank holds ALL exposure rows and a contiguous shard of the scenario rows (trials
+ * [trial_base, trial_base + N_local) of n_global, balanced: N_local <= ceil(n_global / world)).  Per portfolio the
+ * global tail is found from the ranks' local top-m candidates (m ~ tail/world + 6 sigma) exchanged by ONE all-gather;
+ * rows for which that is provably not enough (adversarial trial orders) go through a second round with the full
+ * local tails, so results are exact for any input.  After the run, rank g holds the results of its portfolio slice
+ * [P g / world, P (g+1) / world) (same split as portfolio sharding): mcp_run_sizes / mcp_fetch return that slice.
+ *
+ * (1) with NCCL inside the library: rank 0 calls mcp_comm_unique_id and hands the 128 bytes to the other ranks
+ *     through whatever channel the host application has; every rank calls mcp_comm_init, then mcp_run_trial_sharded.
+ *     NCCL is bound at run time (dlopen "libnccl.so.2"); MCP_E_NCCL if it is not installed.
+ */
+int mcp_comm_unique_id(uint8_t id[128]);
+int mcp_comm_init(mcp_ctx *ctx, const uint8_t id[128], int rank, int world);
+int mcp_comm_destroy(mcp_ctx *ctx);
+int mcp_run_trial_sharded(mcp_ctx *ctx, double alpha, int codec_id, int framing, int64_t n_global, int64_t trial_base);
+/* (2) with the caller's own transport (MPI, sockets, a JVM-side shuffle ...), phase by phase.  All block pointers are
+ *     DEVICE pointers; "gathered" = the world blocks of one round concatenated in rank order.
+ *       mcp_ts_local   : local candidates + moments -> this rank's block (owned by ctx, *block_bytes each)
+ *       mcp_ts_merge   : merge all rows from the gathered blocks; *flagged = rows needing the second round (the same
+ *                        number on every rank).  The gathered buffer must stay valid until mcp_ts_finish.
+ *       mcp_ts_local2 / mcp_ts_merge2 : second round, only if *flagged > 0
+ *       mcp_ts_finish  : breach lists, CVaR, pooled moments and encoding of this rank's portfolio slice
+ */
+int mcp_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes);
+int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *flagged);
+int mcp_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes);
+int mcp_ts_merge2(mcp_ctx *ctx, const void *d_gathered2);
+int mcp_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing);
+/* candidates per rank and portfolio the first round exchanges (for sizing / reporting) */
+int64_t mcp_ts_candidates(int64_t n_global, double alpha, int world);
+
 /* ------------------------------------------------------------- measurement
  * Kernel timing with CUDA events on ctx's own stream.  Classes: */
 enum {
@@ -204,7 +237,8 @@ enum {
     MCP_K_SCAN = 4,    /* prefix sums / bookkeeping                     */
     MCP_K_GEN = 5,     /* generators, FP64 peak probe                   */
     MCP_K_MOMENTS = 6, /* mean / variance (on a side stream: overlaps the valuation) */
-    MCP_K_COUNT = 7
+    MCP_K_COMM = 7,    /* NCCL all-gather of the trial-sharded mode             */
+    MCP_K_COUNT = 8
 };
 int mcp_profile_enable(mcp_ctx *ctx, int on);
 int mcp_profile_reset(mcp_ctx *ctx);

@@ -21,8 +21,8 @@ CODEC_BP32_VB, CODEC_FASTPFOR256_VB, CODEC_FASTPFOR128_VB, CODEC_IBP32_IVB, CODE
 CODEC_COUNT = 7
 FLAG_DELTA = 0x100
 FRAME_WORDS, FRAME_APP = 0, 1
-K_VALUE, K_SELECT, K_ENCODE, K_DECODE, K_SCAN, K_GEN, K_MOMENTS, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 7
-K_NAMES = ["value", "select", "encode", "decode", "scan", "gen", "moments"]
+K_VALUE, K_SELECT, K_ENCODE, K_DECODE, K_SCAN, K_GEN, K_MOMENTS, K_COMM, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
+K_NAMES = ["value", "select", "encode", "decode", "scan", "gen", "moments", "comm"]
 
 
 class McpError(RuntimeError):
@@ -87,6 +87,16 @@ def lib() -> C.CDLL:
         "mcp_run": (C.c_int, [vp, f64, C.c_int, C.c_int]),
         "mcp_run_sizes": (C.c_int, [vp, P(i64), P(i64), P(i64), P(i64)]),
         "mcp_run_stats": (C.c_int, [vp, P(i64)]),
+        "mcp_comm_unique_id": (C.c_int, [vp]),
+        "mcp_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "mcp_comm_destroy": (C.c_int, [vp]),
+        "mcp_run_trial_sharded": (C.c_int, [vp, f64, C.c_int, C.c_int, i64, i64]),
+        "mcp_ts_local": (C.c_int, [vp, f64, i64, i64, C.c_int, P(vp), P(i64)]),
+        "mcp_ts_merge": (C.c_int, [vp, vp, P(i64)]),
+        "mcp_ts_local2": (C.c_int, [vp, P(vp), P(i64)]),
+        "mcp_ts_merge2": (C.c_int, [vp, vp]),
+        "mcp_ts_finish": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "mcp_ts_candidates": (i64, [i64, f64, C.c_int]),
         "mcp_fetch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64]),
         "mcp_simulate": (C.c_int, [vp, vp, i64, vp, i64, i32, f64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, i64, P(i64)]),
         "mcp_profile_enable": (C.c_int, [vp, C.c_int]),

@@ -73,6 +73,7 @@ struct mcp_ctx {
     // results of the last run (device)
     mcp::DevBuf dMean, dVar, dVarLoss, dVarTrial, dCvar, dBreach, dEncOff, dEnc;
     int64_t runP = 0, runN = 0, runTail = 0, runEncBytes = 0;
+    int64_t runRow0 = 0;           // first portfolio of the result arrays that the last run produced (trial-sharded: the rank's slice)
     bool haveRun = false;
 
     // scratch
@@ -93,6 +94,13 @@ struct mcp_ctx {
     bool optimistic = true;        // two-step schedule with the optimistic filter bound (risk_kernels.cu)
     int64_t itemTrials = 2048;     // target trials per valuation CTA work item (amortises the exposure-tile prologue)
     int64_t runFallbackRows = 0;   // rows the last run had to redo with the guaranteed schedule
+    // trial-sharded mode (risk_kernels.cu): state between the phase calls
+    int64_t tsT = 0, tsM = 0, tsNGlobal = 0, tsTrialBase = 0, tsNFlag = 0, tsSlackOverride = -1;
+    int tsWorld = 0;
+    const unsigned char *tsGath = nullptr; // first-round gathered blocks (caller- or library-owned), needed until ts_finish
+    std::vector<int32_t> tsFlagRows;
+    mcp::DevBuf dTsSend, dTsRecv, dTsRecv2, dTsFlags;
+    void *nccl = nullptr;          // NcclComm* (nccl_dyn.cu), null until mcp_comm_init
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
@@ -204,5 +212,18 @@ int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t
 int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
                      int64_t *total);
 int fp64_peak(mcp_ctx *ctx, double *tflops);
+int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world);
+int risk_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes);
+int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *nflag_out);
+int risk_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes);
+int risk_ts_merge2(mcp_ctx *ctx, const void *d_gathered2);
+int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing);
+
+// nccl_dyn.cu: NCCL bound at run time (dlopen), so that libmcp.so loads on boxes without it
+int nccl_unique_id(unsigned char id[128], std::string *err);
+int nccl_comm_init(mcp_ctx *ctx, const unsigned char id[128], int rank, int world);
+void nccl_comm_destroy(mcp_ctx *ctx);
+int nccl_all_gather(mcp_ctx *ctx, const void *send, void *recv, size_t bytes);
+int nccl_rank_world(mcp_ctx *ctx, int *rank, int *world);
 
 } // namespace mcp

@@ -113,6 +113,7 @@ void mcp_destroy(mcp_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     resolve_profile(ctx);
+    nccl_comm_destroy(ctx);
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
     mcp::DevBuf *bufs[] = {&ctx->dE, &ctx->dS, &ctx->dMean, &ctx->dVar, &ctx->dVarLoss, &ctx->dVarTrial, &ctx->dCvar,
                            &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dShift, &ctx->dSizes,
@@ -120,7 +121,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
                            &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
-                           &ctx->dFbKey, &ctx->dFbIdx};
+                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -151,6 +152,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
+    else if (!strcmp(key, "ts_slack")) ctx->tsSlackOverride = value; // trial-sharded test hook: m = ceil(t / world) + value (-1 = automatic)
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
     return MCP_OK;
@@ -491,14 +493,14 @@ int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, in
 {
     MCP_TRY(set_dev(ctx));
     if (!ctx->haveRun) return fail(ctx, MCP_E_STATE, "fetch: no completed run");
-    const size_t P = (size_t)ctx->runP;
+    const size_t P = (size_t)ctx->runP, r0 = (size_t)ctx->runRow0; // r0 > 0: the slice a trial-sharded run left on this rank
     if (enc && enc_cap < ctx->runEncBytes) return fail(ctx, MCP_E_CAP, "fetch: encoded buffer too small");
-    if (mean) MCP_TRY(d2h(ctx, mean, ctx->dMean.p, P * sizeof(double)));
-    if (variance) MCP_TRY(d2h(ctx, variance, ctx->dVar.p, P * sizeof(double)));
-    if (var_loss) MCP_TRY(d2h(ctx, var_loss, ctx->dVarLoss.p, P * sizeof(double)));
-    if (var_trial) MCP_TRY(d2h(ctx, var_trial, ctx->dVarTrial.p, P * sizeof(int32_t)));
-    if (cvar) MCP_TRY(d2h(ctx, cvar, ctx->dCvar.p, P * sizeof(double)));
-    if (breach_idx) MCP_TRY(d2h(ctx, breach_idx, ctx->dBreach.p, P * (size_t)ctx->runTail * sizeof(int32_t)));
+    if (mean) MCP_TRY(d2h(ctx, mean, ctx->dMean.as<double>() + r0, P * sizeof(double)));
+    if (variance) MCP_TRY(d2h(ctx, variance, ctx->dVar.as<double>() + r0, P * sizeof(double)));
+    if (var_loss) MCP_TRY(d2h(ctx, var_loss, ctx->dVarLoss.as<double>() + r0, P * sizeof(double)));
+    if (var_trial) MCP_TRY(d2h(ctx, var_trial, ctx->dVarTrial.as<int32_t>() + r0, P * sizeof(int32_t)));
+    if (cvar) MCP_TRY(d2h(ctx, cvar, ctx->dCvar.as<double>() + r0, P * sizeof(double)));
+    if (breach_idx) MCP_TRY(d2h(ctx, breach_idx, ctx->dBreach.as<int32_t>() + r0 * (size_t)ctx->runTail, P * (size_t)ctx->runTail * sizeof(int32_t)));
     if (enc_off) MCP_TRY(d2h(ctx, enc_off, ctx->dEncOff.p, (P + 1) * sizeof(int64_t)));
     if (enc) MCP_TRY(d2h(ctx, enc, ctx->dEnc.p, (size_t)ctx->runEncBytes));
     return sync(ctx);
@@ -515,6 +517,104 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
     if (enc_len) *enc_len = ctx->runEncBytes;
     return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
+}
+
+// ---------------------------------------------------------- trial-sharded mode
+int mcp_comm_unique_id(uint8_t id[128])
+{
+    if (!id) return MCP_E_ARG;
+    return nccl_unique_id(id, nullptr);
+}
+
+int mcp_comm_init(mcp_ctx *ctx, const uint8_t id[128], int rank, int world)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!id) return fail(ctx, MCP_E_ARG, "comm_init: null id");
+    return nccl_comm_init(ctx, id, rank, world);
+}
+
+int mcp_comm_destroy(mcp_ctx *ctx)
+{
+    MCP_TRY(set_dev(ctx));
+    nccl_comm_destroy(ctx);
+    return MCP_OK;
+}
+
+static int ts_check_args(mcp_ctx *ctx, double alpha, int codec_id, int framing)
+{
+    if (!ctx->haveE || !ctx->haveS) return fail(ctx, MCP_E_STATE, "trial-sharded run: upload exposures and scenarios first");
+    if (!(alpha > 0.0 && alpha <= 1.0)) return fail(ctx, MCP_E_ARG, "run: alpha must be in (0,1]");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
+    return MCP_OK;
+}
+
+int mcp_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(ts_check_args(ctx, alpha, 0, 0));
+    MCP_TRY(risk_ts_local(ctx, alpha, n_global, trial_base, world, d_block, block_bytes));
+    return sync(ctx);
+}
+
+int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *flagged)
+{
+    MCP_TRY(set_dev(ctx));
+    return risk_ts_merge(ctx, d_gathered, flagged);
+}
+
+int mcp_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(risk_ts_local2(ctx, d_block, block_bytes));
+    return sync(ctx);
+}
+
+int mcp_ts_merge2(mcp_ctx *ctx, const void *d_gathered2)
+{
+    MCP_TRY(set_dev(ctx));
+    return risk_ts_merge2(ctx, d_gathered2);
+}
+
+int mcp_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
+    return risk_ts_finish(ctx, rank, world, codec_id, framing);
+}
+
+int64_t mcp_ts_candidates(int64_t n_global, double alpha, int world)
+{
+    if (n_global <= 0 || world < 1) return -1;
+    return ts_candidates_per_rank(n_global, mcp_tail_size(n_global, alpha), world);
+}
+
+int mcp_run_trial_sharded(mcp_ctx *ctx, double alpha, int codec_id, int framing, int64_t n_global, int64_t trial_base)
+{
+    MCP_TRY(set_dev(ctx));
+    MCP_TRY(ts_check_args(ctx, alpha, codec_id, framing));
+    int rank = 0, world = 1;
+    MCP_TRY(nccl_rank_world(ctx, &rank, &world));
+    void *blk = nullptr;
+    int64_t bytes = 0, flagged = 0;
+    MCP_TRY(risk_ts_local(ctx, alpha, n_global, trial_base, world, &blk, &bytes));
+    MCP_CUDA(ctx, ctx->dTsRecv.reserve((size_t)bytes * world));
+    {
+        KScope ks(ctx, MCP_K_COMM);
+        MCP_TRY(nccl_all_gather(ctx, blk, ctx->dTsRecv.p, (size_t)bytes)); // the one exchange of the common case
+    }
+    MCP_TRY(risk_ts_merge(ctx, ctx->dTsRecv.p, &flagged));
+    if (flagged > 0) { // same count on every rank: the collective below is entered by all of them
+        MCP_TRY(risk_ts_local2(ctx, &blk, &bytes));
+        MCP_CUDA(ctx, ctx->dTsRecv2.reserve((size_t)bytes * world));
+        {
+            KScope ks(ctx, MCP_K_COMM);
+            MCP_TRY(nccl_all_gather(ctx, blk, ctx->dTsRecv2.p, (size_t)bytes));
+        }
+        MCP_TRY(risk_ts_merge2(ctx, ctx->dTsRecv2.p));
+    }
+    return risk_ts_finish(ctx, rank, world, codec_id, framing);
 }
 
 // ---------------------------------------------------------------- measurement

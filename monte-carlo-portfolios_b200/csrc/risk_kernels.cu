@@ -738,6 +738,8 @@ struct SelArgs {
     const uint64_t *kept_key_in;
     const int32_t *kept_idx_in;
     int64_t kept_n;            // entries (= row stride) of the kept_*_in rows; 0 on the first step
+    int kept_segs;             // > 1: the kept rows come in `kept_segs` blocks (one per rank of a trial-sharded run,
+    int64_t kept_seg_bytes;    //   `kept_seg_bytes` apart), each [rows][kept_n / kept_segs]: row r = the blocks' rows r
     uint64_t *kept_key_out;    // [rows][tail]
     int32_t *kept_idx_out;
     int64_t tail;              // t
@@ -771,12 +773,29 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
     return t;
 }
 
+// entry i of row `row` of the kept tail handed to the selection (one array, or one block per rank)
+__device__ __forceinline__ void kept_at(const SelArgs &a, int64_t row, int64_t i, uint64_t &key, uint32_t &idx)
+{
+    if (a.kept_segs <= 1) {
+        key = a.kept_key_in[row * a.kept_n + i];
+        idx = (uint32_t)a.kept_idx_in[row * a.kept_n + i];
+        return;
+    }
+    const int64_t m = a.kept_n / a.kept_segs, g = i / m, j = i - g * m;
+    key = *reinterpret_cast<const uint64_t *>(reinterpret_cast<const unsigned char *>(a.kept_key_in) + g * a.kept_seg_bytes + (row * m + j) * 8);
+    idx = (uint32_t)*reinterpret_cast<const int32_t *>(reinterpret_cast<const unsigned char *>(a.kept_idx_in) + g * a.kept_seg_bytes + (row * m + j) * 4);
+}
+
 // visit every candidate of the row straight from global memory
 template <class Fn>
 __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, const int *segoff, Fn f)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) f(a.kept_key_in[row * a.kept_n + i], (uint32_t)a.kept_idx_in[row * a.kept_n + i]);
+    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) {
+        uint64_t k; uint32_t id;
+        kept_at(a, row, i, k, id);
+        f(k, id);
+    }
     const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
     if (a.cnt) {
         // sparse step: many short lane-private segments of 16-byte records.  Flat index over all their entries
@@ -896,7 +915,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             mn = k < mn ? k : mn; mx = k > mx ? k : mx;
         };
         const int kn = (int)a.kept_n;
-        for (int i = tid; i < kn; i += SEL_THREADS) put(i, a.kept_key_in[row * a.kept_n + i], (uint32_t)a.kept_idx_in[row * a.kept_n + i]);
+        for (int i = tid; i < kn; i += SEL_THREADS) {
+            uint64_t k; uint32_t id;
+            kept_at(a, row, i, k, id);
+            put(i, k, id);
+        }
         const unsigned char *rowp = reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch;
         if (a.cnt) {
             // sparse step: ~3 records in each of several hundred lane-private segments.  Phase 1: every thread labels
@@ -1319,14 +1342,16 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
     return steps;
 }
 
-static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *kk, const int32_t *ki, int32_t *breach, double *cvar)
+static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *kk, const int32_t *ki, int32_t *breach, double *cvar,
+                        int64_t n_trials = -1)
 {
-    if (fin_bitmap_smem(ctx->N, t) <= FIN_BITMAP_MAX_SMEM && !ctx->forceSortFinalize) {
-        const size_t bm_smem = fin_bitmap_smem(ctx->N, t);
+    if (n_trials < 0) n_trials = ctx->N;
+    if (fin_bitmap_smem(n_trials, t) <= FIN_BITMAP_MAX_SMEM && !ctx->forceSortFinalize) {
+        const size_t bm_smem = fin_bitmap_smem(n_trials, t);
         if (bm_smem > 48 * 1024)
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
         KScope ks(ctx, MCP_K_SELECT);
-        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, ctx->stream>>>(kk, ki, t, ctx->N, 0, breach, cvar);
+        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, ctx->stream>>>(kk, ki, t, n_trials, 0, breach, cvar);
         return check_launch(ctx, "k_finalize_bitmap");
     }
     int m = 1;
@@ -1530,10 +1555,12 @@ struct StreamIO {
     uint64_t *tkey;                                                      // [P]
     bool moments;                                                        // fused per-trial moments into ctx->dPart
     int *fail_cnt; int32_t *fail_rows;                                   // non-null: optimistic schedule
+    bool keep_only;                                                      // stop after the selection: the kept tail is the result
+    int final_buf;                                                       // (out) which of kkey/kidx holds the kept tail
 };
 
 // streaming valuation (FP64 tensor cores) + threshold filter + radix-select; `optimistic` picks the schedule
-static int risk_stream_core(mcp_ctx *ctx, const StreamIO &io, int64_t t, bool optimistic, int *nparts_out)
+static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimistic, int *nparts_out)
 {
     const int64_t P = io.P, N = ctx->N;
     const int sms = ctx->prop.multiProcessorCount;
@@ -1627,7 +1654,8 @@ static int risk_stream_core(mcp_ctx *ctx, const StreamIO &io, int64_t t, bool op
             cur ^= 1;
             part_base += s.nsub;
         }
-        MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], io.breach + p0 * t, io.cvar + p0));
+        io.final_buf = cur;
+        if (!io.keep_only) MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], io.breach + p0 * t, io.cvar + p0));
     }
     return MCP_OK;
 }
@@ -1702,6 +1730,346 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
     return MCP_OK;
 }
 
+// ============================================================ trial-sharded mode (BASELINE config C5)
+// Rank g holds ALL P exposure rows and the scenario rows [trial_base, trial_base + N_local) of an N_global-trial run.
+// Per portfolio the global tail (t largest losses of N_global) is found from the ranks' LOCAL top-m candidates,
+// m ~ t/G + 6 sigma, exchanged by ONE all-gather of fixed-stride blocks:
+//     block = [header 64 B][keys P*m u64][mean P f64][variance P f64][global trial idx P*m i32]
+// Every rank then merges all P rows from the gathered blocks (cheap next to the valuation), which makes the
+// exactness test deterministic and identical on all ranks without another exchange: a row is exact unless some rank
+// g had more candidates than it sent AND its smallest sent candidate still beats the merged threshold (then rank g may
+// hold unsent trials of the tail).  Such rows -- only adversarial trial orders produce them -- go through a second
+// round with the full local tails (m = t), so the result is exact for any input.  Finalisation (breach list, CVaR,
+// moments by Chan's pooled-variance rule, encoding) is done per rank for its portfolio slice [P g/G, P (g+1)/G).
+// The exchange itself is the caller's (mcp_ts_* phase calls: any transport) or NCCL's (mcp_run_trial_sharded).
+struct TsLayout { int64_t P, m, off_keys, off_mean, off_var, off_idx, bytes; };
+static TsLayout ts_layout(int64_t P, int64_t m)
+{
+    TsLayout L{};
+    L.P = P; L.m = m;
+    L.off_keys = 64;
+    L.off_mean = L.off_keys + P * m * 8;
+    L.off_var = L.off_mean + P * 8;
+    L.off_idx = L.off_var + P * 8;
+    L.bytes = (L.off_idx + P * m * 4 + 15) & ~(int64_t)15;
+    return L;
+}
+
+int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world)
+{
+    const int64_t nmax = (n_global + world - 1) / world; // largest shard of a balanced split
+    const double share = (double)t * (double)nmax / (double)n_global;
+    int64_t m = (int64_t)ceil(share + 6.0 * sqrt(share * (1.0 - 1.0 / world)) + 8.0);
+    if (m > t) m = t;
+    if (m > nmax) m = nmax;
+    return m < 1 ? 1 : m;
+}
+
+// kept tail of the local selection -> this rank's exchange block (trial indices made global; rows with fewer than m
+// local trials are padded with key 0, which sorts below every real loss)
+__global__ void k_ts_pack(const uint64_t *kkey, const int32_t *kidx, int64_t P, int64_t m, int64_t m_have, int64_t trial_base,
+                          int64_t n_local, const double *mean, const double *var, unsigned char *block, TsLayout L)
+{
+    const int64_t total = P * m;
+    uint64_t *ok = reinterpret_cast<uint64_t *>(block + L.off_keys);
+    int32_t *oi = reinterpret_cast<int32_t *>(block + L.off_idx);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / m, j = i - p * m;
+        const bool have = j < m_have;
+        ok[i] = have ? kkey[p * m_have + j] : 0ull;
+        oi[i] = have ? (int32_t)(kidx[p * m_have + j] + trial_base) : -1;
+    }
+    if (mean) {
+        double *om = reinterpret_cast<double *>(block + L.off_mean), *ov = reinterpret_cast<double *>(block + L.off_var);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) { om[i] = mean[i]; ov[i] = var[i]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t *h = reinterpret_cast<int64_t *>(block);
+        h[0] = n_local; h[1] = m; h[2] = P; h[3] = trial_base;
+    }
+}
+
+// one warp per row: exact unless a rank that held back candidates has its smallest sent one above the threshold
+__global__ void __launch_bounds__(256) k_ts_check(const unsigned char *gath, int world, TsLayout L, int64_t rows, const int32_t *row_ids,
+                                                  const double *var_loss, const int32_t *var_trial, unsigned char *flags, int *nflag)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t out_row = row_ids ? row_ids[r] : r; // where the merged threshold of this row lives
+    const uint64_t tk = fkey(var_loss[out_row]);
+    const uint32_t ti = (uint32_t)var_trial[out_row];
+    bool bad = false;
+    for (int g = 0; g < world; ++g) {
+        const unsigned char *blk = gath + (int64_t)g * L.bytes;
+        const int64_t n_local = reinterpret_cast<const int64_t *>(blk)[0];
+        if (L.m >= n_local) continue; // the rank sent every trial it has
+        const uint64_t *k = reinterpret_cast<const uint64_t *>(blk + L.off_keys) + r * L.m;
+        const int32_t *ix = reinterpret_cast<const int32_t *>(blk + L.off_idx) + r * L.m;
+        uint64_t mk = ~0ull;
+        uint32_t mi = 0xffffffffu;
+        for (int64_t j = lane; j < L.m; j += 32) {
+            const uint64_t kk = k[j];
+            const uint32_t ii = (uint32_t)ix[j];
+            if (kk < mk || (kk == mk && ii < mi)) { mk = kk; mi = ii; }
+        }
+        for (int d = 16; d; d >>= 1) {
+            const uint64_t ok = __shfl_xor_sync(kFullMask, mk, d);
+            const uint32_t oi = __shfl_xor_sync(kFullMask, mi, d);
+            if (ok < mk || (ok == mk && oi < mi)) { mk = ok; mi = oi; }
+        }
+        if (mk > tk || (mk == tk && mi > ti)) bad = true;
+    }
+    if (lane == 0) {
+        flags[r] = bad ? 1 : 0;
+        if (bad) atomicAdd(nflag, 1);
+    }
+}
+
+// Chan et al. pooled mean / population variance of the ranks' per-shard moments, rows [p0, p1)
+__global__ void k_ts_moments_merge(const unsigned char *gath, int world, TsLayout L, int64_t p0, int64_t p1, double *mean, double *variance)
+{
+    const int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    double n = 0.0, mu = 0.0, m2 = 0.0;
+    for (int g = 0; g < world; ++g) {
+        const unsigned char *blk = gath + (int64_t)g * L.bytes;
+        const double ng = (double)reinterpret_cast<const int64_t *>(blk)[0];
+        if (ng <= 0.0) continue;
+        const double mg = reinterpret_cast<const double *>(blk + L.off_mean)[p], vg = reinterpret_cast<const double *>(blk + L.off_var)[p];
+        const double d = mg - mu, nn = n + ng;
+        m2 += vg * ng + d * d * (n * ng / nn);
+        mu += d * (ng / nn);
+        n = nn;
+    }
+    mean[p] = mu;
+    variance[p] = m2 / n;
+}
+
+// rows of the [rows][t] kept arrays of a compact problem -> rows `ids` of the full arrays
+__global__ void k_ts_scatter_kept(const int32_t *ids, int64_t t, const uint64_t *kk, const int32_t *ki, const double *vl, const int32_t *vt,
+                                  uint64_t *okk, int32_t *oki, double *ovl, int32_t *ovt)
+{
+    const int64_t i = blockIdx.x, r = ids[i];
+    if (threadIdx.x == 0) { ovl[r] = vl[i]; ovt[r] = vt[i]; }
+    for (int64_t j = threadIdx.x; j < t; j += blockDim.x) { okk[r * t + j] = kk[i * t + j]; oki[r * t + j] = ki[i * t + j]; }
+}
+
+// local top-`m` (keys + local trial indices) of `rows` exposure rows at E, by the guaranteed schedule -> block.
+// kk / ki: two scratch arrays of rows * min(m, N_local) entries each (the selection's ping-pong).
+static int ts_local_block(mcp_ctx *ctx, const double *E, int64_t rows, int64_t m, bool with_moments, uint64_t *const kk[2], int32_t *const ki[2],
+                          mcp::DevBuf &blockbuf, TsLayout &L)
+{
+    const int64_t m_have = m < ctx->N ? m : ctx->N;
+    MCP_CUDA(ctx, ctx->dTau.reserve((size_t)rows * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)rows * 16));
+    {
+        int64_t cap = 4 * m_have + 264;
+        if (cap < 2304) cap = 2304;
+        if (cap > 16384) cap = 16384;
+        ctx->selCap = (int)cap;
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(16384, kSelMaxSeg)));
+    }
+    StreamIO io{};
+    io.E = E; io.P = rows;
+    io.var_loss = ctx->dFbOut.as<double>(); io.var_trial = reinterpret_cast<int32_t *>(ctx->dFbOut.as<double>() + rows); // scratch: local order statistics
+    io.kkey[0] = kk[0]; io.kkey[1] = kk[1];
+    io.kidx[0] = ki[0]; io.kidx[1] = ki[1];
+    io.tkey = ctx->dTau.as<uint64_t>();
+    io.keep_only = true;
+    MCP_TRY(risk_stream_core(ctx, io, m_have, false, nullptr));
+    L = ts_layout(rows, m);
+    MCP_CUDA(ctx, blockbuf.reserve((size_t)L.bytes));
+    KScope ks(ctx, MCP_K_SELECT);
+    k_ts_pack<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(io.kkey[io.final_buf], io.kidx[io.final_buf], rows, m, m_have, ctx->tsTrialBase,
+                                                                         ctx->N, with_moments ? ctx->dMean.as<double>() : nullptr,
+                                                                         with_moments ? ctx->dVar.as<double>() : nullptr, blockbuf.as<unsigned char>(), L);
+    return check_launch(ctx, "k_ts_pack");
+}
+
+int risk_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes)
+{
+    const int64_t P = ctx->P, N = ctx->N;
+    if (P <= 0 || N <= 0) return fail(ctx, MCP_E_STATE, "trial-sharded run: empty problem");
+    if (world < 1 || n_global < N || trial_base < 0 || trial_base + N > n_global || n_global > 0x7fffffff)
+        return fail(ctx, MCP_E_ARG, "trial-sharded run: bad trial range");
+    if (N > (n_global + world - 1) / world) return fail(ctx, MCP_E_ARG, "trial-sharded run: shards must be balanced (N_local <= ceil(N_global / world))");
+    if (!mma_supported(ctx->F)) return fail(ctx, MCP_E_UNSUPPORTED, "trial-sharded run: factor count must be 16, 32, 48 or 64");
+    ctx->haveRun = false;
+    ctx->tsT = mcp_tail_size(n_global, alpha);
+    ctx->tsM = ts_candidates_per_rank(n_global, ctx->tsT, world);
+    if (ctx->tsSlackOverride >= 0) { // test hook: force a tighter m so that the second round is exercised
+        int64_t m = (ctx->tsT + world - 1) / world + ctx->tsSlackOverride;
+        if (m > ctx->tsT) m = ctx->tsT;
+        ctx->tsM = m < 1 ? 1 : m;
+    }
+    ctx->tsNGlobal = n_global; ctx->tsTrialBase = trial_base; ctx->tsWorld = world; ctx->tsNFlag = 0; ctx->tsGath = nullptr;
+    MCP_CUDA(ctx, ctx->dMean.reserve(P * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dVar.reserve(P * sizeof(double)));
+    // mean / variance of this shard's trials by linearity, on the side stream under the valuation
+    MCP_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+    MCP_TRY(run_moments_linear(ctx));
+    MCP_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+    MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    TsLayout L;
+    {
+        const int64_t mh = ctx->tsM < N ? ctx->tsM : N;
+        MCP_CUDA(ctx, ctx->dKeptKey.reserve((size_t)P * mh * sizeof(uint64_t)));
+        MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * mh * sizeof(int32_t)));
+        MCP_CUDA(ctx, ctx->dKept2Key.reserve((size_t)P * mh * sizeof(uint64_t)));
+        MCP_CUDA(ctx, ctx->dKept2Idx.reserve((size_t)P * mh * sizeof(int32_t)));
+        uint64_t *const kk[2] = {ctx->dKeptKey.as<uint64_t>(), ctx->dKept2Key.as<uint64_t>()};
+        int32_t *const ki[2] = {ctx->dKeptIdx.as<int32_t>(), ctx->dKept2Idx.as<int32_t>()};
+        MCP_TRY(ts_local_block(ctx, ctx->dE.as<double>(), P, ctx->tsM, true, kk, ki, ctx->dTsSend, L));
+    }
+    if (d_block) *d_block = ctx->dTsSend.p;
+    if (block_bytes) *block_bytes = L.bytes;
+    return MCP_OK;
+}
+
+// merge `rows` rows of `world` gathered blocks (layout L): top-t into kkey/kidx[rows][t], thresholds into vl/vt
+static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, const TsLayout &L, int64_t rows, int64_t t, uint64_t *kkey,
+                         int32_t *kidx, double *vl, int32_t *vt)
+{
+    SelArgs a{};
+    a.kept_key_in = reinterpret_cast<const uint64_t *>(gath + L.off_keys);
+    a.kept_idx_in = reinterpret_cast<const int32_t *>(gath + L.off_idx);
+    a.kept_n = (int64_t)world * L.m;
+    a.kept_segs = world;
+    a.kept_seg_bytes = L.bytes;
+    a.kept_key_out = kkey; a.kept_idx_out = kidx;
+    a.tail = t;
+    a.var_loss = vl; a.var_trial = vt;
+    int64_t cap = a.kept_n + 8;
+    if (cap < 2304) cap = 2304;
+    if (cap > 16384) cap = 16384;
+    a.cap = (int)cap;
+    MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(16384, kSelMaxSeg)));
+    KScope ks(ctx, MCP_K_SELECT);
+    k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a);
+    return check_launch(ctx, "k_select (merge)");
+}
+
+int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *nflag_out)
+{
+    if (ctx->tsWorld < 1 || !d_gathered) return fail(ctx, MCP_E_STATE, "ts_merge: call ts_local first");
+    const int64_t P = ctx->P, t = ctx->tsT;
+    const TsLayout L = ts_layout(P, ctx->tsM);
+    const unsigned char *g = reinterpret_cast<const unsigned char *>(d_gathered);
+    ctx->tsGath = g;
+    MCP_CUDA(ctx, ctx->dVarLoss.reserve(P * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dVarTrial.reserve(P * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dKeptKey.reserve((size_t)P * t * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * t * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dFail.reserve((size_t)(P + 4) * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dTsFlags.reserve((size_t)P + 16));
+    MCP_TRY(ts_merge_rows(ctx, g, ctx->tsWorld, L, P, t, ctx->dKeptKey.as<uint64_t>(), ctx->dKeptIdx.as<int32_t>(), ctx->dVarLoss.as<double>(),
+                          ctx->dVarTrial.as<int32_t>()));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dFail.p, 0, sizeof(int), ctx->stream));
+    {
+        KScope ks(ctx, MCP_K_SELECT);
+        k_ts_check<<<(unsigned)((P * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->tsWorld, L, P, nullptr, ctx->dVarLoss.as<double>(),
+                                                                             ctx->dVarTrial.as<int32_t>(), ctx->dTsFlags.as<unsigned char>(), ctx->dFail.as<int>());
+        MCP_TRY(check_launch(ctx, "k_ts_check"));
+    }
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dFail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tsNFlag = *reinterpret_cast<int *>(ctx->hPinned);
+    ctx->tsFlagRows.clear();
+    if (ctx->tsNFlag > 0) {
+        // the flagged rows in ascending order (identical on every rank: all ranks merged the same blocks)
+        std::vector<unsigned char> f((size_t)P);
+        MCP_CUDA(ctx, cudaMemcpyAsync(f.data(), ctx->dTsFlags.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t p = 0; p < P; ++p)
+            if (f[(size_t)p]) ctx->tsFlagRows.push_back((int32_t)p);
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dFail.as<int32_t>() + 4, ctx->tsFlagRows.data(), ctx->tsFlagRows.size() * sizeof(int32_t),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (nflag_out) *nflag_out = ctx->tsNFlag;
+    return MCP_OK;
+}
+
+// second round, flagged rows only: the FULL local tail (min(t, N_local) candidates) of every flagged row
+int risk_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes)
+{
+    const int64_t nf = ctx->tsNFlag;
+    if (nf <= 0) return fail(ctx, MCP_E_STATE, "ts_local2: no flagged rows");
+    const int F = ctx->F;
+    MCP_CUDA(ctx, ctx->dFbE.reserve((size_t)nf * F * sizeof(double)));
+    {
+        KScope ks(ctx, MCP_K_SELECT);
+        k_gather_rows<<<(unsigned)std::min<int64_t>((nf * F + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->dFail.as<int32_t>() + 4, nf, F,
+                                                                                                      ctx->dFbE.as<double>());
+        MCP_TRY(check_launch(ctx, "k_gather_rows"));
+    }
+    // (the first round's merged tails stay in dKeptKey / dKeptIdx; this selection ping-pongs in the fallback buffers)
+    const int64_t t = ctx->tsT, mh = t < ctx->N ? t : ctx->N;
+    MCP_CUDA(ctx, ctx->dFbKey.reserve((size_t)nf * mh * 2 * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dFbIdx.reserve((size_t)nf * mh * 2 * sizeof(int32_t)));
+    uint64_t *const kk[2] = {ctx->dFbKey.as<uint64_t>(), ctx->dFbKey.as<uint64_t>() + nf * mh};
+    int32_t *const ki[2] = {ctx->dFbIdx.as<int32_t>(), ctx->dFbIdx.as<int32_t>() + nf * mh};
+    TsLayout L;
+    MCP_TRY(ts_local_block(ctx, ctx->dFbE.as<double>(), nf, t, false, kk, ki, ctx->dTsSend, L));
+    if (d_block) *d_block = ctx->dTsSend.p;
+    if (block_bytes) *block_bytes = L.bytes;
+    return MCP_OK;
+}
+
+int risk_ts_merge2(mcp_ctx *ctx, const void *d_gathered2)
+{
+    const int64_t nf = ctx->tsNFlag, t = ctx->tsT;
+    if (nf <= 0 || !d_gathered2) return fail(ctx, MCP_E_STATE, "ts_merge2: no flagged rows");
+    const TsLayout L = ts_layout(nf, t);
+    MCP_CUDA(ctx, ctx->dFinKey.reserve((size_t)nf * t * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dFinIdx.reserve((size_t)nf * t * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)nf * 16));
+    double *vl = ctx->dFbOut.as<double>();
+    int32_t *vt = reinterpret_cast<int32_t *>(vl + nf);
+    MCP_TRY(ts_merge_rows(ctx, reinterpret_cast<const unsigned char *>(d_gathered2), ctx->tsWorld, L, nf, t, ctx->dFinKey.as<uint64_t>(),
+                          ctx->dFinIdx.as<int32_t>(), vl, vt));
+    KScope ks(ctx, MCP_K_SELECT);
+    k_ts_scatter_kept<<<(unsigned)nf, 128, 0, ctx->stream>>>(ctx->dFail.as<int32_t>() + 4, t, ctx->dFinKey.as<uint64_t>(), ctx->dFinIdx.as<int32_t>(), vl, vt,
+                                                            ctx->dKeptKey.as<uint64_t>(), ctx->dKeptIdx.as<int32_t>(), ctx->dVarLoss.as<double>(),
+                                                            ctx->dVarTrial.as<int32_t>());
+    return check_launch(ctx, "k_ts_scatter_kept");
+}
+
+// this rank's portfolio slice: breach lists, CVaR, pooled moments, encoding
+int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing)
+{
+    if (!ctx->tsGath || world != ctx->tsWorld || rank < 0 || rank >= world) return fail(ctx, MCP_E_STATE, "ts_finish: merge first");
+    const int64_t P = ctx->P, t = ctx->tsT;
+    const int64_t base = P / world, extra = P % world;
+    const int64_t p0 = rank * base + (rank < extra ? rank : extra), p1 = p0 + base + (rank < extra ? 1 : 0);
+    const int64_t rows = p1 - p0;
+    MCP_CUDA(ctx, ctx->dCvar.reserve(P * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dBreach.reserve((size_t)P * t * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(rows + 1) * sizeof(int64_t)));
+    int64_t total = 0;
+    if (rows > 0) {
+        MCP_TRY(run_finalize(ctx, rows, t, ctx->dKeptKey.as<uint64_t>() + p0 * t, ctx->dKeptIdx.as<int32_t>() + p0 * t,
+                             ctx->dBreach.as<int32_t>() + p0 * t, ctx->dCvar.as<double>() + p0, ctx->tsNGlobal));
+        {
+            KScope ks(ctx, MCP_K_MOMENTS);
+            k_ts_moments_merge<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(ctx->tsGath, world, ts_layout(P, ctx->tsM), p0, p1,
+                                                                                       ctx->dMean.as<double>(), ctx->dVar.as<double>());
+            MCP_TRY(check_launch(ctx, "k_ts_moments_merge"));
+        }
+        MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dBreach.as<int32_t>() + p0 * t, nullptr, t, rows, ctx->dEncOff.as<int64_t>(), &total));
+        MCP_CUDA(ctx, ctx->dEnc.reserve((size_t)total + 16));
+        MCP_TRY(codec_encode_emit(ctx, codec_id, framing, ctx->dBreach.as<int32_t>() + p0 * t, nullptr, t, rows, ctx->dEncOff.as<int64_t>(),
+                                  ctx->dEnc.as<uint8_t>()));
+    } else
+        MCP_CUDA(ctx, cudaMemsetAsync(ctx->dEncOff.p, 0, sizeof(int64_t), ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->runP = rows; ctx->runRow0 = p0; ctx->runN = ctx->tsNGlobal; ctx->runTail = t; ctx->runEncBytes = total; ctx->runFallbackRows = ctx->tsNFlag;
+    ctx->haveRun = true;
+    return MCP_OK;
+}
+
 int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
 {
     const int64_t P = ctx->P, N = ctx->N;
@@ -1747,6 +2115,7 @@ int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     MCP_TRY(codec_encode_emit(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), nullptr, t, P, ctx->dEncOff.as<int64_t>(),
                               ctx->dEnc.as<uint8_t>()));
     ctx->runP = P;
+    ctx->runRow0 = 0;
     ctx->runN = N;
     ctx->runTail = t;
     ctx->runEncBytes = total;

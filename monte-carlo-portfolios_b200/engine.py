@@ -180,6 +180,50 @@ class Context:
         self._check(self._L.mcp_run_sizes(self._h, C.byref(P), C.byref(Nn), C.byref(t), C.byref(eb)), "run_sizes")
         return {"P": P.value, "N": Nn.value, "tail": t.value, "enc_bytes": eb.value}
 
+    # -- trial-sharded mode (BASELINE config C5)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (rank 0 creates it and hands it to the other ranks)."""
+        buf = (C.c_uint8 * 128)()
+        rc = N.lib().mcp_comm_unique_id(buf)
+        if rc != N.MCP_OK:
+            raise N.McpError(rc, "comm_unique_id", "NCCL (libnccl.so.2) is not available")
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._check(self._L.mcp_comm_init(self._h, buf, rank, world), "comm_init")
+
+    def comm_destroy(self):
+        self._check(self._L.mcp_comm_destroy(self._h), "comm_destroy")
+
+    def run_trial_sharded(self, alpha: float, n_global: int, trial_base: int,
+                          codec_id: int = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, framing: int = N.FRAME_APP):
+        """Local candidates -> ONE NCCL all-gather -> merge -> this rank's portfolio slice (fetch() returns it)."""
+        self._check(self._L.mcp_run_trial_sharded(self._h, alpha, codec_id, framing, n_global, trial_base), "run_trial_sharded")
+
+    def ts_local(self, alpha: float, n_global: int, trial_base: int, world: int):
+        """-> (device pointer, bytes) of this rank's exchange block (bring-your-own-transport variant)."""
+        p, nb = C.c_void_p(), C.c_int64()
+        self._check(self._L.mcp_ts_local(self._h, alpha, n_global, trial_base, world, C.byref(p), C.byref(nb)), "ts_local")
+        return p.value, nb.value
+
+    def ts_merge(self, d_gathered: int) -> int:
+        fl = C.c_int64()
+        self._check(self._L.mcp_ts_merge(self._h, C.c_void_p(d_gathered), C.byref(fl)), "ts_merge")
+        return fl.value
+
+    def ts_local2(self):
+        p, nb = C.c_void_p(), C.c_int64()
+        self._check(self._L.mcp_ts_local2(self._h, C.byref(p), C.byref(nb)), "ts_local2")
+        return p.value, nb.value
+
+    def ts_merge2(self, d_gathered2: int):
+        self._check(self._L.mcp_ts_merge2(self._h, C.c_void_p(d_gathered2)), "ts_merge2")
+
+    def ts_finish(self, rank: int, world: int, codec_id: int = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, framing: int = N.FRAME_APP):
+        self._check(self._L.mcp_ts_finish(self._h, rank, world, codec_id, framing), "ts_finish")
+
     def run_stats(self) -> dict:
         fb = C.c_int64()
         self._check(self._L.mcp_run_stats(self._h, C.byref(fb)), "run_stats")

@@ -18,6 +18,55 @@ def portfolio_shard(P: int, rank: int, world: int) -> tuple[int, int]:
     return p0, p0 + base + (1 if rank < extra else 0)
 
 
+def trial_shard(n_trials: int, rank: int, world: int) -> tuple[int, int]:
+    """Balanced contiguous trial ranges for the trial-sharded mode (every shard <= ceil(N / world) rows)."""
+    return portfolio_shard(n_trials, rank, world)
+
+
+def ts_candidates(n_global: int, tail: int, world: int) -> int:
+    """Candidates per rank and portfolio of the first exchange round: the shard's expected share of the tail plus
+    six binomial standard deviations (mirrors ts_candidates_per_rank in csrc/risk_kernels.cu)."""
+    import math
+    nmax = -(-n_global // world)
+    share = tail * nmax / n_global
+    m = math.ceil(share + 6.0 * math.sqrt(share * (1.0 - 1.0 / world)) + 8.0)
+    return max(1, min(m, tail, nmax))
+
+
+def ts_merge_rows(cands, tail: int, sent_all):
+    """Host statement of the merge rule.  cands[g] = (loss[rows][m], trial[rows][m]) from rank g (any order inside a
+    row); sent_all[g] = rank g had no more than m trials.  Returns (loss[rows][tail], trial[rows][tail] sorted by
+    (loss, trial) descending, exact[rows]): a row is exact unless a rank that held candidates back has its smallest
+    sent candidate above the merged threshold (same rule as k_ts_check)."""
+    loss = np.concatenate([c[0] for c in cands], axis=1)
+    trial = np.concatenate([c[1] for c in cands], axis=1)
+    order = np.lexsort((trial, loss), axis=1)[:, ::-1][:, :tail]
+    top_l = np.take_along_axis(loss, order, axis=1)
+    top_t = np.take_along_axis(trial, order, axis=1)
+    thr_l, thr_t = top_l[:, -1], top_t[:, -1]
+    exact = np.ones(loss.shape[0], bool)
+    for (l, tr), everything in zip(cands, sent_all):
+        if everything:
+            continue
+        o = np.lexsort((tr, l), axis=1)[:, 0]
+        ml = np.take_along_axis(l, o[:, None], axis=1)[:, 0]
+        mt = np.take_along_axis(tr, o[:, None], axis=1)[:, 0]
+        exact &= ~((ml > thr_l) | ((ml == thr_l) & (mt > thr_t)))
+    return top_l, top_t, exact
+
+
+def run_trial_sharded_gpu(ctx, E, S_local, alpha, n_global, trial_base, rank, world, codec_id, framing, uid: bytes):
+    """One rank of a trial-sharded run on its own GPU: NCCL inside libmcp.so does the one exchange."""
+    ctx.upload_exposures(E)
+    ctx.upload_scenarios(S_local)
+    ctx.comm_init(uid, rank, world)
+    ctx.run_trial_sharded(alpha, n_global, trial_base, codec_id, framing)
+    r = ctx.fetch()
+    r["range"] = portfolio_shard(E.shape[0], rank, world)
+    r["fallback_rows"] = ctx.run_stats()["fallback_rows"]
+    return r
+
+
 def gpu_compute(device: int):
     """Default shard compute: the CUDA path through the C ABI on `device` (no fallback)."""
     from .engine import Context
