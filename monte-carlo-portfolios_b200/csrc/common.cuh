@@ -64,6 +64,7 @@ struct mcp_ctx {
 
     // ---- risk path state
     mcp::DevBuf dE, dS;            // exposures P x F, scenarios N x F (doubles)
+    mcp::DevBuf dEpad, dSpad;      // zero-padded copies for factor counts without a tensor-core kernel
     mcp::DevBuf dSfrag;            // scenarios in tensor-core B-fragment order (built lazily from dS)
     bool sfragValid = false;
     int64_t P = 0, N = 0;
@@ -109,6 +110,7 @@ struct mcp_ctx {
     bool valueMma = true;          // mcp_value through the tensor-core kernel when F allows (else scalar fma)
     bool fusedMoments = false;     // true: per-trial moment reduction fused in the valuation kernel (scalar FP64)
     mcp::DevBuf dGram;
+    bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)

@@ -121,7 +121,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
                            &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
-                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
+                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -152,6 +152,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
+    else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "ts_slack")) ctx->tsSlackOverride = value; // trial-sharded test hook: m = ceil(t / world) + value (-1 = automatic)
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");

@@ -1191,6 +1191,227 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     }
 }
 
+// ============================================================ selection, dense step, register-resident
+// The dense first step of the streaming path hands every row n0 = max(2048, 4t) contiguous values and wants only the
+// top `tail` of them (the whole tail t on the guaranteed schedule, the ~t n0/N + 7 sigma best under the optimistic
+// bound).  When n0 <= 256 * ITEMS the row fits the CTA's REGISTERS: every thread loads ITEMS values with independent
+// coalesced loads (all in flight at once), the trial index is implicit in the slot, and the range-adaptive radix
+// passes, the gather and the boundary-bucket sort run without staging anything in shared memory -- 5 KB of shared
+// memory per CTA instead of ~60 KB, so the SM holds as many rows as its registers allow.
+// from the histogram (bins descending from FS_BINS-1): the bin where the count from the top reaches `need`
+__device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need, int *s_wsum, int *s_sel, int *s_above, int *s_bucket)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PER = FS_BINS / SEL_THREADS;
+    const int hb = FS_BINS - 1 - tid * PER; // thread 0 owns the highest bins
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) sum += hist[hb - j];
+    int incl = sum;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_wsum[w];
+    incl += woff;
+    const int excl = incl - sum;
+    if ((int64_t)excl < need && need <= (int64_t)incl) {
+        int above = excl;
+        for (int j = 0; j < PER; ++j) {
+            const int h = hist[hb - j];
+            if (need <= (int64_t)above + h) { *s_sel = hb - j; *s_above = above; *s_bucket = h; break; }
+            above += h;
+        }
+    }
+    __syncthreads();
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense(const SelArgs a)
+{
+    __shared__ int hist[FS_BINS];
+    __shared__ uint64_t ckey[FS_SORT];
+    __shared__ uint32_t cidx[FS_SORT];
+    __shared__ double s_red[2 * (SEL_THREADS / 32)];
+    __shared__ int s_wsum[SEL_THREADS / 32];
+    __shared__ int s_sel, s_above, s_bucket;
+    const int64_t row = blockIdx.x;
+    const int64_t t = a.tail;
+    const int n = (int)a.step_len;
+    uint64_t *kk = a.kept_key_out + row * t;
+    int32_t *ki = a.kept_idx_out + row * t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
+    // ---- load: slot i = tid + 256 j holds the loss of trial n_begin + i (slots past n repeat the thread's first
+    // loss: harmless for min / max, masked everywhere else)
+    double x[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int i = tid + SEL_THREADS * j;
+        x[j] = 0.0 - __ldg(V + (i < n ? i : (tid < n ? tid : 0)));
+    }
+    // range of the row from the HIGH WORDS of the order-preserving keys (one integer min / max per value instead of
+    // FP64 compares): [lo, hi] is a slightly generous cover of the losses, which is all the binning needs.  A
+    // non-finite loss shows up as a key beyond +-infinity and sends the row to the key-space passes.
+    uint32_t hmn = 0xffffffffu, hmx = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const uint32_t hw = (uint32_t)__double2hiint(x[j]);
+        const uint32_t hk = (hw >> 31) ? ~hw : (hw | 0x80000000u);
+        hmn = min(hmn, hk); hmx = max(hmx, hk);
+    }
+    hmn = __reduce_min_sync(kFullMask, hmn);
+    hmx = __reduce_max_sync(kFullMask, hmx);
+    uint32_t *s_redw = reinterpret_cast<uint32_t *>(s_red);
+    if (lane == 0) { s_redw[warp] = hmn; s_redw[SEL_THREADS / 32 + warp] = hmx; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SEL_THREADS / 32; ++w) { hmn = min(hmn, s_redw[w]); hmx = max(hmx, s_redw[SEL_THREADS / 32 + w]); }
+    const bool finite = hmx < 0xfff00000u && hmn > 0x000fffffu; // inside (-inf, +inf)
+    const double mn = fkey_inv((uint64_t)hmn << 32), mx = fkey_inv(((uint64_t)hmx << 32) | 0xffffffffull);
+    // ---- pass 0 in VALUE space: FS_BINS equal-width bins of [min, max].  The bin index is a monotone function of
+    // the loss (the same three roundings for every element), so "higher bin" implies "not smaller": the partition is
+    // exact.  Losses of a Monte Carlo run are smooth, so one pass leaves a boundary bin of a few elements; ties and
+    // pathological distributions continue below with the key-space passes, non-finite values skip straight to them.
+    int64_t need = t;
+    int bucket = n;
+    const double width = mx - mn;
+    const bool byval = finite && width > 1.0e-290 && width < 1.0e300; // scale = FS_BINS / width must stay finite (0 * inf = NaN)
+    const double scale = byval ? (double)FS_BINS / width : 0.0;
+    auto bin_of = [&](double v) -> int {
+        const int b = __double2int_rd((v - mn) * scale);
+        return min(max(b, 0), FS_BINS - 1);
+    };
+    int sel = 0;
+    if (byval) {
+        for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+            if (tid + SEL_THREADS * j < n) atomicAdd(&hist[bin_of(x[j])], 1);
+        __syncthreads();
+        find_boundary_bin(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+        sel = s_sel;
+        need -= s_above;
+        bucket = s_bucket;
+    }
+    // ---- key-space refinement of the boundary bucket (rare): range-adaptive radix passes on the 64-bit keys
+    bool on_idx = false, bykey = false;
+    uint64_t kstar = 0, blo = 0, bhi = ~0ull;
+    if (bucket > FS_SORT) {
+        bykey = true;
+        // key range of the bucket (monotonicity: every element whose key lies inside it is in the bucket)
+        uint64_t kmn = ~0ull, kmx = 0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            if (tid + SEL_THREADS * j < n && (!byval || bin_of(x[j]) == sel)) {
+                const uint64_t k = fkey(x[j]);
+                kmn = k < kmn ? k : kmn; kmx = k > kmx ? k : kmx;
+            }
+        }
+        for (int d = 16; d; d >>= 1) {
+            const uint64_t a1 = __shfl_xor_sync(kFullMask, kmn, d), b1 = __shfl_xor_sync(kFullMask, kmx, d);
+            kmn = a1 < kmn ? a1 : kmn; kmx = b1 > kmx ? b1 : kmx;
+        }
+        uint64_t *s_redu = reinterpret_cast<uint64_t *>(s_red);
+        __syncthreads();
+        if (lane == 0) { s_redu[warp] = kmn; s_redu[SEL_THREADS / 32 + warp] = kmx; }
+        __syncthreads();
+        uint64_t lo = ~0ull, hi = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = s_redu[w] < lo ? s_redu[w] : lo; hi = s_redu[SEL_THREADS / 32 + w] > hi ? s_redu[SEL_THREADS / 32 + w] : hi; }
+        blo = lo; bhi = hi;
+        for (int pass = 0; pass < 16; ++pass) {
+            const uint64_t w64 = hi - lo;
+            const int shift = w64 < (uint64_t)FS_BINS ? 0 : (64 - __clzll((long long)w64)) - FS_BITS;
+            for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const int i = tid + SEL_THREADS * j;
+                if (i < n) {
+                    const uint64_t k = fkey(x[j]);
+                    if (on_idx) { if (k == kstar) { const uint64_t v = (uint32_t)(a.n_begin + i); if (v >= lo && v <= hi) atomicAdd(&hist[(int)((v - lo) >> shift)], 1); } }
+                    else if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+                }
+            }
+            __syncthreads();
+            find_boundary_bin(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+            need -= s_above;
+            bucket = s_bucket;
+            blo = lo + ((uint64_t)s_sel << shift);
+            bhi = shift == 0 ? blo : blo + ((1ull << shift) - 1);
+            if (bhi > hi) bhi = hi;
+            __syncthreads();
+            if (bucket <= FS_SORT) break;
+            if (shift == 0) {
+                if (on_idx) break; // cannot happen: trial indices are distinct
+                on_idx = true;
+                kstar = blo;
+                lo = 0; hi = 0xffffffffull;
+            } else { lo = blo; hi = bhi; }
+        }
+    }
+    // ---- gather without atomics: per-thread counts (kept | bucket << 16), one block scan, deterministic slots
+    int cnt = 0;
+    uint32_t relk = 0, relb = 0; // bit j: my item j is above / inside the boundary bin
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int i = tid + SEL_THREADS * j;
+        if (i < n) {
+            int rel; // +1 above, 0 inside, -1 below
+            if (!bykey) { const int b = bin_of(x[j]); rel = b > sel ? 1 : (b == sel ? 0 : -1); }
+            else {
+                const uint64_t k = fkey(x[j]);
+                const uint64_t id = (uint32_t)(a.n_begin + i);
+                if (!on_idx) rel = k > bhi ? 1 : (k >= blo ? 0 : -1);
+                else if (k != kstar) rel = k > kstar ? 1 : -1;
+                else rel = id > bhi ? 1 : (id >= blo ? 0 : -1);
+            }
+            if (rel > 0) { relk |= 1u << j; cnt += 1; }
+            else if (rel == 0) { relb |= 1u << j; cnt += 1 << 16; }
+        }
+    }
+    int incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += v;
+    }
+    __syncthreads();
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int off = incl - cnt;
+    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+    int ok = off & 0xffff, ob = off >> 16;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int32_t id = (int32_t)(a.n_begin + tid + SEL_THREADS * j);
+        if (relk & (1u << j)) { kk[ok] = fkey(x[j]); ki[ok] = id; ++ok; }
+        else if (relb & (1u << j)) { ckey[ob] = fkey(x[j]); cidx[ob] = (uint32_t)id; ++ob; }
+    }
+    __syncthreads();
+    // ---- rank the bucket by (key, trial) descending
+    const int base = (int)(t - need); // elements strictly above the boundary bin
+    if (tid < bucket) {
+        const u128 me = comp_of(ckey[tid], cidx[tid]);
+        int rank = 0;
+        for (int j = 0; j < bucket; ++j) rank += comp_of(ckey[j], cidx[j]) > me;
+        if (rank < (int)need) {
+            kk[base + rank] = ckey[tid];
+            ki[base + rank] = (int32_t)cidx[tid];
+        }
+        if (rank == (int)need - 1) {
+            const double vl = fkey_inv(ckey[tid]);
+            a.var_loss[row] = vl;
+            a.var_trial[row] = (int32_t)cidx[tid];
+            if (a.tkey) a.tkey[row] = fkey(0.0 - vl);
+        }
+    }
+}
+
 static size_t sel_smem_bytes(int cap, int nseg) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4 + (size_t)(nseg + 2) * 4; }
 
 // ============================================================ finalize
@@ -1647,6 +1868,10 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 // sparse steps stage kept + ~2.2 t candidates (optimistic) or ~2 t (guaranteed): a smaller staging area
                 // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
                 a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
+                const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
+                if (reg && a.step_len <= 8 * SEL_THREADS) k_select_dense<8><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(a);
+                else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(a);
+                else
                 k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
@@ -2070,7 +2295,50 @@ int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing)
     return MCP_OK;
 }
 
+// rows x F -> rows x Fp with zero columns appended
+__global__ void k_pad_columns(const double *__restrict__ in, int64_t rows, int F, int Fp, double *__restrict__ out)
+{
+    const int64_t total = rows * Fp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / Fp;
+        const int k = (int)(i - r * Fp);
+        out[i] = k < F ? in[r * F + k] : 0.0;
+    }
+}
+
+static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing);
+
+// Factor counts without a tensor-core kernel (F < 64, not 16/32/48): run the streaming path on copies of E and S
+// padded with zero columns to the next supported count.  A padded step computes fma(0, 0, acc) = acc, so every loss,
+// order statistic, breach list and moment is unchanged (the only observable difference would be V = -0.0 becoming
+// +0.0, and the path consumes 0.0 - V and sums, never V's sign bit; mcp_value keeps the unpadded scalar kernel).
 int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing)
+{
+    const int F = ctx->F;
+    if (mma_supported(F) || F > 64 || ctx->forceDense) return risk_run_inner(ctx, alpha, codec_id, framing);
+    const int Fp = F <= 16 ? 16 : F <= 32 ? 32 : F <= 48 ? 48 : 64;
+    MCP_CUDA(ctx, ctx->dEpad.reserve((size_t)ctx->P * Fp * sizeof(double) + 16));
+    MCP_CUDA(ctx, ctx->dSpad.reserve((size_t)ctx->N * Fp * sizeof(double) + 16));
+    {
+        KScope ks(ctx, MCP_K_GEN, 2);
+        const int grid = ctx->prop.multiProcessorCount * 8;
+        k_pad_columns<<<grid, 256, 0, ctx->stream>>>(ctx->dE.as<double>(), ctx->P, F, Fp, ctx->dEpad.as<double>());
+        k_pad_columns<<<grid, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, F, Fp, ctx->dSpad.as<double>());
+        MCP_TRY(check_launch(ctx, "k_pad_columns"));
+    }
+    std::swap(ctx->dE, ctx->dEpad);
+    std::swap(ctx->dS, ctx->dSpad);
+    ctx->F = Fp;
+    ctx->sfragValid = false;
+    const int rc = risk_run_inner(ctx, alpha, codec_id, framing);
+    std::swap(ctx->dE, ctx->dEpad);
+    std::swap(ctx->dS, ctx->dSpad);
+    ctx->F = F;
+    ctx->sfragValid = false;
+    return rc;
+}
+
+static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
 {
     const int64_t P = ctx->P, N = ctx->N;
     const int64_t t = mcp_tail_size(N, alpha);

@@ -78,18 +78,39 @@ def test_run_matches_oracle(ctx, shape):
     check_against_oracle(ctx, E, S, alpha)
 
 
-@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments"])
+@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic"])
 def test_alternate_kernel_paths_agree(ctx, opt):
-    """F = 32 normally takes the streaming kernels + bitmap compaction; the dense tile + single selection and
-    the sort-based breach list must give identical results."""
-    ctx.set_option(opt, 1)
+    """F = 32 normally takes the streaming kernels (two-step optimistic schedule, dense-step selection from
+    registers) + bitmap compaction; the dense tile + single selection, the sort-based breach list, the fused
+    per-trial moments, the shared-memory selection and the guaranteed schedule must give identical results."""
+    default = 1 if opt in ("reg_select", "optimistic") else 0
+    ctx.set_option(opt, 1 - default)
     try:
         E, S = riskcases.synthetic(40, 9000, 32, 21)
         check_against_oracle(ctx, E, S, 0.99)
         E, S = riskcases.with_ties(8, 5000, 32, 22)
         check_against_oracle(ctx, E, S, 0.9)
+        E, S = riskcases.synthetic(20, 60000, 32, 23)
+        check_against_oracle(ctx, E, S, 0.995)
     finally:
-        ctx.set_option(opt, 0)
+        ctx.set_option(opt, default)
+
+
+@pytest.mark.parametrize("F", [1, 3, 10, 17, 33, 47, 63])
+def test_odd_factor_counts_take_the_padded_tensor_core_path(ctx, F):
+    """F without a tensor-core kernel is padded with zero columns to 16/32/48/64 (exact: fma(0,0,acc) = acc); results
+    must equal the oracle's and the dense scalar-fma path's, and the stored matrices stay unpadded."""
+    E, S = riskcases.synthetic(70, 6000, F, 200 + F)
+    r1 = check_against_oracle(ctx, E, S, 0.99)
+    assert np.array_equal(ctx.download_exposures(70, F), E) and np.array_equal(ctx.download_scenarios(6000, F), S)
+    assert np.array_equal(ctx.value(0, 3, 6000).view(np.uint64), cref.value(E[:3], S).view(np.uint64))
+    ctx.set_option("force_dense", 1)
+    try:
+        r0 = check_against_oracle(ctx, E, S, 0.99)
+    finally:
+        ctx.set_option("force_dense", 0)
+    for k in ("var_loss", "var_trial", "breach", "enc"):
+        assert np.array_equal(r0[k], r1[k]), k
 
 
 def test_streaming_path_many_portfolios_ragged(ctx):
