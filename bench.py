@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the hot path (BASELINE.json: portfolio-scenario valuations/s,
 plus codec ints/s, with roofline fractions and a CPU baseline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]
 
 One "step" = one pass of the whole hot path (valuation -> moments/VaR/CVaR -> breach lists -> JavaFastPFOR
 encoding) over one batch of synthetic portfolios whose inputs are already resident in HBM.
@@ -34,6 +34,9 @@ WORKLOADS = {
     # name: (portfolios per GPU, trials, factors, alpha, seed)
     "c2": (10_000, 100_000, 32, 0.99, 0x5EED0002),
     "c3": (125_000, 10_000, 64, 0.99, 0x5EED0003),
+    # trial-sharded (BASELINE config C5): ALL 100 000 portfolios on every GPU, 1 250 000 trials PER GPU (10 M on 8),
+    # 99.9 % VaR/CVaR, one NCCL all-gather of tail candidates per step
+    "c5": (100_000, 1_250_000, 32, 0.999, 0x5EED0005),
 }
 E_SCALE, S_DRIFT = 100.0, 0.05
 METRIC, UNIT = "portfolio_scenario_valuations_per_sec", "valuations/s"
@@ -183,6 +186,91 @@ def run_reference(args, rank, world):
     }))
 
 
+def run_c5(args, rank, local_rank, world):
+    """--workload c5: the trial-sharded mode.  Every rank holds all P exposure rows and its own 1.25 M-trial shard of
+    the scenarios (generated on device from the global row index); one step = local candidates -> ONE NCCL all-gather
+    -> merge -> breach lists / CVaR / moments / encoding of the rank's portfolio slice."""
+    import mcp_b200
+    from mcp_b200 import native as N
+    import torch
+    import torch.distributed as dist
+    P, Nl, F, alpha, seed = WORKLOADS["c5"]
+    if args.c5_portfolios:
+        P = args.c5_portfolios
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = mcp_b200.Context(local_rank)
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    n_global, base = Nl * world, rank * Nl
+    ctx.generate_exposures(P, F, seed, E_SCALE, 0.0)
+    ctx.generate_scenarios(Nl, F, seed, 1.0, S_DRIFT, row0=base)
+    cid, framing = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.FRAME_APP
+    dfma_peak, dmma_peak = ctx.fp64_peak(), ctx.fp64_mma_peak()
+    peak = max(dfma_peak, dmma_peak)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        ctx.run_trial_sharded(alpha, n_global, base, cid, framing)
+    ctx.profile(True)
+    ctx.profile_reset()
+    barrier()
+    ms = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        barrier()
+        ctx.timer_start()
+        ctx.run_trial_sharded(alpha, n_global, base, cid, framing)
+        ms.append(ctx.timer_stop())
+    barrier()
+    clocks = sampler.stop()
+    prof = ctx.profile_get()
+    dev_ms = float(np.sum(ms))
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    sizes, stats = ctx.run_sizes(), ctx.run_stats()
+    m = int(N.lib().mcp_ts_candidates(n_global, alpha, world))
+    block = 64 + P * m * 12 + P * 16
+    v_ms = prof["value"]["ms"] / args.steps
+    flops = 2.0 * F * P * Nl  # per rank
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": P * n_global / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"c5: {P} portfolios (all on every GPU) x {Nl} trials per GPU ({n_global} in total) x {F} factors, alpha {alpha}, "
+                                   f"tail {sizes['tail']}, trial-sharded: {m} tail candidates per portfolio and rank, one NCCL all-gather of "
+                                   f"{block / 1e6:.0f} MB per rank, merge, Delta+FastPFOR256+VariableByte of the rank's portfolio slice",
+                       "inputs": "Philox4x32-10 synthetic E and S generated on device (S rows by global trial index), resident in HBM",
+                       "l2": "L2 flushed before every timed step; CUDA events on the library's stream, max over ranks",
+                       "second_round_rows": stats["fallback_rows"]},
+            "roofline": {"bound": "tensor", "kernel": "k_value_mma", "achieved": flops / (v_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flops / (v_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                         "peak_source": f"live probes: DMMA {dmma_peak:.1f}, DFMA {dfma_peak:.1f} TF/s (of measured)",
+                         "whole_step_frac": flops / (ms_per_step * 1e-3) / 1e12 / peak},
+            "kernel_breakdown": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                                 for k, v in prof.items() if v["launches"]},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(sum(v["launches"] for v in prof.values())), "clocks": clocks,
+        }))
+    barrier()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,6 +281,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--codec-lists", type=int, default=1_000_000)
+    ap.add_argument("--c5-portfolios", type=int, default=0, help="override the c5 portfolio count (smaller smoke runs)")
     args = ap.parse_args()
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must use every host core, and libgomp reads
     # the variable when it is first loaded (with the oracle, later)
@@ -204,6 +293,9 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "c5":
+        run_c5(args, rank, local_rank, world)
+        return
 
     import mcp_b200
     from mcp_b200 import native as N
@@ -231,7 +323,8 @@ def main():
     # ---- inputs resident in HBM: this rank's portfolio shard + the replicated scenario matrix
     ctx.generate_exposures(P, F, seed, E_SCALE, 0.0, row0=rank * P)
     ctx.generate_scenarios(Nn, F, seed, 1.0, S_DRIFT)
-    fp64_peak = ctx.fp64_peak()
+    dfma_peak, dmma_peak = ctx.fp64_peak(), ctx.fp64_mma_peak()
+    fp64_peak = max(dfma_peak, dmma_peak)  # the kernel issues DMMA: hold it to the higher of the two live probes
     sampler = ClockSampler(local_rank)
     sampler.start()  # sampled from the warm-up on: the timed region itself is only ~0.1 s
     for _ in range(args.warmup):
@@ -268,10 +361,17 @@ def main():
     v_ms = kv["ms"] / max(args.steps, 1)
     flops = 2.0 * F * P * Nn
     achieved = flops / (v_ms * 1e-3) / 1e12 if v_ms > 0 else 0.0
-    roofline = {"bound": "fp64", "kernel": "k_value_mma (FP64 tensor-core valuation + fused tail filter)", "achieved": achieved,
-                "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
-                "peak_source": "mcp_fp64_peak: dependent-free FP64 FMA (DFMA) issue-rate probe measured live on this GPU "
-                               "(MEASURED_PEAKS.json has no FP64 entry; the DMMA probe in profiles/microbench reads 37.1)",
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant (sparse-step) valuation launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "value_kernel_traffic.json")))[args.workload]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "k_value_mma (FP64 tensor-core valuation + fused tail filter)", "achieved": achieved,
+                "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json has no FP64 entry (it holds HBM GB/s and bf16 TF/s): the peak is the higher of two "
+                               "live probes on this GPU, run just before the timed region -- dependent-free mma.sync.m8n8k4.f64 (DMMA, "
+                               f"{dmma_peak:.1f} TF/s) and dependent-free scalar DFMA ({dfma_peak:.1f} TF/s); 'of measured'",
+                "pipe": "FP64 tensor pipe (DMMA.8x8x4); algorithmic FLOPs = 2*F per valuation",
                 "launches_per_step": kv["launches"] / max(args.steps, 1), "ms_per_step": v_ms,
                 "whole_step_frac": (flops / (ms_per_step * 1e-3) / 1e12) / fp64_peak if fp64_peak else None}
     breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps} for k, v in prof.items()

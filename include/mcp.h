@@ -249,6 +249,8 @@ int mcp_timer_start(mcp_ctx *ctx);
 int mcp_timer_stop(mcp_ctx *ctx, double *ms);
 /* dependent-free DFMA issue-rate probe: returns achieved FP64 TFLOP/s (2 flop per FMA) */
 int mcp_fp64_peak(mcp_ctx *ctx, double *tflops);
+/* the same for the FP64 tensor-core instruction the valuation kernel issues (mma.sync.m8n8k4.f64, SASS DMMA) */
+int mcp_fp64_mma_peak(mcp_ctx *ctx, double *tflops);
 /* write `bytes` of zeros to a scratch buffer (> L2) to flush the L2 between timed steps */
 int mcp_flush_l2(mcp_ctx *ctx);
 

@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "mcp_timer_start": (C.c_int, [vp]),
         "mcp_timer_stop": (C.c_int, [vp, P(f64)]),
         "mcp_fp64_peak": (C.c_int, [vp, P(f64)]),
+        "mcp_fp64_mma_peak": (C.c_int, [vp, P(f64)]),
         "mcp_flush_l2": (C.c_int, [vp]),
         "mcp_generate_breach_lists": (C.c_int, [vp, i64, i32, f64, u64, i64, P(vp), P(vp), P(i64)]),
         "mcp_dev_alloc": (C.c_int, [vp, sz, P(vp)]),

@@ -214,6 +214,7 @@ int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t
 int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
                      int64_t *total);
 int fp64_peak(mcp_ctx *ctx, double *tflops);
+int fp64_mma_peak(mcp_ctx *ctx, double *tflops);
 int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world);
 int risk_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes);
 int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *nflag_out);

@@ -672,6 +672,13 @@ int mcp_fp64_peak(mcp_ctx *ctx, double *tflops)
     return fp64_peak(ctx, tflops);
 }
 
+int mcp_fp64_mma_peak(mcp_ctx *ctx, double *tflops)
+{
+    MCP_TRY(set_dev(ctx));
+    if (!tflops) return fail(ctx, MCP_E_ARG, "fp64_mma_peak: null");
+    return fp64_mma_peak(ctx, tflops);
+}
+
 int mcp_flush_l2(mcp_ctx *ctx)
 {
     MCP_TRY(set_dev(ctx));

@@ -172,6 +172,53 @@ int fp64_peak(mcp_ctx *ctx, double *tflops)
     return check_launch(ctx, "k_fp64_peak");
 }
 
+// Same question for the FP64 TENSOR path the valuation kernel actually issues: 8 independent accumulator pairs per
+// warp of mma.sync.m8n8k4.f64 (DMMA), no memory traffic.  512 FMA per instruction per warp.
+__global__ void __launch_bounds__(256) k_fp64_mma_peak(double *out, int iters, double a, double b)
+{
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 1.2345e-300) out[0] = s; // never true; keeps the chains alive
+}
+
+int fp64_mma_peak(mcp_ctx *ctx, double *tflops)
+{
+    MCP_CUDA(ctx, ctx->dErr.reserve(64));
+    const int grid = ctx->prop.multiProcessorCount * 8, iters = 2048;
+    cudaEvent_t a, b;
+    MCP_CUDA(ctx, cudaEventCreate(&a));
+    MCP_CUDA(ctx, cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        KScope ks(ctx, MCP_K_GEN);
+        cudaEventRecord(a, ctx->stream);
+        k_fp64_mma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->dErr.as<double>(), iters, 0.999999, 1e-9);
+        cudaEventRecord(b, ctx->stream);
+        MCP_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        // per warp and instruction: 8 x 8 outputs x 4 k = 256 FMA = 512 flop; 32 instructions per iteration
+        const double flops = 512.0 * 32.0 * iters * 8.0 /* warps per CTA */ * grid;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return check_launch(ctx, "k_fp64_mma_peak");
+}
+
 // ============================================================ valuation (generic F)
 // V tile = 64 portfolios x 64 trials per CTA, 4x4 register micro-tile per thread, k staged
 // through shared memory in slabs of 32.  Every (p,n) accumulator is a single fma chain in
@@ -1569,7 +1616,7 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
     if (n_trials < 0) n_trials = ctx->N;
     if (fin_bitmap_smem(n_trials, t) <= FIN_BITMAP_MAX_SMEM && !ctx->forceSortFinalize) {
         const size_t bm_smem = fin_bitmap_smem(n_trials, t);
-        if (bm_smem > 48 * 1024)
+        if (bm_smem > 40 * 1024)
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
         KScope ks(ctx, MCP_K_SELECT);
         k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, ctx->stream>>>(kk, ki, t, n_trials, 0, breach, cvar);
@@ -1582,7 +1629,7 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
     if (fin_global) {
         MCP_CUDA(ctx, ctx->dFinKey.reserve((size_t)rows * m * sizeof(uint64_t)));
         MCP_CUDA(ctx, ctx->dFinIdx.reserve((size_t)rows * m * sizeof(int32_t)));
-    } else if (fin_smem > 48 * 1024) {
+    } else if (fin_smem > 40 * 1024) { // static shared memory counts against the 48 KB default as well
         MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     }
     KScope ks(ctx, MCP_K_SELECT);

@@ -292,6 +292,11 @@ class Context:
         self._check(self._L.mcp_fp64_peak(self._h, C.byref(tf)), "fp64_peak")
         return tf.value
 
+    def fp64_mma_peak(self) -> float:
+        tf = C.c_double(0)
+        self._check(self._L.mcp_fp64_mma_peak(self._h, C.byref(tf)), "fp64_mma_peak")
+        return tf.value
+
     def flush_l2(self):
         self._check(self._L.mcp_flush_l2(self._h), "flush_l2")
 
