@@ -174,7 +174,7 @@ int fp64_peak(mcp_ctx *ctx, double *tflops)
 
 // Same question for the FP64 TENSOR path the valuation kernel actually issues: 8 independent accumulator pairs per
 // warp of mma.sync.m8n8k4.f64 (DMMA), no memory traffic.  512 FMA per instruction per warp.
-__global__ void __launch_bounds__(256) k_fp64_mma_peak(double *out, int iters, double a, double b)
+__global__ void __launch_bounds__(1024) k_fp64_mma_peak(double *out, int iters, double a, double b)
 {
     double c[8][2];
 #pragma unroll
@@ -195,24 +195,26 @@ __global__ void __launch_bounds__(256) k_fp64_mma_peak(double *out, int iters, d
 int fp64_mma_peak(mcp_ctx *ctx, double *tflops)
 {
     MCP_CUDA(ctx, ctx->dErr.reserve(64));
-    const int grid = ctx->prop.multiProcessorCount * 8, iters = 2048;
+    const int grid = ctx->prop.multiProcessorCount, iters = 4096; // one CTA per SM; the best of 1, 2, 4 and 8 warps per sub-partition
     cudaEvent_t a, b;
     MCP_CUDA(ctx, cudaEventCreate(&a));
     MCP_CUDA(ctx, cudaEventCreate(&b));
     double best = 0;
-    for (int rep = 0; rep < 4; ++rep) {
-        KScope ks(ctx, MCP_K_GEN);
-        cudaEventRecord(a, ctx->stream);
-        k_fp64_mma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->dErr.as<double>(), iters, 0.999999, 1e-9);
-        cudaEventRecord(b, ctx->stream);
-        MCP_CUDA(ctx, cudaEventSynchronize(b));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, a, b);
-        // per warp and instruction: 8 x 8 outputs x 4 k = 256 FMA = 512 flop; 32 instructions per iteration
-        const double flops = 512.0 * 32.0 * iters * 8.0 /* warps per CTA */ * grid;
-        const double tf = flops / (ms * 1e-3) / 1e12;
-        if (rep > 0 && tf > best) best = tf;
-    }
+    const int threads[4] = {128, 256, 512, 1024};
+    for (int cfg = 0; cfg < 4; ++cfg)
+        for (int rep = 0; rep < 3; ++rep) {
+            KScope ks(ctx, MCP_K_GEN);
+            cudaEventRecord(a, ctx->stream);
+            k_fp64_mma_peak<<<grid, threads[cfg], 0, ctx->stream>>>(ctx->dErr.as<double>(), iters, 0.999999, 1e-9);
+            cudaEventRecord(b, ctx->stream);
+            MCP_CUDA(ctx, cudaEventSynchronize(b));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            // per warp and instruction: 8 x 8 outputs x 4 k = 256 FMA = 512 flop; 32 instructions per iteration
+            const double flops = 512.0 * 32.0 * iters * (threads[cfg] / 32.0) * grid;
+            const double tf = flops / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     *tflops = best;

@@ -7,7 +7,10 @@ ctx = mcp_b200.Context(0)
 P, Nn, F, alpha, seed = 10000, 100000, 32, 0.99, 0x5EED0002
 for a in sys.argv[1:]:
     k, v = a.split("=")
-    ctx.set_option(k, int(v))
+    if k == "P": P = int(v)
+    elif k == "N": Nn = int(v)
+    elif k == "F": F = int(v)
+    else: ctx.set_option(k, int(v))
 ctx.generate_exposures(P, F, seed, 100.0, 0.0)
 ctx.generate_scenarios(Nn, F, seed, 1.0, 0.05)
 for _ in range(2):
