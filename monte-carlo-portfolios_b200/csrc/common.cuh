@@ -103,7 +103,10 @@ struct mcp_ctx {
     mcp::DevBuf dTsSend, dTsRecv, dTsRecv2, dTsFlags;
     void *nccl = nullptr;          // NcclComm* (nccl_dyn.cu), null until mcp_comm_init
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr;
+    bool sTailPending = false;     // pipelined upload: scenario rows >= sHeadRows are still arriving on stream2 (evTail)
+    int64_t sHeadRows = 0;
+    void *earlyBreachDst = nullptr; // host buffer the raw breach lists are copied to under the encode (mcp_simulate)
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
     int selCap = 2304;
     uint32_t mmaConfigured = 0;
@@ -213,6 +216,7 @@ int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t
                double shift, int64_t row0);
 int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
                      int64_t *total);
+int64_t risk_first_step_len(int64_t N, int64_t t);
 int fp64_peak(mcp_ctx *ctx, double *tflops);
 int fp64_mma_peak(mcp_ctx *ctx, double *tflops);
 int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world);

@@ -96,6 +96,7 @@ int mcp_create(int device, mcp_ctx **out)
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evTail, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost(&ctx->hPinned, 4096) != cudaSuccess || cudaEventCreate(&ctx->tA) != cudaSuccess ||
         cudaEventCreate(&ctx->tB) != cudaSuccess) {
         cudaGetLastError();
@@ -128,6 +129,7 @@ void mcp_destroy(mcp_ctx *ctx)
     if (ctx->tB) cudaEventDestroy(ctx->tB);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->evTail) cudaEventDestroy(ctx->evTail);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -507,17 +509,51 @@ int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, in
     return sync(ctx);
 }
 
+static bool mma_factor_count(int32_t F) { return F == 16 || F == 32 || F == 48 || F == 64; }
+
 int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int64_t N, int32_t F, double alpha,
                  int codec_id, int framing, double *mean, double *variance, double *var_loss, int32_t *var_trial,
                  double *cvar, int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len)
 {
     MCP_TRY(set_dev(ctx));
     ctx->haveE = ctx->haveS = false;
-    MCP_TRY(mcp_upload_exposures(ctx, E, P, F));
-    MCP_TRY(mcp_upload_scenarios(ctx, S, N, F));
-    MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+    if (P < 0 || N < 0 || F <= 0 || (P > 0 && !E) || (N > 0 && !S)) return fail(ctx, MCP_E_ARG, "simulate: bad argument");
+    if (!(alpha > 0.0 && alpha <= 1.0)) return fail(ctx, MCP_E_ARG, "run: alpha must be in (0,1]");
+    const int64_t t = mcp_tail_size(N, alpha);
+    const int64_t head = N > 0 ? risk_first_step_len(N, t) : 0;
+    if (!mma_factor_count(F) || ctx->forceDense || head >= N || P == 0) {
+        // plain sequence: upload, run, fetch
+        MCP_TRY(mcp_upload_exposures(ctx, E, P, F));
+        MCP_TRY(mcp_upload_scenarios(ctx, S, N, F));
+        MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+        if (enc_len) *enc_len = ctx->runEncBytes;
+        return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
+    }
+    // Pipelined: the dense first step needs E and only the first `head` scenario rows, so the bulk of S (96 % at C2)
+    // is uploaded on the side stream while that step and its selection run; on the way out the raw breach lists (if
+    // wanted) leave on the side stream under the encode.  (Host buffers should be pinned for the overlap to happen.)
+    MCP_CUDA(ctx, ctx->dE.reserve((size_t)P * F * sizeof(double) + 16));
+    MCP_CUDA(ctx, ctx->dS.reserve((size_t)N * F * sizeof(double) + 16));
+    MCP_TRY(h2d(ctx, ctx->dE.p, E, (size_t)P * F * sizeof(double)));
+    MCP_TRY(h2d(ctx, ctx->dS.p, S, (size_t)head * F * sizeof(double)));
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dS.as<double>() + head * F, S + head * F, (size_t)(N - head) * F * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream2));
+    MCP_CUDA(ctx, cudaEventRecord(ctx->evTail, ctx->stream2));
+    ctx->P = P; ctx->N = N; ctx->F = F;
+    ctx->haveE = ctx->haveS = true; ctx->haveRun = false; ctx->sfragValid = false;
+    ctx->sTailPending = true; ctx->sHeadRows = head;
+    ctx->earlyBreachDst = breach_idx;
+    const int rc = mcp_run(ctx, alpha, codec_id, framing);
+    ctx->earlyBreachDst = nullptr;
+    if (ctx->sTailPending) { // the run failed before it consumed the tail: drain the copy, keep the state consistent
+        ctx->sTailPending = false;
+        cudaStreamSynchronize(ctx->stream2);
+    }
+    if (rc != MCP_OK) { cudaStreamSynchronize(ctx->stream2); return rc; }
     if (enc_len) *enc_len = ctx->runEncBytes;
-    return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
+    MCP_TRY(mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, nullptr, enc_off, enc, enc_cap));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2)); // the raw lists
+    return MCP_OK;
 }
 
 // ---------------------------------------------------------- trial-sharded mode

@@ -390,12 +390,11 @@ constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * VM_ST * (
 // S[N][F] -> Sfrag[ceil(N/8)][NK][32]: element (b, s, lane) = S[8b + lane/4][4s + lane%4] (0 past the last trial).
 // In this order a stage of 32 trials is one contiguous block (a single TMA bulk copy) and every B-fragment load is
 // 32 consecutive doubles: bank-conflict free without padding.
-__global__ void k_repack_scenarios(const double *__restrict__ S, int64_t N, int NK, double *__restrict__ Sfrag)
+__global__ void k_repack_scenarios(const double *__restrict__ S, int64_t N, int NK, double *__restrict__ Sfrag, int64_t blk0, int64_t blk1)
 {
-    const int64_t nblk = (N + 7) >> 3;
-    const int64_t total = nblk * NK * 32;
+    const int64_t total = blk1 * NK * 32; // trial blocks [blk0, blk1)
     const int F = NK * 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blk0 * NK * 32 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int lane = (int)(i & 31);
         const int64_t bs = i >> 5;
         const int sidx = (int)(bs % NK);
@@ -1584,6 +1583,8 @@ static int64_t first_step_len(int64_t N, int64_t t)
     return c0 < N ? c0 : N;
 }
 
+int64_t risk_first_step_len(int64_t N, int64_t t) { return first_step_len(N, t); }
+
 // Trial schedule of the streaming path.  Guaranteed: a dense first step of ~4 tail sizes establishes each
 // portfolio's threshold, then steps grow 3x; every later step inserts ~2 tail sizes of candidates.  Optimistic
 // (`two_step`): the dense first step, then ONE sparse step over all remaining trials (see optimistic_rank).
@@ -1709,18 +1710,38 @@ static int launch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 
 static bool mma_supported(int32_t F) { return F == 16 || F == 32 || F == 48 || F == 64; }
 
 // (re)build the fragment-order copy of the scenario matrix when it is stale
+// With a pipelined upload (mcp_simulate) only the first `sHeadRows` scenario rows are on the device when the dense
+// step starts; the rest arrives on the side stream and is repacked by scenarios_tail_ready() before the first kernel
+// that touches those trials.
 static int ensure_sfrag(mcp_ctx *ctx)
 {
     if (ctx->sfragValid) return MCP_OK;
     const int NK = ctx->F / 4;
     const int64_t nblk = (ctx->N + 7) / 8;
     MCP_CUDA(ctx, ctx->dSfrag.reserve((size_t)nblk * NK * 32 * sizeof(double) + 16));
+    const int64_t b1 = ctx->sTailPending ? ctx->sHeadRows / 8 : nblk;
     KScope ks(ctx, MCP_K_GEN);
-    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, NK, ctx->dSfrag.as<double>());
+    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, NK, ctx->dSfrag.as<double>(), 0, b1);
     MCP_TRY(check_launch(ctx, "k_repack_scenarios"));
+    ctx->sfragValid = !ctx->sTailPending;
+    return MCP_OK;
+}
+
+static int scenarios_tail_ready(mcp_ctx *ctx)
+{
+    if (!ctx->sTailPending) return MCP_OK;
+    MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evTail, 0));
+    ctx->sTailPending = false;
+    const int NK = ctx->F / 4;
+    KScope ks(ctx, MCP_K_GEN);
+    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, NK, ctx->dSfrag.as<double>(),
+                                                                                  ctx->sHeadRows / 8, (ctx->N + 7) / 8);
+    MCP_TRY(check_launch(ctx, "k_repack_scenarios (tail)"));
     ctx->sfragValid = true;
     return MCP_OK;
 }
+
+int64_t risk_first_step_len(int64_t N, int64_t t);
 
 static int dispatch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 grid)
 {
@@ -1873,6 +1894,7 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
         for (size_t si = 0; si < steps.size(); ++si) {
             const Step &s = steps[si];
             const bool dense = si == 0;
+            if (ctx->sTailPending && s.end > ctx->sHeadRows) MCP_TRY(scenarios_tail_ready(ctx));
             StreamArgs v{};
             v.E = io.E;
             v.S = ctx->dS.as<double>();
@@ -2424,6 +2446,13 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     else MCP_TRY(risk_run_dense(ctx, t));
     if (side_moments) MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 
+    MCP_TRY(scenarios_tail_ready(ctx)); // (a schedule that never reached the tail rows cannot exist, but the event must not dangle)
+    if (ctx->earlyBreachDst) {
+        // the caller wants the raw lists on the host: start that copy on the side stream now, under the encode
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream2));
+    }
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));
     int64_t total = 0;
