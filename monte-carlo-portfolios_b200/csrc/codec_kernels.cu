@@ -764,7 +764,8 @@ constexpr int FE_THREADS = 128;
 constexpr int FE_VCAP = 4096;   // staged values per batch: one 32-int block per thread
 constexpr int FE_MAXL = 128;    // lists per batch
 constexpr int FE_MINB = 7;      // resident CTAs per SM the kernels are compiled for (<= 72 registers, <= 31 KB shared memory)
-constexpr int FE_OCAP = 2304;   // staged compressed words per batch
+constexpr int FE_OCAP = 2048;   // staged compressed words per batch
+constexpr int FE_TCAP = 1024;   // VariableByte tail values per batch (n mod 32 of every list)
 constexpr int FE_VPAD = FE_VCAP + FE_VCAP / 32 + 2;
 
 __host__ __device__ inline bool fast_codec_ok(int codec, bool delta)
@@ -850,7 +851,9 @@ __device__ __forceinline__ uint32_t tail_value(const uint32_t *s_val, int g, int
 
 __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const FastEncArgs a)
 {
-    __shared__ int s_tw[FE_MAXL];       // words of each list's VariableByte tail
+    __shared__ int s_tw[FE_MAXL];       // bytes of each list's VariableByte tail
+    __shared__ int s_tb[FE_MAXL];       // first slot of each list in the tail table
+    __shared__ uint16_t s_tt[FE_TCAP];  // tail table: (list << 8) | byte length, later (list << 8) | byte offset
     __shared__ uint32_t s_val[FE_VPAD];
     __shared__ uint32_t s_out[FE_OCAP];
     __shared__ int s_in[FE_MAXL + 1];   // value offset of each list inside the batch
@@ -884,7 +887,12 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
     __syncthreads();
     const int64_t vbase = s_vbase;
     const int nv = s_in[nl];
-    const bool staged = nv <= FE_VCAP;
+    // slots of the lists' VariableByte tails (n mod 32 values each) in the tail table
+    int ntv = 0;
+    const int my_r = tid < nl ? (s_in[tid + 1] - s_in[tid]) & 31 : 0;
+    const int my_tb = cta_excl_scan(my_r, s_scan, &ntv);
+    if (tid < nl) s_tb[tid] = my_tb;
+    const bool staged = nv <= FE_VCAP && ntv <= FE_TCAP;
     bool fit = false;
     long long T = 0; // words this batch produces
     int my_pos = 0, my_b = 0, my_list = 0, my_k = 0, my_start = 0;
@@ -928,14 +936,25 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
         s_bsum[tid] = bex;
         if (tid == 0) s_bsum[FE_THREADS] = tb;
         __syncthreads();
-        // ---- VariableByte tails (n mod 32 values per list): a warp per list, a lane per value
-        for (int j = warp; j < nl; j += FE_THREADS / 32) {
-            const int n = s_in[j + 1] - s_in[j], nb = n >> 5, r = n & 31;
-            int len = 0;
-            if (lane < r) len = vb_len(tail_value(s_val, s_in[j] + 32 * nb + lane, lane, nb, tr, a.delta));
-#pragma unroll
-            for (int d = 16; d; d >>= 1) len += __shfl_xor_sync(kFull, len, d);
-            if (lane == 0) s_tw[j] = (len + 3) >> 2;
+        // ---- VariableByte tails (n mod 32 values per list), one THREAD per tail value: (1) every list claims a run of
+        // slots in the tail table, (2) every value computes its byte length, (3) one thread per list turns the lengths
+        // of its < 32 values into byte offsets.  The table entry is (list << 8) | length, then (list << 8) | offset.
+        if (tid < nl)
+            for (int i = 0; i < my_r; ++i) s_tt[my_tb + i] = (uint16_t)(tid << 8);
+        __syncthreads();
+        {
+            for (int v = tid; v < ntv; v += FE_THREADS) {
+                const int j = s_tt[v] >> 8, i = v - s_tb[j];
+                const int nb = (s_in[j + 1] - s_in[j]) >> 5;
+                s_tt[v] = (uint16_t)((j << 8) | vb_len(tail_value(s_val, s_in[j] + 32 * nb + i, i, nb, tr, a.delta)));
+            }
+            __syncthreads();
+            if (tid < nl) {
+                const int r = (s_in[tid + 1] - s_in[tid]) & 31, v0 = s_tb[tid];
+                int run = 0;
+                for (int i = 0; i < r; ++i) { const int len = s_tt[v0 + i] & 255; s_tt[v0 + i] = (uint16_t)((tid << 8) | run); run += len; }
+                s_tw[tid] = run; // bytes (<= 155)
+            }
         }
         __syncthreads();
         // ---- per list: words of the whole list
@@ -945,7 +964,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
             const int i0 = s_ib[tid];
             const int bw = s_bsum[i0 + nb] - s_bsum[i0]; // i0 + nb <= ni <= FE_THREADS
             const int hdrs = (nb >> 2) + (nb & 3);
-            lw = (n > 0 ? 1 + bw + hdrs + s_tw[tid] : (tr.sk ? 1 : 0)) + (a.app ? 1 : 0);
+            lw = (n > 0 ? 1 + bw + hdrs + ((s_tw[tid] + 3) >> 2) : (tr.sk ? 1 : 0)) + (a.app ? 1 : 0);
         }
         int Tw = 0;
         const int lex = cta_excl_scan(lw, s_scan, &Tw);
@@ -982,30 +1001,27 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
                 else if ((my_k & 3) == 0)
                     s_out[my_pos - 1] = ((uint32_t)my_b << 24) | ((uint32_t)s_w[tid + 1] << 16) | ((uint32_t)s_w[tid + 2] << 8) | (uint32_t)s_w[tid + 3];
             }
-            // ---- per list: header word and the trailing zero int of the loader's framing
+            // ---- per list: header word, zero padding of the VariableByte tail, trailing zero int of the loader's framing
             if (tid < nl) {
                 const int n = s_in[tid + 1] - s_in[tid], nb = n >> 5;
                 if (n > 0 || tr.sk) s_out[s_lo[tid]] = tr.sk ? (uint32_t)n : (uint32_t)(32 * nb); // IntCompressor: n; Composition: F1 header / 0 marker
-                if (a.app) s_out[s_lo[tid + 1] - 1] = 0u; // LoadPortfolios.java:622: outpos + 1 ints
+                const int tbytes = s_tw[tid], tend = (int)s_lo[tid + 1] - (a.app ? 1 : 0);
+                uint8_t *tbp = reinterpret_cast<uint8_t *>(s_out + tend - ((tbytes + 3) >> 2));
+                for (int q = tbytes; q & 3; ++q) tbp[q] = 0;   // zero-padded to a word (VariableByte.java:62-66)
+                if (a.app) s_out[s_lo[tid + 1] - 1] = 0u;       // LoadPortfolios.java:622: outpos + 1 ints
             }
-            // ---- VariableByte tails: lane i writes the bytes of tail value i at the warp-prefix of the byte lengths
-            for (int j = warp; j < nl; j += FE_THREADS / 32) {
-                const int n = s_in[j + 1] - s_in[j], nb = n >> 5, r = n & 31;
-                if (r == 0) continue;
-                uint32_t d = 0;
-                int len = 0;
-                if (lane < r) { d = tail_value(s_val, s_in[j] + 32 * nb + lane, lane, nb, tr, a.delta); len = vb_len(d); }
-                const int incl = (int)warp_incl_scan((uint32_t)len, lane);
-                const int total = __shfl_sync(kFull, incl, 31);
-                uint8_t *tb = reinterpret_cast<uint8_t *>(s_out + s_lo[j + 1] - (a.app ? 1 : 0) - s_tw[j]);
-                int o = incl - len;
-                for (int q = 0; q < len - 1; ++q) { tb[o++] = (uint8_t)(d & 127u); d >>= 7; }
-                if (len) tb[o] = (uint8_t)(d | 128u);
-                if (lane < ((4 - (total & 3)) & 3)) tb[total + lane] = 0; // zero-padded to a word (VariableByte.java:62-66)
+            // ---- VariableByte tails: every value writes its bytes at its offset
+            for (int v = tid; v < ntv; v += FE_THREADS) {
+                const int e = s_tt[v], j = e >> 8, off = e & 255, i = v - s_tb[j];
+                const int nb = (s_in[j + 1] - s_in[j]) >> 5;
+                uint32_t d = tail_value(s_val, s_in[j] + 32 * nb + i, i, nb, tr, a.delta);
+                uint8_t *tbp = reinterpret_cast<uint8_t *>(s_out + (int)s_lo[j + 1] - (a.app ? 1 : 0) - ((s_tw[j] + 3) >> 2)) + off;
+                while (d >= 128u) { *tbp++ = (uint8_t)(d & 127u); d >>= 7; }
+                *tbp = (uint8_t)(d | 128u);
             }
         }
     }
-    // ---- batches whose values do not fit the staging area: sizes by the per-warp routines (one list per warp at a time)
+    // ---- batches whose values or tails do not fit the staging areas: sizes by the per-warp routines (one list per warp at a time)
     if (!staged) {
         for (int j = warp; j < nl; j += FE_THREADS / 32) {
             const int64_t beg = a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len;

@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     }
     uint64_t tk[VM_G];   // generic compare: candidate iff fkey(V) <= tk
     uint64_t traw[VM_G]; // fast compare (negative bound, the normal case): candidate iff bits(V) >= traw, unsigned
+    uint32_t thi[VM_G];  // ... tested on the high words only
     int cnt[VM_G];
     double s1[VM_G], s2[VM_G];
     double *drow[VM_G];   // DENSE: the portfolio's row as doubles, at this sub-chunk
@@ -482,10 +483,12 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     for (int g = 0; g < VM_G; ++g) {
         tk[g] = 0; // fkey(x) <= 0 never holds for a finite x: inactive rows never append
         traw[g] = ~0ull;
+        thi[g] = 0xffffffffu;
         if (!DENSE && ok[g]) {
             tk[g] = a.tkey[prow[g]];
             const double bound = fkey_inv(tk[g]);
             traw[g] = (uint64_t)__double_as_longlong(bound);
+            thi[g] = (uint32_t)(traw[g] >> 32);
             neg = neg && (bound < 0.0);
         }
         cnt[g] = 0;
@@ -530,8 +533,11 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 #ifndef MCP_EXP_NO_FILTER
                 uint32_t h0, h1;
                 if (fastcmp) {
-                    h0 = ((uint64_t)__double_as_longlong(pd0[g]) >= traw[g]) & v0;
-                    h1 = ((uint64_t)__double_as_longlong(pd1[g]) >= traw[g]) & v1;
+                    // high words only: one 32-bit compare per value.  A superset of the exact test (values whose high
+                    // word ties with the bound's pass regardless of the low word, a 2^-20 relative band): the filter
+                    // only has to be conservative, the selection is exact.
+                    h0 = ((uint32_t)__double2hiint(pd0[g]) >= thi[g]) & v0;
+                    h1 = ((uint32_t)__double2hiint(pd1[g]) >= thi[g]) & v1;
                 } else {
                     h0 = (fkey(pd0[g]) <= tk[g]) & v0;
                     h1 = (fkey(pd1[g]) <= tk[g]) & v1;
@@ -1574,11 +1580,15 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_k
 struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
 
-// length of the dense first step: ~4 tail sizes, at least 2048 trials, a multiple of 8 (tensor-core trial blocks)
+// length of the dense first step: ~4 tail sizes, at least kDenseFloor trials, a multiple of 8 (tensor-core trial blocks)
+#ifndef MCP_DENSE_FLOOR
+#define MCP_DENSE_FLOOR 2048
+#endif
+constexpr int64_t kDenseFloor = MCP_DENSE_FLOOR;
 static int64_t first_step_len(int64_t N, int64_t t)
 {
     int64_t c0 = 4 * t;
-    if (c0 < 2048) c0 = 2048;
+    if (c0 < kDenseFloor) c0 = kDenseFloor;
     c0 = (c0 + 7) & ~(int64_t)7;
     return c0 < N ? c0 : N;
 }
