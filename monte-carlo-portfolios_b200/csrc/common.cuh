@@ -102,6 +102,11 @@ struct mcp_ctx {
     std::vector<int32_t> tsFlagRows;
     mcp::DevBuf dTsSend, dTsRecv, dTsRecv2, dTsFlags;
     void *nccl = nullptr;          // NcclComm* (nccl_dyn.cu), null until mcp_comm_init
+    cudaStream_t stream3 = nullptr; // second tile stream (risk_stream_core), `cur` = the stream the tile helpers launch on
+    cudaStream_t cur = nullptr;
+    cudaEvent_t evTileFork = nullptr, evTileJoin = nullptr, evSfrag = nullptr;
+    int64_t overlapTiles = 1;      // >1: that many portfolio tiles alternate between two streams (selection of one tile under the valuation of the next); measured -2 % at best on C2 -- the valuation kernel leaves no idle issue slots to hide in -- so off by default
+    mcp::DevBuf dCandKey2, dCandCnt2;
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr;
     bool sTailPending = false;     // pipelined upload: scenario rows >= sHeadRows are still arriving on stream2 (evTail)
@@ -159,7 +164,7 @@ struct KScope {
     int cls;
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t st;
-    KScope(mcp_ctx *c, int k, int nlaunch = 1, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : c->stream)
+    KScope(mcp_ctx *c, int k, int nlaunch = 1, cudaStream_t s = nullptr) : ctx(c), cls(k), st(s ? s : (c->cur ? c->cur : c->stream))
     {
         ctx->prof.launches[cls] += nlaunch;
         if (!ctx->prof.on) return;
@@ -180,6 +185,8 @@ struct KScope {
         ctx->prof.recs.push_back({cls, a, b});
     }
 };
+
+inline cudaStream_t cur_stream(mcp_ctx *ctx) { return ctx->cur ? ctx->cur : ctx->stream; }
 
 inline int check_launch(mcp_ctx *ctx, const char *what)
 {

@@ -94,6 +94,10 @@ int mcp_create(int device, mcp_ctx **out)
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evTileFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evTileJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evSfrag, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evTail, cudaEventDisableTiming) != cudaSuccess ||
@@ -113,6 +117,7 @@ void mcp_destroy(mcp_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream3) cudaStreamSynchronize(ctx->stream3);
     resolve_profile(ctx);
     nccl_comm_destroy(ctx);
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
@@ -122,7 +127,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
                            &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
-                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
+                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dCandKey2, &ctx->dCandCnt2, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -130,6 +135,10 @@ void mcp_destroy(mcp_ctx *ctx)
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evTail) cudaEventDestroy(ctx->evTail);
+    if (ctx->evTileFork) cudaEventDestroy(ctx->evTileFork);
+    if (ctx->evTileJoin) cudaEventDestroy(ctx->evTileJoin);
+    if (ctx->evSfrag) cudaEventDestroy(ctx->evSfrag);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -155,6 +164,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
+    else if (!strcmp(key, "overlap_tiles")) ctx->overlapTiles = value < 1 ? 1 : value;
     else if (!strcmp(key, "ts_slack")) ctx->tsSlackOverride = value; // trial-sharded test hook: m = ceil(t / world) + value (-1 = automatic)
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");

@@ -1598,6 +1598,8 @@ int64_t risk_first_step_len(int64_t N, int64_t t) { return first_step_len(N, t);
 // Trial schedule of the streaming path.  Guaranteed: a dense first step of ~4 tail sizes establishes each
 // portfolio's threshold, then steps grow 3x; every later step inserts ~2 tail sizes of candidates.  Optimistic
 // (`two_step`): the dense first step, then ONE sparse step over all remaining trials (see optimistic_rank).
+static inline bool steps_hint_two(bool, int64_t N, int64_t e) { return e < N; } // a dense step that is followed by sparse ones
+
 static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sms, bool two_step = false, int64_t kItemTrials = 2048)
 {
     std::vector<Step> steps;
@@ -1607,7 +1609,9 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
         int64_t e = b + len;
         if (e > N || (b > 0 && (two_step || N - e < len / 4))) e = N; // fold a short remainder into the last (sparse) step
         const int64_t L = e - b;
-        int64_t waves = (L * nsg + (int64_t)sms * kItemTrials / 2) / ((int64_t)sms * kItemTrials);
+        // the short dense step wants small work items (two or three full waves of CTAs instead of a part-filled one)
+        const int64_t item = (b == 0 && steps_hint_two(two_step, N, e)) ? std::min<int64_t>(kItemTrials, 512) : kItemTrials;
+        int64_t waves = (L * nsg + (int64_t)sms * item / 2) / ((int64_t)sms * item);
         if (waves < 1) waves = 1;
         int64_t nsub = (sms * waves) / nsg;
         if (nsub < 1) nsub = 1;
@@ -1632,7 +1636,7 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
         if (bm_smem > 40 * 1024)
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
         KScope ks(ctx, MCP_K_SELECT);
-        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, ctx->stream>>>(kk, ki, t, n_trials, 0, breach, cvar);
+        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         return check_launch(ctx, "k_finalize_bitmap");
     }
     int m = 1;
@@ -1646,7 +1650,7 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
         MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     }
     KScope ks(ctx, MCP_K_SELECT);
-    k_finalize<<<(unsigned)rows, FIN_THREADS, fin_global ? 0 : fin_smem, ctx->stream>>>(
+    k_finalize<<<(unsigned)rows, FIN_THREADS, fin_global ? 0 : fin_smem, cur_stream(ctx)>>>(
         kk, ki, t, m, breach, cvar, fin_global ? ctx->dFinKey.as<uint64_t>() : nullptr, fin_global ? ctx->dFinIdx.as<int32_t>() : nullptr);
     return check_launch(ctx, "k_finalize");
 }
@@ -1710,10 +1714,10 @@ static int launch_value_mma(mcp_ctx *ctx, const StreamArgs &v, bool dense, dim3 
     KScope ks(ctx, MCP_K_VALUE);
     const size_t sm = vm_smem_bytes<NK>();
     const bool mom = v.part != nullptr;
-    if (dense && mom) k_value_mma<NK, true, true><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
-    else if (dense) k_value_mma<NK, true, false><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
-    else if (mom) k_value_mma<NK, false, true><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
-    else k_value_mma<NK, false, false><<<grid, VM_THREADS, sm, ctx->stream>>>(v);
+    if (dense && mom) k_value_mma<NK, true, true><<<grid, VM_THREADS, sm, cur_stream(ctx)>>>(v);
+    else if (dense) k_value_mma<NK, true, false><<<grid, VM_THREADS, sm, cur_stream(ctx)>>>(v);
+    else if (mom) k_value_mma<NK, false, true><<<grid, VM_THREADS, sm, cur_stream(ctx)>>>(v);
+    else k_value_mma<NK, false, false><<<grid, VM_THREADS, sm, cur_stream(ctx)>>>(v);
     return check_launch(ctx, "k_value_mma");
 }
 
@@ -1743,7 +1747,7 @@ static int scenarios_tail_ready(mcp_ctx *ctx)
     MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evTail, 0));
     ctx->sTailPending = false;
     const int NK = ctx->F / 4;
-    KScope ks(ctx, MCP_K_GEN);
+    KScope ks(ctx, MCP_K_GEN, 1, ctx->stream);
     k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, NK, ctx->dSfrag.as<double>(),
                                                                                   ctx->sHeadRows / 8, (ctx->N + 7) / 8);
     MCP_TRY(check_launch(ctx, "k_repack_scenarios (tail)"));
@@ -1869,6 +1873,12 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
     size_t budget = ctx->prop.totalGlobalMem / 4;
     if (budget > ((size_t)40 << 30)) budget = (size_t)40 << 30;
     int64_t Pt = P;
+    // Portfolio tiles alternate between two streams: the selection / compaction kernels of one tile (latency-bound,
+    // small CTAs) then run under the valuation kernel of the next (DMMA-bound, one 512-thread CTA per SM that leaves
+    // registers and shared memory for them) instead of after it.
+    const int64_t groups = (P + VM_PG - 1) / VM_PG;
+    const int64_t want_tiles = ctx->overlapTiles > 1 && groups >= 2 * ctx->overlapTiles ? ctx->overlapTiles : 1;
+    if (want_tiles > 1) Pt = ((groups + want_tiles - 1) / want_tiles) * VM_PG;
     std::vector<Step> steps;
     int64_t stride = 0, rank0 = t;
     int max_nsub = 0, nparts = 0;
@@ -1889,14 +1899,28 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
     if (optimistic) rank0 = optimistic_rank(N, steps[0].end, t);
     if (nparts_out) *nparts_out = nparts;
     if (Pt > 65535 * (int64_t)VM_PG) Pt = 65535 * (int64_t)VM_PG;
-    MCP_CUDA(ctx, ctx->dCandKey.reserve((size_t)Pt * stride * 16));
-    MCP_CUDA(ctx, ctx->dCandCnt.reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
+    const int nstreams = (P > Pt && ctx->overlapTiles > 1) ? 2 : 1;
+    mcp::DevBuf *candKey[2] = {&ctx->dCandKey, &ctx->dCandKey2}, *candCnt[2] = {&ctx->dCandCnt, &ctx->dCandCnt2};
+    for (int i = 0; i < nstreams; ++i) {
+        MCP_CUDA(ctx, candKey[i]->reserve((size_t)Pt * stride * 16));
+        MCP_CUDA(ctx, candCnt[i]->reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
+    }
     if (io.moments) MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
     MCP_TRY(ensure_sfrag(ctx));
+    cudaStream_t tile_stream[2] = {ctx->stream, ctx->stream3};
+    if (nstreams == 2) {
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evTileFork, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->evTileFork, 0));
+    }
+    bool tail_event = false, tail_waited = false; // pipelined upload: the second stream waits for the tail repack too
+    struct CurReset { mcp_ctx *c; ~CurReset() { c->cur = nullptr; } } cur_reset{ctx};
 
-    for (int64_t p0 = 0; p0 < P; p0 += Pt) {
+    int64_t tile = 0;
+    for (int64_t p0 = 0; p0 < P; p0 += Pt, ++tile) {
         const int64_t p1 = (p0 + Pt < P) ? p0 + Pt : P;
         const int64_t rows = p1 - p0;
+        const int sidx_ = (int)(tile % nstreams);
+        ctx->cur = tile_stream[sidx_];
         uint64_t *kkey[2] = {io.kkey[0] + p0 * t, io.kkey[1] + p0 * t};
         int32_t *kidx[2] = {io.kidx[0] + p0 * t, io.kidx[1] + p0 * t};
         int cur = 0, part_base = 0;
@@ -1904,7 +1928,15 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
         for (size_t si = 0; si < steps.size(); ++si) {
             const Step &s = steps[si];
             const bool dense = si == 0;
-            if (ctx->sTailPending && s.end > ctx->sHeadRows) MCP_TRY(scenarios_tail_ready(ctx));
+            if (ctx->sTailPending && s.end > ctx->sHeadRows) {
+                MCP_TRY(scenarios_tail_ready(ctx)); // on ctx->stream
+                MCP_CUDA(ctx, cudaEventRecord(ctx->evSfrag, ctx->stream));
+                tail_event = true;
+            }
+            if (sidx_ == 1 && tail_event && !tail_waited && s.end > ctx->sHeadRows) {
+                MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->evSfrag, 0));
+                tail_waited = true;
+            }
             StreamArgs v{};
             v.E = io.E;
             v.S = ctx->dS.as<double>();
@@ -1913,9 +1945,9 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
             v.n_begin = s.begin; v.n_end = s.end;
             v.nsub = s.nsub; v.sub_len = s.sub_len;
             v.tkey = io.tkey;
-            v.cand = ctx->dCandKey.p;
+            v.cand = candKey[sidx_]->p;
             v.pitch = stride * 16;
-            v.cnt = ctx->dCandCnt.as<int32_t>();
+            v.cnt = candCnt[sidx_]->as<int32_t>();
             v.part = io.moments ? ctx->dPart.as<double>() : nullptr;
             v.part_stride = nparts; v.part_base = part_base;
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
@@ -1950,10 +1982,10 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
                 a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
-                if (reg && a.step_len <= 8 * SEL_THREADS) k_select_dense<8><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(a);
-                else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(a);
+                if (reg && a.step_len <= 8 * SEL_THREADS) k_select_dense<8><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
+                else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
                 else
-                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
+                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
             kept = a.tail;
@@ -1962,6 +1994,11 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
         }
         io.final_buf = cur;
         if (!io.keep_only) MCP_TRY(run_finalize(ctx, rows, t, kkey[cur], kidx[cur], io.breach + p0 * t, io.cvar + p0));
+    }
+    ctx->cur = nullptr;
+    if (nstreams == 2) {
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evTileJoin, ctx->stream3));
+        MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evTileJoin, 0));
     }
     return MCP_OK;
 }

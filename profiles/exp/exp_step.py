@@ -14,7 +14,7 @@ def bench(tag, steps=8):
         ctx.flush_l2(); ctx.sync(); ctx.timer_start(); ctx.run(alpha,cid,N.FRAME_APP); ms.append(ctx.timer_stop())
     pr=ctx.profile_get(); ctx.profile(False)
     print(tag, "step %.3f ms"%np.mean(ms), {k:round(v['ms']/steps,3) for k,v in pr.items() if v['launches']}, ctx.run_stats(), flush=True)
-for it in (2048,4096,1024):
-    ctx.set_option("item_trials", it); bench("item_trials=%d"%it)
-ctx.set_option("item_trials", 2048)
+for ot in (4, 1, 2, 3, 5, 8):
+    ctx.set_option("overlap_tiles", ot); bench("overlap_tiles=%d"%ot)
+ctx.set_option("overlap_tiles", 1)
 ctx.set_option("optimistic",0); bench("guaranteed"); ctx.set_option("optimistic",1)

@@ -78,6 +78,23 @@ def test_run_matches_oracle(ctx, shape):
     check_against_oracle(ctx, E, S, alpha)
 
 
+def test_tile_overlap_on_two_streams_gives_identical_results(ctx):
+    """overlap_tiles > 1 alternates portfolio tiles between two streams with separate candidate buffers."""
+    E, S = riskcases.synthetic(2100, 9000, 32, 77)
+    rows = list(range(0, 2100, 97)) + [2099]
+    r1 = check_against_oracle(ctx, E, S, 0.99, rows=rows)
+    ctx.set_option("overlap_tiles", 4)
+    try:
+        r4 = check_against_oracle(ctx, E, S, 0.99, rows=rows)
+        ctx.set_option("optimistic", 0)
+        r4g = check_against_oracle(ctx, E, S, 0.99, rows=rows)
+    finally:
+        ctx.set_option("overlap_tiles", 1)
+        ctx.set_option("optimistic", 1)
+    for k in ("var_loss", "var_trial", "breach", "enc_off", "enc", "cvar", "mean", "variance"):
+        assert np.array_equal(r1[k], r4[k]) and np.array_equal(r1[k], r4g[k]), k
+
+
 @pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic"])
 def test_alternate_kernel_paths_agree(ctx, opt):
     """F = 32 normally takes the streaming kernels (two-step optimistic schedule, dense-step selection from
