@@ -153,6 +153,12 @@ int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing,
  */
 int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F);
 int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F);
+/* Ingest: build E on the device from what the loader parses (LoadPortfolios.java:352-379: per portfolio the
+ * `instruments` array of {instrument, weight}), CSR: positions pos_off[p] .. pos_off[p+1] belong to portfolio p.
+ * E[p][f] = fma chain in FILE ORDER of weight * loadings[instrument][f], loadings = n_instruments x F row-major
+ * (the instrument -> factor table; the reference ships none).  MCP_E_ARG on an id outside the table. */
+int mcp_build_exposures(mcp_ctx *ctx, const int32_t *instruments, const double *weights, const int64_t *pos_off, int64_t P,
+                        const double *loadings, int64_t n_instruments, int32_t F);
 /* Counter-based on-device generation (Philox4x32-10, Irwin-Hall(12) variates;
  * value = fma(x, scale, shift); bit-identical to oracle/risk_oracle.c orc_gen_normal).
  * row0 = global index of the first row (for sharded generation). */

@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         "mcp_codec_decode_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp]),
         "mcp_upload_exposures": (C.c_int, [vp, vp, i64, i32]),
         "mcp_upload_scenarios": (C.c_int, [vp, vp, i64, i32]),
+        "mcp_build_exposures": (C.c_int, [vp, vp, vp, vp, i64, vp, i64, i32]),
         "mcp_generate_exposures": (C.c_int, [vp, i64, i32, u64, f64, f64, i64]),
         "mcp_generate_scenarios": (C.c_int, [vp, i64, i32, u64, f64, f64, i64]),
         "mcp_download_exposures": (C.c_int, [vp, vp]),

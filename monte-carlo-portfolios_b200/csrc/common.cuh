@@ -224,6 +224,8 @@ int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t
 int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
                      int64_t *total);
 int64_t risk_first_step_len(int64_t N, int64_t t);
+int build_exposures(mcp_ctx *ctx, const int32_t *d_inst, const double *d_w, const int64_t *d_off, int64_t P, const double *d_B,
+                    int64_t n_inst, int32_t F, double *d_E);
 int fp64_peak(mcp_ctx *ctx, double *tflops);
 int fp64_mma_peak(mcp_ctx *ctx, double *tflops);
 int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world);

@@ -413,6 +413,33 @@ int mcp_upload_exposures(mcp_ctx *ctx, const double *E, int64_t P, int32_t F)
     return MCP_OK;
 }
 
+int mcp_build_exposures(mcp_ctx *ctx, const int32_t *instruments, const double *weights, const int64_t *pos_off, int64_t P,
+                        const double *loadings, int64_t n_instruments, int32_t F)
+{
+    MCP_TRY(set_dev(ctx));
+    if (P < 0 || F <= 0 || n_instruments <= 0 || !pos_off || !loadings) return fail(ctx, MCP_E_ARG, "build_exposures: bad argument");
+    if (pos_off[0] != 0) return fail(ctx, MCP_E_ARG, "build_exposures: offsets must start at 0");
+    for (int64_t p = 0; p < P; ++p)
+        if (pos_off[p + 1] < pos_off[p]) return fail(ctx, MCP_E_ARG, "build_exposures: offsets not monotone");
+    const int64_t npos = pos_off[P];
+    if (npos > 0 && (!instruments || !weights)) return fail(ctx, MCP_E_ARG, "build_exposures: null positions");
+    if (ctx->haveS && ctx->F != F) ctx->haveS = false;
+    ctx->haveE = false;
+    MCP_CUDA(ctx, ctx->dE.reserve((size_t)P * F * sizeof(double) + 16));
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)(npos + 1) * sizeof(int32_t)));
+    MCP_CUDA(ctx, ctx->dIo1.reserve((size_t)(P + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)(npos + 1) * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve((size_t)n_instruments * F * sizeof(double)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, instruments, (size_t)npos * sizeof(int32_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo1.p, pos_off, (size_t)(P + 1) * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo2.p, weights, (size_t)npos * sizeof(double)));
+    MCP_TRY(h2d(ctx, ctx->dIo3.p, loadings, (size_t)n_instruments * F * sizeof(double)));
+    MCP_TRY(build_exposures(ctx, ctx->dIo0.as<int32_t>(), ctx->dIo2.as<double>(), ctx->dIo1.as<int64_t>(), P, ctx->dIo3.as<double>(),
+                            n_instruments, F, ctx->dE.as<double>()));
+    ctx->P = P; ctx->F = F; ctx->haveE = true; ctx->haveRun = false;
+    return MCP_OK;
+}
+
 int mcp_upload_scenarios(mcp_ctx *ctx, const double *S, int64_t N, int32_t F)
 {
     MCP_TRY(set_dev(ctx));

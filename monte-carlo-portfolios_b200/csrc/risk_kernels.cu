@@ -129,6 +129,59 @@ int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate
     return MCP_OK;
 }
 
+// ============================================================ ingest: positions -> exposure matrix
+// E[p][f] = fma chain, in file order, of weight_j * B[instrument_j][f] over the portfolio's (instrument, weight)
+// positions (LoadPortfolios.java:352-379 reads them; DESIGN.md 3.0 defines the product; oracle: orc_build_exposures).
+// One warp per portfolio: 32 positions are fetched coalesced and handed round by shuffle, lane l owns factors l, l+32, ...
+// The loading rows it gathers (F doubles each, 2.5 MB table for the shipped sample) stay in L2.
+__global__ void __launch_bounds__(256) k_build_exposures(const int32_t *__restrict__ inst, const double *__restrict__ w,
+                                                         const int64_t *__restrict__ off, int64_t P, const double *__restrict__ B,
+                                                         int64_t n_inst, int F, double *__restrict__ E, int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const int64_t j0 = off[p], j1 = off[p + 1];
+    for (int f0 = 0; f0 < F; f0 += 64) {
+        const int fa = f0 + lane, fb = f0 + 32 + lane;
+        double acc_a = 0.0, acc_b = 0.0;
+        for (int64_t base = j0; base < j1; base += 32) {
+            const int64_t j = base + lane;
+            int32_t my_i = 0;
+            double my_w = 0.0;
+            if (j < j1) { my_i = inst[j]; my_w = w[j]; }
+            if (j < j1 && (my_i < 0 || my_i >= n_inst)) { *err = 1; my_i = 0; my_w = 0.0; }
+            const int cnt = (int)min((int64_t)32, j1 - base);
+            for (int k = 0; k < cnt; ++k) {
+                const int32_t ii = __shfl_sync(kFullMask, my_i, k);
+                const double ww = __shfl_sync(kFullMask, my_w, k);
+                const double *row = B + (int64_t)ii * F;
+                if (fa < F) acc_a = fma(ww, __ldg(row + fa), acc_a);
+                if (fb < F) acc_b = fma(ww, __ldg(row + fb), acc_b);
+            }
+        }
+        if (fa < F) E[p * F + fa] = acc_a;
+        if (fb < F) E[p * F + fb] = acc_b;
+    }
+}
+
+int build_exposures(mcp_ctx *ctx, const int32_t *d_inst, const double *d_w, const int64_t *d_off, int64_t P, const double *d_B,
+                    int64_t n_inst, int32_t F, double *d_E)
+{
+    if (P == 0) return MCP_OK;
+    MCP_CUDA(ctx, ctx->dErr.reserve(64));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
+    {
+        KScope ks(ctx, MCP_K_GEN);
+        k_build_exposures<<<(unsigned)((P * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_inst, d_w, d_off, P, d_B, n_inst, F, d_E, ctx->dErr.as<int>());
+        MCP_TRY(check_launch(ctx, "k_build_exposures"));
+    }
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dErr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*reinterpret_cast<int *>(ctx->hPinned) != 0) return fail(ctx, MCP_E_ARG, "build_exposures: instrument id outside the loading table");
+    return MCP_OK;
+}
+
 // ============================================================ FP64 peak probe
 // 8 independent DFMA chains per thread, no memory traffic: measures the FP64 FMA issue
 // rate that the valuation kernel is bounded by (MEASURED_PEAKS.json has no FP64 entry).

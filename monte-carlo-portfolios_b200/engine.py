@@ -145,6 +145,15 @@ class Context:
         E = np.ascontiguousarray(E, np.float64)
         self._check(self._L.mcp_upload_exposures(self._h, _ptr(E), E.shape[0], E.shape[1]), "upload_exposures")
 
+    def build_exposures(self, instruments, weights, pos_off, loadings):
+        """Ingest: (instrument, weight) positions in CSR form x the instrument -> factor loading table -> E on the device."""
+        inst = np.ascontiguousarray(instruments, np.int32)
+        w = np.ascontiguousarray(weights, np.float64)
+        off = np.ascontiguousarray(pos_off, np.int64)
+        B = np.ascontiguousarray(loadings, np.float64)
+        self._check(self._L.mcp_build_exposures(self._h, _ptr(inst), _ptr(w), _ptr(off), off.size - 1, _ptr(B), B.shape[0], B.shape[1]),
+                    "build_exposures")
+
     def upload_scenarios(self, S):
         S = np.ascontiguousarray(S, np.float64)
         self._check(self._L.mcp_upload_scenarios(self._h, _ptr(S), S.shape[0], S.shape[1]), "upload_scenarios")

@@ -65,3 +65,27 @@ class LoadPortfolios:
                                       "min_weight": min(w), "max_weight": max(w)},
                          "instruments": self.getInstrumentDocument(ins, blob)})
         return docs
+
+
+def read_portfolios_json(path: str):
+    """portfolios.json (one JSON object per line, LoadPortfolios.java:177-419 / synth/portfolios.synth): -> ids, and the
+    positions in CSR form (instruments int32, weights float64, pos_off int64[P+1]) in file order."""
+    ids, inst, w, off = [], [], [], [0]
+    for line in open(path):
+        if not line.strip():
+            continue
+        r = json.loads(line)
+        ids.append(r.get("id", len(ids)))
+        for pos in r["instruments"]:
+            inst.append(int(pos["instrument"]))
+            w.append(float(pos["weight"]))
+        off.append(len(inst))
+    return ids, np.asarray(inst, np.int32), np.asarray(w, np.float64), np.asarray(off, np.int64)
+
+
+def read_macro_json(path: str) -> np.ndarray:
+    """macro.json (synth/macro.synth): one row per date_offset, factors m0..m{F-1} -> S[N][F] (row = trial)."""
+    rows = [json.loads(line) for line in open(path) if line.strip()]
+    rows.sort(key=lambda r: r.get("date_offset", 0))
+    F = sum(1 for k in rows[0] if k.startswith("m") and k[1:].isdigit())
+    return np.array([[float(r[f"m{k}"]) for k in range(F)] for r in rows], np.float64)

@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
         L.orc_batch_uncompress.restype = C.c_int
         L.orc_batch_uncompress.argtypes = [C.c_int, C.c_int, u8p, C.c_int64, i64p, C.c_int64, i32p, i64p, C.c_int]
         L.orc_value.restype = None
+        L.orc_build_exposures.argtypes = [i32p, f64p, i64p, C.c_int64, f64p, C.c_int64, C.c_int32, f64p]
+        L.orc_build_exposures.restype = C.c_int
         L.orc_value.argtypes = [f64p, f64p, C.c_int64, C.c_int64, C.c_int32, f64p, C.c_int]
         L.orc_risk.restype = C.c_int64
         L.orc_risk.argtypes = [f64p, f64p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int64, C.c_int64,
@@ -240,6 +242,20 @@ def batch_uncompress(codec: int, framing: int, buf: np.ndarray, stride: int, len
 
 
 # ----------------------------------------------------------------------- risk
+def build_exposures(instruments, weights, pos_off, loadings) -> np.ndarray:
+    """E[p][f] = fma chain over the portfolio's positions in file order of weight * loadings[instrument][f]."""
+    inst = np.ascontiguousarray(instruments, np.int32)
+    w = np.ascontiguousarray(weights, np.float64)
+    off = np.ascontiguousarray(pos_off, np.int64)
+    B = np.ascontiguousarray(loadings, np.float64)
+    P, F = off.size - 1, B.shape[1]
+    E = np.empty((P, F), np.float64)
+    if lib().orc_build_exposures(_p(inst, C.c_int32), _p(w, C.c_double), _p(off, C.c_int64), P, _p(B, C.c_double), B.shape[0], F,
+                                 _p(E, C.c_double)) != 0:
+        raise ValueError("instrument id outside the loading table")
+    return E
+
+
 def value(E: np.ndarray, S: np.ndarray, nthreads: int = 0) -> np.ndarray:
     E = np.ascontiguousarray(E, np.float64)
     S = np.ascontiguousarray(S, np.float64)

@@ -105,6 +105,8 @@ int orc_batch_uncompress(int codec, int framing, const uint8_t *in, int64_t stri
 /* ---------------- risk half (builder-defined spec) ---------------- */
 
 /* V[p*N+n] = fma-chain over k ascending of E[p*F+k]*S[n*F+k], acc starts at +0.0 */
+int orc_build_exposures(const int32_t *inst, const double *w, const int64_t *off, int64_t P, const double *B, int64_t n_inst,
+                        int32_t F, double *E);
 void orc_value(const double *E, const double *S, int64_t P, int64_t N, int32_t F, double *V, int nthreads);
 
 /*

@@ -200,3 +200,26 @@ int64_t orc_gen_breach_list(int32_t *out, int64_t list, int32_t N, double rate, 
     }
     return cnt;
 }
+
+
+/*
+ * Ingest ([builder-defined]: the reference holds (instrument, weight) positions per portfolio,
+ * LoadPortfolios.java:352-379, and no instrument -> factor model).  Exposure of portfolio p to factor f:
+ *     acc = +0.0; for every position j of p in FILE ORDER: acc = fma(weight_j, B[instrument_j][f], acc)
+ * with B the n_inst x F loading table.  Duplicate instruments simply contribute twice.  Returns -1 if an instrument
+ * id is outside [0, n_inst).
+ */
+int orc_build_exposures(const int32_t *inst, const double *w, const int64_t *off, int64_t P, const double *B, int64_t n_inst,
+                        int32_t F, double *E)
+{
+    for (int64_t p = 0; p < P; ++p)
+        for (int64_t j = off[p]; j < off[p + 1]; ++j)
+            if (inst[j] < 0 || inst[j] >= n_inst) return -1;
+    for (int64_t p = 0; p < P; ++p)
+        for (int32_t f = 0; f < F; ++f) {
+            double acc = 0.0;
+            for (int64_t j = off[p]; j < off[p + 1]; ++j) acc = fma(w[j], B[(int64_t)inst[j] * F + f], acc);
+            E[p * F + f] = acc;
+        }
+    return 0;
+}

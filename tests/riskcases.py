@@ -16,12 +16,18 @@ def c1_inputs():
     d = json.load(open(os.path.join(GOLD, "c1_sample.json")))
     F = 10
     B = cref.gen_normal(10000, F, 0x5EED0001, 3, 1e-2, 0.0)
-    E = np.zeros((len(d["portfolios"]), F))
-    for p, port in enumerate(d["portfolios"]):
-        for inst, w in zip(port["instruments"], port["weights"]):
-            E[p] += w * B[inst]   # (the oracle and the GPU consume the same E; its derivation is host-side ingest)
+    inst, w, off = c1_positions(d)
+    E = cref.build_exposures(inst, w, off, B)  # fma chain in file order; the GPU ingest kernel must match it bit for bit
     S = np.array(d["macro"], np.float64)
     return d, E, S
+
+
+def c1_positions(d):
+    inst = np.concatenate([np.asarray(p["instruments"], np.int32) for p in d["portfolios"]])
+    w = np.concatenate([np.asarray(p["weights"], np.float64) for p in d["portfolios"]])
+    off = np.zeros(len(d["portfolios"]) + 1, np.int64)
+    np.cumsum([len(p["instruments"]) for p in d["portfolios"]], out=off[1:])
+    return inst, w, off
 
 
 def synthetic(P, N, F, seed, scale_e=100.0, drift=0.05):

@@ -200,6 +200,35 @@ def test_optimistic_bound_falls_back_exactly(ctx):
         assert np.array_equal(r0[k], r1[k]), k
 
 
+def test_ingest_builds_the_exposure_matrix_on_the_device(ctx):
+    """Positions (instrument, weight) x loading table -> E on the GPU (mcp_build_exposures), bit-identical to the
+    oracle's file-order fma chain: the shipped sample (3 204 positions, duplicates, unsorted ids) and a synthetic
+    batch with empty portfolios, F up to 70, and portfolios longer than one warp round."""
+    d, E, S = riskcases.c1_inputs()
+    inst, w, off = riskcases.c1_positions(d)
+    B = cref.gen_normal(10000, 10, 0x5EED0001, 3, 1e-2, 0.0)
+    ctx.build_exposures(inst, w, off, B)
+    assert np.array_equal(ctx.download_exposures(10, 10).view(np.uint64), E.view(np.uint64))
+    ctx.upload_scenarios(S)
+    ctx.run(0.9)                                    # ... and straight into the path
+    o = cref.risk(E, S, 0.9)
+    r = ctx.fetch()
+    assert np.array_equal(r["breach"], o["breach"]) and np.array_equal(r["var_loss"], o["var_loss"])
+    rng = np.random.default_rng(5)
+    for F in (1, 32, 64, 70):
+        lens = rng.integers(0, 200, 300)
+        lens[[3, 77]] = 0
+        off = np.zeros(301, np.int64)
+        np.cumsum(lens, out=off[1:])
+        inst = rng.integers(0, 500, off[-1]).astype(np.int32)
+        w = rng.normal(size=off[-1]) * np.exp2(rng.integers(-10, 10, off[-1]))
+        B = rng.normal(size=(500, F))
+        ctx.build_exposures(inst, w, off, B)
+        assert np.array_equal(ctx.download_exposures(300, F).view(np.uint64), cref.build_exposures(inst, w, off, B).view(np.uint64)), F
+    with pytest.raises(Exception):
+        ctx.build_exposures(np.array([500], np.int32), np.ones(1), np.array([0, 1], np.int64), np.ones((500, 4)))
+
+
 def test_c1_shipped_sample(ctx):
     """BASELINE config C1: portfolios.json x macro.json (fixture tests/golden/c1_sample.json)."""
     d, E, S = riskcases.c1_inputs()

@@ -101,3 +101,42 @@ def test_generators():
 def test_tail_size_rule():
     assert cref.tail_size(100000, 0.99) == 1001 and cref.tail_size(10, 0.9) == 2 and cref.tail_size(10, 0.91) == 1
     assert cref.tail_size(7, 0.5) == 4  # k = ceil(3.5) = 4 -> t = 4
+
+
+def test_ingest_oracle_matches_exact_arithmetic():
+    """orc_build_exposures = fma chain in file order: check against exact rational arithmetic rounded once per step."""
+    from fractions import Fraction
+    rng = np.random.default_rng(3)
+    inst = rng.integers(0, 20, 40).astype(np.int32)
+    w = rng.normal(size=40)
+    off = np.array([0, 0, 7, 40], np.int64)
+    B = rng.normal(size=(20, 3))
+    E = cref.build_exposures(inst, w, off, B)
+    for p in range(3):
+        for f in range(3):
+            acc = 0.0
+            for j in range(off[p], off[p + 1]):
+                acc = float(Fraction(w[j]) * Fraction(B[inst[j], f]) + Fraction(acc))   # one rounding: fma
+            assert E[p, f] == acc
+    assert E[0].tolist() == [0.0, 0.0, 0.0]
+    with pytest.raises(ValueError):
+        cref.build_exposures(np.array([20], np.int32), np.ones(1), np.array([0, 1], np.int64), B)
+
+
+def test_json_readers_on_the_c1_fixture(tmp_path):
+    """read_portfolios_json / read_macro_json parse the reference's file formats (JSON lines)."""
+    import json
+    from mcp_b200 import portfolio
+    d, E, S = riskcases.c1_inputs()
+    pf = tmp_path / "portfolios.json"
+    with open(pf, "w") as fh:
+        for p in d["portfolios"]:
+            fh.write(json.dumps({"id": p["id"], "instruments": [{"instrument": i, "weight": w} for i, w in zip(p["instruments"], p["weights"])]}) + "\n")
+    mf = tmp_path / "macro.json"
+    with open(mf, "w") as fh:
+        for k, row in enumerate(d["macro"]):
+            fh.write(json.dumps({"date_offset": k, **{f"m{j}": v for j, v in enumerate(row)}}) + "\n")
+    ids, inst, w, off = portfolio.read_portfolios_json(str(pf))
+    i2, w2, o2 = riskcases.c1_positions(d)
+    assert np.array_equal(inst, i2) and np.array_equal(w, w2) and np.array_equal(off, o2) and len(ids) == 10
+    assert np.array_equal(portfolio.read_macro_json(str(mf)), S)
