@@ -134,6 +134,10 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing,
                      const uint8_t *in, const int64_t *in_off, int64_t nlists,
                      int32_t *out, const int64_t *out_off);
 
+/* diagnostics: encode calls served by the batched single-pass kernels since the context was created, and calls those
+ * kernels handed back to the warp-per-list kernels because a batch did not fit their staging areas */
+int mcp_codec_stats(mcp_ctx *ctx, int64_t *fast_encodes, int64_t *fast_fallbacks);
+
 /* ----------------------------------------------------- batched codec, device
  * Same, but every pointer is a DEVICE pointer on ctx's GPU (for callers whose lists
  * are already in HBM).  total_out is a HOST pointer.  d_out_off is written.

@@ -1258,6 +1258,295 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_decode_fast(const Fa
     for (int i = tid; i < nv; i += FE_THREADS) gout[i] = s_val[sw33(i)];
 }
 
+// ============================================================ batched fast path (FastPFOR / FastPFOR128)
+// Same batch machinery for the codec the north star names: Composition(FastPFOR, VariableByte) on lists of a few
+// hundred to a few thousand ints (one page each; the risk path's breach lists are ~1 000).  Per batch (<= 16 lists,
+// <= 4 096 values staged in shared memory):
+//   * one thread per 32-value group: bit widths into a per-block histogram (FastPFOR.getBestBFromData's freqs);
+//   * one thread per block: the cost search (b, cexcept, maxb);
+//   * one thread per list: running packed-word / metadata-byte offsets of its blocks and the fill of the 32 exception
+//     streams (the serial part: <= 16 blocks);
+//   * one thread per group again: fastpack of its 32 values at the block's width, exception positions into the byte
+//     metadata and exception high bits into their stream with shared-memory atomicOr;
+//   * VariableByte tail (n mod block, up to 255 values): one thread per value, offsets by a warp scan per list;
+//   * single pass over the input; output offsets by the decoupled look-back of k_bp_encode_fast.
+// A batch that does not fit (a list beyond the staging area, incompressible data) raises flag 2 and the host reruns
+// the call through the warp-per-list kernels.
+constexpr int FP_MAXL = 16;   // lists per batch
+constexpr int FP_MAXBLK = 32; // FastPFOR blocks per batch (4 096 / 128)
+
+template <int BG> // 32-value groups per block: 8 (FastPFOR) or 4 (FastPFOR128)
+__global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncArgs a)
+{
+    constexpr int B = BG * 32;
+    __shared__ uint32_t s_val[FE_VPAD];
+    __shared__ uint32_t s_out[FE_OCAP];
+    __shared__ int s_in[FP_MAXL + 1];       // value offset of each list inside the batch
+    __shared__ int s_fb[FP_MAXL + 1];       // first block of each list
+    __shared__ long long s_lo[FP_MAXL + 1]; // word offset of each list's output inside the batch
+    __shared__ int s_hist[FP_MAXBLK][33];   // bit-width histogram of each block
+    __shared__ uint8_t s_bb[FP_MAXBLK], s_bc[FP_MAXBLK], s_bm[FP_MAXBLK], s_bl[FP_MAXBLK]; // b, cexcept, maxb, list of each block
+    __shared__ uint16_t s_bpw[FP_MAXBLK], s_bmo[FP_MAXBLK], s_bsp[FP_MAXBLK]; // packed-word offset, metadata byte offset, stream position
+    __shared__ uint16_t s_cntk[FP_MAXL][33];  // exceptions of each width difference k, per list
+    __shared__ uint16_t s_sbase[FP_MAXL][33]; // word offset of stream k (its count word) behind the bitmap
+    __shared__ int s_pw[FP_MAXL], s_mb[FP_MAXL], s_ew[FP_MAXL]; // packed words, metadata bytes, exception words per list
+    __shared__ int s_tw[FP_MAXL], s_tb[FP_MAXL];                // tail bytes, first tail-table slot per list
+    __shared__ uint8_t s_ge[FE_THREADS];      // exceptions in each group
+    __shared__ uint16_t s_tt[FE_TCAP];        // tail table: (list << 11) | byte length, later | byte offset
+    __shared__ int s_scan[8];
+    __shared__ long long s_base, s_vbase;
+    __shared__ unsigned long long s_batch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_batch = atomicAdd(a.ticket, 1ull);
+    __syncthreads();
+    const int64_t batch = (int64_t)s_batch;
+    const int64_t l0 = batch * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    {
+        const int64_t vb = a.list_off ? a.list_off[l0] : l0 * a.uniform_len;
+        if (tid == 0) s_vbase = vb;
+        for (int j = tid; j <= nl; j += FE_THREADS) {
+            const int64_t o = (a.list_off ? a.list_off[l0 + j] : (l0 + j) * a.uniform_len) - vb;
+            s_in[j] = (int)(o > 0x7fffffff ? 0x7fffffff : o);
+        }
+    }
+    __syncthreads();
+    const int64_t vbase = s_vbase;
+    const int nv = s_in[nl];
+    // blocks and tail slots of every list
+    int nblk = 0, ntv = 0;
+    const int my_n = tid < nl ? s_in[tid + 1] - s_in[tid] : 0;
+    const int my_nb = my_n / B, my_r = my_n - my_nb * B;
+    const int my_fb = cta_excl_scan(my_nb, s_scan, &nblk);
+    const int my_tb = cta_excl_scan(my_r, s_scan, &ntv);
+    if (tid < nl) { s_fb[tid] = my_fb; s_tb[tid] = my_tb; }
+    if (tid == 0) s_fb[nl] = nblk;
+    bool fit = nv <= FE_VCAP && ntv <= FE_TCAP && nl <= FP_MAXL && nblk <= FP_MAXBLK;
+    long long T = 0;
+    if (fit) {
+        for (int i = tid; i < nv; i += FE_THREADS) s_val[sw33(i)] = __ldg(a.vals + vbase + i);
+        for (int i = tid; i < FP_MAXBLK * 33; i += FE_THREADS) (&s_hist[0][0])[i] = 0;
+        if (tid < nl) {
+            for (int q = 0; q < my_nb; ++q) s_bl[my_fb + q] = (uint8_t)tid;
+            for (int i = 0; i < my_r; ++i) s_tt[my_tb + i] = (uint16_t)(tid << 11);
+        }
+        __syncthreads();
+        // ---- group items: thread it <-> block it / BG, group it % BG
+        const int bi = tid / BG, g = tid % BG;
+        const bool have = bi < nblk;
+        uint32_t v[32];
+        int my_start = 0;
+        if (have) {
+            const int j = s_bl[bi], q = bi - s_fb[j];
+            my_start = s_in[j] + q * B + g * 32;
+            uint32_t prev = (a.delta && my_start > s_in[j]) ? s_val[sw33(my_start - 1)] : 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t x = s_val[sw33(my_start + i)];
+                v[i] = a.delta ? x - prev : x;
+                if (a.delta) prev = x;
+                atomicAdd(&s_hist[bi][bits32(v[i])], 1);
+            }
+        }
+        // ---- tails: byte length of every value
+        for (int t = tid; t < ntv; t += FE_THREADS) {
+            const int j = s_tt[t] >> 11, i = t - s_tb[j];
+            const int gidx = s_in[j] + ((s_in[j + 1] - s_in[j]) / B) * B + i;
+            const uint32_t x = s_val[sw33(gidx)];
+            const uint32_t d = (a.delta && gidx > s_in[j]) ? x - s_val[sw33(gidx - 1)] : x;
+            s_tt[t] = (uint16_t)((j << 11) | vb_len(d));
+        }
+        __syncthreads();
+        // ---- one thread per block: getBestBFromData (FastPFOR.java:107-134)
+        if (tid < nblk) {
+            const int *f = s_hist[tid];
+            int maxb = 32;
+            while (maxb > 0 && f[maxb] == 0) --maxb;
+            int bestb = maxb, bestc = 0, bestcost = maxb * B, c = 0;
+            for (int cand = maxb - 1; cand >= 0; --cand) {
+                c += f[cand + 1];
+                if (c == B) break;
+                int cost = c * 8 + c * (maxb - cand) + cand * B + 8;
+                if (maxb - cand == 1) cost -= c;
+                if (cost < bestcost) { bestcost = cost; bestb = cand; bestc = c; }
+            }
+            s_bb[tid] = (uint8_t)bestb; s_bc[tid] = (uint8_t)bestc; s_bm[tid] = (uint8_t)maxb;
+        }
+        // ---- tails: byte offsets, a warp per list (inclusive scans over chunks of 32 values)
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int n = s_in[j + 1] - s_in[j], r = n - (n / B) * B, t0 = s_tb[j];
+            int run = 0;
+            for (int base = 0; base < r; base += 32) {
+                const int i = base + lane;
+                const int len = i < r ? (s_tt[t0 + i] & 2047) : 0;
+                const int incl = (int)warp_incl_scan((uint32_t)len, lane);
+                if (i < r) s_tt[t0 + i] = (uint16_t)((j << 11) | (run + incl - len));
+                run += __shfl_sync(kFull, incl, 31);
+            }
+            if (lane == 0) s_tw[j] = run;
+        }
+        __syncthreads();
+        // ---- one thread per list: offsets of its blocks, fill of its exception streams (encodePage's bookkeeping)
+        int lw = 0;
+        if (tid < nl) {
+            uint16_t cnt[33];
+#pragma unroll
+            for (int k = 0; k < 33; ++k) cnt[k] = 0;
+            int pw = 0, mb = 0;
+            for (int q = 0; q < my_nb; ++q) {
+                const int b_ = my_fb + q, b = s_bb[b_], c = s_bc[b_];
+                s_bpw[b_] = (uint16_t)pw; pw += BG * b;
+                s_bmo[b_] = (uint16_t)mb; mb += 2 + (c ? 1 + c : 0);
+                if (c) { const int k = s_bm[b_] - b; s_bsp[b_] = cnt[k]; cnt[k] += (uint16_t)c; }
+            }
+            int ew = 0;
+            for (int k = 2; k <= 32; ++k) {
+                s_sbase[tid][k] = (uint16_t)ew;
+                s_cntk[tid][k] = cnt[k];
+                if (cnt[k]) ew += 1 + ((cnt[k] * k + 31) >> 5);
+            }
+            s_pw[tid] = pw; s_mb[tid] = mb; s_ew[tid] = ew;
+            const int page = my_nb ? 1 + pw + 1 + ((mb + 3) >> 2) + 1 + ew : 0;
+            lw = (my_n > 0 ? 1 + page + ((s_tw[tid] + 3) >> 2) : 0) + (a.app ? 1 : 0);
+        }
+        int Tw = 0;
+        const int lex = cta_excl_scan(lw, s_scan, &Tw);
+        T = Tw;
+        if (tid < nl) s_lo[tid] = lex;
+        if (tid == 0) s_lo[nl] = Tw;
+        __syncthreads();
+        fit = Tw <= FE_OCAP;
+        if (fit) {
+            if (tid == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+            for (int i = tid; i < Tw; i += FE_THREADS) s_out[i] = 0u;
+            // exceptions of my group, and of the groups before it in the block
+            int my_e = 0;
+            if (have) {
+                const int b = s_bb[bi];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) my_e += (b < 32 && (v[i] >> b) != 0) ? 1 : 0;
+                s_ge[tid] = (uint8_t)my_e;
+            }
+            __syncthreads();
+            if (have) {
+                const int j = s_bl[bi], b = s_bb[bi], c = s_bc[bi], maxb = s_bm[bi];
+                uint32_t *page = s_out + s_lo[j] + 1;
+                // BitPacking.fastpack = masked (FastPFOR.java:175-179)
+                uint32_t *o = page + 1 + s_bpw[bi] + g * b;
+                const uint32_t mask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+                if (b == 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = v[i];
+                } else if (b > 0) {
+                    uint64_t acc = 0;
+                    int fill = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        acc |= (uint64_t)(v[i] & mask) << fill;
+                        fill += b;
+                        if (fill >= 32) { *o++ = (uint32_t)acc; acc >>= 32; fill -= 32; }
+                    }
+                }
+                if (c > 0 && my_e > 0) {
+                    int rank = 0;
+                    for (int gg = 0; gg < g; ++gg) rank += s_ge[bi * BG + gg];
+                    const int k = maxb - b, where_meta = 1 + s_pw[j];
+                    uint8_t *meta = reinterpret_cast<uint8_t *>(page + where_meta + 1) + s_bmo[bi] + 3;
+                    uint32_t *sw = page + where_meta + 1 + ((s_mb[j] + 3) >> 2) + 1 + s_sbase[j][k < 2 ? 2 : k] + 1;
+                    const int spos = s_bsp[bi];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t hi = v[i] >> b; // b <= 31 whenever c > 0
+                        if (hi != 0) {
+                            meta[rank] = (uint8_t)(g * 32 + i); // :166
+                            if (k >= 2) { // stream 1 is implicit (the decoder ORs 1 << b, :291-295)
+                                const int bit = (spos + rank) * k, w = bit >> 5, sh = bit & 31;
+                                atomicOr(sw + w, hi << sh);
+                                if (sh + k > 32) atomicOr(sw + w + 1, hi >> (32 - sh));
+                            }
+                            ++rank;
+                        }
+                    }
+                }
+                if (g == 0) { // block metadata bytes (:159-165)
+                    uint8_t *meta = reinterpret_cast<uint8_t *>(page + 1 + s_pw[j] + 1) + s_bmo[bi];
+                    meta[0] = (uint8_t)b; meta[1] = (uint8_t)c;
+                    if (c > 0) meta[2] = (uint8_t)maxb;
+                }
+            }
+            // ---- one thread per list: header words of the list and of the page
+            if (tid < nl && my_n > 0) {
+                uint32_t *o = s_out + s_lo[tid];
+                o[0] = (uint32_t)(my_nb * B); // Composition: FastPFOR's header, or the 0 marker
+                if (my_nb) {
+                    uint32_t *page = o + 1;
+                    const int where_meta = 1 + s_pw[tid], mw = (s_mb[tid] + 3) >> 2;
+                    page[0] = (uint32_t)where_meta;       // :182
+                    page[where_meta] = (uint32_t)s_mb[tid]; // :186
+                    uint32_t bitmap = 0;
+                    for (int k = 2; k <= 32; ++k)
+                        if (s_cntk[tid][k]) {
+                            bitmap |= 1u << (k - 1);
+                            page[where_meta + 1 + mw + 1 + s_sbase[tid][k]] = s_cntk[tid][k]; // :200
+                        }
+                    page[where_meta + 1 + mw] = bitmap; // :191-196
+                }
+            }
+            // ---- VariableByte tail bytes
+            for (int t = tid; t < ntv; t += FE_THREADS) {
+                const int e = s_tt[t], j = e >> 11, off = e & 2047, i = t - s_tb[j];
+                const int gidx = s_in[j] + ((s_in[j + 1] - s_in[j]) / B) * B + i;
+                const uint32_t x = s_val[sw33(gidx)];
+                uint32_t d = (a.delta && gidx > s_in[j]) ? x - s_val[sw33(gidx - 1)] : x;
+                uint8_t *tbp = reinterpret_cast<uint8_t *>(s_out + (int)s_lo[j + 1] - (a.app ? 1 : 0) - ((s_tw[j] + 3) >> 2)) + off;
+                while (d >= 128u) { *tbp++ = (uint8_t)(d & 127u); d >>= 7; }
+                *tbp = (uint8_t)(d | 128u);
+            }
+        }
+    }
+    if (!fit) { // the warp-per-list kernels will redo the call: keep the look-back chain moving
+        if (tid == 0) {
+            *a.err = 2;
+            st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | 0ull);
+        }
+        T = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        long long base = 0;
+        if (batch > 0) {
+            for (int64_t j = batch - 1;; j -= 32) {
+                const int64_t idx = j - lane;
+                uint64_t st = kLbInc;
+                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
+                const int first = inc ? __ffs(inc) - 1 : 31;
+                long long vv = lane <= first ? (long long)(st & kLbMask) : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) vv += __shfl_xor_sync(kFull, vv, d);
+                base += vv;
+                if (inc) break;
+            }
+            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
+        }
+        if (lane == 0) {
+            s_base = base;
+            if (batch == a.nbatches - 1) {
+                *a.total = 4 * (base + T);
+                a.out_off[a.nlists] = 4 * (base + T);
+            }
+            if (4 * (base + T) > a.cap) atomicMax(a.err, 1);
+        }
+    }
+    __syncthreads();
+    if (!fit) return;
+    const int64_t base = s_base;
+    for (int j = tid; j < nl; j += FE_THREADS) a.out_off[l0 + j] = 4 * (base + s_lo[j]);
+    if (4 * (base + T) > a.cap) return;
+    uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + base;
+    for (int i = tid; i < (int)T; i += FE_THREADS) gout[i] = a.app ? bswap32(s_out[i]) : s_out[i];
+}
+
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
 // block, then a second sweep.  Sizes here are "number of lists": bookkeeping, not hot.
@@ -1354,28 +1643,46 @@ int exclusive_scan_i64(mcp_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_
 // ---- fast-path launchers -------------------------------------------------------------------------------------
 // lists per batch: fill ~92 % of the value staging area on average (a batch that overflows is still handled, by the
 // per-warp routines); 0 = the fast path is not worth it (long lists: the per-warp kernels are the better fit)
-static int fast_lists_per_batch(int64_t total_vals, int64_t nlists)
+static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
 {
     if (nlists <= 0) return 0;
+    const CodecTraits tr = codec_traits(codec);
     const double avg = (double)total_vals / (double)nlists;
-    if (avg > 1024.0) return 0;
+    if (avg > (tr.fastpfor ? 2048.0 : 1024.0)) return 0;
     int64_t g = (int64_t)(0.92 * FE_VCAP / (avg > 1.0 ? avg : 1.0));
+    int64_t gmax = FE_MAXL;
+    if (tr.fastpfor) { // VariableByte tails of up to block-1 values per list share the tail table
+        const double tail = avg < tr.fp_block - 1 ? avg : tr.fp_block - 1;
+        const int64_t gt = (int64_t)(0.85 * FE_TCAP / (tail > 1.0 ? tail : 1.0));
+        if (gt < g) g = gt;
+        gmax = FP_MAXL;
+    }
     if (g < 1) g = 1;
-    if (g > FE_MAXL) g = FE_MAXL;
+    if (g > gmax) g = gmax;
     return (int)g;
 }
 
-bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists)
+// encode: BinaryPacking family and FastPFOR / FastPFOR128; decode: BinaryPacking family
+bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, bool encode)
 {
-    return fast_codec_ok(codec_id & MCP_CODEC_MASK, (codec_id & MCP_FLAG_DELTA) != 0) && fast_lists_per_batch(total_vals, nlists) > 0;
+    const int codec = codec_id & MCP_CODEC_MASK;
+    const bool delta = (codec_id & MCP_FLAG_DELTA) != 0;
+    const bool ok = fast_codec_ok(codec, delta) || (encode && codec_traits(codec).fastpfor);
+    return ok && fast_lists_per_batch(codec, total_vals, nlists) > 0;
 }
 
 // upper bound of the encoded size in bytes for the fast-path codecs: 33 words per 32-int block worst case, a 31-value
-// VariableByte tail of 5 bytes each, count / header / trailing-zero words
-int64_t codec_fast_max_bytes(int64_t total_vals, int64_t nlists) { return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64); }
+// VariableByte tail of 5 bytes each, count / header / trailing-zero words; FastPFOR: at most 32 bits per value plus the
+// byte metadata and page words, and a tail of up to 255 values
+int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists)
+{
+    if (codec_traits(codec_id & MCP_CODEC_MASK).fastpfor) return 4 * (total_vals + total_vals / 8 + 384 * nlists + 64);
+    return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64);
+}
 
 // Single-pass encode of nlists lists; writes d_out_off[0..nlists] (bytes) and the stream.  *total_out = bytes needed;
-// MCP_E_CAP when that exceeds cap (nothing useful is written then).
+// MCP_E_CAP when that exceeds cap (nothing useful is written then); MCP_E_UNSUPPORTED when a batch did not fit the
+// FastPFOR kernel's staging areas (the caller then takes the warp-per-list kernels).
 int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
                       int64_t uniform_len, int64_t nlists, int64_t total_vals, int64_t *d_out_off, uint8_t *d_out, int64_t cap,
                       int64_t *total_out)
@@ -1393,7 +1700,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.list_off = d_list_off;
     a.uniform_len = uniform_len;
     a.nlists = nlists;
-    a.lists_per_batch = fast_lists_per_batch(total_vals, nlists);
+    a.lists_per_batch = fast_lists_per_batch(a.codec, total_vals, nlists);
     a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
     if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
     // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
@@ -1410,13 +1717,19 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.cap = d_out ? cap : 0;
     {
         KScope ks(ctx, MCP_K_ENCODE);
-        k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        MCP_TRY(check_launch(ctx, "k_bp_encode_fast"));
+        const CodecTraits tr = codec_traits(a.codec);
+        if (!tr.fastpfor) k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        else if (tr.fp_block == 256) k_fp_encode_fast<8><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        else k_fp_encode_fast<4><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        MCP_TRY(check_launch(ctx, "k_encode_fast"));
     }
     MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, sp + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);
-    if (*reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8) != 0) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+    const int flag = *reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8);
+    if (flag == 2) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; } // a batch did not fit: not an error, the caller falls back
+    ++ctx->fastEncodeCalls;
+    if (flag != 0) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
     return MCP_OK;
 }
 
@@ -1431,7 +1744,7 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     a.in = d_in;
     a.in_off = d_in_off;
     a.nlists = nlists;
-    a.lists_per_batch = fast_lists_per_batch(total_out_vals, nlists);
+    a.lists_per_batch = fast_lists_per_batch(a.codec, total_out_vals, nlists);
     a.out = reinterpret_cast<uint32_t *>(d_out);
     a.out_off = d_out_off;
     MCP_CUDA(ctx, ctx->dErr.reserve(64));

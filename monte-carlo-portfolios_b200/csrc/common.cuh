@@ -118,6 +118,7 @@ struct mcp_ctx {
     bool valueMma = true;          // mcp_value through the tensor-core kernel when F allows (else scalar fma)
     bool fusedMoments = false;     // true: per-trial moment reduction fused in the valuation kernel (scalar FP64)
     mcp::DevBuf dGram;
+    int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
@@ -206,8 +207,8 @@ int codec_decode_counts(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *
                         int64_t nlists, int64_t *d_counts);
 int codec_decode_device(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off,
                         int64_t nlists, int32_t *d_out, const int64_t *d_out_off);
-bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists);
-int64_t codec_fast_max_bytes(int64_t total_vals, int64_t nlists);
+bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, bool encode);
+int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists);
 int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
                       int64_t uniform_len, int64_t nlists, int64_t total_vals, int64_t *d_out_off, uint8_t *d_out, int64_t cap,
                       int64_t *total_out);

@@ -202,10 +202,12 @@ int mcp_codec_encode_dev(mcp_ctx *ctx, int codec_id, int framing, const int32_t 
     if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
     if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
     int64_t total = 0;
-    if (ctx->fastCodec && codec_fast_applicable(codec_id, total_vals, nlists)) {
+    if (ctx->fastCodec && codec_fast_applicable(codec_id, total_vals, nlists, true)) {
         const int rc = codec_fast_encode(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, total_vals, d_out_off, d_out, cap, &total);
-        if (total_out) *total_out = total;
-        return rc;
+        if (rc != MCP_E_UNSUPPORTED) {
+            if (total_out) *total_out = total;
+            return rc;
+        }
     }
     MCP_TRY(codec_encode_plan(ctx, codec_id, framing, d_vals, d_list_off, 0, nlists, d_out_off, &total));
     if (total_out) *total_out = total;
@@ -220,13 +222,13 @@ int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing, const uint8_t 
     if (nlists < 0 || (nlists > 0 && (!d_in_off || !d_out_off))) return fail(ctx, MCP_E_ARG, "decode_dev: bad argument");
     if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
     if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
-    if (ctx->fastCodec && nlists > 0 && codec_fast_applicable(codec_id, 0, nlists)) {
+    if (ctx->fastCodec && nlists > 0 && codec_fast_applicable(codec_id, 0, nlists, false)) {
         // the batch size follows the average list length: two offsets from the device
         MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, d_out_off, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hPinned) + 8, d_out_off + nlists, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const int64_t tv = reinterpret_cast<int64_t *>(ctx->hPinned)[1] - reinterpret_cast<int64_t *>(ctx->hPinned)[0];
-        if (tv >= 0 && codec_fast_applicable(codec_id, tv, nlists))
+        if (tv >= 0 && codec_fast_applicable(codec_id, tv, nlists, false))
             return codec_fast_decode(ctx, codec_id, framing, d_in, d_in_off, nlists, tv, d_out, d_out_off);
     }
     return codec_decode_device(ctx, codec_id, framing, d_in, d_in_off, nlists, d_out, d_out_off);
@@ -256,22 +258,26 @@ int mcp_codec_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *val
         MCP_TRY(sync(ctx));
     }
     int64_t total = 0;
-    if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, total_vals, nlists)) {
+    bool fast = ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, total_vals, nlists, true);
+    if (fast) {
         // single pass: encode into a worst-case device buffer, then copy back what was produced
-        const int64_t bound = codec_fast_max_bytes(total_vals, nlists);
+        const int64_t bound = codec_fast_max_bytes(codec_id, total_vals, nlists);
         MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)bound + 16));
         const bool sizing = !out || cap <= 0; // size query: nothing is written
         const int rc = codec_fast_encode(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists, total_vals,
                                          ctx->dIo3.as<int64_t>(), sizing ? nullptr : ctx->dIo2.as<uint8_t>(), sizing ? 0 : (cap < bound ? cap : bound), &total);
-        if (out_len) *out_len = total;
-        if (rc != MCP_OK && rc != MCP_E_CAP) return rc;
-        MCP_TRY(d2h(ctx, out_off, ctx->dIo3.p, (size_t)(nlists + 1) * sizeof(int64_t)));
-        if (rc == MCP_E_CAP || (total > 0 && sizing)) {
-            sync(ctx);
-            return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+        if (rc == MCP_E_UNSUPPORTED) fast = false; // a batch did not fit the FastPFOR kernel: warp-per-list kernels below
+        else {
+            if (out_len) *out_len = total;
+            if (rc != MCP_OK && rc != MCP_E_CAP) return rc;
+            MCP_TRY(d2h(ctx, out_off, ctx->dIo3.p, (size_t)(nlists + 1) * sizeof(int64_t)));
+            if (rc == MCP_E_CAP || (total > 0 && sizing)) {
+                sync(ctx);
+                return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+            }
+            MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)total));
+            return sync(ctx);
         }
-        MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)total));
-        return sync(ctx);
     }
     MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dIo0.as<int32_t>(), ctx->dIo1.as<int64_t>(), 0, nlists,
                               ctx->dIo3.as<int64_t>(), &total));
@@ -310,7 +316,7 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *in,
     MCP_TRY(h2d(ctx, ctx->dIo0.p, in, (size_t)in_bytes));
     MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, (size_t)(nlists + 1) * sizeof(int64_t)));
     MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, (size_t)(nlists + 1) * sizeof(int64_t)));
-    if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, out_n, nlists))
+    if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, out_n, nlists, false))
         MCP_TRY(codec_fast_decode(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists, out_n,
                                   ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
     else
@@ -525,6 +531,14 @@ int mcp_run_stats(mcp_ctx *ctx, int64_t *fallback_rows)
     if (!ctx) return MCP_E_ARG;
     if (!ctx->haveRun) return fail(ctx, MCP_E_STATE, "run_stats: no completed run");
     if (fallback_rows) *fallback_rows = ctx->runFallbackRows;
+    return MCP_OK;
+}
+
+int mcp_codec_stats(mcp_ctx *ctx, int64_t *fast_encodes, int64_t *fast_fallbacks)
+{
+    if (!ctx) return MCP_E_ARG;
+    if (fast_encodes) *fast_encodes = ctx->fastEncodeCalls;
+    if (fast_fallbacks) *fast_fallbacks = ctx->fastEncodeFallbacks;
     return MCP_OK;
 }
 

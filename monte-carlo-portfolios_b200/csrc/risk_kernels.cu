@@ -2126,6 +2126,22 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
     return MCP_OK;
 }
 
+// breach lists of uniform length t -> CSR of encoded lists: the single-pass batched kernels when the codec and the list
+// length allow, else size pass + scan + emit pass of the warp-per-list kernels
+static int encode_uniform_lists(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_lists, int64_t t, int64_t rows, mcp::DevBuf &off,
+                                mcp::DevBuf &enc, int64_t *total)
+{
+    if (ctx->fastCodec && codec_fast_applicable(codec_id, rows * t, rows, true)) {
+        const int64_t bound = codec_fast_max_bytes(codec_id, rows * t, rows);
+        MCP_CUDA(ctx, enc.reserve((size_t)bound + 16));
+        const int rc = codec_fast_encode(ctx, codec_id, framing, d_lists, nullptr, t, rows, rows * t, off.as<int64_t>(), enc.as<uint8_t>(), bound, total);
+        if (rc != MCP_E_UNSUPPORTED) return rc;
+    }
+    MCP_TRY(codec_encode_plan(ctx, codec_id, framing, d_lists, nullptr, t, rows, off.as<int64_t>(), total));
+    MCP_CUDA(ctx, enc.reserve((size_t)*total + 16));
+    return codec_encode_emit(ctx, codec_id, framing, d_lists, nullptr, t, rows, off.as<int64_t>(), enc.as<uint8_t>());
+}
+
 // ============================================================ trial-sharded mode (BASELINE config C5)
 // Rank g holds ALL P exposure rows and the scenario rows [trial_base, trial_base + N_local) of an N_global-trial run.
 // Per portfolio the global tail (t largest losses of N_global) is found from the ranks' LOCAL top-m candidates,
@@ -2454,10 +2470,7 @@ int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing)
                                                                                        ctx->dMean.as<double>(), ctx->dVar.as<double>());
             MCP_TRY(check_launch(ctx, "k_ts_moments_merge"));
         }
-        MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dBreach.as<int32_t>() + p0 * t, nullptr, t, rows, ctx->dEncOff.as<int64_t>(), &total));
-        MCP_CUDA(ctx, ctx->dEnc.reserve((size_t)total + 16));
-        MCP_TRY(codec_encode_emit(ctx, codec_id, framing, ctx->dBreach.as<int32_t>() + p0 * t, nullptr, t, rows, ctx->dEncOff.as<int64_t>(),
-                                  ctx->dEnc.as<uint8_t>()));
+        MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>() + p0 * t, t, rows, ctx->dEncOff, ctx->dEnc, &total));
     } else
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dEncOff.p, 0, sizeof(int64_t), ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2556,10 +2569,7 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));
     int64_t total = 0;
-    MCP_TRY(codec_encode_plan(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), nullptr, t, P, ctx->dEncOff.as<int64_t>(), &total));
-    MCP_CUDA(ctx, ctx->dEnc.reserve((size_t)total + 16));
-    MCP_TRY(codec_encode_emit(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), nullptr, t, P, ctx->dEncOff.as<int64_t>(),
-                              ctx->dEnc.as<uint8_t>()));
+    MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), t, P, ctx->dEncOff, ctx->dEnc, &total));
     ctx->runP = P;
     ctx->runRow0 = 0;
     ctx->runN = N;

@@ -107,6 +107,11 @@ class Context:
         self._check(rc, "codec_decode")
         return out[: int(oo[-1])]
 
+    def codec_stats(self) -> dict:
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.mcp_codec_stats(self._h, C.byref(a), C.byref(b)), "codec_stats")
+        return {"fast_encodes": a.value, "fast_fallbacks": b.value}
+
     # -- single-list drop-ins
     def compress_ints(self, codec_id: int, vals, out_cap: int | None = None) -> np.ndarray:
         v = as_i32(vals)

@@ -8,7 +8,7 @@ ctx = mcp_b200.Context(0)
 nl = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 ntr = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
 dv, do, total = ctx.generate_breach_lists(nl, ntr, 0.01, 0x5EED0004)
-cid = N.CODEC_BP32_VB | N.FLAG_DELTA
+cid = (N.CODEC_FASTPFOR256_VB if len(sys.argv) > 3 and sys.argv[3] == "fp" else N.CODEC_BP32_VB) | N.FLAG_DELTA
 capb = 4 * total + 16 * nl
 d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
 for fast in (1, 0, 1):

@@ -158,6 +158,33 @@ def test_fast_path_batch_edges(ctx, cid, framing):
         assert e.value.code == N.MCP_E_FORMAT
 
 
+def test_fast_kernels_are_the_ones_that_run(ctx):
+    """The batched single-pass kernels must actually serve the shapes they were built for (C4's ~100-int lists under
+    the loader's codec, ~1 000-int breach lists under FastPFOR) instead of silently handing them back."""
+    rng = np.random.default_rng(2)
+    for cid, (nl, ntr) in ((N.CODEC_BP32_VB | N.FLAG_DELTA, (2000, 10000)), (N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, (400, 100000)),
+                           (N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, (400, 100000)), (N.CODEC_FASTPFOR256_VB, (2000, 10000))):
+        vals, off = cases.breach_like_lists(rng, nl, ntr, 0.01)
+        before = ctx.codec_stats()
+        out_off, out = ctx.codec_encode(cid, N.FRAME_APP, vals, off, cap=int(8 * vals.size + 64 * nl))
+        after = ctx.codec_stats()
+        assert after["fast_encodes"] == before["fast_encodes"] + 1 and after["fast_fallbacks"] == before["fast_fallbacks"], cid
+        for i in (0, nl // 2, nl - 1):
+            assert bytes(out[out_off[i]: out_off[i + 1]]) == cref.get_compressed_instruments(cid, vals[off[i]: off[i + 1]]), (cid, i)
+    # a list far beyond the staging area among short ones: handed back, still right
+    lists = [np.cumsum(rng.geometric(0.01, 900)) for _ in range(40)]
+    lists[7] = np.cumsum(rng.geometric(0.01, 30000))
+    vals = np.concatenate(lists).astype(np.int32)
+    off = np.zeros(41, np.int64)
+    np.cumsum([len(x) for x in lists], out=off[1:])
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    before = ctx.codec_stats()
+    out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off, cap=int(8 * vals.size))
+    assert ctx.codec_stats()["fast_fallbacks"] == before["fast_fallbacks"] + 1
+    for i in (0, 7, 39):
+        assert bytes(out[out_off[i]: out_off[i + 1]]) == cref.compress(cid, lists[i]).tobytes(), i
+
+
 def test_multipage_fastpfor(ctx):
     """> 65 536 ints: FastPFOR pages (FastPFOR.java:98-102), including the stale exception-buffer padding that a
     Java instance carries from page to page (FastPFOR.java:143): bytes identical to the oracle's emulation."""
