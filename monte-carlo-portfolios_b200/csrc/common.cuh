@@ -119,6 +119,7 @@ struct mcp_ctx {
     bool fusedMoments = false;     // true: per-trial moment reduction fused in the valuation kernel (scalar FP64)
     mcp::DevBuf dGram;
     int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
+    bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
@@ -225,6 +226,7 @@ int gen_matrix(mcp_ctx *ctx, double *d_out, int64_t rows, int32_t cols, uint64_t
 int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate, uint64_t seed, int64_t first_list,
                      int64_t *total);
 int64_t risk_first_step_len(int64_t N, int64_t t);
+void risk_set_dense_floor(int64_t v);
 int build_exposures(mcp_ctx *ctx, const int32_t *d_inst, const double *d_w, const int64_t *d_off, int64_t P, const double *d_B,
                     int64_t n_inst, int32_t F, double *d_E);
 int fp64_peak(mcp_ctx *ctx, double *tflops);

@@ -824,8 +824,8 @@ typedef unsigned __int128 u128;
 __device__ __forceinline__ u128 comp_of(uint64_t key, uint32_t idx) { return ((u128)key << 32) | idx; }
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_BITS = 11;
-constexpr int SEL_BINS = 1 << SEL_BITS; // 11-bit digits over the 96-bit composite (key64, trial32), MSB first
+constexpr int SEL_BITS_MAX = 11;
+constexpr int SEL_BINS_MAX = 1 << SEL_BITS_MAX; // widest digit of the general path (k_select_t<256>)
 constexpr int SEL_SORT = 256;           // keep refining digits until the boundary bucket is at most this big
 constexpr int FS_BITS = 10, FS_BINS = 1 << FS_BITS; // staged fast path: bins per range-adaptive pass
 constexpr int FS_SORT = 96;                        // ... and the bucket size its rank sort takes
@@ -894,11 +894,11 @@ __device__ __forceinline__ void kept_at(const SelArgs &a, int64_t row, int64_t i
 }
 
 // visit every candidate of the row straight from global memory
-template <class Fn>
+template <int THREADS, class Fn>
 __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, const int *segoff, Fn f)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int64_t i = tid; i < a.kept_n; i += SEL_THREADS) {
+    for (int64_t i = tid; i < a.kept_n; i += THREADS) {
         uint64_t k; uint32_t id;
         kept_at(a, row, i, k, id);
         f(k, id);
@@ -909,7 +909,7 @@ __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, c
         // (segoff = exclusive prefix of the segment counts, in shared memory): independent loads in flight.
         const int4 *R = reinterpret_cast<const int4 *>(rowp);
         const int total = segoff[a.nsub];
-        for (int i = tid; i < total; i += SEL_THREADS) {
+        for (int i = tid; i < total; i += THREADS) {
             int lo = 0, hi = a.nsub; // largest seg with segoff[seg] <= i
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -922,7 +922,7 @@ __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, c
         return;
     }
     const double *V = reinterpret_cast<const double *>(rowp);
-    for (int seg = warp; seg < a.nsub; seg += SEL_THREADS / 32) {
+    for (int seg = warp; seg < a.nsub; seg += THREADS / 32) {
         const int64_t base = (int64_t)seg * a.sub_len;
         int64_t c = a.step_len - base;
         c = c < 0 ? 0 : (c > a.sub_len ? a.sub_len : c);
@@ -935,8 +935,14 @@ __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, c
 // (the normal case: a few tail sizes), so the digit passes never go back to HBM; rows with
 // more candidates than `cap` (adversarial trial orders, very large tails) run the same
 // passes straight from global memory.
-__global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
+// THREADS = 256 for tails of a thousand trials, 64 for small tails (t ~ 100: a 256-thread CTA per row would spend its
+// time in barriers); the digit widths follow so that the histogram scans stay one pass per thread.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_select_t(const SelArgs a)
 {
+    constexpr int SEL_BITS = THREADS >= 256 ? 11 : 8, SEL_BINS = 1 << SEL_BITS; // general path: digits of the 96-bit composite
+    constexpr int FS_BITS = THREADS >= 256 ? 10 : 8, FS_BINS = 1 << FS_BITS;    // staged path: bins per range-adaptive pass
+    constexpr int FS_SORT = THREADS >= 256 ? 96 : 64;                           // ... and its rank-sorted bucket (one thread per element)
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint64_t *skey = reinterpret_cast<uint64_t *>(sel_smem);
     uint32_t *sidx = reinterpret_cast<uint32_t *>(skey + a.cap);
@@ -945,7 +951,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     __shared__ uint64_t ckey[SEL_SORT];
     __shared__ uint32_t cidx[SEL_SORT];
     __shared__ double red[32];
-    __shared__ int s_wsum[SEL_THREADS / 32];
+    __shared__ int s_wsum[THREADS / 32];
     __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept;
     const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
@@ -958,7 +964,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
         const double c = V[0];
         double s1 = 0.0, s2 = 0.0;
-        for (int64_t i = tid; i < a.step_len; i += SEL_THREADS) {
+        for (int64_t i = tid; i < a.step_len; i += THREADS) {
             const double d = V[i] - c;
             s1 += d;
             s2 = fma(d, d, s2);
@@ -977,10 +983,10 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     int64_t M;
     if (a.cnt) {
         // exclusive prefix of the segment counts: coalesced load, every thread scans a contiguous run, block scan
-        for (int sgi = tid; sgi < a.nsub; sgi += SEL_THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
+        for (int sgi = tid; sgi < a.nsub; sgi += THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
         if (tid == 0) segoff[0] = 0;
         __syncthreads();
-        const int per = (a.nsub + SEL_THREADS - 1) / SEL_THREADS;
+        const int per = (a.nsub + THREADS - 1) / THREADS;
         const int g0 = min(a.nsub, tid * per), g1 = min(a.nsub, g0 + per);
         int c = 0;
         for (int g = g0; g < g1; ++g) c += segoff[g + 1];
@@ -1015,14 +1021,14 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         // ===== fast path: stage the row's candidates ONCE in shared memory (deterministic slots, independent
         // loads), tracking the key range on the way.
         __shared__ uint64_t s_lo, s_hi;
-        __shared__ uint64_t s_red[2 * (SEL_THREADS / 32)];
+        __shared__ uint64_t s_red[2 * (THREADS / 32)];
         uint64_t mn = ~0ull, mx = 0;
         auto put = [&](int slot, uint64_t k, uint32_t id) {
             skey[slot] = k; sidx[slot] = id;
             mn = k < mn ? k : mn; mx = k > mx ? k : mx;
         };
         const int kn = (int)a.kept_n;
-        for (int i = tid; i < kn; i += SEL_THREADS) {
+        for (int i = tid; i < kn; i += THREADS) {
             uint64_t k; uint32_t id;
             kept_at(a, row, i, k, id);
             put(i, k, id);
@@ -1032,7 +1038,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             // sparse step: ~3 records in each of several hundred lane-private segments.  Phase 1: every thread labels
             // the slots of its own segments with the segment id (shared memory only); phase 2: a flat, unrolled loop
             // over the slots issues the 16-byte record loads independently of one another.
-            const int per = (a.nsub + SEL_THREADS - 1) / SEL_THREADS;
+            const int per = (a.nsub + THREADS - 1) / THREADS;
             const int g0 = min(a.nsub, tid * per), g1 = min(a.nsub, g0 + per);
             for (int g = g0; g < g1; ++g)
                 for (int j = segoff[g]; j < segoff[g + 1]; ++j) sidx[kn + j] = (uint32_t)g;
@@ -1040,7 +1046,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             const int4 *R = reinterpret_cast<const int4 *>(rowp);
             const int total = segoff[a.nsub];
 #pragma unroll 4
-            for (int i = tid; i < total; i += SEL_THREADS) {
+            for (int i = tid; i < total; i += THREADS) {
                 const int g = (int)sidx[kn + i];
                 const int4 rec = __ldg(R + (int64_t)g * a.sub_len + (i - segoff[g]));
                 put(kn + i, fkey(0.0 - __hiloint2double(rec.y, rec.x)), (uint32_t)rec.z);
@@ -1049,17 +1055,17 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
             const double *V = reinterpret_cast<const double *>(rowp);
             const int total = (int)a.step_len; // dense rows are contiguous: slot = trial - n_begin
 #pragma unroll 4
-            for (int i = tid; i < total; i += SEL_THREADS) put(kn + i, fkey(0.0 - __ldg(V + i)), (uint32_t)(a.n_begin + i));
+            for (int i = tid; i < total; i += THREADS) put(kn + i, fkey(0.0 - __ldg(V + i)), (uint32_t)(a.n_begin + i));
         }
         for (int d = 16; d; d >>= 1) {
             const uint64_t a1 = __shfl_xor_sync(kFullMask, mn, d), b1 = __shfl_xor_sync(kFullMask, mx, d);
             mn = a1 < mn ? a1 : mn; mx = b1 > mx ? b1 : mx;
         }
-        if (lane == 0) { s_red[warp] = mn; s_red[SEL_THREADS / 32 + warp] = mx; }
+        if (lane == 0) { s_red[warp] = mn; s_red[THREADS / 32 + warp] = mx; }
         __syncthreads();
         if (tid == 0) {
             uint64_t lo = ~0ull, hi = 0;
-            for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = s_red[w] < lo ? s_red[w] : lo; hi = s_red[SEL_THREADS / 32 + w] > hi ? s_red[SEL_THREADS / 32 + w] : hi; }
+            for (int w = 0; w < THREADS / 32; ++w) { lo = s_red[w] < lo ? s_red[w] : lo; hi = s_red[THREADS / 32 + w] > hi ? s_red[THREADS / 32 + w] : hi; }
             s_lo = lo; s_hi = hi;
         }
         __syncthreads();
@@ -1075,16 +1081,16 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         for (int pass = 0; pass < 16; ++pass) {
             const uint64_t width = hi - lo;
             const int shift = width < (uint64_t)FS_BINS ? 0 : (64 - __clzll((long long)width)) - FS_BITS;
-            for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
+            for (int b = tid; b < FS_BINS; b += THREADS) hist[b] = 0;
             __syncthreads();
-            for (int i = tid; i < Ms; i += SEL_THREADS) {
+            for (int i = tid; i < Ms; i += THREADS) {
                 const uint64_t k = skey[i];
                 if (on_idx) { if (k == kstar) { const uint64_t v = sidx[i]; if (v >= lo && v <= hi) atomicAdd(&hist[(int)((v - lo) >> shift)], 1); } }
                 else if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
             }
             __syncthreads();
             {
-                constexpr int PER = FS_BINS / SEL_THREADS;
+                constexpr int PER = FS_BINS / THREADS;
                 const int hb = FS_BINS - 1 - tid * PER; // thread 0 owns the highest bins
                 int sum = 0;
 #pragma unroll
@@ -1127,7 +1133,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         }
         // --- gather: above the boundary bin -> kept; inside it -> the small bucket.  Warp-aggregated slot claims
         // (one shared-memory atomic per warp and round, not one per element)
-        for (int base = 0; base < Ms; base += SEL_THREADS) {
+        for (int base = 0; base < Ms; base += THREADS) {
             const int i = base + tid;
             int rel = -1; // +1 above, 0 inside, -1 below / out of range
             uint64_t k = 0;
@@ -1179,7 +1185,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         return;
     }
     // ===== general path: more candidates than shared memory holds; digit passes straight from global memory
-    auto for_each = [&](auto f) { for_each_global(a, row, segoff, f); };
+    auto for_each = [&](auto f) { for_each_global<THREADS>(a, row, segoff, f); };
 
     // Radix select on the 64-bit loss key first (cheap 64-bit digit extraction); the trial index only breaks ties,
     // so its digits are visited only if more than SEL_SORT candidates share one exact loss value.
@@ -1200,7 +1206,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         const int width = rem >= SEL_BITS ? SEL_BITS : rem;
         const int sh = rem - width;
         const uint32_t dmask = (1u << width) - 1u;
-        for (int b = tid; b < SEL_BINS; b += SEL_THREADS) hist[b] = 0;
+        for (int b = tid; b < SEL_BINS; b += THREADS) hist[b] = 0;
         __syncthreads();
         for_each([&](uint64_t key, uint32_t id) {
             if (in_prefix(key, id)) atomicAdd(&hist[on_key ? (uint32_t)(key >> sh) & dmask : (id >> sh) & dmask], 1);
@@ -1208,7 +1214,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         __syncthreads();
         // find the digit where the count from the top reaches `need`: thread 0 owns the highest bins
         {
-            constexpr int PER = SEL_BINS / SEL_THREADS;
+            constexpr int PER = SEL_BINS / THREADS;
             const int hi = SEL_BINS - 1 - tid * PER;
             int sum = 0;
 #pragma unroll
@@ -1267,11 +1273,11 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
     // ---- bitonic sort of the boundary bucket, descending composite; pads (0,0) sink to the end
     int m = 1;
     while (m < bucket) m <<= 1;
-    for (int i = bucket + tid; i < m; i += SEL_THREADS) { ckey[i] = 0; cidx[i] = 0; }
+    for (int i = bucket + tid; i < m; i += THREADS) { ckey[i] = 0; cidx[i] = 0; }
     __syncthreads();
     for (int k = 2; k <= m; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < m; i += SEL_THREADS) {
+            for (int i = tid; i < m; i += THREADS) {
                 const int p = i ^ j;
                 if (p > i) {
                     const u128 ci = comp_of(ckey[i], cidx[i]), cp = comp_of(ckey[p], cidx[p]);
@@ -1286,7 +1292,7 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(const SelArgs a)
         }
     }
     const int base = s_nkept; // == t - need
-    for (int i = tid; i < (int)need; i += SEL_THREADS) {
+    for (int i = tid; i < (int)need; i += THREADS) {
         kk[base + i] = ckey[i];
         ki[base + i] = (int32_t)cidx[i];
     }
@@ -1519,7 +1525,18 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     }
 }
 
-static size_t sel_smem_bytes(int cap, int nseg) { return (size_t)cap * 12 + (size_t)SEL_BINS * 4 + (size_t)(nseg + 2) * 4; }
+static size_t sel_smem_bytes(int cap, int nseg, int threads = SEL_THREADS)
+{
+    return (size_t)cap * 12 + (size_t)(threads >= 256 ? SEL_BINS_MAX : 256) * 4 + (size_t)(nseg + 2) * 4;
+}
+
+// opt-in to the large dynamic shared memory of both instantiations
+static cudaError_t sel_configure(int bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_select_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_select_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 // ============================================================ finalize
 // Kernel (3): the kept tail -> ascending breach-trial list, and CVaR = mean tail loss.
@@ -1531,7 +1548,8 @@ constexpr int FIN_THREADS = 256;
 static size_t fin_bitmap_smem(int64_t n_trials, int64_t t) { return (size_t)((n_trials + 31) / 32) * 8 + (size_t)t * 8; }
 constexpr size_t FIN_BITMAP_MAX_SMEM = 200 * 1024;
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
+template <int FIN_THREADS>
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap_t(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
                                                                  int64_t n_trials, int32_t trial_base, int32_t *breach,
                                                                  double *cvar)
 {
@@ -1634,14 +1652,12 @@ struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
 
 // length of the dense first step: ~4 tail sizes, at least kDenseFloor trials, a multiple of 8 (tensor-core trial blocks)
-#ifndef MCP_DENSE_FLOOR
-#define MCP_DENSE_FLOOR 2048
-#endif
-constexpr int64_t kDenseFloor = MCP_DENSE_FLOOR;
+static int64_t g_dense_floor = 2048; // process-wide tuning knob (mcp_set_option "dense_floor")
+void risk_set_dense_floor(int64_t v) { g_dense_floor = v < 64 ? 64 : v; }
 static int64_t first_step_len(int64_t N, int64_t t)
 {
     int64_t c0 = 4 * t;
-    if (c0 < kDenseFloor) c0 = kDenseFloor;
+    if (c0 < g_dense_floor) c0 = g_dense_floor;
     c0 = (c0 + 7) & ~(int64_t)7;
     return c0 < N ? c0 : N;
 }
@@ -1686,10 +1702,14 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
     if (n_trials < 0) n_trials = ctx->N;
     if (fin_bitmap_smem(n_trials, t) <= FIN_BITMAP_MAX_SMEM && !ctx->forceSortFinalize) {
         const size_t bm_smem = fin_bitmap_smem(n_trials, t);
-        if (bm_smem > 40 * 1024)
-            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        const bool small = ctx->smallSelect && t <= 256; // small tails: 64-thread CTAs, more rows resident per SM
+        if (bm_smem > 40 * 1024) {
+            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        }
         KScope ks(ctx, MCP_K_SELECT);
-        k_finalize_bitmap<<<(unsigned)rows, FIN_THREADS, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
+        if (small) k_finalize_bitmap_t<64><<<(unsigned)rows, 64, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
+        else k_finalize_bitmap_t<256><<<(unsigned)rows, 256, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         return check_launch(ctx, "k_finalize_bitmap");
     }
     int m = 1;
@@ -1743,7 +1763,7 @@ static int risk_run_dense(mcp_ctx *ctx, int64_t t)
         {
             KScope ks(ctx, MCP_K_SELECT);
             a.cap = ctx->selCap;
-            k_select<<<(unsigned)(p1 - p0), SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
+            k_select_t<256><<<(unsigned)(p1 - p0), 256, sel_smem_bytes(a.cap, a.nsub), ctx->stream>>>(a);
             MCP_TRY(check_launch(ctx, "k_select"));
         }
         MCP_TRY(run_finalize(ctx, p1 - p0, t, a.kept_key_out, a.kept_idx_out, ctx->dBreach.as<int32_t>() + p0 * t,
@@ -2037,8 +2057,13 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
                 if (reg && a.step_len <= 8 * SEL_THREADS) k_select_dense<8><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
                 else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
-                else
-                k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
+                else if (!dense && ctx->smallSelect && a.kept_n + 4 * t + 64 <= 1024) {
+                    // small tails (t ~ 100): a 64-thread CTA per row, a staging area to match (rows beyond it take the
+                    // global-memory path): a dozen rows resident per SM instead of four
+                    a.cap = 1024;
+                    k_select_t<64><<<(unsigned)rows, 64, sel_smem_bytes(a.cap, a.nsub, 64), cur_stream(ctx)>>>(a);
+                } else
+                    k_select_t<256><<<(unsigned)rows, 256, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
             kept = a.tail;
@@ -2280,7 +2305,7 @@ static int ts_local_block(mcp_ctx *ctx, const double *E, int64_t rows, int64_t m
         if (cap < 2304) cap = 2304;
         if (cap > 16384) cap = 16384;
         ctx->selCap = (int)cap;
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(16384, kSelMaxSeg)));
+        MCP_CUDA(ctx, sel_configure((int)sel_smem_bytes(16384, kSelMaxSeg)));
     }
     StreamIO io{};
     io.E = E; io.P = rows;
@@ -2357,9 +2382,9 @@ static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, con
     if (cap < 2304) cap = 2304;
     if (cap > 16384) cap = 16384;
     a.cap = (int)cap;
-    MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(16384, kSelMaxSeg)));
+    MCP_CUDA(ctx, sel_configure((int)sel_smem_bytes(16384, kSelMaxSeg)));
     KScope ks(ctx, MCP_K_SELECT);
-    k_select<<<(unsigned)rows, SEL_THREADS, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a);
+    k_select_t<256><<<(unsigned)rows, 256, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a);
     return check_launch(ctx, "k_select (merge)");
 }
 
@@ -2543,7 +2568,7 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
         if (cap < 2304) cap = 2304;
         if (cap > 16384) cap = 16384; // 200 KB; larger rows select straight from global memory
         ctx->selCap = (int)cap;
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem_bytes(ctx->selCap, kSelMaxSeg)));
+        MCP_CUDA(ctx, sel_configure((int)sel_smem_bytes(ctx->selCap, kSelMaxSeg)));
     }
 
     const bool stream_path = mma_supported(ctx->F) && !ctx->forceDense;

@@ -95,12 +95,12 @@ def test_tile_overlap_on_two_streams_gives_identical_results(ctx):
         assert np.array_equal(r1[k], r4[k]) and np.array_equal(r1[k], r4g[k]), k
 
 
-@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic"])
+@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic", "small_select"])
 def test_alternate_kernel_paths_agree(ctx, opt):
     """F = 32 normally takes the streaming kernels (two-step optimistic schedule, dense-step selection from
     registers) + bitmap compaction; the dense tile + single selection, the sort-based breach list, the fused
     per-trial moments, the shared-memory selection and the guaranteed schedule must give identical results."""
-    default = 1 if opt in ("reg_select", "optimistic") else 0
+    default = 1 if opt in ("reg_select", "optimistic", "small_select") else 0
     ctx.set_option(opt, 1 - default)
     try:
         E, S = riskcases.synthetic(40, 9000, 32, 21)
@@ -108,6 +108,10 @@ def test_alternate_kernel_paths_agree(ctx, opt):
         E, S = riskcases.with_ties(8, 5000, 32, 22)
         check_against_oracle(ctx, E, S, 0.9)
         E, S = riskcases.synthetic(20, 60000, 32, 23)
+        check_against_oracle(ctx, E, S, 0.995)
+        E, S = riskcases.synthetic(300, 10000, 64, 24)           # C3 shape: tail of 101 -> the 64-thread selection kernels
+        check_against_oracle(ctx, E, S, 0.99, rows=list(range(0, 300, 13)))
+        E, S = riskcases.with_ties(6, 12000, 32, 25)             # ... with thousands of tied losses
         check_against_oracle(ctx, E, S, 0.995)
     finally:
         ctx.set_option(opt, default)
