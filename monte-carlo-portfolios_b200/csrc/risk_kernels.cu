@@ -1342,8 +1342,12 @@ __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need,
     __syncthreads();
 }
 
+#ifndef SD_MINB16
+#define SD_MINB16 3
+#define SD_MINB8 4
+#endif
 template <int ITEMS>
-__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense(const SelArgs a)
+__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? SD_MINB16 : SD_MINB8) k_select_dense(const SelArgs a)
 {
     __shared__ int hist[FS_BINS];
     __shared__ uint64_t ckey[FS_SORT];
@@ -1358,6 +1362,7 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
+    for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0; // (visible after the barrier of the range reduction)
     // ---- load: slot i = tid + 256 j holds the loss of trial n_begin + i (slots past n repeat the thread's first
     // loss: harmless for min / max, masked everywhere else)
     double x[ITEMS];
@@ -1400,8 +1405,6 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     };
     int sel = 0;
     if (byval) {
-        for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
-        __syncthreads();
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j)
             if (tid + SEL_THREADS * j < n) atomicAdd(&hist[bin_of(x[j])], 1);
