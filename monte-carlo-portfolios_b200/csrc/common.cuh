@@ -80,7 +80,6 @@ struct mcp_ctx {
     // scratch
     mcp::DevBuf dLoss;             // dense loss tile
     mcp::DevBuf dPart;             // moment partials
-    mcp::DevBuf dShift;            // per-portfolio shift c_p
     mcp::DevBuf dSizes, dScanTmp;  // codec size/scan scratch
     mcp::DevBuf dIo0, dIo1, dIo2, dIo3; // host-API staging (vals, offsets, out, out offsets)
     mcp::DevBuf dErr;              // int flags (error, multi-page count, shadow ticket)
@@ -88,7 +87,7 @@ struct mcp_ctx {
     int planMultiPage = 0;
     mcp::DevBuf dFlush;            // L2 flush buffer
     mcp::DevBuf dGenVals, dGenOff; // synthetic breach lists
-    mcp::DevBuf dCandKey, dCandIdx, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
+    mcp::DevBuf dCandKey, dCandCnt, dTau, dKeptKey, dKeptIdx; // streaming tail filter
     mcp::DevBuf dKept2Key, dKept2Idx, dFinKey, dFinIdx;
     mcp::DevBuf dFail;             // [0] = number of rows that failed the optimistic bound, [4..] = their indices
     mcp::DevBuf dFbE, dFbOut, dFbKey, dFbIdx; // fallback problem (failed rows, guaranteed schedule)

@@ -122,9 +122,9 @@ void mcp_destroy(mcp_ctx *ctx)
     nccl_comm_destroy(ctx);
     for (auto e : ctx->prof.pool) cudaEventDestroy(e);
     mcp::DevBuf *bufs[] = {&ctx->dE, &ctx->dS, &ctx->dMean, &ctx->dVar, &ctx->dVarLoss, &ctx->dVarTrial, &ctx->dCvar,
-                           &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dShift, &ctx->dSizes,
+                           &ctx->dBreach, &ctx->dEncOff, &ctx->dEnc, &ctx->dLoss, &ctx->dPart, &ctx->dSizes,
                            &ctx->dScanTmp, &ctx->dIo0, &ctx->dIo1, &ctx->dIo2, &ctx->dIo3, &ctx->dErr, &ctx->dFlush,
-                           &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandIdx, &ctx->dCandCnt, &ctx->dTau,
+                           &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
                            &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
                            &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dCandKey2, &ctx->dCandCnt2, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};

@@ -338,15 +338,16 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 // shared-memory operand fetch per 256 fma instead of one per 64: the scalar DFMA version of this kernel
 // (git history) was shared-memory-bandwidth bound at 48 % of the FP64 peak.  (tcgen05 has no FP64 kind.)
 //
-// "E-stationary": a warp keeps the A fragments of 4 portfolio groups (32 portfolios x all F factors) in
-// registers and streams trials past them; a CTA = 8 warps = 256 portfolios.  The scenario rows of the
-// CTA's trial sub-chunk are staged into shared memory by one elected thread with cp.async.bulk (TMA bulk
-// copy, SASS UBLKCP) completing on mbarriers, 4 stages x 32 trials, rows padded by 32 B so that the B-fragment
-// loads are bank-conflict free.  Fused on each value while it is still in a register:
-//   * moments: d = V - c_p (c_p = V[p][trial 0]), s1 += d, s2 = fma(d,d,s2)
-//   * tail filter: DENSE steps store every V; SPARSE steps append (V, trial) only when
-//     fkey(V) <= tkey_p, i.e. loss >= the current lower bound of the portfolio's VaR: a 64-bit integer
-//     compare on the order-preserving image, and predicated stores -- no divergence, no FP64-pipe slots.
+// "E-stationary": a warp keeps the A fragments of VM_G = 2 portfolio groups (16 portfolios x all F factors) in
+// registers and streams trials past them; a CTA = 16 warps = 256 portfolios x one trial sub-chunk.  The scenario rows of
+// the sub-chunk arrive in B-FRAGMENT ORDER (k_repack_scenarios), so a stage of 32 trials is ONE contiguous block: a
+// single cp.async.bulk (TMA bulk copy, SASS UBLKCP) by one elected thread, completing on mbarriers, 4 stages deep, and
+// every B-fragment load reads 32 consecutive doubles -- bank-conflict free without padding.  Fused on each value while
+// it is still in a register:
+//   * moments (MOMENTS variant only): d = V - c_p (c_p = V[p][trial 0]), s1 += d, s2 = fma(d,d,s2)
+//   * tail filter: DENSE steps store every V; SPARSE steps append (V, trial) only when V is at or beyond the
+//     portfolio's current bound: an integer compare on the raw bit pattern (its high word, when every bound of the
+//     warp is negative) and predicated stores -- no divergence, no FP64-pipe slots.
 // Each lane appends to its own private segment (portfolio, sub-chunk, lane%4): no atomics.
 constexpr int VM_WARPS = 16;
 constexpr int VM_THREADS = VM_WARPS * 32;
@@ -399,15 +400,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-
-// named barriers between the two warps that share an SM sub-partition (ids 1..8; 0 is __syncthreads)
-#ifndef MCP_EXP_NO_PINGPONG
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-#else
-__device__ __forceinline__ void pair_sync(int) {}
-__device__ __forceinline__ void pair_arrive(int) {}
-#endif
 
 // D(8x8) += A(8x4) * B(4x8), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -556,11 +548,11 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     const bool vec_ok = (a.sub_len & 1) == 0 && (a.pitch & 15) == 0;
     constexpr bool moments = MOMENTS; // compile-time: even predicated-off scalar FP64 instructions cost DMMA-pipe slots
     // Scheduling.  The FP64 tensor pipe is the bound resource and scalar FP64 ops (the moments) share it, while
-    // integer work from the partner warp co-issues with DMMA (profiles/microbench/dmma_coissue.cu).  So:
-    //  * warps w and w+4 (same SM sub-partition) ping-pong through two named barriers: one owns the pipe
-    //    (DMMAs + the moment updates), the other runs its integer epilogue (filter, address math, stores);
-    //  * the epilogue is software-pipelined by one block: the moments of block i-1 are interleaved between the
-    //    k-steps of block i's DMMAs (no dependency bubble), its filter runs after the hand-off.
+    // integer work co-issues with DMMA (profiles/microbench/dmma_coissue.cu).  Four warps per SM sub-partition give
+    // the scheduler another warp's integer epilogue to run while one warp's DMMAs occupy the pipe (an explicit
+    // two-warp ping-pong through named barriers was measured slower: the barrier round trips idled the pipe).  The
+    // epilogue is software-pipelined by one block: the moments of block i-1 are interleaved between the k-steps of
+    // block i's DMMAs (no dependency bubble), its filter runs after them.
     double pd0[VM_G], pd1[VM_G]; // previous block's values; initialised to the shift so that they add exactly 0
 #pragma unroll
     for (int g = 0; g < VM_G; ++g) { pd0[g] = cs[g]; pd1[g] = cs[g]; }
@@ -583,7 +575,6 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                     }
                 }
             } else {
-#ifndef MCP_EXP_NO_FILTER
                 uint32_t h0, h1;
                 if (fastcmp) {
                     // high words only: one 32-bit compare per value.  A superset of the exact test (values whose high
@@ -599,18 +590,15 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                 cnt[g] += h0;
                 append_if(h1, srec[g] + cnt[g], pd1[g], n0 + 1);
                 cnt[g] += h1;
-#endif
             }
         }
     };
     // FP64 half for value v (0..7) of the block held in pd0/pd1
     auto moment_of = [&](int v) {
-#ifndef MCP_EXP_NO_MOMENTS
         const int g = v >> 1;
         const double d = ((v & 1) ? pd1[g] : pd0[g]) - cs[g];
         s1[g] += d;
         s2[g] = fma(d, d, s2[g]);
-#endif
     };
 
     for (int it = 0; it < nst; ++it) {
@@ -1342,12 +1330,8 @@ __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need,
     __syncthreads();
 }
 
-#ifndef SD_MINB16
-#define SD_MINB16 3
-#define SD_MINB8 4
-#endif
 template <int ITEMS>
-__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? SD_MINB16 : SD_MINB8) k_select_dense(const SelArgs a)
+__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense(const SelArgs a) // (more resident CTAs measured no faster)
 {
     __shared__ int hist[FS_BINS];
     __shared__ uint64_t ckey[FS_SORT];
