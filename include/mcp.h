@@ -208,9 +208,9 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
 /* ------------------------------------------------- trial-sharded mode (optional)
  * BASELINE config C5: every rank holds ALL exposure rows and a contiguous shard of the scenario rows (trials
  * [trial_base, trial_base + N_local) of n_global, balanced: N_local <= ceil(n_global / world)).  Per portfolio the
- * global tail is found from the ranks' local top-m candidates (m ~ tail/world + 6 sigma) exchanged by ONE all-gather;
- * rows for which that is provably not enough (adversarial trial orders) go through a second round with the full
- * local tails, so results are exact for any input.  After the run, rank g holds the results of its portfolio slice
+ * global tail is found from the ranks' local top-m candidates (m ~ tail/world + 6 sigma) exchanged by ONE all-gather
+ * (plus one byte per portfolio saying whether that was provably enough); rows for which it was not (adversarial
+ * trial orders) go through a second round with the full local tails, so results are exact for any input.  After the run, rank g holds the results of its portfolio slice
  * [P g / world, P (g+1) / world) (same split as portfolio sharding): mcp_run_sizes / mcp_fetch return that slice.
  *
  * (1) with NCCL inside the library: rank 0 calls mcp_comm_unique_id and hands the 128 bytes to the other ranks
@@ -224,13 +224,17 @@ int mcp_run_trial_sharded(mcp_ctx *ctx, double alpha, int codec_id, int framing,
 /* (2) with the caller's own transport (MPI, sockets, a JVM-side shuffle ...), phase by phase.  All block pointers are
  *     DEVICE pointers; "gathered" = the world blocks of one round concatenated in rank order.
  *       mcp_ts_local   : local candidates + moments -> this rank's block (owned by ctx, *block_bytes each)
- *       mcp_ts_merge   : merge all rows from the gathered blocks; *flagged = rows needing the second round (the same
- *                        number on every rank).  The gathered buffer must stay valid until mcp_ts_finish.
+ *       mcp_ts_merge   : merge THIS RANK'S portfolio slice from the gathered blocks and test it for exactness; returns
+ *                        the slice's flag block (one byte per row, ceil(P / world) bytes, owned by ctx).  The gathered
+ *                        candidate buffer must stay valid until mcp_ts_finish.
+ *       mcp_ts_flags   : the ranks' flag blocks gathered in rank order -> *flagged = rows needing the second round (the
+ *                        same on every rank)
  *       mcp_ts_local2 / mcp_ts_merge2 : second round, only if *flagged > 0
  *       mcp_ts_finish  : breach lists, CVaR, pooled moments and encoding of this rank's portfolio slice
  */
 int mcp_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes);
-int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *flagged);
+int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int rank, void **d_flags, int64_t *flag_bytes);
+int mcp_ts_flags(mcp_ctx *ctx, const void *d_gathered_flags, int64_t *flagged);
 int mcp_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes);
 int mcp_ts_merge2(mcp_ctx *ctx, const void *d_gathered2);
 int mcp_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing);

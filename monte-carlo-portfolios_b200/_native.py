@@ -94,7 +94,8 @@ def lib() -> C.CDLL:
         "mcp_comm_destroy": (C.c_int, [vp]),
         "mcp_run_trial_sharded": (C.c_int, [vp, f64, C.c_int, C.c_int, i64, i64]),
         "mcp_ts_local": (C.c_int, [vp, f64, i64, i64, C.c_int, P(vp), P(i64)]),
-        "mcp_ts_merge": (C.c_int, [vp, vp, P(i64)]),
+        "mcp_ts_merge": (C.c_int, [vp, vp, C.c_int, P(vp), P(i64)]),
+        "mcp_ts_flags": (C.c_int, [vp, vp, P(i64)]),
         "mcp_ts_local2": (C.c_int, [vp, P(vp), P(i64)]),
         "mcp_ts_merge2": (C.c_int, [vp, vp]),
         "mcp_ts_finish": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),

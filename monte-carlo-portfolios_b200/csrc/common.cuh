@@ -96,10 +96,10 @@ struct mcp_ctx {
     int64_t runFallbackRows = 0;   // rows the last run had to redo with the guaranteed schedule
     // trial-sharded mode (risk_kernels.cu): state between the phase calls
     int64_t tsT = 0, tsM = 0, tsNGlobal = 0, tsTrialBase = 0, tsNFlag = 0, tsSlackOverride = -1;
-    int tsWorld = 0;
+    int tsWorld = 0, tsRank = -1;
     const unsigned char *tsGath = nullptr; // first-round gathered blocks (caller- or library-owned), needed until ts_finish
     std::vector<int32_t> tsFlagRows;
-    mcp::DevBuf dTsSend, dTsRecv, dTsRecv2, dTsFlags;
+    mcp::DevBuf dTsSend, dTsRecv, dTsRecv2, dTsFlags, dTsFlagsAll;
     void *nccl = nullptr;          // NcclComm* (nccl_dyn.cu), null until mcp_comm_init
     cudaStream_t stream3 = nullptr; // second tile stream (risk_stream_core), `cur` = the stream the tile helpers launch on
     cudaStream_t cur = nullptr;
@@ -232,7 +232,8 @@ int fp64_peak(mcp_ctx *ctx, double *tflops);
 int fp64_mma_peak(mcp_ctx *ctx, double *tflops);
 int64_t ts_candidates_per_rank(int64_t n_global, int64_t t, int world);
 int risk_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_base, int world, void **d_block, int64_t *block_bytes);
-int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *nflag_out);
+int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int rank, void **d_flags, int64_t *flag_bytes);
+int risk_ts_flags(mcp_ctx *ctx, const void *d_gathered_flags, int64_t *nflag_out);
 int risk_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes);
 int risk_ts_merge2(mcp_ctx *ctx, const void *d_gathered2);
 int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing);

@@ -127,7 +127,7 @@ void mcp_destroy(mcp_ctx *ctx)
                            &ctx->dGenVals, &ctx->dGenOff, &ctx->dCandKey, &ctx->dCandCnt, &ctx->dTau,
                            &ctx->dKeptKey, &ctx->dKeptIdx, &ctx->dShadow, &ctx->dKept2Key, &ctx->dKept2Idx,
                            &ctx->dFinKey, &ctx->dFinIdx, &ctx->dSfrag, &ctx->dGram, &ctx->dFail, &ctx->dFbE, &ctx->dFbOut,
-                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dCandKey2, &ctx->dCandCnt2, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags};
+                           &ctx->dFbKey, &ctx->dFbIdx, &ctx->dEpad, &ctx->dSpad, &ctx->dCandKey2, &ctx->dCandCnt2, &ctx->dTsSend, &ctx->dTsRecv, &ctx->dTsRecv2, &ctx->dTsFlags, &ctx->dTsFlagsAll};
     for (auto b : bufs) b->release();
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
@@ -647,10 +647,17 @@ int mcp_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_bas
     return sync(ctx);
 }
 
-int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *flagged)
+int mcp_ts_merge(mcp_ctx *ctx, const void *d_gathered, int rank, void **d_flags, int64_t *flag_bytes)
 {
     MCP_TRY(set_dev(ctx));
-    return risk_ts_merge(ctx, d_gathered, flagged);
+    MCP_TRY(risk_ts_merge(ctx, d_gathered, rank, d_flags, flag_bytes));
+    return sync(ctx);
+}
+
+int mcp_ts_flags(mcp_ctx *ctx, const void *d_gathered_flags, int64_t *flagged)
+{
+    MCP_TRY(set_dev(ctx));
+    return risk_ts_flags(ctx, d_gathered_flags, flagged);
 }
 
 int mcp_ts_local2(mcp_ctx *ctx, void **d_block, int64_t *block_bytes)
@@ -694,7 +701,15 @@ int mcp_run_trial_sharded(mcp_ctx *ctx, double alpha, int codec_id, int framing,
         KScope ks(ctx, MCP_K_COMM);
         MCP_TRY(nccl_all_gather(ctx, blk, ctx->dTsRecv.p, (size_t)bytes)); // the one exchange of the common case
     }
-    MCP_TRY(risk_ts_merge(ctx, ctx->dTsRecv.p, &flagged));
+    void *flags = nullptr;
+    int64_t fbytes = 0;
+    MCP_TRY(risk_ts_merge(ctx, ctx->dTsRecv.p, rank, &flags, &fbytes)); // this rank's portfolio slice
+    MCP_CUDA(ctx, ctx->dTsFlagsAll.reserve((size_t)fbytes * world + 16));
+    {
+        KScope ks(ctx, MCP_K_COMM);
+        MCP_TRY(nccl_all_gather(ctx, flags, ctx->dTsFlagsAll.p, (size_t)fbytes)); // one byte per row: which rows need round two
+    }
+    MCP_TRY(risk_ts_flags(ctx, ctx->dTsFlagsAll.p, &flagged));
     if (flagged > 0) { // same count on every rank: the collective below is entered by all of them
         MCP_TRY(risk_ts_local2(ctx, &blk, &bytes));
         MCP_CUDA(ctx, ctx->dTsRecv2.reserve((size_t)bytes * world));

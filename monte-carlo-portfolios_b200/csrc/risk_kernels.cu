@@ -834,7 +834,8 @@ struct SelArgs {
     const int32_t *kept_idx_in;
     int64_t kept_n;            // entries (= row stride) of the kept_*_in rows; 0 on the first step
     int kept_segs;             // > 1: the kept rows come in `kept_segs` blocks (one per rank of a trial-sharded run,
-    int64_t kept_seg_bytes;    //   `kept_seg_bytes` apart), each [rows][kept_n / kept_segs]: row r = the blocks' rows r
+    int64_t kept_seg_bytes;    //   `kept_seg_bytes` apart), each [rows][kept_n / kept_segs]: row r = the blocks' rows kept_row0 + r
+    int64_t kept_row0;
     uint64_t *kept_key_out;    // [rows][tail]
     int32_t *kept_idx_out;
     int64_t tail;              // t
@@ -876,9 +877,9 @@ __device__ __forceinline__ void kept_at(const SelArgs &a, int64_t row, int64_t i
         idx = (uint32_t)a.kept_idx_in[row * a.kept_n + i];
         return;
     }
-    const int64_t m = a.kept_n / a.kept_segs, g = i / m, j = i - g * m;
-    key = *reinterpret_cast<const uint64_t *>(reinterpret_cast<const unsigned char *>(a.kept_key_in) + g * a.kept_seg_bytes + (row * m + j) * 8);
-    idx = (uint32_t)*reinterpret_cast<const int32_t *>(reinterpret_cast<const unsigned char *>(a.kept_idx_in) + g * a.kept_seg_bytes + (row * m + j) * 4);
+    const int64_t m = a.kept_n / a.kept_segs, g = i / m, j = i - g * m, r = a.kept_row0 + row;
+    key = *reinterpret_cast<const uint64_t *>(reinterpret_cast<const unsigned char *>(a.kept_key_in) + g * a.kept_seg_bytes + (r * m + j) * 8);
+    idx = (uint32_t)*reinterpret_cast<const int32_t *>(reinterpret_cast<const unsigned char *>(a.kept_idx_in) + g * a.kept_seg_bytes + (r * m + j) * 4);
 }
 
 // visit every candidate of the row straight from global memory
@@ -2214,15 +2215,15 @@ __global__ void k_ts_pack(const uint64_t *kkey, const int32_t *kidx, int64_t P, 
 }
 
 // one warp per row: exact unless a rank that held back candidates has its smallest sent one above the threshold
-__global__ void __launch_bounds__(256) k_ts_check(const unsigned char *gath, int world, TsLayout L, int64_t rows, const int32_t *row_ids,
+__global__ void __launch_bounds__(256) k_ts_check(const unsigned char *gath, int world, TsLayout L, int64_t row0, int64_t rows,
                                                   const double *var_loss, const int32_t *var_trial, unsigned char *flags, int *nflag)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
-    const int64_t out_row = row_ids ? row_ids[r] : r; // where the merged threshold of this row lives
-    const uint64_t tk = fkey(var_loss[out_row]);
-    const uint32_t ti = (uint32_t)var_trial[out_row];
+    const int64_t rl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (rl >= rows) return;
+    const int64_t r = row0 + rl; // global row: this rank checks its own portfolio slice
+    const uint64_t tk = fkey(var_loss[r]);
+    const uint32_t ti = (uint32_t)var_trial[r];
     bool bad = false;
     for (int g = 0; g < world; ++g) {
         const unsigned char *blk = gath + (int64_t)g * L.bytes;
@@ -2245,7 +2246,7 @@ __global__ void __launch_bounds__(256) k_ts_check(const unsigned char *gath, int
         if (mk > tk || (mk == tk && mi > ti)) bad = true;
     }
     if (lane == 0) {
-        flags[r] = bad ? 1 : 0;
+        flags[rl] = bad ? 1 : 0;
         if (bad) atomicAdd(nflag, 1);
     }
 }
@@ -2301,7 +2302,48 @@ static int ts_local_block(mcp_ctx *ctx, const double *E, int64_t rows, int64_t m
     io.kidx[0] = ki[0]; io.kidx[1] = ki[1];
     io.tkey = ctx->dTau.as<uint64_t>();
     io.keep_only = true;
-    MCP_TRY(risk_stream_core(ctx, io, m_have, false, nullptr));
+    // first round: the two-step optimistic schedule (section 4.0) for the local top-m as well; rows where the bet fails
+    // are redone by the guaranteed schedule and their kept lists scattered back
+    const int64_t n0 = first_step_len(ctx->N, m_have);
+    const bool optimistic = with_moments && ctx->optimistic && ctx->N >= 2 * n0 && optimistic_rank(ctx->N, n0, m_have) < m_have;
+    if (optimistic) {
+        MCP_CUDA(ctx, ctx->dFail.reserve((size_t)(rows + 4) * sizeof(int32_t)));
+        MCP_CUDA(ctx, cudaMemsetAsync(ctx->dFail.p, 0, sizeof(int), ctx->stream));
+        io.fail_cnt = ctx->dFail.as<int>();
+        io.fail_rows = ctx->dFail.as<int32_t>() + 4;
+    }
+    MCP_TRY(risk_stream_core(ctx, io, m_have, optimistic, nullptr));
+    if (optimistic) {
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dFail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int64_t nf = *reinterpret_cast<int *>(ctx->hPinned);
+        if (nf > 0) {
+            const int F = ctx->F;
+            MCP_CUDA(ctx, ctx->dFbE.reserve((size_t)nf * F * sizeof(double)));
+            MCP_CUDA(ctx, ctx->dFbKey.reserve((size_t)nf * m_have * 2 * sizeof(uint64_t)));
+            MCP_CUDA(ctx, ctx->dFbIdx.reserve((size_t)nf * m_have * 2 * sizeof(int32_t)));
+            MCP_CUDA(ctx, ctx->dFinKey.reserve((size_t)nf * 16));
+            {
+                KScope ks(ctx, MCP_K_SELECT);
+                k_gather_rows<<<(unsigned)std::min<int64_t>((nf * F + 255) / 256, 4096), 256, 0, ctx->stream>>>(E, io.fail_rows, nf, F, ctx->dFbE.as<double>());
+                MCP_TRY(check_launch(ctx, "k_gather_rows"));
+            }
+            StreamIO fb{};
+            fb.E = ctx->dFbE.as<double>(); fb.P = nf;
+            fb.var_loss = ctx->dFinKey.as<double>(); fb.var_trial = reinterpret_cast<int32_t *>(ctx->dFinKey.as<double>() + nf);
+            fb.kkey[0] = ctx->dFbKey.as<uint64_t>(); fb.kkey[1] = fb.kkey[0] + nf * m_have;
+            fb.kidx[0] = ctx->dFbIdx.as<int32_t>(); fb.kidx[1] = fb.kidx[0] + nf * m_have;
+            mcp::DevBuf &tk = ctx->dTsFlags;       // thresholds of the compact problem
+            MCP_CUDA(ctx, tk.reserve((size_t)nf * sizeof(uint64_t) + 16));
+            fb.tkey = tk.as<uint64_t>();
+            fb.keep_only = true;
+            MCP_TRY(risk_stream_core(ctx, fb, m_have, false, nullptr));
+            KScope ks(ctx, MCP_K_SELECT);
+            k_ts_scatter_kept<<<(unsigned)nf, 128, 0, ctx->stream>>>(io.fail_rows, m_have, fb.kkey[fb.final_buf], fb.kidx[fb.final_buf], fb.var_loss, fb.var_trial,
+                                                                    io.kkey[io.final_buf], io.kidx[io.final_buf], io.var_loss, io.var_trial);
+            MCP_TRY(check_launch(ctx, "k_ts_scatter_kept"));
+        }
+    }
     L = ts_layout(rows, m);
     MCP_CUDA(ctx, blockbuf.reserve((size_t)L.bytes));
     KScope ks(ctx, MCP_K_SELECT);
@@ -2353,10 +2395,12 @@ int risk_ts_local(mcp_ctx *ctx, double alpha, int64_t n_global, int64_t trial_ba
 }
 
 // merge `rows` rows of `world` gathered blocks (layout L): top-t into kkey/kidx[rows][t], thresholds into vl/vt
-static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, const TsLayout &L, int64_t rows, int64_t t, uint64_t *kkey,
-                         int32_t *kidx, double *vl, int32_t *vt)
+static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, const TsLayout &L, int64_t row0, int64_t rows, int64_t t,
+                         uint64_t *kkey, int32_t *kidx, double *vl, int32_t *vt)
 {
+    if (rows <= 0) return MCP_OK;
     SelArgs a{};
+    a.kept_row0 = row0;
     a.kept_key_in = reinterpret_cast<const uint64_t *>(gath + L.off_keys);
     a.kept_idx_in = reinterpret_cast<const int32_t *>(gath + L.off_idx);
     a.kept_n = (int64_t)world * L.m;
@@ -2375,39 +2419,65 @@ static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, con
     return check_launch(ctx, "k_select (merge)");
 }
 
-int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int64_t *nflag_out)
+static void ts_slice(int64_t P, int rank, int world, int64_t &p0, int64_t &p1)
+{
+    const int64_t base = P / world, extra = P % world;
+    p0 = rank * base + (rank < extra ? rank : extra);
+    p1 = p0 + base + (rank < extra ? 1 : 0);
+}
+
+// Merge THIS RANK'S portfolio slice from the gathered blocks and test it; the slice's flags (one byte per row, padded to
+// ceil(P / world) bytes so that every rank's block has the same size) are what the ranks exchange next.
+int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int rank, void **d_flags, int64_t *flag_bytes)
 {
     if (ctx->tsWorld < 1 || !d_gathered) return fail(ctx, MCP_E_STATE, "ts_merge: call ts_local first");
+    if (rank < 0 || rank >= ctx->tsWorld) return fail(ctx, MCP_E_ARG, "ts_merge: bad rank");
     const int64_t P = ctx->P, t = ctx->tsT;
     const TsLayout L = ts_layout(P, ctx->tsM);
     const unsigned char *g = reinterpret_cast<const unsigned char *>(d_gathered);
     ctx->tsGath = g;
+    ctx->tsRank = rank;
+    int64_t p0, p1;
+    ts_slice(P, rank, ctx->tsWorld, p0, p1);
+    const int64_t fb = (P + ctx->tsWorld - 1) / ctx->tsWorld;
     MCP_CUDA(ctx, ctx->dVarLoss.reserve(P * sizeof(double)));
     MCP_CUDA(ctx, ctx->dVarTrial.reserve(P * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dKeptKey.reserve((size_t)P * t * sizeof(uint64_t)));
     MCP_CUDA(ctx, ctx->dKeptIdx.reserve((size_t)P * t * sizeof(int32_t)));
     MCP_CUDA(ctx, ctx->dFail.reserve((size_t)(P + 4) * sizeof(int32_t)));
-    MCP_CUDA(ctx, ctx->dTsFlags.reserve((size_t)P + 16));
-    MCP_TRY(ts_merge_rows(ctx, g, ctx->tsWorld, L, P, t, ctx->dKeptKey.as<uint64_t>(), ctx->dKeptIdx.as<int32_t>(), ctx->dVarLoss.as<double>(),
-                          ctx->dVarTrial.as<int32_t>()));
+    MCP_CUDA(ctx, ctx->dTsFlags.reserve((size_t)fb + 16));
+    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dTsFlags.p, 0, (size_t)fb + 16, ctx->stream));
+    MCP_TRY(ts_merge_rows(ctx, g, ctx->tsWorld, L, p0, p1 - p0, t, ctx->dKeptKey.as<uint64_t>() + p0 * t, ctx->dKeptIdx.as<int32_t>() + p0 * t,
+                          ctx->dVarLoss.as<double>() + p0, ctx->dVarTrial.as<int32_t>() + p0));
     MCP_CUDA(ctx, cudaMemsetAsync(ctx->dFail.p, 0, sizeof(int), ctx->stream));
-    {
+    if (p1 > p0) {
         KScope ks(ctx, MCP_K_SELECT);
-        k_ts_check<<<(unsigned)((P * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->tsWorld, L, P, nullptr, ctx->dVarLoss.as<double>(),
-                                                                             ctx->dVarTrial.as<int32_t>(), ctx->dTsFlags.as<unsigned char>(), ctx->dFail.as<int>());
+        k_ts_check<<<(unsigned)(((p1 - p0) * 32 + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->tsWorld, L, p0, p1 - p0, ctx->dVarLoss.as<double>(),
+                                                                                     ctx->dVarTrial.as<int32_t>(), ctx->dTsFlags.as<unsigned char>(), ctx->dFail.as<int>());
         MCP_TRY(check_launch(ctx, "k_ts_check"));
     }
-    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dFail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_flags) *d_flags = ctx->dTsFlags.p;
+    if (flag_bytes) *flag_bytes = fb;
+    return MCP_OK;
+}
+
+// every rank's flag block (world x ceil(P / world) bytes, rank order) -> the flagged rows, ascending, identical everywhere
+int risk_ts_flags(mcp_ctx *ctx, const void *d_gathered_flags, int64_t *nflag_out)
+{
+    if (ctx->tsWorld < 1 || !ctx->tsGath || !d_gathered_flags) return fail(ctx, MCP_E_STATE, "ts_flags: merge first");
+    const int64_t P = ctx->P, fb = (P + ctx->tsWorld - 1) / ctx->tsWorld;
+    std::vector<unsigned char> f((size_t)fb * ctx->tsWorld);
+    MCP_CUDA(ctx, cudaMemcpyAsync(f.data(), d_gathered_flags, f.size(), cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->tsNFlag = *reinterpret_cast<int *>(ctx->hPinned);
     ctx->tsFlagRows.clear();
+    for (int g = 0; g < ctx->tsWorld; ++g) {
+        int64_t p0, p1;
+        ts_slice(P, g, ctx->tsWorld, p0, p1);
+        for (int64_t p = p0; p < p1; ++p)
+            if (f[(size_t)(g * fb + (p - p0))]) ctx->tsFlagRows.push_back((int32_t)p);
+    }
+    ctx->tsNFlag = (int64_t)ctx->tsFlagRows.size();
     if (ctx->tsNFlag > 0) {
-        // the flagged rows in ascending order (identical on every rank: all ranks merged the same blocks)
-        std::vector<unsigned char> f((size_t)P);
-        MCP_CUDA(ctx, cudaMemcpyAsync(f.data(), ctx->dTsFlags.p, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int64_t p = 0; p < P; ++p)
-            if (f[(size_t)p]) ctx->tsFlagRows.push_back((int32_t)p);
         MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dFail.as<int32_t>() + 4, ctx->tsFlagRows.data(), ctx->tsFlagRows.size() * sizeof(int32_t),
                                       cudaMemcpyHostToDevice, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2452,7 +2522,7 @@ int risk_ts_merge2(mcp_ctx *ctx, const void *d_gathered2)
     MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)nf * 16));
     double *vl = ctx->dFbOut.as<double>();
     int32_t *vt = reinterpret_cast<int32_t *>(vl + nf);
-    MCP_TRY(ts_merge_rows(ctx, reinterpret_cast<const unsigned char *>(d_gathered2), ctx->tsWorld, L, nf, t, ctx->dFinKey.as<uint64_t>(),
+    MCP_TRY(ts_merge_rows(ctx, reinterpret_cast<const unsigned char *>(d_gathered2), ctx->tsWorld, L, 0, nf, t, ctx->dFinKey.as<uint64_t>(),
                           ctx->dFinIdx.as<int32_t>(), vl, vt));
     KScope ks(ctx, MCP_K_SELECT);
     k_ts_scatter_kept<<<(unsigned)nf, 128, 0, ctx->stream>>>(ctx->dFail.as<int32_t>() + 4, t, ctx->dFinKey.as<uint64_t>(), ctx->dFinIdx.as<int32_t>(), vl, vt,
@@ -2464,10 +2534,10 @@ int risk_ts_merge2(mcp_ctx *ctx, const void *d_gathered2)
 // this rank's portfolio slice: breach lists, CVaR, pooled moments, encoding
 int risk_ts_finish(mcp_ctx *ctx, int rank, int world, int codec_id, int framing)
 {
-    if (!ctx->tsGath || world != ctx->tsWorld || rank < 0 || rank >= world) return fail(ctx, MCP_E_STATE, "ts_finish: merge first");
+    if (!ctx->tsGath || world != ctx->tsWorld || rank != ctx->tsRank) return fail(ctx, MCP_E_STATE, "ts_finish: merge first (same rank / world)");
     const int64_t P = ctx->P, t = ctx->tsT;
-    const int64_t base = P / world, extra = P % world;
-    const int64_t p0 = rank * base + (rank < extra ? rank : extra), p1 = p0 + base + (rank < extra ? 1 : 0);
+    int64_t p0, p1;
+    ts_slice(P, rank, world, p0, p1);
     const int64_t rows = p1 - p0;
     MCP_CUDA(ctx, ctx->dCvar.reserve(P * sizeof(double)));
     MCP_CUDA(ctx, ctx->dBreach.reserve((size_t)P * t * sizeof(int32_t)));

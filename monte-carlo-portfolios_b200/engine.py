@@ -222,9 +222,15 @@ class Context:
         self._check(self._L.mcp_ts_local(self._h, alpha, n_global, trial_base, world, C.byref(p), C.byref(nb)), "ts_local")
         return p.value, nb.value
 
-    def ts_merge(self, d_gathered: int) -> int:
+    def ts_merge(self, d_gathered: int, rank: int):
+        """Merge this rank's portfolio slice -> (device pointer, bytes) of its flag block."""
+        p, nb = C.c_void_p(), C.c_int64()
+        self._check(self._L.mcp_ts_merge(self._h, C.c_void_p(d_gathered), rank, C.byref(p), C.byref(nb)), "ts_merge")
+        return p.value, nb.value
+
+    def ts_flags(self, d_gathered_flags: int) -> int:
         fl = C.c_int64()
-        self._check(self._L.mcp_ts_merge(self._h, C.c_void_p(d_gathered), C.byref(fl)), "ts_merge")
+        self._check(self._L.mcp_ts_flags(self._h, C.c_void_p(d_gathered_flags), C.byref(fl)), "ts_flags")
         return fl.value
 
     def ts_local2(self):

@@ -34,13 +34,23 @@ def emulate(E, S, alpha, world, cid=CID, framing=N.FRAME_APP, slack=None):
             blocks.append(b)
         assert len({b.size for b in blocks}) == 1
         gathered = np.concatenate(blocks)
-        flagged = []
-        for c in ctxs:
+        fblocks = []
+        for g, c in enumerate(ctxs):
             d = c.dev_alloc(gathered.size)
             bufs.append((c, d))
             c.h2d(d, gathered)
-            flagged.append(c.ts_merge(d))
-        assert len(set(flagged)) == 1, flagged            # every rank reaches the same verdict
+            ptr, nb = c.ts_merge(d, g)                    # each rank merges and tests its own portfolio slice
+            b = np.empty(nb, np.uint8)
+            c.d2h(b, ptr)
+            fblocks.append(b)
+        allflags = np.concatenate(fblocks)                # the second (tiny) exchange: one byte per portfolio
+        flagged = []
+        for c in ctxs:
+            d = c.dev_alloc(allflags.size)
+            bufs.append((c, d))
+            c.h2d(d, allflags)
+            flagged.append(c.ts_flags(d))
+        assert len(set(flagged)) == 1, flagged            # every rank sees the same list
         if flagged[0] > 0:
             blocks2 = []
             for c in ctxs:
