@@ -1523,6 +1523,8 @@ static cudaError_t sel_configure(int bytes)
 {
     cudaError_t e = cudaFuncSetAttribute(k_select_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_select_t<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_select_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
@@ -1642,15 +1644,18 @@ constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail siz
 // length of the dense first step: ~4 tail sizes, at least kDenseFloor trials, a multiple of 8 (tensor-core trial blocks)
 static int64_t g_dense_floor = 2048; // process-wide tuning knob (mcp_set_option "dense_floor")
 void risk_set_dense_floor(int64_t v) { g_dense_floor = v < 64 ? 64 : v; }
-static int64_t first_step_len(int64_t N, int64_t t)
+// `two_step` (optimistic schedule): the sample only has to pin down a quantile, so it is capped at the 4 096 values the
+// register-resident selection handles -- for large tails the bound gets relatively tighter, not looser (r ~ t n0 / N).
+static int64_t first_step_len(int64_t N, int64_t t, bool two_step = false)
 {
     int64_t c0 = 4 * t;
     if (c0 < g_dense_floor) c0 = g_dense_floor;
+    if (two_step && c0 > 16 * SEL_THREADS) c0 = 16 * SEL_THREADS;
     c0 = (c0 + 7) & ~(int64_t)7;
     return c0 < N ? c0 : N;
 }
 
-int64_t risk_first_step_len(int64_t N, int64_t t) { return first_step_len(N, t); }
+int64_t risk_first_step_len(int64_t N, int64_t t) { return first_step_len(N, t, true); }
 
 // Trial schedule of the streaming path.  Guaranteed: a dense first step of ~4 tail sizes establishes each
 // portfolio's threshold, then steps grow 3x; every later step inserts ~2 tail sizes of candidates.  Optimistic
@@ -1660,7 +1665,7 @@ static inline bool steps_hint_two(bool, int64_t N, int64_t e) { return e < N; } 
 static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sms, bool two_step = false, int64_t kItemTrials = 2048)
 {
     std::vector<Step> steps;
-    const int64_t c0 = first_step_len(N, t);
+    const int64_t c0 = first_step_len(N, t, two_step);
     int64_t b = 0, len = c0;
     while (b < N) {
         int64_t e = b + len;
@@ -1694,9 +1699,11 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
         if (bm_smem > 40 * 1024) {
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
             MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_bitmap_t<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
         }
         KScope ks(ctx, MCP_K_SELECT);
         if (small) k_finalize_bitmap_t<64><<<(unsigned)rows, 64, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
+        else if (bm_smem > 72 * 1024) k_finalize_bitmap_t<1024><<<(unsigned)rows, 1024, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         else k_finalize_bitmap_t<256><<<(unsigned)rows, 256, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         return check_launch(ctx, "k_finalize_bitmap");
     }
@@ -2050,7 +2057,10 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                     // global-memory path): a dozen rows resident per SM instead of four
                     a.cap = 1024;
                     k_select_t<64><<<(unsigned)rows, 64, sel_smem_bytes(a.cap, a.nsub, 64), cur_stream(ctx)>>>(a);
-                } else
+                } else if (sel_smem_bytes(a.cap, a.nsub) > 110 * 1024)
+                    // large tails: the staging area leaves room for ONE CTA per SM, so make it 1 024 threads wide
+                    k_select_t<1024><<<(unsigned)rows, 1024, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
+                else
                     k_select_t<256><<<(unsigned)rows, 256, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
                 MCP_TRY(check_launch(ctx, "k_select"));
             }
@@ -2079,8 +2089,8 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
     int *fail_cnt = ctx->dFail.as<int>();
     int32_t *fail_rows = ctx->dFail.as<int32_t>() + 4;
     // the optimistic bound needs a sample that is a small part of the trials and a rank below the tail size
-    const int64_t n0 = first_step_len(N, t);
-    const bool optimistic = ctx->optimistic && N >= 2 * n0 && optimistic_rank(N, n0, t) < t;
+    const int64_t n0 = first_step_len(N, t, true);
+    const bool optimistic = ctx->optimistic && N >= 2 * n0 && optimistic_rank(N, n0, t) < t && 2 * optimistic_rank(N, n0, t) <= n0;
     StreamIO io{};
     io.E = ctx->dE.as<double>(); io.P = P;
     io.var_loss = ctx->dVarLoss.as<double>(); io.var_trial = ctx->dVarTrial.as<int32_t>();
@@ -2304,8 +2314,9 @@ static int ts_local_block(mcp_ctx *ctx, const double *E, int64_t rows, int64_t m
     io.keep_only = true;
     // first round: the two-step optimistic schedule (section 4.0) for the local top-m as well; rows where the bet fails
     // are redone by the guaranteed schedule and their kept lists scattered back
-    const int64_t n0 = first_step_len(ctx->N, m_have);
-    const bool optimistic = with_moments && ctx->optimistic && ctx->N >= 2 * n0 && optimistic_rank(ctx->N, n0, m_have) < m_have;
+    const int64_t n0 = first_step_len(ctx->N, m_have, true);
+    const bool optimistic = with_moments && ctx->optimistic && ctx->N >= 2 * n0 && optimistic_rank(ctx->N, n0, m_have) < m_have &&
+                            2 * optimistic_rank(ctx->N, n0, m_have) <= n0;
     if (optimistic) {
         MCP_CUDA(ctx, ctx->dFail.reserve((size_t)(rows + 4) * sizeof(int32_t)));
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dFail.p, 0, sizeof(int), ctx->stream));

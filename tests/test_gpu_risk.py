@@ -142,6 +142,15 @@ def test_streaming_path_many_portfolios_ragged(ctx):
         check_against_oracle(ctx, E, S, alpha, rows=list(range(0, P, max(1, P // 37))) + [P - 1])
 
 
+def test_large_tails_take_the_wide_selection_kernels(ctx):
+    """Confidence levels with tails of thousands of trials: the optimistic sample is capped at 4 096 values, the sparse
+    selection runs with 1 024-thread CTAs (one per SM), very large tails overflow into the global-memory passes."""
+    E, S = riskcases.synthetic(24, 100000, 32, 91)
+    for alpha in (0.95, 0.9, 0.6):
+        check_against_oracle(ctx, E, S, alpha, rows=[0, 11, 23])
+        assert ctx.run_stats()["fallback_rows"] == 0
+
+
 def test_ties_break_by_trial_index(ctx):
     E, S = riskcases.with_ties(20, 3000, 4, 9)
     check_against_oracle(ctx, E, S, 0.9)
