@@ -1648,7 +1648,7 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     if (nlists <= 0) return 0;
     const CodecTraits tr = codec_traits(codec);
     const double avg = (double)total_vals / (double)nlists;
-    if (avg > (tr.fastpfor ? 2048.0 : 1024.0)) return 0;
+    if (avg > (tr.fastpfor ? 4000.0 : 1024.0)) return 0; // (a FastPFOR batch may be a single list of up to FE_VCAP values)
     int64_t g = (int64_t)(0.92 * FE_VCAP / (avg > 1.0 ? avg : 1.0));
     int64_t gmax = FE_MAXL;
     if (tr.fastpfor) { // VariableByte tails of up to block-1 values per list share the tail table
