@@ -11,7 +11,7 @@ from .codec import (BinaryPacking, Composition, FastPFOR, FastPFOR128, IntCompre
                     IntegratedComposition, IntegratedIntCompressor, IntegratedVariableByte, IntWrapper, VariableByte,
                     VariableByteCodec, default_context)
 from .engine import Context
-from .portfolio import LoadPortfolios
+from .portfolio import LoadPortfolios, SimulatePortfolios, simulation_documents
 from . import sharding
 
 __all__ = [n for n in dir() if not n.startswith("_")]

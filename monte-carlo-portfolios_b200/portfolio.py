@@ -89,3 +89,50 @@ def read_macro_json(path: str) -> np.ndarray:
     rows.sort(key=lambda r: r.get("date_offset", 0))
     F = sum(1 for k in rows[0] if k.startswith("m") and k[1:].isdigit())
     return np.array([[float(r[f"m{k}"]) for k in range(F)] for r in rows], np.float64)
+
+
+RESULTS_TABLE = "/apps/simulation_results"  # created, never written, by the reference: ManageMapRDBTable.java:15
+BREACH_CODEC_NAME = "delta+fastpfor+variablebyte"
+
+
+def simulation_documents(ids, result: dict, alpha: float, algo: str = BREACH_CODEC_NAME) -> list[dict]:
+    """One sink document per portfolio from a run's result arrays (Context.simulate / fetch, or sharding.assemble),
+    shaped like the loader's instrument document (LoadPortfolios.java:597-606) and with its storage rule (:254-260):
+    the encoded breach list is stored only if it is smaller than the raw big-endian ints, else those with algo "none".
+    The blob decodes with the stock Java library (Composition(FastPFOR, VariableByte) + Delta.fastinverseDelta)."""
+    t = int(result["tail"])
+    enc, off = result["enc"], result["enc_off"]
+    docs = []
+    for p, pid in enumerate(ids):
+        blob = bytes(enc[off[p]: off[p + 1]])
+        a = algo
+        if not (len(blob) < 4 * t):
+            if result.get("breach") is None:
+                raise ValueError("the raw breach lists are needed for the uncompressed fallback")
+            blob, a = LoadPortfolios.integersToBytes(result["breach"][p]), "none"
+        docs.append({"_id": str(pid), "alpha": alpha, "trials": int(result.get("trials", 0)),
+                     "mean": float(result["mean"][p]), "variance": float(result["variance"][p]),
+                     "var": {"loss": float(result["var_loss"][p]), "trial": int(result["var_trial"][p])},
+                     "cvar": float(result["cvar"][p]),
+                     "breaches": {"uncompressedIntegerSize": t, "compressed": blob, "compressedByteSize": len(blob), "algo": a}})
+    return docs
+
+
+class SimulatePortfolios:
+    """The entry point the reference names a table for but never wrote: portfolios.json x macro.json -> exposures on the
+    device (mcp_build_exposures) -> the hot path -> one document per portfolio for /apps/simulation_results."""
+
+    def __init__(self, ctx: Context | None = None, codec_id: int = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA):
+        from .codec import default_context
+        self.ctx = ctx or default_context()
+        self.codec_id = codec_id
+
+    def run(self, portfolios_json: str, macro_json: str, loadings, alpha: float) -> list[dict]:
+        ids, inst, w, off = read_portfolios_json(portfolios_json)
+        S = read_macro_json(macro_json)
+        self.ctx.build_exposures(inst, w, off, loadings)
+        self.ctx.upload_scenarios(S)
+        self.ctx.run(alpha, self.codec_id, N.FRAME_APP)
+        r = self.ctx.fetch()
+        r["trials"] = S.shape[0]
+        return simulation_documents(ids, r, alpha)

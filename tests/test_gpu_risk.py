@@ -242,6 +242,34 @@ def test_ingest_builds_the_exposure_matrix_on_the_device(ctx):
         ctx.build_exposures(np.array([500], np.int32), np.ones(1), np.array([0, 1], np.int64), np.ones((500, 4)))
 
 
+def test_simulate_portfolios_entry_point_on_the_shipped_sample(ctx, tmp_path):
+    """portfolios.json x macro.json -> SimulatePortfolios -> one sink document per portfolio (the reference creates the
+    /apps/simulation_results table, ManageMapRDBTable.java:15, and never writes it)."""
+    import json
+    import mcp_b200
+    d, E, S = riskcases.c1_inputs()
+    pf, mf = tmp_path / "portfolios.json", tmp_path / "macro.json"
+    with open(pf, "w") as fh:
+        for p in d["portfolios"]:
+            fh.write(json.dumps({"id": p["id"], "instruments": [{"instrument": i, "weight": w} for i, w in zip(p["instruments"], p["weights"])]}) + "\n")
+    with open(mf, "w") as fh:
+        for k, row in enumerate(d["macro"]):
+            fh.write(json.dumps({"date_offset": k, **{f"m{j}": v for j, v in enumerate(row)}}) + "\n")
+    B = cref.gen_normal(10000, 10, 0x5EED0001, 3, 1e-2, 0.0)
+    docs = mcp_b200.SimulatePortfolios(ctx).run(str(pf), str(mf), B, 0.9)
+    o = cref.risk(E, S, 0.9)
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    assert len(docs) == 10
+    for p, doc in enumerate(docs):
+        assert doc["var"]["loss"] == o["var_loss"][p] and doc["var"]["trial"] == o["var_trial"][p]
+        b = doc["breaches"]
+        lst = o["breach"][p]
+        if b["algo"] == "none":
+            assert b["compressed"] == mcp_b200.LoadPortfolios.integersToBytes(lst)
+        else:
+            assert np.array_equal(cref.get_decompressed_instruments(cid, b["compressed"], o["tail"]), lst)
+
+
 def test_c1_shipped_sample(ctx):
     """BASELINE config C1: portfolios.json x macro.json (fixture tests/golden/c1_sample.json)."""
     d, E, S = riskcases.c1_inputs()

@@ -140,3 +140,27 @@ def test_json_readers_on_the_c1_fixture(tmp_path):
     i2, w2, o2 = riskcases.c1_positions(d)
     assert np.array_equal(inst, i2) and np.array_equal(w, w2) and np.array_equal(off, o2) and len(ids) == 10
     assert np.array_equal(portfolio.read_macro_json(str(mf)), S)
+
+
+def test_simulation_documents_follow_the_loader_document_shape():
+    """simulation_documents: the sink document of a run (schema by analogy with LoadPortfolios.java:597-606, storage rule
+    :254-260), here fed from the oracle's results: blobs decode back to the breach lists with the reference's codec."""
+    from mcp_b200 import portfolio
+    E, S = riskcases.synthetic(5, 3000, 8, 12)
+    cid = cref.CODEC_FASTPFOR256_VB | cref.FLAG_DELTA
+    o = cref.risk(E, S, 0.98)
+    blobs = [cref.get_compressed_instruments(cid, o["breach"][p]) for p in range(5)]
+    off = np.zeros(6, np.int64)
+    np.cumsum([len(b) for b in blobs], out=off[1:])
+    o.update(enc=np.frombuffer(b"".join(blobs), np.uint8), enc_off=off, trials=3000)
+    docs = portfolio.simulation_documents(["a", "b", "c", "d", "e"], o, 0.98)
+    assert [d["_id"] for d in docs] == ["a", "b", "c", "d", "e"]
+    for p, d in enumerate(docs):
+        b = d["breaches"]
+        assert b["algo"] == portfolio.BREACH_CODEC_NAME and b["uncompressedIntegerSize"] == o["tail"] and b["compressedByteSize"] == len(b["compressed"])
+        assert np.array_equal(cref.get_decompressed_instruments(cid, b["compressed"], o["tail"]), o["breach"][p])
+        assert d["var"]["trial"] == o["var_trial"][p] and d["cvar"] == o["cvar"][p]
+    # incompressible lists fall back to raw big-endian ints, like the loader's "none" branch
+    o2 = dict(o, tail=2, breach=np.array([[5, 2**30]] * 5, np.int32), enc=np.zeros(5 * 64, np.uint8), enc_off=np.arange(6, dtype=np.int64) * 64)
+    d2 = portfolio.simulation_documents(range(5), o2, 0.98)
+    assert d2[0]["breaches"]["algo"] == "none" and d2[0]["breaches"]["compressed"] == (5).to_bytes(4, "big") + (2**30).to_bytes(4, "big")
