@@ -353,8 +353,12 @@ constexpr int VM_WARPS = 16;
 constexpr int VM_THREADS = VM_WARPS * 32;
 constexpr int VM_G = 2;                      // portfolio groups (of 8) per warp
 constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 256
-constexpr int VM_ST = 32;                    // trials per stage
-constexpr int VM_NSTAGE = 4;
+// Scenario staging: TWO stages of as many trials as ~196 KB of shared memory hold (256 for F <= 48, 192 for F = 64).
+// Measured on C2: 4 stages x 32 trials 2.157 ms, 4 x 64 2.102, 3 x 128 2.068, 2 x 256 2.056 -- what costs is the
+// per-stage handshake (mbarrier wait / arrive, the producer thread's detour), not the prefetch depth: one stage of
+// compute (>= 192 trials) covers the latency of the next stage's single bulk copy many times over.
+constexpr int VM_NSTAGE = 2;
+template <int NK> constexpr int vm_stage_trials() { return NK <= 12 ? 256 : 192; }
 
 struct StreamArgs {
     const double *E, *S;
@@ -430,7 +434,7 @@ __device__ __forceinline__ void append_if(uint32_t hit, CandRec *dst, double v, 
 }
 
 template <int NK>
-constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * VM_ST * (NK * 4); }
+constexpr size_t vm_smem_bytes() { return sizeof(double) * VM_NSTAGE * vm_stage_trials<NK>() * (NK * 4); }
 
 // S[N][F] -> Sfrag[ceil(N/8)][NK][32]: element (b, s, lane) = S[8b + lane/4][4s + lane%4] (0 past the last trial).
 // In this order a stage of 32 trials is one contiguous block (a single TMA bulk copy) and every B-fragment load is
@@ -454,7 +458,8 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 {
     constexpr int F = NK * 4;
     constexpr int BLK = NK * 32;            // doubles per 8-trial block in fragment order
-    constexpr int STG = (VM_ST / 8) * BLK;  // doubles per stage
+    constexpr int VM_ST = vm_stage_trials<NK>(); // trials per stage
+    constexpr int STG = (VM_ST / 8) * BLK;       // doubles per stage
     extern __shared__ __align__(128) unsigned char vm_smem[];
     double *s_S = reinterpret_cast<double *>(vm_smem); // [NSTAGE][ST/8][NK][32]
     __shared__ __align__(8) uint64_t s_full[VM_NSTAGE], s_empty[VM_NSTAGE];
