@@ -1306,10 +1306,11 @@ __global__ void __launch_bounds__(THREADS) k_select_t(const SelArgs a)
 // passes, the gather and the boundary-bucket sort run without staging anything in shared memory -- 5 KB of shared
 // memory per CTA instead of ~60 KB, so the SM holds as many rows as its registers allow.
 // from the histogram (bins descending from FS_BINS-1): the bin where the count from the top reaches `need`
+template <int THREADS>
 __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need, int *s_wsum, int *s_sel, int *s_above, int *s_bucket)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int PER = FS_BINS / SEL_THREADS;
+    constexpr int PER = FS_BINS / THREADS;
     const int hb = FS_BINS - 1 - tid * PER; // thread 0 owns the highest bins
     int sum = 0;
 #pragma unroll
@@ -1336,14 +1337,14 @@ __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need,
     __syncthreads();
 }
 
-template <int ITEMS>
-__global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense(const SelArgs a) // (more resident CTAs measured no faster)
+template <int ITEMS, int THREADS>
+__global__ void __launch_bounds__(THREADS, (ITEMS > 8 ? 3 : 4) * (256 / THREADS)) k_select_dense(const SelArgs a)
 {
     __shared__ int hist[FS_BINS];
     __shared__ uint64_t ckey[FS_SORT];
     __shared__ uint32_t cidx[FS_SORT];
-    __shared__ double s_red[2 * (SEL_THREADS / 32)];
-    __shared__ int s_wsum[SEL_THREADS / 32];
+    __shared__ double s_red[2 * (THREADS / 32)];
+    __shared__ int s_wsum[THREADS / 32];
     __shared__ int s_sel, s_above, s_bucket;
     const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
@@ -1352,13 +1353,13 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
-    for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0; // (visible after the barrier of the range reduction)
+    for (int b = tid; b < FS_BINS; b += THREADS) hist[b] = 0; // (visible after the barrier of the range reduction)
     // ---- load: slot i = tid + 256 j holds the loss of trial n_begin + i (slots past n repeat the thread's first
     // loss: harmless for min / max, masked everywhere else)
     double x[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const int i = tid + SEL_THREADS * j;
+        const int i = tid + THREADS * j;
         x[j] = 0.0 - __ldg(V + (i < n ? i : (tid < n ? tid : 0)));
     }
     // range of the row from the HIGH WORDS of the order-preserving keys (one integer min / max per value instead of
@@ -1374,10 +1375,10 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     hmn = __reduce_min_sync(kFullMask, hmn);
     hmx = __reduce_max_sync(kFullMask, hmx);
     uint32_t *s_redw = reinterpret_cast<uint32_t *>(s_red);
-    if (lane == 0) { s_redw[warp] = hmn; s_redw[SEL_THREADS / 32 + warp] = hmx; }
+    if (lane == 0) { s_redw[warp] = hmn; s_redw[THREADS / 32 + warp] = hmx; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < SEL_THREADS / 32; ++w) { hmn = min(hmn, s_redw[w]); hmx = max(hmx, s_redw[SEL_THREADS / 32 + w]); }
+    for (int w = 0; w < THREADS / 32; ++w) { hmn = min(hmn, s_redw[w]); hmx = max(hmx, s_redw[THREADS / 32 + w]); }
     const bool finite = hmx < 0xfff00000u && hmn > 0x000fffffu; // inside (-inf, +inf)
     const double mn = fkey_inv((uint64_t)hmn << 32), mx = fkey_inv(((uint64_t)hmx << 32) | 0xffffffffull);
     // ---- pass 0 in VALUE space: FS_BINS equal-width bins of [min, max].  The bin index is a monotone function of
@@ -1397,9 +1398,9 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     if (byval) {
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j)
-            if (tid + SEL_THREADS * j < n) atomicAdd(&hist[bin_of(x[j])], 1);
+            if (tid + THREADS * j < n) atomicAdd(&hist[bin_of(x[j])], 1);
         __syncthreads();
-        find_boundary_bin(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+        find_boundary_bin<THREADS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
         sel = s_sel;
         need -= s_above;
         bucket = s_bucket;
@@ -1413,7 +1414,7 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
         uint64_t kmn = ~0ull, kmx = 0;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            if (tid + SEL_THREADS * j < n && (!byval || bin_of(x[j]) == sel)) {
+            if (tid + THREADS * j < n && (!byval || bin_of(x[j]) == sel)) {
                 const uint64_t k = fkey(x[j]);
                 kmn = k < kmn ? k : kmn; kmx = k > kmx ? k : kmx;
             }
@@ -1424,20 +1425,20 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
         }
         uint64_t *s_redu = reinterpret_cast<uint64_t *>(s_red);
         __syncthreads();
-        if (lane == 0) { s_redu[warp] = kmn; s_redu[SEL_THREADS / 32 + warp] = kmx; }
+        if (lane == 0) { s_redu[warp] = kmn; s_redu[THREADS / 32 + warp] = kmx; }
         __syncthreads();
         uint64_t lo = ~0ull, hi = 0;
 #pragma unroll
-        for (int w = 0; w < SEL_THREADS / 32; ++w) { lo = s_redu[w] < lo ? s_redu[w] : lo; hi = s_redu[SEL_THREADS / 32 + w] > hi ? s_redu[SEL_THREADS / 32 + w] : hi; }
+        for (int w = 0; w < THREADS / 32; ++w) { lo = s_redu[w] < lo ? s_redu[w] : lo; hi = s_redu[THREADS / 32 + w] > hi ? s_redu[THREADS / 32 + w] : hi; }
         blo = lo; bhi = hi;
         for (int pass = 0; pass < 16; ++pass) {
             const uint64_t w64 = hi - lo;
             const int shift = w64 < (uint64_t)FS_BINS ? 0 : (64 - __clzll((long long)w64)) - FS_BITS;
-            for (int b = tid; b < FS_BINS; b += SEL_THREADS) hist[b] = 0;
+            for (int b = tid; b < FS_BINS; b += THREADS) hist[b] = 0;
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
-                const int i = tid + SEL_THREADS * j;
+                const int i = tid + THREADS * j;
                 if (i < n) {
                     const uint64_t k = fkey(x[j]);
                     if (on_idx) { if (k == kstar) { const uint64_t v = (uint32_t)(a.n_begin + i); if (v >= lo && v <= hi) atomicAdd(&hist[(int)((v - lo) >> shift)], 1); } }
@@ -1445,7 +1446,7 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
                 }
             }
             __syncthreads();
-            find_boundary_bin(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+            find_boundary_bin<THREADS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
             need -= s_above;
             bucket = s_bucket;
             blo = lo + ((uint64_t)s_sel << shift);
@@ -1466,7 +1467,7 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     uint32_t relk = 0, relb = 0; // bit j: my item j is above / inside the boundary bin
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const int i = tid + SEL_THREADS * j;
+        const int i = tid + THREADS * j;
         if (i < n) {
             int rel; // +1 above, 0 inside, -1 below
             if (!bykey) { const int b = bin_of(x[j]); rel = b > sel ? 1 : (b == sel ? 0 : -1); }
@@ -1494,7 +1495,7 @@ __global__ void __launch_bounds__(SEL_THREADS, ITEMS > 8 ? 3 : 4) k_select_dense
     int ok = off & 0xffff, ob = off >> 16;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        const int32_t id = (int32_t)(a.n_begin + tid + SEL_THREADS * j);
+        const int32_t id = (int32_t)(a.n_begin + tid + THREADS * j);
         if (relk & (1u << j)) { kk[ok] = fkey(x[j]); ki[ok] = id; ++ok; }
         else if (relb & (1u << j)) { ckey[ob] = fkey(x[j]); cidx[ob] = (uint32_t)id; ++ob; }
     }
@@ -2055,8 +2056,9 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
                 a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
-                if (reg && a.step_len <= 8 * SEL_THREADS) k_select_dense<8><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
-                else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16><<<(unsigned)rows, SEL_THREADS, 0, cur_stream(ctx)>>>(a);
+                // rows of <= 2 048 values: 128-thread CTAs (six rows resident per SM: the kernel is latency-bound per row)
+                if (reg && a.step_len <= 16 * 128) k_select_dense<16, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
+                else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16, 256><<<(unsigned)rows, 256, 0, cur_stream(ctx)>>>(a);
                 else if (!dense && ctx->smallSelect && a.kept_n + 4 * t + 64 <= 1024) {
                     // small tails (t ~ 100): a 64-thread CTA per row, a staging area to match (rows beyond it take the
                     // global-memory path): a dozen rows resident per SM instead of four
