@@ -1547,6 +1547,229 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
     for (int i = tid; i < (int)T; i += FE_THREADS) gout[i] = a.app ? bswap32(s_out[i]) : s_out[i];
 }
 
+// ------------------------------------------------------------------------------------------------ FastPFOR, decode
+// Inverse of k_fp_encode_fast for the same shapes (one page per list).  One thread per list parses the page header, the
+// exception-stream table and the per-block byte metadata (the serial part: positions depend on the widths before
+// them); one thread per 32-value group unpacks; the exceptions of a block are patched in by its group threads, strided;
+// the VariableByte tail (up to block-1 values) goes through the warp-cooperative terminator-popcount routine; the
+// Delta prefix is a three-level scan (inside the group, over a list's groups, over its tail).
+struct SmemSrc {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t get(int64_t j) const { return w[j]; }
+};
+struct SwzOut { // value i of a tail -> its 33-stride slot in the staged batch
+    uint32_t *s_val;
+    int base;
+    __device__ __forceinline__ void operator()(int64_t i, uint32_t v) const { s_val[sw33(base + (int)i)] = v; }
+};
+
+template <int BG>
+__global__ void __launch_bounds__(FE_THREADS, 6) k_fp_decode_fast(const FastDecArgs a)
+{
+    constexpr int B = BG * 32;
+    __shared__ uint32_t s_val[FE_VPAD];
+    __shared__ uint32_t s_wd[FE_OCAP];
+    __shared__ int s_in[FP_MAXL + 1], s_oo[FP_MAXL + 1], s_fb[FP_MAXL + 1];
+    __shared__ int s_page[FP_MAXL], s_meta[FP_MAXL], s_tp[FP_MAXL]; // word of the page / of its metadata bytes / of the VByte tail, in s_wd
+    __shared__ uint16_t s_sbase[FP_MAXL][33];                       // first packed word of stream k, relative to the page
+    __shared__ uint8_t s_bb[FP_MAXBLK], s_bc[FP_MAXBLK], s_bk[FP_MAXBLK], s_bl[FP_MAXBLK];
+    __shared__ uint16_t s_bpw[FP_MAXBLK], s_bmo[FP_MAXBLK], s_bsp[FP_MAXBLK];
+    __shared__ uint32_t s_gt[FE_THREADS]; // sum of each group's values (Delta)
+    __shared__ uint32_t s_gc[FE_THREADS]; // carry into each group
+    __shared__ uint32_t s_tc[FP_MAXL];    // carry into each tail
+    __shared__ int s_scan[8];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t l0 = (int64_t)blockIdx.x * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    const int64_t ibase = a.in_off[l0], obase = a.out_off[l0];
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int j = tid; j <= nl; j += FE_THREADS) {
+        const int64_t ib = a.in_off[l0 + j] - ibase, ob = a.out_off[l0 + j] - obase;
+        if ((a.in_off[l0 + j] & 3) != 0) s_bad = 1;
+        s_in[j] = (int)((ib >> 2) > 0x7fffffff ? 0x7fffffff : (ib >> 2));
+        s_oo[j] = (int)(ob > 0x7fffffff ? 0x7fffffff : ob);
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) atomicExch(a.err, 1); return; }
+    const int nw = s_in[nl], nv = s_oo[nl];
+    int nblk = 0;
+    const int my_n = tid < nl ? s_oo[tid + 1] - s_oo[tid] : 0;
+    const int my_nb = my_n / B;
+    const int my_fb = cta_excl_scan(my_nb, s_scan, &nblk);
+    if (tid < nl) s_fb[tid] = my_fb;
+    if (tid == 0) s_fb[nl] = nblk;
+    if (nw > FE_OCAP || nv > FE_VCAP || nl > FP_MAXL || nblk > FP_MAXBLK) { // not this kernel's shape: the host reruns the call
+        if (tid == 0) atomicMax(a.err, 2);
+        return;
+    }
+    const uint32_t *gin = reinterpret_cast<const uint32_t *>(a.in + ibase);
+    for (int i = tid; i < nw; i += FE_THREADS) { const uint32_t x = __ldg(gin + i); s_wd[i] = a.app ? bswap32(x) : x; }
+    __syncthreads();
+    // ---- one thread per list: page header, stream table, block metadata (FastPFOR.decodePage, FastPFOR.java:233-307)
+    if (tid < nl) {
+        const int avail = s_in[tid + 1] - s_in[tid] - (a.app ? 1 : 0); // the loader's trailing zero int is not part of the stream
+        const uint32_t *w = s_wd + s_in[tid];
+        bool ok = true;
+        int p = 0;
+        if (my_n > 0) {
+            ok = avail >= 1 && w[0] == (uint32_t)(my_nb * B);
+            p = 1;
+            if (ok && my_nb > 0) {
+                const uint32_t *page = w + 1;
+                const int pav = avail - 1;
+                const int where_meta = pav >= 3 ? (int)page[0] : -1;
+                ok = where_meta >= 1 && where_meta < pav;
+                int bytesize = 0, mw = 0, q = 0;
+                if (ok) {
+                    bytesize = (int)page[where_meta];
+                    mw = (bytesize + 3) >> 2;
+                    q = where_meta + 1 + mw;
+                    ok = bytesize >= 0 && q < pav;
+                }
+                uint16_t ssize[33];
+                if (ok) {
+                    const uint32_t bitmap = page[q++];
+                    for (int k = 2; k <= 32; ++k) {
+                        ssize[k] = 0;
+                        s_sbase[tid][k] = 0;
+                        if (ok && (bitmap & (1u << (k - 1)))) {
+                            if (q >= pav) { ok = false; break; }
+                            const uint32_t size = page[q];
+                            if (size > 65535u) { ok = false; break; }
+                            ssize[k] = (uint16_t)size;
+                            s_sbase[tid][k] = (uint16_t)(q + 1);
+                            q += 1 + (int)((size * (uint32_t)k + 31u) >> 5);
+                        }
+                    }
+                    ok = ok && q <= pav;
+                }
+                if (ok) {
+                    const uint8_t *meta = reinterpret_cast<const uint8_t *>(page + where_meta + 1);
+                    uint16_t cnt[33];
+#pragma unroll
+                    for (int k = 0; k < 33; ++k) cnt[k] = 0;
+                    int mpos = 0, pw = 1;
+                    for (int blk = 0; blk < my_nb; ++blk) {
+                        const int b_ = my_fb + blk;
+                        if (mpos + 2 > bytesize) { ok = false; break; }
+                        const int b = meta[mpos], c = meta[mpos + 1];
+                        if (b > 32 || pw + BG * b > where_meta) { ok = false; break; }
+                        int k = 0;
+                        if (c > 0) {
+                            if (mpos + 3 + c > bytesize) { ok = false; break; }
+                            k = meta[mpos + 2] - b;
+                            if (k < 1 || k > 32 || b + k > 32) { ok = false; break; }
+                            if (k >= 2 && cnt[k] + c > ssize[k]) { ok = false; break; }
+                        }
+                        s_bl[b_] = (uint8_t)tid; s_bb[b_] = (uint8_t)b; s_bc[b_] = (uint8_t)c; s_bk[b_] = (uint8_t)k;
+                        s_bpw[b_] = (uint16_t)pw; s_bmo[b_] = (uint16_t)mpos; s_bsp[b_] = cnt[k];
+                        pw += BG * b;
+                        if (c > 0) { cnt[k] += (uint16_t)c; mpos += 3 + c; } else mpos += 2;
+                    }
+                    s_page[tid] = s_in[tid] + 1;
+                    s_meta[tid] = s_in[tid] + 1 + where_meta + 1;
+                    p = 1 + q;
+                }
+            }
+        }
+        s_tp[tid] = p;
+        if (!ok) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) atomicExch(a.err, 1); return; }
+    // ---- VariableByte tails: a warp per list
+    for (int j = warp; j < nl; j += FE_THREADS / 32) {
+        const int n = s_oo[j + 1] - s_oo[j], r = n - (n / B) * B;
+        if (r == 0) continue;
+        const int avail = s_in[j + 1] - s_in[j] - (a.app ? 1 : 0);
+        const SmemSrc src{s_wd + s_in[j]};
+        const SwzOut put{s_val, s_oo[j] + (n / B) * B};
+        if (!warp_vb_decode_to<false>(src, s_tp[j], avail, r, put, 0u, lane) && lane == 0) s_bad = 1;
+    }
+    // ---- one thread per 32-value group: fastunpack
+    const int bi = tid / BG, g = tid % BG;
+    const bool have = bi < nblk;
+    int my_start = 0;
+    if (have) {
+        const int j = s_bl[bi], b = s_bb[bi];
+        my_start = s_oo[j] + (bi - s_fb[j]) * B + g * 32;
+        const uint32_t *ptr = s_wd + s_page[j] + s_bpw[bi] + g * b;
+        if (b == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s_val[sw33(my_start + i)] = ptr[i];
+        } else {
+            const uint32_t mask = (1u << b) - 1u;
+            uint64_t acc = 0;
+            int fill = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (fill < b) { acc |= (uint64_t)(*ptr++) << fill; fill += 32; }
+                s_val[sw33(my_start + i)] = (uint32_t)acc & mask;
+                acc >>= b;
+                fill -= b;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) atomicExch(a.err, 1); return; }
+    // ---- exceptions: the BG group threads of a block share its list, strided (FastPFOR.java:283-300)
+    if (have && s_bc[bi] > 0) {
+        const int j = s_bl[bi], b = s_bb[bi], c = s_bc[bi], k = s_bk[bi];
+        const uint8_t *pos = reinterpret_cast<const uint8_t *>(s_wd + s_meta[j]) + s_bmo[bi] + 3;
+        const uint32_t *sw = s_wd + s_page[j] + s_sbase[j][k < 2 ? 2 : k];
+        const int blk_start = s_oo[j] + (bi - s_fb[j]) * B, spos = s_bsp[bi];
+        for (int e = g; e < c; e += BG) {
+            const int ps = pos[e];
+            if (ps >= B) continue;
+            uint32_t hi = 1u;
+            if (k >= 2) {
+                const int bit = (spos + e) * k, w = bit >> 5, sh = bit & 31;
+                const uint32_t lo = sw[w], hw = (sh + k > 32) ? sw[w + 1] : 0u;
+                hi = __funnelshift_r(lo, hw, sh);
+                if (k < 32) hi &= (1u << k) - 1u;
+            }
+            s_val[sw33(blk_start + ps)] |= hi << b;
+        }
+    }
+    __syncthreads();
+    if (a.delta) { // Delta.inverseDelta over each list: inside the groups, over the groups, over the tail
+        if (have) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { run += s_val[sw33(my_start + i)]; s_val[sw33(my_start + i)] = run; }
+            s_gt[tid] = run;
+        }
+        __syncthreads();
+        if (tid < nl) {
+            uint32_t carry = 0;
+            for (int it = my_fb * BG; it < (my_fb + my_nb) * BG; ++it) { s_gc[it] = carry; carry += s_gt[it]; }
+            s_tc[tid] = carry;
+        }
+        __syncthreads();
+        if (have) {
+            const uint32_t c = s_gc[tid];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s_val[sw33(my_start + i)] += c;
+        }
+        for (int j = warp; j < nl; j += FE_THREADS / 32) {
+            const int n = s_oo[j + 1] - s_oo[j], m = (n / B) * B, r = n - m;
+            uint32_t run = s_tc[j];
+            for (int base = 0; base < r; base += 32) {
+                const int i = base + lane, o = sw33(s_oo[j] + m + i);
+                const uint32_t x = i < r ? s_val[o] : 0u;
+                const uint32_t incl = warp_incl_scan(x, lane) + run;
+                if (i < r) s_val[o] = incl;
+                run = __shfl_sync(kFull, incl, 31);
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t *gout = a.out + obase;
+    for (int i = tid; i < nv; i += FE_THREADS) gout[i] = s_val[sw33(i)];
+}
+
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
 // block, then a second sweep.  Sizes here are "number of lists": bookkeeping, not hot.
@@ -1662,12 +1885,12 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     return (int)g;
 }
 
-// encode: BinaryPacking family and FastPFOR / FastPFOR128; decode: BinaryPacking family
 bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, bool encode)
 {
     const int codec = codec_id & MCP_CODEC_MASK;
     const bool delta = (codec_id & MCP_FLAG_DELTA) != 0;
-    const bool ok = fast_codec_ok(codec, delta) || (encode && codec_traits(codec).fastpfor);
+    (void)encode; // both directions: BinaryPacking family and FastPFOR / FastPFOR128
+    const bool ok = fast_codec_ok(codec, delta) || codec_traits(codec).fastpfor;
     return ok && fast_lists_per_batch(codec, total_vals, nlists) > 0;
 }
 
@@ -1753,12 +1976,17 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
     {
         KScope ks(ctx, MCP_K_DECODE);
-        k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        MCP_TRY(check_launch(ctx, "k_bp_decode_fast"));
+        const CodecTraits tr = codec_traits(a.codec);
+        if (!tr.fastpfor) k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        else if (tr.fp_block == 256) k_fp_decode_fast<8><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        else k_fp_decode_fast<4><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+        MCP_TRY(check_launch(ctx, "k_decode_fast"));
     }
     MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dErr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*reinterpret_cast<int *>(ctx->hPinned) != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
+    const int flag = *reinterpret_cast<int *>(ctx->hPinned);
+    if (flag == 2) return MCP_E_UNSUPPORTED; // a batch did not fit the FastPFOR kernel: the caller takes the warp-per-list kernel
+    if (flag != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
     return MCP_OK;
 }
 

@@ -230,8 +230,10 @@ int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing, const uint8_t 
         MCP_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hPinned) + 8, d_out_off + nlists, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const int64_t tv = reinterpret_cast<int64_t *>(ctx->hPinned)[1] - reinterpret_cast<int64_t *>(ctx->hPinned)[0];
-        if (tv >= 0 && codec_fast_applicable(codec_id, tv, nlists, false))
-            return codec_fast_decode(ctx, codec_id, framing, d_in, d_in_off, nlists, tv, d_out, d_out_off);
+        if (tv >= 0 && codec_fast_applicable(codec_id, tv, nlists, false)) {
+            const int rc = codec_fast_decode(ctx, codec_id, framing, d_in, d_in_off, nlists, tv, d_out, d_out_off);
+            if (rc != MCP_E_UNSUPPORTED) return rc;
+        }
     }
     return codec_decode_device(ctx, codec_id, framing, d_in, d_in_off, nlists, d_out, d_out_off);
 }
@@ -318,12 +320,14 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *in,
     MCP_TRY(h2d(ctx, ctx->dIo0.p, in, (size_t)in_bytes));
     MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, (size_t)(nlists + 1) * sizeof(int64_t)));
     MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    int rc = MCP_E_UNSUPPORTED;
     if (ctx->fastCodec && (framing == MCP_FRAME_WORDS || framing == MCP_FRAME_APP) && codec_fast_applicable(codec_id, out_n, nlists, false))
-        MCP_TRY(codec_fast_decode(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists, out_n,
-                                  ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
-    else
-        MCP_TRY(codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists,
-                                    ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>()));
+        rc = codec_fast_decode(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists, out_n,
+                               ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>());
+    if (rc == MCP_E_UNSUPPORTED)
+        rc = codec_decode_device(ctx, codec_id, framing, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists,
+                                 ctx->dIo2.as<int32_t>(), ctx->dIo3.as<int64_t>());
+    MCP_TRY(rc);
     MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)out_n * sizeof(int32_t)));
     return sync(ctx);
 }

@@ -185,6 +185,28 @@ def test_fast_kernels_are_the_ones_that_run(ctx):
         assert bytes(out[out_off[i]: out_off[i + 1]]) == cref.compress(cid, lists[i]).tobytes(), i
 
 
+def test_fastpfor_fast_decode_rejects_malformed_pages(ctx):
+    rng = np.random.default_rng(8)
+    vals, off = cases.breach_like_lists(rng, 50, 100000, 0.01)      # ~1 000 ints per list: FastPFOR pages
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off)
+    assert np.array_equal(ctx.codec_decode(cid, N.FRAME_WORDS, out, out_off, off), vals)
+    w = out.view(np.uint32)
+    for what in ("where_meta", "block width", "header"):
+        bad = w.copy()
+        p0 = out_off[7] // 4
+        if what == "where_meta":
+            bad[p0 + 1] = 0x7fffffff                      # page[0] points outside the list
+        elif what == "block width":
+            wm = int(w[p0 + 1])
+            bad[p0 + 1 + wm + 1] = (bad[p0 + 1 + wm + 1] & 0xffffff00) | 77  # first metadata byte: b = 77 > 32
+        else:
+            bad[p0] = 256 * 17                            # Composition header disagrees with the list length
+        with pytest.raises(mcp_b200.McpError) as e:
+            ctx.codec_decode(cid, N.FRAME_WORDS, bad.view(np.uint8), out_off, off)
+        assert e.value.code == N.MCP_E_FORMAT, what
+
+
 def test_multipage_fastpfor(ctx):
     """> 65 536 ints: FastPFOR pages (FastPFOR.java:98-102), including the stale exception-buffer padding that a
     Java instance carries from page to page (FastPFOR.java:143): bytes identical to the oracle's emulation."""
