@@ -93,6 +93,7 @@ struct mcp_ctx {
     mcp::DevBuf dFbE, dFbOut, dFbKey, dFbIdx; // fallback problem (failed rows, guaranteed schedule)
     bool optimistic = true;        // two-step schedule with the optimistic filter bound (risk_kernels.cu)
     int64_t itemTrials = 2048;     // target trials per valuation CTA work item (amortises the exposure-tile prologue)
+    bool failPending = false;      // the optimistic run's failed-row count is in flight to hPinned + 64
     int64_t runFallbackRows = 0;   // rows the last run had to redo with the guaranteed schedule
     // trial-sharded mode (risk_kernels.cu): state between the phase calls
     int64_t tsT = 0, tsM = 0, tsNGlobal = 0, tsTrialBase = 0, tsNFlag = 0, tsSlackOverride = -1;

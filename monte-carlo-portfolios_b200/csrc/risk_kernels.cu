@@ -2120,40 +2120,44 @@ static int risk_run_stream(mcp_ctx *ctx, int64_t t)
         MCP_TRY(check_launch(ctx, "k_moments_finalize"));
     }
     ctx->runFallbackRows = 0;
+    ctx->failPending = false;
     if (optimistic) {
-        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, fail_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const int64_t nf = *reinterpret_cast<int *>(ctx->hPinned);
-        ctx->runFallbackRows = nf;
-        if (nf > 0) {
-            // redo the failed rows with the guaranteed schedule on a compact copy of their exposures
-            const int F = ctx->F;
-            MCP_CUDA(ctx, ctx->dFbE.reserve((size_t)nf * F * sizeof(double)));
-            MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)nf * (3 * sizeof(double) + (size_t)(t + 1) * sizeof(int32_t)) + 64));
-            MCP_CUDA(ctx, ctx->dFbKey.reserve((size_t)nf * t * 2 * sizeof(uint64_t)));
-            MCP_CUDA(ctx, ctx->dFbIdx.reserve((size_t)nf * t * 2 * sizeof(int32_t)));
-            {
-                KScope ks(ctx, MCP_K_SELECT);
-                k_gather_rows<<<(unsigned)std::min<int64_t>((nf * F + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), fail_rows, nf, F,
-                                                                                                              ctx->dFbE.as<double>());
-                MCP_TRY(check_launch(ctx, "k_gather_rows"));
-            }
-            StreamIO fb{};
-            fb.E = ctx->dFbE.as<double>(); fb.P = nf;
-            // dFbOut: [var_loss nf f64][cvar nf f64][tkey nf u64][breach nf*t i32][var_trial nf i32]
-            double *o = ctx->dFbOut.as<double>();
-            fb.var_loss = o; fb.cvar = o + nf; fb.tkey = reinterpret_cast<uint64_t *>(o + 2 * nf);
-            fb.breach = reinterpret_cast<int32_t *>(o + 3 * nf); fb.var_trial = fb.breach + nf * t;
-            fb.kkey[0] = ctx->dFbKey.as<uint64_t>(); fb.kkey[1] = fb.kkey[0] + nf * t;
-            fb.kidx[0] = ctx->dFbIdx.as<int32_t>(); fb.kidx[1] = fb.kidx[0] + nf * t;
-            MCP_TRY(risk_stream_core(ctx, fb, t, false, nullptr));
-            KScope ks(ctx, MCP_K_SELECT);
-            k_scatter_rows<<<(unsigned)nf, 128, 0, ctx->stream>>>(fail_rows, t, fb.var_loss, fb.var_trial, fb.cvar, fb.breach, io.var_loss,
-                                                                 io.var_trial, io.cvar, io.breach);
-            MCP_TRY(check_launch(ctx, "k_scatter_rows"));
-        }
+        // The count of rows that lost the bet is read LATER, together with the encoded size (risk_run_inner): the
+        // encode is enqueued speculatively, so the common case (no such row) has no host round trip in the middle.
+        MCP_CUDA(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->hPinned) + 64, fail_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->failPending = true;
     }
     return MCP_OK;
+}
+
+// redo the rows whose optimistic bound was too tight with the guaranteed schedule on a compact copy of their exposures
+static int risk_stream_fallback(mcp_ctx *ctx, int64_t t, int64_t nf)
+{
+    const int F = ctx->F;
+    int32_t *fail_rows = ctx->dFail.as<int32_t>() + 4;
+    MCP_CUDA(ctx, ctx->dFbE.reserve((size_t)nf * F * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dFbOut.reserve((size_t)nf * (3 * sizeof(double) + (size_t)(t + 1) * sizeof(int32_t)) + 64));
+    MCP_CUDA(ctx, ctx->dFbKey.reserve((size_t)nf * t * 2 * sizeof(uint64_t)));
+    MCP_CUDA(ctx, ctx->dFbIdx.reserve((size_t)nf * t * 2 * sizeof(int32_t)));
+    {
+        KScope ks(ctx, MCP_K_SELECT);
+        k_gather_rows<<<(unsigned)std::min<int64_t>((nf * F + 255) / 256, 4096), 256, 0, ctx->stream>>>(ctx->dE.as<double>(), fail_rows, nf, F,
+                                                                                                      ctx->dFbE.as<double>());
+        MCP_TRY(check_launch(ctx, "k_gather_rows"));
+    }
+    StreamIO fb{};
+    fb.E = ctx->dFbE.as<double>(); fb.P = nf;
+    // dFbOut: [var_loss nf f64][cvar nf f64][tkey nf u64][breach nf*t i32][var_trial nf i32]
+    double *o = ctx->dFbOut.as<double>();
+    fb.var_loss = o; fb.cvar = o + nf; fb.tkey = reinterpret_cast<uint64_t *>(o + 2 * nf);
+    fb.breach = reinterpret_cast<int32_t *>(o + 3 * nf); fb.var_trial = fb.breach + nf * t;
+    fb.kkey[0] = ctx->dFbKey.as<uint64_t>(); fb.kkey[1] = fb.kkey[0] + nf * t;
+    fb.kidx[0] = ctx->dFbIdx.as<int32_t>(); fb.kidx[1] = fb.kidx[0] + nf * t;
+    MCP_TRY(risk_stream_core(ctx, fb, t, false, nullptr));
+    KScope ks(ctx, MCP_K_SELECT);
+    k_scatter_rows<<<(unsigned)nf, 128, 0, ctx->stream>>>(fail_rows, t, fb.var_loss, fb.var_trial, fb.cvar, fb.breach, ctx->dVarLoss.as<double>(),
+                                                         ctx->dVarTrial.as<int32_t>(), ctx->dCvar.as<double>(), ctx->dBreach.as<int32_t>());
+    return check_launch(ctx, "k_scatter_rows");
 }
 
 // breach lists of uniform length t -> CSR of encoded lists: the single-pass batched kernels when the codec and the list
@@ -2669,7 +2673,20 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));
     int64_t total = 0;
-    MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), t, P, ctx->dEncOff, ctx->dEnc, &total));
+    MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), t, P, ctx->dEncOff, ctx->dEnc, &total)); // (synchronises)
+    if (ctx->failPending) {
+        ctx->failPending = false;
+        const int64_t nf = *reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 64);
+        ctx->runFallbackRows = nf;
+        if (nf > 0) { // rare: some rows lost the optimistic bet -- redo them exactly, then encode again
+            MCP_TRY(risk_stream_fallback(ctx, t, nf));
+            if (ctx->earlyBreachDst) { // the raw lists already left for the host under the first encode: send the repaired ones
+                MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+                MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), t, P, ctx->dEncOff, ctx->dEnc, &total));
+        }
+    }
     ctx->runP = P;
     ctx->runRow0 = 0;
     ctx->runN = N;
