@@ -953,6 +953,11 @@ __global__ void __launch_bounds__(THREADS) k_select_t(const SelArgs a)
     int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // a row that already lost its optimistic bet at an earlier step stays lost (it is redone separately)
+    if (a.kept_n > 0 && a.kept_segs <= 1 && a.kept_idx_in[row * a.kept_n] < 0) {
+        if (tid == 0) ki[0] = -1;
+        return;
+    }
     // ---- moments of the dense row with shift c = V[0] (generic path only)
     if (a.moments_n > 0) {
         const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
@@ -1675,7 +1680,14 @@ static std::vector<Step> make_schedule(int64_t N, int64_t t, int64_t nsg, int sm
     int64_t b = 0, len = c0;
     while (b < N) {
         int64_t e = b + len;
-        if (e > N || (b > 0 && (two_step || N - e < len / 4))) e = N; // fold a short remainder into the last (sparse) step
+        if (two_step && b > 0) {
+            // optimistic schedule: one sparse step over the rest -- unless the sample's share of the tail is so thin
+            // (t n0 / N < 16: trial-sharded runs, very high confidence levels) that its bound would let several tail
+            // sizes through; then a middle step up to ~64 N / t trials tightens it first (see optimistic_rank)
+            e = N;
+            const int64_t mid = (64 * N / (t > 0 ? t : 1) + 7) & ~(int64_t)7;
+            if (steps.size() == 1 && t * b < 16 * N && mid > 2 * b && mid <= N / 8) e = mid;
+        } else if (e > N || (b > 0 && N - e < len / 4)) e = N; // fold a short remainder into the last (sparse) step
         const int64_t L = e - b;
         // the short dense step wants small work items (two or three full waves of CTAs instead of a part-filled one)
         const int64_t item = (b == 0 && steps_hint_two(two_step, N, e)) ? std::min<int64_t>(kItemTrials, 512) : kItemTrials;
@@ -2042,7 +2054,7 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
             a.kept_idx_out = kidx[cur ^ 1];
             // optimistic schedule: the dense step keeps only the top `rank0` of the sample (its rank0-th largest loss
             // is the bound of the one sparse step); every other selection keeps the full tail
-            a.tail = (optimistic && dense && steps.size() > 1) ? rank0 : t;
+            a.tail = (optimistic && si + 1 < steps.size()) ? (dense ? rank0 : optimistic_rank(N, s.end, t)) : t;
             a.moments_n = 0;
             a.var_loss = io.var_loss + p0;
             a.var_trial = io.var_trial + p0;

@@ -151,6 +151,21 @@ def test_large_tails_take_the_wide_selection_kernels(ctx):
         assert ctx.run_stats()["fallback_rows"] == 0
 
 
+def test_thin_samples_take_a_middle_step(ctx):
+    """Many trials per tail element (t n0 / N < 16): the optimistic schedule inserts a middle step that tightens the
+    bound before the long final step; adversarial orders still fall back exactly."""
+    E, S = riskcases.synthetic(10, 1_000_000, 32, 93)
+    check_against_oracle(ctx, E, S, 0.999)                      # t = 1001 of 10^6: ts(4096) = 4.1 -> middle step at 64 000
+    assert ctx.run_stats()["fallback_rows"] == 0
+    Nn = 600_000
+    S2 = np.zeros((Nn, 32))
+    S2[:, 0] = np.linspace(0.0, 1.0, Nn)                         # descending losses: every row loses the bet at the middle step
+    S2[:, 1] = 1e-3 * np.cos(np.arange(Nn))
+    E2 = np.abs(riskcases.synthetic(6, 1, 32, 3)[0]) + 1.0
+    check_against_oracle(ctx, E2, S2, 0.999)
+    assert ctx.run_stats()["fallback_rows"] == 6
+
+
 def test_ties_break_by_trial_index(ctx):
     E, S = riskcases.with_ties(20, 3000, 4, 9)
     check_against_oracle(ctx, E, S, 0.9)
