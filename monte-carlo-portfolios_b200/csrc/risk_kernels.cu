@@ -1605,7 +1605,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap_t(const uint64_
     if (tid == 0) cvar[row] = s / (double)t;
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
+template <int FIN_THREADS>
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_t(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t,
                                                           int m /* pow2 >= t */, int32_t *breach, double *cvar,
                                                           uint64_t *gkey /* global scratch or null */, int32_t *gidx)
 {
@@ -1733,11 +1734,14 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
         MCP_CUDA(ctx, ctx->dFinKey.reserve((size_t)rows * m * sizeof(uint64_t)));
         MCP_CUDA(ctx, ctx->dFinIdx.reserve((size_t)rows * m * sizeof(int32_t)));
     } else if (fin_smem > 40 * 1024) { // static shared memory counts against the 48 KB default as well
-        MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+        MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_t<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     }
     KScope ks(ctx, MCP_K_SELECT);
-    k_finalize<<<(unsigned)rows, FIN_THREADS, fin_global ? 0 : fin_smem, cur_stream(ctx)>>>(
-        kk, ki, t, m, breach, cvar, fin_global ? ctx->dFinKey.as<uint64_t>() : nullptr, fin_global ? ctx->dFinIdx.as<int32_t>() : nullptr);
+    uint64_t *gk = fin_global ? ctx->dFinKey.as<uint64_t>() : nullptr;
+    int32_t *gi = fin_global ? ctx->dFinIdx.as<int32_t>() : nullptr;
+    if (m >= 8192) k_finalize_t<1024><<<(unsigned)rows, 1024, fin_global ? 0 : fin_smem, cur_stream(ctx)>>>(kk, ki, t, m, breach, cvar, gk, gi); // >= 96 KB: one CTA per SM
+    else k_finalize_t<256><<<(unsigned)rows, 256, fin_global ? 0 : fin_smem, cur_stream(ctx)>>>(kk, ki, t, m, breach, cvar, gk, gi);
     return check_launch(ctx, "k_finalize");
 }
 
@@ -2449,7 +2453,8 @@ static int ts_merge_rows(mcp_ctx *ctx, const unsigned char *gath, int world, con
     a.cap = (int)cap;
     MCP_CUDA(ctx, sel_configure((int)sel_smem_bytes(16384, kSelMaxSeg)));
     KScope ks(ctx, MCP_K_SELECT);
-    k_select_t<256><<<(unsigned)rows, 256, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a);
+    if (sel_smem_bytes(a.cap, 0) > 110 * 1024) k_select_t<1024><<<(unsigned)rows, 1024, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a); // one CTA per SM: make it wide
+    else k_select_t<256><<<(unsigned)rows, 256, sel_smem_bytes(a.cap, 0), ctx->stream>>>(a);
     return check_launch(ctx, "k_select (merge)");
 }
 

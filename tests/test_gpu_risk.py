@@ -149,6 +149,11 @@ def test_large_tails_take_the_wide_selection_kernels(ctx):
     for alpha in (0.95, 0.9, 0.6):
         check_against_oracle(ctx, E, S, alpha, rows=[0, 11, 23])
         assert ctx.run_stats()["fallback_rows"] == 0
+    ctx.set_option("force_sort_finalize", 1)        # the sort-based breach list with 1 024-thread CTAs (tails >= 4 097)
+    try:
+        check_against_oracle(ctx, E, S, 0.93, rows=[0, 11, 23])
+    finally:
+        ctx.set_option("force_sort_finalize", 0)
 
 
 def test_thin_samples_take_a_middle_step(ctx):
