@@ -137,6 +137,11 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing,
 /* diagnostics: encode calls served by the batched single-pass kernels since the context was created, and calls those
  * kernels handed back to the warp-per-list kernels because a batch did not fit their staging areas */
 int mcp_codec_stats(mcp_ctx *ctx, int64_t *fast_encodes, int64_t *fast_fallbacks);
+/* same for the thread-per-list kernels that take lists averaging <= 144 values (BASELINE config C4's ~100-int breach
+ * lists): encode + decode calls they served, and calls they handed on to the batched kernels because a list did not
+ * fit (a FastPFOR list of a block or more, or more than 64 compressed words).  mcp_set_option("short_list_codec", 0)
+ * turns them off. */
+int mcp_codec_stats_short(mcp_ctx *ctx, int64_t *short_calls, int64_t *short_fallbacks);
 
 /* ----------------------------------------------------- batched codec, device
  * Same, but every pointer is a DEVICE pointer on ctx's GPU (for callers whose lists

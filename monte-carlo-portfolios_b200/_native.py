@@ -75,6 +75,7 @@ def lib() -> C.CDLL:
         "mcp_codec_encode": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp, i64, P(i64)]),
         "mcp_codec_decode": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp]),
         "mcp_codec_stats": (C.c_int, [vp, P(i64), P(i64)]),
+        "mcp_codec_stats_short": (C.c_int, [vp, P(i64), P(i64)]),
         "mcp_codec_encode_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, i64, vp, vp, i64, P(i64)]),
         "mcp_codec_decode_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp]),
         "mcp_upload_exposures": (C.c_int, [vp, vp, i64, i32]),

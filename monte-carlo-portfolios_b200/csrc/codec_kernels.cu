@@ -1770,6 +1770,361 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_decode_fast(const FastDecA
     for (int i = tid; i < nv; i += FE_THREADS) gout[i] = s_val[sw33(i)];
 }
 
+// ============================================================ short-list path: one THREAD per list
+// Lists of ~100 ints (BASELINE config C4: 1 % of 10 000 trials) spend the batched kernels above on bookkeeping: block
+// items, tail tables, four CTA-wide scans and a dozen CTA barriers per batch -- 2.3 warp instructions per integer, 40 %
+// of the stall samples at a barrier.  Here a WARP owns 32 consecutive lists and a THREAD owns one list from its first
+// value to its last word, so every piece of list state (position, width headers, the VariableByte byte accumulator,
+// the running value of the Delta / integrated chain) is a register and nothing ever waits on another warp:
+//   * values arrive 32 per list per round: the warp loads 128 contiguous bytes of list j and stores them TRANSPOSED
+//     (value i of list j at word 33 i + j): coalesced in global memory, conflict-free in shared memory both ways;
+//   * thread j packs its block (or VariableByte-encodes its tail values) of the round into its column of a transposed
+//     output area (word w of list j at 33 w + j), again conflict-free;
+//   * the 32 list sizes are scanned with shuffles, the batch takes its place in the output by the same decoupled
+//     look-back as above (one state word per warp batch), and the lists leave with coalesced stores.
+// Decode mirrors it.  A batch whose lists do not fit the SL_OC-word columns takes the warp-per-list routines inside the
+// same kernel (BinaryPacking family) or raises flag 2 (FastPFOR lists of a block or more, long VariableByte lists), and
+// the host then takes the batched kernels above.  Codecs: every id; FastPFOR / FastPFOR128 only while a list is
+// shorter than one block (Composition.java:45-48 writes the 0 marker and the whole list goes to VariableByte).
+constexpr int SL_WARPS = 2;      // warps per CTA (independent of each other)
+constexpr int SL_OC = 64;        // words of one list's compressed stream that fit its column
+constexpr int SL_CTAS = 8;       // resident CTAs per SM (25 KB of shared memory each)
+constexpr double SL_MAXAVG = 144.0; // lists averaging more values go to the thread-per-block kernels
+
+__host__ __device__ inline bool sl_codec_ok(int codec, bool delta)
+{
+    const CodecTraits t = codec_traits(codec);
+    return !(t.integrated && delta);
+}
+
+// 7-bit groups of d spread over the low bytes of a 64-bit word, terminator bit on byte len-1 (VariableByte.java:44-68)
+__device__ __forceinline__ uint64_t vb_spread(uint32_t d, int len)
+{
+    const uint32_t lo = (d & 0x7fu) | ((d & 0x3f80u) << 1) | ((d & 0x1fc000u) << 2) | ((d & 0xfe00000u) << 3);
+    return (((uint64_t)(d >> 28) << 32) | lo) | (0x80ull << (8 * (len - 1)));
+}
+
+__global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const FastEncArgs a)
+{
+    __shared__ uint32_t s_inw[SL_WARPS][32 * 33];
+    __shared__ uint32_t s_outw[SL_WARPS][SL_OC * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *s_in = s_inw[warp];
+    uint32_t *my_out = s_outw[warp] + lane; // word w of my list: my_out[33 * w]
+    const CodecTraits tr = codec_traits(a.codec);
+    const bool diff = a.delta || tr.integrated;
+    for (;;) {
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
+        tk = __shfl_sync(kFull, tk, 0);
+        if ((int64_t)tk >= a.nbatches) break;
+        __syncwarp(); // the previous batch's columns have been read
+        const int64_t batch = (int64_t)tk, l0 = batch * 32;
+        const int nl = (int)min((int64_t)32, a.nlists - l0);
+        int64_t beg = 0, n64 = 0;
+        if (lane < nl) {
+            beg = a.list_off ? a.list_off[l0 + lane] : (l0 + lane) * a.uniform_len;
+            n64 = (a.list_off ? a.list_off[l0 + lane + 1] : (l0 + lane + 1) * a.uniform_len) - beg;
+        }
+        const int64_t vbase = __shfl_sync(kFull, beg, 0);
+        const bool big = lane < nl && (beg - vbase > 0x3fffffff || n64 > 0x3fffffff || (tr.fastpfor && n64 >= tr.fp_block));
+        bool ovf = __any_sync(kFull, big);
+        const int off = ovf ? 0 : (int)(beg - vbase), n = ovf ? 0 : (int)n64;
+        const int nb = tr.blocks ? n >> 5 : 0, ng4 = nb & ~3;
+        int pos = 0;
+        if (!ovf) {
+            // IntCompressor: compressed[0] = n; Composition: the first stage's header, 0 when it wrote nothing
+            if (tr.sk) { my_out[0] = (uint32_t)n; pos = 1; }
+            else if (n > 0 && (tr.fastpfor || tr.blocks)) { my_out[0] = (uint32_t)(32 * nb); pos = 1; }
+            uint32_t prev = 0, hdrw = 0;
+            int hpos = 0, vfill = 0;
+            uint64_t vacc = 0;
+            const int maxn = __reduce_max_sync(kFull, n);
+            const uint32_t *gv = a.vals + vbase;
+            for (int k = 0; 32 * k < maxn && !ovf; ++k) {
+                __syncwarp();
+                // ---- stage values [32k, 32k + 32) of every list, transposed
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int oj = __shfl_sync(kFull, off, j), nj = __shfl_sync(kFull, n, j);
+                    const int idx = 32 * k + lane;
+                    if (idx < nj) s_in[lane * 33 + j] = __ldg(gv + oj + idx);
+                }
+                __syncwarp();
+                const uint32_t *col = s_in + lane; // value i of my list in this round: col[33 * i]
+                const int c = min(32, n - 32 * k);
+                bool t_ovf = false;
+                if (k < nb) {
+                    // ---- one 32-int block: Util.maxbits / maxdiffbits, BitPacking.fastpackwithoutmask
+                    uint32_t v[32];
+                    uint32_t orv = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t x = col[33 * i];
+                        v[i] = diff ? x - prev : x;
+                        if (diff) prev = x;
+                        orv |= v[i];
+                    }
+                    const int b = bits32(orv);
+                    if (pos + 1 + b > SL_OC) t_ovf = true;
+                    else {
+                        if (k < ng4) { // BinaryPacking.java:59-78: one header word per four blocks
+                            if ((k & 3) == 0) { hpos = pos++; hdrw = 0; }
+                            hdrw |= (uint32_t)b << (24 - 8 * (k & 3));
+                            if ((k & 3) == 3) my_out[33 * hpos] = hdrw;
+                        } else
+                            my_out[33 * pos++] = (uint32_t)b; // :79-86
+                        uint32_t *o = my_out + 33 * pos;
+                        if (b == 32) { // IntegratedBitPacking stores the raw values at width 32
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[33 * i] = tr.integrated ? col[33 * i] : v[i];
+                        } else if (b > 0) {
+                            uint64_t acc = 0;
+                            int fill = 0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                acc |= (uint64_t)v[i] << fill;
+                                fill += b;
+                                if (fill >= 32) { *o = (uint32_t)acc; o += 33; acc >>= 32; fill -= 32; }
+                            }
+                        }
+                        pos += b;
+                    }
+                } else if (c > 0) {
+                    // ---- VariableByte on the values past the last block (VariableByte.java:38-77); the non-skippable
+                    // integrated composition restarts the chain at 0 (IntegratedVariableByte.java:40)
+                    if (tr.integrated && !tr.chain_tail && k == nb) prev = 0;
+                    for (int i = 0; i < c; ++i) {
+                        const uint32_t x = col[33 * i];
+                        const uint32_t d = diff ? x - prev : x;
+                        if (diff) prev = x;
+                        const int len = vb_len(d);
+                        vacc |= vb_spread(d, len) << (8 * vfill);
+                        vfill += len;
+                        if (vfill >= 4) {
+                            if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
+                            ++pos; vacc >>= 32; vfill -= 4;
+                            if (vfill >= 4) {
+                                if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
+                                ++pos; vacc >>= 32; vfill -= 4;
+                            }
+                        }
+                    }
+                }
+                ovf = __any_sync(kFull, t_ovf);
+            }
+            bool t_ovf = false;
+            if (vfill > 0) { // zero-padded to a word (VariableByte.java:69-70)
+                if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
+                ++pos;
+            }
+            if (a.app) { // LoadPortfolios.java:622: outpos + 1 ints
+                if (pos < SL_OC) my_out[33 * pos] = 0u; else t_ovf = true;
+                ++pos;
+            }
+            const bool late = __any_sync(kFull, t_ovf);
+            ovf = ovf || late;
+        }
+        long long lw = lane < nl ? pos : 0; // (lanes past the last list carry an empty list's framing words)
+        bool emit_slow = false;
+        if (ovf) {
+            lw = 0;
+            if (tr.blocks) { // sizes by the warp-per-list routine, one list at a time
+                emit_slow = true;
+                for (int j = 0; j < nl; ++j) {
+                    const int64_t bj = __shfl_sync(kFull, beg, j), nj = __shfl_sync(kFull, n64, j);
+                    __syncwarp();
+                    const int64_t w = warp_bp_list_encode<false>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{nullptr, a.app}, a.app, s_in, lane);
+                    if (lane == j) lw = w;
+                }
+            } else if (lane == 0)
+                atomicMax(a.err, 2); // the host takes the batched kernels
+        }
+        // ---- place of every list inside the batch, of the batch inside the output
+        long long incl = lw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long t = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const long long T = __shfl_sync(kFull, incl, 31), lex = incl - lw;
+        if (lane == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+        long long base = 0;
+        if (batch > 0) {
+            for (int64_t j = batch - 1;; j -= 32) {
+                const int64_t idx = j - lane;
+                uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
+                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
+                const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
+                long long v = lane <= first ? (long long)(st & kLbMask) : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+                base += v;
+                if (inc) break;
+            }
+            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
+        }
+        if (lane < nl) a.out_off[l0 + lane] = 4 * (base + lex);
+        if (lane == 0 && batch == a.nbatches - 1) {
+            *a.total = 4 * (base + T);
+            a.out_off[a.nlists] = 4 * (base + T);
+        }
+        if (4 * (base + T) > a.cap) { // caller's buffer too small: report, write nothing
+            if (lane == 0) atomicMax(a.err, 1);
+            continue;
+        }
+        uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + base;
+        if (!ovf) {
+            const int ilw = (int)lw, ilex = (int)lex;
+            const uint32_t *so = s_outw[warp];
+            __syncwarp();
+            for (int j = 0; j < nl; ++j) {
+                const int wj = __shfl_sync(kFull, ilw, j), oj = __shfl_sync(kFull, ilex, j);
+                for (int w = lane; w < wj; w += 32) {
+                    const uint32_t x = so[33 * w + j];
+                    gout[oj + w] = a.app ? bswap32(x) : x;
+                }
+            }
+        } else if (emit_slow) {
+            for (int j = 0; j < nl; ++j) {
+                const int64_t bj = __shfl_sync(kFull, beg, j), nj = __shfl_sync(kFull, n64, j);
+                const long long oj = __shfl_sync(kFull, lex, j);
+                __syncwarp();
+                warp_bp_list_encode<true>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{gout + oj, a.app}, a.app, s_in, lane);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_decode(const FastDecArgs a, int64_t nbatches)
+{
+    __shared__ uint32_t s_valw[SL_WARPS][32 * 33];
+    __shared__ uint32_t s_wdw[SL_WARPS][SL_OC * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *s_val = s_valw[warp], *s_wd = s_wdw[warp];
+    const uint32_t *my = s_wd + lane; // word p of my list's stream: my[33 * p]
+    const CodecTraits tr = codec_traits(a.codec);
+    const bool diff = a.delta || tr.integrated;
+    for (int64_t batch = (int64_t)blockIdx.x * SL_WARPS + warp; batch < nbatches; batch += (int64_t)gridDim.x * SL_WARPS) {
+        const int64_t l0 = batch * 32;
+        const int nl = (int)min((int64_t)32, a.nlists - l0);
+        int64_t ib = 0, ie = 0, ob = 0, n64 = 0;
+        if (lane < nl) {
+            ib = a.in_off[l0 + lane]; ie = a.in_off[l0 + lane + 1];
+            ob = a.out_off[l0 + lane]; n64 = a.out_off[l0 + lane + 1] - ob;
+        }
+        if (__any_sync(kFull, ((ib | ie) & 3) != 0 || ie < ib || n64 < 0)) {
+            if (lane == 0) atomicMax(a.err, 1);
+            continue;
+        }
+        const int64_t aw = (ie - ib) >> 2;
+        const int64_t obase = __shfl_sync(kFull, ob, 0);
+        const bool big = aw > SL_OC || n64 > 32 * SL_OC || ob - obase > 0x3fffffff || (tr.fastpfor && n64 >= tr.fp_block);
+        if (__any_sync(kFull, big)) {
+            if (!tr.blocks) { if (lane == 0) atomicMax(a.err, 2); continue; } // the host takes the batched kernels
+            for (int j = 0; j < nl; ++j) {
+                const int64_t ibj = __shfl_sync(kFull, ib, j), awj = __shfl_sync(kFull, aw, j);
+                const int64_t obj = __shfl_sync(kFull, ob, j), nj = __shfl_sync(kFull, n64, j);
+                const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + ibj), a.app};
+                const bool ok = warp_bp_list_decode(tr, src, awj, nj, a.out + obj, a.delta, lane);
+                if (!ok && lane == 0) atomicMax(a.err, 1);
+                __syncwarp();
+            }
+            continue;
+        }
+        const int avail = (int)aw, n = (int)n64, oo = (int)(ob - obase);
+        // ---- stage the streams, transposed (at most two words per lane and list)
+        __syncwarp();
+        for (int j = 0; j < nl; ++j) {
+            const int awj = __shfl_sync(kFull, avail, j);
+            const int64_t ibj = __shfl_sync(kFull, ib, j);
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(a.in + ibj);
+            if (lane < awj) { const uint32_t x = __ldg(g + lane); s_wd[33 * lane + j] = a.app ? bswap32(x) : x; }
+            if (lane + 32 < awj) { const uint32_t x = __ldg(g + lane + 32); s_wd[33 * (lane + 32) + j] = a.app ? bswap32(x) : x; }
+        }
+        __syncwarp();
+        const int nb = tr.blocks ? n >> 5 : 0, ng4 = nb & ~3;
+        int p = 0;
+        bool ok = true;
+        if (tr.sk) { ok = lane >= nl || (avail >= 1 && my[0] == (uint32_t)n); p = 1; }
+        else if (n > 0 && (tr.fastpfor || tr.blocks)) { ok = avail >= 1 && my[0] == (uint32_t)(32 * nb); p = 1; }
+        uint32_t carry = 0, hdr = 0, vv = 0;
+        int vs = 0, vshift = 0;
+        const int maxn = __reduce_max_sync(kFull, n);
+        uint32_t *gout = a.out + obase;
+        for (int k = 0; 32 * k < maxn; ++k) {
+            const int c = min(32, n - 32 * k);
+            uint32_t *col = s_val + lane; // value i of my list in this round: col[33 * i]
+            if (ok && k < nb) {
+                // ---- one block: width from the group header (BinaryPacking.java:102-123) or its own (:124-131)
+                int b = 33;
+                if (k < ng4) {
+                    if ((k & 3) == 0) { if (p < avail) hdr = my[33 * p++]; else ok = false; }
+                    b = (int)((hdr >> (24 - 8 * (k & 3))) & 255u);
+                } else if (p < avail)
+                    b = (int)min(my[33 * p++], 33u);
+                if (b > 32 || p + b > avail) ok = false;
+                if (ok) {
+                    uint32_t v[32];
+                    const uint32_t *ptr = my + 33 * p;
+                    if (b == 32) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = ptr[33 * i];
+                    } else {
+                        const uint32_t mask = (1u << b) - 1u;
+                        uint64_t acc = 0;
+                        int fill = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (fill < b) { acc |= (uint64_t)(*ptr) << fill; ptr += 33; fill += 32; }
+                            v[i] = (uint32_t)acc & mask;
+                            acc >>= b;
+                            fill -= b;
+                        }
+                    }
+                    const bool raw = tr.integrated && b == 32; // IntegratedBitPacking stores raw values at width 32
+                    if (diff && !raw) {
+                        v[0] += carry;
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) v[i] += v[i - 1];
+                    }
+                    carry = v[31];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) col[33 * i] = v[i];
+                    p += b;
+                }
+            } else if (ok && c > 0) {
+                // ---- VariableByte.headlessUncompress (VariableByte.java:180-203); IntegratedVariableByte.java:40 restarts
+                if (tr.integrated && !tr.chain_tail && k == nb) carry = 0;
+                int got = 0;
+                while (got < c) {
+                    if (p >= avail) { ok = false; break; }
+                    const uint32_t by = (my[33 * p] >> vs) & 0xffu;
+                    vs += 8; p += vs >> 5; vs &= 31;
+                    vv += (by & 127u) << (vshift & 31);
+                    if (by & 128u) {
+                        if (diff) { carry += vv; vv = carry; }
+                        col[33 * got] = vv;
+                        ++got; vv = 0; vshift = 0;
+                    } else
+                        vshift += 7;
+                }
+            }
+            __syncwarp();
+            // ---- the round's values leave: 128 contiguous bytes per list
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int oj = __shfl_sync(kFull, oo, j), nj = __shfl_sync(kFull, n, j);
+                const int idx = 32 * k + lane;
+                if (idx < nj) gout[oj + idx] = s_val[33 * lane + j];
+            }
+            __syncwarp();
+        }
+        if (__any_sync(kFull, !ok) && lane == 0) atomicMax(a.err, 1);
+    }
+}
+
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
 // block, then a second sweep.  Sizes here are "number of lists": bookkeeping, not hot.
@@ -1885,13 +2240,26 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     return (int)g;
 }
 
+// the batched (thread-per-block) kernels: BinaryPacking family and FastPFOR / FastPFOR128
+static bool batched_applicable(int codec, bool delta, int64_t total_vals, int64_t nlists)
+{
+    const bool ok = fast_codec_ok(codec, delta) || codec_traits(codec).fastpfor;
+    return ok && fast_lists_per_batch(codec, total_vals, nlists) > 0;
+}
+
+// the short-list (thread-per-list) kernels: every codec, lists averaging <= SL_MAXAVG values
+static bool shortlist_applicable(mcp_ctx *ctx, int codec, bool delta, int64_t total_vals, int64_t nlists)
+{
+    if (ctx && !ctx->shortListCodec) return false;
+    return nlists > 0 && sl_codec_ok(codec, delta) && (double)total_vals <= SL_MAXAVG * (double)nlists;
+}
+
 bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, bool encode)
 {
     const int codec = codec_id & MCP_CODEC_MASK;
     const bool delta = (codec_id & MCP_FLAG_DELTA) != 0;
-    (void)encode; // both directions: BinaryPacking family and FastPFOR / FastPFOR128
-    const bool ok = fast_codec_ok(codec, delta) || codec_traits(codec).fastpfor;
-    return ok && fast_lists_per_batch(codec, total_vals, nlists) > 0;
+    (void)encode; // both directions
+    return batched_applicable(codec, delta, total_vals, nlists) || shortlist_applicable(nullptr, codec, delta, total_vals, nlists);
 }
 
 // upper bound of the encoded size in bytes for the fast-path codecs: 33 words per 32-int block worst case, a 31-value
@@ -1899,7 +2267,9 @@ bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, boo
 // byte metadata and page words, and a tail of up to 255 values
 int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists)
 {
-    if (codec_traits(codec_id & MCP_CODEC_MASK).fastpfor) return 4 * (total_vals + total_vals / 8 + 384 * nlists + 64);
+    const CodecTraits tr = codec_traits(codec_id & MCP_CODEC_MASK);
+    if (tr.fastpfor) return 4 * (total_vals + total_vals / 8 + 384 * nlists + 64);
+    if (!tr.blocks) return 4 * (total_vals + total_vals / 4 + 4 * nlists + 64); // VariableByte alone: 5 bytes per value at worst
     return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64);
 }
 
@@ -1923,37 +2293,53 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.list_off = d_list_off;
     a.uniform_len = uniform_len;
     a.nlists = nlists;
-    a.lists_per_batch = fast_lists_per_batch(a.codec, total_vals, nlists);
-    a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
-    if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
-    // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
-    const size_t sbytes = 32 + (size_t)a.nbatches * sizeof(uint64_t);
-    MCP_CUDA(ctx, ctx->dScanTmp.reserve(sbytes));
-    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dScanTmp.p, 0, sbytes, ctx->stream));
-    unsigned char *sp = ctx->dScanTmp.as<unsigned char>();
-    a.ticket = reinterpret_cast<unsigned long long *>(sp);
-    a.total = reinterpret_cast<int64_t *>(sp + 8);
-    a.err = reinterpret_cast<int *>(sp + 16);
-    a.state = reinterpret_cast<uint64_t *>(sp + 32);
     a.out_off = d_out_off;
     a.out = d_out;
     a.cap = d_out ? cap : 0;
-    {
-        KScope ks(ctx, MCP_K_ENCODE);
-        const CodecTraits tr = codec_traits(a.codec);
-        if (!tr.fastpfor) k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        else if (tr.fp_block == 256) k_fp_encode_fast<8><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        else k_fp_encode_fast<4><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        MCP_TRY(check_launch(ctx, "k_encode_fast"));
+    const bool batched = batched_applicable(a.codec, a.delta, total_vals, nlists);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists);
+    if (!batched && !shortl) return MCP_E_UNSUPPORTED;
+    // pass 0: thread-per-list kernel (short lists); pass 1: thread-per-block kernels
+    for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
+        if (pass == 1 && !batched) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; }
+        a.lists_per_batch = pass == 0 ? 32 : fast_lists_per_batch(a.codec, total_vals, nlists);
+        a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
+        if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
+        // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
+        const size_t sbytes = 32 + (size_t)a.nbatches * sizeof(uint64_t);
+        MCP_CUDA(ctx, ctx->dScanTmp.reserve(sbytes));
+        MCP_CUDA(ctx, cudaMemsetAsync(ctx->dScanTmp.p, 0, sbytes, ctx->stream));
+        unsigned char *sp = ctx->dScanTmp.as<unsigned char>();
+        a.ticket = reinterpret_cast<unsigned long long *>(sp);
+        a.total = reinterpret_cast<int64_t *>(sp + 8);
+        a.err = reinterpret_cast<int *>(sp + 16);
+        a.state = reinterpret_cast<uint64_t *>(sp + 32);
+        {
+            KScope ks(ctx, MCP_K_ENCODE);
+            const CodecTraits tr = codec_traits(a.codec);
+            if (pass == 0) {
+                const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
+                k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);
+            } else if (!tr.fastpfor) k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            else if (tr.fp_block == 256) k_fp_encode_fast<8><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            else k_fp_encode_fast<4><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            MCP_TRY(check_launch(ctx, "k_encode_fast"));
+        }
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, sp + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);
+        const int flag = *reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8);
+        if (flag == 2) { // a batch did not fit this kernel: not an error, the next kind of kernel takes the call
+            if (pass == 0) { ++ctx->shortListFallbacks; continue; }
+            ++ctx->fastEncodeFallbacks;
+            return MCP_E_UNSUPPORTED;
+        }
+        if (pass == 0) ++ctx->shortListCalls;
+        ++ctx->fastEncodeCalls;
+        if (flag != 0) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
+        return MCP_OK;
     }
-    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, sp + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);
-    const int flag = *reinterpret_cast<int *>(reinterpret_cast<char *>(ctx->hPinned) + 8);
-    if (flag == 2) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; } // a batch did not fit: not an error, the caller falls back
-    ++ctx->fastEncodeCalls;
-    if (flag != 0) return fail(ctx, MCP_E_CAP, "encode: output buffer too small");
-    return MCP_OK;
+    return MCP_E_UNSUPPORTED;
 }
 
 int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off, int64_t nlists,
@@ -1967,27 +2353,41 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     a.in = d_in;
     a.in_off = d_in_off;
     a.nlists = nlists;
-    a.lists_per_batch = fast_lists_per_batch(a.codec, total_out_vals, nlists);
     a.out = reinterpret_cast<uint32_t *>(d_out);
     a.out_off = d_out_off;
+    const bool batched = batched_applicable(a.codec, a.delta, total_out_vals, nlists);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists);
+    if (!batched && !shortl) return MCP_E_UNSUPPORTED;
     MCP_CUDA(ctx, ctx->dErr.reserve(64));
-    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
     a.err = ctx->dErr.as<int>();
-    const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
-    {
-        KScope ks(ctx, MCP_K_DECODE);
-        const CodecTraits tr = codec_traits(a.codec);
-        if (!tr.fastpfor) k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        else if (tr.fp_block == 256) k_fp_decode_fast<8><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        else k_fp_decode_fast<4><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
-        MCP_TRY(check_launch(ctx, "k_decode_fast"));
+    for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
+        if (pass == 1 && !batched) return MCP_E_UNSUPPORTED;
+        MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
+        a.lists_per_batch = pass == 0 ? 32 : fast_lists_per_batch(a.codec, total_out_vals, nlists);
+        const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
+        {
+            KScope ks(ctx, MCP_K_DECODE);
+            const CodecTraits tr = codec_traits(a.codec);
+            if (pass == 0) {
+                const int64_t want = (nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
+                k_sl_decode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a, nbatches);
+            } else if (!tr.fastpfor) k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            else if (tr.fp_block == 256) k_fp_decode_fast<8><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            else k_fp_decode_fast<4><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
+            MCP_TRY(check_launch(ctx, "k_decode_fast"));
+        }
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dErr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int flag = *reinterpret_cast<int *>(ctx->hPinned);
+        if (flag == 2) { // a batch did not fit this kernel: the next kind of kernel (or the warp-per-list one) takes the call
+            if (pass == 0) { ++ctx->shortListFallbacks; continue; }
+            return MCP_E_UNSUPPORTED;
+        }
+        if (pass == 0) ++ctx->shortListCalls;
+        if (flag != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
+        return MCP_OK;
     }
-    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, ctx->dErr.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int flag = *reinterpret_cast<int *>(ctx->hPinned);
-    if (flag == 2) return MCP_E_UNSUPPORTED; // a batch did not fit the FastPFOR kernel: the caller takes the warp-per-list kernel
-    if (flag != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
-    return MCP_OK;
+    return MCP_E_UNSUPPORTED;
 }
 
 static int grid_for_lists(mcp_ctx *ctx, int64_t nlists)

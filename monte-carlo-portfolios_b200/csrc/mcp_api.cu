@@ -163,6 +163,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
+    else if (!strcmp(key, "short_list_codec")) ctx->shortListCodec = value != 0;
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);
@@ -545,6 +546,14 @@ int mcp_codec_stats(mcp_ctx *ctx, int64_t *fast_encodes, int64_t *fast_fallbacks
     if (!ctx) return MCP_E_ARG;
     if (fast_encodes) *fast_encodes = ctx->fastEncodeCalls;
     if (fast_fallbacks) *fast_fallbacks = ctx->fastEncodeFallbacks;
+    return MCP_OK;
+}
+
+int mcp_codec_stats_short(mcp_ctx *ctx, int64_t *short_calls, int64_t *short_fallbacks)
+{
+    if (!ctx) return MCP_E_ARG;
+    if (short_calls) *short_calls = ctx->shortListCalls;
+    if (short_fallbacks) *short_fallbacks = ctx->shortListFallbacks;
     return MCP_OK;
 }
 

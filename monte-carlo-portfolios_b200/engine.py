@@ -110,7 +110,9 @@ class Context:
     def codec_stats(self) -> dict:
         a, b = C.c_int64(), C.c_int64()
         self._check(self._L.mcp_codec_stats(self._h, C.byref(a), C.byref(b)), "codec_stats")
-        return {"fast_encodes": a.value, "fast_fallbacks": b.value}
+        c, d = C.c_int64(), C.c_int64()
+        self._check(self._L.mcp_codec_stats_short(self._h, C.byref(c), C.byref(d)), "codec_stats_short")
+        return {"fast_encodes": a.value, "fast_fallbacks": b.value, "short_calls": c.value, "short_fallbacks": d.value}
 
     # -- single-list drop-ins
     def compress_ints(self, codec_id: int, vals, out_cap: int | None = None) -> np.ndarray:

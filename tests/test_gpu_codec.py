@@ -35,13 +35,16 @@ def test_kat_through_the_c_abi(ctx):
     assert doc["algo"] == "bpacking+variablebyte" and doc["compressedByteSize"] == 36 and doc["uncompressedIntegerSize"] == 17
 
 
-@pytest.fixture(params=[1, 0], ids=["fastpath", "warp-per-list"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["shortlist+batched", "batched", "warp-per-list"])
 def codec_ctx(ctx, request):
-    """Both kernel families behind the codec ABI: the batched single-pass fast path (BinaryPacking family, short
-    lists) and the warp-per-list size/scan/emit kernels that handle everything else."""
-    ctx.set_option("fast_codec", request.param)
+    """The three kernel families behind the codec ABI: the thread-per-list kernels (lists averaging <= 144 values), the
+    batched single-pass kernels (thread per block) and the warp-per-list size/scan/emit kernels that handle everything
+    else."""
+    ctx.set_option("fast_codec", request.param[0])
+    ctx.set_option("short_list_codec", request.param[1])
     yield ctx
     ctx.set_option("fast_codec", 1)
+    ctx.set_option("short_list_codec", 1)
 
 
 @pytest.mark.parametrize("codec", cases.ALL_CODECS, ids=cases.NAMES)
@@ -331,3 +334,122 @@ def test_full_size_c4_properties(ctx):
     finally:
         for p in (d_out_off, d_out, d_back):
             ctx.dev_free(p)
+
+
+def _short_lists(rng, count, lengths):
+    lists = []
+    for _ in range(count):
+        kind = rng.integers(0, 8)
+        n = int(rng.choice(lengths))
+        if kind == 0:
+            v = rng.integers(-2**31, 2**31 - 1, n)                              # incompressible: width 32, 5-byte VByte
+        elif kind == 1:
+            v = np.sort(rng.integers(0, 2**31 - 1, n))                          # sorted, big gaps
+        elif kind == 3:
+            v = np.full(n, int(rng.integers(0, 1000)))                          # constant: width 0 under delta
+        elif kind == 4:
+            v = rng.integers(0, 2 ** int(rng.integers(1, 31)), n)               # uniform width
+        elif kind == 5:
+            v = np.cumsum(rng.integers(0, 3, n)) + 2**31 - 50                   # crosses the sign bit
+        else:
+            v = np.cumsum(rng.geometric(0.01, n))                               # breach-like
+        lists.append(np.asarray(v, np.int64))
+    return lists
+
+
+@pytest.mark.parametrize("codec", cases.ALL_CODECS, ids=cases.NAMES)
+@pytest.mark.parametrize("delta", [0, cases.DELTA], ids=["plain", "delta"])
+@pytest.mark.parametrize("framing", [N.FRAME_WORDS, N.FRAME_APP], ids=["words", "app"])
+def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
+    """The thread-per-list kernels on the lengths around every boundary they have (empty, all tail, 31/32/33,
+    127/128/129, a FastPFOR128 block, columns that overflow and send the warp batch to the warp-per-list routines or
+    the call to the batched kernels), every codec id, both framings: bytes equal to the oracle's, decode round trip."""
+    if codec in (N.CODEC_IBP32_IVB, N.CODEC_SK_IBP32_IVB) and delta:
+        pytest.skip("Delta before an integrated codec is not a combination the reference uses")
+    rng = np.random.default_rng(1000 + 16 * codec + 2 * (1 if delta else 0) + framing)
+    cid = codec | delta
+    for lengths in ([0, 1, 5, 31, 32, 33, 64, 96, 100, 127], [0, 1, 31, 32, 33, 64, 96, 100, 127, 128, 129, 160, 200, 255, 256, 300]):
+        lists = _short_lists(rng, 333, lengths)
+        vals = np.concatenate([cases.to_i32(v) for v in lists])
+        off = np.zeros(len(lists) + 1, np.int64)
+        np.cumsum([len(v) for v in lists], out=off[1:])
+        assert vals.size <= 144 * len(lists)
+        before = ctx.codec_stats()
+        out_off, out = ctx.codec_encode(cid, framing, vals, off, cap=int(8 * vals.size + 64 * len(lists)))
+        mid = ctx.codec_stats()
+        assert mid["short_calls"] + mid["short_fallbacks"] == before["short_calls"] + before["short_fallbacks"] + 1
+        assert out_off[0] == 0 and out_off[-1] == out.size
+        for i, v in enumerate(lists):
+            ref = cref.get_compressed_instruments(cid, v) if framing == N.FRAME_APP else cref.compress(cid, v).tobytes()
+            assert bytes(out[out_off[i]: out_off[i + 1]]) == ref, (i, len(v))
+        assert np.array_equal(ctx.codec_decode(cid, framing, out, out_off, off), vals)
+        after = ctx.codec_stats()
+        assert after["short_calls"] + after["short_fallbacks"] == mid["short_calls"] + mid["short_fallbacks"] + 1
+
+
+@pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA,
+                                 N.CODEC_VB | N.FLAG_DELTA, N.CODEC_SK_IBP32_IVB, N.CODEC_IBP32_IVB, N.CODEC_SK_BP32_VB | N.FLAG_DELTA],
+                         ids=["bp+delta", "fastpfor256+delta", "fastpfor128+delta", "vb+delta", "skibp", "ibp", "skbp+delta"])
+def test_short_list_kernels_serve_c4(ctx, cid):
+    """BASELINE config C4's shape (1 % of 10 000 trials, ~100 ints per list, not a multiple of 32 lists) is served by the
+    thread-per-list kernels themselves -- no hand-over -- in both directions, and the bytes are the ones the batched
+    and the warp-per-list kernels produce."""
+    rng = np.random.default_rng(77)
+    vals, off = cases.breach_like_lists(rng, 4099, 10000, 0.01)
+    nl = off.size - 1
+    before = ctx.codec_stats()
+    out_off, out = ctx.codec_encode(cid, N.FRAME_APP, vals, off, cap=int(8 * vals.size + 64 * nl))
+    back = ctx.codec_decode(cid, N.FRAME_APP, out, out_off, off)
+    after = ctx.codec_stats()
+    if (cid & 0xff) == N.CODEC_FASTPFOR128_VB and np.max(np.diff(off)) >= 128:
+        # a list of a whole FastPFOR128 block is not theirs: the call moves on to the batched kernels
+        assert after["short_calls"] == before["short_calls"] and after["short_fallbacks"] == before["short_fallbacks"] + 2
+    else:
+        assert after["short_calls"] == before["short_calls"] + 2 and after["short_fallbacks"] == before["short_fallbacks"]
+    assert np.array_equal(back, vals)
+    stride = int(np.max(np.diff(out_off)))
+    ref, lens = cref.batch_compress(cid, 1, vals, off, stride)
+    assert np.array_equal(np.diff(out_off), lens)
+    for i in range(nl):
+        assert bytes(out[out_off[i]: out_off[i + 1]]) == bytes(ref[i * stride: i * stride + lens[i]]), i
+    try:
+        for opts in (("short_list_codec", 0), ("fast_codec", 0)):
+            ctx.set_option(*opts)
+            o2, b2 = ctx.codec_encode(cid, N.FRAME_APP, vals, off)
+            assert np.array_equal(o2, out_off) and np.array_equal(b2, out)
+            assert np.array_equal(ctx.codec_decode(cid, N.FRAME_APP, out, out_off, off), vals)
+    finally:
+        ctx.set_option("fast_codec", 1)
+        ctx.set_option("short_list_codec", 1)
+
+
+def test_short_list_decode_rejects_malformed_streams(ctx):
+    rng = np.random.default_rng(5)
+    vals, off = cases.breach_like_lists(rng, 500, 10000, 0.01)
+    cid = N.CODEC_BP32_VB | N.FLAG_DELTA
+    out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off)
+    w = out.view(np.uint32)
+    i = 123
+    assert off[i + 1] - off[i] >= 64
+    for what, (pos, val) in {"count header": (0, 31), "block width": (1, 40), "truncated": (None, None)}.items():
+        bad, boff = out.copy(), out_off.copy()
+        if pos is None:
+            boff = out_off.copy()
+            boff[i + 1:] -= 8                                   # the list loses its last two words
+            bad = np.concatenate([out[: out_off[i + 1] - 8], out[out_off[i + 1]:]])
+        else:
+            bad.view(np.uint32)[out_off[i] // 4 + pos] = val
+        with pytest.raises(mcp_b200.McpError) as e:
+            ctx.codec_decode(cid, N.FRAME_WORDS, bad, boff, off)
+        assert e.value.code == N.MCP_E_FORMAT, what
+    assert w[out_off[i] // 4] == 32 * ((off[i + 1] - off[i]) // 32)
+
+
+def test_short_list_encode_reports_capacity(ctx):
+    rng = np.random.default_rng(6)
+    vals, off = cases.breach_like_lists(rng, 300, 10000, 0.01)
+    out_off, out = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off)
+    with pytest.raises(mcp_b200.CapacityError):
+        ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size) - 4)
+    o2, b2 = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size))
+    assert np.array_equal(b2, out) and np.array_equal(o2, out_off)
