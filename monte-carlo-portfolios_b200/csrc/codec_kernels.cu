@@ -1772,23 +1772,27 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_decode_fast(const FastDecA
 
 // ============================================================ short-list path: one THREAD per list
 // Lists of ~100 ints (BASELINE config C4: 1 % of 10 000 trials) spend the batched kernels above on bookkeeping: block
-// items, tail tables, four CTA-wide scans and a dozen CTA barriers per batch -- 2.3 warp instructions per integer, 40 %
-// of the stall samples at a barrier.  Here a WARP owns 32 consecutive lists and a THREAD owns one list from its first
-// value to its last word, so every piece of list state (position, width headers, the VariableByte byte accumulator,
-// the running value of the Delta / integrated chain) is a register and nothing ever waits on another warp:
-//   * values arrive 32 per list per round: the warp loads 128 contiguous bytes of list j and stores them TRANSPOSED
-//     (value i of list j at word 33 i + j): coalesced in global memory, conflict-free in shared memory both ways;
-//   * thread j packs its block (or VariableByte-encodes its tail values) of the round into its column of a transposed
-//     output area (word w of list j at 33 w + j), again conflict-free;
+// items, tail tables, four CTA-wide scans and a dozen CTA barriers per batch.  Here a WARP owns 32 consecutive lists and
+// a THREAD owns one list from its first value to its last word, so every piece of list state (position, width headers,
+// the VariableByte byte accumulator, the running value of the Delta / integrated chain) is a register and nothing ever
+// waits on another warp:
+//   * values arrive in STAGES of 32 per list: the warp copies 128 contiguous bytes of list j with 4-byte cp.async
+//     (LDGSTS) into a TRANSPOSED tile (value i of list j at word 33 i + j): coalesced in global memory, conflict-free
+//     in shared memory both ways.  Block stages first (stage k = block k of every list that has one), then the
+//     VariableByte tails of all lists together, so a warp runs ONE tail loop however the list lengths fall.  Two
+//     tiles: stage s + 1 -- and the first stage of the warp's NEXT batch -- is in flight while stage s is packed;
+//   * thread j packs its block (or VariableByte-encodes its tail values) into its column of a transposed output
+//     area (word w of list j at 33 w + j), again conflict-free;
 //   * the 32 list sizes are scanned with shuffles, the batch takes its place in the output by the same decoupled
-//     look-back as above (one state word per warp batch), and the lists leave with coalesced stores.
-// Decode mirrors it.  A batch whose lists do not fit the SL_OC-word columns takes the warp-per-list routines inside the
-// same kernel (BinaryPacking family) or raises flag 2 (FastPFOR lists of a block or more, long VariableByte lists), and
-// the host then takes the batched kernels above.  Codecs: every id; FastPFOR / FastPFOR128 only while a list is
-// shorter than one block (Composition.java:45-48 writes the 0 marker and the whole list goes to VariableByte).
-constexpr int SL_WARPS = 2;      // warps per CTA (independent of each other)
-constexpr int SL_OC = 64;        // words of one list's compressed stream that fit its column
-constexpr int SL_CTAS = 8;       // resident CTAs per SM (25 KB of shared memory each)
+//     look-back as above (one state word per warp batch; the next batch's first stage is requested BEFORE the
+//     look-back, which hides most of the wait for the predecessors), and the lists leave with coalesced stores.
+// Decode mirrors it: the NEXT batch's compressed streams stream into a second transposed area while this batch's are
+// unpacked.  A batch with a list that does not fit its SL_OC-word column takes the warp-per-list routines inside the
+// same kernel; only a FastPFOR list of a whole block or more raises flag 2 (the host then takes the batched kernels).
+constexpr int SL_WARPS = 2;      // warps per CTA in the encoder (independent of each other)
+constexpr int SL_OC = 56;        // words of one list's compressed stream that fit its column
+constexpr int SL_CTAS = 7;       // resident encoder CTAs per SM (2 x (2 x 4.2 + 7.4) KB of shared memory each)
+constexpr int SL_DCTAS = 11;     // resident decoder CTAs per SM (one warp, 4.2 + 2 x 7.4 KB each)
 constexpr double SL_MAXAVG = 144.0; // lists averaging more values go to the thread-per-block kernels
 
 __host__ __device__ inline bool sl_codec_ok(int codec, bool delta)
@@ -1797,64 +1801,130 @@ __host__ __device__ inline bool sl_codec_ok(int codec, bool delta)
     return !(t.integrated && delta);
 }
 
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // 7-bit groups of d spread over the low bytes of a 64-bit word, terminator bit on byte len-1 (VariableByte.java:44-68)
 __device__ __forceinline__ uint64_t vb_spread(uint32_t d, int len)
 {
-    const uint32_t lo = (d & 0x7fu) | ((d & 0x3f80u) << 1) | ((d & 0x1fc000u) << 2) | ((d & 0xfe00000u) << 3);
+    const uint32_t lo = (d & 0x7fu) | ((d << 1) & 0x7f00u) | ((d << 2) & 0x7f0000u) | ((d << 3) & 0x7f000000u);
     return (((uint64_t)(d >> 28) << 32) | lo) | (0x80ull << (8 * (len - 1)));
 }
 
+// A list the thread-per-list kernels cannot hold, by one warp: the BinaryPacking family through warp_bp_list_encode,
+// a list that is all VariableByte (FastPFOR below one block: Composition's 0 marker first; VariableByte alone) here.
+template <bool WRITE>
+__device__ __forceinline__ int64_t warp_short_list_encode(const CodecTraits tr, const ValSeq x, int64_t n, const WordSink sink, bool app,
+                                                          uint32_t *stage, int lane)
+{
+    if (tr.blocks) return warp_bp_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
+    int64_t pos = 0;
+    if (n > 0) {
+        if (tr.fastpfor) { if (WRITE && lane == 0) sink.put(0, 0u); pos = 1; }
+        auto getv = [&](int64_t i) -> uint32_t { return x(i); };
+        pos += warp_vb_encode<WRITE>(getv, n, sink, pos, stage, lane);
+    }
+    if (app) { if (WRITE && lane == 0) sink.put(pos, 0u); ++pos; }
+    return pos;
+}
+
+__device__ __forceinline__ bool warp_short_list_decode(const CodecTraits tr, const WordSrc src, int64_t avail, int64_t n, uint32_t *out,
+                                                       bool delta, int lane)
+{
+    if (tr.blocks) return warp_bp_list_decode(tr, src, avail, n, out, delta, lane);
+    if (n == 0) return true;
+    int64_t p = 0;
+    if (tr.fastpfor) { if (avail < 1 || src.get(0) != 0u) return false; p = 1; }
+    if (!warp_vb_decode<false>(src, p, avail, n, out, 0u, lane)) return false;
+    if (delta) { __syncwarp(); warp_inverse_delta(out, n, lane); }
+    return true;
+}
+
+// what a lane knows about its list of the batch the warp is working on (or about to)
+struct SlList {
+    int64_t beg, n64; // first value (index into vals), length
+    int off, n;       // first value relative to the batch's first value, length (0 when the batch takes the slow path)
+    int nb, r;        // 32-int blocks of the first stage, values past them
+};
+
 __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const FastEncArgs a)
 {
-    __shared__ uint32_t s_inw[SL_WARPS][32 * 33];
+    __shared__ uint32_t s_inw[SL_WARPS][2][32 * 33];
     __shared__ uint32_t s_outw[SL_WARPS][SL_OC * 33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *s_in = s_inw[warp];
     uint32_t *my_out = s_outw[warp] + lane; // word w of my list: my_out[33 * w]
     const CodecTraits tr = codec_traits(a.codec);
     const bool diff = a.delta || tr.integrated;
-    for (;;) {
+
+    // ---- a batch's extents, and the request for its first stage
+    auto take_batch = [&](int64_t &batch, int &nl, SlList &L, int64_t &vbase, bool &slow, int &maxnb, int &nst) {
         unsigned long long tk = 0;
         if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
-        tk = __shfl_sync(kFull, tk, 0);
-        if ((int64_t)tk >= a.nbatches) break;
-        __syncwarp(); // the previous batch's columns have been read
-        const int64_t batch = (int64_t)tk, l0 = batch * 32;
-        const int nl = (int)min((int64_t)32, a.nlists - l0);
-        int64_t beg = 0, n64 = 0;
+        batch = (int64_t)__shfl_sync(kFull, tk, 0);
+        nl = 0; slow = false; maxnb = 0; nst = 0; vbase = 0;
+        L = SlList{0, 0, 0, 0, 0, 0};
+        if (batch >= a.nbatches) return;
+        const int64_t l0 = batch * 32;
+        nl = (int)min((int64_t)32, a.nlists - l0);
         if (lane < nl) {
-            beg = a.list_off ? a.list_off[l0 + lane] : (l0 + lane) * a.uniform_len;
-            n64 = (a.list_off ? a.list_off[l0 + lane + 1] : (l0 + lane + 1) * a.uniform_len) - beg;
+            L.beg = a.list_off ? a.list_off[l0 + lane] : (l0 + lane) * a.uniform_len;
+            L.n64 = (a.list_off ? a.list_off[l0 + lane + 1] : (l0 + lane + 1) * a.uniform_len) - L.beg;
         }
-        const int64_t vbase = __shfl_sync(kFull, beg, 0);
-        const bool big = lane < nl && (beg - vbase > 0x3fffffff || n64 > 0x3fffffff || (tr.fastpfor && n64 >= tr.fp_block));
-        bool ovf = __any_sync(kFull, big);
-        const int off = ovf ? 0 : (int)(beg - vbase), n = ovf ? 0 : (int)n64;
-        const int nb = tr.blocks ? n >> 5 : 0, ng4 = nb & ~3;
+        vbase = __shfl_sync(kFull, L.beg, 0);
+        const bool big = lane < nl && (L.beg - vbase > 0x3fffffff || L.n64 > 0x3fffffff || (tr.fastpfor && L.n64 >= tr.fp_block));
+        slow = __any_sync(kFull, big);
+        if (!slow) {
+            L.off = (int)(L.beg - vbase); L.n = (int)L.n64;
+            L.nb = tr.blocks ? L.n >> 5 : 0; L.r = L.n - 32 * L.nb;
+            maxnb = __reduce_max_sync(kFull, L.nb);
+            nst = maxnb + ((__reduce_max_sync(kFull, L.r) + 31) >> 5);
+        }
+    };
+    // stage s of a batch: block s of every list that has one, then the values past the blocks, 32 per list and stage
+    auto request_stage = [&](int s, const SlList &L, int maxnb, int64_t vbase, uint32_t *tile) {
+        int src, cnt;
+        if (s < maxnb) { src = L.off + 32 * s; cnt = s < L.nb ? 32 : 0; }
+        else { const int t = s - maxnb; src = L.off + 32 * L.nb + 32 * t; cnt = min(32, max(0, L.r - 32 * t)); }
+        const uint32_t *gv = a.vals + vbase + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int sj = __shfl_sync(kFull, src, j), cj = __shfl_sync(kFull, cnt, j);
+            if (lane < cj) cp_async4(tile + lane * 33 + j, gv + sj);
+        }
+        cp_async_commit();
+    };
+
+    int64_t batch, vbase;
+    int nl, maxnb, nst;
+    bool slow;
+    SlList L;
+    take_batch(batch, nl, L, vbase, slow, maxnb, nst);
+    if (nst > 0) request_stage(0, L, maxnb, vbase, s_inw[warp][0]);
+    while (batch < a.nbatches) {
+        const int64_t l0 = batch * 32;
+        bool ovf = slow;
         int pos = 0;
         if (!ovf) {
+            const int n = L.n, nb = L.nb, ng4 = nb & ~3;
             // IntCompressor: compressed[0] = n; Composition: the first stage's header, 0 when it wrote nothing
             if (tr.sk) { my_out[0] = (uint32_t)n; pos = 1; }
             else if (n > 0 && (tr.fastpfor || tr.blocks)) { my_out[0] = (uint32_t)(32 * nb); pos = 1; }
             uint32_t prev = 0, hdrw = 0;
             int hpos = 0, vfill = 0;
             uint64_t vacc = 0;
-            const int maxn = __reduce_max_sync(kFull, n);
-            const uint32_t *gv = a.vals + vbase;
-            for (int k = 0; 32 * k < maxn && !ovf; ++k) {
+            for (int s = 0; s < nst; ++s) {
+                if (s + 1 < nst) { request_stage(s + 1, L, maxnb, vbase, s_inw[warp][(s + 1) & 1]); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
                 __syncwarp();
-                // ---- stage values [32k, 32k + 32) of every list, transposed
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int oj = __shfl_sync(kFull, off, j), nj = __shfl_sync(kFull, n, j);
-                    const int idx = 32 * k + lane;
-                    if (idx < nj) s_in[lane * 33 + j] = __ldg(gv + oj + idx);
-                }
-                __syncwarp();
-                const uint32_t *col = s_in + lane; // value i of my list in this round: col[33 * i]
-                const int c = min(32, n - 32 * k);
+                const uint32_t *col = s_inw[warp][s & 1] + lane; // value i of my list in this stage: col[33 * i]
                 bool t_ovf = false;
-                if (k < nb) {
+                if (s < nb) {
                     // ---- one 32-int block: Util.maxbits / maxdiffbits, BitPacking.fastpackwithoutmask
                     uint32_t v[32];
                     uint32_t orv = 0;
@@ -1868,10 +1938,10 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                     const int b = bits32(orv);
                     if (pos + 1 + b > SL_OC) t_ovf = true;
                     else {
-                        if (k < ng4) { // BinaryPacking.java:59-78: one header word per four blocks
-                            if ((k & 3) == 0) { hpos = pos++; hdrw = 0; }
-                            hdrw |= (uint32_t)b << (24 - 8 * (k & 3));
-                            if ((k & 3) == 3) my_out[33 * hpos] = hdrw;
+                        if (s < ng4) { // BinaryPacking.java:59-78: one header word per four blocks
+                            if ((s & 3) == 0) { hpos = pos++; hdrw = 0; }
+                            hdrw |= (uint32_t)b << (24 - 8 * (s & 3));
+                            if ((s & 3) == 3) my_out[33 * hpos] = hdrw;
                         } else
                             my_out[33 * pos++] = (uint32_t)b; // :79-86
                         uint32_t *o = my_out + 33 * pos;
@@ -1890,10 +1960,11 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                         }
                         pos += b;
                     }
-                } else if (c > 0) {
+                } else if (s >= maxnb) {
                     // ---- VariableByte on the values past the last block (VariableByte.java:38-77); the non-skippable
                     // integrated composition restarts the chain at 0 (IntegratedVariableByte.java:40)
-                    if (tr.integrated && !tr.chain_tail && k == nb) prev = 0;
+                    const int c = min(32, L.r - 32 * (s - maxnb));
+                    if (tr.integrated && !tr.chain_tail && s == maxnb) prev = 0;
                     for (int i = 0; i < c; ++i) {
                         const uint32_t x = col[33 * i];
                         const uint32_t d = diff ? x - prev : x;
@@ -1904,7 +1975,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                         if (vfill >= 4) {
                             if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
                             ++pos; vacc >>= 32; vfill -= 4;
-                            if (vfill >= 4) {
+                            if (vfill >= 4) { // only after a 5-byte value
                                 if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
                                 ++pos; vacc >>= 32; vfill -= 4;
                             }
@@ -1912,7 +1983,10 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                     }
                 }
                 ovf = __any_sync(kFull, t_ovf);
+                __syncwarp(); // this stage's tile has been read: it may be requested again
+                if (ovf) break;
             }
+            cp_async_wait<0>();
             bool t_ovf = false;
             if (vfill > 0) { // zero-padded to a word (VariableByte.java:69-70)
                 if (pos < SL_OC) my_out[33 * pos] = (uint32_t)vacc; else t_ovf = true;
@@ -1929,18 +2003,21 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
         bool emit_slow = false;
         if (ovf) {
             lw = 0;
-            if (tr.blocks) { // sizes by the warp-per-list routine, one list at a time
+            if (__any_sync(kFull, lane < nl && tr.fastpfor && L.n64 >= tr.fp_block)) {
+                if (lane == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
+            } else { // sizes by the warp-per-list routines, one list at a time
                 emit_slow = true;
                 for (int j = 0; j < nl; ++j) {
-                    const int64_t bj = __shfl_sync(kFull, beg, j), nj = __shfl_sync(kFull, n64, j);
+                    const int64_t bj = __shfl_sync(kFull, L.beg, j), nj = __shfl_sync(kFull, L.n64, j);
                     __syncwarp();
-                    const int64_t w = warp_bp_list_encode<false>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{nullptr, a.app}, a.app, s_in, lane);
+                    const int64_t w = warp_short_list_encode<false>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{nullptr, a.app}, a.app,
+                                                                    s_inw[warp][0], lane);
                     if (lane == j) lw = w;
                 }
-            } else if (lane == 0)
-                atomicMax(a.err, 2); // the host takes the batched kernels
+                __syncwarp();
+            }
         }
-        // ---- place of every list inside the batch, of the batch inside the output
+        // ---- place of every list inside the batch; publish the batch's size
         long long incl = lw;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1949,12 +2026,19 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
         }
         const long long T = __shfl_sync(kFull, incl, 31), lex = incl - lw;
         if (lane == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+        // ---- the next batch: its ticket, its extents and its first stage go out before this batch's look-back
+        const int64_t c_batch = batch, c_beg = L.beg, c_n64 = L.n64;
+        const int c_nl = nl;
+        take_batch(batch, nl, L, vbase, slow, maxnb, nst);
+        if (nst > 0) request_stage(0, L, maxnb, vbase, s_inw[warp][0]);
+        // ---- decoupled look-back, 32 predecessors per round
         long long base = 0;
-        if (batch > 0) {
-            for (int64_t j = batch - 1;; j -= 32) {
+        if (c_batch > 0) {
+            for (int64_t j = c_batch - 1;; j -= 32) {
                 const int64_t idx = j - lane;
                 uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
-                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                if (idx >= 0)
+                    while (((st = ld_acquire_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
                 const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
                 const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
                 long long v = lane <= first ? (long long)(st & kLbMask) : 0;
@@ -1963,92 +2047,117 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                 base += v;
                 if (inc) break;
             }
-            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
+            if (lane == 0) st_release_u64(a.state + c_batch, kLbInc | (uint64_t)(base + T));
         }
-        if (lane < nl) a.out_off[l0 + lane] = 4 * (base + lex);
-        if (lane == 0 && batch == a.nbatches - 1) {
+        if (lane < c_nl) a.out_off[l0 + lane] = 4 * (base + lex);
+        if (lane == 0 && c_batch == a.nbatches - 1) {
             *a.total = 4 * (base + T);
             a.out_off[a.nlists] = 4 * (base + T);
         }
         if (4 * (base + T) > a.cap) { // caller's buffer too small: report, write nothing
             if (lane == 0) atomicMax(a.err, 1);
+            __syncwarp();
             continue;
         }
         uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + base;
         if (!ovf) {
             const int ilw = (int)lw, ilex = (int)lex;
             const uint32_t *so = s_outw[warp];
+            const uint32_t sel = a.app ? 0x0123u : 0x3210u;
             __syncwarp();
-            for (int j = 0; j < nl; ++j) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) { // at most two words per lane and list (SL_OC <= 64)
                 const int wj = __shfl_sync(kFull, ilw, j), oj = __shfl_sync(kFull, ilex, j);
-                for (int w = lane; w < wj; w += 32) {
-                    const uint32_t x = so[33 * w + j];
-                    gout[oj + w] = a.app ? bswap32(x) : x;
-                }
+                if (lane < wj) gout[oj + lane] = __byte_perm(so[33 * lane + j], 0, sel);
+                if (lane + 32 < wj) gout[oj + lane + 32] = __byte_perm(so[33 * (lane + 32) + j], 0, sel);
             }
         } else if (emit_slow) {
-            for (int j = 0; j < nl; ++j) {
-                const int64_t bj = __shfl_sync(kFull, beg, j), nj = __shfl_sync(kFull, n64, j);
+            // (the next batch's first stage may be landing in tile 0: the slow path stages in tile 1)
+            for (int j = 0; j < c_nl; ++j) {
+                const int64_t bj = __shfl_sync(kFull, c_beg, j), nj = __shfl_sync(kFull, c_n64, j);
                 const long long oj = __shfl_sync(kFull, lex, j);
                 __syncwarp();
-                warp_bp_list_encode<true>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{gout + oj, a.app}, a.app, s_in, lane);
+                warp_short_list_encode<true>(tr, ValSeq{a.vals + bj, a.delta}, nj, WordSink{gout + oj, a.app}, a.app, s_inw[warp][1], lane);
             }
         }
+        __syncwarp(); // the columns have been read: the next batch may write them
     }
+    cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_decode(const FastDecArgs a, int64_t nbatches)
+__global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a, int64_t nbatches)
 {
-    __shared__ uint32_t s_valw[SL_WARPS][32 * 33];
-    __shared__ uint32_t s_wdw[SL_WARPS][SL_OC * 33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *s_val = s_valw[warp], *s_wd = s_wdw[warp];
-    const uint32_t *my = s_wd + lane; // word p of my list's stream: my[33 * p]
+    __shared__ uint32_t s_val[32 * 33];
+    __shared__ uint32_t s_wdw[2][SL_OC * 33];
+    const int lane = threadIdx.x;
     const CodecTraits tr = codec_traits(a.codec);
     const bool diff = a.delta || tr.integrated;
-    for (int64_t batch = (int64_t)blockIdx.x * SL_WARPS + warp; batch < nbatches; batch += (int64_t)gridDim.x * SL_WARPS) {
+    const uint32_t sel = a.app ? 0x0123u : 0x3210u; // big-endian framing: words are swapped as they are read
+
+    struct Ext { int64_t ib, ob, aw, n64; bool bad, big; };
+    // a batch's extents, and the request for its streams (transposed: word w of list j at 33 w + j)
+    auto prefetch = [&](int64_t batch, Ext &x, uint32_t *wd) {
+        x = Ext{0, 0, 0, 0, false, false};
+        if (batch < nbatches) {
+            const int64_t l0 = batch * 32;
+            const int nl = (int)min((int64_t)32, a.nlists - l0);
+            int64_t ie = 0;
+            if (lane < nl) {
+                x.ib = a.in_off[l0 + lane]; ie = a.in_off[l0 + lane + 1];
+                x.ob = a.out_off[l0 + lane]; x.n64 = a.out_off[l0 + lane + 1] - x.ob;
+            }
+            x.bad = __any_sync(kFull, ((x.ib | ie) & 3) != 0 || ie < x.ib || x.n64 < 0);
+            x.aw = (ie - x.ib) >> 2;
+            const int64_t obase = __shfl_sync(kFull, x.ob, 0);
+            x.big = __any_sync(kFull, x.aw > SL_OC || x.n64 > 32 * SL_OC || x.ob - obase > 0x3fffffff || (tr.fastpfor && x.n64 >= tr.fp_block));
+            if (!x.bad && !x.big) {
+                const int avail = (int)x.aw;
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    const int awj = __shfl_sync(kFull, avail, j);
+                    const int64_t ibj = __shfl_sync(kFull, x.ib, j);
+                    const uint32_t *g = reinterpret_cast<const uint32_t *>(a.in + ibj) + lane;
+                    if (lane < awj) cp_async4(wd + 33 * lane + j, g);
+                    if (lane + 32 < awj) cp_async4(wd + 33 * (lane + 32) + j, g + 32);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int64_t stride = gridDim.x;
+    int64_t batch = blockIdx.x;
+    Ext cur, nxt;
+    prefetch(batch, cur, s_wdw[0]);
+    for (int it = 0; batch < nbatches; batch += stride, ++it, cur = nxt) {
+        __syncwarp(); // the previous batch's area has been read: the next batch's streams may land in it
+        prefetch(batch + stride, nxt, s_wdw[(it + 1) & 1]);
+        cp_async_wait<1>();
+        __syncwarp();
         const int64_t l0 = batch * 32;
         const int nl = (int)min((int64_t)32, a.nlists - l0);
-        int64_t ib = 0, ie = 0, ob = 0, n64 = 0;
-        if (lane < nl) {
-            ib = a.in_off[l0 + lane]; ie = a.in_off[l0 + lane + 1];
-            ob = a.out_off[l0 + lane]; n64 = a.out_off[l0 + lane + 1] - ob;
-        }
-        if (__any_sync(kFull, ((ib | ie) & 3) != 0 || ie < ib || n64 < 0)) {
-            if (lane == 0) atomicMax(a.err, 1);
-            continue;
-        }
-        const int64_t aw = (ie - ib) >> 2;
-        const int64_t obase = __shfl_sync(kFull, ob, 0);
-        const bool big = aw > SL_OC || n64 > 32 * SL_OC || ob - obase > 0x3fffffff || (tr.fastpfor && n64 >= tr.fp_block);
-        if (__any_sync(kFull, big)) {
-            if (!tr.blocks) { if (lane == 0) atomicMax(a.err, 2); continue; } // the host takes the batched kernels
+        if (cur.bad) { if (lane == 0) atomicMax(a.err, 1); continue; }
+        if (cur.big) {
+            if (__any_sync(kFull, tr.fastpfor && cur.n64 >= tr.fp_block)) { if (lane == 0) atomicMax(a.err, 2); continue; } // the host takes the batched kernels
             for (int j = 0; j < nl; ++j) {
-                const int64_t ibj = __shfl_sync(kFull, ib, j), awj = __shfl_sync(kFull, aw, j);
-                const int64_t obj = __shfl_sync(kFull, ob, j), nj = __shfl_sync(kFull, n64, j);
+                const int64_t ibj = __shfl_sync(kFull, cur.ib, j), awj = __shfl_sync(kFull, cur.aw, j);
+                const int64_t obj = __shfl_sync(kFull, cur.ob, j), nj = __shfl_sync(kFull, cur.n64, j);
                 const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + ibj), a.app};
-                const bool ok = warp_bp_list_decode(tr, src, awj, nj, a.out + obj, a.delta, lane);
+                const bool ok = warp_short_list_decode(tr, src, awj, nj, a.out + obj, a.delta, lane);
                 if (!ok && lane == 0) atomicMax(a.err, 1);
                 __syncwarp();
             }
             continue;
         }
-        const int avail = (int)aw, n = (int)n64, oo = (int)(ob - obase);
-        // ---- stage the streams, transposed (at most two words per lane and list)
-        __syncwarp();
-        for (int j = 0; j < nl; ++j) {
-            const int awj = __shfl_sync(kFull, avail, j);
-            const int64_t ibj = __shfl_sync(kFull, ib, j);
-            const uint32_t *g = reinterpret_cast<const uint32_t *>(a.in + ibj);
-            if (lane < awj) { const uint32_t x = __ldg(g + lane); s_wd[33 * lane + j] = a.app ? bswap32(x) : x; }
-            if (lane + 32 < awj) { const uint32_t x = __ldg(g + lane + 32); s_wd[33 * (lane + 32) + j] = a.app ? bswap32(x) : x; }
-        }
-        __syncwarp();
+        const int64_t obase = __shfl_sync(kFull, cur.ob, 0);
+        const int avail = (int)cur.aw, n = (int)cur.n64, oo = (int)(cur.ob - obase);
+        const uint32_t *my = s_wdw[it & 1] + lane; // word p of my list's stream: my[33 * p]
+        auto rd = [&](int p) -> uint32_t { return __byte_perm(my[33 * p], 0, sel); };
         const int nb = tr.blocks ? n >> 5 : 0, ng4 = nb & ~3;
         int p = 0;
         bool ok = true;
-        if (tr.sk) { ok = lane >= nl || (avail >= 1 && my[0] == (uint32_t)n); p = 1; }
-        else if (n > 0 && (tr.fastpfor || tr.blocks)) { ok = avail >= 1 && my[0] == (uint32_t)(32 * nb); p = 1; }
+        if (tr.sk) { ok = lane >= nl || (avail >= 1 && rd(0) == (uint32_t)n); p = 1; }
+        else if (n > 0 && (tr.fastpfor || tr.blocks)) { ok = avail >= 1 && rd(0) == (uint32_t)(32 * nb); p = 1; }
         uint32_t carry = 0, hdr = 0, vv = 0;
         int vs = 0, vshift = 0;
         const int maxn = __reduce_max_sync(kFull, n);
@@ -2060,24 +2169,24 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_decode(const Fast
                 // ---- one block: width from the group header (BinaryPacking.java:102-123) or its own (:124-131)
                 int b = 33;
                 if (k < ng4) {
-                    if ((k & 3) == 0) { if (p < avail) hdr = my[33 * p++]; else ok = false; }
+                    if ((k & 3) == 0) { if (p < avail) hdr = rd(p++); else ok = false; }
                     b = (int)((hdr >> (24 - 8 * (k & 3))) & 255u);
                 } else if (p < avail)
-                    b = (int)min(my[33 * p++], 33u);
+                    b = (int)min(rd(p++), 33u);
                 if (b > 32 || p + b > avail) ok = false;
                 if (ok) {
                     uint32_t v[32];
                     const uint32_t *ptr = my + 33 * p;
                     if (b == 32) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = ptr[33 * i];
+                        for (int i = 0; i < 32; ++i) v[i] = __byte_perm(ptr[33 * i], 0, sel);
                     } else {
                         const uint32_t mask = (1u << b) - 1u;
                         uint64_t acc = 0;
                         int fill = 0;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            if (fill < b) { acc |= (uint64_t)(*ptr) << fill; ptr += 33; fill += 32; }
+                            if (fill < b) { acc |= (uint64_t)__byte_perm(*ptr, 0, sel) << fill; ptr += 33; fill += 32; }
                             v[i] = (uint32_t)acc & mask;
                             acc >>= b;
                             fill -= b;
@@ -2098,10 +2207,12 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_decode(const Fast
                 // ---- VariableByte.headlessUncompress (VariableByte.java:180-203); IntegratedVariableByte.java:40 restarts
                 if (tr.integrated && !tr.chain_tail && k == nb) carry = 0;
                 int got = 0;
+                uint32_t w = p < avail ? rd(p) : 0u;
                 while (got < c) {
                     if (p >= avail) { ok = false; break; }
-                    const uint32_t by = (my[33 * p] >> vs) & 0xffu;
-                    vs += 8; p += vs >> 5; vs &= 31;
+                    const uint32_t by = (w >> vs) & 0xffu;
+                    vs += 8;
+                    if (vs == 32) { vs = 0; ++p; w = p < avail ? rd(p) : 0u; }
                     vv += (by & 127u) << (vshift & 31);
                     if (by & 128u) {
                         if (diff) { carry += vv; vv = carry; }
@@ -2123,6 +2234,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_decode(const Fast
         }
         if (__any_sync(kFull, !ok) && lane == 0) atomicMax(a.err, 1);
     }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------- scan
@@ -2251,6 +2363,11 @@ static bool batched_applicable(int codec, bool delta, int64_t total_vals, int64_
 static bool shortlist_applicable(mcp_ctx *ctx, int codec, bool delta, int64_t total_vals, int64_t nlists)
 {
     if (ctx && !ctx->shortListCodec) return false;
+    // measured on C4 (profiles/r1/codec_short_lists.txt): twice as fast as the batched kernels when the whole list is a
+    // VariableByte tail (FastPFOR / FastPFOR128 below one block, VariableByte alone), slower than them for the
+    // BinaryPacking family, which they take only when asked to (option short_list_codec = 2)
+    const CodecTraits tr = codec_traits(codec);
+    if (tr.blocks && !(ctx && ctx->shortListCodec >= 2)) return false;
     return nlists > 0 && sl_codec_ok(codec, delta) && (double)total_vals <= SL_MAXAVG * (double)nlists;
 }
 
@@ -2369,8 +2486,8 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
             KScope ks(ctx, MCP_K_DECODE);
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0) {
-                const int64_t want = (nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
-                k_sl_decode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a, nbatches);
+                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * SL_DCTAS;
+                k_sl_decode<<<(unsigned)(nbatches < res ? nbatches : res), 32, 0, ctx->stream>>>(a, nbatches);
             } else if (!tr.fastpfor) k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
             else if (tr.fp_block == 256) k_fp_decode_fast<8><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
             else k_fp_decode_fast<4><<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);

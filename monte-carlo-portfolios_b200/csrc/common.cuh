@@ -122,7 +122,7 @@ struct mcp_ctx {
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
-    bool shortListCodec = true;    // thread-per-list kernels for lists averaging <= 144 values (codec_kernels.cu)
+    int shortListCodec = 1;        // thread-per-list kernels for lists averaging <= 144 values: 0 off, 1 where they win, 2 every codec
     int64_t shortListCalls = 0, shortListFallbacks = 0; // encode + decode calls they served / handed on to the batched kernels
     bool forceDense = false;       // debug: use the generic dense path even when F == 32
     void *hPinned = nullptr;       // small pinned staging (scalars)

@@ -35,7 +35,7 @@ def test_kat_through_the_c_abi(ctx):
     assert doc["algo"] == "bpacking+variablebyte" and doc["compressedByteSize"] == 36 and doc["uncompressedIntegerSize"] == 17
 
 
-@pytest.fixture(params=[(1, 1), (1, 0), (0, 0)], ids=["shortlist+batched", "batched", "warp-per-list"])
+@pytest.fixture(params=[(1, 2), (1, 1), (1, 0), (0, 0)], ids=["shortlist-everywhere", "default", "batched", "warp-per-list"])
 def codec_ctx(ctx, request):
     """The three kernel families behind the codec ABI: the thread-per-list kernels (lists averaging <= 144 values), the
     batched single-pass kernels (thread per block) and the warp-per-list size/scan/emit kernels that handle everything
@@ -368,6 +368,7 @@ def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
         pytest.skip("Delta before an integrated codec is not a combination the reference uses")
     rng = np.random.default_rng(1000 + 16 * codec + 2 * (1 if delta else 0) + framing)
     cid = codec | delta
+    ctx.set_option("short_list_codec", 2)
     for lengths in ([0, 1, 5, 31, 32, 33, 64, 96, 100, 127], [0, 1, 31, 32, 33, 64, 96, 100, 127, 128, 129, 160, 200, 255, 256, 300]):
         lists = _short_lists(rng, 333, lengths)
         vals = np.concatenate([cases.to_i32(v) for v in lists])
@@ -385,6 +386,7 @@ def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
         assert np.array_equal(ctx.codec_decode(cid, framing, out, out_off, off), vals)
         after = ctx.codec_stats()
         assert after["short_calls"] + after["short_fallbacks"] == mid["short_calls"] + mid["short_fallbacks"] + 1
+    ctx.set_option("short_list_codec", 1)
 
 
 @pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA,
@@ -397,6 +399,7 @@ def test_short_list_kernels_serve_c4(ctx, cid):
     rng = np.random.default_rng(77)
     vals, off = cases.breach_like_lists(rng, 4099, 10000, 0.01)
     nl = off.size - 1
+    ctx.set_option("short_list_codec", 2)
     before = ctx.codec_stats()
     out_off, out = ctx.codec_encode(cid, N.FRAME_APP, vals, off, cap=int(8 * vals.size + 64 * nl))
     back = ctx.codec_decode(cid, N.FRAME_APP, out, out_off, off)
@@ -427,6 +430,7 @@ def test_short_list_decode_rejects_malformed_streams(ctx):
     rng = np.random.default_rng(5)
     vals, off = cases.breach_like_lists(rng, 500, 10000, 0.01)
     cid = N.CODEC_BP32_VB | N.FLAG_DELTA
+    ctx.set_option("short_list_codec", 2)
     out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off)
     w = out.view(np.uint32)
     i = 123
@@ -443,13 +447,16 @@ def test_short_list_decode_rejects_malformed_streams(ctx):
             ctx.codec_decode(cid, N.FRAME_WORDS, bad, boff, off)
         assert e.value.code == N.MCP_E_FORMAT, what
     assert w[out_off[i] // 4] == 32 * ((off[i + 1] - off[i]) // 32)
+    ctx.set_option("short_list_codec", 1)
 
 
 def test_short_list_encode_reports_capacity(ctx):
     rng = np.random.default_rng(6)
     vals, off = cases.breach_like_lists(rng, 300, 10000, 0.01)
+    ctx.set_option("short_list_codec", 2)
     out_off, out = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off)
     with pytest.raises(mcp_b200.CapacityError):
         ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size) - 4)
     o2, b2 = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size))
     assert np.array_equal(b2, out) and np.array_equal(o2, out_off)
+    ctx.set_option("short_list_codec", 1)
