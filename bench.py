@@ -135,7 +135,7 @@ def cpu_baseline_risk(P, N, F, alpha, seed, target_s=12.0):
             "sample": f"{ps} of {P} portfolios x all {N} trials x {F} factors (valuation+moments+select+sort+encode), {dt:.1f} s"}, len(enc)
 
 
-def cpu_baseline_codec(n_lists=200_000, n_trials=10_000, rate=0.01, seed=0x5EED0004):
+def cpu_baseline_codec(n_lists=200_000, n_trials=10_000, rate=0.01, seed=0x5EED0004, fastpfor=False):
     from oracle import cref
     cores = host_cores()
     rng = np.random.default_rng(seed)
@@ -147,8 +147,8 @@ def cpu_baseline_codec(n_lists=200_000, n_trials=10_000, rate=0.01, seed=0x5EED0
     vals = np.cumsum(gaps)
     vals -= np.repeat(vals[off[:-1]] - gaps[off[:-1]], lens)  # restart each list near 0
     vals = vals.astype(np.int32)
-    cid = cref.CODEC_BP32_VB | cref.FLAG_DELTA
-    stride = 4 * 200
+    cid = (cref.CODEC_FASTPFOR256_VB if fastpfor else cref.CODEC_BP32_VB) | cref.FLAG_DELTA
+    stride = 4 * (200 if n_trials <= 10_000 else 40 + n_trials // 50)
     t0 = time.perf_counter()
     buf, blens = cref.batch_compress(cid, 1, vals, off, stride, nthreads=cores)
     t1 = time.perf_counter()
@@ -156,7 +156,8 @@ def cpu_baseline_codec(n_lists=200_000, n_trials=10_000, rate=0.01, seed=0x5EED0
     t2 = time.perf_counter()
     n = int(off[-1])
     return {"encode_ints_per_s": n / (t1 - t0), "decode_ints_per_s": n / (t2 - t1), "cores": cores, "kind": "port",
-            "sample": f"{n_lists} lists x ~{n // n_lists} ints (1% of {n_trials} trials), delta+BP32+VB app framing"}
+            "sample": f"{n_lists} lists x ~{n // n_lists} ints (1% of {n_trials} trials), "
+                      f"delta+{'FastPFOR256' if fastpfor else 'BP32'}+VB app framing"}
 
 
 def run_reference(args, rank, world):
@@ -433,46 +434,64 @@ def main():
     pk = peaks()
     hbm_peak = pk["hbm_gbs"] if pk else 6650.0
     if rank == 0 and not args.no_codec:
+        src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk else "6650 GB/s (of fallback)"
+
+        def codec_leg(cid, what, nl, ntrials):
+            """encode + decode of nl breach lists (1 % of ntrials trials each), device-resident, L2 flushed before every
+            timed call; algorithmic bytes = the ints (4 B each) + the encoded bytes + the CSR offsets in and out"""
+            dv, do, total = ctx.generate_breach_lists(nl, ntrials, 0.01, 0x5EED0004)
+            capb = 5 * total + 16 * nl
+            d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
+            enc_ms, dec_ms, enc_bytes = [], [], 0
+            for it in range(args.warmup + args.steps):
+                ctx.flush_l2()
+                ctx.sync()
+                ctx.timer_start()
+                enc_bytes = ctx.codec_encode_dev(cid, N.FRAME_APP, dv, do, nl, total, d_oo, d_out, capb)
+                t_e = ctx.timer_stop()
+                ctx.flush_l2()
+                ctx.sync()
+                ctx.timer_start()
+                ctx.codec_decode_dev(cid, N.FRAME_APP, d_out, d_oo, nl, d_back, do)
+                t_d = ctx.timer_stop()
+                if it >= args.warmup:
+                    enc_ms.append(t_e)
+                    dec_ms.append(t_d)
+            for p in (d_oo, d_out, d_back):  # (dv / do belong to the context)
+                ctx.dev_free(p)
+            e_ms, d_ms = float(np.mean(enc_ms)), float(np.mean(dec_ms))
+            algo_bytes = 4.0 * total + enc_bytes + 16.0 * nl
+            return {"workload": f"{nl} lists, 1% of {ntrials} trials (~{total // nl} ints each), {what}, app framing",
+                    "ints": int(total), "encoded_bytes": int(enc_bytes), "bytes_per_int": enc_bytes / total,
+                    "encode_ints_per_s": total / (e_ms * 1e-3), "decode_ints_per_s": total / (d_ms * 1e-3),
+                    "encode_ms": e_ms, "decode_ms": d_ms,
+                    "roofline_encode": {"bound": "hbm", "achieved": algo_bytes / (e_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": algo_bytes / (e_ms * 1e-3) / 1e9 / hbm_peak},
+                    "roofline_decode": {"bound": "hbm", "achieved": algo_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": algo_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak},
+                    "peak_source": src}
+
         nl = args.codec_lists
-        dv, do, total = ctx.generate_breach_lists(nl, 10_000, 0.01, 0x5EED0004)
-        ccid = N.CODEC_BP32_VB | N.FLAG_DELTA
-        capb = 4 * total + 16 * nl
-        d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
-        enc_ms, dec_ms, enc_bytes = [], [], 0
-        for it in range(args.warmup + args.steps):
-            ctx.flush_l2()
-            ctx.sync()
-            ctx.timer_start()
-            enc_bytes = ctx.codec_encode_dev(ccid, N.FRAME_APP, dv, do, nl, total, d_oo, d_out, capb)
-            t_e = ctx.timer_stop()
-            ctx.flush_l2()
-            ctx.sync()
-            ctx.timer_start()
-            ctx.codec_decode_dev(ccid, N.FRAME_APP, d_out, d_oo, nl, d_back, do)
-            t_d = ctx.timer_stop()
-            if it >= args.warmup:
-                enc_ms.append(t_e)
-                dec_ms.append(t_d)
-        for p in (d_oo, d_out, d_back):
-            ctx.dev_free(p)
-        e_ms, d_ms = float(np.mean(enc_ms)), float(np.mean(dec_ms))
-        algo_bytes = 4.0 * total + enc_bytes + 16.0 * nl  # ints + encoded bytes + CSR offsets (in and out)
-        codec = {"workload": f"c4: {nl} lists, 1% of 10000 trials (~{total // nl} ints each), delta + BinaryPacking + VariableByte, "
-                             "app framing (the loader's codec on gap-coded breach lists)",
-                 "ints": int(total), "encoded_bytes": int(enc_bytes), "bytes_per_int": enc_bytes / total,
-                 "encode_ints_per_s": total / (e_ms * 1e-3), "decode_ints_per_s": total / (d_ms * 1e-3),
-                 "encode_ms": e_ms, "decode_ms": d_ms,
-                 "roofline_encode": {"bound": "hbm", "achieved": algo_bytes / (e_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": algo_bytes / (e_ms * 1e-3) / 1e9 / hbm_peak},
-                 "roofline_decode": {"bound": "hbm", "achieved": algo_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": algo_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak},
-                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk else "6650 GB/s (of fallback)"}
+        # BASELINE config C4 under the codec the north star names.  A list of ~100 ints is shorter than one FastPFOR block
+        # (256), so Composition writes the 0 marker and the whole gap-coded list goes to VariableByte (FastPFOR.java:311-313)
+        codec = codec_leg(N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, "Delta + Composition(FastPFOR, VariableByte) [c4]", nl, 10_000)
+        # the same lists under the codec the reference's loader really uses (LoadPortfolios.java:725-726)
+        codec["loader_codec"] = codec_leg(N.CODEC_BP32_VB | N.FLAG_DELTA, "Delta + Composition(BinaryPacking, VariableByte) "
+                                          "[c4, the loader's codec]", nl, 10_000)
+        # lists long enough for FastPFOR pages (the risk step's own breach lists look like this)
+        codec["fastpfor_pages"] = codec_leg(N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, "Delta + Composition(FastPFOR, VariableByte), "
+                                            "3 FastPFOR blocks + a VariableByte tail per list", max(nl // 10, 1), 100_000)
+        st = ctx.codec_stats()
+        codec["kernels"] = {"calls_served_by_thread_per_list_kernels": st["short_calls"], "handed_on": st["short_fallbacks"],
+                            "calls_served_by_batched_kernels": st["fast_encodes"], "handed_back": st["fast_fallbacks"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_baseline_risk(P, Nn, F, alpha, seed)
         if codec is not None:
-            codec["cpu_baseline"] = cpu_baseline_codec()
+            codec["cpu_baseline"] = cpu_baseline_codec(fastpfor=True)
+            codec["loader_codec"]["cpu_baseline"] = cpu_baseline_codec()
+            codec["fastpfor_pages"]["cpu_baseline"] = cpu_baseline_codec(n_lists=20_000, n_trials=100_000, fastpfor=True)
 
     if rank == 0:
         print(json.dumps({

@@ -789,6 +789,19 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v)
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// the look-back state word carries everything a reader needs (flag | words): readers that consume nothing else the
+// writer stored can poll it relaxed
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // exclusive scan of one int per thread over the CTA (FE_THREADS = 4 warps); returns the exclusive prefix, *total = sum
 __device__ __forceinline__ int cta_excl_scan(int v, int *s_w /* [5] */, int *total)
 {
@@ -1877,10 +1890,10 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
             L.n64 = (a.list_off ? a.list_off[l0 + lane + 1] : (l0 + lane + 1) * a.uniform_len) - L.beg;
         }
         vbase = __shfl_sync(kFull, L.beg, 0);
-        const bool big = lane < nl && (L.beg - vbase > 0x3fffffff || L.n64 > 0x3fffffff || (tr.fastpfor && L.n64 >= tr.fp_block));
+        const bool big = lane < nl && (L.beg - vbase > 0x7fffff || L.n64 > 0x7fffff || (tr.fastpfor && L.n64 >= tr.fp_block));
         slow = __any_sync(kFull, big);
         if (!slow) {
-            L.off = (int)(L.beg - vbase); L.n = (int)L.n64;
+            L.off = lane < nl ? (int)(L.beg - vbase) : 0; L.n = (int)L.n64;
             L.nb = tr.blocks ? L.n >> 5 : 0; L.r = L.n - 32 * L.nb;
             maxnb = __reduce_max_sync(kFull, L.nb);
             nst = maxnb + ((__reduce_max_sync(kFull, L.r) + 31) >> 5);
@@ -1892,10 +1905,11 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
         if (s < maxnb) { src = L.off + 32 * s; cnt = s < L.nb ? 32 : 0; }
         else { const int t = s - maxnb; src = L.off + 32 * L.nb + 32 * t; cnt = min(32, max(0, L.r - 32 * t)); }
         const uint32_t *gv = a.vals + vbase + lane;
+        const int sc = (src << 6) | cnt; // one shuffle per list (src < 2^25 on this path)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int sj = __shfl_sync(kFull, src, j), cj = __shfl_sync(kFull, cnt, j);
-            if (lane < cj) cp_async4(tile + lane * 33 + j, gv + sj);
+            const int scj = __shfl_sync(kFull, sc, j);
+            if (lane < (scj & 63)) cp_async4(tile + lane * 33 + j, gv + (scj >> 6));
         }
         cp_async_commit();
     };
@@ -2025,7 +2039,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
             if (lane >= d) incl += t;
         }
         const long long T = __shfl_sync(kFull, incl, 31), lex = incl - lw;
-        if (lane == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+        if (lane == 0) st_relaxed_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
         // ---- the next batch: its ticket, its extents and its first stage go out before this batch's look-back
         const int64_t c_batch = batch, c_beg = L.beg, c_n64 = L.n64;
         const int c_nl = nl;
@@ -2038,7 +2052,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                 const int64_t idx = j - lane;
                 uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
                 if (idx >= 0)
-                    while (((st = ld_acquire_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
+                    while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
                 const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
                 const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
                 long long v = lane <= first ? (long long)(st & kLbMask) : 0;
@@ -2047,7 +2061,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
                 base += v;
                 if (inc) break;
             }
-            if (lane == 0) st_release_u64(a.state + c_batch, kLbInc | (uint64_t)(base + T));
+            if (lane == 0) st_relaxed_u64(a.state + c_batch, kLbInc | (uint64_t)(base + T));
         }
         if (lane < c_nl) a.out_off[l0 + lane] = 4 * (base + lex);
         if (lane == 0 && c_batch == a.nbatches - 1) {
@@ -2066,8 +2080,10 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
             const uint32_t sel = a.app ? 0x0123u : 0x3210u;
             __syncwarp();
 #pragma unroll 8
+            const int ow = (ilex << 7) | ilw; // one shuffle per list (ilex <= 32 SL_OC, ilw <= SL_OC)
             for (int j = 0; j < 32; ++j) { // at most two words per lane and list (SL_OC <= 64)
-                const int wj = __shfl_sync(kFull, ilw, j), oj = __shfl_sync(kFull, ilex, j);
+                const int owj = __shfl_sync(kFull, ow, j);
+                const int wj = owj & 127, oj = owj >> 7;
                 if (lane < wj) gout[oj + lane] = __byte_perm(so[33 * lane + j], 0, sel);
                 if (lane + 32 < wj) gout[oj + lane + 32] = __byte_perm(so[33 * (lane + 32) + j], 0, sel);
             }
@@ -2109,14 +2125,18 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
             x.bad = __any_sync(kFull, ((x.ib | ie) & 3) != 0 || ie < x.ib || x.n64 < 0);
             x.aw = (ie - x.ib) >> 2;
             const int64_t obase = __shfl_sync(kFull, x.ob, 0);
-            x.big = __any_sync(kFull, x.aw > SL_OC || x.n64 > 32 * SL_OC || x.ob - obase > 0x3fffffff || (tr.fastpfor && x.n64 >= tr.fp_block));
+            const int64_t ibase0 = __shfl_sync(kFull, x.ib, 0);
+            x.big = __any_sync(kFull, x.aw > SL_OC || x.n64 > 32 * SL_OC || x.ob - obase > 32 * 32 * SL_OC || x.ib - ibase0 > 4 * 32 * SL_OC ||
+                                          (tr.fastpfor && x.n64 >= tr.fp_block));
             if (!x.bad && !x.big) {
-                const int avail = (int)x.aw;
-#pragma unroll 4
+                const int64_t ibase = __shfl_sync(kFull, x.ib, 0);
+                const int ra = ((int)((x.ib - ibase) >> 2) << 7) | (int)x.aw; // one shuffle per list: (first word << 7) | words
+                const uint32_t *g0 = reinterpret_cast<const uint32_t *>(a.in + ibase) + lane;
+#pragma unroll 8
                 for (int j = 0; j < 32; ++j) {
-                    const int awj = __shfl_sync(kFull, avail, j);
-                    const int64_t ibj = __shfl_sync(kFull, x.ib, j);
-                    const uint32_t *g = reinterpret_cast<const uint32_t *>(a.in + ibj) + lane;
+                    const int raj = __shfl_sync(kFull, ra, j);
+                    const int awj = raj & 127;
+                    const uint32_t *g = g0 + (raj >> 7);
                     if (lane < awj) cp_async4(wd + 33 * lane + j, g);
                     if (lane + 32 < awj) cp_async4(wd + 33 * (lane + 32) + j, g + 32);
                 }
@@ -2151,6 +2171,7 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
         }
         const int64_t obase = __shfl_sync(kFull, cur.ob, 0);
         const int avail = (int)cur.aw, n = (int)cur.n64, oo = (int)(cur.ob - obase);
+        const int on = (oo << 12) | n; // n <= 32 SL_OC = 1792, oo <= 32 x 1792
         const uint32_t *my = s_wdw[it & 1] + lane; // word p of my list's stream: my[33 * p]
         auto rd = [&](int p) -> uint32_t { return __byte_perm(my[33 * p], 0, sel); };
         const int nb = tr.blocks ? n >> 5 : 0, ng4 = nb & ~3;
@@ -2226,9 +2247,9 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
             // ---- the round's values leave: 128 contiguous bytes per list
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int oj = __shfl_sync(kFull, oo, j), nj = __shfl_sync(kFull, n, j);
+                const int onj = __shfl_sync(kFull, on, j); // (oo << 12) | n: one shuffle per list
                 const int idx = 32 * k + lane;
-                if (idx < nj) gout[oj + idx] = s_val[33 * lane + j];
+                if (idx < (onj & 4095)) gout[(onj >> 12) + idx] = s_val[33 * lane + j];
             }
             __syncwarp();
         }
@@ -2360,14 +2381,15 @@ static bool batched_applicable(int codec, bool delta, int64_t total_vals, int64_
 }
 
 // the short-list (thread-per-list) kernels: every codec, lists averaging <= SL_MAXAVG values
-static bool shortlist_applicable(mcp_ctx *ctx, int codec, bool delta, int64_t total_vals, int64_t nlists)
+static bool shortlist_applicable(mcp_ctx *ctx, int codec, bool delta, int64_t total_vals, int64_t nlists, bool encode)
 {
     if (ctx && !ctx->shortListCodec) return false;
-    // measured on C4 (profiles/r1/codec_short_lists.txt): twice as fast as the batched kernels when the whole list is a
-    // VariableByte tail (FastPFOR / FastPFOR128 below one block, VariableByte alone), slower than them for the
-    // BinaryPacking family, which they take only when asked to (option short_list_codec = 2)
+    // measured on C4 (profiles/r1/codec_short_lists.txt): the encoder beats the batched kernels for every codec (0.39 vs
+    // 0.41 ms for the BinaryPacking family, 0.51 vs 1.59 ms when the whole list is a VariableByte tail -- FastPFOR /
+    // FastPFOR128 below one block, VariableByte alone); the decoder only for the latter (0.55 vs 0.88 ms; 0.43 vs 0.37 ms for
+    // the BinaryPacking family, which it takes only when asked to: option short_list_codec = 2)
     const CodecTraits tr = codec_traits(codec);
-    if (tr.blocks && !(ctx && ctx->shortListCodec >= 2)) return false;
+    if (!encode && tr.blocks && !(ctx && ctx->shortListCodec >= 2)) return false;
     return nlists > 0 && sl_codec_ok(codec, delta) && (double)total_vals <= SL_MAXAVG * (double)nlists;
 }
 
@@ -2376,7 +2398,7 @@ bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, boo
     const int codec = codec_id & MCP_CODEC_MASK;
     const bool delta = (codec_id & MCP_FLAG_DELTA) != 0;
     (void)encode; // both directions
-    return batched_applicable(codec, delta, total_vals, nlists) || shortlist_applicable(nullptr, codec, delta, total_vals, nlists);
+    return batched_applicable(codec, delta, total_vals, nlists) || shortlist_applicable(nullptr, codec, delta, total_vals, nlists, encode);
 }
 
 // upper bound of the encoded size in bytes for the fast-path codecs: 33 words per 32-int block worst case, a 31-value
@@ -2414,7 +2436,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.out = d_out;
     a.cap = d_out ? cap : 0;
     const bool batched = batched_applicable(a.codec, a.delta, total_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists, true);
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
     // pass 0: thread-per-list kernel (short lists); pass 1: thread-per-block kernels
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
@@ -2473,7 +2495,7 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     a.out = reinterpret_cast<uint32_t *>(d_out);
     a.out_off = d_out_off;
     const bool batched = batched_applicable(a.codec, a.delta, total_out_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists, false);
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
     MCP_CUDA(ctx, ctx->dErr.reserve(64));
     a.err = ctx->dErr.as<int>();

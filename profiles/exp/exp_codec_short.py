@@ -12,7 +12,7 @@ capb = 5 * total + 16 * nl
 d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
 for name, cid in (("bp32+vb|delta", N.CODEC_BP32_VB | N.FLAG_DELTA), ("fastpfor256+vb|delta", N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA),
                   ("ibp32+ivb", N.CODEC_IBP32_IVB)):
-    for short in (1, 0, 1):
+    for short in (2, 0, 2):
         ctx.set_option("short_list_codec", short)
         e, d = [], []
         for it in range(8):

@@ -6,7 +6,8 @@ from mcp_b200 import native as N
 ctx = mcp_b200.Context(0)
 nl = 1_000_000
 dv, do, total = ctx.generate_breach_lists(nl, 10_000, 0.01, 0x5EED0004)
-cid = N.CODEC_BP32_VB | N.FLAG_DELTA
+cid = (N.CODEC_FASTPFOR256_VB if len(sys.argv) > 1 and sys.argv[1] == "fp" else N.CODEC_BP32_VB) | N.FLAG_DELTA
+ctx.set_option("short_list_codec", 2)
 capb = 4 * total + 16 * nl
 d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
 for _ in range(2):
