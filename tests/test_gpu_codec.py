@@ -301,15 +301,16 @@ def test_empty_batch_and_empty_lists(ctx):
     assert np.array_equal(ctx.codec_decode(N.CODEC_BP32_VB, N.FRAME_APP, out, out_off, off), [7, 8, 9])
 
 
-def test_full_size_c4_properties(ctx):
-    """BASELINE config C4 at full size (1 M lists at 1 % of 10 000 trials), device-resident: a bit-exact
-    encode -> decode round trip, plus a spot check of 64 lists against the oracle generator + oracle codec."""
+@pytest.mark.parametrize("cid", [N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_BP32_VB | N.FLAG_DELTA], ids=["fastpfor256+delta", "bp+delta"])
+def test_full_size_c4_properties(ctx, cid):
+    """BASELINE config C4 at full size (1 M lists at 1 % of 10 000 trials), device-resident, under the codec the north
+    star names and under the loader's: a bit-exact encode -> decode round trip, plus a spot check of 64 lists against
+    the oracle generator + oracle codec."""
     nl = 1_000_000
     dv, do, total = ctx.generate_breach_lists(nl, 10000, 0.01, 0x5EED0004)
     assert 0.95e8 < total < 1.05e8
     d_out_off = ctx.dev_alloc(8 * (nl + 1))
-    cid = N.CODEC_BP32_VB | N.FLAG_DELTA
-    cap = 4 * total + 16 * nl
+    cap = 5 * total + 16 * nl
     d_out = ctx.dev_alloc(cap)
     d_back = ctx.dev_alloc(4 * total + 16)
     try:
