@@ -139,8 +139,9 @@ int mcp_codec_decode(mcp_ctx *ctx, int codec_id, int framing,
 int mcp_codec_stats(mcp_ctx *ctx, int64_t *fast_encodes, int64_t *fast_fallbacks);
 /* same for the thread-per-list kernels that take lists averaging <= 144 values (BASELINE config C4's ~100-int breach
  * lists): encode + decode calls they served, and calls they handed on to the batched kernels because a list did not
- * fit (a FastPFOR list of a block or more, or more than 64 compressed words).  mcp_set_option("short_list_codec", 0)
- * turns them off. */
+ * fit (a FastPFOR list of a whole block or more).  mcp_set_option("short_list_codec", v): 0 = off, 1 (default) = where
+ * they are the faster kernels (the encoder for every codec, the decoder for FastPFOR / VariableByte), 2 = everywhere.
+ * Bytes are identical whichever kernels run. */
 int mcp_codec_stats_short(mcp_ctx *ctx, int64_t *short_calls, int64_t *short_fallbacks);
 
 /* ----------------------------------------------------- batched codec, device
