@@ -461,3 +461,54 @@ def test_short_list_encode_reports_capacity(ctx):
     o2, b2 = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size))
     assert np.array_equal(b2, out) and np.array_equal(o2, out_off)
     ctx.set_option("short_list_codec", 1)
+
+
+@pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_VB, N.CODEC_SK_IBP32_IVB],
+                         ids=["bp+delta", "fastpfor256+delta", "vb", "skibp"])
+@pytest.mark.parametrize("short", [2, 0], ids=["thread-per-list", "batched"])
+def test_device_codec_stays_inside_its_buffers(ctx, cid, short):
+    """No compute-sanitizer on this pool: the device-resident entry points run between guard words instead.  Output
+    offsets, the encoded stream and the decoded values each sit in a buffer of exactly the size the call is entitled to,
+    followed by 4 KiB of a known pattern that must survive (mixed lengths, so that the in-kernel warp-per-list route
+    and the last, partial warp batch are exercised too)."""
+    rng = np.random.default_rng(31 + cid)
+    lists = _short_lists(rng, 1000 + 13, [0, 1, 31, 32, 33, 64, 96, 100, 127, 128, 129, 160, 200])
+    vals = np.concatenate([cases.to_i32(v) for v in lists])
+    off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum([len(v) for v in lists], out=off[1:])
+    nl, total = len(lists), int(vals.size)
+    ref_off, ref = ctx.codec_encode(cid, N.FRAME_APP, vals, off)
+    enc_bytes = int(ref.size)
+    guard = np.full(1024, 0x5AC3A55A, np.uint32)
+    sizes = {"vals": 4 * total, "off": 8 * (nl + 1), "ooff": 8 * (nl + 1), "enc": enc_bytes, "back": 4 * total}
+    bufs = {k: ctx.dev_alloc(v + guard.nbytes) for k, v in sizes.items()}
+    try:
+        ctx.set_option("short_list_codec", short)
+        for k, v in sizes.items():
+            ctx.h2d(bufs[k] + v, guard)
+        ctx.h2d(bufs["vals"], vals)
+        ctx.h2d(bufs["off"], off)
+        got = ctx.codec_encode_dev(cid, N.FRAME_APP, bufs["vals"], bufs["off"], nl, total, bufs["ooff"], bufs["enc"], enc_bytes)
+        assert got == enc_bytes
+        ctx.codec_decode_dev(cid, N.FRAME_APP, bufs["enc"], bufs["ooff"], nl, bufs["back"], bufs["off"])
+        out = np.empty(enc_bytes, np.uint8)
+        ooff = np.empty(nl + 1, np.int64)
+        back = np.empty(total, np.int32)
+        ctx.d2h(out, bufs["enc"])
+        ctx.d2h(ooff, bufs["ooff"])
+        ctx.d2h(back, bufs["back"])
+        assert np.array_equal(ooff, ref_off) and np.array_equal(out, ref) and np.array_equal(back, vals)
+        for k, v in sizes.items():
+            g = np.empty_like(guard)
+            ctx.d2h(g, bufs[k] + v)
+            assert np.array_equal(g, guard), f"guard after `{k}` overwritten"
+        # one byte less than needed: reported, and still nothing outside
+        with pytest.raises(mcp_b200.CapacityError):
+            ctx.codec_encode_dev(cid, N.FRAME_APP, bufs["vals"], bufs["off"], nl, total, bufs["ooff"], bufs["enc"], enc_bytes - 4)
+        g = np.empty_like(guard)
+        ctx.d2h(g, bufs["enc"] + enc_bytes)
+        assert np.array_equal(g, guard)
+    finally:
+        ctx.set_option("short_list_codec", 1)
+        for p in bufs.values():
+            ctx.dev_free(p)
