@@ -42,6 +42,25 @@ E_SCALE, S_DRIFT = 100.0, 0.05
 METRIC, UNIT = "portfolio_scenario_valuations_per_sec", "valuations/s"
 
 
+_JSON_OUT = None
+
+
+def keep_stdout_for_the_json_line():
+    """Libraries print to fd 1 (NCCL's version banner, for one): point fd 1 at stderr for the run and keep the real
+    stdout for the ONE JSON line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -174,7 +193,7 @@ def run_reference(args, rank, world):
     v = float(np.mean(vals))
     cb["value"] = v
     ms = 1e3 * P * N / v
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -248,7 +267,7 @@ def run_c5(args, rank, local_rank, world):
     v_ms = prof["value"]["ms"] / args.steps
     flops = 2.0 * F * P * Nl  # per rank
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": P * n_global / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -284,6 +303,7 @@ def main():
     ap.add_argument("--codec-lists", type=int, default=1_000_000)
     ap.add_argument("--c5-portfolios", type=int, default=0, help="override the c5 portfolio count (smaller smoke runs)")
     args = ap.parse_args()
+    keep_stdout_for_the_json_line()
     # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline must use every host core, and libgomp reads
     # the variable when it is first loaded (with the oracle, later)
     os.environ["OMP_NUM_THREADS"] = str(host_cores())
@@ -494,7 +514,7 @@ def main():
             codec["fastpfor_pages"]["cpu_baseline"] = cpu_baseline_codec(n_lists=20_000, n_trials=100_000, fastpfor=True)
 
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
