@@ -67,7 +67,11 @@ enum {
     MCP_CODEC_SK_IBP32_IVB   = 4, /* new IntegratedIntCompressor()  (n, then headless stream)   IntegratedIntCompressor.java:38-62 */
     MCP_CODEC_VB             = 5, /* new VariableByte()                                         VariableByte.java:32     */
     MCP_CODEC_SK_BP32_VB     = 6, /* new IntCompressor()            (n, then headless stream)   IntCompressor.java:38-61 */
-    MCP_CODEC_COUNT          = 7,
+    MCP_CODEC_SK_FASTPFOR256_VB = 7, /* new IntCompressor(new SkippableComposition(new FastPFOR(), new VariableByte()))
+                                        (n, then the headless stream: FastPFOR pages without their count word, VariableByte tail)
+                                        IntCompressor.java:27-61, SkippableComposition.java:37-54, FastPFOR.java:92-105,222-231 */
+    MCP_CODEC_SK_FASTPFOR128_VB = 8, /* the same over new FastPFOR128()                          FastPFOR128.java:33      */
+    MCP_CODEC_COUNT          = 9,
     MCP_CODEC_MASK           = 0xff,
     MCP_FLAG_DELTA           = 0x100 /* Delta.delta(int[]) before compress, inverse after uncompress (Delta.java:24-28,84-88) */
 };
@@ -108,6 +112,16 @@ int64_t mcp_codec_max_bytes(int codec_id, int framing, int64_t n);
  */
 int mcp_codec_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
                        int32_t *out, int32_t out_cap, int32_t *out_words);
+/* SkippableIntegerCODEC.headlessCompress(in, inpos, inlength, out, outpos) (SkippableIntegerCODEC.java:43-48) of the
+ * composition behind one of the MCP_CODEC_SK_* ids (SkippableComposition(BinaryPacking | FastPFOR | FastPFOR128, VariableByte),
+ * SkippableIntegratedComposition(IntegratedBinaryPacking, IntegratedVariableByte) with initvalue 0): the stream WITHOUT
+ * any count word -- what IntCompressor.compress writes after compressed[0].  MCP_E_ARG for the other ids. */
+int mcp_codec_headless_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
+                                int32_t *out, int32_t out_cap, int32_t *out_words);
+/* SkippableIntegerCODEC.headlessUncompress(in, inpos, inlength, out, outpos, num) (:58-66): exactly `num` ints are
+ * produced (out must hold them); *in_words receives the ints consumed (what Java adds to inpos). */
+int mcp_codec_headless_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
+                                  int32_t *out, int32_t num, int32_t *in_words);
 /* IntegerCODEC.uncompress(in, inpos, inlength, out, outpos): *out_count = ints produced */
 int mcp_codec_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
                          int32_t *out, int32_t out_cap, int32_t *out_count);

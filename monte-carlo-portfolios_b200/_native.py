@@ -17,8 +17,9 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mcp.h")
 MCP_OK, MCP_E_ARG, MCP_E_CAP, MCP_E_CUDA, MCP_E_NOMEM, MCP_E_FORMAT, MCP_E_STATE, MCP_E_UNSUPPORTED, MCP_E_NCCL = (
     0, -1, -2, -3, -4, -5, -6, -7, -8)
 
-CODEC_BP32_VB, CODEC_FASTPFOR256_VB, CODEC_FASTPFOR128_VB, CODEC_IBP32_IVB, CODEC_SK_IBP32_IVB, CODEC_VB, CODEC_SK_BP32_VB = range(7)
-CODEC_COUNT = 7
+(CODEC_BP32_VB, CODEC_FASTPFOR256_VB, CODEC_FASTPFOR128_VB, CODEC_IBP32_IVB, CODEC_SK_IBP32_IVB, CODEC_VB, CODEC_SK_BP32_VB,
+ CODEC_SK_FASTPFOR256_VB, CODEC_SK_FASTPFOR128_VB) = range(9)
+CODEC_COUNT = 9
 FLAG_DELTA = 0x100
 FRAME_WORDS, FRAME_APP = 0, 1
 K_VALUE, K_SELECT, K_ENCODE, K_DECODE, K_SCAN, K_GEN, K_MOMENTS, K_COMM, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
@@ -70,6 +71,8 @@ def lib() -> C.CDLL:
         "mcp_codec_max_bytes": (i64, [C.c_int, C.c_int, i64]),
         "mcp_codec_compress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
         "mcp_codec_uncompress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
+        "mcp_codec_headless_compress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
+        "mcp_codec_headless_uncompress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
         "mcp_get_compressed_instruments": (C.c_int, [vp, C.c_int, vp, i32, vp, i64, P(i64)]),
         "mcp_get_decompressed_instruments": (C.c_int, [vp, C.c_int, vp, i64, i32, vp]),
         "mcp_codec_encode": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp, i64, P(i64)]),

@@ -155,11 +155,67 @@ class VariableByteCodec(IntegerCODEC):
         super().__init__(N.CODEC_VB, ctx, "VariableByte")
 
 
+_SKIPPABLE = {
+    ("BinaryPacking", "VariableByte"): N.CODEC_SK_BP32_VB,
+    ("FastPFOR", "VariableByte"): N.CODEC_SK_FASTPFOR256_VB,
+    ("FastPFOR128", "VariableByte"): N.CODEC_SK_FASTPFOR128_VB,
+    ("IntegratedBinaryPacking", "IntegratedVariableByte"): N.CODEC_SK_IBP32_IVB,
+}
+
+
+class SkippableComposition:
+    """SkippableComposition.java:37-54 (and differential/SkippableIntegratedComposition.java:46-71 with initvalue 0) behind
+    the SkippableIntegerCODEC interface (SkippableIntegerCODEC.java:43-66): the stream carries no count word, the caller
+    supplies `num` when decoding."""
+
+    def __init__(self, f1: _Stage, f2: _Stage, ctx: Context | None = None):
+        key = (f1.name, f2.name)
+        if key not in _SKIPPABLE:
+            raise NotImplementedError(f"no sm_100a kernel for SkippableComposition({f1}, {f2}); supported: {sorted(_SKIPPABLE)}")
+        self.codec_id = _SKIPPABLE[key]
+        self._ctx = ctx
+        self._name = f"{f1}+{f2}"
+
+    @property
+    def ctx(self) -> Context:
+        return self._ctx or default_context()
+
+    def headlessCompress(self, in_, inpos: IntWrapper, inlength: int, out, outpos: IntWrapper):
+        src = as_i32(in_)[inpos.get(): inpos.get() + inlength]
+        room = len(out) - outpos.get()
+        words = self.ctx.headless_compress_ints(self.codec_id, src, out_cap=max(room, 0))
+        out[outpos.get(): outpos.get() + words.size] = words
+        inpos.add(inlength)
+        outpos.add(words.size)
+
+    def headlessUncompress(self, in_, inpos: IntWrapper, inlength: int, out, outpos: IntWrapper, num: int):
+        src = as_i32(in_)[inpos.get(): inpos.get() + inlength]
+        if len(out) - outpos.get() < num:
+            raise IndexError("out too small")  # Java: ArrayIndexOutOfBoundsException
+        vals, used = self.ctx.headless_uncompress_ints(self.codec_id, src, num)
+        out[outpos.get(): outpos.get() + num] = vals
+        inpos.add(used)
+        outpos.add(num)
+
+    def toString(self) -> str:
+        return self._name
+
+    __repr__ = toString
+
+
 class IntCompressor:
-    """IntCompressor.java:38-61 (default codec SkippableComposition(BinaryPacking, VariableByte))."""
+    """IntCompressor.java:27-61: default codec SkippableComposition(BinaryPacking, VariableByte), or the one given
+    (IntCompressor(SkippableIntegerCODEC c), :27-29)."""
     _codec = N.CODEC_SK_BP32_VB
 
-    def __init__(self, ctx: Context | None = None):
+    def __init__(self, codec: SkippableComposition | None = None, ctx: Context | None = None):
+        if isinstance(codec, Context):  # (older call sites passed the context first)
+            codec, ctx = None, codec
+        if codec is not None:
+            if codec.codec_id == N.CODEC_SK_IBP32_IVB:
+                raise NotImplementedError("integrated compositions belong to IntegratedIntCompressor")
+            self._codec = codec.codec_id
+            ctx = ctx or codec._ctx
         self._ctx = ctx
 
     @property

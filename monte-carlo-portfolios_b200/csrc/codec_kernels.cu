@@ -38,6 +38,8 @@ __host__ __device__ inline CodecTraits codec_traits(int codec)
     case MCP_CODEC_SK_IBP32_IVB: t.blocks = true; t.integrated = true; t.sk = true; t.chain_tail = true; break;
     case MCP_CODEC_VB: break;
     case MCP_CODEC_SK_BP32_VB: t.blocks = true; t.sk = true; break;
+    case MCP_CODEC_SK_FASTPFOR256_VB: t.fastpfor = true; t.fp_block = 256; t.sk = true; break;
+    case MCP_CODEC_SK_FASTPFOR128_VB: t.fastpfor = true; t.fp_block = 128; t.sk = true; break;
     }
     return t;
 }
@@ -529,8 +531,10 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
             int64_t m = 0;
             if (tr.fastpfor) {
                 m = n - n % tr.fp_block;
-                if (WRITE && lane == 0) sink.put(pos, (uint32_t)m); // header, or Composition's 0 marker
-                ++pos;
+                if (!tr.sk) { // FastPFOR.compress's count word, or Composition's 0 marker; headlessCompress has neither
+                    if (WRITE && lane == 0) sink.put(pos, (uint32_t)m);
+                    ++pos;
+                }
                 if (m > 0) {
                     // FastPFOR writes native words (byte-granular metadata); APP framing swaps afterwards
                     int64_t w;
@@ -622,15 +626,15 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_decode(const DecArgs a)
         if (ok && n > 0) {
             int64_t m = 0;
             uint32_t carry = 0;
-            if (tr.fastpfor || (tr.blocks && !tr.sk)) {
+            if (!tr.sk && (tr.fastpfor || tr.blocks)) {
                 ok = p < avail;
                 if (ok) {
                     m = src.get(p++);
                     const int64_t blk = tr.fastpfor ? tr.fp_block : 32;
                     ok = (m == n - n % blk);
                 }
-            } else if (tr.blocks)
-                m = n & ~(int64_t)31;
+            } else if (tr.blocks || tr.fastpfor)
+                m = n - n % (tr.fastpfor ? tr.fp_block : 32);
             if (ok && m > 0) {
                 if (tr.fastpfor) {
                     // FastPFOR pages were written as native words; APP framing stores them swapped.
@@ -1838,8 +1842,9 @@ __device__ __forceinline__ int64_t warp_short_list_encode(const CodecTraits tr, 
 {
     if (tr.blocks) return warp_bp_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
     int64_t pos = 0;
+    if (tr.sk) { if (WRITE && lane == 0) sink.put(0, (uint32_t)n); pos = 1; } // IntCompressor: compressed[0] = n
     if (n > 0) {
-        if (tr.fastpfor) { if (WRITE && lane == 0) sink.put(0, 0u); pos = 1; }
+        if (tr.fastpfor && !tr.sk) { if (WRITE && lane == 0) sink.put(0, 0u); pos = 1; }
         auto getv = [&](int64_t i) -> uint32_t { return x(i); };
         pos += warp_vb_encode<WRITE>(getv, n, sink, pos, stage, lane);
     }
@@ -1851,9 +1856,10 @@ __device__ __forceinline__ bool warp_short_list_decode(const CodecTraits tr, con
                                                        bool delta, int lane)
 {
     if (tr.blocks) return warp_bp_list_decode(tr, src, avail, n, out, delta, lane);
-    if (n == 0) return true;
     int64_t p = 0;
-    if (tr.fastpfor) { if (avail < 1 || src.get(0) != 0u) return false; p = 1; }
+    if (tr.sk) { if (avail < 1 || (int64_t)src.get(0) != n) return false; p = 1; }
+    if (n == 0) return true;
+    if (tr.fastpfor && !tr.sk) { if (avail < 1 || src.get(0) != 0u) return false; p = 1; }
     if (!warp_vb_decode<false>(src, p, avail, n, out, 0u, lane)) return false;
     if (delta) { __syncwarp(); warp_inverse_delta(out, n, lane); }
     return true;
@@ -2376,7 +2382,8 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
 // the batched (thread-per-block) kernels: BinaryPacking family and FastPFOR / FastPFOR128
 static bool batched_applicable(int codec, bool delta, int64_t total_vals, int64_t nlists)
 {
-    const bool ok = fast_codec_ok(codec, delta) || codec_traits(codec).fastpfor;
+    const CodecTraits tr = codec_traits(codec);
+    const bool ok = fast_codec_ok(codec, delta) || (tr.fastpfor && !tr.sk); // (the batched FastPFOR kernels write Composition's framing)
     return ok && fast_lists_per_batch(codec, total_vals, nlists) > 0;
 }
 

@@ -389,6 +389,58 @@ int mcp_codec_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t 
     return rc;
 }
 
+// SkippableIntegerCODEC.headlessCompress / headlessUncompress (SkippableIntegerCODEC.java:43-66) of the composition behind a
+// MCP_CODEC_SK_* id: IntCompressor's stream is [n][headless stream] (IntCompressor.java:38-46), so the headless stream is
+// that stream without its first word, and decoding it is decoding [num] + stream.
+static bool sk_codec(int codec_id)
+{
+    const int c = codec_id & MCP_CODEC_MASK;
+    return c == MCP_CODEC_SK_BP32_VB || c == MCP_CODEC_SK_IBP32_IVB || c == MCP_CODEC_SK_FASTPFOR256_VB || c == MCP_CODEC_SK_FASTPFOR128_VB;
+}
+
+int mcp_codec_headless_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength, int32_t *out, int32_t out_cap,
+                                int32_t *out_words)
+{
+    if (!ctx || inlength < 0 || out_cap < 0 || !out_words) return ctx ? fail(ctx, MCP_E_ARG, "headlessCompress: bad argument") : MCP_E_ARG;
+    if (!codec_ok(codec_id) || !sk_codec(codec_id)) return fail(ctx, MCP_E_ARG, "headlessCompress: not a skippable codec id");
+    *out_words = 0;
+    if (inlength == 0) return MCP_OK; // (SkippableComposition writes nothing for an empty input)
+    const int64_t lo[2] = {0, inlength};
+    int64_t oo[2] = {0, 0}, len = 0;
+    std::vector<int32_t> tmp((size_t)out_cap + 1);
+    const int rc = mcp_codec_encode(ctx, codec_id, MCP_FRAME_WORDS, in, lo, 1, oo, reinterpret_cast<uint8_t *>(tmp.data()),
+                                    ((int64_t)out_cap + 1) * 4, &len);
+    if (rc != MCP_OK) return rc;
+    *out_words = (int32_t)(len / 4 - 1);
+    if (*out_words > 0) memcpy(out, tmp.data() + 1, (size_t)*out_words * sizeof(int32_t));
+    return MCP_OK;
+}
+
+int mcp_codec_headless_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength, int32_t *out, int32_t num,
+                                  int32_t *in_words)
+{
+    if (!ctx || inlength < 0 || num < 0) return ctx ? fail(ctx, MCP_E_ARG, "headlessUncompress: bad argument") : MCP_E_ARG;
+    if (!codec_ok(codec_id) || !sk_codec(codec_id)) return fail(ctx, MCP_E_ARG, "headlessUncompress: not a skippable codec id");
+    if (in_words) *in_words = 0;
+    if (num == 0) return MCP_OK;
+    MCP_TRY(set_dev(ctx));
+    // [num] + stream through the batched decoder with the count known; the words consumed come from a re-encode-free
+    // walk of the headers: decode, then measure what an encoder would have written for exactly these ints
+    std::vector<int32_t> tmp((size_t)inlength + 1);
+    tmp[0] = num;
+    if (inlength > 0) memcpy(tmp.data() + 1, in, (size_t)inlength * sizeof(int32_t));
+    const int64_t io[2] = {0, ((int64_t)inlength + 1) * 4}, oo[2] = {0, num};
+    MCP_TRY(mcp_codec_decode(ctx, codec_id, MCP_FRAME_WORDS, reinterpret_cast<const uint8_t *>(tmp.data()), io, 1, out, oo));
+    if (in_words) {
+        const int64_t lo[2] = {0, num};
+        int64_t eo[2] = {0, 0}, len = 0;
+        const int rc = mcp_codec_encode(ctx, codec_id, MCP_FRAME_WORDS, out, lo, 1, eo, nullptr, 0, &len);
+        if (rc != MCP_OK && rc != MCP_E_CAP) return rc;
+        *in_words = (int32_t)(len / 4 - 1);
+    }
+    return MCP_OK;
+}
+
 int mcp_get_compressed_instruments(mcp_ctx *ctx, int codec_id, const int32_t *instruments, int32_t n, uint8_t *bytes,
                                    int64_t cap, int64_t *nbytes)
 {

@@ -131,6 +131,25 @@ class Context:
                     "uncompress")
         return out[: n.value]
 
+    def headless_compress_ints(self, codec_id: int, vals, out_cap: int | None = None) -> np.ndarray:
+        """SkippableIntegerCODEC.headlessCompress of the composition behind a CODEC_SK_* id: no count word."""
+        v = as_i32(vals)
+        cap = int(N.lib().mcp_codec_max_bytes(codec_id, N.FRAME_WORDS, v.size) // 4) if out_cap is None else out_cap
+        out = np.zeros(max(cap, 1), np.int32)
+        n = C.c_int32(0)
+        self._check(self._L.mcp_codec_headless_compress(self._h, codec_id, _ptr(v), v.size, _ptr(out), cap, C.byref(n)),
+                    "headlessCompress")
+        return out[: n.value]
+
+    def headless_uncompress_ints(self, codec_id: int, words, num: int):
+        """SkippableIntegerCODEC.headlessUncompress: -> (the `num` ints, words consumed)."""
+        w = as_i32(words)
+        out = np.zeros(max(num, 1), np.int32)
+        used = C.c_int32(0)
+        self._check(self._L.mcp_codec_headless_uncompress(self._h, codec_id, _ptr(w), w.size, _ptr(out), num, C.byref(used)),
+                    "headlessUncompress")
+        return out[:num], used.value
+
     def get_compressed_instruments(self, codec_id: int, instruments) -> bytes:
         v = as_i32(instruments)
         cap = int(self._L.mcp_codec_max_bytes(codec_id, N.FRAME_APP, v.size))

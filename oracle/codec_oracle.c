@@ -534,6 +534,23 @@ int64_t orc_compress(int codec_flags, const int32_t *in_, int64_t n, int32_t *ou
         o += vb_encode(in + m, n - m, out + o, 0, NULL);
         break;
     }
+    case ORC_CODEC_SK_FASTPFOR256_VB:
+    case ORC_CODEC_SK_FASTPFOR128_VB: {          /* IntCompressor.java:38-46 over SkippableComposition.headlessCompress (:37-45) */
+        out[o++] = (uint32_t)n;
+        const int B = codec == ORC_CODEC_SK_FASTPFOR256_VB ? 256 : 128;
+        const int64_t m = n - n % B;             /* FastPFOR.headlessCompress: greatestMultiple, no count word (FastPFOR.java:92-105) */
+        if (m > 0) {
+            orc_fastpfor *f = orc_fastpfor_new(B);
+            for (int64_t s = 0; s < m;) {
+                const int64_t sz = (m - s < FP_PAGE) ? m - s : FP_PAGE;
+                o += fp_encode_page(f, in + s, sz, out + o);
+                s += sz;
+            }
+            orc_fastpfor_free(f);
+        }
+        o += vb_encode(in + m, n - m, out + o, 0, NULL); /* VariableByte.headlessCompress (VariableByte.java:38-77) */
+        break;
+    }
     case ORC_CODEC_VB:
         o += vb_encode(in, n, out, 0, NULL);
         break;
@@ -593,6 +610,27 @@ int64_t orc_uncompress(int codec_flags, const int32_t *in_, int64_t inlen, int32
         uint32_t init = 0;
         const int64_t p = 1 + bp32_decode(in + 1, out, m, integ, &init);
         vb_decode_n(in + p, out + m, n - m, integ, &init);
+        break;
+    }
+    case ORC_CODEC_SK_FASTPFOR256_VB:
+    case ORC_CODEC_SK_FASTPFOR128_VB: {          /* IntCompressor.java:55-61 over SkippableComposition.headlessUncompress (:47-54) */
+        if (inlen == 0) return -1;
+        const int B = codec == ORC_CODEC_SK_FASTPFOR256_VB ? 256 : 128;
+        n = in[0];
+        if (n > out_cap) return -1;
+        const int64_t m = n - n % B;             /* FastPFOR.headlessUncompress (FastPFOR.java:222-231) */
+        int64_t p = 1;
+        if (m > 0) {
+            orc_fastpfor *f = orc_fastpfor_new(B);
+            for (int64_t s = 0; s < m;) {
+                const int64_t sz = (m - s < FP_PAGE) ? m - s : FP_PAGE;
+                p += fp_decode_page(f, in + p, out + s, sz);
+                s += sz;
+            }
+            orc_fastpfor_free(f);
+        }
+        uint32_t init = 0;
+        vb_decode_n(in + p, out + m, n - m, 0, &init); /* VariableByte.headlessUncompress (VariableByte.java:180-203) */
         break;
     }
     case ORC_CODEC_VB: {

@@ -21,6 +21,8 @@ CODEC_IBP32_IVB = 3
 CODEC_SK_IBP32_IVB = 4
 CODEC_VB = 5
 CODEC_SK_BP32_VB = 6
+CODEC_SK_FASTPFOR256_VB = 7
+CODEC_SK_FASTPFOR128_VB = 8
 FLAG_DELTA = 0x100
 
 

@@ -40,7 +40,10 @@ enum {
     ORC_CODEC_SK_IBP32_IVB   = 4, /* IntegratedIntCompressor framing  IntegratedIntCompressor.java:38-62 */
     ORC_CODEC_VB             = 5, /* bare VariableByte                                   VariableByte.java:32 */
     ORC_CODEC_SK_BP32_VB     = 6, /* IntCompressor framing             IntCompressor.java:38-61 */
-    ORC_CODEC_COUNT          = 7,
+    ORC_CODEC_SK_FASTPFOR256_VB = 7, /* IntCompressor(SkippableComposition(FastPFOR, VariableByte)): n, then the headless stream
+                                         IntCompressor.java:38-61, SkippableComposition.java:37-54, FastPFOR.java:92-105 */
+    ORC_CODEC_SK_FASTPFOR128_VB = 8, /* the same over FastPFOR128 (FastPFOR128.java:33) */
+    ORC_CODEC_COUNT          = 9,
     ORC_CODEC_MASK           = 0xff,
     ORC_FLAG_DELTA           = 0x100 /* Delta.delta(int[]) before compress / inverseDelta after (Delta.java:24-28,84-88) */
 };

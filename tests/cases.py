@@ -8,8 +8,8 @@ from __future__ import annotations
 
 import numpy as np
 
-ALL_CODECS = list(range(7))
-NAMES = ["BP32_VB", "FASTPFOR256_VB", "FASTPFOR128_VB", "IBP32_IVB", "SK_IBP32_IVB", "VB", "SK_BP32_VB"]
+ALL_CODECS = list(range(9))
+NAMES = ["BP32_VB", "FASTPFOR256_VB", "FASTPFOR128_VB", "IBP32_IVB", "SK_IBP32_IVB", "VB", "SK_BP32_VB", "SK_FASTPFOR256_VB", "SK_FASTPFOR128_VB"]
 DELTA = 0x100
 
 

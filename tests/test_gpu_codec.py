@@ -512,3 +512,58 @@ def test_device_codec_stays_inside_its_buffers(ctx, cid, short):
         ctx.set_option("short_list_codec", 1)
         for p in bufs.values():
             ctx.dev_free(p)
+
+
+SKIPPABLE = [(mcp_b200.BinaryPacking, mcp_b200.VariableByte), (mcp_b200.FastPFOR, mcp_b200.VariableByte),
+             (mcp_b200.FastPFOR128, mcp_b200.VariableByte), (mcp_b200.IntegratedBinaryPacking, mcp_b200.IntegratedVariableByte)]
+
+
+@pytest.mark.parametrize("stages", SKIPPABLE, ids=["bp+vb", "fastpfor+vb", "fastpfor128+vb", "ibp+ivb"])
+def test_skippable_headless_api_like_the_reference_tests(ctx, stages):
+    """SkippableBasicTest.java:34-66 consistentTest: headlessCompress then headlessUncompress with the count supplied by
+    the caller, asserting that the decoder consumed exactly what the encoder produced (:57-58) -- lengths around every
+    block boundary instead of all of 0..4096 (each call is a GPU round trip).  The stream equals IntCompressor's without
+    compressed[0] (IntCompressor.java:38-46) and, for the non-integrated compositions, the oracle's."""
+    c = mcp_b200.SkippableComposition(stages[0](), stages[1](), ctx)
+    for n in (0, 1, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 512, 1000, 4096):
+        data = np.array([k % 128 for k in range(n)], np.int32)
+        if stages[0] is mcp_b200.IntegratedBinaryPacking:
+            data = np.cumsum(data).astype(np.int32)
+        out = np.zeros(n + 1024, np.int32)
+        inpos, outpos = mcp_b200.IntWrapper(0), mcp_b200.IntWrapper(7)
+        c.headlessCompress(data, inpos, n, out, outpos)
+        assert inpos.get() == n
+        produced = outpos.get() - 7
+        assert np.array_equal(out[7: outpos.get()], cref.compress(c.codec_id, data)[1:]), n
+        back = np.zeros(n + 3, np.int32)
+        ipos, opos = mcp_b200.IntWrapper(7), mcp_b200.IntWrapper(3)
+        c.headlessUncompress(out, ipos, len(out) - 7, back, opos, n)   # the whole padded buffer, like the Java test
+        assert opos.get() == 3 + n and ipos.get() - 7 == produced, n   # SkippableBasicTest.java:57-58
+        assert np.array_equal(back[3:], data), n
+
+
+def test_two_lists_back_to_back_headless(ctx):
+    """ExampleTest.java's headless example: two arrays compressed one after the other into the same output, decoded
+    from their known lengths."""
+    c = mcp_b200.SkippableComposition(mcp_b200.FastPFOR(), mcp_b200.VariableByte(), ctx)
+    rng = np.random.default_rng(21)
+    a = np.cumsum(rng.geometric(0.01, 2342)).astype(np.int32)
+    b = rng.integers(0, 1 << 20, 777).astype(np.int32)
+    out = np.zeros(a.size + b.size + 2048, np.int32)
+    inpos, outpos = mcp_b200.IntWrapper(0), mcp_b200.IntWrapper(0)
+    c.headlessCompress(a, inpos, a.size, out, outpos)
+    mid = outpos.get()
+    inpos.set(0)
+    c.headlessCompress(b, inpos, b.size, out, outpos)
+    end = outpos.get()
+    ra, rb = np.zeros(a.size, np.int32), np.zeros(b.size, np.int32)
+    ipos = mcp_b200.IntWrapper(0)
+    c.headlessUncompress(out, ipos, end, ra, mcp_b200.IntWrapper(0), a.size)
+    assert ipos.get() == mid
+    c.headlessUncompress(out, ipos, end - mid, rb, mcp_b200.IntWrapper(0), b.size)
+    assert ipos.get() == end and np.array_equal(ra, a) and np.array_equal(rb, b)
+    ic = mcp_b200.IntCompressor(c)
+    w = ic.compress(a)
+    assert w[0] == a.size and np.array_equal(w[1:], out[:mid]) and np.array_equal(ic.uncompress(w), a)
+    with pytest.raises(mcp_b200.McpError):
+        ctx.headless_compress_ints(N.CODEC_FASTPFOR256_VB, a)  # not a skippable id

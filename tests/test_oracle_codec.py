@@ -100,8 +100,8 @@ def test_empty_and_spurious_output():
     # BasicTest.java:325-396 zeroinzerouttest / spuriousouttest
     for codec in cases.ALL_CODECS:
         w = cref.compress(codec, [])
-        if codec in (cref.CODEC_SK_IBP32_IVB, cref.CODEC_SK_BP32_VB):
-            assert list(w) == [0]
+        if codec in (cref.CODEC_SK_IBP32_IVB, cref.CODEC_SK_BP32_VB, cref.CODEC_SK_FASTPFOR256_VB, cref.CODEC_SK_FASTPFOR128_VB):
+            assert list(w) == [0]  # IntCompressor: compressed[0] = input.length
         else:
             assert w.size == 0
     # block codecs emit nothing for inlength < block: the bare FastPFOR instance
@@ -212,3 +212,24 @@ def test_batch_matches_single():
                 assert bytes(buf[i * 1600: i * 1600 + lens[i]]) == ref
             back = cref.batch_uncompress(codec, framing, buf, 1600, lens, off)
             assert np.array_equal(back, vals)
+
+
+@pytest.mark.parametrize("sk,comp", [(cref.CODEC_SK_FASTPFOR256_VB, cref.CODEC_FASTPFOR256_VB), (cref.CODEC_SK_FASTPFOR128_VB, cref.CODEC_FASTPFOR128_VB),
+                                     (cref.CODEC_SK_BP32_VB, cref.CODEC_BP32_VB)])
+def test_skippable_stream_is_the_composition_stream_without_its_header(sk, comp):
+    """IntCompressor over SkippableComposition(F1, VariableByte) writes [n][headless F1][headless VB]
+    (IntCompressor.java:38-46, SkippableComposition.java:37-45); Composition(F1, VariableByte) writes [F1's count word or the
+    0 marker][the same two headless streams] (Composition.java:37-51, FastPFOR.java:309-317, BinaryPacking.java:43-51).  So
+    the two differ in word 0 only -- which ties the skippable framing to the KAT-pinned composition."""
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 31, 32, 100, 127, 128, 129, 255, 256, 257, 1000, 4096, 70000):
+        v = np.cumsum(rng.geometric(0.02, n)).astype(np.int32)
+        if n > 300:
+            v[rng.integers(0, n, 5)] = -7  # 32-bit exceptions
+        a, b = cref.compress(sk, v), cref.compress(comp, v)
+        assert a[0] == n
+        if n == 0:
+            assert a.size == 1 and b.size == 0
+        else:
+            assert np.array_equal(a[1:], b[1:]), n
+        assert np.array_equal(cref.uncompress(sk, a, n), v)
