@@ -2235,11 +2235,7 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
                 if (tr.integrated && !tr.chain_tail && k == nb) carry = 0;
                 int got = 0;
                 uint32_t w = p < avail ? rd(p) : 0u;
-                while (got < c) {
-                    if (p >= avail) { ok = false; break; }
-                    const uint32_t by = (w >> vs) & 0xffu;
-                    vs += 8;
-                    if (vs == 32) { vs = 0; ++p; w = p < avail ? rd(p) : 0u; }
+                auto one_byte = [&](uint32_t by) {
                     vv += (by & 127u) << (vshift & 31);
                     if (by & 128u) {
                         if (diff) { carry += vv; vv = carry; }
@@ -2247,6 +2243,23 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
                         ++got; vv = 0; vshift = 0;
                     } else
                         vshift += 7;
+                };
+                while (got < c) {
+                    if (p >= avail) { ok = false; break; }
+                    if (vs == 0 && got + 4 <= c) {
+                        // a whole word at a time while all of its (at most four) values belong to this round: no
+                        // per-byte position bookkeeping
+                        one_byte(w & 0xffu);
+                        one_byte((w >> 8) & 0xffu);
+                        one_byte((w >> 16) & 0xffu);
+                        one_byte(w >> 24);
+                        ++p; w = p < avail ? rd(p) : 0u;
+                        continue;
+                    }
+                    const uint32_t by = (w >> vs) & 0xffu;
+                    vs += 8;
+                    if (vs == 32) { vs = 0; ++p; w = p < avail ? rd(p) : 0u; }
+                    one_byte(by);
                 }
             }
             __syncwarp();
