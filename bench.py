@@ -449,18 +449,29 @@ def main():
                                          "d2h_bytes_per_step": int(d2h + outs["breach"].nbytes),
                                          "note": "same call, additionally downloading the uncompressed int32 breach lists"}}
 
-    # ---- codec throughput (BASELINE config C4), device-resident, rank 0 only
+    # ---- codec throughput (BASELINE config C4), device-resident.  Lists are independent, so N GPUs are N shards with no
+    # collective (weak scaling, like the valuation): EVERY rank encodes and decodes its own lists (first_list = rank * nl),
+    # the time is the max over ranks, ints/s is the whole job's; the roofline fraction is per GPU.
     codec = None
     pk = peaks()
     hbm_peak = pk["hbm_gbs"] if pk else 6650.0
-    if rank == 0 and not args.no_codec:
+    if not args.no_codec:
         src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk else "6650 GB/s (of fallback)"
+
+        def over_ranks(x, op):
+            if dist is None:
+                return x
+            import torch
+            t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=op)
+            return float(t.item())
 
         def codec_leg(cid, what, nl, ntrials):
             """encode + decode of nl breach lists (1 % of ntrials trials each), device-resident, L2 flushed before every
             timed call; algorithmic bytes = the ints (4 B each) + the encoded bytes + the CSR offsets in and out"""
-            dv, do, total = ctx.generate_breach_lists(nl, ntrials, 0.01, 0x5EED0004)
+            dv, do, total = ctx.generate_breach_lists(nl, ntrials, 0.01, 0x5EED0004, first_list=rank * nl)
             capb = 5 * total + 16 * nl
+            barrier()
             d_oo, d_out, d_back = ctx.dev_alloc(8 * (nl + 1)), ctx.dev_alloc(capb), ctx.dev_alloc(4 * total + 16)
             enc_ms, dec_ms, enc_bytes = [], [], 0
             for it in range(args.warmup + args.steps):
@@ -479,15 +490,17 @@ def main():
                     dec_ms.append(t_d)
             for p in (d_oo, d_out, d_back):  # (dv / do belong to the context)
                 ctx.dev_free(p)
-            e_ms, d_ms = float(np.mean(enc_ms)), float(np.mean(dec_ms))
-            algo_bytes = 4.0 * total + enc_bytes + 16.0 * nl
-            return {"workload": f"{nl} lists, 1% of {ntrials} trials (~{total // nl} ints each), {what}, app framing",
-                    "ints": int(total), "encoded_bytes": int(enc_bytes), "bytes_per_int": enc_bytes / total,
-                    "encode_ints_per_s": total / (e_ms * 1e-3), "decode_ints_per_s": total / (d_ms * 1e-3),
+            MAXOP, SUMOP = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if dist is not None else (None, None)
+            e_ms, d_ms = over_ranks(float(np.mean(enc_ms)), MAXOP), over_ranks(float(np.mean(dec_ms)), MAXOP)
+            all_ints, all_bytes = over_ranks(float(total), SUMOP), over_ranks(float(enc_bytes), SUMOP)
+            algo_bytes = (4.0 * all_ints + all_bytes + 16.0 * nl * world) / world  # per GPU
+            return {"workload": f"{nl} lists per GPU, 1% of {ntrials} trials (~{total // nl} ints each), {what}, app framing",
+                    "n_gpus": world, "ints": int(all_ints), "encoded_bytes": int(all_bytes), "bytes_per_int": all_bytes / all_ints,
+                    "encode_ints_per_s": all_ints / (e_ms * 1e-3), "decode_ints_per_s": all_ints / (d_ms * 1e-3),
                     "encode_ms": e_ms, "decode_ms": d_ms,
-                    "roofline_encode": {"bound": "hbm", "achieved": algo_bytes / (e_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "roofline_encode": {"bound": "hbm", "achieved": algo_bytes / (e_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU",
                                         "frac": algo_bytes / (e_ms * 1e-3) / 1e9 / hbm_peak},
-                    "roofline_decode": {"bound": "hbm", "achieved": algo_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "roofline_decode": {"bound": "hbm", "achieved": algo_bytes / (d_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s per GPU",
                                         "frac": algo_bytes / (d_ms * 1e-3) / 1e9 / hbm_peak},
                     "peak_source": src}
 
