@@ -782,17 +782,6 @@ constexpr uint64_t kLbAgg = 1ull << 62, kLbInc = 2ull << 62, kLbMask = (1ull << 
 
 __device__ __forceinline__ int sw33(int i) { return i + (i >> 5); } // 33-word stride per 32 values: conflict-free block reads
 
-__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p)
-{
-    uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v)
-{
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // the look-back state word carries everything a reader needs (flag | words): readers that consume nothing else the
 // writer stored can poll it relaxed
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
@@ -992,7 +981,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
         fit = T <= FE_OCAP;
         // the batch's total is known: publish it NOW, so that by the time this batch has packed its blocks its
         // predecessors' totals (and usually their prefixes) are already there
-        if (tid == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+        if (tid == 0) st_relaxed_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
         if (fit) {
             // ---- pack my block into the staged output (BitPacking.fastpackwithoutmask; IntegratedBitPacking
             // stores the raw values at width 32)
@@ -1051,7 +1040,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
             long long run = 0;
             for (int j = 0; j < nl; ++j) { const long long w = s_lo[j]; s_lo[j] = run; run += w; }
             s_lo[nl] = run;
-            st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)run);
+            st_relaxed_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)run);
         }
         __syncthreads();
         T = s_lo[nl];
@@ -1066,7 +1055,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
             for (int64_t j = batch - 1;; j -= 32) {
                 const int64_t idx = j - lane;
                 uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
-                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                if (idx >= 0) while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
                 const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
                 const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
                 long long v = lane <= first ? (long long)(st & kLbMask) : 0;
@@ -1075,7 +1064,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
                 base += v;
                 if (inc) break;
             }
-            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
+            if (lane == 0) st_relaxed_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
         }
         if (lane == 0) {
             s_base = base;
@@ -1434,7 +1423,7 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
         __syncthreads();
         fit = Tw <= FE_OCAP;
         if (fit) {
-            if (tid == 0) st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+            if (tid == 0) st_relaxed_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
             for (int i = tid; i < Tw; i += FE_THREADS) s_out[i] = 0u;
             // exceptions of my group, and of the groups before it in the block
             int my_e = 0;
@@ -1524,7 +1513,7 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
     if (!fit) { // the warp-per-list kernels will redo the call: keep the look-back chain moving
         if (tid == 0) {
             *a.err = 2;
-            st_release_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | 0ull);
+            st_relaxed_u64(a.state + batch, (batch == 0 ? kLbInc : kLbAgg) | 0ull);
         }
         T = 0;
     }
@@ -1535,7 +1524,7 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
             for (int64_t j = batch - 1;; j -= 32) {
                 const int64_t idx = j - lane;
                 uint64_t st = kLbInc;
-                if (idx >= 0) do { st = ld_acquire_u64(a.state + idx); } while ((st >> 62) == 0);
+                if (idx >= 0) while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
                 const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
                 const int first = inc ? __ffs(inc) - 1 : 31;
                 long long vv = lane <= first ? (long long)(st & kLbMask) : 0;
@@ -1544,7 +1533,7 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
                 base += vv;
                 if (inc) break;
             }
-            if (lane == 0) st_release_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
+            if (lane == 0) st_relaxed_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
         }
         if (lane == 0) {
             s_base = base;
