@@ -65,7 +65,9 @@ enum {
     MCP_CODEC_FASTPFOR128_VB = 2, /* new Composition(new FastPFOR128(), new VariableByte())     FastPFOR128.java:33      */
     MCP_CODEC_IBP32_IVB      = 3, /* new IntegratedComposition(new IntegratedBinaryPacking(), new IntegratedVariableByte()) */
     MCP_CODEC_SK_IBP32_IVB   = 4, /* new IntegratedIntCompressor()  (n, then headless stream)   IntegratedIntCompressor.java:38-62 */
-    MCP_CODEC_VB             = 5, /* new VariableByte()                                         VariableByte.java:32     */
+    MCP_CODEC_VB             = 5, /* new VariableByte()                                         VariableByte.java:32
+                                     (| MCP_FLAG_DELTA = new IntegratedVariableByte(): gaps from 0, the same bytes --
+                                     differential/IntegratedVariableByte.java:35-76)                                     */
     MCP_CODEC_SK_BP32_VB     = 6, /* new IntCompressor()            (n, then headless stream)   IntCompressor.java:38-61 */
     MCP_CODEC_SK_FASTPFOR256_VB = 7, /* new IntCompressor(new SkippableComposition(new FastPFOR(), new VariableByte()))
                                         (n, then the headless stream: FastPFOR pages without their count word, VariableByte tail)

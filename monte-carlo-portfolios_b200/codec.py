@@ -203,6 +203,14 @@ class SkippableComposition:
     __repr__ = toString
 
 
+class IntegratedVariableByteCodec(IntegerCODEC):
+    """A bare `new IntegratedVariableByte()` used as an IntegerCODEC (differential/IntegratedVariableByte.java:35-76,114-141):
+    VariableByte over the gaps from 0 -- byte for byte what VariableByte writes after Delta.delta."""
+
+    def __init__(self, ctx: Context | None = None):
+        super().__init__(N.CODEC_VB | N.FLAG_DELTA, ctx, "IntegratedVariableByte")
+
+
 class IntCompressor:
     """IntCompressor.java:27-61: default codec SkippableComposition(BinaryPacking, VariableByte), or the one given
     (IntCompressor(SkippableIntegerCODEC c), :27-29)."""

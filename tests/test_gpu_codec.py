@@ -239,7 +239,7 @@ def test_integercodec_interface_like_the_reference_tests(ctx):
                   mcp_b200.Composition(mcp_b200.FastPFOR(), mcp_b200.VariableByte(), ctx),
                   mcp_b200.Composition(mcp_b200.FastPFOR128(), mcp_b200.VariableByte(), ctx),
                   mcp_b200.IntegratedComposition(mcp_b200.IntegratedBinaryPacking(), mcp_b200.IntegratedVariableByte(), ctx),
-                  mcp_b200.VariableByteCodec(ctx)):
+                  mcp_b200.VariableByteCodec(ctx), mcp_b200.IntegratedVariableByteCodec(ctx)):
         for x in (0, 1, 7, 49):
             a = np.array([2, 3, 4, 5], np.int32)
             b = np.zeros(90, np.int32)
@@ -258,7 +258,9 @@ def test_intcompressor_interfaces(ctx):
     # IntCompressorTest.java:32-76
     for N_ in (1, 10, 100, 1000, 10000):
         orig = 3 * np.arange(N_, dtype=np.int32) + 5
-        for ic in (mcp_b200.IntCompressor(ctx), mcp_b200.IntegratedIntCompressor(ctx)):
+        for ic in (mcp_b200.IntCompressor(ctx), mcp_b200.IntegratedIntCompressor(ctx),
+                   mcp_b200.IntCompressor(mcp_b200.SkippableComposition(mcp_b200.FastPFOR(), mcp_b200.VariableByte(), ctx)),
+                   mcp_b200.IntCompressor(mcp_b200.SkippableComposition(mcp_b200.FastPFOR128(), mcp_b200.VariableByte(), ctx))):
             comp = ic.compress(orig)
             assert comp[0] == N_
             assert np.array_equal(ic.uncompress(comp), orig)
