@@ -112,6 +112,9 @@ struct mcp_ctx {
     bool sTailPending = false;     // pipelined upload: scenario rows >= sHeadRows are still arriving on stream2 (evTail)
     int64_t sHeadRows = 0;
     void *earlyBreachDst = nullptr; // host buffer the raw breach lists are copied to under the encode (mcp_simulate)
+    // host buffers the per-portfolio statistics are copied to under the encode (mcp_simulate); any may be null
+    double *earlyMean = nullptr, *earlyVar = nullptr, *earlyVarLoss = nullptr, *earlyCvar = nullptr;
+    int32_t *earlyVarTrial = nullptr;
     bool forceSortFinalize = false; // debug: breach list by bitonic sort instead of the trial bitmap
     int selCap = 2304;
     uint32_t mmaConfigured = 0;

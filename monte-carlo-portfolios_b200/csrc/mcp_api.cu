@@ -661,16 +661,19 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     ctx->haveE = ctx->haveS = true; ctx->haveRun = false; ctx->sfragValid = false;
     ctx->sTailPending = true; ctx->sHeadRows = head;
     ctx->earlyBreachDst = breach_idx;
+    ctx->earlyMean = mean; ctx->earlyVar = variance; ctx->earlyVarLoss = var_loss; ctx->earlyVarTrial = var_trial; ctx->earlyCvar = cvar;
     const int rc = mcp_run(ctx, alpha, codec_id, framing);
     ctx->earlyBreachDst = nullptr;
+    ctx->earlyMean = ctx->earlyVar = ctx->earlyVarLoss = ctx->earlyCvar = nullptr;
+    ctx->earlyVarTrial = nullptr;
     if (ctx->sTailPending) { // the run failed before it consumed the tail: drain the copy, keep the state consistent
         ctx->sTailPending = false;
         cudaStreamSynchronize(ctx->stream2);
     }
     if (rc != MCP_OK) { cudaStreamSynchronize(ctx->stream2); return rc; }
     if (enc_len) *enc_len = ctx->runEncBytes;
-    MCP_TRY(mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, nullptr, enc_off, enc, enc_cap));
-    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2)); // the raw lists
+    MCP_TRY(mcp_fetch(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, enc_off, enc, enc_cap)); // (the statistics left under the encode)
+    MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2)); // the statistics and the raw lists
     return MCP_OK;
 }
 

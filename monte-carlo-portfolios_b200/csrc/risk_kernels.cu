@@ -2681,11 +2681,22 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
     if (side_moments) MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
 
     MCP_TRY(scenarios_tail_ready(ctx)); // (a schedule that never reached the tail rows cannot exist, but the event must not dangle)
-    if (ctx->earlyBreachDst) {
-        // the caller wants the raw lists on the host: start that copy on the side stream now, under the encode
+    const bool early_stats = ctx->earlyMean || ctx->earlyVar || ctx->earlyVarLoss || ctx->earlyVarTrial || ctx->earlyCvar;
+    auto send_stats = [&](cudaStream_t st, bool moments_too) -> int {
+        if (moments_too && ctx->earlyMean) MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyMean, ctx->dMean.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (moments_too && ctx->earlyVar) MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyVar, ctx->dVar.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (ctx->earlyVarLoss) MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyVarLoss, ctx->dVarLoss.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (ctx->earlyVarTrial) MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyVarTrial, ctx->dVarTrial.p, (size_t)P * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (ctx->earlyCvar) MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyCvar, ctx->dCvar.p, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, st));
+        return MCP_OK;
+    };
+    if (ctx->earlyBreachDst || early_stats) {
+        // the caller wants the statistics / the raw lists on the host: those copies start on the side stream now, under the encode
         MCP_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
         MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream2));
+        MCP_TRY(send_stats(ctx->stream2, true));
+        if (ctx->earlyBreachDst)
+            MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream2));
     }
     // ---- encode the breach lists (uniform length t) into the JavaFastPFOR format
     MCP_CUDA(ctx, ctx->dEncOff.reserve((size_t)(P + 1) * sizeof(int64_t)));
@@ -2697,9 +2708,11 @@ static int risk_run_inner(mcp_ctx *ctx, double alpha, int codec_id, int framing)
         ctx->runFallbackRows = nf;
         if (nf > 0) { // rare: some rows lost the optimistic bet -- redo them exactly, then encode again
             MCP_TRY(risk_stream_fallback(ctx, t, nf));
-            if (ctx->earlyBreachDst) { // the raw lists already left for the host under the first encode: send the repaired ones
+            if (ctx->earlyBreachDst || early_stats) { // they already left for the host under the first encode: send the repaired ones
                 MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
-                MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                MCP_TRY(send_stats(ctx->stream, false));
+                if (ctx->earlyBreachDst)
+                    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->earlyBreachDst, ctx->dBreach.p, (size_t)P * t * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
             }
             MCP_TRY(encode_uniform_lists(ctx, codec_id, framing, ctx->dBreach.as<int32_t>(), t, P, ctx->dEncOff, ctx->dEnc, &total));
         }

@@ -315,6 +315,28 @@ def test_simulate_one_call(ctx):
         assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
 
 
+def test_simulate_when_the_optimistic_bet_fails(ctx):
+    """mcp_simulate sends the statistics and the raw lists to the host under the (speculative) encode; rows that lost the
+    optimistic bet are redone afterwards, and what the caller finally holds must be the repaired values."""
+    F, Nn, P = 32, 60000, 60
+    S = np.zeros((Nn, F))
+    S[:, 0] = np.linspace(0.0, 1.0, Nn)           # losses descend with the trial index for positive exposures
+    S[:, 1] = 1e-3 * np.cos(np.arange(Nn))
+    E = np.abs(riskcases.synthetic(P, 1, F, 3)[0]) + 1.0
+    E[::3] *= -1.0
+    r = ctx.simulate(E, S, 0.99)
+    assert ctx.run_stats()["fallback_rows"] == P - len(range(0, P, 3))
+    o = cref.risk(E, S, 0.99)
+    assert np.array_equal(r["var_trial"], o["var_trial"]) and np.array_equal(r["var_loss"], o["var_loss"])
+    assert np.array_equal(r["breach"], o["breach"])
+    np.testing.assert_allclose(r["cvar"], o["cvar"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(r["mean"], o["mean"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(r["variance"], o["variance"], rtol=RTOL, atol=0)
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    for p in (0, 1, P - 1):
+        assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
+
+
 def test_device_generators_match_the_oracle(ctx):
     ctx.generate_exposures(100, 32, 0x5EED0002, 100.0, 0.0)
     ctx.generate_scenarios(1000, 32, 0x5EED0002, 1.0, 0.05)
