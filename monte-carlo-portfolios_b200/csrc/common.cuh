@@ -108,9 +108,11 @@ struct mcp_ctx {
     int64_t overlapTiles = 1;      // >1: that many portfolio tiles alternate between two streams (selection of one tile under the valuation of the next); measured -2 % at best on C2 -- the valuation kernel leaves no idle issue slots to hide in -- so off by default
     mcp::DevBuf dCandKey2, dCandCnt2;
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
-    cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr, evTail1 = nullptr;
     bool sTailPending = false;     // pipelined upload: scenario rows >= sHeadRows are still arriving on stream2 (evTail)
     int64_t sHeadRows = 0;
+    bool uploadSplit = true;       // mcp_simulate: scenario tail in two parts, sparse valuation in two launches
+    int64_t sMidRows = 0;          // > 0: the tail arrives in two parts, rows [sHeadRows, sMidRows) first (evTail1), then the rest (evTail)
     void *earlyBreachDst = nullptr; // host buffer the raw breach lists are copied to under the encode (mcp_simulate)
     // host buffers the per-portfolio statistics are copied to under the encode (mcp_simulate); any may be null
     double *earlyMean = nullptr, *earlyVar = nullptr, *earlyVarLoss = nullptr, *earlyCvar = nullptr;

@@ -101,6 +101,7 @@ int mcp_create(int device, mcp_ctx **out)
         cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->evTail, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evTail1, cudaEventDisableTiming) != cudaSuccess ||
         cudaMallocHost(&ctx->hPinned, 4096) != cudaSuccess || cudaEventCreate(&ctx->tA) != cudaSuccess ||
         cudaEventCreate(&ctx->tB) != cudaSuccess) {
         cudaGetLastError();
@@ -135,6 +136,7 @@ void mcp_destroy(mcp_ctx *ctx)
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evTail) cudaEventDestroy(ctx->evTail);
+    if (ctx->evTail1) cudaEventDestroy(ctx->evTail1);
     if (ctx->evTileFork) cudaEventDestroy(ctx->evTileFork);
     if (ctx->evTileJoin) cudaEventDestroy(ctx->evTileJoin);
     if (ctx->evSfrag) cudaEventDestroy(ctx->evSfrag);
@@ -165,6 +167,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
     else if (!strcmp(key, "short_list_codec")) ctx->shortListCodec = (int)(value < 0 ? 0 : value > 2 ? 2 : value);
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
+    else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);
     else if (!strcmp(key, "overlap_tiles")) ctx->overlapTiles = value < 1 ? 1 : value;
@@ -654,18 +657,29 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     MCP_CUDA(ctx, ctx->dS.reserve((size_t)N * F * sizeof(double) + 16));
     MCP_TRY(h2d(ctx, ctx->dE.p, E, (size_t)P * F * sizeof(double)));
     MCP_TRY(h2d(ctx, ctx->dS.p, S, (size_t)head * F * sizeof(double)));
-    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dS.as<double>() + head * F, S + head * F, (size_t)(N - head) * F * sizeof(double),
+    // the tail in two parts: the sparse valuation is launched in two halves, the first as soon as ITS scenario rows are
+    // there (the whole tail takes longer to arrive than the dense step and its selection take to run)
+    int64_t mid = (head + (N - head) / 2) & ~(int64_t)7;
+    if (mid <= head || N - head < 16384 || !ctx->uploadSplit) mid = 0;
+    const int64_t split = mid > 0 ? mid : N;
+    MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dS.as<double>() + head * F, S + head * F, (size_t)(split - head) * F * sizeof(double),
                                   cudaMemcpyHostToDevice, ctx->stream2));
+    if (mid > 0) {
+        MCP_CUDA(ctx, cudaEventRecord(ctx->evTail1, ctx->stream2));
+        MCP_CUDA(ctx, cudaMemcpyAsync(ctx->dS.as<double>() + mid * F, S + mid * F, (size_t)(N - mid) * F * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream2));
+    }
     MCP_CUDA(ctx, cudaEventRecord(ctx->evTail, ctx->stream2));
     ctx->P = P; ctx->N = N; ctx->F = F;
     ctx->haveE = ctx->haveS = true; ctx->haveRun = false; ctx->sfragValid = false;
-    ctx->sTailPending = true; ctx->sHeadRows = head;
+    ctx->sTailPending = true; ctx->sHeadRows = head; ctx->sMidRows = mid;
     ctx->earlyBreachDst = breach_idx;
     ctx->earlyMean = mean; ctx->earlyVar = variance; ctx->earlyVarLoss = var_loss; ctx->earlyVarTrial = var_trial; ctx->earlyCvar = cvar;
     const int rc = mcp_run(ctx, alpha, codec_id, framing);
     ctx->earlyBreachDst = nullptr;
     ctx->earlyMean = ctx->earlyVar = ctx->earlyVarLoss = ctx->earlyCvar = nullptr;
     ctx->earlyVarTrial = nullptr;
+    ctx->sMidRows = 0;
     if (ctx->sTailPending) { // the run failed before it consumed the tail: drain the copy, keep the state consistent
         ctx->sTailPending = false;
         cudaStreamSynchronize(ctx->stream2);

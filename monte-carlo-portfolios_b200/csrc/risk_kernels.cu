@@ -365,7 +365,8 @@ struct StreamArgs {
     const double *Sfrag;     // scenarios repacked in B-fragment order: [trial block of 8][k-step][lane] (k_repack_scenarios)
     int64_t p0, p1;          // portfolio tile
     int64_t n_begin, n_end;  // trial range of this step
-    int nsub;                // sub-chunks (gridDim.x)
+    int nsub;                // sub-chunks of the step
+    int sub0;                // first sub-chunk of this launch (gridDim.x of them): a step may be launched in parts
     int sub_len;             // trials per sub-chunk (multiple of 8)
     const uint64_t *tkey;    // [P] candidate iff fkey(V) <= tkey, i.e. V <= -(current VaR lower bound)  (SPARSE)
     void *cand;              // candidate buffer, one row of `pitch` bytes per portfolio.  DENSE steps use the row as a
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     __shared__ __align__(8) uint64_t s_full[VM_NSTAGE], s_empty[VM_NSTAGE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = lane >> 2, c = lane & 3;
-    const int sub = blockIdx.x;
+    const int sub = blockIdx.x + a.sub0;
     const int64_t nb = a.n_begin + (int64_t)sub * a.sub_len;
     const int64_t ne = min(a.n_end, nb + a.sub_len);
     const int ntr = (int)(ne - nb);
@@ -2018,6 +2019,20 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
         for (size_t si = 0; si < steps.size(); ++si) {
             const Step &s = steps[si];
             const bool dense = si == 0;
+            int split_a = 0; // > 0: this step's valuation is launched in two parts, sub-chunks [0, split_a) first
+            if (ctx->sTailPending && s.end > ctx->sHeadRows && ctx->sMidRows > s.begin && nstreams == 1 && P <= Pt && !dense &&
+                s.begin >= ctx->sHeadRows) {
+                const int64_t na = (ctx->sMidRows - s.begin) / s.sub_len; // sub-chunks whose trials all lie below sMidRows
+                if (na > 0 && na < s.nsub) {
+                    split_a = (int)na;
+                    MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evTail1, 0));
+                    ctx->sTailPending = false;
+                    KScope ks(ctx, MCP_K_GEN, 1, ctx->stream);
+                    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, ctx->F / 4, ctx->dSfrag.as<double>(),
+                                                                                                  ctx->sHeadRows / 8, ctx->sMidRows / 8);
+                    MCP_TRY(check_launch(ctx, "k_repack_scenarios (tail, first part)"));
+                }
+            }
             if (ctx->sTailPending && s.end > ctx->sHeadRows) {
                 MCP_TRY(scenarios_tail_ready(ctx)); // on ctx->stream
                 MCP_CUDA(ctx, cudaEventRecord(ctx->evSfrag, ctx->stream));
@@ -2041,6 +2056,21 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
             v.part = io.moments ? ctx->dPart.as<double>() : nullptr;
             v.part_stride = nparts; v.part_base = part_base;
             dim3 grid((unsigned)s.nsub, (unsigned)((rows + VM_PG - 1) / VM_PG));
+            if (split_a > 0) {
+                // pipelined upload in two parts: the sub-chunks whose trials arrived first now, the others behind the rest
+                grid.x = (unsigned)split_a;
+                MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
+                MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evTail, 0));
+                {
+                    KScope ks(ctx, MCP_K_GEN, 1, ctx->stream);
+                    k_repack_scenarios<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->dS.as<double>(), ctx->N, ctx->F / 4, ctx->dSfrag.as<double>(),
+                                                                                                  ctx->sMidRows / 8, (ctx->N + 7) / 8);
+                    MCP_TRY(check_launch(ctx, "k_repack_scenarios (tail, second part)"));
+                }
+                ctx->sfragValid = true;
+                v.sub0 = split_a;
+                grid.x = (unsigned)(s.nsub - split_a);
+            }
             MCP_TRY(dispatch_value_mma(ctx, v, dense, grid));
             SelArgs a{};
             a.cand = v.cand;

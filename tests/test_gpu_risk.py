@@ -315,6 +315,26 @@ def test_simulate_one_call(ctx):
         assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
 
 
+def test_simulate_with_the_scenario_tail_uploaded_in_two_parts(ctx):
+    """mcp_simulate uploads the scenario tail in two parts and launches the sparse valuation in two halves, the first as
+    soon as its rows are there; results are those of the single upload and of the oracle."""
+    E, S = riskcases.synthetic(300, 40000, 32, 12)
+    o = cref.risk(E, S, 0.99)
+    got = {}
+    try:
+        for split in (1, 0):
+            ctx.set_option("upload_split", split)
+            r = ctx.simulate(E, S, 0.99)
+            assert np.array_equal(r["breach"], o["breach"]) and np.array_equal(r["var_trial"], o["var_trial"]), split
+            assert np.array_equal(r["var_loss"], o["var_loss"]), split
+            np.testing.assert_allclose(r["cvar"], o["cvar"], rtol=RTOL, atol=0)
+            got[split] = r
+    finally:
+        ctx.set_option("upload_split", 1)
+    for k in ("enc", "enc_off", "cvar", "mean", "variance"):
+        assert np.array_equal(got[0][k], got[1][k]), k
+
+
 def test_simulate_when_the_optimistic_bet_fails(ctx):
     """mcp_simulate sends the statistics and the raw lists to the host under the (speculative) encode; rows that lost the
     optimistic bet are redone afterwards, and what the caller finally holds must be the repaired values."""
