@@ -339,6 +339,18 @@ def test_full_size_c4_properties(ctx, cid):
             ctx.dev_free(p)
 
 
+@pytest.fixture
+def shortlist_everywhere(ctx):
+    """short_list_codec = 2: every codec with short lists goes to the thread-per-list kernels; the default is restored
+    whatever the test does."""
+    ctx.set_option("short_list_codec", 2)
+    try:
+        yield ctx
+    finally:
+        ctx.set_option("fast_codec", 1)
+        ctx.set_option("short_list_codec", 1)
+
+
 def _short_lists(rng, count, lengths):
     lists = []
     for _ in range(count):
@@ -363,7 +375,7 @@ def _short_lists(rng, count, lengths):
 @pytest.mark.parametrize("codec", cases.ALL_CODECS, ids=cases.NAMES)
 @pytest.mark.parametrize("delta", [0, cases.DELTA], ids=["plain", "delta"])
 @pytest.mark.parametrize("framing", [N.FRAME_WORDS, N.FRAME_APP], ids=["words", "app"])
-def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
+def test_short_list_kernels_bit_exact(shortlist_everywhere, codec, delta, framing):
     """The thread-per-list kernels on the lengths around every boundary they have (empty, all tail, 31/32/33,
     127/128/129, a FastPFOR128 block, columns that overflow and send the warp batch to the warp-per-list routines or
     the call to the batched kernels), every codec id, both framings: bytes equal to the oracle's, decode round trip."""
@@ -371,7 +383,7 @@ def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
         pytest.skip("Delta before an integrated codec is not a combination the reference uses")
     rng = np.random.default_rng(1000 + 16 * codec + 2 * (1 if delta else 0) + framing)
     cid = codec | delta
-    ctx.set_option("short_list_codec", 2)
+    ctx = shortlist_everywhere
     for lengths in ([0, 1, 5, 31, 32, 33, 64, 96, 100, 127], [0, 1, 31, 32, 33, 64, 96, 100, 127, 128, 129, 160, 200, 255, 256, 300]):
         lists = _short_lists(rng, 333, lengths)
         vals = np.concatenate([cases.to_i32(v) for v in lists])
@@ -389,20 +401,19 @@ def test_short_list_kernels_bit_exact(ctx, codec, delta, framing):
         assert np.array_equal(ctx.codec_decode(cid, framing, out, out_off, off), vals)
         after = ctx.codec_stats()
         assert after["short_calls"] + after["short_fallbacks"] == mid["short_calls"] + mid["short_fallbacks"] + 1
-    ctx.set_option("short_list_codec", 1)
 
 
 @pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA,
                                  N.CODEC_VB | N.FLAG_DELTA, N.CODEC_SK_IBP32_IVB, N.CODEC_IBP32_IVB, N.CODEC_SK_BP32_VB | N.FLAG_DELTA],
                          ids=["bp+delta", "fastpfor256+delta", "fastpfor128+delta", "vb+delta", "skibp", "ibp", "skbp+delta"])
-def test_short_list_kernels_serve_c4(ctx, cid):
+def test_short_list_kernels_serve_c4(shortlist_everywhere, cid):
     """BASELINE config C4's shape (1 % of 10 000 trials, ~100 ints per list, not a multiple of 32 lists) is served by the
     thread-per-list kernels themselves -- no hand-over -- in both directions, and the bytes are the ones the batched
     and the warp-per-list kernels produce."""
     rng = np.random.default_rng(77)
     vals, off = cases.breach_like_lists(rng, 4099, 10000, 0.01)
     nl = off.size - 1
-    ctx.set_option("short_list_codec", 2)
+    ctx = shortlist_everywhere
     before = ctx.codec_stats()
     out_off, out = ctx.codec_encode(cid, N.FRAME_APP, vals, off, cap=int(8 * vals.size + 64 * nl))
     back = ctx.codec_decode(cid, N.FRAME_APP, out, out_off, off)
@@ -429,11 +440,11 @@ def test_short_list_kernels_serve_c4(ctx, cid):
         ctx.set_option("short_list_codec", 1)
 
 
-def test_short_list_decode_rejects_malformed_streams(ctx):
+def test_short_list_decode_rejects_malformed_streams(shortlist_everywhere):
     rng = np.random.default_rng(5)
     vals, off = cases.breach_like_lists(rng, 500, 10000, 0.01)
     cid = N.CODEC_BP32_VB | N.FLAG_DELTA
-    ctx.set_option("short_list_codec", 2)
+    ctx = shortlist_everywhere
     out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off)
     w = out.view(np.uint32)
     i = 123
@@ -450,19 +461,17 @@ def test_short_list_decode_rejects_malformed_streams(ctx):
             ctx.codec_decode(cid, N.FRAME_WORDS, bad, boff, off)
         assert e.value.code == N.MCP_E_FORMAT, what
     assert w[out_off[i] // 4] == 32 * ((off[i + 1] - off[i]) // 32)
-    ctx.set_option("short_list_codec", 1)
 
 
-def test_short_list_encode_reports_capacity(ctx):
+def test_short_list_encode_reports_capacity(shortlist_everywhere):
     rng = np.random.default_rng(6)
     vals, off = cases.breach_like_lists(rng, 300, 10000, 0.01)
-    ctx.set_option("short_list_codec", 2)
+    ctx = shortlist_everywhere
     out_off, out = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off)
     with pytest.raises(mcp_b200.CapacityError):
         ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size) - 4)
     o2, b2 = ctx.codec_encode(N.CODEC_BP32_VB | N.FLAG_DELTA, N.FRAME_APP, vals, off, cap=int(out.size))
     assert np.array_equal(b2, out) and np.array_equal(o2, out_off)
-    ctx.set_option("short_list_codec", 1)
 
 
 @pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_VB, N.CODEC_SK_IBP32_IVB],
