@@ -1655,7 +1655,7 @@ struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
 
 // length of the dense first step: ~4 tail sizes, at least kDenseFloor trials, a multiple of 8 (tensor-core trial blocks)
-static int64_t g_dense_floor = 2048; // process-wide tuning knob (mcp_set_option "dense_floor")
+static int64_t g_dense_floor = 1024; // process-wide tuning knob (mcp_set_option "dense_floor"); 1 024: C3 6.93 ms vs 7.17 at 2 048
 void risk_set_dense_floor(int64_t v) { g_dense_floor = v < 64 ? 64 : v; }
 // `two_step` (optimistic schedule): the sample only has to pin down a quantile, so it is capped at the 4 096 values the
 // register-resident selection handles -- for large tails the bound gets relatively tighter, not looser (r ~ t n0 / N).
@@ -2103,7 +2103,8 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
                 // rows of <= 2 048 values: 128-thread CTAs (six rows resident per SM: the kernel is latency-bound per row)
-                if (reg && a.step_len <= 16 * 128) k_select_dense<16, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
+                if (reg && a.step_len <= 8 * 128) k_select_dense<8, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
+                else if (reg && a.step_len <= 16 * 128) k_select_dense<16, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
                 else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16, 256><<<(unsigned)rows, 256, 0, cur_stream(ctx)>>>(a);
                 else if (!dense && ctx->smallSelect && a.kept_n + 4 * t + 64 <= 1024) {
                     // small tails (t ~ 100): a 64-thread CTA per row, a staging area to match (rows beyond it take the
