@@ -96,8 +96,13 @@ int  mcp_sync(mcp_ctx *ctx);
  * tensor-core kernel), "fused_moments" (1 = mean/variance by a per-trial reduction fused into the valuation kernel
  * instead of by linearity, mean = E.mean(S), var = E^T Cov(S) E), "optimistic" (0 = always use the guaranteed
  * geometric trial schedule; 1 (default) = two-step schedule with an optimistic filter bound and an exact fallback
- * for the rows where the bet fails).  Trial indices, breach lists and byte streams are identical either way, moments
- * agree to 1e-9; only the kernels differ. */
+ * for the rows where the bet fails), "fast_codec" (0 = warp-per-list codec kernels only), "short_list_codec" (0 / 1 / 2:
+ * thread-per-list codec kernels off / where they are the faster ones / for every codec), "reg_select" / "small_select"
+ * (0 = dense-step selection staged in shared memory / 256-thread selection CTAs for small tails), "dense_floor"
+ * (smallest dense sample in trials, default 1024; process-wide), "overlap_tiles" (> 1 = portfolio tiles alternate between
+ * two streams), "item_trials" (trials per valuation work item), "upload_split" (0 = mcp_simulate uploads the scenario
+ * tail in one part), "ts_slack" (trial-sharded test hook).  Trial indices, breach lists and byte streams are identical
+ * either way, moments agree to 1e-9; only the kernels differ. */
 int  mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value);
 
 /* Upper bound on the encoded size in BYTES of one list of n ints under `framing`
