@@ -1,0 +1,69 @@
+"""Property tests of the CPU oracle (hypothesis): the checker has to be right for ANY list, not only for the shapes the
+reference's JUnit tests use.  Each property is one the Java library guarantees by construction."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+import cases
+from oracle import cref
+
+INTS = st.lists(st.integers(-2**31, 2**31 - 1), min_size=0, max_size=700)
+SMALL = st.lists(st.integers(0, 1 << 14), min_size=0, max_size=1500)
+CODECS = st.sampled_from(cases.ALL_CODECS)
+DELTA = st.sampled_from([0, cases.DELTA])
+
+
+def _ok(codec, delta):
+    return not (delta and codec in (cref.CODEC_IBP32_IVB, cref.CODEC_SK_IBP32_IVB))
+
+
+@settings(max_examples=300, deadline=None)
+@given(vals=st.one_of(INTS, SMALL), codec=CODECS, delta=DELTA)
+def test_round_trip_any_list(vals, codec, delta):
+    """uncompress(compress(x)) == x for every codec id, with Java's 32-bit wrap-around for Delta."""
+    if not _ok(codec, delta):
+        return
+    v = np.array(vals, np.int64).astype(np.int32)
+    w = cref.compress(codec | delta, v)
+    assert np.array_equal(cref.uncompress(codec | delta, w, v.size), v)
+    # the loader's framing: big-endian bytes, one trailing zero int (LoadPortfolios.java:622)
+    b = cref.get_compressed_instruments(codec | delta, v)
+    assert len(b) == 4 * (w.size + 1) and b[-4:] == b"\0\0\0\0"
+    assert bytes(b[:-4]) == w.astype(">i4").tobytes()
+
+
+@settings(max_examples=200, deadline=None)
+@given(vals=st.one_of(INTS, SMALL))
+def test_skippable_streams_differ_from_compositions_in_word_zero_only(vals):
+    v = np.array(vals, np.int64).astype(np.int32)
+    for sk, comp in ((cref.CODEC_SK_BP32_VB, cref.CODEC_BP32_VB), (cref.CODEC_SK_FASTPFOR256_VB, cref.CODEC_FASTPFOR256_VB),
+                     (cref.CODEC_SK_FASTPFOR128_VB, cref.CODEC_FASTPFOR128_VB)):
+        a, b = cref.compress(sk, v), cref.compress(comp, v)
+        assert a[0] == v.size
+        if v.size:
+            assert np.array_equal(a[1:], b[1:])
+        else:
+            assert a.size == 1 and b.size == 0
+
+
+@settings(max_examples=200, deadline=None)
+@given(vals=SMALL)
+def test_delta_flag_is_delta_then_codec(vals):
+    """MCP_FLAG_DELTA = Delta.delta on a copy, then the codec (Delta.java:24-28): same words as encoding the gaps."""
+    v = np.array(vals, np.int64).astype(np.int32)
+    gaps = v.copy()
+    if v.size:
+        gaps[1:] = (v[1:].astype(np.int64) - v[:-1].astype(np.int64)).astype(np.int32)
+    for codec in (cref.CODEC_BP32_VB, cref.CODEC_FASTPFOR256_VB, cref.CODEC_VB, cref.CODEC_SK_BP32_VB):
+        assert np.array_equal(cref.compress(codec | cases.DELTA, v), cref.compress(codec, gaps)), codec
+
+
+@settings(max_examples=150, deadline=None)
+@given(vals=st.lists(st.integers(0, 2**31 - 1), min_size=0, max_size=600))
+def test_integrated_vbyte_is_vbyte_of_the_gaps_for_sorted_lists(vals):
+    """IntegratedComposition's blocks carry differences, its VariableByte tail restarts at 0 (IntegratedVariableByte.java:40):
+    for a list shorter than one block the stream is Composition's 0 marker + VariableByte of the gaps from 0."""
+    v = np.sort(np.array(vals, np.int64)).astype(np.int32)[:31]
+    a = cref.compress(cref.CODEC_IBP32_IVB, v)
+    b = cref.compress(cref.CODEC_VB | cases.DELTA, v)
+    if v.size:
+        assert a[0] == 0 and np.array_equal(a[1:], b)
