@@ -67,3 +67,28 @@ def test_integrated_vbyte_is_vbyte_of_the_gaps_for_sorted_lists(vals):
     b = cref.compress(cref.CODEC_VB | cases.DELTA, v)
     if v.size:
         assert a[0] == 0 and np.array_equal(a[1:], b)
+
+
+# ---------------------------------------------------------------- risk oracle
+from test_oracle_risk import brute  # noqa: E402  (the lexsort restatement of the specification)
+
+
+@settings(max_examples=120, deadline=None)
+@given(P=st.integers(1, 4), N=st.integers(1, 300), F=st.integers(1, 9), levels=st.integers(1, 5), seed=st.integers(0, 2**31 - 1),
+       alpha=st.sampled_from([0.5, 0.9, 0.95, 0.99, 1.0]))
+def test_risk_oracle_against_lexsort_with_heavy_ties(P, N, F, levels, seed, alpha):
+    """Small integer exposures and scenario values make most losses collide exactly: the VaR order statistic, its trial
+    index and the breach list must still be the lexicographic (loss, trial) ones of the specification."""
+    rng = np.random.default_rng(seed)
+    E = rng.integers(-levels, levels + 1, (P, F)).astype(np.float64)
+    S = rng.integers(-levels, levels + 1, (N, F)).astype(np.float64)
+    V, ref, t = brute(E, S, alpha)
+    r = cref.risk(E, S, alpha)
+    assert r["tail"] == t and 1 <= t <= N
+    assert np.array_equal(r["var_trial"], ref["var_trial"]) and np.array_equal(r["var_loss"], ref["var_loss"])
+    for p in range(P):
+        b = r["breach"][p]
+        assert np.array_equal(b, ref["breach"][p]) and np.all(np.diff(b) > 0) and b.size == t
+        assert r["var_trial"][p] in b
+    assert np.allclose(r["cvar"], ref["cvar"], rtol=1e-12, atol=1e-12)
+    assert np.all(np.asarray(r["cvar"]) >= np.asarray(r["var_loss"]) - 1e-12)   # the tail mean is not below its smallest element
