@@ -126,7 +126,9 @@ int mcp_codec_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t in
 int mcp_codec_headless_compress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
                                 int32_t *out, int32_t out_cap, int32_t *out_words);
 /* SkippableIntegerCODEC.headlessUncompress(in, inpos, inlength, out, outpos, num) (:58-66): exactly `num` ints are
- * produced (out must hold them); *in_words receives the ints consumed (what Java adds to inpos). */
+ * produced (out must hold them); *in_words receives the ints consumed (what Java adds to inpos).  The consumed count is
+ * obtained by re-encoding the decoded values, so it is exact for streams one of these encoders (or the reference) wrote;
+ * for a foreign stream that decodes to the same values through a different layout it may differ. */
 int mcp_codec_headless_uncompress(mcp_ctx *ctx, int codec_id, const int32_t *in, int32_t inlength,
                                   int32_t *out, int32_t num, int32_t *in_words);
 /* IntegerCODEC.uncompress(in, inpos, inlength, out, outpos): *out_count = ints produced */
@@ -198,7 +200,10 @@ int mcp_generate_scenarios(mcp_ctx *ctx, int64_t N, int32_t F, uint64_t seed, do
 int mcp_download_exposures(mcp_ctx *ctx, double *E);
 int mcp_download_scenarios(mcp_ctx *ctx, double *S);
 
-/* V[p0..p1) x [0..N) -> host, row-major (debug / parity: bit-identical to the oracle) */
+/* V[p0..p1) x [0..N) -> host, row-major (debug / parity: bit-identical to the oracle).
+ * The tensor-core kernel (mma.sync.m8n8k4.f64) equals the k-ascending fma chain bit for bit on B200 -- a measured
+ * property of this GPU (profiles/microbench/dmma_probe.cu), not an architectural guarantee: re-run `pytest -m gpu` on a
+ * new GPU stepping or driver.  mcp_set_option("value_mma", 0) + ("force_dense", 1) is the scalar-fma escape hatch. */
 int mcp_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *V);
 
 /* tail size t = N - ceil(alpha*N - 1e-7) + 1 */

@@ -38,7 +38,7 @@ class CapacityError(McpError, IndexError):
 
 def build(verbose: bool = False) -> str:
     """Compile libmcp.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j8", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("libmcp.so build failed:\n" + r.stdout + r.stderr)
     if verbose:

@@ -49,8 +49,11 @@ int64_t codec_max_words(int codec, int64_t n)
     // worst case: 32 bits/int packed + one header per 32-int block, or 5 VByte bytes per tail int
     // (tail < 256 ints), plus FastPFOR page/bitmap/exception-count words.  Generous on purpose;
     // the reference sizes its scratch 4n+1024 (LoadPortfolios.java:611).
-    (void)codec;
-    return n + n / 16 + (n / kFpPage + 1) * 40 + 400;
+    // Per FastPFOR page: offset, byte count, byte padding, bitmap and up to 31 x (count + one rounding word).
+    int64_t w = n + n / 16 + (n / kFpPage + 1) * 80 + 400;
+    // VariableByte alone spends up to 5 bytes on every int (values >= 2^28: negative ints, wrapped deltas)
+    if ((codec & MCP_CODEC_MASK) == MCP_CODEC_VB) w = std::max<int64_t>(w, (5 * n + 3) / 4 + 2);
+    return w;
 }
 
 struct EncArgs {
@@ -480,6 +483,7 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
             if (k < 1 || k > 32 || (k >= 2 && stream_base[k] < 0)) return -1;
             __syncwarp();
             const int spos = stream_pos[k];
+            bool past_end = false;
             for (int ex = lane; ex < c; ex += 32) {
                 const int posn = meta[mpos + 3 + ex];
                 if (posn >= B) continue;
@@ -489,6 +493,8 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
                     const int64_t bit = (int64_t)(spos + ex) * k;
                     const int64_t w = bit >> 5;
                     const int sh = (int)(bit & 31);
+                    // a malformed stream may claim more exceptions than its streams hold: never read past the page
+                    if (stream_base[k] + w + (sh + k > 32 ? 1 : 0) >= page_end) { past_end = true; continue; }
                     const uint32_t lo = __ldg(sw + w);
                     const uint32_t hw = (sh + k > 32) ? __ldg(sw + w + 1) : 0u;
                     hi = __funnelshift_r(lo, hw, sh);
@@ -497,6 +503,7 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
                 o[posn] |= hi << b;
             }
             __syncwarp();
+            if (__any_sync(kFull, past_end)) return -1;
             if (lane == 0) stream_pos[k] = spos + c;
             mpos += 3 + c;
         } else

@@ -637,9 +637,11 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
                  double *cvar, int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len)
 {
     MCP_TRY(set_dev(ctx));
-    ctx->haveE = ctx->haveS = false;
     if (P < 0 || N < 0 || F <= 0 || (P > 0 && !E) || (N > 0 && !S)) return fail(ctx, MCP_E_ARG, "simulate: bad argument");
     if (!(alpha > 0.0 && alpha <= 1.0)) return fail(ctx, MCP_E_ARG, "run: alpha must be in (0,1]");
+    if (!codec_ok(codec_id)) return fail(ctx, MCP_E_ARG, "unknown codec id");
+    if (framing != MCP_FRAME_WORDS && framing != MCP_FRAME_APP) return fail(ctx, MCP_E_ARG, "unknown framing");
+    ctx->haveE = ctx->haveS = false; // (only once the arguments are known to be good: a rejected call keeps earlier uploads)
     const int64_t t = mcp_tail_size(N, alpha);
     const int64_t head = N > 0 ? risk_first_step_len(N, t) : 0;
     if (!mma_factor_count(F) || ctx->forceDense || head >= N || P == 0) {
@@ -686,9 +688,11 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     }
     if (rc != MCP_OK) { cudaStreamSynchronize(ctx->stream2); return rc; }
     if (enc_len) *enc_len = ctx->runEncBytes;
-    MCP_TRY(mcp_fetch(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, enc_off, enc, enc_cap)); // (the statistics left under the encode)
+    // (the statistics left under the encode.)  Whatever the fetch says, the side stream's copies into the caller's
+    // buffers must have landed before the call returns: the caller may free or reuse them right away.
+    const int frc = mcp_fetch(ctx, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, enc_off, enc, enc_cap);
     MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream2)); // the statistics and the raw lists
-    return MCP_OK;
+    return frc;
 }
 
 // ---------------------------------------------------------- trial-sharded mode

@@ -4,6 +4,9 @@
 // (e.g. the one bundled with PyTorch), so both sides share one NCCL.
 #include <dlfcn.h>
 
+#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mcp {
@@ -28,18 +31,19 @@ struct Api {
     std::string why;
 };
 
-Api *api()
+void load_api(Api &a)
 {
-    static Api a;
-    static bool tried = false;
-    if (tried) return &a;
-    tried = true;
-    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    // MCP_NCCL_LIB names the library explicitly (tests point it at a path that does not exist to exercise the failure)
+    const char *forced = getenv("MCP_NCCL_LIB");
+    const char *names[] = {forced && *forced ? forced : "libnccl.so.2", forced && *forced ? forced : "libnccl.so"};
+    std::string first_error;
     for (const char *n : names) {
         a.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (a.handle) break;
+        const char *e = dlerror();  // glibc clears the message on read: fetch it exactly once per failure
+        if (first_error.empty()) first_error = e ? e : "not found";
     }
-    if (!a.handle) { a.why = std::string("dlopen(libnccl.so.2): ") + (dlerror() ? dlerror() : "not found"); return &a; }
+    if (!a.handle) { a.why = std::string("dlopen(") + names[0] + "): " + first_error; return; }
     a.get_unique_id = (fn_get_unique_id)dlsym(a.handle, "ncclGetUniqueId");
     a.comm_init_rank = (fn_comm_init_rank)dlsym(a.handle, "ncclCommInitRank");
     a.comm_destroy = (fn_comm_destroy)dlsym(a.handle, "ncclCommDestroy");
@@ -49,6 +53,13 @@ Api *api()
         a.why = "libnccl.so.2 lacks a required symbol";
         a.handle = nullptr;
     }
+}
+
+Api *api()
+{
+    static Api a;
+    static std::once_flag once;  // contexts live on different threads: bind NCCL exactly once
+    std::call_once(once, [] { load_api(a); });
     return &a;
 }
 

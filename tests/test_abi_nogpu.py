@@ -111,3 +111,31 @@ def test_as_i32_java_int_semantics():
     from mcp_b200.engine import as_i32
     assert list(as_i32([-1, 2**31 - 1, 2**32 - 1, 2**31])) == [-1, 2**31 - 1, -1, -2**31]
     assert as_i32(np.array([1, 2], np.uint32)).dtype == np.int32
+
+
+def test_max_bytes_bounds_the_worst_case_of_every_codec():
+    """mcp_codec_max_bytes is documented as an upper bound: VariableByte alone needs 5 bytes per int for values
+    >= 2^28 (negative ints, wrapped deltas of unsorted input) -- the oracle's real sizes must fit for every codec."""
+    from oracle import cref
+    L = N.lib()
+    rng = np.random.default_rng(7)
+    inputs = [np.full(10000, -1), np.full(2351, 1 << 28), rng.integers(-2**31, 2**31, size=70001),
+              np.where(rng.random(66000) < 0.5, rng.integers(0, 1 << 31, size=66000), 0), np.arange(5000)[::-1] * 100003]
+    for codec in range(N.CODEC_COUNT):
+        for flag in (0, N.FLAG_DELTA):
+            for v in inputs:
+                words = cref.compress(codec | flag, v).size
+                assert 4 * words <= L.mcp_codec_max_bytes(codec | flag, N.FRAME_WORDS, len(v)), (codec, flag, len(v), words)
+
+
+def test_missing_nccl_is_an_error_code_not_a_crash():
+    """libmcp.so binds NCCL with dlopen at first use; without the library mcp_comm_unique_id must return MCP_E_NCCL
+    (not segfault: dlerror() may be read only once).  Run in a child process: the binding is cached per process."""
+    import subprocess
+    import sys
+    code = ("import ctypes, sys; sys.path.insert(0, %r); from mcp_b200 import native as N; L = N.lib(); "
+            "buf = (ctypes.c_uint8 * 128)(); rc = L.mcp_comm_unique_id(buf); print('rc', rc); "
+            "sys.exit(0 if rc == N.MCP_E_NCCL else 3)") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MCP_NCCL_LIB="/nonexistent/libnccl.so.2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)

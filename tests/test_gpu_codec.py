@@ -578,3 +578,53 @@ def test_two_lists_back_to_back_headless(ctx):
     assert w[0] == a.size and np.array_equal(w[1:], out[:mid]) and np.array_equal(ic.uncompress(w), a)
     with pytest.raises(mcp_b200.McpError):
         ctx.headless_compress_ints(N.CODEC_FASTPFOR256_VB, a)  # not a skippable id
+
+
+@pytest.mark.parametrize("big", [False, True], ids=["matrix", "multipage"])
+def test_gpu_equals_streams_executed_from_the_reference_java(codec_ctx, big):
+    """tests/golden/codec_streams_golden.json holds what the reference's own Java classes write (executed from
+    /root/reference by the javamini transpiler): the CUDA encoders must produce those words, the CUDA decoders must read
+    them -- for every codec id, with and without Delta, in every kernel family."""
+    import goldenstreams as G
+    ctx = codec_ctx
+    by_cid = {}
+    for label, vals, cid, want, dig in G.entries(N.CODEC_COUNT, big=big):
+        if big != (len(vals) > 1000000):
+            continue
+        by_cid.setdefault(cid, []).append((label, vals, want, dig))
+    assert len(by_cid) == 2 * N.CODEC_COUNT
+    for cid, items in sorted(by_cid.items()):
+        vals, off = batch_of([(lb, v) for lb, v, _, _ in items])
+        out_off, out = ctx.codec_encode(cid, N.FRAME_WORDS, vals, off)
+        for i, (label, v, want, dig) in enumerate(items):
+            G.check(out[out_off[i]: out_off[i + 1]].view(np.int32), want, dig, f"{label} codec {cid:#x}")
+        # decode the REFERENCE's streams (where the fixture holds them in full), not our own
+        full = [(lb, v, w) for lb, v, w, _ in items if w is not None]
+        if full:
+            blobs = [w.view(np.uint8) for _, _, w in full]
+            in_off = np.zeros(len(full) + 1, np.int64)
+            np.cumsum([b.size for b in blobs], out=in_off[1:])
+            o_off = np.zeros(len(full) + 1, np.int64)
+            np.cumsum([len(v) for _, v, _ in full], out=o_off[1:])
+            back = ctx.codec_decode(cid, N.FRAME_WORDS, np.concatenate(blobs) if in_off[-1] else np.zeros(0, np.uint8), in_off, o_off)
+            assert np.array_equal(back, np.concatenate([cases.to_i32(v) for _, v, _ in full]))
+
+
+def test_loader_bytes_of_the_shipped_portfolios_on_the_gpu(ctx):
+    """The bytes LoadPortfolios.getCompressedInstruments (executed from the reference's Java) stores for portfolios.json."""
+    import hashlib
+    import goldenstreams as G
+    c1 = json.load(open(os.path.join(GOLD, "c1_sample.json")))
+    lp = mcp_b200.LoadPortfolios(ctx)
+    for p, rec in zip(c1["portfolios"], G.gold()["loader"]):
+        blob = lp.getCompressedInstruments(p["instruments"])
+        assert len(blob) == rec["bytes"] and hashlib.sha256(blob).hexdigest() == rec["sha256"]
+        assert list(lp.getDecompressedInstruments(blob, rec["n"])) == p["instruments"]
+
+
+def test_variablebyte_worst_case_fits_the_documented_bound(ctx):
+    """mcp_codec_max_bytes must bound VariableByte's 5 bytes per int (values >= 2^28; wrapped deltas)."""
+    v = np.full(10000, -1, np.int64)
+    for cid in (N.CODEC_VB, N.CODEC_VB | N.FLAG_DELTA):
+        words = ctx.compress_ints(cid, v)
+        assert np.array_equal(np.asarray(words).view(np.int32), cref.compress(cid, v))
