@@ -28,7 +28,7 @@ FLAG_DELTA = 0x100
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, a few seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("codec_oracle.c", "risk_oracle.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("codec_oracle.c", "risk_oracle.c", "risk_fast.c", "oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
@@ -83,6 +83,11 @@ def lib() -> C.CDLL:
         L.orc_risk.restype = C.c_int64
         L.orc_risk.argtypes = [f64p, f64p, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int64, C.c_int64,
                                f64p, f64p, f64p, i32p, f64p, i32p, C.c_int]
+        L.orc_risk_fast.restype = C.c_int64
+        L.orc_risk_fast.argtypes = L.orc_risk.argtypes
+        L.orc_value_fast.restype = None
+        L.orc_value_fast.argtypes = L.orc_value.argtypes
+        L.orc_fast_isa.restype = C.c_char_p
         L.orc_tail_size.restype = C.c_int64
         L.orc_tail_size.argtypes = [C.c_int64, C.c_double]
         L.orc_philox4x32_10.restype = None
@@ -258,14 +263,15 @@ def build_exposures(instruments, weights, pos_off, loadings) -> np.ndarray:
     return E
 
 
-def value(E: np.ndarray, S: np.ndarray, nthreads: int = 0) -> np.ndarray:
+def value(E: np.ndarray, S: np.ndarray, nthreads: int = 0, fast: bool = False) -> np.ndarray:
+    """fast=True: the SIMD baseline (risk_fast.c) instead of the literal scalar chain -- bit-identical by construction."""
     E = np.ascontiguousarray(E, np.float64)
     S = np.ascontiguousarray(S, np.float64)
     P, F = E.shape
     N = S.shape[0]
     assert S.shape[1] == F
     V = np.empty((P, N), np.float64)
-    lib().orc_value(_p(E, C.c_double), _p(S, C.c_double), P, N, F, _p(V, C.c_double), nthreads or lib().orc_num_threads())
+    (lib().orc_value_fast if fast else lib().orc_value)(_p(E, C.c_double), _p(S, C.c_double), P, N, F, _p(V, C.c_double), nthreads or lib().orc_num_threads())
     return V
 
 
@@ -273,7 +279,12 @@ def tail_size(N: int, alpha: float) -> int:
     return lib().orc_tail_size(N, alpha)
 
 
-def risk(E: np.ndarray, S: np.ndarray, alpha: float, p0: int = 0, p1: int | None = None, nthreads: int = 0) -> dict:
+def fast_isa() -> str:
+    return lib().orc_fast_isa().decode()
+
+
+def risk(E: np.ndarray, S: np.ndarray, alpha: float, p0: int = 0, p1: int | None = None, nthreads: int = 0,
+         fast: bool = False) -> dict:
     E = np.ascontiguousarray(E, np.float64)
     S = np.ascontiguousarray(S, np.float64)
     P, F = E.shape
@@ -285,7 +296,7 @@ def risk(E: np.ndarray, S: np.ndarray, alpha: float, p0: int = 0, p1: int | None
         "mean": np.empty(q), "variance": np.empty(q), "var_loss": np.empty(q),
         "var_trial": np.empty(q, np.int32), "cvar": np.empty(q), "breach": np.empty((q, t), np.int32),
     }
-    lib().orc_risk(_p(E, C.c_double), _p(S, C.c_double), P, N, F, alpha, p0, p1,
+    (lib().orc_risk_fast if fast else lib().orc_risk)(_p(E, C.c_double), _p(S, C.c_double), P, N, F, alpha, p0, p1,
                    _p(res["mean"], C.c_double), _p(res["variance"], C.c_double), _p(res["var_loss"], C.c_double),
                    _p(res["var_trial"], C.c_int32), _p(res["cvar"], C.c_double), _p(res["breach"], C.c_int32),
                    nthreads or lib().orc_num_threads())

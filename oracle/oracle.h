@@ -128,6 +128,16 @@ int64_t orc_risk(const double *E, const double *S, int64_t P, int64_t N, int32_t
 
 int64_t orc_tail_size(int64_t N, double alpha);
 
+/* risk_fast.c: the same results computed fast (SIMD across trials, portfolio-blocked, threshold-prefiltered select) --
+ * the CPU BASELINE bench.py times.  V, var_loss, var_trial, the breach lists and cvar are bit-identical to orc_value /
+ * orc_risk (asserted in tests/test_oracle_risk.py); mean / variance agree to 1e-9 (double two-pass instead of long double). */
+void orc_value_fast(const double *E, const double *S, int64_t P, int64_t N, int32_t F, double *V, int nthreads);
+int64_t orc_risk_fast(const double *E, const double *S, int64_t P, int64_t N, int32_t F, double alpha,
+                      int64_t p0, int64_t p1,
+                      double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
+                      int32_t *breach_idx, int nthreads);
+const char *orc_fast_isa(void); /* "avx512f" or "avx2+fma": the body picked on this host */
+
 /* Philox4x32-10 synthetic generators (shared definition with the CUDA side) */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_gen_normal(double *out, int64_t rows, int32_t cols, uint64_t seed, uint32_t tensor_id,

@@ -164,3 +164,36 @@ def test_simulation_documents_follow_the_loader_document_shape():
     o2 = dict(o, tail=2, breach=np.array([[5, 2**30]] * 5, np.int32), enc=np.zeros(5 * 64, np.uint8), enc_off=np.arange(6, dtype=np.int64) * 64)
     d2 = portfolio.simulation_documents(range(5), o2, 0.98)
     assert d2[0]["breaches"]["algo"] == "none" and d2[0]["breaches"]["compressed"] == (5).to_bytes(4, "big") + (2**30).to_bytes(4, "big")
+
+
+@pytest.mark.parametrize("isa", ["auto", "avx2"])
+@pytest.mark.parametrize("shape", [(5, 10, 10, 0.9), (9, 5000, 32, 0.99), (6, 20011, 64, 0.99), (7, 4099, 17, 0.95), (3, 257, 5, 0.5),
+                                   (2, 64, 3, 1.0), (13, 40000, 32, 0.999)])
+def test_fast_cpu_baseline_equals_the_scalar_oracle(shape, isa, monkeypatch):
+    """risk_fast.c (what bench.py times as the CPU baseline: SIMD across trials, blocked, prefiltered select) must give the
+    scalar oracle's results: V, VaR loss + trial, breach lists and CVaR bit for bit, moments to 1e-9."""
+    if isa == "avx2":
+        monkeypatch.setenv("ORC_FAST_ISA", "avx2")
+    P, N, F, alpha = shape
+    for E, S in (riskcases.synthetic(P, N, F, 5), riskcases.with_ties(P, N, F, 6)):
+        assert np.array_equal(cref.value(E, S, fast=True), cref.value(E, S))
+        a, b = cref.risk(E, S, alpha, fast=True), cref.risk(E, S, alpha)
+        for k in ("var_loss", "var_trial", "breach", "cvar"):
+            assert np.array_equal(a[k], b[k]), k
+        np.testing.assert_allclose(a["mean"], b["mean"], rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(a["variance"], b["variance"], rtol=1e-9, atol=0)
+    # a sub-range of the portfolios, like the bench's bounded sample
+    E, S = riskcases.synthetic(11, 6000, 32, 9)
+    a, b = cref.risk(E, S, 0.99, 3, 10, fast=True), cref.risk(E, S, 0.99, 3, 10)
+    assert np.array_equal(a["breach"], b["breach"]) and np.array_equal(a["var_trial"], b["var_trial"])
+
+
+def test_fast_cpu_baseline_survives_an_unlucky_sample():
+    """Descending losses put the whole tail where the 1/64 sample cannot see it coming: the fallback must be exact."""
+    N, F = 8192, 4
+    S = np.zeros((N, F))
+    S[:, 0] = np.linspace(1.0, 0.0, N) ** 8
+    S[::64, 0] = 5.0  # every sampled trial is a gain: the threshold lands far above the real tail
+    E = np.ones((3, F))
+    a, b = cref.risk(E, S, 0.99, fast=True), cref.risk(E, S, 0.99)
+    assert np.array_equal(a["breach"], b["breach"]) and np.array_equal(a["var_loss"], b["var_loss"])
