@@ -802,6 +802,44 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Decoupled look-back by one warp: the word offset of batch `batch` in the output = the sum of the totals of all batches
+// before it.  Every batch publishes its aggregate before it looks back and its inclusive prefix after; hundreds to
+// thousands of batches are in flight at any time and none of them has an inclusive prefix until its own look-back ends,
+// so the walk is long: FOUR state words per lane (128 predecessors) are requested together per round -- one round trip
+// where a 32-wide poll takes four.  Publishes the inclusive prefix; returns the exclusive one.
+__device__ __forceinline__ long long lookback_wide(uint64_t *state, int64_t batch, long long T, int lane)
+{
+    long long base = 0;
+    if (batch > 0) {
+        for (int64_t j = batch - 1;; j -= 128) {
+            uint64_t st[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t idx = j - lane - 32 * q;
+                st[q] = idx >= 0 ? ld_relaxed_u64(state + idx) : kLbInc; // before the first batch: an inclusive prefix of 0
+            }
+            bool done = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!done) {
+                    const int64_t idx = j - lane - 32 * q;
+                    while ((st[q] >> 62) == 0) { __nanosleep(32); st[q] = ld_relaxed_u64(state + idx); }
+                    const unsigned inc = __ballot_sync(kFull, (st[q] >> 62) == 2);
+                    const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
+                    long long v = lane <= first ? (long long)(st[q] & kLbMask) : 0;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+                    base += v;
+                    done = inc != 0;
+                }
+            }
+            if (done) break;
+        }
+        if (lane == 0) st_relaxed_u64(state + batch, kLbInc | (uint64_t)(base + T));
+    }
+    return base;
+}
+
 // exclusive scan of one int per thread over the CTA (FE_THREADS = 4 warps); returns the exclusive prefix, *total = sum
 __device__ __forceinline__ int cta_excl_scan(int v, int *s_w /* [5] */, int *total)
 {
@@ -1057,22 +1095,7 @@ __global__ void __launch_bounds__(FE_THREADS, FE_MINB) k_bp_encode_fast(const Fa
     // Batches take tickets in launch order, so every predecessor is already running and publishes its aggregate
     // without waiting on anyone: the spin below is bounded.
     if (warp == 0) {
-        long long base = 0;
-        if (batch > 0) {
-            for (int64_t j = batch - 1;; j -= 32) {
-                const int64_t idx = j - lane;
-                uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
-                if (idx >= 0) while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
-                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
-                const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
-                long long v = lane <= first ? (long long)(st & kLbMask) : 0;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-                base += v;
-                if (inc) break;
-            }
-            if (lane == 0) st_relaxed_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
-        }
+        const long long base = lookback_wide(a.state, batch, T, lane);
         if (lane == 0) {
             s_base = base;
             if (batch == a.nbatches - 1) {
@@ -1526,22 +1549,7 @@ __global__ void __launch_bounds__(FE_THREADS, 6) k_fp_encode_fast(const FastEncA
     }
     __syncthreads();
     if (warp == 0) {
-        long long base = 0;
-        if (batch > 0) {
-            for (int64_t j = batch - 1;; j -= 32) {
-                const int64_t idx = j - lane;
-                uint64_t st = kLbInc;
-                if (idx >= 0) while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
-                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
-                const int first = inc ? __ffs(inc) - 1 : 31;
-                long long vv = lane <= first ? (long long)(st & kLbMask) : 0;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) vv += __shfl_xor_sync(kFull, vv, d);
-                base += vv;
-                if (inc) break;
-            }
-            if (lane == 0) st_relaxed_u64(a.state + batch, kLbInc | (uint64_t)(base + T));
-        }
+        const long long base = lookback_wide(a.state, batch, T, lane);
         if (lane == 0) {
             s_base = base;
             if (batch == a.nbatches - 1) {
@@ -2047,24 +2055,8 @@ __global__ void __launch_bounds__(SL_WARPS * 32, SL_CTAS) k_sl_encode(const Fast
         const int c_nl = nl;
         take_batch(batch, nl, L, vbase, slow, maxnb, nst);
         if (nst > 0) request_stage(0, L, maxnb, vbase, s_inw[warp][0]);
-        // ---- decoupled look-back, 32 predecessors per round
-        long long base = 0;
-        if (c_batch > 0) {
-            for (int64_t j = c_batch - 1;; j -= 32) {
-                const int64_t idx = j - lane;
-                uint64_t st = kLbInc; // before the first batch: an inclusive prefix of 0
-                if (idx >= 0)
-                    while (((st = ld_relaxed_u64(a.state + idx)) >> 62) == 0) __nanosleep(64);
-                const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
-                const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
-                long long v = lane <= first ? (long long)(st & kLbMask) : 0;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-                base += v;
-                if (inc) break;
-            }
-            if (lane == 0) st_relaxed_u64(a.state + c_batch, kLbInc | (uint64_t)(base + T));
-        }
+        // ---- decoupled look-back, 128 predecessors per round (lookback_wide)
+        const long long base = lookback_wide(a.state, c_batch, T, lane);
         if (lane < c_nl) a.out_off[l0 + lane] = 4 * (base + lex);
         if (lane == 0 && c_batch == a.nbatches - 1) {
             *a.total = 4 * (base + T);
@@ -2273,6 +2265,611 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
     cp_async_wait<0>();
 }
 
+// ================================================================================================
+// Flat (lane-parallel) VariableByte kernels: lists that are ALL VariableByte -- Composition(FastPFOR | FastPFOR128,
+// VariableByte) on lists shorter than one block (Composition writes the 0 marker and hands the whole list to
+// VariableByte, FastPFOR.java:311-313, Composition.java:45-48: BASELINE config C4 under the north-star codec), the
+// skippable forms of the same, and VariableByte alone.
+//
+// The thread-per-list kernels above walk a list serially (~45 instructions per value, a warp as slow as its longest
+// list).  Here a CTA owns a TILE of consecutive lists and works on the tile's values as ONE flat array:
+//   encode  a thread owns 8 consecutive values of a 16-byte-aligned window over `vals` (two LDG.128, fully coalesced);
+//           list starts are one bit per window position in shared memory; gaps, byte lengths, ONE block scan of
+//           (bytes | starts << 16) gives every value its byte offset in the tile and its list; per-list sizes, framing words
+//           and the tile's place in the output (decoupled look-back on one state word per tile, published BEFORE the bytes
+//           are written) are one warp's work; bytes go to a staging area with byte stores, the tile leaves with coalesced
+//           word stores (byte-swapped for the loader's framing);
+//   decode  a thread owns 4 consecutive compressed words (one LDG.128): terminator-bit popcounts, one block scan, a
+//           16-byte serial walk that restarts at every list's first payload word (the Java decoder starts each list with
+//           v = 0, shift = 0), values into a staging area aligned like the output; then 8 values per thread: flat
+//           prefix sums minus the sum at the list's start (Delta.inverseDelta), two STG.128 per thread.
+// A tile that does not fit (window, staging area) is done by the warp-per-list routines inside the same kernel; a
+// FastPFOR list of a whole block or more raises flag 2 and the host takes the batched kernels, as before.
+constexpr int VF_THREADS = 256;
+constexpr int VF_VPT = 8;                      // window positions per thread (encode)
+constexpr int VF_SPAN = VF_THREADS * VF_VPT;   // 2 048 window positions per tile
+constexpr int VF_MAXL = 32;                    // lists per tile: one warp keeps the per-list books
+constexpr int VF_OCAP = 2816;                  // staged output words per tile (encode)
+constexpr int VF_WSPAN = VF_THREADS * 4;       // compressed words per tile (decode)
+constexpr int VF_VCAP = 4 * VF_WSPAN + 8;      // staged values per tile (decode): at most four values end in a word
+
+__device__ __forceinline__ uint4 ldg128(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// exclusive block scan of one 32-bit word per thread (VF_THREADS threads); *total = the block's sum.  s_w: 8 words.
+__device__ __forceinline__ uint32_t vf_block_scan(uint32_t v, uint32_t *s_w, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < VF_THREADS / 32; ++w) {
+        const uint32_t x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    *total = tot;
+    return off + incl - v;
+}
+
+// sum of the nibbles of x below nibble k
+__device__ __forceinline__ int nib_prefix(uint32_t x, int k)
+{
+    x = k >= 8 ? x : x & ((1u << (4 * k)) - 1u);
+    x = (x & 0x0f0f0f0fu) + ((x >> 4) & 0x0f0f0f0fu);
+    return (int)((x * 0x01010101u) >> 24);
+}
+
+// the tile's word base in the output: decoupled look-back by ONE warp over the per-tile state words (aggregate
+// published by the caller beforehand); publishes the inclusive prefix
+// `early` = this lane's predecessor state word as read at the tile's start (usually already published by now)
+__device__ __forceinline__ long long vf_lookback(uint64_t *state, int64_t tile, long long T, int lane, uint64_t early)
+{
+    long long base = 0;
+    if (tile > 0) {
+        bool first_round = true;
+        for (int64_t j = tile - 1;; j -= 32) {
+            const int64_t idx = j - lane;
+            uint64_t st = kLbInc; // before the first tile: an inclusive prefix of 0
+            if (idx >= 0) {
+                st = first_round ? early : 0;
+                while ((st >> 62) == 0) { st = ld_relaxed_u64(state + idx); if ((st >> 62) == 0) __nanosleep(32); }
+            }
+            first_round = false;
+            const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
+            const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
+            long long v = lane <= first ? (long long)(st & kLbMask) : 0;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+            base += v;
+            if (inc) break;
+        }
+        if (lane == 0) st_relaxed_u64(state + tile, kLbInc | (uint64_t)(base + T));
+    }
+    return base;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+// Tiles are handed out by a ticket counter, in order, to CTAs that are running -- so the look-back can never wait on
+// a tile nobody works on (the smallest unfinished tile is always some CTA's CURRENT tile) -- but three tiles ahead:
+// the global-memory latencies are taken off the per-tile critical path.  While tile i is worked on, the ticket of
+// tile i+3, the list offsets of tile i+2 and the values of tile i+1 (cp.async, 16 bytes per copy) are in flight, and
+// the predecessors' look-back state words are read at the tile's start, long before they are needed.
+__global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs a)
+{
+    __shared__ __align__(16) uint32_t s_vals[2][VF_SPAN];
+    __shared__ uint32_t s_out[VF_OCAP];
+    __shared__ uint32_t s_flag[VF_SPAN / 32];
+    __shared__ int64_t s_offr[3][VF_MAXL + 1]; // ring: list offsets of this tile, the next and the one after
+    __shared__ int s_rel[VF_MAXL + 1]; // list starts as window positions
+    __shared__ int s_ps[VF_MAXL + 2];  // flat byte prefix at the first value of the r-th NON-EMPTY list; [count] = total
+    __shared__ int s_ob[VF_MAXL];      // r-th non-empty list: byte address of its payload in s_out minus s_ps[r]
+    __shared__ int s_wb[VF_MAXL + 1];  // first output word of each list inside the tile (list order); [nl] = total
+    __shared__ uint32_t s_scan[VF_THREADS / 32];
+    __shared__ long long s_base;
+    __shared__ long long s_tq[4];      // ring: this CTA's tickets (tile ids), three ahead
+    __shared__ int s_slow;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    uint8_t *sb = reinterpret_cast<uint8_t *>(s_out);
+
+    auto tile_lists = [&](int64_t tile) -> int { return tile < a.nbatches ? (int)min((int64_t)a.lists_per_batch, a.nlists - tile * a.lists_per_batch) : 0; };
+    auto load_off = [&](int64_t tile) -> int64_t { // this thread's entry of a tile's offsets (0 past the end)
+        const int nl = tile_lists(tile);
+        if (tile >= a.nbatches || tid > nl) return 0;
+        const int64_t l = tile * a.lists_per_batch + tid;
+        return a.list_off ? a.list_off[l] : l * a.uniform_len;
+    };
+    // the tile's window over vals: 16-byte aligned start, a0 = position of the first value in it
+    auto request_values = [&](int64_t tile, const int64_t *off, uint32_t *buf) {
+        const int nl = tile_lists(tile);
+        if (nl > 0) {
+            const int64_t base = off[0], nv = off[nl] - base;
+            const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3);
+            const int64_t span = a0 + nv;
+            if (nv >= 0 && span <= VF_SPAN) {
+                const uint32_t *wp = a.vals + base - a0;
+                const int p0 = VF_VPT * tid;
+                if (p0 < span) cp_async16(buf + p0, wp + p0);
+                if (p0 + 4 < span) cp_async16(buf + p0 + 4, wp + p0 + 4);
+            }
+        }
+        cp_async_commit();
+    };
+
+    {
+        // the first three tiles of every CTA are k, k + G, k + 2G (the counter starts at 3G): a well-mixed start -- consecutive
+        // tiles belong to different CTAs, all of them running (the grid is sized to be fully resident)
+        if (tid == 0) { s_tq[0] = blockIdx.x; s_tq[1] = blockIdx.x + (long long)gridDim.x; s_tq[2] = blockIdx.x + 2ll * gridDim.x; }
+        __syncthreads();
+        const int64_t o0 = load_off(s_tq[0]), o1 = load_off(s_tq[1]);
+        if (tid <= VF_MAXL) { s_offr[0][tid] = o0; s_offr[1][tid] = o1; }
+        __syncthreads();
+        request_values(s_tq[0], s_offr[0], s_vals[0]);
+    }
+    for (int it = 0;; ++it) {
+        const int64_t tile = s_tq[it & 3];
+        if (tile >= a.nbatches) break; // (tickets only grow: every later one of this CTA is past the end too)
+        const int64_t *off = s_offr[it % 3];
+        const uint32_t *vbuf = s_vals[it & 1];
+        const int64_t l0 = tile * a.lists_per_batch;
+        const int nl = tile_lists(tile);
+        // ---- requests for later tiles, and an early look at the predecessors' state words
+        long long tk_next3 = 0;
+        if (tid == 0) tk_next3 = (long long)atomicAdd(a.ticket, 1ull);
+        const int64_t off_next2 = load_off(s_tq[(it + 2) & 3]);
+        request_values(s_tq[(it + 1) & 3], s_offr[(it + 1) % 3], s_vals[(it + 1) & 1]);
+        uint64_t st_early = kLbInc;
+        if (warp == 0 && tile - 1 - lane >= 0) st_early = ld_relaxed_u64(a.state + (tile - 1 - lane));
+        if (tid < VF_SPAN / 32) s_flag[tid] = 0;
+        const int64_t base = off[0], nv = off[nl] - base;
+        const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3);
+        const int64_t span = a0 + nv;
+        bool bad = false;
+        if (tid < nl) {
+            const int64_t n = off[tid + 1] - off[tid];
+            bad = n < 0 || (tr.fastpfor && n >= tr.fp_block);
+        }
+        bad = bad || span > VF_SPAN || nv < 0;
+        if (tid <= nl && !(span > VF_SPAN || nv < 0)) s_rel[tid] = a0 + (int)(off[tid] - base);
+        cp_async_wait<1>(); // this tile's values (requested one tile ago) have landed
+        const int slow = __syncthreads_or(bad);
+        long long T = 0; // words of the tile
+        if (!slow) {
+            // ---- list starts (non-empty lists only: a value belongs to the LAST list that starts at its position)
+            if (tid < nl && s_rel[tid + 1] > s_rel[tid]) atomicOr(&s_flag[s_rel[tid] >> 5], 1u << (s_rel[tid] & 31));
+            // ---- this thread's 8 window positions
+            const int p0 = VF_VPT * tid;
+            uint32_t x[8];
+            {
+                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+                if (p0 < span) q0 = *reinterpret_cast<const uint4 *>(vbuf + p0);
+                if (p0 + 4 < span) q1 = *reinterpret_cast<const uint4 *>(vbuf + p0 + 4);
+                x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+            }
+            uint32_t prev = __shfl_up_sync(kFull, x[7], 1);
+            if (lane == 0) prev = (tid > 0 && p0 < span) ? vbuf[p0 - 1] : 0u;
+            __syncthreads(); // the start bits are in place
+            const uint32_t fw = (s_flag[p0 >> 5] >> (p0 & 31)) & 0xffu;
+            uint32_t vm = 0; // valid positions
+#pragma unroll
+            for (int k = 0; k < 8; ++k) vm |= (uint32_t)(p0 + k >= a0 && p0 + k < span) << k;
+            // ---- the sequence the codec sees (Delta.delta: gaps, the first value of a list as it is), byte lengths
+            uint32_t d[8], wor = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                d[k] = (a.delta && !((fw >> k) & 1u)) ? x[k] - prev : x[k];
+                prev = x[k];
+                if ((vm >> k) & 1u) wor |= d[k];
+            }
+            const bool small = __reduce_or_sync(kFull, wor) < 16384u; // warp-uniform: every value takes one or two bytes
+            uint32_t lens = 0;
+            int nbytes = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int len = small ? 1 + (int)(d[k] >= 128u) : vb_len(d[k]);
+                len = ((vm >> k) & 1u) ? len : 0;
+                lens |= (uint32_t)len << (4 * k);
+                nbytes += len;
+            }
+            uint32_t tot;
+            const uint32_t ex = vf_block_scan((uint32_t)nbytes | ((uint32_t)__popc(fw) << 16), s_scan, &tot);
+            const int B0 = (int)(ex & 0xffffu), L0 = (int)(ex >> 16);
+            {
+                uint32_t f = fw;
+                int r = L0;
+                while (f) {
+                    const int k = __ffs(f) - 1;
+                    f &= f - 1;
+                    s_ps[r++] = B0 + nib_prefix(lens, k);
+                }
+            }
+            if (tid == VF_THREADS - 1) s_ps[tot >> 16] = (int)(tot & 0xffffu);
+            __syncthreads();
+            // ---- per-list sizes and framing (one warp): IntCompressor writes n first, Composition the 0 marker when FastPFOR
+            // took nothing, the loader's framing one trailing zero word (LoadPortfolios.java:622)
+            if (warp == 0) {
+                const int n = lane < nl ? s_rel[lane + 1] - s_rel[lane] : 0;
+                const unsigned ne = __ballot_sync(kFull, n > 0);
+                const int r = __popc(ne & ((1u << lane) - 1u));
+                const int bytes = n > 0 ? s_ps[r + 1] - s_ps[r] : 0;
+                const int hdr = lane < nl ? (tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0)) : 0;
+                const int words = lane < nl ? hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0) : 0;
+                int incl = words;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int t = __shfl_up_sync(kFull, incl, dd);
+                    if (lane >= dd) incl += t;
+                }
+                const int wb = incl - words;
+                T = __shfl_sync(kFull, incl, 31);
+                const bool fits = T <= VF_OCAP;
+                if (lane < nl) s_wb[lane] = wb;
+                if (lane == 0) s_wb[nl] = (int)T;
+                if (fits && lane < nl) {
+                    if (hdr) s_out[wb] = tr.sk ? (uint32_t)n : 0u;
+                    if (bytes > 0) s_out[wb + hdr + ((bytes - 1) >> 2)] = 0u; // the zero padding of the last payload word
+                    if (a.app) s_out[wb + words - 1] = 0u;
+                    if (n > 0) s_ob[r] = 4 * (wb + hdr) - s_ps[r];
+                }
+                if (lane == 0) {
+                    s_slow = fits ? 0 : 1;
+                    if (fits) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+                }
+            }
+            __syncthreads();
+            if (!s_slow) {
+                if (warp == 0) {
+                    // the tile's place in the output: the look-back runs while the other warps write the bytes
+                    const long long b = vf_lookback(a.state, tile, T, lane, st_early);
+                    if (lane == 0) s_base = b;
+                }
+                {
+                    // ---- bytes (VariableByte.java:44-68: 7-bit groups, low group first, bit 7 on the LAST byte)
+                    int li = L0 - 1, ob = li >= 0 ? s_ob[li] : 0, bo = B0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if ((fw >> k) & 1u) ob = s_ob[++li];
+                        const int len = (int)((lens >> (4 * k)) & 15u);
+                        if (len) {
+                            uint8_t *dst = sb + ob + bo;
+                            uint32_t v = d[k];
+                            if (small) {
+                                dst[0] = (uint8_t)((v & 127u) | (len == 1 ? 128u : 0u));
+                                if (len == 2) dst[1] = (uint8_t)((v >> 7) | 128u);
+                            } else {
+                                for (int j = 0; j < len - 1; ++j) { dst[j] = (uint8_t)(v & 127u); v >>= 7; }
+                                dst[len - 1] = (uint8_t)(v | 128u);
+                            }
+                            bo += len;
+                        }
+                    }
+                }
+                __syncthreads();
+                const long long gbase = s_base;
+                T = s_wb[nl];
+                if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
+                if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
+                if (4 * (gbase + T) > a.cap) { // caller's buffer too small: report, write nothing
+                    if (tid == 0) atomicMax(a.err, 1);
+                } else {
+                    uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
+                    const uint32_t sel = a.app ? 0x0123u : 0x3210u;
+                    for (int i = tid; i < (int)T; i += VF_THREADS) gout[i] = __byte_perm(s_out[i], 0, sel);
+                }
+                if (tid <= VF_MAXL) s_offr[(it + 2) % 3][tid] = off_next2;
+                if (tid == 0) s_tq[(it + 3) & 3] = tk_next3;
+                __syncthreads();
+                continue;
+            }
+        }
+        // ---- a tile that does not fit: sizes, look-back and streams by the warp-per-list routines
+        bool page = false;
+        if (tid < nl) page = tr.fastpfor && off[tid + 1] - off[tid] >= tr.fp_block;
+        const int has_page = __syncthreads_or(page);
+        uint32_t *stage = s_out + 64 * warp;
+        if (has_page) {
+            if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
+        } else {
+            for (int j = warp; j < nl; j += VF_THREADS / 32) {
+                const int64_t w = warp_short_list_encode<false>(tr, ValSeq{a.vals + off[j], a.delta}, off[j + 1] - off[j],
+                                                                WordSink{nullptr, a.app}, a.app, stage, lane);
+                if (lane == 0) s_ob[j] = (int)w; // (the slow path reuses s_ob for the lists' sizes in words)
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            long long w = (!has_page && lane < nl) ? (long long)s_ob[lane] : 0;
+            long long incl = w;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const long long t = __shfl_up_sync(kFull, incl, dd);
+                if (lane >= dd) incl += t;
+            }
+            T = __shfl_sync(kFull, incl, 31);
+            if (lane < nl) s_wb[lane] = (int)(incl - w);
+            if (lane == 0) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
+            const long long b = vf_lookback(a.state, tile, T, lane, st_early);
+            if (lane == 0) { s_base = b; s_wb[nl] = (int)T; }
+        }
+        __syncthreads();
+        {
+            const long long gbase = s_base;
+            T = s_wb[nl];
+            if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
+            if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
+            if (4 * (gbase + T) > a.cap) {
+                if (tid == 0) atomicMax(a.err, 1);
+            } else if (!has_page) {
+                uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
+                for (int j = warp; j < nl; j += VF_THREADS / 32) {
+                    const int64_t beg = off[j], n = off[j + 1] - beg;
+                    warp_short_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_wb[j], a.app}, a.app, stage, lane);
+                    __syncwarp();
+                }
+            }
+        }
+        if (tid <= VF_MAXL) s_offr[(it + 2) % 3][tid] = off_next2;
+        if (tid == 0) s_tq[(it + 3) & 3] = tk_next3;
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+__global__ void __launch_bounds__(VF_THREADS, 4) k_vbf_decode(const FastDecArgs a, int64_t ntiles)
+{
+    __shared__ __align__(16) uint32_t s_val[VF_VCAP + 8];
+    __shared__ __align__(16) uint32_t s_words[2][VF_WSPAN]; // this tile's and the next tile's compressed words (cp.async)
+    __shared__ uint32_t s_wflag[VF_WSPAN / 32]; // bit w: a list's payload starts at window word w (the decoder restarts there)
+    __shared__ uint32_t s_hmask[VF_WSPAN / 32]; // bit w: window word w is an IntCompressor count word (not payload)
+    __shared__ int64_t s_inr[3][VF_MAXL + 1], s_oor[3][VF_MAXL + 1]; // rings: offsets of this tile, the next, the one after
+    __shared__ int s_wrel[VF_MAXL + 1], s_vrel[VF_MAXL + 1];
+    __shared__ uint32_t s_ss[VF_MAXL];          // flat sum of the staged values before the list's first one
+    __shared__ int s_cp[VF_THREADS + 1];        // values ending before each thread's first word
+    __shared__ uint32_t s_scan[VF_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    const uint32_t sel = a.app ? 0x0123u : 0x3210u; // big-endian framing: words are swapped as they are read
+    const int64_t G = gridDim.x;
+
+    auto tile_lists = [&](int64_t tile) -> int { return tile < ntiles ? (int)min((int64_t)a.lists_per_batch, a.nlists - tile * a.lists_per_batch) : 0; };
+    auto load_off = [&](int64_t tile, int64_t &io, int64_t &oo) {
+        io = 0; oo = 0;
+        if (tile < ntiles && tid <= tile_lists(tile)) { io = a.in_off[tile * a.lists_per_batch + tid]; oo = a.out_off[tile * a.lists_per_batch + tid]; }
+    };
+    auto request_words = [&](int64_t tile, const int64_t *in, uint32_t *buf) {
+        const int nl = tile_lists(tile);
+        if (nl > 0) {
+            const int64_t ib = in[0], nwords = (in[nl] - ib) >> 2;
+            const int aw = (int)((reinterpret_cast<uintptr_t>(a.in + ib) >> 2) & 3);
+            if ((ib & 3) == 0 && nwords >= 0 && aw + nwords <= VF_WSPAN) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a.in + ib) - aw;
+                if (4 * tid < aw + nwords) cp_async16(buf + 4 * tid, wp + 4 * tid);
+            }
+        }
+        cp_async_commit();
+    };
+    {
+        int64_t i0, o0, i1, o1;
+        load_off(blockIdx.x, i0, o0);
+        load_off(blockIdx.x + G, i1, o1);
+        if (tid <= VF_MAXL) { s_inr[0][tid] = i0; s_oor[0][tid] = o0; s_inr[1][tid] = i1; s_oor[1][tid] = o1; }
+        __syncthreads();
+        request_words(blockIdx.x, s_inr[0], s_words[0]);
+    }
+    int it = -1;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
+        ++it;
+        const int64_t *s_in = s_inr[it % 3], *s_oo = s_oor[it % 3];
+        const uint32_t *wbuf = s_words[it & 1];
+        const int64_t l0 = tile * a.lists_per_batch;
+        const int nl = tile_lists(tile);
+        (void)l0;
+        __syncthreads(); // the previous tile's shared state has been consumed; its ring slots have been written
+        int64_t in2, oo2;
+        load_off(tile + 2 * G, in2, oo2);
+        request_words(tile + G, s_inr[(it + 1) % 3], s_words[(it + 1) & 1]);
+        // the ring slot of the tile after next is free from here on (its previous user was the tile before this one)
+        if (tid <= VF_MAXL) { s_inr[(it + 2) % 3][tid] = in2; s_oor[(it + 2) % 3][tid] = oo2; }
+        if (tid < VF_WSPAN / 32) { s_wflag[tid] = 0; s_hmask[tid] = 0; }
+        cp_async_wait<1>(); // this tile's words (requested one tile ago) have landed
+        __syncthreads();
+        const int64_t ib = s_in[0], ob = s_oo[0];
+        const int64_t nwords = (s_in[nl] - ib) >> 2, nvals = s_oo[nl] - ob;
+        const int aw = (int)((reinterpret_cast<uintptr_t>(a.in + ib) >> 2) & 3);   // 16-byte aligned window over the words
+        const int ao = (int)((reinterpret_cast<uintptr_t>(a.out + ob) >> 2) & 3);  // staging area aligned like the output
+        int st = 0; // 1 = malformed, 2 = FastPFOR page, 4 = does not fit the tile
+        if (tid < nl) {
+            const int64_t b0 = s_in[tid], b1 = s_in[tid + 1], n = s_oo[tid + 1] - s_oo[tid];
+            if (((b0 | b1) & 3) != 0 || b1 < b0 || n < 0) st = 1;
+            else if (tr.fastpfor && n >= tr.fp_block) st = 2;
+        }
+        if (((ib & 3) != 0) || nwords < 0 || nvals < 0) st |= 1;
+        else if (aw + nwords > VF_WSPAN || nvals > VF_VCAP - 8) st |= 4;
+        int tile_st = 0; // (__syncthreads_or returns a truth value, not the OR of the arguments)
+        if (__syncthreads_or(st)) tile_st = (__syncthreads_or(st & 1) ? 1 : 0) | (__syncthreads_or(st & 2) ? 2 : 0) | (__syncthreads_or(st & 4) ? 4 : 0);
+        if (tile_st & 1) { if (tid == 0) atomicMax(a.err, 3); continue; }
+        if (tile_st & 2) { if (tid == 0) atomicMax(a.err, 2); continue; }
+        if (tile_st & 4) {
+            for (int j = warp; j < nl; j += VF_THREADS / 32) {
+                const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + s_in[j]), a.app};
+                const bool ok = warp_short_list_decode(tr, src, (s_in[j + 1] - s_in[j]) >> 2, s_oo[j + 1] - s_oo[j], a.out + s_oo[j], a.delta, lane);
+                if (!ok && lane == 0) atomicMax(a.err, 4);
+                __syncwarp();
+            }
+            continue;
+        }
+        const uint32_t *wp = wbuf; // the window, staged
+        const int wspan = aw + (int)nwords;
+        // ---- per-list books: word / value extents, header checks, restart and count-word bits
+        bool ok = true;
+        if (tid <= nl) {
+            s_wrel[tid] = aw + (int)((s_in[tid] - ib) >> 2);
+            s_vrel[tid] = (int)(s_oo[tid] - ob);
+        }
+        if (tid < nl) {
+            const int w0 = aw + (int)((s_in[tid] - ib) >> 2), w1 = aw + (int)((s_in[tid + 1] - ib) >> 2);
+            const int n = (int)(s_oo[tid + 1] - s_oo[tid]);
+            const int hdr = tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0);
+            if (w1 - w0 < hdr) ok = false;
+            else {
+                if (hdr) {
+                    const uint32_t h = __byte_perm(wp[w0], 0, sel);
+                    if (h != (tr.sk ? (uint32_t)n : 0u)) ok = false; // IntCompressor's n / Composition's marker (FastPFOR took nothing)
+                    if (tr.sk) atomicOr(&s_hmask[w0 >> 5], 1u << (w0 & 31));
+                }
+                if (w1 > w0 + hdr) atomicOr(&s_wflag[(w0 + hdr) >> 5], 1u << ((w0 + hdr) & 31));
+                else if (n > 0) ok = false;
+            }
+        }
+        // ---- this thread's 4 words
+        const int q0 = 4 * tid;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (q0 < wspan) q = *reinterpret_cast<const uint4 *>(wp + q0);
+        uint32_t pw = __shfl_up_sync(kFull, q.w, 1);
+        if (lane == 0) pw = (tid > 0 && q0 < wspan) ? wp[q0 - 1] : 0u;
+        __syncthreads(); // the bitmaps are in place
+        const uint32_t fl = (s_wflag[q0 >> 5] >> (q0 & 31)) & 15u, hm = (s_hmask[q0 >> 5] >> (q0 & 31)) & 15u;
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool in = q0 + k >= aw && q0 + k < wspan && !((hm >> k) & 1u);
+            w[k] = in ? __byte_perm(w[k], 0, sel) : 0u;
+            cnt += __popc(w[k] & 0x80808080u);
+        }
+        uint32_t tot;
+        const int V0 = (int)vf_block_scan((uint32_t)cnt, s_scan, &tot);
+        s_cp[tid] = V0;
+        if (tid == 0) s_cp[VF_THREADS] = (int)tot;
+        // ---- the 16-byte walk (VariableByte.java:115-138): v += (c & 127) << shift; a set bit 7 ends the value
+        {
+            uint32_t acc = 0;
+            int sh = 0;
+            if (!(fl & 1u) && q0 > aw && q0 < wspan) { // bytes of a value that began in the previous word
+                const bool pin = !((s_hmask[(q0 - 1) >> 5] >> ((q0 - 1) & 31)) & 1u);
+                const uint32_t pv = pin ? __byte_perm(pw, 0, sel) : 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t by = (pv >> (8 * e)) & 255u;
+                    if (by & 128u) { acc = 0; sh = 0; }
+                    else { acc += (by & 127u) << (sh & 31); sh += 7; }
+                }
+                // (if the previous word is itself a list's first payload word, only its own bytes count: exactly what was walked)
+            }
+            uint32_t *o = s_val + ao + V0;
+            if ((int)tot <= VF_VCAP - 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((fl >> k) & 1u) { acc = 0; sh = 0; }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t by = (w[k] >> (8 * e)) & 255u;
+                        acc += (by & 127u) << (sh & 31);
+                        if (by & 128u) { *o++ = acc; acc = 0; sh = 0; }
+                        else sh += 7;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- every list must hold exactly its n values: values ending before its first word = values before it
+        if (tid <= nl) {
+            const int wpos = tid < nl ? s_wrel[tid] : wspan;
+            int c = s_cp[(wpos >> 2) < VF_THREADS ? (wpos >> 2) : VF_THREADS];
+            if ((wpos >> 2) < VF_THREADS)
+                for (int k = 0; k < (wpos & 3); ++k) {
+                    const int p = (wpos & ~3) + k;
+                    const bool in = p >= aw && p < wspan && !((s_hmask[p >> 5] >> (p & 31)) & 1u);
+                    if (in) c += __popc(wp[p] & 0x80808080u); // (terminator bits are where they are in either byte order)
+                }
+            if (c != s_vrel[tid]) ok = false;
+        }
+        if ((int)tot != (int)nvals) ok = false;
+        const int fail = __syncthreads_or(!ok);
+        if (fail) { if (tid == 0) atomicMax(a.err, 5); continue; }
+        // ---- values leave, 8 per thread, aligned like the output; Delta.inverseDelta = flat sums minus the sum at the list's start
+        uint32_t *gout = a.out + ob - ao;
+        const int vspan = ao + (int)nvals;
+        uint32_t carry = 0; // flat sum of the passes before this one
+        for (int p0 = 0; p0 < vspan; p0 += VF_THREADS * 8) {
+            const int v0 = p0 + 8 * tid;
+            uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (v0 < vspan) {
+                const uint4 u0 = *reinterpret_cast<const uint4 *>(s_val + v0), u1 = *reinterpret_cast<const uint4 *>(s_val + v0 + 4);
+                x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
+            }
+            uint32_t vm = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) vm |= (uint32_t)(v0 + k >= ao && v0 + k < vspan) << k;
+            if (a.delta) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { x[k] = ((vm >> k) & 1u) ? x[k] : 0u; sum += x[k]; x[k] = sum; } // inclusive within the thread
+                uint32_t ptot;
+                __syncthreads(); // s_scan / s_ss of the previous pass have been read
+                const uint32_t ex = vf_block_scan(sum, s_scan, &ptot) + carry;
+                // list of the first valid position: the LAST list starting at or before it
+                int lid = 0;
+                if (vm) {
+                    const int pos = v0 + (__ffs(vm) - 1) - ao;
+                    int lo = 0, hi = nl; // s_vrel[lo] <= pos < s_vrel[hi]
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_vrel[mid] <= pos) lo = mid; else hi = mid; }
+                    lid = lo;
+                }
+                // starts inside this thread's positions publish the flat sum before them
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if ((vm >> k) & 1u) {
+                        const int pos = v0 + k - ao;
+                        int l = lid;
+                        while (l + 1 < nl && s_vrel[l + 1] <= pos) ++l;
+                        if (s_vrel[l] == pos) s_ss[l] = ex + (k ? x[k - 1] : 0u);
+                        lid = l;
+                    }
+                }
+                __syncthreads();
+                if (vm) {
+                    const int pos = v0 + (__ffs(vm) - 1) - ao;
+                    int lo = 0, hi = nl;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_vrel[mid] <= pos) lo = mid; else hi = mid; }
+                    int l = lo;
+                    uint32_t ss = s_ss[l];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if ((vm >> k) & 1u) {
+                            const int pos2 = v0 + k - ao;
+                            if (l + 1 < nl && s_vrel[l + 1] <= pos2) { while (l + 1 < nl && s_vrel[l + 1] <= pos2) ++l; ss = s_ss[l]; }
+                            x[k] = ex + x[k] - ss;
+                        }
+                    }
+                }
+                carry += ptot;
+            }
+            if (vm == 0xffu) {
+                *reinterpret_cast<uint4 *>(gout + v0) = make_uint4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<uint4 *>(gout + v0 + 4) = make_uint4(x[4], x[5], x[6], x[7]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((vm >> k) & 1u) gout[v0 + k] = x[k];
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
 // block, then a second sweep.  Sizes here are "number of lists": bookkeeping, not hot.
@@ -2388,6 +2985,15 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     return (int)g;
 }
 
+// lists per tile of the flat VariableByte kernels: `target` values per tile on average (the tile's window holds
+// VF_SPAN values / VF_WSPAN words; a tile that overflows is done by the warp-per-list routines inside the kernel)
+static int vbf_lists_per_tile(int64_t total_vals, int64_t nlists, double target)
+{
+    const double avg = nlists > 0 ? (double)total_vals / (double)nlists : 1.0;
+    int64_t g = (int64_t)(target / (avg > 1.0 ? avg : 1.0));
+    return (int)(g < 1 ? 1 : (g > VF_MAXL ? VF_MAXL : g));
+}
+
 // the batched (thread-per-block) kernels: BinaryPacking family and FastPFOR / FastPFOR128
 static bool batched_applicable(int codec, bool delta, int64_t total_vals, int64_t nlists)
 {
@@ -2457,7 +3063,10 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     // pass 0: thread-per-list kernel (short lists); pass 1: thread-per-block kernels
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1 && !batched) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; }
-        a.lists_per_batch = pass == 0 ? 32 : fast_lists_per_batch(a.codec, total_vals, nlists);
+        // lists that are all VariableByte (FastPFOR / FastPFOR128 below one block, VariableByte alone) take the flat kernel
+        const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.8 * VF_SPAN) : 32)
+                                      : fast_lists_per_batch(a.codec, total_vals, nlists);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
         // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
@@ -2472,7 +3081,16 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         {
             KScope ks(ctx, MCP_K_ENCODE);
             const CodecTraits tr = codec_traits(a.codec);
-            if (pass == 0) {
+            if (pass == 0 && flat) {
+                int per_sm = 0;
+                MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vbf_encode, VF_THREADS, 0));
+                if (per_sm < 1) return fail(ctx, MCP_E_CUDA, "k_vbf_encode does not fit an SM");
+                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * per_sm; // every CTA resident: see the kernel's ticket scheme
+                const unsigned grid = (unsigned)(a.nbatches < res ? a.nbatches : res);
+                const unsigned long long first_ticket = 3ull * grid;
+                MCP_CUDA(ctx, cudaMemcpyAsync(a.ticket, &first_ticket, sizeof first_ticket, cudaMemcpyHostToDevice, ctx->stream));
+                k_vbf_encode<<<grid, VF_THREADS, 0, ctx->stream>>>(a);
+            } else if (pass == 0) {
                 const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
                 k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);
             } else if (!tr.fastpfor) k_bp_encode_fast<<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
@@ -2518,12 +3136,17 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1 && !batched) return MCP_E_UNSUPPORTED;
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
-        a.lists_per_batch = pass == 0 ? 32 : fast_lists_per_batch(a.codec, total_out_vals, nlists);
+        const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 2000.0) : 32)
+                                      : fast_lists_per_batch(a.codec, total_out_vals, nlists);
         const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         {
             KScope ks(ctx, MCP_K_DECODE);
             const CodecTraits tr = codec_traits(a.codec);
-            if (pass == 0) {
+            if (pass == 0 && flat) {
+                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * 4;
+                k_vbf_decode<<<(unsigned)(nbatches < res ? nbatches : res), VF_THREADS, 0, ctx->stream>>>(a, nbatches);
+            } else if (pass == 0) {
                 const int64_t res = (int64_t)ctx->prop.multiProcessorCount * SL_DCTAS;
                 k_sl_decode<<<(unsigned)(nbatches < res ? nbatches : res), 32, 0, ctx->stream>>>(a, nbatches);
             } else if (!tr.fastpfor) k_bp_decode_fast<<<(unsigned)nbatches, FE_THREADS, 0, ctx->stream>>>(a);
@@ -2539,7 +3162,11 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
             return MCP_E_UNSUPPORTED;
         }
         if (pass == 0) ++ctx->shortListCalls;
-        if (flag != 0) return fail(ctx, MCP_E_FORMAT, "decode: malformed compressed stream");
+        if (flag != 0) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "decode: malformed compressed stream (kernel pass %d, check %d)", pass, flag);
+            return fail(ctx, MCP_E_FORMAT, msg);
+        }
         return MCP_OK;
     }
     return MCP_E_UNSUPPORTED;

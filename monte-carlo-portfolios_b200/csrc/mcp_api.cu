@@ -165,6 +165,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "fused_moments")) ctx->fusedMoments = value != 0;
     else if (!strcmp(key, "optimistic")) ctx->optimistic = value != 0;
     else if (!strcmp(key, "fast_codec")) ctx->fastCodec = value != 0;
+    else if (!strcmp(key, "flat_codec")) ctx->flatCodec = value != 0;
     else if (!strcmp(key, "short_list_codec")) ctx->shortListCodec = (int)(value < 0 ? 0 : value > 2 ? 2 : value);
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;

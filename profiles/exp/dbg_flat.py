@@ -1,0 +1,17 @@
+import sys, os
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import numpy as np, cases, mcp_b200
+from mcp_b200 import native as N
+from oracle import cref
+ctx = mcp_b200.Context(0)
+ctx.set_option("short_list_codec", 2)
+rng = np.random.default_rng(11)
+vals, off = cases.breach_like_lists(rng, 3000, 10000, 0.01)
+for cid in (N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB, N.CODEC_SK_FASTPFOR256_VB|N.FLAG_DELTA):
+    for fr in (N.FRAME_APP, N.FRAME_WORDS):
+        out_off, out = ctx.codec_encode(cid, fr, vals, off)
+        try:
+            back = ctx.codec_decode(cid, fr, out, out_off, off)
+            print(hex(cid), fr, 'ok', np.array_equal(back, vals), ctx.codec_stats())
+        except Exception as e:
+            print(hex(cid), fr, 'FAIL', e)
