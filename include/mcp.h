@@ -73,7 +73,11 @@ enum {
                                         (n, then the headless stream: FastPFOR pages without their count word, VariableByte tail)
                                         IntCompressor.java:27-61, SkippableComposition.java:37-54, FastPFOR.java:92-105,222-231 */
     MCP_CODEC_SK_FASTPFOR128_VB = 8, /* the same over new FastPFOR128()                          FastPFOR128.java:33      */
-    MCP_CODEC_COUNT          = 9,
+    MCP_CODEC_XOR128_IVB     = 9, /* new IntegratedComposition(new XorBinaryPacking(), new IntegratedVariableByte())
+                                     differential/XorBinaryPacking.java:26-139 (128-value blocks, XOR with the predecessor) */
+    MCP_CODEC_OPTPFD_VB      = 10, /* new Composition(new OptPFD(), new VariableByte())        OptPFD.java:35-200, S16.java
+                                      (128-value blocks, Simple16-coded exceptions; 9 and 10 run in the warp-per-list kernels) */
+    MCP_CODEC_COUNT          = 11,
     MCP_CODEC_MASK           = 0xff,
     MCP_FLAG_DELTA           = 0x100 /* Delta.delta(int[]) before compress, inverse after uncompress (Delta.java:24-28,84-88) */
 };

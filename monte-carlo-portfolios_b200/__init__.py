@@ -6,10 +6,10 @@ path.  Import as `import mcp_b200` (see /mcp_b200.py).
 """
 from . import _native as native
 from ._native import (CODEC_BP32_VB, CODEC_FASTPFOR128_VB, CODEC_FASTPFOR256_VB, CODEC_IBP32_IVB, CODEC_SK_BP32_VB,
-                      CODEC_SK_FASTPFOR128_VB, CODEC_SK_FASTPFOR256_VB, CODEC_SK_IBP32_IVB, CODEC_VB, FLAG_DELTA, FRAME_APP, FRAME_WORDS, CapacityError, McpError, build)
+                      CODEC_SK_FASTPFOR128_VB, CODEC_SK_FASTPFOR256_VB, CODEC_SK_IBP32_IVB, CODEC_VB, CODEC_XOR128_IVB, CODEC_OPTPFD_VB, FLAG_DELTA, FRAME_APP, FRAME_WORDS, CapacityError, McpError, build)
 from .codec import (BinaryPacking, Composition, FastPFOR, FastPFOR128, IntCompressor, IntegerCODEC, IntegratedBinaryPacking,
                     IntegratedComposition, IntegratedIntCompressor, IntegratedVariableByte, IntegratedVariableByteCodec, IntWrapper,
-                    SkippableComposition,
+                    OptPFD, SkippableComposition, XorBinaryPacking,
                     VariableByte,
                     VariableByteCodec, default_context)
 from .engine import Context

@@ -18,8 +18,8 @@ MCP_OK, MCP_E_ARG, MCP_E_CAP, MCP_E_CUDA, MCP_E_NOMEM, MCP_E_FORMAT, MCP_E_STATE
     0, -1, -2, -3, -4, -5, -6, -7, -8)
 
 (CODEC_BP32_VB, CODEC_FASTPFOR256_VB, CODEC_FASTPFOR128_VB, CODEC_IBP32_IVB, CODEC_SK_IBP32_IVB, CODEC_VB, CODEC_SK_BP32_VB,
- CODEC_SK_FASTPFOR256_VB, CODEC_SK_FASTPFOR128_VB) = range(9)
-CODEC_COUNT = 9
+ CODEC_SK_FASTPFOR256_VB, CODEC_SK_FASTPFOR128_VB, CODEC_XOR128_IVB, CODEC_OPTPFD_VB) = range(11)
+CODEC_COUNT = 11
 FLAG_DELTA = 0x100
 FRAME_WORDS, FRAME_APP = 0, 1
 K_VALUE, K_SELECT, K_ENCODE, K_DECODE, K_SCAN, K_GEN, K_MOMENTS, K_COMM, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8

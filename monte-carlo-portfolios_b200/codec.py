@@ -82,6 +82,16 @@ class IntegratedBinaryPacking(_Stage):
     name = "IntegratedBinaryPacking"
 
 
+class XorBinaryPacking(_Stage):
+    """differential/XorBinaryPacking.java:26 (an IntegratedIntegerCODEC: use it inside IntegratedComposition)."""
+    name = "XorBinaryPacking"
+
+
+class OptPFD(_Stage):
+    """OptPFD.java:35."""
+    name = "OptPFD"
+
+
 class IntegratedVariableByte(_Stage):
     name = "IntegratedVariableByte"
 
@@ -126,6 +136,11 @@ _COMPOSITIONS = {
     ("BinaryPacking", "VariableByte"): N.CODEC_BP32_VB,
     ("FastPFOR", "VariableByte"): N.CODEC_FASTPFOR256_VB,
     ("FastPFOR128", "VariableByte"): N.CODEC_FASTPFOR128_VB,
+    ("OptPFD", "VariableByte"): N.CODEC_OPTPFD_VB,
+}
+_INTEGRATED_COMPOSITIONS = {
+    ("IntegratedBinaryPacking", "IntegratedVariableByte"): N.CODEC_IBP32_IVB,
+    ("XorBinaryPacking", "IntegratedVariableByte"): N.CODEC_XOR128_IVB,
 }
 
 
@@ -143,9 +158,10 @@ class IntegratedComposition(IntegerCODEC):
     """differential/IntegratedComposition.java:41-66."""
 
     def __init__(self, f1: _Stage, f2: _Stage, ctx: Context | None = None):
-        if (f1.name, f2.name) != ("IntegratedBinaryPacking", "IntegratedVariableByte"):
+        key = (f1.name, f2.name)
+        if key not in _INTEGRATED_COMPOSITIONS:
             raise NotImplementedError(f"no sm_100a kernel for IntegratedComposition({f1}, {f2})")
-        super().__init__(N.CODEC_IBP32_IVB, ctx, f"{f1} + {f2}")
+        super().__init__(_INTEGRATED_COMPOSITIONS[key], ctx, f"{f1} + {f2}")
 
 
 class VariableByteCodec(IntegerCODEC):

@@ -25,11 +25,13 @@ struct CodecTraits {
     bool integrated; // differential coding inside the codec
     bool sk;         // "skippable" framing: word 0 = n, no Composition marker
     bool chain_tail; // VByte tail continues the delta chain (Skippable) vs restarts at 0
+    bool xorbp;      // XorBinaryPacking first stage (128-value blocks, XOR with the predecessor)
+    bool optpfd;     // OptPFD first stage (128-value blocks, S16-coded exceptions)
 };
 
 __host__ __device__ inline CodecTraits codec_traits(int codec)
 {
-    CodecTraits t{false, 0, false, false, false, false};
+    CodecTraits t{false, 0, false, false, false, false, false, false};
     switch (codec) {
     case MCP_CODEC_BP32_VB: t.blocks = true; break;
     case MCP_CODEC_FASTPFOR256_VB: t.fastpfor = true; t.fp_block = 256; break;
@@ -40,6 +42,9 @@ __host__ __device__ inline CodecTraits codec_traits(int codec)
     case MCP_CODEC_SK_BP32_VB: t.blocks = true; t.sk = true; break;
     case MCP_CODEC_SK_FASTPFOR256_VB: t.fastpfor = true; t.fp_block = 256; t.sk = true; break;
     case MCP_CODEC_SK_FASTPFOR128_VB: t.fastpfor = true; t.fp_block = 128; t.sk = true; break;
+    // the two below run in the warp-per-list kernels only (`blocks` / `fastpfor` stay false: no batched kernel takes them)
+    case MCP_CODEC_XOR128_IVB: t.xorbp = true; t.integrated = true; break;
+    case MCP_CODEC_OPTPFD_VB: t.optpfd = true; break;
     }
     return t;
 }
@@ -53,6 +58,8 @@ int64_t codec_max_words(int codec, int64_t n)
     int64_t w = n + n / 16 + (n / kFpPage + 1) * 80 + 400;
     // VariableByte alone spends up to 5 bytes on every int (values >= 2^28: negative ints, wrapped deltas)
     if ((codec & MCP_CODEC_MASK) == MCP_CODEC_VB) w = std::max<int64_t>(w, (5 * n + 3) / 4 + 2);
+    // OptPFD: a block may spend up to 4 x 20 + 2 x 127 S16 words + its header where BinaryPacking spends 4 x 32 + 1
+    if ((codec & MCP_CODEC_MASK) == MCP_CODEC_OPTPFD_VB) w += 2 * n + 2 * (n / 128);
     return w;
 }
 
@@ -243,6 +250,268 @@ __device__ __forceinline__ bool warp_bp_list_decode(const CodecTraits tr, const 
         warp_inverse_delta(out, n, lane);
     }
     return true;
+}
+
+// ------------------------------------------------------------ XorBinaryPacking
+// differential/XorBinaryPacking.java:31-71: blocks of 128 values; one header word (four widths), then four sub-blocks of
+// 32, every value XOR-ed with its predecessor (the list's first one with 0), packed without masking at the width of the
+// sub-block's OR.  Returns words produced.
+template <bool WRITE>
+__device__ __forceinline__ int64_t warp_xor128_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, int lane)
+{
+    const int64_t pos0 = pos;
+    for (int64_t s = 0; s < m; s += 128) {
+        uint32_t d[4];
+        int b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t base = s + 32 * j;
+            const uint32_t raw = x(base + lane);
+            uint32_t prev = __shfl_up_sync(kFull, raw, 1);
+            if (lane == 0) prev = base > 0 ? x(base - 1) : 0u;
+            d[j] = raw ^ prev;
+            b[j] = bits32(__reduce_or_sync(kFull, d[j]));
+        }
+        if (WRITE && lane == 0)
+            sink.put(pos, ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | (uint32_t)b[3]);
+        ++pos;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (WRITE) {
+                const uint32_t w = warp_pack_word(d[j], b[j], lane);
+                if (lane < b[j]) sink.put(pos + lane, w);
+            }
+            pos += b[j];
+        }
+    }
+    return pos - pos0;
+}
+
+// XorBinaryPacking.java:73-111.  Returns words consumed, -1 on a malformed width; `carry` = the last value decoded.
+__device__ __forceinline__ int64_t warp_xor128_decode(const WordSrc &src, int64_t p, int64_t avail, int64_t m, uint32_t *out,
+                                                      uint32_t &carry, int lane)
+{
+    const int64_t p0 = p;
+    for (int64_t s = 0; s < m; s += 128) {
+        if (p >= avail) return -1;
+        const uint32_t h = src.get(p++);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = (int)((h >> (24 - 8 * j)) & 255u);
+            if (b > 32 || p + b > avail) return -1;
+            const uint32_t word = (lane < b) ? src.get(p + lane) : 0u;
+            uint32_t v = warp_unpack_val(word, b, lane);
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { // inclusive XOR scan: value i = x_0 ^ ... ^ x_i ^ carry
+                const uint32_t t = __shfl_up_sync(kFull, v, dd);
+                if (lane >= dd) v ^= t;
+            }
+            v ^= carry;
+            out[s + 32 * j + lane] = v;
+            carry = __shfl_sync(kFull, v, 31);
+            p += b;
+        }
+    }
+    return p - p0;
+}
+
+// ------------------------------------------------------------------ OptPFD
+// OptPFD.java:35-200 with S16.java (Simple16 as adapted for the PFD codecs).  Blocks of 128 values: one header word
+// b | c << 8 | s << 16 (b = INDEX into kOptBits, c = exceptions, s = S16 words), the S16-coded exceptions (the c high
+// parts in block order, then their c positions), four fastpack groups at kOptBits[b] bits.
+__device__ __constant__ int kOptBits[17] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 20, 32};
+__device__ __constant__ int kOptInvBits[33] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 14, 14, 15, 15, 15, 15, 16, 16, 16, 16, 16, 16,
+                                               16, 16, 16, 16, 16, 16};
+__device__ __constant__ int kS16Num[16] = {28, 21, 21, 21, 14, 9, 8, 7, 6, 6, 5, 5, 4, 3, 2, 1};
+__device__ __constant__ unsigned char kS16Bits[16][28] = {
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+    {2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+    {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1},
+    {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2},
+    {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2},
+    {4, 3, 3, 3, 3, 3, 3, 3, 3}, {3, 4, 4, 4, 4, 3, 3, 3}, {4, 4, 4, 4, 4, 4, 4}, {5, 5, 5, 5, 4, 4}, {4, 4, 5, 5, 5, 5},
+    {6, 6, 6, 5, 5}, {5, 5, 6, 6, 6}, {7, 7, 7, 7}, {10, 9, 9}, {14, 14}, {28}};
+
+// The exception sequence of a block at width `w` without materialising it: entry e < c is the e-th exception's high part
+// (block order), entry c + e its position.  `blk` = the block's 128 values (shared memory), `mask` = exception bits.
+struct OptSeq {
+    const uint32_t *blk;
+    uint32_t mask[4];
+    int c, w;
+    __device__ __forceinline__ int position(int e) const
+    {
+        int wi = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int cnt = __popc(mask[wi]);
+            if (e >= cnt && wi == q) { e -= cnt; ++wi; }
+        }
+        return 32 * wi + (int)__fns(mask[wi], 0, e + 1);
+    }
+    __device__ __forceinline__ int32_t operator()(int e) const // as a Java int (S16 compares signed)
+    {
+        if (e >= c) return position(e - c);
+        return (int32_t)(blk[position(e)] >> (w & 31));
+    }
+};
+
+// S16.compressblock (S16.java:80-100): the first of the 16 layouts that holds the next min(num, n) entries; returns
+// how many it took (0 = "Too big a number": cannot happen, high parts are < 2^28) and the word
+__device__ __forceinline__ int s16_block(const OptSeq &q, int first, int n, uint32_t *word)
+{
+    for (int idx = 0; idx < 16; ++idx) {
+        uint32_t wv = (uint32_t)idx << 28;
+        const int num = kS16Num[idx] < n ? kS16Num[idx] : n;
+        int j = 0, bits = 0;
+        while (j < num) {
+            const int32_t v = q(first + j);
+            const int bw = kS16Bits[idx][j];
+            if (!(v < (int32_t)(1u << bw))) break;
+            wv |= (uint32_t)v << bits;
+            bits += bw;
+            ++j;
+        }
+        if (j == num) { *word = wv; return num; }
+    }
+    *word = 0;
+    return 0;
+}
+
+// words S16.compress spends on the block's exception sequence (S16.estimatecompress, S16.java:57-72)
+__device__ __forceinline__ int s16_words(const OptSeq &q)
+{
+    int pos = 0, words = 0;
+    const int n = 2 * q.c;
+    while (pos < n) {
+        uint32_t w;
+        const int took = s16_block(q, pos, n - pos, &w);
+        if (took <= 0) return 1 << 20;
+        pos += took;
+        ++words;
+    }
+    return words;
+}
+
+// exception bits of the staged block at width w (all lanes compute the same four words)
+__device__ __forceinline__ void opt_mask(const uint32_t (&v)[4], int w, uint32_t (&mask)[4])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mask[j] = __ballot_sync(kFull, w < 32 && (v[j] >> (w & 31)) != 0u);
+}
+
+template <bool WRITE>
+__device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, uint32_t *blk /* 128 words */, int lane)
+{
+    const int64_t pos0 = pos;
+    for (int64_t s = 0; s < m; s += 128) {
+        uint32_t v[4];
+        uint32_t orv = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = x(s + 32 * j + lane); blk[32 * j + lane] = v[j]; orv |= v[j]; }
+        __syncwarp();
+        // ---- getBestBFromData (OptPFD.java:61-98): lane i - mini prices candidate i; `mini` is computed from bit WIDTHS but
+        // used as the first INDEX, as the reference does; ties go to the later candidate (<=)
+        const int mb = bits32(__reduce_or_sync(kFull, orv));
+        int mini = 0;
+        if (mini + 28 < kOptBits[kOptInvBits[mb]]) mini = kOptBits[kOptInvBits[mb]] - 28;
+        const int cand = mini + lane;
+        unsigned key = 0xffffffffu; // (cost << 5) | (31 - candidate): the minimum is the cheapest, latest candidate
+        {
+            // every lane needs the exception bits of ITS candidate: 16 rounds of ballots, round r serves candidate mini + r
+            OptSeq q{blk, {0, 0, 0, 0}, 0, 0};
+            for (int r = 0; mini + r < 16; ++r) {
+                uint32_t mk[4];
+                opt_mask(v, kOptBits[mini + r], mk);
+                if (lane == r) { q.mask[0] = mk[0]; q.mask[1] = mk[1]; q.mask[2] = mk[2]; q.mask[3] = mk[3]; }
+            }
+            if (cand < 16) {
+                q.w = kOptBits[cand];
+                q.c = __popc(q.mask[0]) + __popc(q.mask[1]) + __popc(q.mask[2]) + __popc(q.mask[3]);
+                if (q.c < 128) {
+                    const int cost = 4 * q.w + s16_words(q);
+                    if (cost <= 4 * 32) key = ((unsigned)cost << 5) | (unsigned)(31 - cand);
+                }
+            }
+        }
+        key = __reduce_min_sync(kFull, key);
+        const int b = key == 0xffffffffu ? 16 : 31 - (int)(key & 31u);
+        const int w = kOptBits[b];
+        OptSeq q{blk, {0, 0, 0, 0}, 0, w};
+        if (b < 16) {
+            opt_mask(v, w, q.mask);
+            q.c = __popc(q.mask[0]) + __popc(q.mask[1]) + __popc(q.mask[2]) + __popc(q.mask[3]);
+        }
+        // ---- header, S16 words (serial by nature: one lane), packed groups (fastpack masks to w bits)
+        int sw = 0;
+        if (lane == 0 && q.c > 0) {
+            int at = 0;
+            const int n = 2 * q.c;
+            while (at < n) {
+                uint32_t word;
+                const int took = s16_block(q, at, n - at, &word);
+                if (took <= 0) break;
+                if (WRITE) sink.put(pos + 1 + sw, word);
+                at += took;
+                ++sw;
+            }
+        }
+        sw = __shfl_sync(kFull, sw, 0);
+        if (WRITE && lane == 0) sink.put(pos, (uint32_t)b | ((uint32_t)q.c << 8) | ((uint32_t)sw << 16));
+        pos += 1 + sw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (WRITE) {
+                const uint32_t word = warp_pack_word(w >= 32 ? v[j] : (v[j] & ((1u << w) - 1u)), w, lane);
+                if (lane < w) sink.put(pos + lane, word);
+            }
+            pos += w;
+        }
+        __syncwarp(); // the staged block has been read: the next one may overwrite it
+    }
+    return pos - pos0;
+}
+
+// OptPFD.java:136-160 (decodePage).  `ex` = 2 x 128 + 28 words of shared memory.  Returns words consumed, -1 if malformed.
+__device__ int64_t warp_optpfd_decode(const WordSrc &src, int64_t p, int64_t avail, int64_t m, uint32_t *out, uint32_t *ex, int lane)
+{
+    const int64_t p0 = p;
+    for (int64_t s = 0; s < m; s += 128) {
+        if (p >= avail) return -1;
+        const uint32_t h = src.get(p++);
+        const int b = (int)(h & 255u), c = (int)((h >> 8) & 255u), sw = (int)(h >> 16);
+        if (b > 16 || c > 128 || p + sw > avail) return -1;
+        const int w = kOptBits[b];
+        if (lane == 0) { // S16.uncompress (S16.java:135-147): at most 2c values from sw words
+            int at = 0, left = 2 * c;
+            for (int k = 0; k < sw; ++k) {
+                const uint32_t word = src.get(p + k);
+                const int idx = (int)(word >> 28);
+                const int num = kS16Num[idx] < left ? kS16Num[idx] : left;
+                int bits = 0;
+                for (int j = 0; j < num; ++j) {
+                    const int bw = kS16Bits[idx][j];
+                    ex[at + j] = (word >> bits) & (0xffffffffu >> (32 - bw));
+                    bits += bw;
+                }
+                at += num;
+                left -= num;
+            }
+            ex[2 * 128 + 27] = (uint32_t)left; // values the stream failed to deliver
+        }
+        p += sw;
+        if (p + 4 * (int64_t)w > avail) return -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t word = (lane < w) ? src.get(p + lane) : 0u;
+            out[s + 32 * j + lane] = warp_unpack_val(word, w, lane);
+            p += w;
+        }
+        __syncwarp();
+        if (ex[2 * 128 + 27] != 0u) return -1;
+        for (int k = lane; k < c; k += 32) out[s + (ex[k + c] & 127u)] |= w >= 32 ? 0u : ex[k] << w; // Java: << (w & 31); w = 32 has no exceptions
+        __syncwarp();
+    }
+    return p - p0;
 }
 
 // ------------------------------------------------------------------- FastPFOR
@@ -518,6 +787,7 @@ template <bool WRITE>
 __global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
 {
     __shared__ uint32_t s_stage[kEncWarps][48];
+    __shared__ uint32_t s_blk[kEncWarps][128]; // OptPFD: the block being priced
     __shared__ int s_freq[kEncWarps][34];
     __shared__ int s_cnt[kEncWarps][34];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -572,6 +842,12 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
                     ++pos;
                 }
                 pos += warp_bp32_encode<WRITE>(x, m, tr.integrated, sink, pos, lane);
+            } else if (tr.xorbp || tr.optpfd) {
+                m = n - n % 128; // XorBinaryPacking.java:33 / OptPFD.java:170
+                if (WRITE && lane == 0) sink.put(pos, (uint32_t)m); // F1's count word, or Composition's 0 marker
+                ++pos;
+                if (tr.xorbp) pos += warp_xor128_encode<WRITE>(x, m, sink, pos, lane);
+                else pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, s_blk[wib], lane);
             }
             const int64_t r = n - m;
             if (r > 0) {
@@ -615,6 +891,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_decode(const DecArgs a)
 {
     __shared__ int s_sbase[kEncWarps][34];
     __shared__ int s_spos[kEncWarps][34];
+    __shared__ uint32_t s_ex[kEncWarps][2 * 128 + 28]; // OptPFD: the block's S16-decoded exceptions
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * kEncWarps;
     const CodecTraits tr = codec_traits(a.codec);
@@ -633,16 +910,20 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_decode(const DecArgs a)
         if (ok && n > 0) {
             int64_t m = 0;
             uint32_t carry = 0;
-            if (!tr.sk && (tr.fastpfor || tr.blocks)) {
+            if (!tr.sk && (tr.fastpfor || tr.blocks || tr.xorbp || tr.optpfd)) {
                 ok = p < avail;
                 if (ok) {
                     m = src.get(p++);
-                    const int64_t blk = tr.fastpfor ? tr.fp_block : 32;
+                    const int64_t blk = tr.fastpfor ? tr.fp_block : (tr.blocks ? 32 : 128);
                     ok = (m == n - n % blk);
                 }
             } else if (tr.blocks || tr.fastpfor)
                 m = n - n % (tr.fastpfor ? tr.fp_block : 32);
-            if (ok && m > 0) {
+            if (ok && m > 0 && (tr.xorbp || tr.optpfd)) {
+                const int64_t used = tr.xorbp ? warp_xor128_decode(src, p, avail, m, out, carry, lane)
+                                              : warp_optpfd_decode(src, p, avail, m, out, s_ex[wib], lane);
+                if (used < 0) ok = false; else p += used;
+            } else if (ok && m > 0) {
                 if (tr.fastpfor) {
                     // FastPFOR pages were written as native words; APP framing stores them swapped.
                     // Decode needs byte access to the metadata, so un-swap into the output tail is not
@@ -695,7 +976,18 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_decode_count(const DecArgs a
             if (ok) n = src.get(0);
         } else if (ok && avail > 0) {
             int64_t p = 0, m = 0;
-            if (tr.fastpfor || tr.blocks) {
+            if (tr.xorbp || tr.optpfd) {
+                m = src.get(p++);
+                ok = m >= 0 && m % 128 == 0;
+                for (int64_t s = 0; ok && s < m; s += 128) { // walk the block headers
+                    if (p >= avail) { ok = false; break; }
+                    const uint32_t h = src.get(p);
+                    if (tr.xorbp) p += 1 + (h >> 24) + ((h >> 16) & 255u) + ((h >> 8) & 255u) + (h & 255u);
+                    else if ((h & 255u) > 16u) ok = false;
+                    else p += 1 + (h >> 16) + 4 * kOptBits[h & 255u];
+                }
+                if (p > avail) ok = false;
+            } else if (tr.fastpfor || tr.blocks) {
                 m = src.get(p++);
                 const int64_t blk = tr.fastpfor ? tr.fp_block : 32;
                 ok = m >= 0 && m % blk == 0;
@@ -1806,7 +2098,7 @@ constexpr double SL_MAXAVG = 144.0; // lists averaging more values go to the thr
 __host__ __device__ inline bool sl_codec_ok(int codec, bool delta)
 {
     const CodecTraits t = codec_traits(codec);
-    return !(t.integrated && delta);
+    return !(t.integrated && delta) && !t.xorbp && !t.optpfd; // (XorBinaryPacking / OptPFD: warp-per-list kernels only)
 }
 
 __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc)

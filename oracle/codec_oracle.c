@@ -460,6 +460,178 @@ int64_t orc_fastpfor_uncompress(orc_fastpfor *f, const int32_t *in_, int64_t inl
     return m;
 }
 
+/* --------------------------------------------------------- XorBinaryPacking
+ * differential/XorBinaryPacking.java:31-71 (compress), :73-111 (uncompress), :118-127 (xorMaxBits), :129-139 (xorPack).
+ * Blocks of 128: one header word (bits1<<24 | bits2<<16 | bits3<<8 | bits4), then four sub-blocks of 32 values, each
+ * value XOR-ed with its predecessor (the first one of the list with 0) and packed with fastpackwithoutmask at the
+ * sub-block's width = bits(OR of the XORs).  `ctx_io`: the last value seen (0 at the start). */
+static int64_t xor128_encode(const uint32_t *in, int64_t m, uint32_t *out, uint32_t *ctx_io)
+{
+    int64_t o = 0;
+    uint32_t ctx = *ctx_io;
+    for (int64_t ip = 0; ip < m; ip += 128) {
+        uint32_t work[4][32];
+        int bits[4];
+        for (int q = 0; q < 4; ++q) {
+            uint32_t mask = 0, prev = q == 0 ? ctx : in[ip + 32 * q - 1];
+            for (int i = 0; i < 32; ++i) { work[q][i] = in[ip + 32 * q + i] ^ prev; prev = in[ip + 32 * q + i]; mask |= work[q][i]; }
+            bits[q] = orc_bits(mask);
+        }
+        out[o++] = ((uint32_t)bits[0] << 24) | ((uint32_t)bits[1] << 16) | ((uint32_t)bits[2] << 8) | (uint32_t)bits[3];
+        for (int q = 0; q < 4; ++q) { orc_fastpackwithoutmask(work[q], out + o, bits[q]); o += bits[q]; }
+        ctx = in[ip + 127];
+    }
+    *ctx_io = ctx;
+    return o;
+}
+
+static int64_t xor128_decode(const uint32_t *in, uint32_t *out, int64_t m)
+{
+    int64_t p = 0;
+    uint32_t ctx = 0;
+    for (int64_t op = 0; op < m; op += 128) {
+        const uint32_t h = in[p++];
+        const int bits[4] = { (int)(h >> 24), (int)((h >> 16) & 0xFF), (int)((h >> 8) & 0xFF), (int)(h & 0xFF) };
+        for (int q = 0; q < 4; ++q) {
+            uint32_t work[32];
+            orc_fastunpack(in + p, work, bits[q]);
+            p += bits[q];
+            for (int i = 0; i < 32; ++i) { ctx = work[i] ^ ctx; out[op + 32 * q + i] = ctx; }
+        }
+    }
+    return p;
+}
+
+/* ------------------------------------------------------------------- S16
+ * S16.java (Simple16 as adapted for NewPFD / OptPFD): 16 layouts of up to 28 values in the low 28 bits of a word, the
+ * layout number in the top 4.  compressblock (:80-100) tries the layouts in order and takes the first one whose widths
+ * hold the next min(S16_NUM, n) values; comparisons are on Java ints (signed). */
+static const int S16_NUM[16] = { 28, 21, 21, 21, 14, 9, 8, 7, 6, 6, 5, 5, 4, 3, 2, 1 };
+static const int S16_BITS[16][28] = {
+    { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 },
+    { 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1 },
+    { 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1 },
+    { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2 },
+    { 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2 },
+    { 4, 3, 3, 3, 3, 3, 3, 3, 3 }, { 3, 4, 4, 4, 4, 3, 3, 3 },
+    { 4, 4, 4, 4, 4, 4, 4 }, { 5, 5, 5, 5, 4, 4 },
+    { 4, 4, 5, 5, 5, 5 }, { 6, 6, 6, 5, 5 }, { 5, 5, 6, 6, 6 },
+    { 7, 7, 7, 7 }, { 10, 9, 9 }, { 14, 14 }, { 28 } };
+
+/* one word: returns how many values it took (S16.compressblock / fakecompressblock); -1 = "Too big a number" */
+static int s16_block(const int32_t *in, int n, uint32_t *word)
+{
+    for (int idx = 0; idx < 16; ++idx) {
+        uint32_t w = (uint32_t)idx << 28;
+        const int num = S16_NUM[idx] < n ? S16_NUM[idx] : n;
+        int j = 0, bits = 0;
+        while (j < num && in[j] < (int32_t)(1u << S16_BITS[idx][j])) {
+            w |= (uint32_t)in[j] << bits;
+            bits += S16_BITS[idx][j];
+            ++j;
+        }
+        if (j == num) { if (word) *word = w; return num; }
+    }
+    return -1;
+}
+
+/* S16.compress (:30-44) / estimatecompress (:57-72): words written (out may be NULL to only count) */
+static int s16_compress(const int32_t *in, int n, uint32_t *out)
+{
+    int pos = 0, words = 0;
+    while (pos < n) {
+        const int took = s16_block(in + pos, n - pos, out ? out + words : NULL);
+        if (took < 0) return -1;
+        pos += took;
+        ++words;
+    }
+    return words;
+}
+
+/* S16.uncompress (:135-147) over `nwords` words, at most `n` values */
+static void s16_uncompress(const uint32_t *in, int nwords, int32_t *out, int n)
+{
+    int pos = 0;
+    for (int w = 0; w < nwords; ++w) {
+        const int idx = (int)(in[w] >> 28);
+        const int num = S16_NUM[idx] < n ? S16_NUM[idx] : n;
+        int bits = 0;
+        for (int j = 0; j < num; ++j) {
+            out[pos + j] = (int32_t)((in[w] >> bits) & (0xffffffffu >> (32 - S16_BITS[idx][j])));
+            bits += S16_BITS[idx][j];
+        }
+        n -= num;
+        pos += num;
+    }
+}
+
+/* ----------------------------------------------------------------- OptPFD
+ * OptPFD.java:35-200.  Blocks of 128; per block one header word b | c << 8 | s << 16 (b = INDEX into `bits`, c =
+ * exceptions, s = S16 words), the S16-coded exceptions (c high parts, then c positions), then 4 x fastpack at bits[b].
+ * getBestBFromData (:61-98) as written: `mini` is computed from BIT WIDTHS (bits[invbits[mb]] - 28) but used as the first
+ * INDEX of the search; the cost of a candidate is 4 bits[i] + S16 words against a start of 4 * 32; ties go to the later
+ * candidate (<=). */
+static const int OPT_BITS[17] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 20, 32 };
+static const int OPT_INVBITS[33] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 14, 14, 15, 15, 15, 15, 16, 16, 16, 16, 16, 16, 16, 16,
+                                     16, 16, 16, 16 };
+
+static void optpfd_best(const uint32_t *in, int *bestb, int *bestc)
+{
+    int32_t exbuf[256];
+    const int mb = orc_maxbits(in, 128);
+    int mini = 0;
+    if (mini + 28 < OPT_BITS[OPT_INVBITS[mb]]) mini = OPT_BITS[OPT_INVBITS[mb]] - 28;
+    int besti = 16, bestcost = OPT_BITS[16] * 4, exceptcounter = 0;
+    for (int i = mini; i < 16; ++i) {
+        int tmp = 0;
+        for (int k = 0; k < 128; ++k) tmp += (in[k] >> OPT_BITS[i]) != 0;
+        if (tmp == 128) continue;
+        for (int k = 0, c = 0; k < 128; ++k)
+            if ((in[k] >> OPT_BITS[i]) != 0) { exbuf[tmp + c] = k; exbuf[c] = (int32_t)(in[k] >> OPT_BITS[i]); ++c; }
+        const int thiscost = OPT_BITS[i] * 4 + s16_compress(exbuf, 2 * tmp, NULL);
+        if (thiscost <= bestcost) { bestcost = thiscost; besti = i; exceptcounter = tmp; }
+    }
+    *bestb = besti;
+    *bestc = exceptcounter;
+}
+
+static int64_t optpfd_encode(const uint32_t *in, int64_t m, uint32_t *out)
+{
+    int64_t o = 0;
+    for (int64_t ip = 0; ip < m; ip += 128) {
+        int b, c, s = 0;
+        optpfd_best(in + ip, &b, &c);
+        const int64_t remember = o++;
+        if (c > 0) {
+            int32_t exbuf[256];
+            int cc = 0;
+            for (int i = 0; i < 128; ++i)
+                if ((in[ip + i] >> OPT_BITS[b]) != 0) { exbuf[cc + c] = i; exbuf[cc] = (int32_t)(in[ip + i] >> OPT_BITS[b]); ++cc; }
+            s = s16_compress(exbuf, 2 * c, out + o);
+            o += s;
+        }
+        out[remember] = (uint32_t)b | ((uint32_t)c << 8) | ((uint32_t)s << 16);
+        for (int k = 0; k < 128; k += 32) { orc_fastpack(in + ip + k, out + o, OPT_BITS[b]); o += OPT_BITS[b]; }
+    }
+    return o;
+}
+
+static int64_t optpfd_decode(const uint32_t *in, uint32_t *out, int64_t m)
+{
+    int64_t p = 0;
+    for (int64_t op = 0; op < m; op += 128) {
+        const uint32_t h = in[p++];
+        const int b = (int)(h & 0xFF), c = (int)((h >> 8) & 0xFF), s = (int)(h >> 16);
+        int32_t exbuf[256 + 28];
+        if (b > 16) return -1;
+        s16_uncompress(in + p, s, exbuf, 2 * c);
+        p += s;
+        for (int k = 0; k < 128; k += 32) { orc_fastunpack(in + p, out + op + k, OPT_BITS[b]); p += OPT_BITS[b]; }
+        for (int k = 0; k < c; ++k) out[op + (exbuf[k + c] & 127)] |= (uint32_t)exbuf[k] << (OPT_BITS[b] & 31);
+    }
+    return p;
+}
+
 /* ------------------------------------------------------------ compositions */
 
 int64_t orc_max_compressed_words(int64_t n)
@@ -554,6 +726,24 @@ int64_t orc_compress(int codec_flags, const int32_t *in_, int64_t n, int32_t *ou
     case ORC_CODEC_VB:
         o += vb_encode(in, n, out, 0, NULL);
         break;
+    case ORC_CODEC_XOR128_IVB: {                 /* IntegratedComposition.java:41-55 over XorBinaryPacking.compress (:31-71) */
+        if (n == 0) break;
+        const int64_t m = n - n % 128;
+        uint32_t ctx = 0;
+        if (m > 0) { out[o++] = (uint32_t)m; o += xor128_encode(in, m, out + o, &ctx); }
+        else out[o++] = 0;
+        uint32_t zero = 0;                       /* IntegratedVariableByte.java:40: the tail's gaps restart at 0 */
+        o += vb_encode(in + m, n - m, out + o, 1, &zero);
+        break;
+    }
+    case ORC_CODEC_OPTPFD_VB: {                  /* Composition.java:37-51 over OptPFD.compress (:168-177) */
+        if (n == 0) break;
+        const int64_t m = n / 128 * 128;
+        if (m > 0) { out[o++] = (uint32_t)m; o += optpfd_encode(in, m, out + o); }
+        else out[o++] = 0;
+        o += vb_encode(in + m, n - m, out + o, 0, NULL);
+        break;
+    }
     }
     free(tmp);
     return o;
@@ -637,6 +827,21 @@ int64_t orc_uncompress(int codec_flags, const int32_t *in_, int64_t inlen, int32
         const int64_t r = vb_decode_all(in, inlen, out, out_cap, 0);
         if (r < 0) return -1;
         n = r;
+        break;
+    }
+    case ORC_CODEC_XOR128_IVB:
+    case ORC_CODEC_OPTPFD_VB: {
+        if (inlen == 0) break;
+        const int xr = codec == ORC_CODEC_XOR128_IVB;
+        int64_t m = in[0];                       /* XorBinaryPacking.java:79 / OptPFD.java:184 */
+        m -= m % 128;
+        if (m > out_cap) return -1;
+        const int64_t q = xr ? xor128_decode(in + 1, out, m) : optpfd_decode(in + 1, out, m);
+        if (q < 0) return -1;
+        const int64_t p = 1 + q;
+        const int64_t r = vb_decode_all(in + p, inlen - p, out + m, out_cap - m, xr);
+        if (r < 0) return -1;
+        n = m + r;
         break;
     }
     }

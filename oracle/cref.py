@@ -23,6 +23,8 @@ CODEC_VB = 5
 CODEC_SK_BP32_VB = 6
 CODEC_SK_FASTPFOR256_VB = 7
 CODEC_SK_FASTPFOR128_VB = 8
+CODEC_XOR128_IVB = 9
+CODEC_OPTPFD_VB = 10
 FLAG_DELTA = 0x100
 
 

@@ -43,7 +43,9 @@ enum {
     ORC_CODEC_SK_FASTPFOR256_VB = 7, /* IntCompressor(SkippableComposition(FastPFOR, VariableByte)): n, then the headless stream
                                          IntCompressor.java:38-61, SkippableComposition.java:37-54, FastPFOR.java:92-105 */
     ORC_CODEC_SK_FASTPFOR128_VB = 8, /* the same over FastPFOR128 (FastPFOR128.java:33) */
-    ORC_CODEC_COUNT          = 9,
+    ORC_CODEC_XOR128_IVB     = 9, /* IntegratedComposition(XorBinaryPacking, IntegratedVariableByte)   differential/XorBinaryPacking.java:26-139 */
+    ORC_CODEC_OPTPFD_VB      = 10, /* Composition(OptPFD, VariableByte)                   OptPFD.java:35-200, S16.java */
+    ORC_CODEC_COUNT          = 11,
     ORC_CODEC_MASK           = 0xff,
     ORC_FLAG_DELTA           = 0x100 /* Delta.delta(int[]) before compress / inverseDelta after (Delta.java:24-28,84-88) */
 };

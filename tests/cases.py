@@ -8,8 +8,12 @@ from __future__ import annotations
 
 import numpy as np
 
-ALL_CODECS = list(range(9))
-NAMES = ["BP32_VB", "FASTPFOR256_VB", "FASTPFOR128_VB", "IBP32_IVB", "SK_IBP32_IVB", "VB", "SK_BP32_VB", "SK_FASTPFOR256_VB", "SK_FASTPFOR128_VB"]
+ALL_CODECS = list(range(11))
+NAMES = ["BP32_VB", "FASTPFOR256_VB", "FASTPFOR128_VB", "IBP32_IVB", "SK_IBP32_IVB", "VB", "SK_BP32_VB", "SK_FASTPFOR256_VB", "SK_FASTPFOR128_VB",
+         "XOR128_IVB", "OPTPFD_VB"]
+# codecs the batched / thread-per-list kernels take (XorBinaryPacking and OptPFD run in the warp-per-list kernels only)
+FAST_CODECS = list(range(9))
+FAST_NAMES = NAMES[:9]
 DELTA = 0x100
 
 

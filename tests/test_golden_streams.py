@@ -15,7 +15,7 @@ import cases
 import goldenstreams as G
 from oracle import cref
 
-N_ORACLE_CODECS = 9  # 9 = XorBinaryPacking, 10 = OptPFD: in the fixture, not in the oracle yet
+N_ORACLE_CODECS = 11
 
 
 def test_fixture_covers_every_codec_and_the_multipage_inputs():
