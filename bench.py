@@ -87,6 +87,32 @@ def peaks():
         return None
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off BEFORE any pinned allocation: cudaHostAlloc pages are
+    first-touch, so the rank's pinned buffers then live on the socket whose PCIe root the GPU is on (8 ranks sharing one
+    socket's memory and its UPI link is what stretched e2e from 3.24 to 3.47 ms at N = 8 last round)."""
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                           capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = q[-12:] if len(q) >= 12 else q  # 00000000:1B:00.0 -> 0000:1b:00.0
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= set(os.sched_getaffinity(0))
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:  # containers without sysfs / nvidia-smi: run unbound
+        return {"bound": False, "why": repr(e)[:80]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -252,6 +278,7 @@ class Job:
         import mcp_b200
         from mcp_b200 import native as N
         self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        self.numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False}
         self.N = N
         self.dist = None
         self.torch = None
@@ -612,6 +639,7 @@ def main():
     ap.add_argument("--no-codec", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="only the headline leg (profiling runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check after the timed region")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--codec-lists", type=int, default=1_000_000)
     ap.add_argument("--c3-portfolios", type=int, default=0, help="override the c3 TOTAL portfolio count (smaller smoke runs)")
     ap.add_argument("--c5-portfolios", type=int, default=0, help="override the c5 portfolio count (smaller smoke runs)")
@@ -696,6 +724,7 @@ def main():
                            "tail": head["sizes"]["tail"],
                            "inputs": "Philox4x32-10 Irwin-Hall(12) synthetic E (scale 100) and S (drift 0.05), generated on device, resident in HBM",
                            "sharding": f"portfolio-sharded x{world}, no data-path collective",
+                           "numa": job.numa,
                            "l2": "L2 flushed (256 MiB memset) before every timed step; steps timed individually with CUDA events on the library's stream",
                            "encoded_bytes_per_step": head["sizes"]["enc_bytes"], "fallback_rows": head["fallback_rows"]},
                 "roofline": head["roofline"], "kernel_breakdown": head["kernel_breakdown"], "cpu_baseline": cpu, "e2e": e2e,

@@ -182,6 +182,25 @@ int mcp_codec_decode_dev(mcp_ctx *ctx, int codec_id, int framing,
                          const uint8_t *d_in, const int64_t *d_in_off, int64_t nlists,
                          int32_t *d_out, const int64_t *d_out_off);
 
+/* ------------------------------------------------------------ weights column
+ * The loader's second column: Snappy.compress(double[]) (LoadPortfolios.getCompressedWeights, LoadPortfolios.java:563-595;
+ * Snappy.uncompressDoubleArray, :480,:580) = the RAW SNAPPY FORMAT over the doubles' little-endian bytes, stored if smaller
+ * than 8 n bytes, else big-endian doubles under algo "none" (:270-278; the host-side mirror applies that rule).
+ * snappy-java 1.1.10.4 is an un-vendored dependency of the reference (maprdb-portfolio/pom.xml:50-56): the decoder here
+ * accepts every valid raw-Snappy stream (all four element kinds), so blobs the reference wrote decode; the encoder is a
+ * greedy matcher of this library's own (oracle/weights_oracle.c states it) -- valid Snappy for any Snappy decoder, NOT
+ * snappy-java's byte choices (parity unpinned).  CSR in / CSR out like the integer codecs; list i = weights[list_off[i] ..
+ * list_off[i+1]).  MCP_E_CAP: *out_len holds the size needed.  MCP_E_FORMAT: malformed stream or a length that is not
+ * 8 * (out_off[i+1] - out_off[i]). */
+int64_t mcp_weights_max_bytes(int64_t n);
+int mcp_weights_encode(mcp_ctx *ctx, const double *weights, const int64_t *list_off, int64_t nlists,
+                       int64_t *out_off, uint8_t *out, int64_t cap, int64_t *out_len);
+int mcp_weights_decode(mcp_ctx *ctx, const uint8_t *in, const int64_t *in_off, int64_t nlists,
+                       double *out, const int64_t *out_off);
+/* LoadPortfolios.getCompressedWeights(ArrayList<Double>) -> byte[] / Snappy.uncompressDoubleArray(byte[]) -> double[] */
+int mcp_get_compressed_weights(mcp_ctx *ctx, const double *weights, int32_t n, uint8_t *bytes, int64_t cap, int64_t *nbytes);
+int mcp_get_decompressed_weights(mcp_ctx *ctx, const uint8_t *bytes, int64_t nbytes, int32_t number_of_doubles, double *out);
+
 /* -------------------------------------------------------- risk path: inputs
  * Exposure matrix E: row-major P x F doubles.  Scenario matrix S: row-major N x F
  * doubles, row n = trial n.  (The reference defines neither: portfolios.json holds

@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
         "mcp_codec_headless_uncompress": (C.c_int, [vp, C.c_int, vp, i32, vp, i32, P(i32)]),
         "mcp_get_compressed_instruments": (C.c_int, [vp, C.c_int, vp, i32, vp, i64, P(i64)]),
         "mcp_get_decompressed_instruments": (C.c_int, [vp, C.c_int, vp, i64, i32, vp]),
+        "mcp_weights_max_bytes": (i64, [i64]),
+        "mcp_weights_encode": (C.c_int, [vp, vp, vp, i64, vp, vp, i64, P(i64)]),
+        "mcp_weights_decode": (C.c_int, [vp, vp, vp, i64, vp, vp]),
+        "mcp_get_compressed_weights": (C.c_int, [vp, vp, i32, vp, i64, P(i64)]),
+        "mcp_get_decompressed_weights": (C.c_int, [vp, vp, i64, i32, vp]),
         "mcp_codec_encode": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp, i64, P(i64)]),
         "mcp_codec_decode": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, vp, vp]),
         "mcp_codec_stats": (C.c_int, [vp, P(i64), P(i64)]),

@@ -226,6 +226,11 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
 int exclusive_scan_i64(mcp_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out /* n+1 */);
 int64_t codec_max_words(int codec, int64_t n);
 
+// weights_kernels.cu: the loader's weights column (raw Snappy format over the doubles' bytes)
+int weights_encode_plan(mcp_ctx *ctx, const double *d_w, const int64_t *d_off, int64_t nlists, int64_t *d_out_off, int64_t *total);
+int weights_encode_emit(mcp_ctx *ctx, const double *d_w, const int64_t *d_off, int64_t nlists, const int64_t *d_out_off, uint8_t *d_out);
+int weights_decode_device(mcp_ctx *ctx, const uint8_t *d_in, const int64_t *d_in_off, int64_t nlists, double *d_out, const int64_t *d_out_off);
+
 // risk_kernels.cu
 int risk_run(mcp_ctx *ctx, double alpha, int codec_id, int framing);
 int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V);

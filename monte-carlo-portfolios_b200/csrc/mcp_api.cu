@@ -464,6 +464,79 @@ int mcp_get_decompressed_instruments(mcp_ctx *ctx, int codec_id, const uint8_t *
     return MCP_OK;
 }
 
+// ------------------------------------------------------------ weights column
+int64_t mcp_weights_max_bytes(int64_t n)
+{
+    if (n < 0) return -1;
+    return 32 + 8 * n + (8 * n) / 6; // snappy's MaxCompressedLength over the 8 n bytes
+}
+
+int mcp_weights_encode(mcp_ctx *ctx, const double *weights, const int64_t *list_off, int64_t nlists, int64_t *out_off, uint8_t *out,
+                       int64_t cap, int64_t *out_len)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || !list_off || !out_off || !out_len || cap < 0) return fail(ctx, MCP_E_ARG, "weights encode: bad argument");
+    *out_len = 0;
+    out_off[0] = 0;
+    if (nlists == 0) return MCP_OK;
+    if (list_off[0] != 0) return fail(ctx, MCP_E_ARG, "weights encode: offsets must start at 0");
+    for (int64_t i = 0; i < nlists; ++i)
+        if (list_off[i + 1] < list_off[i]) return fail(ctx, MCP_E_ARG, "weights encode: offsets not monotone");
+    const int64_t n = list_off[nlists];
+    if (n > 0 && !weights) return fail(ctx, MCP_E_ARG, "weights encode: null weights");
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)(n + 2) * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dIo1.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, weights, (size_t)n * sizeof(double)));
+    MCP_TRY(h2d(ctx, ctx->dIo1.p, list_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    int64_t total = 0;
+    MCP_TRY(weights_encode_plan(ctx, ctx->dIo0.as<double>(), ctx->dIo1.as<int64_t>(), nlists, ctx->dIo3.as<int64_t>(), &total));
+    *out_len = total;
+    MCP_TRY(d2h(ctx, out_off, ctx->dIo3.p, (size_t)(nlists + 1) * sizeof(int64_t)));
+    if (total > cap || (total > 0 && !out)) { MCP_TRY(sync(ctx)); return fail(ctx, MCP_E_CAP, "weights encode: output buffer too small"); }
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)total + 16));
+    MCP_TRY(weights_encode_emit(ctx, ctx->dIo0.as<double>(), ctx->dIo1.as<int64_t>(), nlists, ctx->dIo3.as<int64_t>(), ctx->dIo2.as<uint8_t>()));
+    MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)total));
+    return sync(ctx);
+}
+
+int mcp_weights_decode(mcp_ctx *ctx, const uint8_t *in, const int64_t *in_off, int64_t nlists, double *out, const int64_t *out_off)
+{
+    MCP_TRY(set_dev(ctx));
+    if (nlists < 0 || !in_off || !out_off) return fail(ctx, MCP_E_ARG, "weights decode: bad argument");
+    if (nlists == 0) return MCP_OK;
+    if (in_off[0] != 0 || out_off[0] != 0) return fail(ctx, MCP_E_ARG, "weights decode: offsets must start at 0");
+    for (int64_t i = 0; i < nlists; ++i)
+        if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) return fail(ctx, MCP_E_ARG, "weights decode: offsets not monotone");
+    const int64_t in_bytes = in_off[nlists], n = out_off[nlists];
+    if ((in_bytes > 0 && !in) || (n > 0 && !out)) return fail(ctx, MCP_E_ARG, "weights decode: null buffer");
+    MCP_CUDA(ctx, ctx->dIo0.reserve((size_t)in_bytes + 16));
+    MCP_CUDA(ctx, ctx->dIo1.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo3.reserve((size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_CUDA(ctx, ctx->dIo2.reserve((size_t)(n + 2) * sizeof(double)));
+    MCP_TRY(h2d(ctx, ctx->dIo0.p, in, (size_t)in_bytes));
+    MCP_TRY(h2d(ctx, ctx->dIo1.p, in_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(h2d(ctx, ctx->dIo3.p, out_off, (size_t)(nlists + 1) * sizeof(int64_t)));
+    MCP_TRY(weights_decode_device(ctx, ctx->dIo0.as<uint8_t>(), ctx->dIo1.as<int64_t>(), nlists, ctx->dIo2.as<double>(), ctx->dIo3.as<int64_t>()));
+    MCP_TRY(d2h(ctx, out, ctx->dIo2.p, (size_t)n * sizeof(double)));
+    return sync(ctx);
+}
+
+int mcp_get_compressed_weights(mcp_ctx *ctx, const double *weights, int32_t n, uint8_t *bytes, int64_t cap, int64_t *nbytes)
+{
+    if (!ctx || n < 0 || !nbytes) return ctx ? fail(ctx, MCP_E_ARG, "getCompressedWeights: bad argument") : MCP_E_ARG;
+    const int64_t lo[2] = {0, n};
+    int64_t oo[2] = {0, 0};
+    return mcp_weights_encode(ctx, weights, lo, 1, oo, bytes, cap, nbytes);
+}
+
+int mcp_get_decompressed_weights(mcp_ctx *ctx, const uint8_t *bytes, int64_t nbytes, int32_t number_of_doubles, double *out)
+{
+    if (!ctx || number_of_doubles < 0 || nbytes < 0) return ctx ? fail(ctx, MCP_E_ARG, "getDecompressedWeights: bad argument") : MCP_E_ARG;
+    const int64_t io[2] = {0, nbytes}, oo[2] = {0, number_of_doubles};
+    return mcp_weights_decode(ctx, bytes, io, 1, out, oo);
+}
+
 // ------------------------------------------------------------------ risk path
 static int upload_matrix(mcp_ctx *ctx, mcp::DevBuf &buf, const double *h, int64_t rows, int32_t F)
 {

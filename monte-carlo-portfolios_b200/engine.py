@@ -166,6 +166,43 @@ class Context:
                                                              _ptr(out)), "getDecompressedInstruments")
         return out[:number_of_integers]
 
+    # -- weights column (raw Snappy format over the doubles' bytes; include/mcp.h)
+    def get_compressed_weights(self, weights) -> bytes:
+        w = np.ascontiguousarray(weights, np.float64)
+        cap = int(self._L.mcp_weights_max_bytes(w.size))
+        out = np.zeros(cap, np.uint8)
+        n = C.c_int64(0)
+        self._check(self._L.mcp_get_compressed_weights(self._h, _ptr(w), w.size, _ptr(out), cap, C.byref(n)), "getCompressedWeights")
+        return bytes(out[: n.value])
+
+    def get_decompressed_weights(self, blob: bytes, number_of_doubles: int) -> np.ndarray:
+        b = np.frombuffer(blob, np.uint8).copy() if len(blob) else np.zeros(1, np.uint8)
+        out = np.zeros(max(number_of_doubles, 1), np.float64)
+        self._check(self._L.mcp_get_decompressed_weights(self._h, _ptr(b), len(blob), number_of_doubles, _ptr(out)),
+                    "getDecompressedWeights")
+        return out[:number_of_doubles]
+
+    def weights_encode(self, weights, list_off, cap: int | None = None):
+        """Batched: list i = weights[list_off[i] .. list_off[i+1]) -> (byte offsets [nlists + 1], bytes)."""
+        w = np.ascontiguousarray(weights, np.float64)
+        off = np.ascontiguousarray(list_off, np.int64)
+        nl = off.size - 1
+        cap = int(cap if cap is not None else 8 * w.size + (8 * w.size) // 6 + 40 * max(nl, 1))
+        out_off = np.zeros(nl + 1, np.int64)
+        out = np.zeros(max(cap, 1), np.uint8)
+        n = C.c_int64(0)
+        self._check(self._L.mcp_weights_encode(self._h, _ptr(w), _ptr(off), nl, _ptr(out_off), _ptr(out), cap, C.byref(n)), "weights_encode")
+        return out_off, out[: n.value]
+
+    def weights_decode(self, buf, in_off, out_off) -> np.ndarray:
+        b = np.ascontiguousarray(buf, np.uint8)
+        if b.size == 0:
+            b = np.zeros(1, np.uint8)
+        io, oo = np.ascontiguousarray(in_off, np.int64), np.ascontiguousarray(out_off, np.int64)
+        out = np.zeros(max(int(oo[-1]), 1), np.float64)
+        self._check(self._L.mcp_weights_decode(self._h, _ptr(b), _ptr(io), io.size - 1, _ptr(out), _ptr(oo)), "weights_decode")
+        return out[: int(oo[-1])]
+
     # -- risk path
     def upload_exposures(self, E):
         E = np.ascontiguousarray(E, np.float64)

@@ -13,6 +13,7 @@ from . import _native as N
 from .engine import Context
 
 INTEGER_CODEC_NAME = "bpacking+variablebyte"  # LoadPortfolios.java:726
+FLOAT_COMPRESSOR_NAME = "snappy"              # LoadPortfolios.java:723
 
 
 class LoadPortfolios:
@@ -52,18 +53,42 @@ class LoadPortfolios:
             blob, algo = self.integersToBytes(instruments), "none"
         return {"uncompressedIntegerSize": n, "compressed": blob, "compressedByteSize": len(blob), "algo": algo}
 
+    # -- the weights column (LoadPortfolios.java:563-595: Snappy.compress(double[]); raw Snappy format, see include/mcp.h)
+    def getCompressedWeights(self, weights) -> bytes:
+        return self.ctx.get_compressed_weights(weights)
+
+    def getDecompressedWeights(self, compressedWeights: bytes, numberOfDoubles: int) -> np.ndarray:  # Snappy.uncompressDoubleArray
+        return self.ctx.get_decompressed_weights(compressedWeights, numberOfDoubles)
+
+    @staticmethod
+    def doublesToBytes(weights) -> bytes:  # BitManipulationHelper.java:193-208 (the "none" fallback: big-endian IEEE bits)
+        return np.asarray(weights, np.float64).astype(">f8").tobytes()
+
+    def getWeightDocument(self, weights, compressed: bytes | None = None) -> dict:
+        """LoadPortfolios.java:270-278 + 553-561: the Snappy blob iff it is smaller than 8 n bytes, else raw big-endian."""
+        n = len(weights)
+        blob = self.getCompressedWeights(weights) if compressed is None else compressed
+        algo = FLOAT_COMPRESSOR_NAME
+        if not (len(blob) < 8 * n):
+            blob, algo = self.doublesToBytes(weights), "none"
+        return {"uncompressedDoubleSize": n, "compressed": blob, "compressedByteSize": len(blob), "algo": algo}
+
     def documents_from_json(self, path: str) -> list[dict]:
-        """One document per JSON line of a portfolios.json-style file (schema: SURVEY.md A.8), instruments only."""
+        """One document per JSON line of a portfolios.json-style file (schema: SURVEY.md A.8): instruments and weights."""
         rows = [json.loads(line) for line in open(path) if line.strip()]
         lists = [[int(p["instrument"]) for p in r["instruments"]] for r in rows]
         blobs = self.compress_all(lists)
+        wl = [[float(p["weight"]) for p in r["instruments"]] for r in rows]
+        woff = np.zeros(len(wl) + 1, np.int64)
+        np.cumsum([len(x) for x in wl], out=woff[1:])
+        wo, wb = self.ctx.weights_encode(np.concatenate([np.asarray(x, np.float64) for x in wl]) if woff[-1] else np.zeros(0), woff)
         docs = []
-        for r, ins, blob in zip(rows, lists, blobs):
-            w = [float(p["weight"]) for p in r["instruments"]]
+        for i, (r, ins, blob, w) in enumerate(zip(rows, lists, blobs, wl)):
             docs.append({"_id": str(r.get("id", len(docs))),
                          "metadata": {"min_instrument": min(ins), "max_instrument": max(ins),
                                       "min_weight": min(w), "max_weight": max(w)},
-                         "instruments": self.getInstrumentDocument(ins, blob)})
+                         "instruments": self.getInstrumentDocument(ins, blob),
+                         "weights": self.getWeightDocument(w, bytes(wb[wo[i]: wo[i + 1]]))})
         return docs
 
 

@@ -30,7 +30,7 @@ FLAG_DELTA = 0x100
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, a few seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("codec_oracle.c", "risk_oracle.c", "risk_fast.c", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("codec_oracle.c", "risk_oracle.c", "risk_fast.c", "weights_oracle.c", "oracle.h", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _SO
@@ -100,6 +100,12 @@ def lib() -> C.CDLL:
         L.orc_gen_breach_list.restype = C.c_int64
         L.orc_gen_breach_list.argtypes = [i32p, C.c_int64, C.c_int32, C.c_double, C.c_uint64]
         L.orc_num_threads.restype = C.c_int
+        L.orc_snappy_compress.restype = C.c_int64
+        L.orc_snappy_compress.argtypes = [u8p, C.c_int64, u8p]
+        L.orc_snappy_uncompress.restype = C.c_int64
+        L.orc_snappy_uncompress.argtypes = [u8p, C.c_int64, u8p, C.c_int64]
+        L.orc_doubles_to_bytes.restype = None
+        L.orc_doubles_to_bytes.argtypes = [f64p, C.c_int64, u8p]
         _lib = L
     return _lib
 
@@ -326,3 +332,38 @@ def gen_breach_list(list_id: int, N: int, rate: float, seed: int) -> np.ndarray:
     out = np.empty(N, np.int32)
     n = lib().orc_gen_breach_list(_p(out, C.c_int32), list_id, N, rate, seed)
     return out[:n].copy()
+
+
+# -------------------------------------------------------------------- weights
+def snappy_compress(data: bytes) -> bytes:
+    """Raw Snappy stream by the repository's own greedy matcher (weights_oracle.c): valid Snappy, not snappy-java's bytes."""
+    b = np.frombuffer(bytes(data), np.uint8).copy() if len(data) else np.zeros(1, np.uint8)
+    out = np.zeros(32 + len(data) + len(data) // 6, np.uint8)
+    n = lib().orc_snappy_compress(_p(b, C.c_uint8), len(data), _p(out, C.c_uint8))
+    return bytes(out[:n])
+
+
+def snappy_uncompress(blob: bytes, out_cap: int) -> bytes:
+    b = np.frombuffer(bytes(blob), np.uint8).copy() if len(blob) else np.zeros(1, np.uint8)
+    out = np.zeros(max(out_cap, 1), np.uint8)
+    n = lib().orc_snappy_uncompress(_p(b, C.c_uint8), len(blob), _p(out, C.c_uint8), out_cap)
+    if n < 0:
+        raise ValueError("malformed Snappy stream")
+    return bytes(out[:n])
+
+
+def get_compressed_weights(weights) -> bytes:
+    """LoadPortfolios.getCompressedWeights: Snappy.compress(double[]) (LoadPortfolios.java:563-595)."""
+    w = np.ascontiguousarray(weights, np.float64)
+    return snappy_compress(w.tobytes())
+
+
+def get_decompressed_weights(blob: bytes, n: int) -> np.ndarray:
+    return np.frombuffer(snappy_uncompress(blob, 8 * n), np.float64).copy()
+
+
+def doubles_to_bytes(weights) -> bytes:
+    w = np.ascontiguousarray(weights, np.float64)
+    out = np.zeros(max(8 * w.size, 1), np.uint8)
+    lib().orc_doubles_to_bytes(_p(w, C.c_double), w.size, _p(out, C.c_uint8))
+    return bytes(out[: 8 * w.size])

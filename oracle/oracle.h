@@ -107,6 +107,15 @@ int orc_batch_compress(int codec, int framing, const int32_t *vals, const int64_
 int orc_batch_uncompress(int codec, int framing, const uint8_t *in, int64_t stride_bytes, const int64_t *in_len,
                          int64_t nlists, int32_t *out, const int64_t *out_off, int nthreads);
 
+/* ---------------- weights column (weights_oracle.c) ----------------
+ * Raw Snappy format: the decoder takes any valid stream (snappy-java's included); the encoder is this repository's own
+ * greedy matcher -- valid Snappy, not snappy-java's byte choices (un-vendored dependency: parity unpinned). */
+int64_t orc_snappy_compress(const uint8_t *in, int64_t len, uint8_t *out);               /* out == NULL: size only */
+int64_t orc_snappy_uncompress(const uint8_t *in, int64_t inlen, uint8_t *out, int64_t out_cap);
+int64_t orc_get_compressed_weights(const double *w, int64_t n, uint8_t *out);            /* LoadPortfolios.java:563-595 */
+int64_t orc_get_decompressed_weights(const uint8_t *in, int64_t inlen, double *out, int64_t out_cap); /* :480,:580 */
+void    orc_doubles_to_bytes(const double *w, int64_t n, uint8_t *bytes);                /* BitManipulationHelper.java:193-208 */
+
 /* ---------------- risk half (builder-defined spec) ---------------- */
 
 /* V[p*N+n] = fma-chain over k ascending of E[p*F+k]*S[n*F+k], acc starts at +0.0 */
