@@ -2640,130 +2640,144 @@ __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *g
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 
-// Tiles are handed out by a ticket counter, in order, to CTAs that are running -- so the look-back can never wait on
-// a tile nobody works on (the smallest unfinished tile is always some CTA's CURRENT tile) -- but three tiles ahead:
-// the global-memory latencies are taken off the per-tile critical path.  While tile i is worked on, the ticket of
-// tile i+3, the list offsets of tile i+2 and the values of tile i+1 (cp.async, 16 bytes per copy) are in flight, and
-// the predecessors' look-back state words are read at the tile's start, long before they are needed.
-__global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs a)
+// exclusive block scan of one 32-bit word per thread over 128 threads; *total = the block's sum.  s_w: 4 words.
+__device__ __forceinline__ uint32_t vf_block_scan128(uint32_t v, uint32_t *s_w, uint32_t *total)
 {
-    __shared__ __align__(16) uint32_t s_vals[2][VF_SPAN];
-    __shared__ uint32_t s_out[VF_OCAP];
-    __shared__ uint32_t s_flag[VF_SPAN / 32];
-    __shared__ int64_t s_offr[3][VF_MAXL + 1]; // ring: list offsets of this tile, the next and the one after
-    __shared__ int s_rel[VF_MAXL + 1]; // list starts as window positions
-    __shared__ int s_ps[VF_MAXL + 2];  // flat byte prefix at the first value of the r-th NON-EMPTY list; [count] = total
-    __shared__ int s_ob[VF_MAXL];      // r-th non-empty list: byte address of its payload in s_out minus s_ps[r]
-    __shared__ int s_wb[VF_MAXL + 1];  // first output word of each list inside the tile (list order); [nl] = total
-    __shared__ uint32_t s_scan[VF_THREADS / 32];
-    __shared__ long long s_base;
-    __shared__ long long s_tq[4];      // ring: this CTA's tickets (tile ids), three ahead
-    __shared__ int s_slow;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = s_w[w];
+        if (w < warp) off += x;
+        tot += x;
+    }
+    *total = tot;
+    return off + incl - v;
+}
+
+// ---- flat encoder, second cut.  What the first one (8 values per thread, 32-wide look-back) taught, by ncu
+// (profiles/r2/ncu_flat_vb_v1.txt): 144 thread instructions per value, most of them per-TILE work spread over too few
+// values, and 61 % of the stall samples at the barrier behind the look-back -- with a thousand small tiles in flight in
+// lock step and none of them holding an inclusive prefix, the walk is long and the frontier of known prefixes advances
+// by 32 tiles per L2 round trip.  Hence: 32 values per thread (a tile is 4 096 window positions, ~40 lists), values
+// staged once in shared memory (16-byte cp.async into a 36-word row per thread: conflict-free LDS.128), the aggregate
+// published right after the scan, and a look-back in which ALL 128 threads poll two state words each: 256 tiles per
+// round trip, requested before the bytes are written and consumed after.
+constexpr int VE_THREADS = 128;
+constexpr int VE_VPT = 32;                     // window positions per thread
+constexpr int VE_SPAN = VE_THREADS * VE_VPT;   // 4 096
+constexpr int VE_ROW = VE_VPT + 4;             // padded row of a thread's values in shared memory (words)
+constexpr int VE_MAXL = 64;                    // lists per tile (two lanes-rounds of one warp keep the books)
+constexpr int VE_OCAP = 2816;                  // staged output words per tile
+
+__global__ void __launch_bounds__(VE_THREADS, 6) k_vbf_encode(const FastEncArgs a)
+{
+    __shared__ __align__(16) uint32_t s_vals[VE_THREADS * VE_ROW];
+    __shared__ uint32_t s_out[VE_OCAP];
+    __shared__ uint32_t s_flag[VE_THREADS];   // bit k of word t: a non-empty list starts at window position 32 t + k
+    __shared__ int64_t s_off[2][VE_MAXL + 1]; // list offsets of this tile and of the next one
+    __shared__ int s_rel[VE_MAXL + 1];        // list starts as window positions
+    __shared__ int s_ps[VE_MAXL + 2];         // flat byte prefix at the first value of the r-th NON-EMPTY list; [count] = total
+    __shared__ int s_ob[VE_MAXL];             // r-th non-empty list: byte address of its payload in s_out minus s_ps[r]
+    __shared__ int s_wb[VE_MAXL + 1];         // first output word of each list inside the tile (list order); [nl] = total
+    __shared__ uint32_t s_scan[VE_THREADS / 32];
+    __shared__ long long s_red[VE_THREADS / 32];
+    __shared__ int s_slow, s_ne;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CodecTraits tr = codec_traits(a.codec);
     uint8_t *sb = reinterpret_cast<uint8_t *>(s_out);
 
-    auto tile_lists = [&](int64_t tile) -> int { return tile < a.nbatches ? (int)min((int64_t)a.lists_per_batch, a.nlists - tile * a.lists_per_batch) : 0; };
-    auto load_off = [&](int64_t tile) -> int64_t { // this thread's entry of a tile's offsets (0 past the end)
-        const int nl = tile_lists(tile);
-        if (tile >= a.nbatches || tid > nl) return 0;
+    auto tile_lists = [&](long long tile) -> int {
+        return tile < a.nbatches ? (int)min((long long)a.lists_per_batch, (long long)a.nlists - tile * a.lists_per_batch) : 0;
+    };
+    auto load_off = [&](long long tile) -> int64_t { // this thread's entry of a tile's offsets (0 past the end)
+        if (tile >= a.nbatches || tid > tile_lists(tile)) return 0;
         const int64_t l = tile * a.lists_per_batch + tid;
         return a.list_off ? a.list_off[l] : l * a.uniform_len;
     };
-    // the tile's window over vals: 16-byte aligned start, a0 = position of the first value in it
-    auto request_values = [&](int64_t tile, const int64_t *off, uint32_t *buf) {
-        const int nl = tile_lists(tile);
-        if (nl > 0) {
-            const int64_t base = off[0], nv = off[nl] - base;
-            const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3);
-            const int64_t span = a0 + nv;
-            if (nv >= 0 && span <= VF_SPAN) {
-                const uint32_t *wp = a.vals + base - a0;
-                const int p0 = VF_VPT * tid;
-                if (p0 < span) cp_async16(buf + p0, wp + p0);
-                if (p0 + 4 < span) cp_async16(buf + p0 + 4, wp + p0 + 4);
-            }
-        }
-        cp_async_commit();
-    };
+    // Tiles are assigned statically, tile = blockIdx.x + it * gridDim.x, and the grid is sized to be fully resident
+    // (codec_fast_encode asks the occupancy calculator): every predecessor a look-back can wait for is the CURRENT tile
+    // of a running CTA, at the same stage as this one -- handing tickets out ahead of time (to prefetch) makes tiles
+    // wait for predecessors nobody has started yet and serialises the kernel (measured: 1.8 ms instead of 0.5).
+    const long long G = gridDim.x;
+    { const int64_t o0 = load_off(blockIdx.x); if (tid <= VE_MAXL) s_off[0][tid] = o0; }
+    __syncthreads();
 
-    {
-        // the first three tiles of every CTA are k, k + G, k + 2G (the counter starts at 3G): a well-mixed start -- consecutive
-        // tiles belong to different CTAs, all of them running (the grid is sized to be fully resident)
-        if (tid == 0) { s_tq[0] = blockIdx.x; s_tq[1] = blockIdx.x + (long long)gridDim.x; s_tq[2] = blockIdx.x + 2ll * gridDim.x; }
-        __syncthreads();
-        const int64_t o0 = load_off(s_tq[0]), o1 = load_off(s_tq[1]);
-        if (tid <= VF_MAXL) { s_offr[0][tid] = o0; s_offr[1][tid] = o1; }
-        __syncthreads();
-        request_values(s_tq[0], s_offr[0], s_vals[0]);
-    }
     for (int it = 0;; ++it) {
-        const int64_t tile = s_tq[it & 3];
-        if (tile >= a.nbatches) break; // (tickets only grow: every later one of this CTA is past the end too)
-        const int64_t *off = s_offr[it % 3];
-        const uint32_t *vbuf = s_vals[it & 1];
+        const long long tile = blockIdx.x + it * G;
+        if (tile >= a.nbatches) break;
+        const int64_t *off = s_off[it & 1];
         const int64_t l0 = tile * a.lists_per_batch;
         const int nl = tile_lists(tile);
-        // ---- requests for later tiles, and an early look at the predecessors' state words
-        long long tk_next3 = 0;
-        if (tid == 0) tk_next3 = (long long)atomicAdd(a.ticket, 1ull);
-        const int64_t off_next2 = load_off(s_tq[(it + 2) & 3]);
-        request_values(s_tq[(it + 1) & 3], s_offr[(it + 1) % 3], s_vals[(it + 1) & 1]);
-        uint64_t st_early = kLbInc;
-        if (warp == 0 && tile - 1 - lane >= 0) st_early = ld_relaxed_u64(a.state + (tile - 1 - lane));
-        if (tid < VF_SPAN / 32) s_flag[tid] = 0;
+        // ---- a request that need not wait: the next tile's offsets
+        const int64_t off_next = load_off(tile + G);
         const int64_t base = off[0], nv = off[nl] - base;
-        const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3);
+        const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3); // the window starts on a 16-byte boundary
         const int64_t span = a0 + nv;
-        bool bad = false;
+        bool bad = span > VE_SPAN || nv < 0;
         if (tid < nl) {
             const int64_t n = off[tid + 1] - off[tid];
-            bad = n < 0 || (tr.fastpfor && n >= tr.fp_block);
+            bad = bad || n < 0 || (tr.fastpfor && n >= tr.fp_block);
         }
-        bad = bad || span > VF_SPAN || nv < 0;
-        if (tid <= nl && !(span > VF_SPAN || nv < 0)) s_rel[tid] = a0 + (int)(off[tid] - base);
-        cp_async_wait<1>(); // this tile's values (requested one tile ago) have landed
+        const int p0 = VE_VPT * tid;
+        uint32_t *row = s_vals + tid * VE_ROW;
+        if (!(span > VE_SPAN || nv < 0)) {
+            const uint32_t *wp = a.vals + base - a0;
+#pragma unroll
+            for (int c = 0; c < VE_VPT / 4; ++c)
+                if (p0 + 4 * c < span) cp_async16(row + 4 * c, wp + p0 + 4 * c);
+            if (tid <= nl) s_rel[tid] = a0 + (int)(off[tid] - base);
+        }
+        cp_async_commit();
+        s_flag[tid] = 0;
         const int slow = __syncthreads_or(bad);
         long long T = 0; // words of the tile
         if (!slow) {
             // ---- list starts (non-empty lists only: a value belongs to the LAST list that starts at its position)
             if (tid < nl && s_rel[tid + 1] > s_rel[tid]) atomicOr(&s_flag[s_rel[tid] >> 5], 1u << (s_rel[tid] & 31));
-            // ---- this thread's 8 window positions
-            const int p0 = VF_VPT * tid;
-            uint32_t x[8];
+            cp_async_wait<0>();
+            __syncthreads(); // values and start bits are in place
+            const uint32_t fw = s_flag[tid];
+            // valid positions of this thread: [a0, span) intersected with [p0, p0 + 32)
+            const int lo = a0 - p0, hi = (int)(span - p0);
+            const uint32_t vm = (hi <= 0 || lo >= 32) ? 0u : ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u)));
+            uint32_t prev0 = 0;
+            if (tid > 0 && vm) prev0 = s_vals[(tid - 1) * VE_ROW + VE_VPT - 1];
+            // ---- pass A: byte lengths (4 bits each, 8 values per word), warp-uniform "every value takes <= 2 bytes"
+            uint32_t lens[4], wor = 0;
             {
-                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-                if (p0 < span) q0 = *reinterpret_cast<const uint4 *>(vbuf + p0);
-                if (p0 + 4 < span) q1 = *reinterpret_cast<const uint4 *>(vbuf + p0 + 4);
-                x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w; x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
-            }
-            uint32_t prev = __shfl_up_sync(kFull, x[7], 1);
-            if (lane == 0) prev = (tid > 0 && p0 < span) ? vbuf[p0 - 1] : 0u;
-            __syncthreads(); // the start bits are in place
-            const uint32_t fw = (s_flag[p0 >> 5] >> (p0 & 31)) & 0xffu;
-            uint32_t vm = 0; // valid positions
+                uint32_t prev = prev0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vm |= (uint32_t)(p0 + k >= a0 && p0 + k < span) << k;
-            // ---- the sequence the codec sees (Delta.delta: gaps, the first value of a list as it is), byte lengths
-            uint32_t d[8], wor = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 q0 = *reinterpret_cast<const uint4 *>(row + 8 * c), q1 = *reinterpret_cast<const uint4 *>(row + 8 * c + 4);
+                    const uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    uint32_t l = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                d[k] = (a.delta && !((fw >> k) & 1u)) ? x[k] - prev : x[k];
-                prev = x[k];
-                if ((vm >> k) & 1u) wor |= d[k];
+                    for (int k = 0; k < 8; ++k) {
+                        const int pk = 8 * c + k;
+                        const uint32_t d = (a.delta && !((fw >> pk) & 1u)) ? x[k] - prev : x[k];
+                        prev = x[k];
+                        const uint32_t ok = (vm >> pk) & 1u;
+                        wor |= ok ? d : 0u;
+                        const uint32_t len = ok ? (uint32_t)vb_len(d) : 0u;
+                        l |= len << (4 * k);
+                    }
+                    lens[c] = l;
+                }
             }
-            const bool small = __reduce_or_sync(kFull, wor) < 16384u; // warp-uniform: every value takes one or two bytes
-            uint32_t lens = 0;
             int nbytes = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                int len = small ? 1 + (int)(d[k] >= 128u) : vb_len(d[k]);
-                len = ((vm >> k) & 1u) ? len : 0;
-                lens |= (uint32_t)len << (4 * k);
-                nbytes += len;
-            }
+            for (int c = 0; c < 4; ++c) nbytes += nib_prefix(lens[c], 8);
             uint32_t tot;
-            const uint32_t ex = vf_block_scan((uint32_t)nbytes | ((uint32_t)__popc(fw) << 16), s_scan, &tot);
+            const uint32_t ex = vf_block_scan128((uint32_t)nbytes | ((uint32_t)__popc(fw) << 16), s_scan, &tot);
             const int B0 = (int)(ex & 0xffffu), L0 = (int)(ex >> 16);
             {
                 uint32_t f = fw;
@@ -2771,73 +2785,139 @@ __global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs 
                 while (f) {
                     const int k = __ffs(f) - 1;
                     f &= f - 1;
-                    s_ps[r++] = B0 + nib_prefix(lens, k);
+                    int b = B0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) b += c < (k >> 3) ? nib_prefix(lens[c], 8) : (c == (k >> 3) ? nib_prefix(lens[c], k & 7) : 0);
+                    s_ps[r++] = b;
                 }
             }
-            if (tid == VF_THREADS - 1) s_ps[tot >> 16] = (int)(tot & 0xffffu);
+            if (tid == VE_THREADS - 1) { s_ps[tot >> 16] = (int)(tot & 0xffffu); s_ne = (int)(tot >> 16); }
             __syncthreads();
-            // ---- per-list sizes and framing (one warp): IntCompressor writes n first, Composition the 0 marker when FastPFOR
-            // took nothing, the loader's framing one trailing zero word (LoadPortfolios.java:622)
+            // ---- per-list sizes and framing (one warp, two lists per lane): IntCompressor writes n first, Composition the
+            // 0 marker when FastPFOR took nothing, the loader's framing one trailing zero word (LoadPortfolios.java:622)
             if (warp == 0) {
-                const int n = lane < nl ? s_rel[lane + 1] - s_rel[lane] : 0;
-                const unsigned ne = __ballot_sync(kFull, n > 0);
-                const int r = __popc(ne & ((1u << lane) - 1u));
-                const int bytes = n > 0 ? s_ps[r + 1] - s_ps[r] : 0;
-                const int hdr = lane < nl ? (tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0)) : 0;
-                const int words = lane < nl ? hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0) : 0;
-                int incl = words;
+                int run_w = 0, run_r = 0;
+                bool fits = true;
 #pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const int t = __shfl_up_sync(kFull, incl, dd);
-                    if (lane >= dd) incl += t;
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 32 * h + lane;
+                    const int n = j < nl ? s_rel[j + 1] - s_rel[j] : 0;
+                    const unsigned ne = __ballot_sync(kFull, n > 0);
+                    const int r = run_r + __popc(ne & ((1u << lane) - 1u));
+                    const int bytes = n > 0 ? s_ps[r + 1] - s_ps[r] : 0;
+                    const int hdr = j < nl ? (tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0)) : 0;
+                    const int words = j < nl ? hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0) : 0;
+                    int incl = words;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int t = __shfl_up_sync(kFull, incl, dd);
+                        if (lane >= dd) incl += t;
+                    }
+                    const int wb = run_w + incl - words;
+                    const int tot_w = run_w + __shfl_sync(kFull, incl, 31);
+                    fits = fits && tot_w <= VE_OCAP;
+                    if (j < nl) s_wb[j] = wb;
+                    if (tot_w <= VE_OCAP && j < nl) {
+                        if (hdr) s_out[wb] = tr.sk ? (uint32_t)n : 0u;
+                        if (bytes > 0) s_out[wb + hdr + ((bytes - 1) >> 2)] = 0u; // the zero padding of the last payload word
+                        if (a.app) s_out[wb + words - 1] = 0u;
+                        if (n > 0) s_ob[r] = 4 * (wb + hdr) - s_ps[r];
+                    }
+                    run_w = tot_w;
+                    run_r += __popc(ne);
                 }
-                const int wb = incl - words;
-                T = __shfl_sync(kFull, incl, 31);
-                const bool fits = T <= VF_OCAP;
-                if (lane < nl) s_wb[lane] = wb;
-                if (lane == 0) s_wb[nl] = (int)T;
-                if (fits && lane < nl) {
-                    if (hdr) s_out[wb] = tr.sk ? (uint32_t)n : 0u;
-                    if (bytes > 0) s_out[wb + hdr + ((bytes - 1) >> 2)] = 0u; // the zero padding of the last payload word
-                    if (a.app) s_out[wb + words - 1] = 0u;
-                    if (n > 0) s_ob[r] = 4 * (wb + hdr) - s_ps[r];
-                }
+                T = run_w;
                 if (lane == 0) {
+                    s_wb[nl] = (int)T;
                     s_slow = fits ? 0 : 1;
                     if (fits) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
                 }
             }
             __syncthreads();
             if (!s_slow) {
-                if (warp == 0) {
-                    // the tile's place in the output: the look-back runs while the other warps write the bytes
-                    const long long b = vf_lookback(a.state, tile, T, lane, st_early);
-                    if (lane == 0) s_base = b;
-                }
+                T = s_wb[nl];
+                // ---- look-back, first round requested now (256 predecessors: two state words per thread), consumed after
+                // the bytes are written
+                const long long i0 = tile - 1 - tid, i1 = tile - 1 - VE_THREADS - tid;
+                uint64_t st0 = i0 >= 0 ? ld_relaxed_u64(a.state + i0) : kLbInc; // before the first tile: an inclusive prefix of 0
+                uint64_t st1 = i1 >= 0 ? ld_relaxed_u64(a.state + i1) : kLbInc;
+                // ---- pass B: bytes (VariableByte.java:44-68: 7-bit groups, low group first, bit 7 on the LAST byte)
                 {
-                    // ---- bytes (VariableByte.java:44-68: 7-bit groups, low group first, bit 7 on the LAST byte)
+                    const bool small = __reduce_or_sync(kFull, wor) < 16384u; // warp-uniform: one or two bytes per value
                     int li = L0 - 1, ob = li >= 0 ? s_ob[li] : 0, bo = B0;
+                    uint32_t prev = prev0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if ((fw >> k) & 1u) ob = s_ob[++li];
-                        const int len = (int)((lens >> (4 * k)) & 15u);
-                        if (len) {
-                            uint8_t *dst = sb + ob + bo;
-                            uint32_t v = d[k];
-                            if (small) {
-                                dst[0] = (uint8_t)((v & 127u) | (len == 1 ? 128u : 0u));
-                                if (len == 2) dst[1] = (uint8_t)((v >> 7) | 128u);
-                            } else {
-                                for (int j = 0; j < len - 1; ++j) { dst[j] = (uint8_t)(v & 127u); v >>= 7; }
-                                dst[len - 1] = (uint8_t)(v | 128u);
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 q0 = *reinterpret_cast<const uint4 *>(row + 8 * c), q1 = *reinterpret_cast<const uint4 *>(row + 8 * c + 4);
+                        const uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                        const uint32_t f8 = (fw >> (8 * c)) & 0xffu, l8 = lens[c];
+                        if (small) { // warp-uniform: one or two bytes per value, list starts by predication
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const bool st = (f8 >> k) & 1u;
+                                if (st) ob = s_ob[++li];
+                                const uint32_t d = (a.delta && !st) ? x[k] - prev : x[k];
+                                prev = x[k];
+                                const int len = (int)((l8 >> (4 * k)) & 15u);
+                                if (len) {
+                                    uint8_t *dst = sb + ob + bo;
+                                    dst[0] = (uint8_t)((d & 127u) | (len == 1 ? 128u : 0u));
+                                    if (len == 2) dst[1] = (uint8_t)((d >> 7) | 128u);
+                                    bo += len;
+                                }
                             }
-                            bo += len;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const bool st = (f8 >> k) & 1u;
+                                if (st) ob = s_ob[++li];
+                                uint32_t d = (a.delta && !st) ? x[k] - prev : x[k];
+                                prev = x[k];
+                                const int len = (int)((l8 >> (4 * k)) & 15u);
+                                if (len) {
+                                    uint8_t *dst = sb + ob + bo;
+                                    for (int j = 0; j < len - 1; ++j) { dst[j] = (uint8_t)(d & 127u); d >>= 7; }
+                                    dst[len - 1] = (uint8_t)(d | 128u);
+                                    bo += len;
+                                }
+                            }
                         }
                     }
                 }
-                __syncthreads();
-                const long long gbase = s_base;
-                T = s_wb[nl];
+                // ---- the tile's place in the output: block-wide look-back, 256 predecessors per round
+                long long gbase = 0;
+                if (tile > 0) {
+                    for (long long jbase = tile - 1;; jbase -= 2 * VE_THREADS) {
+                        // wait for this thread's two words (aggregates are published early: rarely a wait at all)
+                        while ((st0 >> 62) == 0) { __nanosleep(20); st0 = ld_relaxed_u64(a.state + (jbase - tid)); }
+                        while ((st1 >> 62) == 0) { __nanosleep(20); st1 = ld_relaxed_u64(a.state + (jbase - VE_THREADS - tid)); }
+                        // nearest inclusive prefix among the 256 (distance = tid, or 128 + tid)
+                        const unsigned b0 = __ballot_sync(kFull, (st0 >> 62) == 2), b1 = __ballot_sync(kFull, (st1 >> 62) == 2);
+                        // distance of the nearest inclusive one in this warp's two lane-groups (or a large number)
+                        const int d0 = b0 ? 32 * warp + __ffs(b0) - 1 : 1 << 20;
+                        const int d1 = b1 ? VE_THREADS + 32 * warp + __ffs(b1) - 1 : 1 << 20;
+                        if (lane == 0) s_red[warp] = d0 < d1 ? d0 : d1;
+                        __syncthreads();
+                        int dmin = 1 << 20;
+#pragma unroll
+                        for (int w = 0; w < VE_THREADS / 32; ++w) dmin = min(dmin, (int)s_red[w]);
+                        __syncthreads();
+                        long long v = (tid <= dmin ? (long long)(st0 & kLbMask) : 0) + (VE_THREADS + tid <= dmin ? (long long)(st1 & kLbMask) : 0);
+#pragma unroll
+                        for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(kFull, v, dd);
+                        if (lane == 0) s_red[warp] = v;
+                        __syncthreads();
+#pragma unroll
+                        for (int w = 0; w < VE_THREADS / 32; ++w) gbase += s_red[w];
+                        __syncthreads();
+                        if (dmin < (1 << 20)) break;
+                        const long long n0 = jbase - 2 * VE_THREADS - tid, n1 = n0 - VE_THREADS;
+                        st0 = n0 >= 0 ? ld_relaxed_u64(a.state + n0) : kLbInc;
+                        st1 = n1 >= 0 ? ld_relaxed_u64(a.state + n1) : kLbInc;
+                    }
+                    if (tid == 0) st_relaxed_u64(a.state + tile, kLbInc | (uint64_t)(gbase + T));
+                } else
+                    __syncthreads(); // (the bytes of tile 0 are in place)
                 if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
                 if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
                 if (4 * (gbase + T) > a.cap) { // caller's buffer too small: report, write nothing
@@ -2845,14 +2925,14 @@ __global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs 
                 } else {
                     uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
                     const uint32_t sel = a.app ? 0x0123u : 0x3210u;
-                    for (int i = tid; i < (int)T; i += VF_THREADS) gout[i] = __byte_perm(s_out[i], 0, sel);
+                    for (int i = tid; i < (int)T; i += VE_THREADS) gout[i] = __byte_perm(s_out[i], 0, sel);
                 }
-                if (tid <= VF_MAXL) s_offr[(it + 2) % 3][tid] = off_next2;
-                if (tid == 0) s_tq[(it + 3) & 3] = tk_next3;
+                if (tid <= VE_MAXL) s_off[(it + 1) & 1][tid] = off_next;
                 __syncthreads();
                 continue;
             }
         }
+        cp_async_wait<0>();
         // ---- a tile that does not fit: sizes, look-back and streams by the warp-per-list routines
         bool page = false;
         if (tid < nl) page = tr.fastpfor && off[tid + 1] - off[tid] >= tr.fp_block;
@@ -2861,7 +2941,7 @@ __global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs 
         if (has_page) {
             if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
         } else {
-            for (int j = warp; j < nl; j += VF_THREADS / 32) {
+            for (int j = warp; j < nl; j += VE_THREADS / 32) {
                 const int64_t w = warp_short_list_encode<false>(tr, ValSeq{a.vals + off[j], a.delta}, off[j + 1] - off[j],
                                                                 WordSink{nullptr, a.app}, a.app, stage, lane);
                 if (lane == 0) s_ob[j] = (int)w; // (the slow path reuses s_ob for the lists' sizes in words)
@@ -2870,22 +2950,27 @@ __global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs 
         }
         __syncthreads();
         if (warp == 0) {
-            long long w = (!has_page && lane < nl) ? (long long)s_ob[lane] : 0;
-            long long incl = w;
+            long long run = 0;
+            for (int h = 0; h < 2; ++h) {
+                const int j = 32 * h + lane;
+                long long w = (!has_page && j < nl) ? (long long)s_ob[j] : 0;
+                long long incl = w;
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const long long t = __shfl_up_sync(kFull, incl, dd);
-                if (lane >= dd) incl += t;
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const long long t = __shfl_up_sync(kFull, incl, dd);
+                    if (lane >= dd) incl += t;
+                }
+                if (j < nl) s_wb[j] = (int)(run + incl - w);
+                run += __shfl_sync(kFull, incl, 31);
             }
-            T = __shfl_sync(kFull, incl, 31);
-            if (lane < nl) s_wb[lane] = (int)(incl - w);
+            T = run;
             if (lane == 0) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
-            const long long b = vf_lookback(a.state, tile, T, lane, st_early);
-            if (lane == 0) { s_base = b; s_wb[nl] = (int)T; }
+            const long long b = lookback_warp(a.state, tile, T, lane);
+            if (lane == 0) { s_red[0] = b; s_wb[nl] = (int)T; }
         }
         __syncthreads();
         {
-            const long long gbase = s_base;
+            const long long gbase = s_red[0];
             T = s_wb[nl];
             if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
             if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
@@ -2893,18 +2978,16 @@ __global__ void __launch_bounds__(VF_THREADS, 5) k_vbf_encode(const FastEncArgs 
                 if (tid == 0) atomicMax(a.err, 1);
             } else if (!has_page) {
                 uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
-                for (int j = warp; j < nl; j += VF_THREADS / 32) {
+                for (int j = warp; j < nl; j += VE_THREADS / 32) {
                     const int64_t beg = off[j], n = off[j + 1] - beg;
                     warp_short_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_wb[j], a.app}, a.app, stage, lane);
                     __syncwarp();
                 }
             }
         }
-        if (tid <= VF_MAXL) s_offr[(it + 2) % 3][tid] = off_next2;
-        if (tid == 0) s_tq[(it + 3) & 3] = tk_next3;
+        if (tid <= VE_MAXL) s_off[(it + 1) & 1][tid] = off_next;
         __syncthreads();
     }
-    cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(VF_THREADS, 4) k_vbf_decode(const FastDecArgs a, int64_t ntiles)
@@ -3266,11 +3349,11 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
 
 // lists per tile of the flat VariableByte kernels: `target` values per tile on average (the tile's window holds
 // VF_SPAN values / VF_WSPAN words; a tile that overflows is done by the warp-per-list routines inside the kernel)
-static int vbf_lists_per_tile(int64_t total_vals, int64_t nlists, double target)
+static int vbf_lists_per_tile(int64_t total_vals, int64_t nlists, double target, int maxl)
 {
     const double avg = nlists > 0 ? (double)total_vals / (double)nlists : 1.0;
     int64_t g = (int64_t)(target / (avg > 1.0 ? avg : 1.0));
-    return (int)(g < 1 ? 1 : (g > VF_MAXL ? VF_MAXL : g));
+    return (int)(g < 1 ? 1 : (g > maxl ? maxl : g));
 }
 
 // the batched (thread-per-block) kernels: BinaryPacking family and FastPFOR / FastPFOR128
@@ -3344,7 +3427,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         if (pass == 1 && !batched) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; }
         // lists that are all VariableByte (FastPFOR / FastPFOR128 below one block, VariableByte alone) take the flat kernel
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
-        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.8 * VF_SPAN) : 32)
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.86 * VE_SPAN, VE_MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_vals, nlists);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
@@ -3362,13 +3445,10 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
                 int per_sm = 0;
-                MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vbf_encode, VF_THREADS, 0));
+                MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vbf_encode, VE_THREADS, 0));
                 if (per_sm < 1) return fail(ctx, MCP_E_CUDA, "k_vbf_encode does not fit an SM");
-                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * per_sm; // every CTA resident: see the kernel's ticket scheme
-                const unsigned grid = (unsigned)(a.nbatches < res ? a.nbatches : res);
-                const unsigned long long first_ticket = 3ull * grid;
-                MCP_CUDA(ctx, cudaMemcpyAsync(a.ticket, &first_ticket, sizeof first_ticket, cudaMemcpyHostToDevice, ctx->stream));
-                k_vbf_encode<<<grid, VF_THREADS, 0, ctx->stream>>>(a);
+                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * per_sm;
+                k_vbf_encode<<<(unsigned)(a.nbatches < res ? a.nbatches : res), VE_THREADS, 0, ctx->stream>>>(a);
             } else if (pass == 0) {
                 const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
                 k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);
@@ -3416,7 +3496,7 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
         if (pass == 1 && !batched) return MCP_E_UNSUPPORTED;
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
-        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 2000.0) : 32)
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 2000.0, VF_MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_out_vals, nlists);
         const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         {
