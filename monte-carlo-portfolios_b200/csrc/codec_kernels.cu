@@ -2640,353 +2640,407 @@ __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *g
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 
-// exclusive block scan of one 32-bit word per thread over 128 threads; *total = the block's sum.  s_w: 4 words.
-__device__ __forceinline__ uint32_t vf_block_scan128(uint32_t v, uint32_t *s_w, uint32_t *total)
+// ---- flat VariableByte encoder: size pass, tile scan, emit pass.
+// History, by measurement (profiles/r2/codec_flat_log.md).  Every single-pass version -- thread-per-list batches, flat tiles
+// of 2 048 and 4 096 values, 32-, 256- and 768-wide look-backs, dynamic tickets and static assignment -- ended at ~0.5 ms for
+// the 10^8 ints of C4: with tiles this small (a tile's time on an SM is about one L2 round trip) the decoupled look-back is
+// the clock of the kernel: the frontier of known output positions advances by one poll window per round trip, and a grid in
+// lock step waits for its slowest member at every tile (47 % of the stall samples at the barrier behind the look-back).
+// So the output position of a tile comes from a SIZE pass instead: the same tile kernel without its second half writes the
+// tile's word count, one CTA scans the ~25 000 counts, and the EMIT pass knows where it writes before it starts -- no state
+// words, no polling, no residency requirement: one tile per CTA, the hardware scheduler does the balancing, and the input is
+// read twice (HBM is not the bound here).
+// The tile kernel: THREADS x VPT consecutive values per tile (a fixed number of whole lists); values arrive by coalesced 16-byte
+// cp.async into a chunk-swizzled staging tile (conflict-free for the copy and for the LDS.128 of a thread's row), are turned
+// into gaps once and stay in registers.  A thread whose values are all below 2^14 (one or two bytes: every thread of C4)
+// keeps a "two bytes" bit mask instead of lengths; positions of the window outside the tile are phantom zeros whose bytes go
+// to a scratch area, so no thread carries validity tests.  List bookkeeping is PULLED by one thread per list (byte prefix at
+// a list's first value = its thread's prefix + a popcount), value threads never loop over list starts.
+template <int THREADS, int VPT>
+struct V4 {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int SPAN = THREADS * VPT;           // window positions per tile
+    static constexpr int CH = VPT / 4;                   // 16-byte chunks per thread
+    static constexpr int MAXL = THREADS - 1;             // lists per tile: one thread per list, one more for the end offset
+    static constexpr int OCAP = SPAN / 2 + 3 * THREADS;  // staged output words: two bytes per value + framing of MAXL lists
+    static constexpr int SCR = VPT / 4 + 2;              // words of scratch for phantom bytes (leading and trailing)
+    // word of chunk c of thread t in the staging tile: chunks permuted so that a quarter-warp's 16-byte accesses (row stride
+    // 64 or 128 bytes) fall into eight different bank groups
+    __device__ static __forceinline__ int slot(int t, int c) { return t * VPT + 4 * (VPT == 16 ? (c ^ ((t >> 1) & 3)) : (c ^ (t & 7))); }
+};
+
+// sum of the nibbles of x below nibble k (k <= 16)
+__device__ __forceinline__ int nib_prefix64(uint64_t x, int k)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = v;
+    if (k < 16) x &= (1ull << (4 * k)) - 1ull;
+    x = (x & 0x0f0f0f0f0f0f0f0full) + ((x >> 4) & 0x0f0f0f0f0f0f0f0full);
+    return (int)((x * 0x0101010101010101ull) >> 56);
+}
+
+struct TileEncArgs {
+    FastEncArgs f;
+    int64_t *tile_words;  // [nbatches] size pass: words of the tile; after the scan: first word of the tile in the output
+    int hdr_mode;         // word in front of a list's bytes: 0 none, 1 IntCompressor's n, 2 Composition's 0 marker (non-empty lists)
+    int page;             // FastPFOR block size: a list this long is not all VariableByte (0: no limit)
+};
+
+template <int THREADS, int VPT, bool DELTA, bool EMIT>
+__global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
+{
+    using C = V4<THREADS, VPT>;
+    const FastEncArgs &a = ta.f;
+    __shared__ __align__(16) uint32_t s_vals[C::SPAN];
+    __shared__ __align__(16) uint32_t s_out[EMIT ? C::OCAP + 4 + 2 * C::SCR : 64 * C::WARPS];
+    __shared__ int s_rel[THREADS + 1];              // list starts as window positions ([nl] = the tile's end)
+    __shared__ uint32_t s_flag[C::SPAN / 32 + 1];   // bit p: a non-empty list starts at window position p (and the phantom one at the end)
+    __shared__ uint32_t s_tp[THREADS];              // per thread: (bytes | list starts << 16) of the warp's lower lanes
+    __shared__ uint32_t s_m2[THREADS];              // per thread: bit k = value k takes two bytes
+    __shared__ uint64_t s_len[THREADS][VPT / 16];   // per thread off the short path: byte length of value k in nibble k
+    __shared__ uint8_t s_gen[THREADS];              // per thread: 1 = off the short path
+    __shared__ int s_ob[THREADS + 2];               // [r + 1], r-th non-empty list: byte address of its payload in s_out minus its flat byte prefix
+    __shared__ uint32_t s_w1[C::WARPS], s_w2[C::WARPS];
+    __shared__ long long s_red[C::WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile = blockIdx.x;
+    const int64_t l0 = tile * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    long long gbase = 0;
+    if (EMIT) { // (uniform) the caller's buffer is too small: the scan kernel has reported it, nothing is written
+        if (*a.total > a.cap) return;
+        gbase = ta.tile_words[tile];
+    }
+    // ---- the tile's extent, this thread's list
+    int64_t base, end, my_off = 0, my_end = 0;
+    if (a.list_off) {
+        const int64_t *lo = a.list_off + l0;
+        base = lo[0]; end = lo[nl];
+        if (tid <= nl) { my_off = lo[tid]; my_end = lo[tid < nl ? tid + 1 : tid]; }
+    } else {
+        base = l0 * a.uniform_len; end = base + nl * a.uniform_len;
+        my_off = base + min(tid, nl) * a.uniform_len; my_end = base + min(tid + 1, nl) * a.uniform_len;
+    }
+    const int64_t nv = end - base;
+    const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3); // the window starts on a 16-byte boundary
+    bool bad = nv < 0 || a0 + nv > C::SPAN;
+    const int span = bad ? 0 : a0 + (int)nv;
+    if (tid < C::SPAN / 32 + 1) s_flag[tid] = 0;
+    {
+        const uint32_t *wp = a.vals + base - a0 + 4 * tid;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += t;
+        for (int i = 0; i < C::CH; ++i) { // chunk q = i THREADS + tid of the window: coalesced
+            const int q = i * THREADS + tid;
+            if (4 * q < span) cp_async16(s_vals + C::slot(q / C::CH, q % C::CH), wp + 4 * i * THREADS);
+        }
+    }
+    cp_async_commit();
+    const int64_t my_n = my_end - my_off;
+    if (tid <= nl) bad = bad || my_off < base || my_off > end || my_n < 0 || (ta.page > 0 && my_n >= ta.page);
+    __syncthreads(); // (the start bits are zero)
+    if (tid <= nl && !bad) {
+        const int rel = a0 + (int)(my_off - base);
+        s_rel[tid] = rel;
+        // a value belongs to the LAST list that starts at its position: only non-empty lists set a bit; the window positions
+        // past the tile's end form a phantom list of their own
+        if (tid == nl || my_n > 0) atomicOr(&s_flag[rel >> 5], 1u << (rel & 31));
+    }
+    cp_async_wait<0>();
+    int slow = __syncthreads_or(bad); // values, list starts and start bits are in place
+    if (!slow) {
+        // ---- pass A: the sequence the codec sees (Delta.delta: gaps, a list's first value as it is), byte lengths
+        const int p0 = VPT * tid;
+        const uint32_t fw = VPT == 32 ? s_flag[tid] : (s_flag[tid >> 1] >> (16 * (tid & 1))) & 0xffffu;
+        const uint32_t full = VPT == 32 ? 0xffffffffu : 0xffffu;
+        const int lo = a0 - p0, hi = min(VPT, span - p0);
+        const uint32_t vm = hi <= 0 ? 0u : ((hi >= 32 ? 0xffffffffu : (1u << hi) - 1u) & (lo <= 0 ? full : ~((1u << lo) - 1u)));
+        uint32_t d[VPT];
+        uint32_t m2 = 0, wor = 0;
+        uint64_t nib[VPT / 16];
+        bool gen = false;
+        int nbytes = 0;
+        if (vm) {
+            uint32_t prev = tid > 0 ? s_vals[C::slot(tid - 1, C::CH - 1) + 3] : 0u;
+#pragma unroll
+            for (int c = 0; c < C::CH; ++c) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(s_vals + C::slot(tid, c));
+                const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int pk = 4 * c + k;
+                    d[pk] = (DELTA && !((fw >> pk) & 1u)) ? x[k] - prev : x[k];
+                    prev = x[k];
+                }
+            }
+            if (vm != full) { // phantom positions (before the tile's first value, past its last): zeros, one byte each
+#pragma unroll
+                for (int k = 0; k < VPT; ++k)
+                    if (!((vm >> k) & 1u)) d[k] = 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) wor |= d[k];
+            gen = wor >= 16384u;
+            if (!gen) {
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) m2 |= (d[k] >= 128u ? 1u : 0u) << k;
+                nbytes = VPT + __popc(m2);
+            } else {
+#pragma unroll
+                for (int h = 0; h < VPT / 16; ++h) {
+                    uint64_t nb64 = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int len = vb_len(d[16 * h + k]);
+                        nb64 |= (uint64_t)len << (4 * k);
+                        nbytes += len;
+                    }
+                    nib[h] = nb64;
+                    s_len[tid][h] = nb64;
+                }
+            }
+        }
+        s_m2[tid] = m2;
+        s_gen[tid] = gen ? 1 : 0;
+        const uint32_t my1 = (uint32_t)nbytes | ((uint32_t)__popc(fw) << 16);
+        uint32_t incl1 = my1;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl1, dd);
+            if (lane >= dd) incl1 += t;
+        }
+        s_tp[tid] = incl1 - my1;
+        if (lane == 31) s_w1[warp] = incl1;
+        __syncthreads();
+        uint32_t wo1 = 0, tot1 = 0;
+#pragma unroll
+        for (int w = 0; w < C::WARPS; ++w) {
+            const uint32_t x = s_w1[w];
+            if (w < warp) wo1 += x;
+            tot1 += x;
+        }
+        const uint32_t ex1 = wo1 + incl1 - my1;
+        // ---- one thread per list: its bytes (flat byte prefix at the next list's first value minus the one at its own),
+        // words and framing: IntCompressor writes n first, Composition the 0 marker when FastPFOR took nothing, the
+        // loader's framing one trailing zero word (LoadPortfolios.java:622)
+        auto byte_prefix = [&](int p) -> int {
+            if (p >= C::SPAN) return (int)(tot1 & 0xffffu);
+            const int t = p / VPT, k = p % VPT;
+            int b;
+            if (s_gen[t]) {
+                b = 0;
+#pragma unroll
+                for (int h = 0; h < VPT / 16; ++h)
+                    if (k > 16 * h) b += nib_prefix64(s_len[t][h], min(16, k - 16 * h));
+            } else
+                b = k + __popc(s_m2[t] & ((1u << k) - 1u));
+            b += (int)(s_tp[t] & 0xffffu);
+#pragma unroll
+            for (int w = 0; w < C::WARPS - 1; ++w)
+                if (w < (t >> 5)) b += (int)(s_w1[w] & 0xffffu);
+            return b;
+        };
+        int n = 0, bytes = 0, hdr = 0, words = 0, bplo = 0;
+        if (tid <= nl) {
+            const int plo = s_rel[tid];
+            bplo = byte_prefix(plo);
+            if (tid < nl) {
+                n = (int)my_n;
+                bytes = n > 0 ? byte_prefix(plo + n) - bplo : 0;
+                hdr = ta.hdr_mode == 1 ? 1 : (ta.hdr_mode == 2 && n > 0 ? 1 : 0);
+                words = hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0);
+            }
+        }
+        const uint32_t my2 = (uint32_t)words | ((n > 0 ? 1u : 0u) << 16);
+        uint32_t incl2 = my2;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, incl2, dd);
+            if (lane >= dd) incl2 += t;
+        }
+        if (lane == 31) s_w2[warp] = incl2;
+        __syncthreads();
+        uint32_t wo2 = 0, tot2 = 0;
+#pragma unroll
+        for (int w = 0; w < C::WARPS; ++w) {
+            const uint32_t x = s_w2[w];
+            if (w < warp) wo2 += x;
+            tot2 += x;
+        }
+        const int T = (int)(tot2 & 0xffffu); // words of the tile
+        if (T > C::OCAP) slow = 1; // (uniform) the tile does not fit the staging area
+        else if (!EMIT) {
+            if (tid == 0) ta.tile_words[tile] = T;
+            return;
+        } else {
+            // the tile is staged at the word offset its first word has inside a 16-byte line of the output, so that it leaves
+            // with aligned 16-byte loads and stores
+            uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
+            const int sh = (int)((reinterpret_cast<uintptr_t>(gout) >> 2) & 3);
+            const uint32_t ex2 = wo2 + incl2 - my2;
+            const int Wj = (int)(ex2 & 0xffffu); // first word of list `tid` inside the tile
+            uint8_t *sb = reinterpret_cast<uint8_t *>(s_out);
+            if (tid < nl) {
+                uint32_t *lw = s_out + sh + Wj;
+                if (hdr) lw[0] = ta.hdr_mode == 1 ? (uint32_t)n : 0u;
+                if (bytes > 0) lw[hdr + ((bytes - 1) >> 2)] = 0u; // the zero padding of the last payload word
+                if (a.app) lw[words - 1] = 0u;
+                if (n > 0) s_ob[(ex2 >> 16) + 1] = 4 * (sh + Wj + hdr) - bplo;
+                a.out_off[l0 + tid] = 4 * (gbase + Wj);
+            } else if (tid == nl)
+                s_ob[(ex2 >> 16) + 1] = 4 * (C::OCAP + 4 + C::SCR) - bplo; // the phantom list past the tile's end: its bytes go to scratch
+            if (tid == 0) s_ob[0] = 4 * (C::OCAP + 4); // ... and so do the phantom bytes before the tile's first value
+            __syncthreads(); // framing words and payload addresses are in place
+            // ---- pass B: bytes (VariableByte.java:44-68: 7-bit groups, low group first, bit 7 on the LAST byte)
+            if (vm) {
+                const int *obp = s_ob + (ex1 >> 16); // the list this thread's first position belongs to ([0]: leading phantoms)
+                int adj = *obp;
+                int addr = adj + (int)(ex1 & 0xffffu);
+                if (!gen) {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k) {
+                        if ((fw >> k) & 1u) { ++obp; const int t = *obp; addr += t - adj; adj = t; }
+                        const bool two = (m2 >> k) & 1u;
+                        uint32_t b0 = d[k] & 127u;
+                        if (!two) b0 = d[k] | 128u;
+                        sb[addr] = (uint8_t)b0;
+                        if (two) sb[addr + 1] = (uint8_t)((d[k] + 0x4000u) >> 7);
+                        addr += 1;
+                        if (two) addr += 1;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VPT; ++k) {
+                        if ((fw >> k) & 1u) { ++obp; const int t = *obp; addr += t - adj; adj = t; }
+                        const int len = (int)((nib[k / 16] >> (4 * (k % 16))) & 15u);
+                        uint32_t v = d[k];
+                        uint8_t *dst = sb + addr;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < len - 1) { dst[j] = (uint8_t)(v & 127u); v >>= 7; }
+                        dst[len - 1] = (uint8_t)(v | 128u);
+                        addr += len;
+                    }
+                }
+            }
+            __syncthreads(); // the bytes are in place
+            const uint32_t sel = a.app ? 0x0123u : 0x3210u;
+            uint32_t *gal = gout - sh; // 16-byte aligned; staged word i goes to gal[i], i in [sh, sh + T)
+            const int wend = sh + T;
+            for (int v = tid; 4 * v < wend; v += THREADS) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(s_out + 4 * v);
+                const uint4 o = make_uint4(__byte_perm(q.x, 0, sel), __byte_perm(q.y, 0, sel), __byte_perm(q.z, 0, sel), __byte_perm(q.w, 0, sel));
+                if (4 * v >= sh && 4 * v + 4 <= wend) *reinterpret_cast<uint4 *>(gal + 4 * v) = o;
+                else {
+                    if (4 * v + 0 >= sh && 4 * v + 0 < wend) gal[4 * v + 0] = o.x;
+                    if (4 * v + 1 >= sh && 4 * v + 1 < wend) gal[4 * v + 1] = o.y;
+                    if (4 * v + 2 >= sh && 4 * v + 2 < wend) gal[4 * v + 2] = o.z;
+                    if (4 * v + 3 >= sh && 4 * v + 3 < wend) gal[4 * v + 3] = o.w;
+                }
+            }
+            return;
+        }
+    }
+    // ---- a tile that does not fit: sizes (and streams) by the warp-per-list routines
+    const CodecTraits tr = codec_traits(a.codec);
+    auto list_off = [&](int64_t l) -> int64_t { return a.list_off ? a.list_off[l] : l * a.uniform_len; };
+    bool page = false;
+    if (tid < nl) page = ta.page > 0 && my_n >= ta.page;
+    const int has_page = __syncthreads_or(page);
+    uint32_t *stage = s_out + 64 * warp;
+    int64_t *s_w64 = reinterpret_cast<int64_t *>(s_vals); // (the staging tile is scratch here: the lists' sizes in words)
+    if (has_page) {
+        if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
+    } else {
+        for (int j = warp; j < nl; j += C::WARPS) {
+            const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
+            const int64_t w = warp_short_list_encode<false>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, stage, lane);
+            if (lane == 0) s_w64[j] = w;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const long long wj = (!has_page && tid < nl) ? (long long)s_w64[tid] : 0;
+    long long incl = wj;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const long long t = __shfl_up_sync(kFull, incl, dd);
+        if (lane >= dd) incl += t;
+    }
+    if (lane == 31) s_red[warp] = incl;
+    __syncthreads();
+    long long wo = 0, T = 0;
+#pragma unroll
+    for (int w = 0; w < C::WARPS; ++w) {
+        const long long x = s_red[w];
+        if (w < warp) wo += x;
+        T += x;
+    }
+    if (!EMIT) {
+        if (tid == 0) ta.tile_words[tile] = T;
+        return;
+    }
+    const long long wbase = wo + incl - wj;
+    if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + wbase);
+    __syncthreads(); // (s_w64 is overwritten next)
+    if (tid < nl) s_w64[tid] = wbase;
+    __syncthreads();
+    if (!has_page) {
+        uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
+        for (int j = warp; j < nl; j += C::WARPS) {
+            const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
+            warp_short_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_w64[j], a.app}, a.app, stage, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// exclusive scan of the tiles' word counts in place (one CTA: a few ten thousand tiles); the total in bytes goes to *total and
+// to out_off[nlists], flag 1 when the caller's buffer is too small for it
+__global__ void __launch_bounds__(1024) k_vb4_scan(int64_t *tile_words, int64_t nb, int64_t *total, int64_t *out_off_end, int64_t cap, int *err)
+{
+    __shared__ long long s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t per = (nb + 1023) / 1024, i0 = min(nb, tid * per), i1 = min(nb, i0 + per);
+    long long sum = 0;
+    {
+        int64_t i = i0;
+        for (; i + 8 <= i1; i += 8) { // (independent loads: one round trip per eight)
+            long long x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = tile_words[i + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += x[k];
+        }
+        for (; i < i1; ++i) sum += tile_words[i];
+    }
+    long long incl = sum;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const long long t = __shfl_up_sync(kFull, incl, dd);
+        if (lane >= dd) incl += t;
     }
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    uint32_t off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t x = s_w[w];
-        if (w < warp) off += x;
+    long long wo = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+        const long long x = s_w[w];
+        if (w < warp) wo += x;
         tot += x;
     }
-    *total = tot;
-    return off + incl - v;
-}
-
-// ---- flat encoder, second cut.  What the first one (8 values per thread, 32-wide look-back) taught, by ncu
-// (profiles/r2/ncu_flat_vb_v1.txt): 144 thread instructions per value, most of them per-TILE work spread over too few
-// values, and 61 % of the stall samples at the barrier behind the look-back -- with a thousand small tiles in flight in
-// lock step and none of them holding an inclusive prefix, the walk is long and the frontier of known prefixes advances
-// by 32 tiles per L2 round trip.  Hence: 32 values per thread (a tile is 4 096 window positions, ~40 lists), values
-// staged once in shared memory (16-byte cp.async into a 36-word row per thread: conflict-free LDS.128), the aggregate
-// published right after the scan, and a look-back in which ALL 128 threads poll two state words each: 256 tiles per
-// round trip, requested before the bytes are written and consumed after.
-constexpr int VE_THREADS = 128;
-constexpr int VE_VPT = 32;                     // window positions per thread
-constexpr int VE_SPAN = VE_THREADS * VE_VPT;   // 4 096
-constexpr int VE_ROW = VE_VPT + 4;             // padded row of a thread's values in shared memory (words)
-constexpr int VE_MAXL = 64;                    // lists per tile (two lanes-rounds of one warp keep the books)
-constexpr int VE_OCAP = 2816;                  // staged output words per tile
-
-__global__ void __launch_bounds__(VE_THREADS, 6) k_vbf_encode(const FastEncArgs a)
-{
-    __shared__ __align__(16) uint32_t s_vals[VE_THREADS * VE_ROW];
-    __shared__ uint32_t s_out[VE_OCAP];
-    __shared__ uint32_t s_flag[VE_THREADS];   // bit k of word t: a non-empty list starts at window position 32 t + k
-    __shared__ int64_t s_off[2][VE_MAXL + 1]; // list offsets of this tile and of the next one
-    __shared__ int s_rel[VE_MAXL + 1];        // list starts as window positions
-    __shared__ int s_ps[VE_MAXL + 2];         // flat byte prefix at the first value of the r-th NON-EMPTY list; [count] = total
-    __shared__ int s_ob[VE_MAXL];             // r-th non-empty list: byte address of its payload in s_out minus s_ps[r]
-    __shared__ int s_wb[VE_MAXL + 1];         // first output word of each list inside the tile (list order); [nl] = total
-    __shared__ uint32_t s_scan[VE_THREADS / 32];
-    __shared__ long long s_red[VE_THREADS / 32];
-    __shared__ int s_slow, s_ne;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const CodecTraits tr = codec_traits(a.codec);
-    uint8_t *sb = reinterpret_cast<uint8_t *>(s_out);
-
-    auto tile_lists = [&](long long tile) -> int {
-        return tile < a.nbatches ? (int)min((long long)a.lists_per_batch, (long long)a.nlists - tile * a.lists_per_batch) : 0;
-    };
-    auto load_off = [&](long long tile) -> int64_t { // this thread's entry of a tile's offsets (0 past the end)
-        if (tile >= a.nbatches || tid > tile_lists(tile)) return 0;
-        const int64_t l = tile * a.lists_per_batch + tid;
-        return a.list_off ? a.list_off[l] : l * a.uniform_len;
-    };
-    // Tiles are assigned statically, tile = blockIdx.x + it * gridDim.x, and the grid is sized to be fully resident
-    // (codec_fast_encode asks the occupancy calculator): every predecessor a look-back can wait for is the CURRENT tile
-    // of a running CTA, at the same stage as this one -- handing tickets out ahead of time (to prefetch) makes tiles
-    // wait for predecessors nobody has started yet and serialises the kernel (measured: 1.8 ms instead of 0.5).
-    const long long G = gridDim.x;
-    { const int64_t o0 = load_off(blockIdx.x); if (tid <= VE_MAXL) s_off[0][tid] = o0; }
-    __syncthreads();
-
-    for (int it = 0;; ++it) {
-        const long long tile = blockIdx.x + it * G;
-        if (tile >= a.nbatches) break;
-        const int64_t *off = s_off[it & 1];
-        const int64_t l0 = tile * a.lists_per_batch;
-        const int nl = tile_lists(tile);
-        // ---- a request that need not wait: the next tile's offsets
-        const int64_t off_next = load_off(tile + G);
-        const int64_t base = off[0], nv = off[nl] - base;
-        const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3); // the window starts on a 16-byte boundary
-        const int64_t span = a0 + nv;
-        bool bad = span > VE_SPAN || nv < 0;
-        if (tid < nl) {
-            const int64_t n = off[tid + 1] - off[tid];
-            bad = bad || n < 0 || (tr.fastpfor && n >= tr.fp_block);
+    long long run = wo + incl - sum;
+    {
+        int64_t i = i0;
+        for (; i + 8 <= i1; i += 8) {
+            long long x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = tile_words[i + k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { tile_words[i + k] = run; run += x[k]; }
         }
-        const int p0 = VE_VPT * tid;
-        uint32_t *row = s_vals + tid * VE_ROW;
-        if (!(span > VE_SPAN || nv < 0)) {
-            const uint32_t *wp = a.vals + base - a0;
-#pragma unroll
-            for (int c = 0; c < VE_VPT / 4; ++c)
-                if (p0 + 4 * c < span) cp_async16(row + 4 * c, wp + p0 + 4 * c);
-            if (tid <= nl) s_rel[tid] = a0 + (int)(off[tid] - base);
-        }
-        cp_async_commit();
-        s_flag[tid] = 0;
-        const int slow = __syncthreads_or(bad);
-        long long T = 0; // words of the tile
-        if (!slow) {
-            // ---- list starts (non-empty lists only: a value belongs to the LAST list that starts at its position)
-            if (tid < nl && s_rel[tid + 1] > s_rel[tid]) atomicOr(&s_flag[s_rel[tid] >> 5], 1u << (s_rel[tid] & 31));
-            cp_async_wait<0>();
-            __syncthreads(); // values and start bits are in place
-            const uint32_t fw = s_flag[tid];
-            // valid positions of this thread: [a0, span) intersected with [p0, p0 + 32)
-            const int lo = a0 - p0, hi = (int)(span - p0);
-            const uint32_t vm = (hi <= 0 || lo >= 32) ? 0u : ((hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & (lo <= 0 ? 0xffffffffu : ~((1u << lo) - 1u)));
-            uint32_t prev0 = 0;
-            if (tid > 0 && vm) prev0 = s_vals[(tid - 1) * VE_ROW + VE_VPT - 1];
-            // ---- pass A: byte lengths (4 bits each, 8 values per word), warp-uniform "every value takes <= 2 bytes"
-            uint32_t lens[4], wor = 0;
-            {
-                uint32_t prev = prev0;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint4 q0 = *reinterpret_cast<const uint4 *>(row + 8 * c), q1 = *reinterpret_cast<const uint4 *>(row + 8 * c + 4);
-                    const uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                    uint32_t l = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int pk = 8 * c + k;
-                        const uint32_t d = (a.delta && !((fw >> pk) & 1u)) ? x[k] - prev : x[k];
-                        prev = x[k];
-                        const uint32_t ok = (vm >> pk) & 1u;
-                        wor |= ok ? d : 0u;
-                        const uint32_t len = ok ? (uint32_t)vb_len(d) : 0u;
-                        l |= len << (4 * k);
-                    }
-                    lens[c] = l;
-                }
-            }
-            int nbytes = 0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) nbytes += nib_prefix(lens[c], 8);
-            uint32_t tot;
-            const uint32_t ex = vf_block_scan128((uint32_t)nbytes | ((uint32_t)__popc(fw) << 16), s_scan, &tot);
-            const int B0 = (int)(ex & 0xffffu), L0 = (int)(ex >> 16);
-            {
-                uint32_t f = fw;
-                int r = L0;
-                while (f) {
-                    const int k = __ffs(f) - 1;
-                    f &= f - 1;
-                    int b = B0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) b += c < (k >> 3) ? nib_prefix(lens[c], 8) : (c == (k >> 3) ? nib_prefix(lens[c], k & 7) : 0);
-                    s_ps[r++] = b;
-                }
-            }
-            if (tid == VE_THREADS - 1) { s_ps[tot >> 16] = (int)(tot & 0xffffu); s_ne = (int)(tot >> 16); }
-            __syncthreads();
-            // ---- per-list sizes and framing (one warp, two lists per lane): IntCompressor writes n first, Composition the
-            // 0 marker when FastPFOR took nothing, the loader's framing one trailing zero word (LoadPortfolios.java:622)
-            if (warp == 0) {
-                int run_w = 0, run_r = 0;
-                bool fits = true;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 32 * h + lane;
-                    const int n = j < nl ? s_rel[j + 1] - s_rel[j] : 0;
-                    const unsigned ne = __ballot_sync(kFull, n > 0);
-                    const int r = run_r + __popc(ne & ((1u << lane) - 1u));
-                    const int bytes = n > 0 ? s_ps[r + 1] - s_ps[r] : 0;
-                    const int hdr = j < nl ? (tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0)) : 0;
-                    const int words = j < nl ? hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0) : 0;
-                    int incl = words;
-#pragma unroll
-                    for (int dd = 1; dd < 32; dd <<= 1) {
-                        const int t = __shfl_up_sync(kFull, incl, dd);
-                        if (lane >= dd) incl += t;
-                    }
-                    const int wb = run_w + incl - words;
-                    const int tot_w = run_w + __shfl_sync(kFull, incl, 31);
-                    fits = fits && tot_w <= VE_OCAP;
-                    if (j < nl) s_wb[j] = wb;
-                    if (tot_w <= VE_OCAP && j < nl) {
-                        if (hdr) s_out[wb] = tr.sk ? (uint32_t)n : 0u;
-                        if (bytes > 0) s_out[wb + hdr + ((bytes - 1) >> 2)] = 0u; // the zero padding of the last payload word
-                        if (a.app) s_out[wb + words - 1] = 0u;
-                        if (n > 0) s_ob[r] = 4 * (wb + hdr) - s_ps[r];
-                    }
-                    run_w = tot_w;
-                    run_r += __popc(ne);
-                }
-                T = run_w;
-                if (lane == 0) {
-                    s_wb[nl] = (int)T;
-                    s_slow = fits ? 0 : 1;
-                    if (fits) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
-                }
-            }
-            __syncthreads();
-            if (!s_slow) {
-                T = s_wb[nl];
-                // ---- look-back, first round requested now (256 predecessors: two state words per thread), consumed after
-                // the bytes are written
-                const long long i0 = tile - 1 - tid, i1 = tile - 1 - VE_THREADS - tid;
-                uint64_t st0 = i0 >= 0 ? ld_relaxed_u64(a.state + i0) : kLbInc; // before the first tile: an inclusive prefix of 0
-                uint64_t st1 = i1 >= 0 ? ld_relaxed_u64(a.state + i1) : kLbInc;
-                // ---- pass B: bytes (VariableByte.java:44-68: 7-bit groups, low group first, bit 7 on the LAST byte)
-                {
-                    const bool small = __reduce_or_sync(kFull, wor) < 16384u; // warp-uniform: one or two bytes per value
-                    int li = L0 - 1, ob = li >= 0 ? s_ob[li] : 0, bo = B0;
-                    uint32_t prev = prev0;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint4 q0 = *reinterpret_cast<const uint4 *>(row + 8 * c), q1 = *reinterpret_cast<const uint4 *>(row + 8 * c + 4);
-                        const uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                        const uint32_t f8 = (fw >> (8 * c)) & 0xffu, l8 = lens[c];
-                        if (small) { // warp-uniform: one or two bytes per value, list starts by predication
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const bool st = (f8 >> k) & 1u;
-                                if (st) ob = s_ob[++li];
-                                const uint32_t d = (a.delta && !st) ? x[k] - prev : x[k];
-                                prev = x[k];
-                                const int len = (int)((l8 >> (4 * k)) & 15u);
-                                if (len) {
-                                    uint8_t *dst = sb + ob + bo;
-                                    dst[0] = (uint8_t)((d & 127u) | (len == 1 ? 128u : 0u));
-                                    if (len == 2) dst[1] = (uint8_t)((d >> 7) | 128u);
-                                    bo += len;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const bool st = (f8 >> k) & 1u;
-                                if (st) ob = s_ob[++li];
-                                uint32_t d = (a.delta && !st) ? x[k] - prev : x[k];
-                                prev = x[k];
-                                const int len = (int)((l8 >> (4 * k)) & 15u);
-                                if (len) {
-                                    uint8_t *dst = sb + ob + bo;
-                                    for (int j = 0; j < len - 1; ++j) { dst[j] = (uint8_t)(d & 127u); d >>= 7; }
-                                    dst[len - 1] = (uint8_t)(d | 128u);
-                                    bo += len;
-                                }
-                            }
-                        }
-                    }
-                }
-                // ---- the tile's place in the output: block-wide look-back, 256 predecessors per round
-                long long gbase = 0;
-                if (tile > 0) {
-                    for (long long jbase = tile - 1;; jbase -= 2 * VE_THREADS) {
-                        // wait for this thread's two words (aggregates are published early: rarely a wait at all)
-                        while ((st0 >> 62) == 0) { __nanosleep(20); st0 = ld_relaxed_u64(a.state + (jbase - tid)); }
-                        while ((st1 >> 62) == 0) { __nanosleep(20); st1 = ld_relaxed_u64(a.state + (jbase - VE_THREADS - tid)); }
-                        // nearest inclusive prefix among the 256 (distance = tid, or 128 + tid)
-                        const unsigned b0 = __ballot_sync(kFull, (st0 >> 62) == 2), b1 = __ballot_sync(kFull, (st1 >> 62) == 2);
-                        // distance of the nearest inclusive one in this warp's two lane-groups (or a large number)
-                        const int d0 = b0 ? 32 * warp + __ffs(b0) - 1 : 1 << 20;
-                        const int d1 = b1 ? VE_THREADS + 32 * warp + __ffs(b1) - 1 : 1 << 20;
-                        if (lane == 0) s_red[warp] = d0 < d1 ? d0 : d1;
-                        __syncthreads();
-                        int dmin = 1 << 20;
-#pragma unroll
-                        for (int w = 0; w < VE_THREADS / 32; ++w) dmin = min(dmin, (int)s_red[w]);
-                        __syncthreads();
-                        long long v = (tid <= dmin ? (long long)(st0 & kLbMask) : 0) + (VE_THREADS + tid <= dmin ? (long long)(st1 & kLbMask) : 0);
-#pragma unroll
-                        for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(kFull, v, dd);
-                        if (lane == 0) s_red[warp] = v;
-                        __syncthreads();
-#pragma unroll
-                        for (int w = 0; w < VE_THREADS / 32; ++w) gbase += s_red[w];
-                        __syncthreads();
-                        if (dmin < (1 << 20)) break;
-                        const long long n0 = jbase - 2 * VE_THREADS - tid, n1 = n0 - VE_THREADS;
-                        st0 = n0 >= 0 ? ld_relaxed_u64(a.state + n0) : kLbInc;
-                        st1 = n1 >= 0 ? ld_relaxed_u64(a.state + n1) : kLbInc;
-                    }
-                    if (tid == 0) st_relaxed_u64(a.state + tile, kLbInc | (uint64_t)(gbase + T));
-                } else
-                    __syncthreads(); // (the bytes of tile 0 are in place)
-                if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
-                if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
-                if (4 * (gbase + T) > a.cap) { // caller's buffer too small: report, write nothing
-                    if (tid == 0) atomicMax(a.err, 1);
-                } else {
-                    uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
-                    const uint32_t sel = a.app ? 0x0123u : 0x3210u;
-                    for (int i = tid; i < (int)T; i += VE_THREADS) gout[i] = __byte_perm(s_out[i], 0, sel);
-                }
-                if (tid <= VE_MAXL) s_off[(it + 1) & 1][tid] = off_next;
-                __syncthreads();
-                continue;
-            }
-        }
-        cp_async_wait<0>();
-        // ---- a tile that does not fit: sizes, look-back and streams by the warp-per-list routines
-        bool page = false;
-        if (tid < nl) page = tr.fastpfor && off[tid + 1] - off[tid] >= tr.fp_block;
-        const int has_page = __syncthreads_or(page);
-        uint32_t *stage = s_out + 64 * warp;
-        if (has_page) {
-            if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
-        } else {
-            for (int j = warp; j < nl; j += VE_THREADS / 32) {
-                const int64_t w = warp_short_list_encode<false>(tr, ValSeq{a.vals + off[j], a.delta}, off[j + 1] - off[j],
-                                                                WordSink{nullptr, a.app}, a.app, stage, lane);
-                if (lane == 0) s_ob[j] = (int)w; // (the slow path reuses s_ob for the lists' sizes in words)
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            long long run = 0;
-            for (int h = 0; h < 2; ++h) {
-                const int j = 32 * h + lane;
-                long long w = (!has_page && j < nl) ? (long long)s_ob[j] : 0;
-                long long incl = w;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const long long t = __shfl_up_sync(kFull, incl, dd);
-                    if (lane >= dd) incl += t;
-                }
-                if (j < nl) s_wb[j] = (int)(run + incl - w);
-                run += __shfl_sync(kFull, incl, 31);
-            }
-            T = run;
-            if (lane == 0) st_relaxed_u64(a.state + tile, (tile == 0 ? kLbInc : kLbAgg) | (uint64_t)T);
-            const long long b = lookback_warp(a.state, tile, T, lane);
-            if (lane == 0) { s_red[0] = b; s_wb[nl] = (int)T; }
-        }
-        __syncthreads();
-        {
-            const long long gbase = s_red[0];
-            T = s_wb[nl];
-            if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + s_wb[tid]);
-            if (tid == 0 && tile == a.nbatches - 1) { *a.total = 4 * (gbase + T); a.out_off[a.nlists] = 4 * (gbase + T); }
-            if (4 * (gbase + T) > a.cap) {
-                if (tid == 0) atomicMax(a.err, 1);
-            } else if (!has_page) {
-                uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
-                for (int j = warp; j < nl; j += VE_THREADS / 32) {
-                    const int64_t beg = off[j], n = off[j + 1] - beg;
-                    warp_short_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_wb[j], a.app}, a.app, stage, lane);
-                    __syncwarp();
-                }
-            }
-        }
-        if (tid <= VE_MAXL) s_off[(it + 1) & 1][tid] = off_next;
-        __syncthreads();
+        for (; i < i1; ++i) { const long long x = tile_words[i]; tile_words[i] = run; run += x; }
+    }
+    if (tid == 0) {
+        *total = 4 * tot;
+        *out_off_end = 4 * tot;
+        if (4 * tot > cap) atomicMax(err, 1);
     }
 }
 
@@ -3347,6 +3401,9 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     return (int)g;
 }
 
+constexpr int VB4_THREADS = 128, VB4_VPT = 32;
+using VB4 = V4<VB4_THREADS, VB4_VPT>;
+
 // lists per tile of the flat VariableByte kernels: `target` values per tile on average (the tile's window holds
 // VF_SPAN values / VF_WSPAN words; a tile that overflows is done by the warp-per-list routines inside the kernel)
 static int vbf_lists_per_tile(int64_t total_vals, int64_t nlists, double target, int maxl)
@@ -3427,7 +3484,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         if (pass == 1 && !batched) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; }
         // lists that are all VariableByte (FastPFOR / FastPFOR128 below one block, VariableByte alone) take the flat kernel
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
-        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.86 * VE_SPAN, VE_MAXL) : 32)
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.93 * VB4::SPAN, VB4::MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_vals, nlists);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
@@ -3444,11 +3501,13 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
             KScope ks(ctx, MCP_K_ENCODE);
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
-                int per_sm = 0;
-                MCP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vbf_encode, VE_THREADS, 0));
-                if (per_sm < 1) return fail(ctx, MCP_E_CUDA, "k_vbf_encode does not fit an SM");
-                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * per_sm;
-                k_vbf_encode<<<(unsigned)(a.nbatches < res ? a.nbatches : res), VE_THREADS, 0, ctx->stream>>>(a);
+                // size pass, scan of the tiles' word counts (in place, in the state words), emit pass
+                TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (tr.fastpfor ? 2 : 0), tr.fastpfor ? tr.fp_block : 0};
+                if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                else k_vb4_tile<VB4_THREADS, VB4_VPT, false, false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                k_vb4_scan<<<1, 1024, 0, ctx->stream>>>(ta.tile_words, a.nbatches, a.total, a.out_off + a.nlists, a.cap, a.err);
+                if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                else k_vb4_tile<VB4_THREADS, VB4_VPT, false, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
             } else if (pass == 0) {
                 const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
                 k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);

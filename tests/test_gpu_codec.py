@@ -25,6 +25,9 @@ def batch_of(matrix):
     return vals, off
 
 
+FLAT_DEFAULT = 0  # the library's default for option flat_codec
+
+
 def test_kat_through_the_c_abi(ctx):
     blob = base64.b64decode(KAT_B64)
     assert ctx.get_compressed_instruments(N.CODEC_BP32_VB, KAT_INTS) == blob
@@ -35,16 +38,19 @@ def test_kat_through_the_c_abi(ctx):
     assert doc["algo"] == "bpacking+variablebyte" and doc["compressedByteSize"] == 36 and doc["uncompressedIntegerSize"] == 17
 
 
-@pytest.fixture(params=[(1, 2), (1, 1), (1, 0), (0, 0)], ids=["shortlist-everywhere", "default", "batched", "warp-per-list"])
+@pytest.fixture(params=[(1, 2, 0), (1, 1, 0), (1, 0, 0), (0, 0, 0), (1, 2, 1)],
+                ids=["shortlist-everywhere", "default", "batched", "warp-per-list", "flat"])
 def codec_ctx(ctx, request):
-    """The three kernel families behind the codec ABI: the thread-per-list kernels (lists averaging <= 144 values), the
-    batched single-pass kernels (thread per block) and the warp-per-list size/scan/emit kernels that handle everything
-    else."""
+    """The kernel families behind the codec ABI: the thread-per-list kernels (lists averaging <= 144 values), the
+    batched single-pass kernels (thread per block), the warp-per-list size/scan/emit kernels that handle everything
+    else, and the flat (thread-per-16-values) kernels for short lists that are all VariableByte."""
     ctx.set_option("fast_codec", request.param[0])
     ctx.set_option("short_list_codec", request.param[1])
+    ctx.set_option("flat_codec", request.param[2])
     yield ctx
     ctx.set_option("fast_codec", 1)
     ctx.set_option("short_list_codec", 1)
+    ctx.set_option("flat_codec", FLAT_DEFAULT)
 
 
 @pytest.mark.parametrize("codec", cases.ALL_CODECS, ids=cases.NAMES)
