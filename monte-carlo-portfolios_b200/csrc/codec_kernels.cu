@@ -2669,6 +2669,13 @@ struct V4 {
     __device__ static __forceinline__ int slot(int t, int c) { return t * VPT + 4 * (VPT == 16 ? (c ^ ((t >> 1) & 3)) : (c ^ (t & 7))); }
 };
 
+__device__ __forceinline__ long long warp_sum_i64(long long v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    return v;
+}
+
 // sum of the nibbles of x below nibble k (k <= 16)
 __device__ __forceinline__ int nib_prefix64(uint64_t x, int k)
 {
@@ -2770,10 +2777,16 @@ __global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
                     prev = x[k];
                 }
             }
-            if (vm != full) { // phantom positions (before the tile's first value, past its last): zeros, one byte each
+            // phantom positions (before the tile's first value: at most three; past its last): zeros, one byte each
+            if (lo > 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < lo) d[k] = 0u;
+            }
+            if (hi < VPT) {
 #pragma unroll
                 for (int k = 0; k < VPT; ++k)
-                    if (!((vm >> k) & 1u)) d[k] = 0u;
+                    if (k >= hi) d[k] = 0u;
             }
 #pragma unroll
             for (int k = 0; k < VPT; ++k) wor |= d[k];
@@ -2799,6 +2812,38 @@ __global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
         }
         s_m2[tid] = m2;
         s_gen[tid] = gen ? 1 : 0;
+        if (!EMIT && VPT == 32) {
+            // the size pass needs no prefixes: when every value of the tile takes one or two bytes (the "two bytes" masks
+            // are then a bit vector over the window), a list's bytes are its length plus a popcount over its range
+            if (!__syncthreads_or(gen)) {
+                int words = 0;
+                if (tid < nl) {
+                    const int n = (int)my_n;
+                    int bytes = n;
+                    if (n > 0) {
+                        const int plo = s_rel[tid], phi = plo + n, wlo = plo >> 5, whi = (phi - 1) >> 5;
+                        for (int w = wlo; w <= whi; ++w) {
+                            uint32_t m = s_m2[w];
+                            if (w == wlo) m &= 0xffffffffu << (plo & 31);
+                            if (w == whi && (phi & 31)) m &= (1u << (phi & 31)) - 1u;
+                            bytes += __popc(m);
+                        }
+                    }
+                    const int hdr = ta.hdr_mode == 1 ? 1 : (ta.hdr_mode == 2 && n > 0 ? 1 : 0);
+                    words = hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0);
+                }
+                words = __reduce_add_sync(kFull, words);
+                if (lane == 0) s_w2[warp] = (uint32_t)words;
+                __syncthreads();
+                if (tid == 0) {
+                    long long T = 0;
+#pragma unroll
+                    for (int w = 0; w < C::WARPS; ++w) T += s_w2[w];
+                    ta.tile_words[tile] = T;
+                }
+                return;
+            }
+        }
         const uint32_t my1 = (uint32_t)nbytes | ((uint32_t)__popc(fw) << 16);
         uint32_t incl1 = my1;
 #pragma unroll
@@ -2992,50 +3037,44 @@ __global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
     }
 }
 
-// exclusive scan of the tiles' word counts in place (one CTA: a few ten thousand tiles); the total in bytes goes to *total and
-// to out_off[nlists], flag 1 when the caller's buffer is too small for it
+// exclusive scan of the tiles' word counts in place (one CTA: a few ten thousand tiles; a warp per contiguous segment, 32
+// counts per round, coalesced); the total in bytes goes to *total and to out_off[nlists], flag 1 when the caller's buffer is
+// too small for it
 __global__ void __launch_bounds__(1024) k_vb4_scan(int64_t *tile_words, int64_t nb, int64_t *total, int64_t *out_off_end, int64_t cap, int *err)
 {
     __shared__ long long s_w[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t per = (nb + 1023) / 1024, i0 = min(nb, tid * per), i1 = min(nb, i0 + per);
+    const int64_t per = ((nb + 31) / 32 + 31) & ~(int64_t)31, i0 = min(nb, warp * per), i1 = min(nb, i0 + per);
     long long sum = 0;
-    {
-        int64_t i = i0;
-        for (; i + 8 <= i1; i += 8) { // (independent loads: one round trip per eight)
-            long long x[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = tile_words[i + k];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sum += x[k];
-        }
-        for (; i < i1; ++i) sum += tile_words[i];
-    }
-    long long incl = sum;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) {
-        const long long t = __shfl_up_sync(kFull, incl, dd);
-        if (lane >= dd) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
+#pragma unroll 4
+    for (int64_t i = i0 + lane; i < i1; i += 32) sum += tile_words[i];
+    sum = warp_sum_i64(sum);
+    if (lane == 0) s_w[warp] = sum;
     __syncthreads();
-    long long wo = 0, tot = 0;
+    long long run = 0, tot = 0;
     for (int w = 0; w < 32; ++w) {
         const long long x = s_w[w];
-        if (w < warp) wo += x;
+        if (w < warp) run += x;
         tot += x;
     }
-    long long run = wo + incl - sum;
-    {
-        int64_t i = i0;
-        for (; i + 8 <= i1; i += 8) {
-            long long x[8];
+    for (int64_t i = i0; i < i1; i += 128) { // four rounds' loads in flight
+        long long x[4], incl[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = tile_words[i + k];
+        for (int k = 0; k < 4; ++k) x[k] = i + 32 * k + lane < i1 ? tile_words[i + 32 * k + lane] : 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { tile_words[i + k] = run; run += x[k]; }
+        for (int k = 0; k < 4; ++k) {
+            incl[k] = x[k];
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const long long t = __shfl_up_sync(kFull, incl[k], dd);
+                if (lane >= dd) incl[k] += t;
+            }
         }
-        for (; i < i1; ++i) { const long long x = tile_words[i]; tile_words[i] = run; run += x; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + 32 * k + lane < i1) tile_words[i + 32 * k + lane] = run + incl[k] - x[k];
+            run += __shfl_sync(kFull, incl[k], 31);
+        }
     }
     if (tid == 0) {
         *total = 4 * tot;
