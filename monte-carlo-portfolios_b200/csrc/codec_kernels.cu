@@ -2564,76 +2564,6 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
 //           prefix sums minus the sum at the list's start (Delta.inverseDelta), two STG.128 per thread.
 // A tile that does not fit (window, staging area) is done by the warp-per-list routines inside the same kernel; a
 // FastPFOR list of a whole block or more raises flag 2 and the host takes the batched kernels, as before.
-constexpr int VF_THREADS = 256;
-constexpr int VF_VPT = 8;                      // window positions per thread (encode)
-constexpr int VF_SPAN = VF_THREADS * VF_VPT;   // 2 048 window positions per tile
-constexpr int VF_MAXL = 32;                    // lists per tile: one warp keeps the per-list books
-constexpr int VF_OCAP = 2816;                  // staged output words per tile (encode)
-constexpr int VF_WSPAN = VF_THREADS * 4;       // compressed words per tile (decode)
-constexpr int VF_VCAP = 4 * VF_WSPAN + 8;      // staged values per tile (decode): at most four values end in a word
-
-__device__ __forceinline__ uint4 ldg128(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
-
-// exclusive block scan of one 32-bit word per thread (VF_THREADS threads); *total = the block's sum.  s_w: 8 words.
-__device__ __forceinline__ uint32_t vf_block_scan(uint32_t v, uint32_t *s_w, uint32_t *total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    uint32_t off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < VF_THREADS / 32; ++w) {
-        const uint32_t x = s_w[w];
-        if (w < warp) off += x;
-        tot += x;
-    }
-    *total = tot;
-    return off + incl - v;
-}
-
-// sum of the nibbles of x below nibble k
-__device__ __forceinline__ int nib_prefix(uint32_t x, int k)
-{
-    x = k >= 8 ? x : x & ((1u << (4 * k)) - 1u);
-    x = (x & 0x0f0f0f0fu) + ((x >> 4) & 0x0f0f0f0fu);
-    return (int)((x * 0x01010101u) >> 24);
-}
-
-// the tile's word base in the output: decoupled look-back by ONE warp over the per-tile state words (aggregate
-// published by the caller beforehand); publishes the inclusive prefix
-// `early` = this lane's predecessor state word as read at the tile's start (usually already published by now)
-__device__ __forceinline__ long long vf_lookback(uint64_t *state, int64_t tile, long long T, int lane, uint64_t early)
-{
-    long long base = 0;
-    if (tile > 0) {
-        bool first_round = true;
-        for (int64_t j = tile - 1;; j -= 32) {
-            const int64_t idx = j - lane;
-            uint64_t st = kLbInc; // before the first tile: an inclusive prefix of 0
-            if (idx >= 0) {
-                st = first_round ? early : 0;
-                while ((st >> 62) == 0) { st = ld_relaxed_u64(state + idx); if ((st >> 62) == 0) __nanosleep(32); }
-            }
-            first_round = false;
-            const unsigned inc = __ballot_sync(kFull, (st >> 62) == 2);
-            const int first = inc ? __ffs(inc) - 1 : 31; // nearest predecessor with an inclusive prefix
-            long long v = lane <= first ? (long long)(st & kLbMask) : 0;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-            base += v;
-            if (inc) break;
-        }
-        if (lane == 0) st_relaxed_u64(state + tile, kLbInc | (uint64_t)(base + T));
-    }
-    return base;
-}
-
 __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gsrc)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -3083,149 +3013,176 @@ __global__ void __launch_bounds__(1024) k_vb4_scan(int64_t *tile_words, int64_t 
     }
 }
 
-__global__ void __launch_bounds__(VF_THREADS, 4) k_vbf_decode(const FastDecArgs a, int64_t ntiles)
-{
-    __shared__ __align__(16) uint32_t s_val[VF_VCAP + 8];
-    __shared__ __align__(16) uint32_t s_words[2][VF_WSPAN]; // this tile's and the next tile's compressed words (cp.async)
-    __shared__ uint32_t s_wflag[VF_WSPAN / 32]; // bit w: a list's payload starts at window word w (the decoder restarts there)
-    __shared__ uint32_t s_hmask[VF_WSPAN / 32]; // bit w: window word w is an IntCompressor count word (not payload)
-    __shared__ int64_t s_inr[3][VF_MAXL + 1], s_oor[3][VF_MAXL + 1]; // rings: offsets of this tile, the next, the one after
-    __shared__ int s_wrel[VF_MAXL + 1], s_vrel[VF_MAXL + 1];
-    __shared__ uint32_t s_ss[VF_MAXL];          // flat sum of the staged values before the list's first one
-    __shared__ int s_cp[VF_THREADS + 1];        // values ending before each thread's first word
-    __shared__ uint32_t s_scan[VF_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const CodecTraits tr = codec_traits(a.codec);
-    const uint32_t sel = a.app ? 0x0123u : 0x3210u; // big-endian framing: words are swapped as they are read
-    const int64_t G = gridDim.x;
+// ---- flat VariableByte decoder.  One tile per CTA (a fixed number of whole lists: at most D4_WCAP compressed words, D4_VSPAN
+// values); no cross-CTA state -- the output offsets are an input.
+//   words   arrive by coalesced 16-byte cp.async; a thread owns 4g consecutive words (g = 1, 3 or 5, odd: its LDS.128 are
+//           conflict-free), sets IntCompressor count words to zero (their bytes are not VariableByte), swaps the loader's byte
+//           order, counts terminator bits and writes the clean words back;
+//   values  one block scan gives every thread the index of its first value; the byte walk (VariableByte.java:115-138)
+//           restarts at every list's first payload word (the Java decoder starts each list with v = 0, shift = 0) and scatters
+//           into a chunk-swizzled tile aligned like the output;
+//   Delta   a thread owns 32 consecutive values: running sums that restart at list starts, one segmented scan across threads
+//           (Delta.inverseDelta per list), rows written back; the tile leaves with coalesced 16-byte stores.
+// Every list must hold exactly its n values (terminator counts by list) or the call fails with MCP_E_FORMAT.  A tile that does
+// not fit is done by the warp-per-list routines inside the same kernel; a FastPFOR list of a whole block or more raises flag 2.
+constexpr int D4_THREADS = 128;
+constexpr int D4_WARPS = D4_THREADS / 32;
+constexpr int D4_VPT = 32;
+constexpr int D4_VSPAN = D4_THREADS * D4_VPT;   // 4 096 window positions of the output
+constexpr int D4_WCAP = 20 * D4_THREADS;        // 2 560 compressed words
+constexpr int D4_MAXL = D4_THREADS - 1;
 
-    auto tile_lists = [&](int64_t tile) -> int { return tile < ntiles ? (int)min((int64_t)a.lists_per_batch, a.nlists - tile * a.lists_per_batch) : 0; };
-    auto load_off = [&](int64_t tile, int64_t &io, int64_t &oo) {
-        io = 0; oo = 0;
-        if (tile < ntiles && tid <= tile_lists(tile)) { io = a.in_off[tile * a.lists_per_batch + tid]; oo = a.out_off[tile * a.lists_per_batch + tid]; }
-    };
-    auto request_words = [&](int64_t tile, const int64_t *in, uint32_t *buf) {
-        const int nl = tile_lists(tile);
-        if (nl > 0) {
-            const int64_t ib = in[0], nwords = (in[nl] - ib) >> 2;
-            const int aw = (int)((reinterpret_cast<uintptr_t>(a.in + ib) >> 2) & 3);
-            if ((ib & 3) == 0 && nwords >= 0 && aw + nwords <= VF_WSPAN) {
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(a.in + ib) - aw;
-                if (4 * tid < aw + nwords) cp_async16(buf + 4 * tid, wp + 4 * tid);
-            }
-        }
-        cp_async_commit();
-    };
-    {
-        int64_t i0, o0, i1, o1;
-        load_off(blockIdx.x, i0, o0);
-        load_off(blockIdx.x + G, i1, o1);
-        if (tid <= VF_MAXL) { s_inr[0][tid] = i0; s_oor[0][tid] = o0; s_inr[1][tid] = i1; s_oor[1][tid] = o1; }
-        __syncthreads();
-        request_words(blockIdx.x, s_inr[0], s_words[0]);
+// word of window position i of the output in the staging tile (rows of 32 values, 16-byte chunks permuted by the row index:
+// conflict-free for a thread reading its row and for the coalesced copy-out)
+__device__ __forceinline__ int d4_slot(int i) { return i ^ ((i >> 3) & 0x1c); }
+
+template <bool DELTA>
+__global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, int hdr_mode, int page)
+{
+    __shared__ __align__(16) uint32_t s_words[D4_WCAP];
+    __shared__ __align__(16) uint32_t s_val[D4_VSPAN];
+    __shared__ uint32_t s_wstart[D4_WCAP / 32]; // bit w: a list's payload starts at window word w (the decoder restarts there)
+    __shared__ uint32_t s_whdr[D4_WCAP / 32];   // bit w: window word w is an IntCompressor count word (not payload)
+    __shared__ uint32_t s_vstart[D4_VSPAN / 32 + 1]; // bit p: a non-empty list starts at window position p of the output
+    __shared__ int s_wrel[D4_THREADS + 1];
+    __shared__ int s_cp[D4_THREADS + 1];        // values ending before each thread's first word
+    __shared__ uint32_t s_w[D4_WARPS], s_sv[D4_WARPS], s_sf[D4_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sel = a.app ? 0x0123u : 0x3210u; // big-endian framing: words are swapped as they are read
+    const int64_t l0 = (int64_t)blockIdx.x * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    const int64_t *gin = a.in_off + l0, *goo = a.out_off + l0;
+    const int64_t ib = gin[0], ie = gin[nl], ob = goo[0], oe = goo[nl];
+    int64_t my_i0 = 0, my_i1 = 0, my_o0 = 0, my_o1 = 0;
+    if (tid <= nl) { my_i0 = gin[tid]; my_o0 = goo[tid]; my_i1 = gin[min(tid + 1, nl)]; my_o1 = goo[min(tid + 1, nl)]; }
+    const int64_t nwords = (ie - ib) >> 2, nvals = oe - ob;
+    const int aw = (int)((reinterpret_cast<uintptr_t>(a.in + ib) >> 2) & 3);   // 16-byte aligned window over the words
+    const int ao = (int)((reinterpret_cast<uintptr_t>(a.out + ob) >> 2) & 3);  // staging tile aligned like the output
+    int st = 0; // 1 = malformed, 2 = FastPFOR page, 4 = does not fit the tile
+    if (((ib | ie) & 3) != 0 || nwords < 0 || nvals < 0) st = 1;
+    else if (aw + nwords > D4_WCAP || ao + nvals > D4_VSPAN) st = 4;
+    if (tid < nl) {
+        const int64_t n = my_o1 - my_o0;
+        if (((my_i0 | my_i1) & 3) != 0 || my_i1 < my_i0 || n < 0 || my_i0 < ib || my_i1 > ie || my_o0 < ob || my_o1 > oe) st |= 1;
+        else if (page > 0 && n >= page) st |= 2;
     }
-    int it = -1;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += G) {
-        ++it;
-        const int64_t *s_in = s_inr[it % 3], *s_oo = s_oor[it % 3];
-        const uint32_t *wbuf = s_words[it & 1];
-        const int64_t l0 = tile * a.lists_per_batch;
-        const int nl = tile_lists(tile);
-        (void)l0;
-        __syncthreads(); // the previous tile's shared state has been consumed; its ring slots have been written
-        int64_t in2, oo2;
-        load_off(tile + 2 * G, in2, oo2);
-        request_words(tile + G, s_inr[(it + 1) % 3], s_words[(it + 1) & 1]);
-        // the ring slot of the tile after next is free from here on (its previous user was the tile before this one)
-        if (tid <= VF_MAXL) { s_inr[(it + 2) % 3][tid] = in2; s_oor[(it + 2) % 3][tid] = oo2; }
-        if (tid < VF_WSPAN / 32) { s_wflag[tid] = 0; s_hmask[tid] = 0; }
-        cp_async_wait<1>(); // this tile's words (requested one tile ago) have landed
-        __syncthreads();
-        const int64_t ib = s_in[0], ob = s_oo[0];
-        const int64_t nwords = (s_in[nl] - ib) >> 2, nvals = s_oo[nl] - ob;
-        const int aw = (int)((reinterpret_cast<uintptr_t>(a.in + ib) >> 2) & 3);   // 16-byte aligned window over the words
-        const int ao = (int)((reinterpret_cast<uintptr_t>(a.out + ob) >> 2) & 3);  // staging area aligned like the output
-        int st = 0; // 1 = malformed, 2 = FastPFOR page, 4 = does not fit the tile
-        if (tid < nl) {
-            const int64_t b0 = s_in[tid], b1 = s_in[tid + 1], n = s_oo[tid + 1] - s_oo[tid];
-            if (((b0 | b1) & 3) != 0 || b1 < b0 || n < 0) st = 1;
-            else if (tr.fastpfor && n >= tr.fp_block) st = 2;
-        }
-        if (((ib & 3) != 0) || nwords < 0 || nvals < 0) st |= 1;
-        else if (aw + nwords > VF_WSPAN || nvals > VF_VCAP - 8) st |= 4;
-        int tile_st = 0; // (__syncthreads_or returns a truth value, not the OR of the arguments)
-        if (__syncthreads_or(st)) tile_st = (__syncthreads_or(st & 1) ? 1 : 0) | (__syncthreads_or(st & 2) ? 2 : 0) | (__syncthreads_or(st & 4) ? 4 : 0);
-        if (tile_st & 1) { if (tid == 0) atomicMax(a.err, 3); continue; }
-        if (tile_st & 2) { if (tid == 0) atomicMax(a.err, 2); continue; }
-        if (tile_st & 4) {
-            for (int j = warp; j < nl; j += VF_THREADS / 32) {
-                const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + s_in[j]), a.app};
-                const bool ok = warp_short_list_decode(tr, src, (s_in[j + 1] - s_in[j]) >> 2, s_oo[j + 1] - s_oo[j], a.out + s_oo[j], a.delta, lane);
-                if (!ok && lane == 0) atomicMax(a.err, 4);
-                __syncwarp();
-            }
-            continue;
-        }
-        const uint32_t *wp = wbuf; // the window, staged
-        const int wspan = aw + (int)nwords;
-        // ---- per-list books: word / value extents, header checks, restart and count-word bits
-        bool ok = true;
-        if (tid <= nl) {
-            s_wrel[tid] = aw + (int)((s_in[tid] - ib) >> 2);
-            s_vrel[tid] = (int)(s_oo[tid] - ob);
-        }
-        if (tid < nl) {
-            const int w0 = aw + (int)((s_in[tid] - ib) >> 2), w1 = aw + (int)((s_in[tid + 1] - ib) >> 2);
-            const int n = (int)(s_oo[tid + 1] - s_oo[tid]);
-            const int hdr = tr.sk ? 1 : (tr.fastpfor && n > 0 ? 1 : 0);
-            if (w1 - w0 < hdr) ok = false;
-            else {
-                if (hdr) {
-                    const uint32_t h = __byte_perm(wp[w0], 0, sel);
-                    if (h != (tr.sk ? (uint32_t)n : 0u)) ok = false; // IntCompressor's n / Composition's marker (FastPFOR took nothing)
-                    if (tr.sk) atomicOr(&s_hmask[w0 >> 5], 1u << (w0 & 31));
-                }
-                if (w1 > w0 + hdr) atomicOr(&s_wflag[(w0 + hdr) >> 5], 1u << ((w0 + hdr) & 31));
-                else if (n > 0) ok = false;
-            }
-        }
-        // ---- this thread's 4 words
-        const int q0 = 4 * tid;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (q0 < wspan) q = *reinterpret_cast<const uint4 *>(wp + q0);
-        uint32_t pw = __shfl_up_sync(kFull, q.w, 1);
-        if (lane == 0) pw = (tid > 0 && q0 < wspan) ? wp[q0 - 1] : 0u;
-        __syncthreads(); // the bitmaps are in place
-        const uint32_t fl = (s_wflag[q0 >> 5] >> (q0 & 31)) & 15u, hm = (s_hmask[q0 >> 5] >> (q0 & 31)) & 15u;
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        int cnt = 0;
+    const int wspan = st ? 0 : aw + (int)nwords, vspan = st ? 0 : ao + (int)nvals;
+    if (tid < D4_WCAP / 32) { s_wstart[tid] = 0; s_whdr[tid] = 0; }
+    s_vstart[tid] = 0;
+    if (tid == 0) s_vstart[D4_VSPAN / 32] = 0;
+    {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(a.in + ib) - aw + 4 * tid;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool in = q0 + k >= aw && q0 + k < wspan && !((hm >> k) & 1u);
-            w[k] = in ? __byte_perm(w[k], 0, sel) : 0u;
-            cnt += __popc(w[k] & 0x80808080u);
+        for (int i = 0; i < D4_WCAP / 4 / D4_THREADS; ++i)
+            if (4 * (i * D4_THREADS + tid) < wspan) cp_async16(s_words + 4 * (i * D4_THREADS + tid), wp + 4 * i * D4_THREADS);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    int tile_st = 0; // (__syncthreads_or returns a truth value, not the OR of the arguments)
+    if (__syncthreads_or(st)) tile_st = (__syncthreads_or(st & 1) ? 1 : 0) | (__syncthreads_or(st & 2) ? 2 : 0) | (__syncthreads_or(st & 4) ? 4 : 0);
+    if (tile_st & 1) { if (tid == 0) atomicMax(a.err, 3); return; }
+    if (tile_st & 2) { if (tid == 0) atomicMax(a.err, 2); return; }
+    if (tile_st & 4) {
+        const CodecTraits tr = codec_traits(a.codec);
+        for (int j = warp; j < nl; j += D4_WARPS) {
+            const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + gin[j]), a.app};
+            const bool ok = warp_short_list_decode(tr, src, (gin[j + 1] - gin[j]) >> 2, goo[j + 1] - goo[j], a.out + goo[j], a.delta, lane);
+            if (!ok && lane == 0) atomicMax(a.err, 4);
+            __syncwarp();
         }
-        uint32_t tot;
-        const int V0 = (int)vf_block_scan((uint32_t)cnt, s_scan, &tot);
-        s_cp[tid] = V0;
-        if (tid == 0) s_cp[VF_THREADS] = (int)tot;
-        // ---- the 16-byte walk (VariableByte.java:115-138): v += (c & 127) << shift; a set bit 7 ends the value
-        {
-            uint32_t acc = 0;
-            int sh = 0;
-            if (!(fl & 1u) && q0 > aw && q0 < wspan) { // bytes of a value that began in the previous word
-                const bool pin = !((s_hmask[(q0 - 1) >> 5] >> ((q0 - 1) & 31)) & 1u);
-                const uint32_t pv = pin ? __byte_perm(pw, 0, sel) : 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t by = (pv >> (8 * e)) & 255u;
-                    if (by & 128u) { acc = 0; sh = 0; }
-                    else { acc += (by & 127u) << (sh & 31); sh += 7; }
-                }
-                // (if the previous word is itself a list's first payload word, only its own bytes count: exactly what was walked)
+        return;
+    }
+    // ---- per-list books: header checks, restart / count-word / first-value bits (the words are staged, the bitmaps zero)
+    bool ok = true;
+    int my_n = 0;
+    if (tid <= nl) s_wrel[tid] = aw + (int)((my_i0 - ib) >> 2);
+    if (tid < nl) {
+        const int w0 = aw + (int)((my_i0 - ib) >> 2), w1 = aw + (int)((my_i1 - ib) >> 2);
+        my_n = (int)(my_o1 - my_o0);
+        const int hdr = hdr_mode == 1 ? 1 : (hdr_mode == 2 && my_n > 0 ? 1 : 0);
+        if (w1 - w0 < hdr) ok = false;
+        else {
+            if (hdr) {
+                const uint32_t h = __byte_perm(s_words[w0], 0, sel);
+                if (h != (hdr_mode == 1 ? (uint32_t)my_n : 0u)) ok = false; // IntCompressor's n / Composition's marker (FastPFOR took nothing)
+                if (hdr_mode == 1) atomicOr(&s_whdr[w0 >> 5], 1u << (w0 & 31));
             }
-            uint32_t *o = s_val + ao + V0;
-            if ((int)tot <= VF_VCAP - 8) {
+            if (w1 > w0 + hdr) atomicOr(&s_wstart[(w0 + hdr) >> 5], 1u << ((w0 + hdr) & 31));
+            else if (my_n > 0) ok = false;
+            if (my_n > 0) { const int p = ao + (int)(my_o0 - ob); atomicOr(&s_vstart[p >> 5], 1u << (p & 31)); }
+        }
+    }
+    __syncthreads(); // the bitmaps are in place
+    // ---- this thread's 4g words: clean, count the values that end in them
+    const int g = ((wspan + 4 * D4_THREADS - 1) / (4 * D4_THREADS)) | 1;
+    const int q0 = 4 * g * tid;
+    int cnt = 0;
+    for (int i = 0; i < g; ++i) {
+        const int q = q0 + 4 * i;
+        if (q < wspan) {
+            uint4 u = *reinterpret_cast<const uint4 *>(s_words + q);
+            const uint32_t hm = (s_whdr[q >> 5] >> (q & 31)) & 15u;
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool in = q + k >= aw && q + k < wspan && !((hm >> k) & 1u);
+                w[k] = in ? __byte_perm(w[k], 0, sel) : 0u;
+                cnt += __popc(w[k] & 0x80808080u);
+            }
+            *reinterpret_cast<uint4 *>(s_words + q) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    uint32_t incl = (uint32_t)cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, dd);
+        if (lane >= dd) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads(); // (also: the clean words are in place)
+    uint32_t wo = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < D4_WARPS; ++w) {
+        const uint32_t x = s_w[w];
+        if (w < warp) wo += x;
+        tot += x;
+    }
+    const int V0 = (int)(wo + incl) - cnt;
+    s_cp[tid] = V0;
+    if (tid == 0) s_cp[D4_THREADS] = (int)tot;
+    __syncthreads();
+    // ---- every list must hold exactly its n values: values ending before its first word = values before it
+    if (tid <= nl) {
+        const int wpos = tid < nl ? s_wrel[tid] : wspan;
+        const int t = min(wpos / (4 * g), D4_THREADS);
+        int c = s_cp[t];
+        if (t < D4_THREADS)
+            for (int p = 4 * g * t; p < wpos; ++p) c += __popc(s_words[p] & 0x80808080u);
+        if (c != (int)(my_o0 - ob)) ok = false;
+    }
+    if ((int)tot != (int)nvals) ok = false;
+    if (__syncthreads_or(!ok)) { if (tid == 0) atomicMax(a.err, 5); return; }
+    // ---- the byte walk (VariableByte.java:115-138): v += (c & 127) << shift; a set bit 7 ends the value
+    {
+        uint32_t acc = 0;
+        int sh = 0;
+        if (q0 > aw && q0 < wspan && !((s_wstart[q0 >> 5] >> (q0 & 31)) & 1u)) { // bytes of a value that began in the previous word
+            const uint32_t pv = s_words[q0 - 1];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t by = (pv >> (8 * e)) & 255u;
+                if (by & 128u) { acc = 0; sh = 0; }
+                else { acc += (by & 127u) << (sh & 31); sh += 7; }
+            }
+            // (if the previous word is itself a list's first payload word, only its own bytes count: exactly what was walked)
+        }
+        int idx = ao + V0;
+        for (int i = 0; i < g; ++i) {
+            const int q = q0 + 4 * i;
+            if (q < wspan) {
+                const uint4 u = *reinterpret_cast<const uint4 *>(s_words + q);
+                const uint32_t fl = (s_wstart[q >> 5] >> (q & 31)) & 15u;
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if ((fl >> k) & 1u) { acc = 0; sh = 0; }
@@ -3233,97 +3190,70 @@ __global__ void __launch_bounds__(VF_THREADS, 4) k_vbf_decode(const FastDecArgs 
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t by = (w[k] >> (8 * e)) & 255u;
                         acc += (by & 127u) << (sh & 31);
-                        if (by & 128u) { *o++ = acc; acc = 0; sh = 0; }
+                        if (by & 128u) { s_val[d4_slot(idx)] = acc; ++idx; acc = 0; sh = 0; }
                         else sh += 7;
                     }
                 }
             }
         }
-        __syncthreads();
-        // ---- every list must hold exactly its n values: values ending before its first word = values before it
-        if (tid <= nl) {
-            const int wpos = tid < nl ? s_wrel[tid] : wspan;
-            int c = s_cp[(wpos >> 2) < VF_THREADS ? (wpos >> 2) : VF_THREADS];
-            if ((wpos >> 2) < VF_THREADS)
-                for (int k = 0; k < (wpos & 3); ++k) {
-                    const int p = (wpos & ~3) + k;
-                    const bool in = p >= aw && p < wspan && !((s_hmask[p >> 5] >> (p & 31)) & 1u);
-                    if (in) c += __popc(wp[p] & 0x80808080u); // (terminator bits are where they are in either byte order)
-                }
-            if (c != s_vrel[tid]) ok = false;
+    }
+    __syncthreads(); // the values are staged
+    if (DELTA) {
+        // ---- Delta.inverseDelta per list: running sums that restart at list starts
+        uint32_t *row = s_val + D4_VPT * tid;
+        const uint32_t fw = s_vstart[tid];
+        uint32_t y[D4_VPT];
+#pragma unroll
+        for (int c = 0; c < D4_VPT / 4; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(row + 4 * (c ^ (tid & 7)));
+            y[4 * c] = u.x; y[4 * c + 1] = u.y; y[4 * c + 2] = u.z; y[4 * c + 3] = u.w;
         }
-        if ((int)tot != (int)nvals) ok = false;
-        const int fail = __syncthreads_or(!ok);
-        if (fail) { if (tid == 0) atomicMax(a.err, 5); continue; }
-        // ---- values leave, 8 per thread, aligned like the output; Delta.inverseDelta = flat sums minus the sum at the list's start
-        uint32_t *gout = a.out + ob - ao;
-        const int vspan = ao + (int)nvals;
-        uint32_t carry = 0; // flat sum of the passes before this one
-        for (int p0 = 0; p0 < vspan; p0 += VF_THREADS * 8) {
-            const int v0 = p0 + 8 * tid;
-            uint32_t x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (v0 < vspan) {
-                const uint4 u0 = *reinterpret_cast<const uint4 *>(s_val + v0), u1 = *reinterpret_cast<const uint4 *>(s_val + v0 + 4);
-                x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w; x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-            }
-            uint32_t vm = 0;
+        uint32_t run = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vm |= (uint32_t)(v0 + k >= ao && v0 + k < vspan) << k;
-            if (a.delta) {
-                uint32_t sum = 0;
+        for (int k = 0; k < D4_VPT; ++k) {
+            if ((fw >> k) & 1u) run = 0;
+            run += y[k];
+            y[k] = run;
+        }
+        // segmented scan over the threads: (sum since the last start, a start was seen)
+        uint32_t v = run, f = fw != 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { x[k] = ((vm >> k) & 1u) ? x[k] : 0u; sum += x[k]; x[k] = sum; } // inclusive within the thread
-                uint32_t ptot;
-                __syncthreads(); // s_scan / s_ss of the previous pass have been read
-                const uint32_t ex = vf_block_scan(sum, s_scan, &ptot) + carry;
-                // list of the first valid position: the LAST list starting at or before it
-                int lid = 0;
-                if (vm) {
-                    const int pos = v0 + (__ffs(vm) - 1) - ao;
-                    int lo = 0, hi = nl; // s_vrel[lo] <= pos < s_vrel[hi]
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_vrel[mid] <= pos) lo = mid; else hi = mid; }
-                    lid = lo;
-                }
-                // starts inside this thread's positions publish the flat sum before them
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t pv = __shfl_up_sync(kFull, v, dd), pf = __shfl_up_sync(kFull, f, dd);
+            if (lane >= dd) { if (!f) v += pv; f |= pf; }
+        }
+        if (lane == 31) { s_sv[warp] = v; s_sf[warp] = f; }
+        uint32_t ev = __shfl_up_sync(kFull, v, 1), ef = __shfl_up_sync(kFull, f, 1);
+        if (lane == 0) { ev = 0; ef = 0; }
+        __syncthreads();
+        uint32_t cw = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if ((vm >> k) & 1u) {
-                        const int pos = v0 + k - ao;
-                        int l = lid;
-                        while (l + 1 < nl && s_vrel[l + 1] <= pos) ++l;
-                        if (s_vrel[l] == pos) s_ss[l] = ex + (k ? x[k - 1] : 0u);
-                        lid = l;
-                    }
-                }
-                __syncthreads();
-                if (vm) {
-                    const int pos = v0 + (__ffs(vm) - 1) - ao;
-                    int lo = 0, hi = nl;
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_vrel[mid] <= pos) lo = mid; else hi = mid; }
-                    int l = lo;
-                    uint32_t ss = s_ss[l];
+        for (int w = 0; w < D4_WARPS - 1; ++w)
+            if (w < warp) cw = s_sf[w] ? s_sv[w] : cw + s_sv[w];
+        const uint32_t carry = ef ? ev : cw + ev;
+        const int kf = fw ? __ffs(fw) - 1 : D4_VPT; // the carry reaches the values before this thread's first list start
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if ((vm >> k) & 1u) {
-                            const int pos2 = v0 + k - ao;
-                            if (l + 1 < nl && s_vrel[l + 1] <= pos2) { while (l + 1 < nl && s_vrel[l + 1] <= pos2) ++l; ss = s_ss[l]; }
-                            x[k] = ex + x[k] - ss;
-                        }
-                    }
-                }
-                carry += ptot;
-            }
-            if (vm == 0xffu) {
-                *reinterpret_cast<uint4 *>(gout + v0) = make_uint4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<uint4 *>(gout + v0 + 4) = make_uint4(x[4], x[5], x[6], x[7]);
-            } else {
+        for (int k = 0; k < D4_VPT; ++k)
+            if (k < kf) y[k] += carry;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((vm >> k) & 1u) gout[v0 + k] = x[k];
-            }
+        for (int c = 0; c < D4_VPT / 4; ++c)
+            *reinterpret_cast<uint4 *>(row + 4 * (c ^ (tid & 7))) = make_uint4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+        __syncthreads();
+    }
+    // ---- the tile leaves: coalesced 16-byte stores (the staging tile is aligned like the output)
+    uint32_t *gal = a.out + ob - ao;
+    for (int q = tid; 4 * q < vspan; q += D4_THREADS) {
+        const uint4 u = *reinterpret_cast<const uint4 *>(s_val + d4_slot(4 * q));
+        if (4 * q >= ao && 4 * q + 4 <= vspan) *reinterpret_cast<uint4 *>(gal + 4 * q) = u;
+        else {
+            if (4 * q + 0 >= ao && 4 * q + 0 < vspan) gal[4 * q + 0] = u.x;
+            if (4 * q + 1 >= ao && 4 * q + 1 < vspan) gal[4 * q + 1] = u.y;
+            if (4 * q + 2 >= ao && 4 * q + 2 < vspan) gal[4 * q + 2] = u.z;
+            if (4 * q + 3 >= ao && 4 * q + 3 < vspan) gal[4 * q + 3] = u.w;
         }
     }
 }
+
 
 // ---------------------------------------------------------------------- scan
 // exclusive scan of int64: per-block partial sums, serial scan of the partials by one
@@ -3594,15 +3524,16 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
         if (pass == 1 && !batched) return MCP_E_UNSUPPORTED;
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
-        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 2000.0, VF_MAXL) : 32)
+        a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 0.88 * D4_VSPAN, D4_MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_out_vals, nlists);
         const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         {
             KScope ks(ctx, MCP_K_DECODE);
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
-                const int64_t res = (int64_t)ctx->prop.multiProcessorCount * 4;
-                k_vbf_decode<<<(unsigned)(nbatches < res ? nbatches : res), VF_THREADS, 0, ctx->stream>>>(a, nbatches);
+                const int hdr_mode = tr.sk ? 1 : (tr.fastpfor ? 2 : 0), page = tr.fastpfor ? tr.fp_block : 0;
+                if (a.delta) k_vb4_decode<true><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page);
+                else k_vb4_decode<false><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page);
             } else if (pass == 0) {
                 const int64_t res = (int64_t)ctx->prop.multiProcessorCount * SL_DCTAS;
                 k_sl_decode<<<(unsigned)(nbatches < res ? nbatches : res), 32, 0, ctx->stream>>>(a, nbatches);

@@ -127,7 +127,7 @@ struct mcp_ctx {
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
-    int flatCodec = 0;             // 1 = flat (lane-parallel) VariableByte kernels for all-VariableByte short lists (bit-exact, measured slower: off)
+    int flatCodec = 1;             // 1 = flat (thread per 32 values) VariableByte kernels for short lists that are all VariableByte (default); 0 = thread-per-list kernels
     int shortListCodec = 1;        // thread-per-list kernels for lists averaging <= 144 values: 0 off, 1 where they win, 2 every codec
     int64_t shortListCalls = 0, shortListFallbacks = 0; // encode + decode calls they served / handed on to the batched kernels
     bool forceDense = false;       // debug: use the generic dense path even when F == 32

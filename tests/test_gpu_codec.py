@@ -25,7 +25,7 @@ def batch_of(matrix):
     return vals, off
 
 
-FLAT_DEFAULT = 0  # the library's default for option flat_codec
+FLAT_DEFAULT = 1  # the library's default for option flat_codec
 
 
 def test_kat_through_the_c_abi(ctx):
