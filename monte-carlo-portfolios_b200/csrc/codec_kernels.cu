@@ -3040,7 +3040,7 @@ template <bool DELTA>
 __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, int hdr_mode, int page)
 {
     __shared__ __align__(16) uint32_t s_words[D4_WCAP];
-    __shared__ __align__(16) uint32_t s_val[D4_VSPAN];
+    __shared__ __align__(1024) uint32_t s_val[D4_VSPAN]; // (1 KB aligned: the swizzle can be applied to the shared address itself)
     __shared__ uint32_t s_wstart[D4_WCAP / 32]; // bit w: a list's payload starts at window word w (the decoder restarts there)
     __shared__ uint32_t s_whdr[D4_WCAP / 32];   // bit w: window word w is an IntCompressor count word (not payload)
     __shared__ uint32_t s_vstart[D4_VSPAN / 32 + 1]; // bit p: a non-empty list starts at window position p of the output
@@ -3123,13 +3123,22 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
             uint4 u = *reinterpret_cast<const uint4 *>(s_words + q);
             const uint32_t hm = (s_whdr[q >> 5] >> (q & 31)) & 15u;
             uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            if (q >= aw && q + 4 <= wspan && hm == 0) { // (the usual case: four payload or zero words)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool in = q + k >= aw && q + k < wspan && !((hm >> k) & 1u);
-                w[k] = in ? __byte_perm(w[k], 0, sel) : 0u;
-                cnt += __popc(w[k] & 0x80808080u);
+                for (int k = 0; k < 4; ++k) {
+                    w[k] = __byte_perm(w[k], 0, sel);
+                    cnt += __popc(w[k] & 0x80808080u);
+                }
+                if (a.app) *reinterpret_cast<uint4 *>(s_words + q) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool in = q + k >= aw && q + k < wspan && !((hm >> k) & 1u);
+                    w[k] = in ? __byte_perm(w[k], 0, sel) : 0u;
+                    cnt += __popc(w[k] & 0x80808080u);
+                }
+                *reinterpret_cast<uint4 *>(s_words + q) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4 *>(s_words + q) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
     uint32_t incl = (uint32_t)cnt;
@@ -3176,7 +3185,8 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
             }
             // (if the previous word is itself a list's first payload word, only its own bytes count: exactly what was walked)
         }
-        int idx = ao + V0;
+        // shared byte address of value slot idx before the swizzle; d4_slot on the address: a ^ ((a >> 3) & 0x70)
+        uint32_t va = (uint32_t)__cvta_generic_to_shared(s_val) + 4u * (uint32_t)(ao + V0);
         for (int i = 0; i < g; ++i) {
             const int q = q0 + 4 * i;
             if (q < wspan) {
@@ -3190,8 +3200,11 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t by = (w[k] >> (8 * e)) & 255u;
                         acc += (by & 127u) << (sh & 31);
-                        if (by & 128u) { s_val[d4_slot(idx)] = acc; ++idx; acc = 0; sh = 0; }
-                        else sh += 7;
+                        if (by & 128u) {
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(va ^ ((va >> 3) & 0x70u)), "r"(acc) : "memory");
+                            va += 4; acc = 0; sh = 0;
+                        } else
+                            sh += 7;
                     }
                 }
             }
@@ -3242,9 +3255,10 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
     }
     // ---- the tile leaves: coalesced 16-byte stores (the staging tile is aligned like the output)
     uint32_t *gal = a.out + ob - ao;
+#pragma unroll 2
     for (int q = tid; 4 * q < vspan; q += D4_THREADS) {
         const uint4 u = *reinterpret_cast<const uint4 *>(s_val + d4_slot(4 * q));
-        if (4 * q >= ao && 4 * q + 4 <= vspan) *reinterpret_cast<uint4 *>(gal + 4 * q) = u;
+        if (q > 0 && 4 * q + 4 <= vspan) *reinterpret_cast<uint4 *>(gal + 4 * q) = u;
         else {
             if (4 * q + 0 >= ao && 4 * q + 0 < vspan) gal[4 * q + 0] = u.x;
             if (4 * q + 1 >= ao && 4 * q + 1 < vspan) gal[4 * q + 1] = u.y;
