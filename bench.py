@@ -312,12 +312,17 @@ class Job:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return float(t.item())
 
-    def traffic(self, name):
-        """DRAM bytes per launch of the dominant valuation launch from the committed ncu --set full capture of this workload"""
+    def traffic(self, name, P_local=None):
+        """DRAM bytes per launch of the dominant valuation launch from the committed ncu capture of this workload shape
+        (profiles/tools/capture_value_traffic.sh -> profiles/value_kernel_traffic.json; ncu cannot run inside the bench)"""
         try:
-            return json.load(open(os.path.join(ROOT, "profiles", "value_kernel_traffic.json")))[name]["dram_bytes_per_launch"]
+            t = json.load(open(os.path.join(ROOT, "profiles", "value_kernel_traffic.json")))
+            for key in (f"{name}_{P_local}", name):
+                if key in t:
+                    return t[key]["dram_bytes_per_launch"]
         except Exception:
-            return None
+            pass
+        return None
 
     def close(self):
         self.barrier()
@@ -399,7 +404,7 @@ def risk_leg(job, name, P_local, row0, ranks_active=None, check=True):
         achieved = flops / (v_ms * 1e-3) / 1e12 if v_ms > 0 else 0.0
         pk = job.fp64_peak
         out["roofline"] = {"bound": "tensor", "kernel": "k_value_mma (FP64 tensor-core valuation + fused tail filter)", "achieved": achieved,
-                           "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk if pk else None, "traffic": job.traffic(name),
+                           "peak": pk, "unit": "TFLOP/s", "frac": achieved / pk if pk else None, "traffic": job.traffic(name, P_local),
                            "peak_source": job.peak_source, "pipe": "FP64 tensor pipe (DMMA.8x8x4); algorithmic FLOPs = 2*F per valuation",
                            "launches_per_step": kv["launches"] / max(args.steps, 1), "ms_per_step": v_ms,
                            "whole_step_frac": (flops / (ms_per_step * 1e-3) / 1e12) / pk if pk else None}
@@ -453,16 +458,70 @@ def e2e_leg(job, name, P_local, row0):
         job.barrier()
         return job.over_ranks((time.perf_counter() - t0) / args.steps)
     e_s, e_raw = timed(False), timed(True)
+
+    # ---- the same calls, two in flight: a second context on the same GPU and one host thread per context (contexts are
+    # independent; a context is used by one thread at a time), so that the uploads and downloads of one step ride under the
+    # kernels of the other.  Every step still uploads its own inputs and downloads its own results inside the timed region.
+    import threading
+    import mcp_b200
+    depth = 2
+    ctx2 = mcp_b200.Context(job.local_rank)
+    outs2 = {k: pinned_array(L, v.shape, v.dtype) for k, v in outs.items()}
+    n_enc2 = ctypes.c_int64(0)
+    lanes = [(ctx, outs, n_enc), (ctx2, outs2, n_enc2)]
+
+    def one_on(lane):
+        c, o, n = lane
+        rc = L.mcp_simulate(c._h, ptr(Eh), P_local, ptr(Sh), Nn, F, alpha, cid, framing, ptr(o["mean"]), ptr(o["variance"]),
+                            ptr(o["var_loss"]), ptr(o["var_trial"]), ptr(o["cvar"]), None, ptr(o["enc_off"]), ptr(o["enc"]), cap,
+                            ctypes.byref(n))
+        if rc != 0:
+            raise RuntimeError(f"mcp_simulate failed: {rc} {L.mcp_last_error(c._h)}")
+    per = (args.steps + depth - 1) // depth
+    errs = []
+
+    def worker(lane, count):
+        try:
+            for _ in range(count):
+                one_on(lane)
+        except Exception as ex:  # surfaced after the join
+            errs.append(ex)
+    for lane in lanes:
+        one_on(lane)  # warm-up: allocations of the second context
+    job.barrier()
+    ctx2.sync()
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(lane, per)) for lane in lanes]
+    for t_ in th:
+        t_.start()
+    for t_ in th:
+        t_.join()
+    ctx2.sync()
+    job.barrier()
+    e_pipe = job.over_ranks((time.perf_counter() - t0) / (per * depth))
+    if errs:
+        raise errs[0]
+    same = all(np.array_equal(outs[k], outs2[k]) for k in ("mean", "variance", "var_loss", "var_trial", "cvar", "enc_off")) \
+        and n_enc.value == n_enc2.value and np.array_equal(outs["enc"][: n_enc.value], outs2["enc"][: n_enc2.value])
+    if not same:
+        raise RuntimeError("e2e: the two pipelined contexts disagree")
+    for a in outs2.values():
+        L.mcp_host_free_pinned(ctypes.c_void_p(a.ctypes.data))
+    ctx2.close()
     h2d = Eh.nbytes + Sh.nbytes
     d2h = sum(outs[k].nbytes for k in ("mean", "variance", "var_loss", "var_trial", "cvar", "enc_off")) + int(n_enc.value)
     units = P_local * Nn * (job.world if name == "c2" else 1) if name == "c2" else WORKLOADS[name][0] * Nn
     for a in list(outs.values()) + [Eh, Sh]:
         L.mcp_host_free_pinned(ctypes.c_void_p(a.ctypes.data))
-    return {"value": units / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": e_s * 1e3,
-            "api": "mcp_simulate, one call per step and rank, pinned host buffers: uploads E (the rank's shard) and S, runs the path, "
+    return {"value": units / e_pipe, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": e_pipe * 1e3,
+            "api": "mcp_simulate, one call per step, pinned host buffers: every call uploads E (the rank's shard) and S, runs the path and "
                    "downloads what the sink document holds (mean, variance, VaR loss + trial, CVaR, CSR offsets and the encoded breach "
-                   "lists); wall clock around the calls, max over ranks; bytes are per rank",
+                   "lists).  Two calls in flight per rank (two contexts on the GPU, one host thread each) so that one step's copies ride "
+                   "under the other's kernels; wall clock around all the calls / steps, max over ranks; bytes are per rank and step",
+            "calls_in_flight": depth,
+            "one_call_at_a_time": {"value": units / e_s, "ms_per_step": e_s * 1e3,
+                                   "note": "the same calls back to back on one context (the latency of a step from host buffers)"},
             "with_raw_breach_lists": {"value": units / e_raw, "ms_per_step": e_raw * 1e3,
                                       "d2h_bytes_per_step": int(d2h + outs["breach"].nbytes),
                                       "note": "same call, additionally downloading the uncompressed int32 breach lists"}}

@@ -256,7 +256,11 @@ int mcp_run_stats(mcp_ctx *ctx, int64_t *fallback_rows);
 int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,
               int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap);
 
-/* One-call host-buffer version (upload + run + fetch): the end-to-end path */
+/* One-call host-buffer version (upload + run + fetch): the end-to-end path.  The call returns when the results are in the
+ * caller's buffers.  For throughput keep two calls in flight: contexts are independent, so two contexts on one GPU driven
+ * by two host threads (one context per thread at a time) let the uploads and downloads of one step ride under the kernels
+ * of the other -- measured on C2: 2.85 ms per step against 3.23 ms back to back (kernels alone: 2.81 ms).  The Python
+ * mirror is mcp_b200.SimulatePipeline; the Java shim's SimulatePortfolios would hold two McpNative handles the same way. */
 int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int64_t N, int32_t F,
                  double alpha, int codec_id, int framing,
                  double *mean, double *variance, double *var_loss, int32_t *var_trial, double *cvar,

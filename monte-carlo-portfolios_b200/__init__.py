@@ -12,7 +12,7 @@ from .codec import (BinaryPacking, Composition, FastPFOR, FastPFOR128, IntCompre
                     OptPFD, SkippableComposition, XorBinaryPacking,
                     VariableByte,
                     VariableByteCodec, default_context)
-from .engine import Context
+from .engine import Context, SimulatePipeline
 from .portfolio import LoadPortfolios, SimulatePortfolios, simulation_documents
 from . import sharding
 

@@ -315,6 +315,23 @@ def test_simulate_one_call(ctx):
         assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
 
 
+def test_simulate_pipeline_two_calls_in_flight():
+    """SimulatePipeline: two contexts on one GPU, one host thread each -- steps submitted back to back come back as the
+    steps run one at a time would have (and as the oracle says), whatever the interleaving of their copies and kernels."""
+    steps = [riskcases.synthetic(20 + i, 40000, 32, 100 + i) for i in range(5)]
+    with mcp_b200.SimulatePipeline(device=0, depth=2) as pipe:
+        futures = [pipe.submit(E, S, 0.99) for E, S in steps]
+        results = [f.result() for f in futures]
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    for (E, S), r in zip(steps, results):
+        o = cref.risk(E, S, 0.99)
+        assert np.array_equal(r["breach"], o["breach"]) and np.array_equal(r["var_trial"], o["var_trial"])
+        assert np.array_equal(r["var_loss"], o["var_loss"])
+        np.testing.assert_allclose(r["cvar"], o["cvar"], rtol=RTOL)
+        for p in (0, E.shape[0] - 1):
+            assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
+
+
 def test_simulate_with_the_scenario_tail_uploaded_in_two_parts(ctx):
     """mcp_simulate uploads the scenario tail in two parts and launches the sparse valuation in two halves, the first as
     soon as its rows are there; results are those of the single upload and of the oracle."""
