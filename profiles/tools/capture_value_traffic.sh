@@ -10,4 +10,6 @@ run() { # name P N F
 }
 run c2 10000 100000 32
 run c3_125000 125000 10000 64
+run c3_500000 500000 10000 64
+run c3_250000 250000 10000 64
 run c3_1000000 1000000 10000 64

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import cases
+import mcp_b200
 import riskcases
 from mcp_b200 import native as N
 from oracle import cref
