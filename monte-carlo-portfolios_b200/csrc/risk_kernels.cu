@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 // (git history) was shared-memory-bandwidth bound at 48 % of the FP64 peak.  (tcgen05 has no FP64 kind.)
 //
 // "E-stationary": a warp keeps the A fragments of VM_G = 2 portfolio groups (16 portfolios x all F factors) in
-// registers and streams trials past them; a CTA = 16 warps = 256 portfolios x one trial sub-chunk.  The scenario rows of
+// registers and streams trials past them; a CTA = 8 warps = 128 portfolios x one trial sub-chunk.  The scenario rows of
 // the sub-chunk arrive in B-FRAGMENT ORDER (k_repack_scenarios), so a stage of 32 trials is ONE contiguous block: a
 // single cp.async.bulk (TMA bulk copy, SASS UBLKCP) by one elected thread, completing on mbarriers, 4 stages deep, and
 // every B-fragment load reads 32 consecutive doubles -- bank-conflict free without padding.  Fused on each value while
@@ -349,16 +349,17 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 //     portfolio's current bound: an integer compare on the raw bit pattern (its high word, when every bound of the
 //     warp is negative) and predicated stores -- no divergence, no FP64-pipe slots.
 // Each lane appends to its own private segment (portfolio, sub-chunk, lane%4): no atomics.
-constexpr int VM_WARPS = 16;
+constexpr int VM_WARPS = 8;
 constexpr int VM_THREADS = VM_WARPS * 32;
 constexpr int VM_G = 2;                      // portfolio groups (of 8) per warp
-constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 256
-// Scenario staging: TWO stages of as many trials as ~196 KB of shared memory hold (256 for F <= 48, 192 for F = 64).
-// Measured on C2: 4 stages x 32 trials 2.157 ms, 4 x 64 2.102, 3 x 128 2.068, 2 x 256 2.056 -- what costs is the
-// per-stage handshake (mbarrier wait / arrive, the producer thread's detour), not the prefetch depth: one stage of
-// compute (>= 192 trials) covers the latency of the next stage's single bulk copy many times over.
+constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 128
+// Scenario staging: TWO stages of 128 trials (64 KB per CTA at F = 32, 128 KB at F = 64).  Measured on C2 with 16-warp CTAs:
+// 4 stages x 32 trials 2.157 ms, 4 x 64 2.102, 3 x 128 2.068, 2 x 256 2.056 -- what costs is the per-stage handshake (mbarrier
+// wait / arrive, the producer thread's detour), not the prefetch depth.  Round 2: 8-warp CTAs with 2 x 128-trial stages (two
+// such CTAs share an SM up to F = 48: the same 16 warps, but independent of each other) 2.052 ms, and C3 (F = 64, one 8-warp
+// CTA per SM) 5.11 instead of 5.16 ms per 125 000 rows: eight warps already keep the DMMA pipe as busy as sixteen.
 constexpr int VM_NSTAGE = 2;
-template <int NK> constexpr int vm_stage_trials() { return NK <= 12 ? 256 : 192; }
+template <int NK> constexpr int vm_stage_trials() { return 128; }
 
 struct StreamArgs {
     const double *E, *S;

@@ -434,3 +434,36 @@ def test_sharded_assembly_on_gpu(ctx):
         assert np.array_equal(whole[k], one[k]), k
     o = cref.risk(E, S, 0.99)
     assert np.array_equal(whole["breach"], o["breach"])
+
+
+def test_full_size_c3_properties(ctx):
+    """BASELINE config C3 at full size on ONE GPU (1 000 000 portfolios x 10 000 trials x 64 factors, the N = 1 point of the
+    strong-scaling curve; the 125 000-row k_select_t<64> path runs eight portfolio tiles): spot rows against the oracle,
+    size-independent properties on every row, and the flat codec kernels' encode -> decode round trip over all 10^6 lists."""
+    P, Nn, F, alpha, seed = 1_000_000, 10_000, 64, 0.99, 0x5EED0003
+    ctx.generate_exposures(P, F, seed, 100.0, 0.0)
+    ctx.generate_scenarios(Nn, F, seed, 1.0, 0.05)
+    cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
+    ctx.run(alpha, cid, N.FRAME_APP)
+    r = ctx.fetch()
+    t = r["tail"]
+    assert t == 101
+    assert ctx.run_stats()["fallback_rows"] == 0
+    b = r["breach"]
+    assert b.shape == (P, t)
+    assert np.all(np.diff(b, axis=1) > 0) and b.min() >= 0 and b.max() < Nn
+    assert np.all((b == r["var_trial"][:, None]).sum(axis=1) == 1)
+    assert np.all(r["cvar"] >= r["var_loss"]) and np.all(r["variance"] > 0)
+    assert r["enc_off"][0] == 0 and r["enc_off"][-1] == r["enc"].size and np.all(np.diff(r["enc_off"]) > 0)
+    off = np.arange(P + 1, dtype=np.int64) * t
+    back = ctx.codec_decode(cid, N.FRAME_APP, r["enc"], r["enc_off"], off)
+    assert np.array_equal(back.reshape(P, t), b)
+    S = cref.gen_normal(Nn, F, seed, 2, 1.0, 0.05)
+    for p in (0, 124_999, 125_000, 500_001, 999_999):  # first / last rows of portfolio tiles and of the run
+        E1 = cref.gen_normal(1, F, seed, 1, 100.0, 0.0, row0=p)
+        o = cref.risk(E1, S, alpha)
+        assert r["var_trial"][p] == o["var_trial"][0] and r["var_loss"][p] == o["var_loss"][0]
+        assert np.array_equal(b[p], o["breach"][0])
+        assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][0])
+        np.testing.assert_allclose([r["mean"][p], r["variance"][p], r["cvar"][p]],
+                                   [o["mean"][0], o["variance"][0], o["cvar"][0]], rtol=RTOL, atol=0)
