@@ -105,7 +105,7 @@ struct mcp_ctx {
     cudaStream_t stream3 = nullptr; // second tile stream (risk_stream_core), `cur` = the stream the tile helpers launch on
     cudaStream_t cur = nullptr;
     cudaEvent_t evTileFork = nullptr, evTileJoin = nullptr, evSfrag = nullptr;
-    int64_t overlapTiles = 1;      // >1: that many portfolio tiles alternate between two streams (selection of one tile under the valuation of the next); measured -2 % at best on C2 -- the valuation kernel leaves no idle issue slots to hide in -- so off by default
+    int64_t overlapTiles = 1;      // >1: that many portfolio tiles alternate between two streams (selection of one tile under the valuation of the next); with 8-warp valuation CTAs: C2 2.79 -> 2.70 ms, C3 6.85 -> 6.70 ms per 125 000 rows (round 1, 16-warp CTAs: -2 % at best).  Off by default: the two-calls-in-flight pipeline of mcp_simulate gets the same overlap across steps (2.75 ms e2e), and per-kernel event times stay those of kernels running alone
     mcp::DevBuf dCandKey2, dCandCnt2;
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr, evTail1 = nullptr;
