@@ -26,7 +26,8 @@ def mk(kind):
 bad = 0
 for kind in ("breach", "tiny", "mixed", "big"):
     vals, off = mk(kind)
-    for cid in (N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB, N.CODEC_SK_FASTPFOR256_VB|N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB):
+    for cid in (N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB, N.CODEC_SK_FASTPFOR256_VB|N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB,
+                N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_BP32_VB, N.CODEC_SK_BP32_VB | N.FLAG_DELTA, N.CODEC_SK_BP32_VB):
         for fr in (N.FRAME_APP, N.FRAME_WORDS):
             try:
                 out_off, out = ctx.codec_encode(cid, fr, vals, off)
