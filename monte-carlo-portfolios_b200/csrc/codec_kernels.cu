@@ -2967,46 +2967,214 @@ __global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
     }
 }
 
-// exclusive scan of the tiles' word counts in place (one CTA: a few ten thousand tiles; a warp per contiguous segment, 32
-// counts per round, coalesced); the total in bytes goes to *total and to out_off[nlists], flag 1 when the caller's buffer is
-// too small for it
-__global__ void __launch_bounds__(1024) k_vb4_scan(int64_t *tile_words, int64_t nb, int64_t *total, int64_t *out_off_end, int64_t cap, int *err)
+constexpr int VB4_THREADS = 128, VB4_VPT = 32;
+using VB4 = V4<VB4_THREADS, VB4_VPT>;
+
+// ---- size pass of the flat VariableByte encoder, on its own: what the emit pass needs from it is one number per tile, and
+// that number needs no prefixes, no staging and no per-thread state -- a list's bytes are its length, plus one for every gap of
+// 128 or more (a popcount over the tile's "two bytes" bit vector), plus the rare third to fifth bytes (added to the list's
+// count one by one).  A thread forms 8 consecutive gaps from two 16-byte loads (a warp reads 1 KB at a time) and stores one byte
+// of the bit vector; 4 rounds cover the tile.  HBM-bound: 65 us for the 400 MB of C4 (the tile kernel used as size pass: 82).
+template <bool DELTA>
+__global__ void __launch_bounds__(VB4_THREADS) k_vb4_size(const TileEncArgs ta)
+{
+    using C = V4<VB4_THREADS, 32>;
+    const FastEncArgs &a = ta.f;
+    __shared__ __align__(16) uint32_t s_bits[C::SPAN / 32];  // bit p: the value at window position p takes two bytes or more
+    __shared__ uint32_t s_flag[C::SPAN / 32 + 1];             // bit p: a non-empty list starts at window position p
+    __shared__ int s_rel[VB4_THREADS + 1];                    // list starts as window positions ([nl] = the tile's end)
+    __shared__ int s_extra[VB4_THREADS];                      // per list: bytes beyond the second of its values
+    __shared__ uint32_t s_w[C::WARPS];
+    __shared__ long long s_red[C::WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile = blockIdx.x;
+    const int64_t l0 = tile * a.lists_per_batch;
+    const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+    int64_t base, end, my_off = 0, my_end = 0;
+    if (a.list_off) {
+        const int64_t *lo = a.list_off + l0;
+        base = lo[0]; end = lo[nl];
+        if (tid <= nl) { my_off = lo[tid]; my_end = lo[tid < nl ? tid + 1 : tid]; }
+    } else {
+        base = l0 * a.uniform_len; end = base + nl * a.uniform_len;
+        my_off = base + min(tid, nl) * a.uniform_len; my_end = base + min(tid + 1, nl) * a.uniform_len;
+    }
+    const int64_t nv = end - base;
+    const int a0 = (int)((reinterpret_cast<uintptr_t>(a.vals + base) >> 2) & 3); // the window starts on a 16-byte boundary
+    bool bad = nv < 0 || a0 + nv > C::SPAN;
+    const int span = bad ? 0 : a0 + (int)nv;
+    const int64_t my_n = my_end - my_off;
+    if (tid <= nl) bad = bad || my_off < base || my_off > end || my_n < 0 || (ta.page > 0 && my_n >= ta.page);
+    s_flag[tid] = 0;
+    if (tid == 0) s_flag[C::SPAN / 32] = 0;
+    s_extra[tid] = 0;
+    // the loads do not depend on the list books: request them first
+    const uint32_t *wp = a.vals + base - a0;
+    uint4 u[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = 8 * (i * VB4_THREADS + tid);
+        u[i][0] = p < span ? __ldg(reinterpret_cast<const uint4 *>(wp + p)) : make_uint4(0, 0, 0, 0);
+        u[i][1] = p + 4 < span ? __ldg(reinterpret_cast<const uint4 *>(wp + p + 4)) : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads(); // (the start bits are zero)
+    if (tid <= nl && !bad) {
+        const int rel = a0 + (int)(my_off - base);
+        s_rel[tid] = rel;
+        if (tid < nl && my_n > 0) atomicOr(&s_flag[rel >> 5], 1u << (rel & 31));
+    }
+    const int slow = __syncthreads_or(bad);
+    if (!slow) {
+        uint8_t *sbits8 = reinterpret_cast<uint8_t *>(s_bits);
+        const uint8_t *sflag8 = reinterpret_cast<const uint8_t *>(s_flag);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int bidx = i * VB4_THREADS + tid, p = 8 * bidx; // this thread's byte of the bit vector, its first position
+            const uint32_t x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
+            uint32_t prev = __shfl_up_sync(kFull, x[7], 1);
+            if (lane == 0) prev = (p > 0 && p < span) ? __ldg(wp + p - 1) : 0u;
+            uint32_t bits = 0;
+            if (p < span) {
+                const uint32_t st = sflag8[bidx];
+                uint32_t d[8], wor = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    d[k] = (DELTA && !((st >> k) & 1u)) ? x[k] - prev : x[k];
+                    prev = x[k];
+                }
+                if (p < a0 || p + 8 > span) { // positions outside the tile count as nothing
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (p + k < a0 || p + k >= span) d[k] = 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    wor |= d[k];
+                    bits |= (d[k] >= 128u ? 1u : 0u) << k;
+                }
+                if (wor >= 16384u) { // rare: third to fifth bytes, added to their list's count (the list: by bisection)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (d[k] >= 16384u) {
+                            int lo = 0, hi = nl; // s_rel[lo] <= p + k < s_rel[hi]
+                            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_rel[mid] <= p + k) lo = mid; else hi = mid; }
+                            atomicAdd(&s_extra[lo], vb_len(d[k]) - 2);
+                        }
+                    }
+                }
+            }
+            sbits8[bidx] = (uint8_t)bits;
+        }
+        __syncthreads();
+        int words = 0;
+        if (tid < nl) {
+            const int n = (int)my_n;
+            int bytes = n + s_extra[tid];
+            if (n > 0) {
+                const int plo = s_rel[tid], phi = plo + n, wlo = plo >> 5, whi = (phi - 1) >> 5;
+                for (int w = wlo; w <= whi; ++w) {
+                    uint32_t m = s_bits[w];
+                    if (w == wlo) m &= 0xffffffffu << (plo & 31);
+                    if (w == whi && (phi & 31)) m &= (1u << (phi & 31)) - 1u;
+                    bytes += __popc(m);
+                }
+            }
+            const int hdr = ta.hdr_mode == 1 ? 1 : (ta.hdr_mode == 2 && n > 0 ? 1 : 0);
+            words = hdr + ((bytes + 3) >> 2) + (a.app ? 1 : 0);
+        }
+        words = __reduce_add_sync(kFull, words);
+        if (lane == 0) s_w[warp] = (uint32_t)words;
+        __syncthreads();
+        if (tid == 0) {
+            long long T = 0;
+#pragma unroll
+            for (int w = 0; w < C::WARPS; ++w) T += s_w[w];
+            ta.tile_words[tile] = T;
+        }
+        return;
+    }
+    // ---- a tile that does not fit the window: sizes by the warp-per-list routines
+    const CodecTraits tr = codec_traits(a.codec);
+    auto list_off = [&](int64_t l) -> int64_t { return a.list_off ? a.list_off[l] : l * a.uniform_len; };
+    bool page = false;
+    if (tid < nl) page = ta.page > 0 && my_n >= ta.page;
+    const int has_page = __syncthreads_or(page);
+    __shared__ uint32_t s_stage[C::WARPS][64];
+    long long mine = 0;
+    if (has_page) {
+        if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
+    } else {
+        for (int j = warp; j < nl; j += C::WARPS) {
+            const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
+            mine += warp_short_list_encode<false>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp], lane);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) s_red[warp] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        long long T = 0;
+#pragma unroll
+        for (int w = 0; w < C::WARPS; ++w) T += s_red[w];
+        ta.tile_words[tile] = T;
+    }
+}
+
+// exclusive scan of the tiles' word counts in place (one CTA: a few ten thousand tiles).  Every thread owns a contiguous run
+// of counts and loads it with 16-byte loads that are all in flight at once (the kernel is two memory round trips and a block
+// scan: ~5 us for 26 000 tiles; a warp-per-segment version that walked its segment 32 counts at a time took 18).  The total in
+// bytes goes to *total and to out_off[nlists], flag 1 when the caller's buffer is too small for it.
+constexpr int SCN_THREADS = 1024, SCN_VEC = 12; // longlong2 loads per thread and pass (24 counts)
+__global__ void __launch_bounds__(SCN_THREADS, 1) k_vb4_scan(int64_t *tile_words, int64_t nb, int64_t *total, int64_t *out_off_end, int64_t cap, int *err)
 {
     __shared__ long long s_w[32];
+    __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t per = ((nb + 31) / 32 + 31) & ~(int64_t)31, i0 = min(nb, warp * per), i1 = min(nb, i0 + per);
-    long long sum = 0;
-#pragma unroll 4
-    for (int64_t i = i0 + lane; i < i1; i += 32) sum += tile_words[i];
-    sum = warp_sum_i64(sum);
-    if (lane == 0) s_w[warp] = sum;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    long long run = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) {
-        const long long x = s_w[w];
-        if (w < warp) run += x;
-        tot += x;
-    }
-    for (int64_t i = i0; i < i1; i += 128) { // four rounds' loads in flight
-        long long x[4], incl[4];
+    const int64_t chunk = (int64_t)SCN_THREADS * 2 * SCN_VEC; // counts per pass of the CTA
+    for (int64_t c0 = 0; c0 < nb; c0 += chunk) {
+        const int64_t i0 = c0 + (int64_t)tid * 2 * SCN_VEC; // (even: 16-byte aligned, the array starts 32 bytes into a 256-byte aligned block)
+        longlong2 x[SCN_VEC];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = i + 32 * k + lane < i1 ? tile_words[i + 32 * k + lane] : 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            incl[k] = x[k];
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const long long t = __shfl_up_sync(kFull, incl[k], dd);
-                if (lane >= dd) incl[k] += t;
-            }
+        for (int k = 0; k < SCN_VEC; ++k) {
+            const int64_t i = i0 + 2 * k;
+            if (i + 1 < nb) x[k] = *reinterpret_cast<const longlong2 *>(tile_words + i);
+            else x[k] = make_longlong2(i < nb ? tile_words[i] : 0, 0);
         }
+        long long sum = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + 32 * k + lane < i1) tile_words[i + 32 * k + lane] = run + incl[k] - x[k];
-            run += __shfl_sync(kFull, incl[k], 31);
+        for (int k = 0; k < SCN_VEC; ++k) sum += x[k].x + x[k].y;
+        long long incl = sum;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const long long t = __shfl_up_sync(kFull, incl, dd);
+            if (lane >= dd) incl += t;
         }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        long long run = s_carry, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const long long y = s_w[w];
+            if (w < warp) run += y;
+            tot += y;
+        }
+        run += incl - sum;
+#pragma unroll
+        for (int k = 0; k < SCN_VEC; ++k) {
+            const int64_t i = i0 + 2 * k;
+            const long long e0 = run, e1 = run + x[k].x;
+            run = e1 + x[k].y;
+            if (i + 1 < nb) *reinterpret_cast<longlong2 *>(tile_words + i) = make_longlong2(e0, e1);
+            else if (i < nb) tile_words[i] = e0;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+        __syncthreads();
     }
     if (tid == 0) {
+        const long long tot = s_carry;
         *total = 4 * tot;
         *out_off_end = 4 * tot;
         if (4 * tot > cap) atomicMax(err, 1);
@@ -3171,17 +3339,18 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
     }
     if ((int)tot != (int)nvals) ok = false;
     if (__syncthreads_or(!ok)) { if (tid == 0) atomicMax(a.err, 5); return; }
-    // ---- the byte walk (VariableByte.java:115-138): v += (c & 127) << shift; a set bit 7 ends the value
+    // ---- the byte walk (VariableByte.java:115-138): v += (c & 127) << shift; a set bit 7 ends the value.  The shift is kept
+    // as a multiplier (1 << shift: one IMAD per byte instead of a shift and an add); past the fifth byte of a value -- which
+    // only the zero bytes after a list's last value reach -- it is 0, and those bytes add nothing either way.
     {
-        uint32_t acc = 0;
-        int sh = 0;
+        uint32_t acc = 0, mul = 1;
         if (q0 > aw && q0 < wspan && !((s_wstart[q0 >> 5] >> (q0 & 31)) & 1u)) { // bytes of a value that began in the previous word
             const uint32_t pv = s_words[q0 - 1];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const uint32_t by = (pv >> (8 * e)) & 255u;
-                if (by & 128u) { acc = 0; sh = 0; }
-                else { acc += (by & 127u) << (sh & 31); sh += 7; }
+                if (by & 128u) { acc = 0; mul = 1; }
+                else { acc += (by & 127u) * mul; mul <<= 7; }
             }
             // (if the previous word is itself a list's first payload word, only its own bytes count: exactly what was walked)
         }
@@ -3195,16 +3364,16 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if ((fl >> k) & 1u) { acc = 0; sh = 0; }
+                    if ((fl >> k) & 1u) { acc = 0; mul = 1; }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const uint32_t by = (w[k] >> (8 * e)) & 255u;
-                        acc += (by & 127u) << (sh & 31);
+                        acc += (by & 127u) * mul;
                         if (by & 128u) {
                             asm volatile("st.shared.u32 [%0], %1;" ::"r"(va ^ ((va >> 3) & 0x70u)), "r"(acc) : "memory");
-                            va += 4; acc = 0; sh = 0;
+                            va += 4; acc = 0; mul = 1;
                         } else
-                            sh += 7;
+                            mul <<= 7;
                     }
                 }
             }
@@ -3384,9 +3553,6 @@ static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
     return (int)g;
 }
 
-constexpr int VB4_THREADS = 128, VB4_VPT = 32;
-using VB4 = V4<VB4_THREADS, VB4_VPT>;
-
 // lists per tile of the flat VariableByte kernels: `target` values per tile on average (the tile's window holds
 // VF_SPAN values / VF_WSPAN words; a tile that overflows is done by the warp-per-list routines inside the kernel)
 static int vbf_lists_per_tile(int64_t total_vals, int64_t nlists, double target, int maxl)
@@ -3486,8 +3652,8 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
             if (pass == 0 && flat) {
                 // size pass, scan of the tiles' word counts (in place, in the state words), emit pass
                 TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (tr.fastpfor ? 2 : 0), tr.fastpfor ? tr.fp_block : 0};
-                if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
-                else k_vb4_tile<VB4_THREADS, VB4_VPT, false, false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                if (a.delta) k_vb4_size<true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                else k_vb4_size<false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 k_vb4_scan<<<1, 1024, 0, ctx->stream>>>(ta.tile_words, a.nbatches, a.total, a.out_off + a.nlists, a.cap, a.err);
                 if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 else k_vb4_tile<VB4_THREADS, VB4_VPT, false, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
