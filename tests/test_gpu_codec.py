@@ -634,3 +634,84 @@ def test_variablebyte_worst_case_fits_the_documented_bound(ctx):
     for cid in (N.CODEC_VB, N.CODEC_VB | N.FLAG_DELTA):
         words = ctx.compress_ints(cid, v)
         assert np.array_equal(np.asarray(words).view(np.int32), cref.compress(cid, v))
+
+
+def _awkward(kind, rng):
+    """list shapes that stress the flat (thread-per-32-values) kernels: tile boundaries, empty lists, long lists, wide values"""
+    if kind == "breach":
+        return cases.breach_like_lists(rng, 3000, 10000, 0.01)
+    if kind == "tiny":        # many empty / one-value lists: up to 127 lists per tile
+        lens = rng.integers(0, 4, 5000)
+    elif kind == "mixed":     # 0..250 values: a tile holds 4 000 positions, lists straddle every thread boundary
+        lens = rng.integers(0, 250, 800)
+    elif kind == "wide":      # values that need 3-5 bytes (negative ints, unsorted data: wrapped deltas)
+        lens = rng.integers(0, 120, 1500)
+    elif kind == "long":      # lists longer than a tile next to short ones (VariableByte alone: no block limit)
+        lens = np.concatenate([rng.integers(0, 60, 300), [5000, 0, 4096, 4095, 1, 9000], rng.integers(0, 60, 100)])
+    elif kind == "exact":     # lists of exactly 32 / 64 / 128 values: list starts fall on thread boundaries
+        lens = rng.choice([32, 64, 128, 0, 96], 700)
+    off = np.zeros(lens.size + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    if kind == "wide":
+        vals = rng.integers(-2**31, 2**31 - 1, off[-1]).astype(np.int32)
+    else:
+        vals = np.concatenate([np.sort(rng.integers(0, 50000, int(l))) for l in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    return vals, off
+
+
+@pytest.mark.parametrize("kind", ["breach", "tiny", "mixed", "wide", "long", "exact"])
+@pytest.mark.parametrize("shift", [0, 1, 3], ids=["aligned", "shift1", "shift3"])
+def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
+    """The flat VariableByte kernels (size pass + tile scan + emit pass; tile-per-CTA decoder) against the oracle, list by
+    list, on shapes chosen to hit their edges; device buffers start `shift` ints off a 16-byte boundary (the kernels align
+    their windows themselves) and are followed by guard words."""
+    rng = np.random.default_rng(1000 + shift)
+    vals, off = _awkward(kind, rng)
+    nl, total = off.size - 1, int(vals.size)
+    codecs = [N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB]
+    if kind not in ("long",):
+        codecs += [N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_SK_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB]
+    guard = np.full(256, 0x5AC3A55A, np.uint32)
+    ctx.set_option("short_list_codec", 2)
+    ctx.set_option("flat_codec", 1)
+    try:
+        for cid in codecs:
+            for fr in (N.FRAME_APP, N.FRAME_WORDS):
+                want = [cref.get_compressed_instruments(cid, vals[off[i]:off[i + 1]]) if fr == N.FRAME_APP
+                        else cref.compress(cid, vals[off[i]:off[i + 1]]).tobytes() for i in range(nl)]
+                enc_bytes = sum(len(w) for w in want)
+                sizes = {"vals": 4 * total, "off": 8 * (nl + 1), "ooff": 8 * (nl + 1), "enc": enc_bytes, "back": 4 * total}
+                bufs = {k: ctx.dev_alloc(v + guard.nbytes + 64) for k, v in sizes.items()}
+                sh = {k: (4 * shift if k in ("vals", "enc", "back") else 0) for k in sizes}
+                try:
+                    for k, v in sizes.items():
+                        ctx.h2d(bufs[k] + sh[k] + v, guard)
+                    if total:
+                        ctx.h2d(bufs["vals"] + sh["vals"], vals)
+                    ctx.h2d(bufs["off"], off)
+                    got = ctx.codec_encode_dev(cid, fr, bufs["vals"] + sh["vals"], bufs["off"], nl, total, bufs["ooff"],
+                                               bufs["enc"] + sh["enc"], enc_bytes)
+                    assert got == enc_bytes, (kind, hex(cid), fr)
+                    ooff = np.empty(nl + 1, np.int64)
+                    ctx.d2h(ooff, bufs["ooff"])
+                    out = np.empty(enc_bytes, np.uint8)
+                    if enc_bytes:
+                        ctx.d2h(out, bufs["enc"] + sh["enc"])
+                    assert ooff[0] == 0 and ooff[-1] == enc_bytes
+                    for i in range(nl):
+                        assert bytes(out[ooff[i]:ooff[i + 1]]) == want[i], (kind, hex(cid), fr, i)
+                    ctx.codec_decode_dev(cid, fr, bufs["enc"] + sh["enc"], bufs["ooff"], nl, bufs["back"] + sh["back"], bufs["off"])
+                    back = np.empty(total, np.int32)
+                    if total:
+                        ctx.d2h(back, bufs["back"] + sh["back"])
+                    assert np.array_equal(back, vals), (kind, hex(cid), fr)
+                    for k, v in sizes.items():
+                        g = np.empty_like(guard)
+                        ctx.d2h(g, bufs[k] + sh[k] + v)
+                        assert np.array_equal(g, guard), f"guard after `{k}` overwritten ({kind}, {hex(cid)}, {fr})"
+                finally:
+                    for q in bufs.values():
+                        ctx.dev_free(q)
+    finally:
+        ctx.set_option("short_list_codec", 1)
+        ctx.set_option("flat_codec", FLAT_DEFAULT)
