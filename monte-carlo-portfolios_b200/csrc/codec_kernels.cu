@@ -2551,19 +2551,12 @@ __global__ void __launch_bounds__(32, SL_DCTAS) k_sl_decode(const FastDecArgs a,
 // skippable forms of the same, and VariableByte alone.
 //
 // The thread-per-list kernels above walk a list serially (~45 instructions per value, a warp as slow as its longest
-// list).  Here a CTA owns a TILE of consecutive lists and works on the tile's values as ONE flat array:
-//   encode  a thread owns 8 consecutive values of a 16-byte-aligned window over `vals` (two LDG.128, fully coalesced);
-//           list starts are one bit per window position in shared memory; gaps, byte lengths, ONE block scan of
-//           (bytes | starts << 16) gives every value its byte offset in the tile and its list; per-list sizes, framing words
-//           and the tile's place in the output (decoupled look-back on one state word per tile, published BEFORE the bytes
-//           are written) are one warp's work; bytes go to a staging area with byte stores, the tile leaves with coalesced
-//           word stores (byte-swapped for the loader's framing);
-//   decode  a thread owns 4 consecutive compressed words (one LDG.128): terminator-bit popcounts, one block scan, a
-//           16-byte serial walk that restarts at every list's first payload word (the Java decoder starts each list with
-//           v = 0, shift = 0), values into a staging area aligned like the output; then 8 values per thread: flat
-//           prefix sums minus the sum at the list's start (Delta.inverseDelta), two STG.128 per thread.
-// A tile that does not fit (window, staging area) is done by the warp-per-list routines inside the same kernel; a
-// FastPFOR list of a whole block or more raises flag 2 and the host takes the batched kernels, as before.
+// list).  Here a CTA owns a TILE of consecutive whole lists and works on the tile's values as ONE flat array, one tile per CTA,
+// with no state shared between CTAs:
+//   encode  k_vb4_size (words per tile) -> k_vb4_scan (one CTA: where every tile goes) -> k_vb4_tile<.., EMIT> (the bytes);
+//   decode  k_vb4_decode (the output offsets are an input: one launch).
+// Each kernel's comment says how.  A tile that does not fit its window / staging areas is done by the warp-per-list routines
+// inside the same kernel; a FastPFOR list of a whole block or more raises flag 2 and the host takes the batched kernels.
 __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *gsrc)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -2576,8 +2569,9 @@ __device__ __forceinline__ void cp_async16(uint32_t *smem_dst, const uint32_t *g
 // the 10^8 ints of C4: with tiles this small (a tile's time on an SM is about one L2 round trip) the decoupled look-back is
 // the clock of the kernel: the frontier of known output positions advances by one poll window per round trip, and a grid in
 // lock step waits for its slowest member at every tile (47 % of the stall samples at the barrier behind the look-back).
-// So the output position of a tile comes from a SIZE pass instead: the same tile kernel without its second half writes the
-// tile's word count, one CTA scans the ~25 000 counts, and the EMIT pass knows where it writes before it starts -- no state
+// So the output position of a tile comes from a SIZE pass instead: k_vb4_size (below; this kernel with EMIT = false computes the
+// same number from its own prefixes -- it was the first size pass, 82 us instead of 75) writes the tile's word count, one CTA scans the
+// ~26 000 counts, and the EMIT pass knows where it writes before it starts -- no state
 // words, no polling, no residency requirement: one tile per CTA, the hardware scheduler does the balancing, and the input is
 // read twice (HBM is not the bound here).
 // The tile kernel: THREADS x VPT consecutive values per tile (a fixed number of whole lists); values arrive by coalesced 16-byte
