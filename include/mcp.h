@@ -103,8 +103,9 @@ int  mcp_sync(mcp_ctx *ctx);
  * for the rows where the bet fails), "fast_codec" (0 = warp-per-list codec kernels only), "short_list_codec" (0 / 1 / 2:
  * thread-per-list codec kernels off / where they are the faster ones / for every codec), "flat_codec" (1 (default) = short
  * lists that are all VariableByte -- FastPFOR / FastPFOR128 below one block, VariableByte alone -- take the flat kernels: a
- * thread per 32 consecutive values, size pass + tile scan + emit pass; 0 = the thread-per-list kernels), "reg_select" / "small_select"
- * (0 = dense-step selection staged in shared memory / 256-thread selection CTAs for small tails), "dense_floor"
+ * thread per 32 consecutive values, size pass + tile scan + emit pass; 0 = the thread-per-list kernels), "reg_select" / "small_select" /
+ * "warp_select" (0 = dense-step selection staged in shared memory / 256-thread selection CTAs for small tails / no warp-per-row
+ * selection of the sparse step for rows of <= 512 candidates), "dense_floor"
  * (smallest dense sample in trials, default 1024; process-wide), "overlap_tiles" (> 1 = portfolio tiles alternate between
  * two streams), "item_trials" (trials per valuation work item), "upload_split" (0 = mcp_simulate uploads the scenario
  * tail in one part), "ts_slack" (trial-sharded test hook).  Trial indices, breach lists and byte streams are identical

@@ -107,6 +107,7 @@ struct mcp_ctx {
     cudaEvent_t evTileFork = nullptr, evTileJoin = nullptr, evSfrag = nullptr;
     int64_t overlapTiles = 1;      // >1: that many portfolio tiles alternate between two streams (selection of one tile under the valuation of the next); with 8-warp valuation CTAs: C2 2.79 -> 2.70 ms, C3 6.85 -> 6.70 ms per 125 000 rows (round 1, 16-warp CTAs: -2 % at best).  Off by default: the two-calls-in-flight pipeline of mcp_simulate gets the same overlap across steps (2.75 ms e2e), and per-kernel event times stay those of kernels running alone
     mcp::DevBuf dCandKey2, dCandCnt2;
+    mcp::DevBuf dOvf;                  // [2][tile rows + 16] rows the warp-per-row selection handed back (count, then row indices)
     cudaStream_t stream2 = nullptr; // side stream: the moments (independent of the selection chain) overlap the valuation
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evTail = nullptr, evTail1 = nullptr;
     bool sTailPending = false;     // pipelined upload: scenario rows >= sHeadRows are still arriving on stream2 (evTail)
@@ -125,6 +126,7 @@ struct mcp_ctx {
     mcp::DevBuf dGram;
     int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
+    bool warpSelect = true;        // small rows (dense samples of <= 1 024 values, <= 512 staged candidates): one warp per row
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
     int flatCodec = 1;             // 1 = flat (thread per 32 values) VariableByte kernels for short lists that are all VariableByte (default); 0 = thread-per-list kernels

@@ -855,6 +855,8 @@ struct SelArgs {
     int *fail_cnt;             // optimistic bound (see risk_run_stream): rows with fewer than `tail` candidates are
     int32_t *fail_rows;        // appended here (row index) and redone by the guaranteed schedule; null otherwise
     int64_t row_base;          // global index of row 0 (for fail_rows)
+    const int32_t *rows;       // k_select_t_list: the CTAs walk rows[0 .. *nrows) (the rows a warp-per-row kernel handed back)
+    const int *nrows;
 };
 
 __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 */)
@@ -934,7 +936,27 @@ __device__ __forceinline__ void for_each_global(const SelArgs &a, int64_t row, c
 // THREADS = 256 for tails of a thousand trials, 64 for small tails (t ~ 100: a 256-thread CTA per row would spend its
 // time in barriers); the digit widths follow so that the histogram scans stay one pass per thread.
 template <int THREADS>
+__device__ void select_t_row(const SelArgs &a, int64_t row);
+
+// one CTA per row ...
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_select_t(const SelArgs a)
+{
+    select_t_row<THREADS>(a, blockIdx.x);
+}
+// ... or a grid-stride walk over the listed rows (what a warp-per-row kernel handed back: usually none)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_select_t_list(const SelArgs a)
+{
+    const int n = *a.nrows;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        select_t_row<THREADS>(a, (int64_t)a.rows[b]);
+        __syncthreads();
+    }
+}
+
+template <int THREADS>
+__device__ void select_t_row(const SelArgs &a, const int64_t row)
 {
     constexpr int SEL_BITS = THREADS >= 256 ? 11 : 8, SEL_BINS = 1 << SEL_BITS; // general path: digits of the 96-bit composite
     constexpr int FS_BITS = THREADS >= 256 ? 10 : 8, FS_BINS = 1 << FS_BITS;    // staged path: bins per range-adaptive pass
@@ -949,7 +971,6 @@ __global__ void __launch_bounds__(THREADS) k_select_t(const SelArgs a)
     __shared__ double red[32];
     __shared__ int s_wsum[THREADS / 32];
     __shared__ int s_sel, s_above, s_bucket, s_ncand, s_nkept;
-    const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
     uint64_t *kk = a.kept_key_out + row * t;
     int32_t *ki = a.kept_idx_out + row * t;
@@ -1345,7 +1366,16 @@ __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need,
 }
 
 template <int ITEMS, int THREADS>
+__device__ void select_dense_row(const SelArgs &a, int64_t row);
+
+template <int ITEMS, int THREADS>
 __global__ void __launch_bounds__(THREADS, (ITEMS > 8 ? 3 : 4) * (256 / THREADS)) k_select_dense(const SelArgs a)
+{
+    select_dense_row<ITEMS, THREADS>(a, blockIdx.x);
+}
+
+template <int ITEMS, int THREADS>
+__device__ void select_dense_row(const SelArgs &a, const int64_t row)
 {
     __shared__ int hist[FS_BINS];
     __shared__ uint64_t ckey[FS_SORT];
@@ -1353,7 +1383,6 @@ __global__ void __launch_bounds__(THREADS, (ITEMS > 8 ? 3 : 4) * (256 / THREADS)
     __shared__ double s_red[2 * (THREADS / 32)];
     __shared__ int s_wsum[THREADS / 32];
     __shared__ int s_sel, s_above, s_bucket;
-    const int64_t row = blockIdx.x;
     const int64_t t = a.tail;
     const int n = (int)a.step_len;
     uint64_t *kk = a.kept_key_out + row * t;
@@ -1526,6 +1555,218 @@ __global__ void __launch_bounds__(THREADS, (ITEMS > 8 ? 3 : 4) * (256 / THREADS)
     }
 }
 
+// ============================================================ selection, one WARP per row (sparse steps of small rows)
+// The CTA-per-row kernel spends a small row's time on its fixed work: C3 (10 000 trials, tail 101) hands k_select_t<64> ~340
+// candidates per row, and ncu counts 280 thread instructions per CANDIDATE for it (a 256-bin histogram zeroed and scanned, a
+// dozen CTA barriers, per-segment books by 64 threads): 0.73 ms for 125 000 rows.  Here a warp owns a row: 128 bins (four per
+// lane, found by one shuffle scan), a 32-element boundary bucket ranked by one lane per element, warp barriers only, four
+// independent rows per CTA: 0.48 ms.  Same results: the top `tail` of (loss key, trial) exactly, in any order, and the tail-th
+// largest as the VaR order statistic.  A row that does not fit (more staged candidates than WS_CAP: hostile trial orders) is
+// appended to a list and redone by the CTA-per-row kernel right after (k_select_t_list): exactness never depends on the row
+// being small.  (The same for the dense first step -- 1 024 values per row in a warp's registers -- was measured at 0.57 ms
+// against 0.55 for k_select_dense<8,128> and dropped: per-slot ballots and 167 registers.)
+constexpr int WS_WARPS = 4;     // rows per CTA
+constexpr int WS_CAP = 512;     // staged candidates per row
+constexpr int WS_BITS = 7, WS_BINS = 1 << WS_BITS; // bins per range-adaptive pass: four per lane
+constexpr int WS_SORT = 32;     // rank-sorted boundary bucket: one lane per element
+constexpr int WS_MAXSEG = 64;   // segments of a sparse step the warp keeps books for (two per lane)
+
+struct WsRow { // one warp's shared memory
+    uint64_t key[WS_CAP];
+    uint32_t idx[WS_CAP];
+    int hist[WS_BINS];
+    uint64_t ckey[WS_SORT];
+    uint32_t cidx[WS_SORT];
+    int segoff[WS_MAXSEG + 2];
+};
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(kFullMask, v, d); v = o < v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v)
+{
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { const uint64_t o = __shfl_xor_sync(kFullMask, v, d); v = o > v ? o : v; }
+    return v;
+}
+
+// From the warp's histogram (bins descending from WS_BINS-1, lane 0 owns the four highest): the bin where the count from the
+// top reaches `need`, the count above it and its own population.
+__device__ __forceinline__ void ws_boundary_bin(const int *hist, int need, int lane, int &sel, int &above, int &bucket)
+{
+    const int hb = WS_BINS - 1 - 4 * lane;
+    const int h0 = hist[hb], h1 = hist[hb - 1], h2 = hist[hb - 2], h3 = hist[hb - 3];
+    const int sum = h0 + h1 + h2 + h3;
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int excl = incl - sum;
+    const bool mine = excl < need && need <= incl;
+    int s = 0, ab = 0, bu = 0;
+    if (mine) {
+        ab = excl;
+        if (need <= ab + h0) { s = hb; bu = h0; }
+        else if (need <= ab + h0 + h1) { s = hb - 1; ab += h0; bu = h1; }
+        else if (need <= ab + h0 + h1 + h2) { s = hb - 2; ab += h0 + h1; bu = h2; }
+        else { s = hb - 3; ab += h0 + h1 + h2; bu = h3; }
+    }
+    const unsigned who = __ballot_sync(kFullMask, mine);
+    const int src = who ? __ffs(who) - 1 : 0;
+    sel = __shfl_sync(kFullMask, s, src);
+    above = __shfl_sync(kFullMask, ab, src);
+    bucket = __shfl_sync(kFullMask, bu, src);
+}
+
+// The top `need` of the M staged candidates of W (need <= M <= WS_CAP) by (key, trial), written to kk / ki slots
+// [out0, out0 + need) in any order; the need-th largest is the VaR order statistic (so far).
+__device__ __forceinline__ void ws_select(WsRow &W, int M, int need, int out0, uint64_t mn, uint64_t mx, uint64_t *kk, int32_t *ki, const SelArgs &a,
+                                          int64_t row, int lane)
+{
+    uint64_t lo = warp_min_u64(mn), hi = warp_max_u64(mx); // (mn / mx: this lane's share of the staged keys' range)
+    bool on_idx = false;      // ties: more than WS_SORT candidates share one loss value -> continue on the trial index
+    uint64_t kstar = 0, blo = lo, bhi = hi;
+    int bucket = M, rem = need; // rem: rank from the top still to resolve inside the boundary bucket
+    for (int pass = 0; pass < 16; ++pass) {
+        const uint64_t width = hi - lo;
+        const int shift = width < (uint64_t)WS_BINS ? 0 : (64 - __clzll((long long)width)) - WS_BITS;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) W.hist[lane + 32 * b] = 0;
+        __syncwarp();
+        for (int i = lane; i < M; i += 32) {
+            const uint64_t k = W.key[i];
+            if (on_idx) { if (k == kstar) { const uint64_t v = W.idx[i]; if (v >= lo && v <= hi) atomicAdd(&W.hist[(int)((v - lo) >> shift)], 1); } }
+            else if (k >= lo && k <= hi) atomicAdd(&W.hist[(int)((k - lo) >> shift)], 1);
+        }
+        __syncwarp();
+        int sel, above;
+        ws_boundary_bin(W.hist, rem, lane, sel, above, bucket);
+        rem -= above;
+        blo = lo + ((uint64_t)sel << shift);
+        bhi = shift == 0 ? blo : blo + ((1ull << shift) - 1);
+        if (bhi > hi) bhi = hi;
+        __syncwarp();
+        if (bucket <= WS_SORT) break;
+        if (shift == 0) {
+            if (on_idx) break; // cannot happen: trial indices are distinct
+            on_idx = true;
+            kstar = blo;
+            lo = 0; hi = 0xffffffffull;
+        } else { lo = blo; hi = bhi; }
+    }
+    // --- gather: strictly above the boundary bin (need - rem of them) -> kept; inside it -> the bucket (ballot-ranked slots)
+    int nk = 0, nb = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int b0 = 0; b0 < M; b0 += 32) {
+        const int i = b0 + lane;
+        int rel = -1; // +1 above, 0 inside, -1 below / out of range
+        uint64_t k = 0;
+        uint32_t id = 0;
+        if (i < M) {
+            k = W.key[i]; id = W.idx[i];
+            if (!on_idx) rel = k > bhi ? 1 : (k >= blo ? 0 : -1);
+            else if (k != kstar) rel = k > kstar ? 1 : -1;
+            else rel = (uint64_t)id > bhi ? 1 : ((uint64_t)id >= blo ? 0 : -1);
+        }
+        const unsigned mk = __ballot_sync(kFullMask, rel > 0), mc = __ballot_sync(kFullMask, rel == 0);
+        if (rel > 0) { const int o = out0 + nk + __popc(mk & lt); kk[o] = k; ki[o] = (int32_t)id; }
+        else if (rel == 0) { const int o = nb + __popc(mc & lt); if (o < WS_SORT) { W.ckey[o] = k; W.cidx[o] = id; } }
+        nk += __popc(mk); nb += __popc(mc);
+    }
+    __syncwarp();
+    // --- rank the bucket by (key, trial) descending: rank = number of larger elements
+    const int base = out0 + need - rem; // == out0 + nk
+    if (lane < bucket && lane < WS_SORT) {
+        const uint64_t mk = W.ckey[lane];
+        const uint32_t mi = W.cidx[lane];
+        int rank = 0;
+        for (int j = 0; j < bucket; ++j) {
+            const uint64_t kj = W.ckey[j];
+            rank += (kj > mk || (kj == mk && W.cidx[j] > mi)) ? 1 : 0;
+        }
+        if (rank < rem) { kk[base + rank] = W.ckey[lane]; ki[base + rank] = (int32_t)W.cidx[lane]; }
+        if (rank == rem - 1) { // the need-th largest candidate is the VaR order statistic (so far)
+            const double vl = fkey_inv(W.ckey[lane]);
+            a.var_loss[row] = vl;
+            a.var_trial[row] = (int32_t)W.cidx[lane];
+            if (a.tkey) a.tkey[row] = fkey(0.0 - vl); // canonical +0.0 for a zero loss, so V = -0.0 and +0.0 both pass
+        }
+    }
+    __syncwarp();
+}
+
+// sparse step (and any step whose candidates are the kept tail + lane-private segments of records): M <= WS_CAP staged
+__global__ void __launch_bounds__(WS_WARPS * 32) k_wsel_sparse(const SelArgs a, int64_t rows, int *ovf_cnt, int32_t *ovf_rows)
+{
+    __shared__ WsRow s_rows[WS_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * WS_WARPS + warp;
+    if (row >= rows) return;
+    WsRow &W = s_rows[warp];
+    const int t = (int)a.tail;
+    uint64_t *kk = a.kept_key_out + row * a.tail;
+    int32_t *ki = a.kept_idx_out + row * a.tail;
+    const int kn = (int)a.kept_n;
+    // a row that already lost its optimistic bet at an earlier step stays lost (it is redone separately)
+    if (kn > 0 && a.kept_idx_in[row * a.kept_n] < 0) {
+        if (lane == 0) ki[0] = -1;
+        return;
+    }
+    // ---- segment books: exclusive prefix of the counts (two segments per lane)
+    int c0 = lane < a.nsub ? a.cnt[row * a.nsub + lane] : 0;
+    int c1 = lane + 32 < a.nsub ? a.cnt[row * a.nsub + lane + 32] : 0;
+    int i0 = c0, i1 = c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u0 = __shfl_up_sync(kFullMask, i0, d), u1 = __shfl_up_sync(kFullMask, i1, d);
+        if (lane >= d) { i0 += u0; i1 += u1; }
+    }
+    const int tot0 = __shfl_sync(kFullMask, i0, 31), total = tot0 + __shfl_sync(kFullMask, i1, 31);
+    const int M = kn + total;
+    if (M < t) {
+        // only possible under an optimistic filter bound that turned out too tight for this row: report the row (it is
+        // redone with the guaranteed schedule) and mark its kept list so that the finalize kernel skips it
+        if (lane == 0) {
+            ki[0] = -1;
+            if (a.fail_cnt) a.fail_rows[atomicAdd(a.fail_cnt, 1)] = (int32_t)(a.row_base + row);
+        }
+        return;
+    }
+    if (M > WS_CAP) { // does not fit the warp's staging area: the CTA-per-row kernel redoes the row
+        if (lane == 0) ovf_rows[atomicAdd(ovf_cnt, 1)] = (int32_t)row;
+        return;
+    }
+    W.segoff[lane] = i0 - c0;
+    W.segoff[lane + 32] = tot0 + i1 - c1;
+    if (lane == 0) W.segoff[WS_MAXSEG] = total;
+    // ---- stage: the kept tail, then the records (every lane labels the slots of its segments, a flat loop loads them)
+    uint64_t mn = ~0ull, mx = 0;
+    for (int i = lane; i < kn; i += 32) {
+        const uint64_t k = a.kept_key_in[row * a.kept_n + i];
+        W.key[i] = k; W.idx[i] = (uint32_t)a.kept_idx_in[row * a.kept_n + i];
+        mn = k < mn ? k : mn; mx = k > mx ? k : mx;
+    }
+    for (int j = 0; j < c0; ++j) W.idx[kn + i0 - c0 + j] = (uint32_t)lane;
+    for (int j = 0; j < c1; ++j) W.idx[kn + tot0 + i1 - c1 + j] = (uint32_t)(lane + 32);
+    __syncwarp();
+    const int4 *R = reinterpret_cast<const int4 *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
+    for (int i = lane; i < total; i += 32) {
+        const int g = (int)W.idx[kn + i];
+        const int4 rec = __ldg(R + (int64_t)g * a.sub_len + (i - W.segoff[g]));
+        const uint64_t k = fkey(0.0 - __hiloint2double(rec.y, rec.x));
+        W.key[kn + i] = k;
+        W.idx[kn + i] = (uint32_t)rec.z;
+        mn = k < mn ? k : mn; mx = k > mx ? k : mx;
+    }
+    __syncwarp();
+    ws_select(W, M, t, 0, mn, mx, kk, ki, a, row, lane);
+}
+
 static size_t sel_smem_bytes(int cap, int nseg, int threads = SEL_THREADS)
 {
     return (size_t)cap * 12 + (size_t)(threads >= 256 ? SEL_BINS_MAX : 256) * 4 + (size_t)(nseg + 2) * 4;
@@ -1537,6 +1778,12 @@ static cudaError_t sel_configure(int bytes)
     cudaError_t e = cudaFuncSetAttribute(k_select_t<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_select_t<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_select_t_list<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_select_t_list<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_select_t_list<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_select_t<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
@@ -1998,6 +2245,7 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
         MCP_CUDA(ctx, candCnt[i]->reserve((size_t)Pt * max_nsub * 4 * sizeof(int32_t)));
     }
     if (io.moments) MCP_CUDA(ctx, ctx->dPart.reserve((size_t)P * nparts * 2 * sizeof(double)));
+    MCP_CUDA(ctx, ctx->dOvf.reserve((size_t)2 * (Pt + 16) * sizeof(int32_t))); // rows handed back by the warp-per-row selection
     MCP_TRY(ensure_sfrag(ctx));
     cudaStream_t tile_stream[2] = {ctx->stream, ctx->stream3};
     if (nstreams == 2) {
@@ -2103,8 +2351,29 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
                 a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
-                // rows of <= 2 048 values: 128-thread CTAs (six rows resident per SM: the kernel is latency-bound per row)
-                if (reg && a.step_len <= 8 * 128) k_select_dense<8, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
+                // sparse steps of small rows: one WARP per row; the rows that do not fit come back in a list and take the kernels below
+                const bool wsparse = !dense && ctx->warpSelect && a.kept_segs <= 1 && a.nsub <= WS_MAXSEG && a.tail <= WS_CAP &&
+                                     a.kept_n + 4 * t + 64 <= WS_CAP;
+                if (wsparse) {
+                    int *ovf_cnt = ctx->dOvf.as<int>() + (size_t)sidx_ * (Pt + 16);
+                    int32_t *ovf_rows = ovf_cnt + 4;
+                    MCP_CUDA(ctx, cudaMemsetAsync(ovf_cnt, 0, sizeof(int), cur_stream(ctx)));
+                    k_wsel_sparse<<<(unsigned)((rows + WS_WARPS - 1) / WS_WARPS), WS_WARPS * 32, 0, cur_stream(ctx)>>>(a, rows, ovf_cnt, ovf_rows);
+                    MCP_TRY(check_launch(ctx, "k_wsel_sparse"));
+                    a.rows = ovf_rows;
+                    a.nrows = ovf_cnt;
+                }
+                if (wsparse) {
+                    // the rows handed back (usually none): a grid-stride walk of a small grid over the list
+                    const unsigned sgrid = (unsigned)std::min<int64_t>(rows, 2 * ctx->prop.multiProcessorCount);
+                    if (ctx->smallSelect && a.kept_n + 4 * t + 64 <= 1024) {
+                        a.cap = 1024;
+                        k_select_t_list<64><<<sgrid, 64, sel_smem_bytes(a.cap, a.nsub, 64), cur_stream(ctx)>>>(a);
+                    } else if (sel_smem_bytes(a.cap, a.nsub) > 110 * 1024)
+                        k_select_t_list<1024><<<sgrid, 1024, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
+                    else
+                        k_select_t_list<256><<<sgrid, 256, sel_smem_bytes(a.cap, a.nsub), cur_stream(ctx)>>>(a);
+                } else if (reg && a.step_len <= 8 * 128) k_select_dense<8, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
                 else if (reg && a.step_len <= 16 * 128) k_select_dense<16, 128><<<(unsigned)rows, 128, 0, cur_stream(ctx)>>>(a);
                 else if (reg && a.step_len <= 16 * SEL_THREADS) k_select_dense<16, 256><<<(unsigned)rows, 256, 0, cur_stream(ctx)>>>(a);
                 else if (!dense && ctx->smallSelect && a.kept_n + 4 * t + 64 <= 1024) {

@@ -96,12 +96,12 @@ def test_tile_overlap_on_two_streams_gives_identical_results(ctx):
         assert np.array_equal(r1[k], r4[k]) and np.array_equal(r1[k], r4g[k]), k
 
 
-@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic", "small_select"])
+@pytest.mark.parametrize("opt", ["force_dense", "force_sort_finalize", "fused_moments", "reg_select", "optimistic", "small_select", "warp_select"])
 def test_alternate_kernel_paths_agree(ctx, opt):
     """F = 32 normally takes the streaming kernels (two-step optimistic schedule, dense-step selection from
     registers) + bitmap compaction; the dense tile + single selection, the sort-based breach list, the fused
     per-trial moments, the shared-memory selection and the guaranteed schedule must give identical results."""
-    default = 1 if opt in ("reg_select", "optimistic", "small_select") else 0
+    default = 1 if opt in ("reg_select", "optimistic", "small_select", "warp_select") else 0
     ctx.set_option(opt, 1 - default)
     try:
         E, S = riskcases.synthetic(40, 9000, 32, 21)
@@ -179,6 +179,28 @@ def test_ties_break_by_trial_index(ctx):
     check_against_oracle(ctx, E, S, 0.75)
     E, S = riskcases.with_ties(70, 40000, 32, 11)  # same through the F = 32 streaming path
     check_against_oracle(ctx, E, S, 0.75, rows=[0, 1, 35, 69])
+
+
+@pytest.mark.parametrize("warp", [1, 0], ids=["warp-per-row", "cta-per-row"])
+def test_small_tails_on_hostile_rows(ctx, warp):
+    """Tails of ~100 trials (the C3 shape) take the warp-per-row selection of the sparse step.  Rows it cannot hold -- trial
+    orders that make every trial a candidate -- are handed back in a list and redone by the CTA-per-row kernel; rows whose
+    optimistic bound was too tight are reported and redone with the guaranteed schedule; heavy ties are broken by trial
+    index.  All in one run, next to ordinary rows, against the oracle; identical with the warp kernel switched off."""
+    F, Nn, P = 64, 10000, 96
+    E, S = riskcases.synthetic(P, Nn, F, 77)
+    S[:, 0] = np.linspace(0.0, 1.0, Nn)            # a trend in factor 0 ...
+    E[:, 0] = 0.0
+    E[0::4, 0] = 5.0e4                             # ... that dominates these rows: losses descend with the trial index (the bet fails)
+    E[1::4, 0] = -5.0e4                            # ... losses ascend: every trial beats the sample's bound (the row does not fit a warp)
+    Et, St = riskcases.with_ties(8, Nn, F, 78)     # heavily tied losses (integer inputs), in a run of their own
+    ctx.set_option("warp_select", warp)
+    try:
+        check_against_oracle(ctx, E, S, 0.99, rows=list(range(0, P, 5)) + [1, 2, 3, P - 1])
+        assert ctx.run_stats()["fallback_rows"] == len(range(0, P, 4))
+        check_against_oracle(ctx, Et, St, 0.99)
+    finally:
+        ctx.set_option("warp_select", 1)
 
 
 def test_degenerate_rows(ctx):
