@@ -126,6 +126,7 @@ struct mcp_ctx {
     mcp::DevBuf dGram;
     int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
+    int selSlack = 0;              // extra entries of the sparse steps' staging area (experiment knob)
     bool warpSelect = true;        // small rows (dense samples of <= 1 024 values, <= 512 staged candidates): one warp per row
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)

@@ -169,6 +169,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "short_list_codec")) ctx->shortListCodec = (int)(value < 0 ? 0 : value > 2 ? 2 : value);
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "warp_select")) ctx->warpSelect = value != 0;
+    else if (!strcmp(key, "sel_slack")) ctx->selSlack = (int)value;
     else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);

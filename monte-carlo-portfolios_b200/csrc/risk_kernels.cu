@@ -962,10 +962,13 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
     constexpr int FS_BITS = THREADS >= 256 ? 10 : 8, FS_BINS = 1 << FS_BITS;    // staged path: bins per range-adaptive pass
     constexpr int FS_SORT = THREADS >= 256 ? 96 : 64;                           // ... and its rank-sorted bucket (one thread per element)
     extern __shared__ __align__(16) unsigned char sel_smem[];
-    uint64_t *skey = reinterpret_cast<uint64_t *>(sel_smem);
+    // layout: [segoff: nsub + 2 ints, rounded up to 16 bytes] then EITHER the staging area and the staged path's histogram
+    // ([cap] keys, [cap] trials, FS_BINS bins) OR the general path's wider histogram (SEL_BINS bins; it stages nothing)
+    int *segoff = reinterpret_cast<int *>(sel_smem); // [nsub + 1] exclusive prefix of the segment counts (sparse steps)
+    unsigned char *area = sel_smem + (((size_t)(a.nsub + 2) * 4 + 15) & ~(size_t)15);
+    uint64_t *skey = reinterpret_cast<uint64_t *>(area);
     uint32_t *sidx = reinterpret_cast<uint32_t *>(skey + a.cap);
     int *hist = reinterpret_cast<int *>(sidx + a.cap);
-    int *segoff = hist + SEL_BINS; // [nsub + 1] exclusive prefix of the segment counts (sparse steps)
     __shared__ uint64_t ckey[SEL_SORT];
     __shared__ uint32_t cidx[SEL_SORT];
     __shared__ double red[32];
@@ -1207,6 +1210,7 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
         return;
     }
     // ===== general path: more candidates than shared memory holds; digit passes straight from global memory
+    hist = reinterpret_cast<int *>(area); // (nothing is staged: the wider histogram takes the staging area's place)
     auto for_each = [&](auto f) { for_each_global<THREADS>(a, row, segoff, f); };
 
     // Radix select on the 64-bit loss key first (cheap 64-bit digit extraction); the trial index only breaks ties,
@@ -1769,7 +1773,10 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsel_sparse(const SelArgs a, 
 
 static size_t sel_smem_bytes(int cap, int nseg, int threads = SEL_THREADS)
 {
-    return (size_t)cap * 12 + (size_t)(threads >= 256 ? SEL_BINS_MAX : 256) * 4 + (size_t)(nseg + 2) * 4;
+    const size_t seg = ((size_t)(nseg + 2) * 4 + 15) & ~(size_t)15;
+    const size_t staged = (size_t)cap * 12 + (size_t)(threads >= 256 ? 1024 : 256) * 4;  // keys, trials, the staged path's bins
+    const size_t general = (size_t)(threads >= 256 ? SEL_BINS_MAX : 256) * 4;            // the general path's bins
+    return seg + (staged > general ? staged : general);
 }
 
 // opt-in to the large dynamic shared memory of both instantiations
@@ -2349,7 +2356,7 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
                 KScope ks(ctx, MCP_K_SELECT);
                 // sparse steps stage kept + ~2.2 t candidates (optimistic) or ~2 t (guaranteed): a smaller staging area
                 // than the dense step's 4 t buys a resident CTA per SM more; rows beyond it take the global path
-                a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 3 * t + 512));
+                a.cap = dense ? ctx->selCap : (int)std::min<int64_t>(ctx->selCap, std::max<int64_t>(2304, 2 * t + 900 + ctx->selSlack));
                 const bool reg = dense && ctx->regSelect && a.tail <= a.step_len; // the row fits the CTA's registers
                 // sparse steps of small rows: one WARP per row; the rows that do not fit come back in a list and take the kernels below
                 const bool wsparse = !dense && ctx->warpSelect && a.kept_segs <= 1 && a.nsub <= WS_MAXSEG && a.tail <= WS_CAP &&
