@@ -1338,12 +1338,12 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
 // passes, the gather and the boundary-bucket sort run without staging anything in shared memory -- 5 KB of shared
 // memory per CTA instead of ~60 KB, so the SM holds as many rows as its registers allow.
 // from the histogram (bins descending from FS_BINS-1): the bin where the count from the top reaches `need`
-template <int THREADS>
+template <int THREADS, int BINS = FS_BINS>
 __device__ __forceinline__ void find_boundary_bin(const int *hist, int64_t need, int *s_wsum, int *s_sel, int *s_above, int *s_bucket)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int PER = FS_BINS / THREADS;
-    const int hb = FS_BINS - 1 - tid * PER; // thread 0 owns the highest bins
+    constexpr int PER = BINS / THREADS;
+    const int hb = BINS - 1 - tid * PER; // thread 0 owns the highest bins
     int sum = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) sum += hist[hb - j];
@@ -1381,7 +1381,10 @@ __global__ void __launch_bounds__(THREADS, (ITEMS > 8 ? 3 : 4) * (256 / THREADS)
 template <int ITEMS, int THREADS>
 __device__ void select_dense_row(const SelArgs &a, const int64_t row)
 {
-    __shared__ int hist[FS_BINS];
+    // bins per pass: 1 024 for the 2 048 - 4 096-value samples, 256 for samples of up to 1 024 values (C3: fewer bins to zero
+    // and scan per row; the boundary bin still holds a handful of elements)
+    constexpr int DB_BITS = ITEMS * THREADS <= 1024 ? 8 : FS_BITS, DB_BINS = 1 << DB_BITS;
+    __shared__ int hist[DB_BINS];
     __shared__ uint64_t ckey[FS_SORT];
     __shared__ uint32_t cidx[FS_SORT];
     __shared__ double s_red[2 * (THREADS / 32)];
@@ -1393,7 +1396,7 @@ __device__ void select_dense_row(const SelArgs &a, const int64_t row)
     int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *V = reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
-    for (int b = tid; b < FS_BINS; b += THREADS) hist[b] = 0; // (visible after the barrier of the range reduction)
+    for (int b = tid; b < DB_BINS; b += THREADS) hist[b] = 0; // (visible after the barrier of the range reduction)
     // ---- load: slot i = tid + 256 j holds the loss of trial n_begin + i (slots past n repeat the thread's first
     // loss: harmless for min / max, masked everywhere else)
     double x[ITEMS];
@@ -1421,18 +1424,18 @@ __device__ void select_dense_row(const SelArgs &a, const int64_t row)
     for (int w = 0; w < THREADS / 32; ++w) { hmn = min(hmn, s_redw[w]); hmx = max(hmx, s_redw[THREADS / 32 + w]); }
     const bool finite = hmx < 0xfff00000u && hmn > 0x000fffffu; // inside (-inf, +inf)
     const double mn = fkey_inv((uint64_t)hmn << 32), mx = fkey_inv(((uint64_t)hmx << 32) | 0xffffffffull);
-    // ---- pass 0 in VALUE space: FS_BINS equal-width bins of [min, max].  The bin index is a monotone function of
+    // ---- pass 0 in VALUE space: DB_BINS equal-width bins of [min, max].  The bin index is a monotone function of
     // the loss (the same three roundings for every element), so "higher bin" implies "not smaller": the partition is
     // exact.  Losses of a Monte Carlo run are smooth, so one pass leaves a boundary bin of a few elements; ties and
     // pathological distributions continue below with the key-space passes, non-finite values skip straight to them.
     int64_t need = t;
     int bucket = n;
     const double width = mx - mn;
-    const bool byval = finite && width > 1.0e-290 && width < 1.0e300; // scale = FS_BINS / width must stay finite (0 * inf = NaN)
-    const double scale = byval ? (double)FS_BINS / width : 0.0;
+    const bool byval = finite && width > 1.0e-290 && width < 1.0e300; // scale = DB_BINS / width must stay finite (0 * inf = NaN)
+    const double scale = byval ? (double)DB_BINS / width : 0.0;
     auto bin_of = [&](double v) -> int {
         const int b = __double2int_rd((v - mn) * scale);
-        return min(max(b, 0), FS_BINS - 1);
+        return min(max(b, 0), DB_BINS - 1);
     };
     int sel = 0;
     if (byval) {
@@ -1440,7 +1443,7 @@ __device__ void select_dense_row(const SelArgs &a, const int64_t row)
         for (int j = 0; j < ITEMS; ++j)
             if (tid + THREADS * j < n) atomicAdd(&hist[bin_of(x[j])], 1);
         __syncthreads();
-        find_boundary_bin<THREADS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+        find_boundary_bin<THREADS, DB_BINS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
         sel = s_sel;
         need -= s_above;
         bucket = s_bucket;
@@ -1473,8 +1476,8 @@ __device__ void select_dense_row(const SelArgs &a, const int64_t row)
         blo = lo; bhi = hi;
         for (int pass = 0; pass < 16; ++pass) {
             const uint64_t w64 = hi - lo;
-            const int shift = w64 < (uint64_t)FS_BINS ? 0 : (64 - __clzll((long long)w64)) - FS_BITS;
-            for (int b = tid; b < FS_BINS; b += THREADS) hist[b] = 0;
+            const int shift = w64 < (uint64_t)DB_BINS ? 0 : (64 - __clzll((long long)w64)) - DB_BITS;
+            for (int b = tid; b < DB_BINS; b += THREADS) hist[b] = 0;
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
@@ -1486,7 +1489,7 @@ __device__ void select_dense_row(const SelArgs &a, const int64_t row)
                 }
             }
             __syncthreads();
-            find_boundary_bin<THREADS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
+            find_boundary_bin<THREADS, DB_BINS>(hist, need, s_wsum, &s_sel, &s_above, &s_bucket);
             need -= s_above;
             bucket = s_bucket;
             blo = lo + ((uint64_t)s_sel << shift);
