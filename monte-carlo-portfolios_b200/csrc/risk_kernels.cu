@@ -351,8 +351,11 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 // Each lane appends to its own private segment (portfolio, sub-chunk, lane%4): no atomics.
 constexpr int VM_WARPS = 8;
 constexpr int VM_THREADS = VM_WARPS * 32;
-constexpr int VM_G = 2;                      // portfolio groups (of 8) per warp
-constexpr int VM_PG = VM_WARPS * VM_G * 8;   // portfolios per CTA = 128
+// portfolio groups (of 8) per warp: two up to F = 48 (106 registers: two CTAs per SM), FOUR at F = 64 -- there one CTA per SM is all
+// the 128 KB of stages allow anyway, and four accumulator chains per warp and half the B-fragment loads per DMMA took C3 from
+// 5.05 to 4.84 ms per 125 000 rows (234 registers).  (Four groups at F = 32 means one 8-warp CTA per SM: 2.40 instead of 2.03 ms.)
+template <int NK> constexpr int vm_groups() { return NK >= 16 ? 4 : 2; }
+static inline int vm_pg(int F) { return VM_WARPS * (F >= 64 ? 4 : 2) * 8; } // portfolios per CTA: 128, or 256 at F = 64
 // Scenario staging: TWO stages of 128 trials (64 KB per CTA at F = 32, 128 KB at F = 64).  Measured on C2 with 16-warp CTAs:
 // 4 stages x 32 trials 2.157 ms, 4 x 64 2.102, 3 x 128 2.068, 2 x 256 2.056 -- what costs is the per-stage handshake (mbarrier
 // wait / arrive, the producer thread's detour), not the prefetch depth.  Round 2: 8-warp CTAs with 2 x 128-trial stages (two
@@ -459,6 +462,8 @@ template <int NK, bool DENSE, bool MOMENTS>
 __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
 {
     constexpr int F = NK * 4;
+    constexpr int VM_G = vm_groups<NK>();
+    constexpr int VM_PG = VM_WARPS * VM_G * 8;
     constexpr int BLK = NK * 32;            // doubles per 8-trial block in fragment order
     constexpr int VM_ST = vm_stage_trials<NK>(); // trials per stage
     constexpr int STG = (VM_ST / 8) * BLK;       // doubles per stage
@@ -600,7 +605,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
             }
         }
     };
-    // FP64 half for value v (0..7) of the block held in pd0/pd1
+    // FP64 half for value v (0 .. 2 VM_G - 1) of the block held in pd0/pd1
     auto moment_of = [&](int v) {
         const int g = v >> 1;
         const double d = ((v & 1) ? pd1[g] : pd0[g]) - cs[g];
@@ -630,8 +635,8 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
                 for (int g = 0; g < VM_G; ++g) dmma884(d0[g], d1[g], ef[g][s], sf[s]);
                 if (moments) {
 #pragma unroll
-                    for (int v = 0; v < 8; ++v)
-                        if ((v * NK) / 8 == s) moment_of(v);
+                    for (int v = 0; v < 2 * VM_G; ++v)
+                        if ((v * NK) / (2 * VM_G) == s) moment_of(v);
                 }
             }
             int_epilogue();                    // previous block, integer pipe only
@@ -656,7 +661,7 @@ __global__ void __launch_bounds__(VM_THREADS, 1) k_value_mma(const StreamArgs a)
     // drain the software pipeline: the last block
     if (moments) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) moment_of(v);
+        for (int v = 0; v < 2 * VM_G; ++v) moment_of(v);
     }
     int_epilogue();
     // ---- epilogue: per-portfolio partial moments (fixed 4-lane tree: deterministic) and segment counts
@@ -2137,6 +2142,7 @@ int risk_value(mcp_ctx *ctx, int64_t p0, int64_t p1, double *d_V)
     if (p1 <= p0) return MCP_OK;
     if (ctx->valueMma && mma_supported(ctx->F)) {
         // the streaming kernel in DENSE mode writes V itself: [p - p0][N]
+        const int VM_PG = vm_pg(ctx->F);
         const int64_t nsg = (p1 - p0 + VM_PG - 1) / VM_PG;
         std::vector<Step> st = make_schedule(ctx->N, ctx->N, nsg, ctx->prop.multiProcessorCount); // one step: [0, N)
         MCP_TRY(ensure_sfrag(ctx));
@@ -2240,6 +2246,7 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
     // Portfolio tiles alternate between two streams: the selection / compaction kernels of one tile (latency-bound,
     // small CTAs) then run under the valuation kernel of the next (DMMA-bound, one 512-thread CTA per SM that leaves
     // registers and shared memory for them) instead of after it.
+    const int VM_PG = vm_pg(ctx->F);
     const int64_t groups = (P + VM_PG - 1) / VM_PG;
     const int64_t want_tiles = ctx->overlapTiles > 1 && groups >= 2 * ctx->overlapTiles ? ctx->overlapTiles : 1;
     if (want_tiles > 1) Pt = ((groups + want_tiles - 1) / want_tiles) * VM_PG;
