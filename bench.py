@@ -599,6 +599,38 @@ def c5_leg(job, steps, warmup):
     return out
 
 
+def weights_leg(ctx, args, nl=100_000, per_list=320):
+    """Row f3: the loader's weights column (LoadPortfolios.getCompressedWeights, raw Snappy over the little-endian doubles;
+    C1's portfolios hold ~320 positions each).  mcp_weights_encode / _decode take HOST buffers, so the wall time holds the copies;
+    the kernels' own time is the library's event time around its launches."""
+    rng = np.random.default_rng(0x5EED0F3)
+    lens = rng.integers(per_list // 2, per_list * 3 // 2, nl)
+    off = np.zeros(nl + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    # weights as the generator writes them: a few decimal digits, many repeats inside a portfolio (that is what Snappy finds)
+    w = np.round(rng.random(int(off[-1])) * 100.0, 1)
+    reps = max(min(args.steps, 5), 1)
+    oo, blob = ctx.weights_encode(w, off)
+    ctx.profile(True)
+    ctx.profile_reset()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oo, blob = ctx.weights_encode(w, off)
+    t_e = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        back = ctx.weights_decode(blob, oo, off)
+    t_d = (time.perf_counter() - t0) / reps
+    prof = ctx.profile_get()
+    ctx.profile(False)
+    assert np.array_equal(back, w), "weights column round trip"
+    return {"workload": f"{nl} portfolios x ~{per_list} weights (doubles with one decimal), raw-Snappy format, host buffers",
+            "doubles": int(off[-1]), "encoded_bytes": int(blob.size), "ratio": float(blob.size) / (8.0 * float(off[-1])),
+            "encode_doubles_per_s_host_call": float(off[-1]) / t_e, "decode_doubles_per_s_host_call": float(off[-1]) / t_d,
+            "encode_kernels_ms": prof["encode"]["ms"] / reps, "decode_kernels_ms": prof["decode"]["ms"] / reps,
+            "round_trip_checked": True}
+
+
 def codec_legs(job):
     """BASELINE config C4, device-resident.  Lists are independent, so N GPUs are N shards with no collective (weak scaling):
     EVERY rank encodes and decodes its own lists (first_list = rank * nl), the time is the max over ranks, ints/s is the whole
@@ -664,6 +696,23 @@ def codec_legs(job):
     # lists long enough for FastPFOR pages (the risk step's own breach lists look like this)
     codec["fastpfor_pages"] = codec_leg(N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, "Delta + Composition(FastPFOR, VariableByte), "
                                         "3 FastPFOR blocks + a VariableByte tail per list", max(nl // 10, 1), 100_000)
+    # the other wire formats of SURVEY.md section 8 rows a8 / f4 on the C4 lists (same timing rules, fewer repetitions)
+    if not args.no_extras:
+        keep = (args.steps, args.warmup)
+        args.steps, args.warmup = max(min(args.steps, 5), 1), min(args.warmup, 3)
+        others = {}
+        for key, cid, what in (("ibp32_ivb", N.CODEC_IBP32_IVB, "IntegratedComposition(IntegratedBinaryPacking, IntegratedVariableByte)"),
+                               ("sk_ibp32_ivb", N.CODEC_SK_IBP32_IVB, "IntegratedIntCompressor framing of the same"),
+                               ("fastpfor128_vb", N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, "Delta + Composition(FastPFOR128, VariableByte)"),
+                               ("xor128_ivb", N.CODEC_XOR128_IVB, "IntegratedComposition(XorBinaryPacking, IntegratedVariableByte)"),
+                               ("optpfd_vb", N.CODEC_OPTPFD_VB | N.FLAG_DELTA, "Delta + Composition(OptPFD, VariableByte)")):
+            leg = codec_leg(cid, what + " [c4 lists]", nl, 10_000)
+            others[key] = {k: leg[k] for k in ("workload", "bytes_per_int", "encode_ints_per_s", "decode_ints_per_s", "encode_ms", "decode_ms")}
+            others[key]["roofline_frac"] = [leg["roofline_encode"]["frac"], leg["roofline_decode"]["frac"]]
+        codec["other_codecs"] = others
+        args.steps, args.warmup = keep
+        if rank == 0:
+            codec["weights_column"] = weights_leg(ctx, args)
     st = ctx.codec_stats()
     codec["kernels"] = {"calls_served_by_thread_per_list_kernels": st["short_calls"], "handed_on": st["short_fallbacks"],
                         "calls_served_by_batched_kernels": st["fast_encodes"], "handed_back": st["fast_fallbacks"]}

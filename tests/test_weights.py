@@ -104,6 +104,33 @@ def test_gpu_weights_codec_equals_the_oracle_and_reads_foreign_streams(ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_weights_codec_on_many_lists(ctx):
+    """Many lists of every length up to the loader's 8 192-position cap (LoadPortfolios.java:705), bytes against the oracle:
+    decimal weights give a copy every few bytes, random mantissas none."""
+    rng = np.random.default_rng(77)
+    lens = list(rng.integers(0, 400, 600)) + [1279, 1280, 1281, 1023, 1024, 1025, 2047, 2049, 640, 8191]
+    lists = []
+    for i, n in enumerate(lens):
+        kind = i % 4
+        if kind == 0:
+            w = np.round(rng.random(n) * 100.0, 1)
+        elif kind == 1:
+            w = rng.random(n)
+        elif kind == 2:
+            w = rng.integers(0, 5, n).astype(np.float64) * 0.25
+        else:
+            w = np.where(rng.random(n) < 0.5, 1.0, np.round(rng.random(n), 2))
+        lists.append(w)
+    off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum([len(x) for x in lists], out=off[1:])
+    vals = np.concatenate(lists)
+    out_off, out = ctx.weights_encode(vals, off)
+    for i, w in enumerate(lists):
+        assert bytes(out[out_off[i]: out_off[i + 1]]) == cref.get_compressed_weights(w), (i, len(w))
+    assert np.array_equal(ctx.weights_decode(out, out_off, off), vals)
+
+
+@pytest.mark.gpu
 def test_weight_documents_of_the_shipped_portfolios(ctx):
     c1 = json.load(open(os.path.join(GOLD, "c1_sample.json")))
     lp = mcp_b200.LoadPortfolios(ctx)
