@@ -695,20 +695,24 @@ __device__ int64_t warp_fastpfor_encode(const ValSeq &x, int64_t m, uint32_t *ou
     return pos;
 }
 
-// decodePage (FastPFOR.java:233-307).  Returns words consumed or -1.
-template <int ROUNDS>
+// decodePage (FastPFOR.java:233-307).  Returns words consumed or -1.  GLD: the page lies in global memory (read-only
+// loads); otherwise wherever the pointer says (a page staged in shared memory).
+template <bool GLD>
+__device__ __forceinline__ uint32_t page_word(const uint32_t *p) { return GLD ? __ldg(p) : *p; }
+
+template <int ROUNDS, bool GLD = true>
 __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n, uint32_t *out, int *stream_base,
                                        int *stream_pos, int lane)
 {
     constexpr int B = ROUNDS * 32;
     if (avail < 3) return -1;
-    const int64_t where_meta = __ldg(inw);
+    const int64_t where_meta = page_word<GLD>(inw);
     if (where_meta < 1 || where_meta >= avail) return -1;
-    const int64_t bytesize = __ldg(inw + where_meta);
+    const int64_t bytesize = page_word<GLD>(inw + where_meta);
     const int64_t meta_words = (bytesize + 3) >> 2;
     int64_t e = where_meta + 1 + meta_words;
     if (bytesize < 0 || e >= avail) return -1;
-    const uint32_t bitmap = __ldg(inw + e);
+    const uint32_t bitmap = page_word<GLD>(inw + e);
     ++e;
     // stream table (serial over set bits: at most 31)
     if (lane == 0) {
@@ -718,7 +722,7 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
             stream_pos[k] = 0;
             if (bitmap & (1u << (k - 1))) {
                 if (q >= avail) { ok = false; break; }
-                const int64_t size = __ldg(inw + q);
+                const int64_t size = page_word<GLD>(inw + q);
                 stream_base[k] = (int)(q + 1);
                 q += 1 + ((size * k + 31) >> 5);
             } else
@@ -741,7 +745,7 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
         uint32_t *o = out + (int64_t)j * B;
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
-            const uint32_t word = (lane < b) ? __ldg(inw + p + lane) : 0u;
+            const uint32_t word = (lane < b) ? page_word<GLD>(inw + p + lane) : 0u;
             o[32 * r + lane] = warp_unpack_val(word, b, lane);
             p += b;
         }
@@ -764,8 +768,8 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
                     const int sh = (int)(bit & 31);
                     // a malformed stream may claim more exceptions than its streams hold: never read past the page
                     if (stream_base[k] + w + (sh + k > 32 ? 1 : 0) >= page_end) { past_end = true; continue; }
-                    const uint32_t lo = __ldg(sw + w);
-                    const uint32_t hw = (sh + k > 32) ? __ldg(sw + w + 1) : 0u;
+                    const uint32_t lo = page_word<GLD>(sw + w);
+                    const uint32_t hw = (sh + k > 32) ? page_word<GLD>(sw + w + 1) : 0u;
                     hi = __funnelshift_r(lo, hw, sh);
                     if (k < 32) hi &= (1u << k) - 1u;
                 }
@@ -2148,6 +2152,60 @@ __device__ __forceinline__ bool warp_short_list_decode(const CodecTraits tr, con
     return true;
 }
 
+// Any list of a flat-kernel call by one warp, FastPFOR pages included (a list of at least one block among lists that are
+// otherwise all VariableByte: FastPFOR128 on ~100-value lists meets one every few hundred lists).  Same steps as k_encode.
+// fq: 68 ints of scratch.  *unsupported is raised for a multi-page list (the stale-buffer emulation lives in k_encode).
+template <bool WRITE>
+__device__ __forceinline__ int64_t warp_any_list_encode(const CodecTraits tr, const ValSeq x, int64_t n, const WordSink sink, bool app,
+                                                        uint32_t *stage, int *fq, int lane, bool *unsupported)
+{
+    if (!(tr.fastpfor && n >= tr.fp_block)) return warp_short_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
+    const int64_t m = n - n % tr.fp_block;
+    if (m > kFpPage) { *unsupported = true; return 0; }
+    if (WRITE && lane == 0) sink.put(0, (uint32_t)(tr.sk ? n : m)); // IntCompressor's n, or FastPFOR.compress's count word
+    int64_t pos = 1;
+    const int64_t w = tr.fp_block == 256 ? warp_fastpfor_encode<WRITE, 8>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane)
+                                         : warp_fastpfor_encode<WRITE, 4>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane);
+    if (WRITE && app) { // pages are written as native words (byte-granular metadata): swapped afterwards
+        __syncwarp();
+        for (int64_t j = pos + lane; j < pos + w; j += 32) sink.w[j] = bswap32(sink.w[j]);
+    }
+    pos += w;
+    if (n > m) {
+        auto getv = [&](int64_t i) -> uint32_t { return x(m + i); };
+        pos += warp_vb_encode<WRITE>(getv, n - m, sink, pos, stage, lane);
+    }
+    if (app) { if (WRITE && lane == 0) sink.put(pos, 0u); ++pos; }
+    return pos;
+}
+
+// scr: cap words of shared memory (a big-endian-framed page is un-swapped into it); fq: 68 ints
+__device__ __forceinline__ bool warp_any_list_decode(const CodecTraits tr, const WordSrc src, int64_t avail, int64_t n, uint32_t *out,
+                                                     bool delta, uint32_t *scr, int cap, int *fq, int lane, bool *unsupported)
+{
+    if (!(tr.fastpfor && n >= tr.fp_block)) return warp_short_list_decode(tr, src, avail, n, out, delta, lane);
+    const int64_t m = n - n % tr.fp_block;
+    if (m > kFpPage) { *unsupported = true; return true; }
+    if (avail < 1 || (int64_t)src.get(0) != (tr.sk ? n : m)) return false;
+    int64_t p = 1, used;
+    if (src.swap) {
+        const int64_t take = avail - p;
+        if (take > cap) { *unsupported = true; return true; }
+        for (int64_t j = lane; j < take; j += 32) scr[j] = src.get(p + j);
+        __syncwarp();
+        used = tr.fp_block == 256 ? warp_fp_decode_page<8, false>(scr, take, (int)m, out, fq, fq + 34, lane)
+                                  : warp_fp_decode_page<4, false>(scr, take, (int)m, out, fq, fq + 34, lane);
+    } else
+        used = tr.fp_block == 256 ? warp_fp_decode_page<8, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane)
+                                  : warp_fp_decode_page<4, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane);
+    __syncwarp();
+    if (used < 0) return false;
+    p += used;
+    if (n > m && !warp_vb_decode<false>(src, p, avail, n - m, out + m, 0u, lane)) return false;
+    if (delta) { __syncwarp(); warp_inverse_delta(out, n, lane); }
+    return true;
+}
+
 // what a lane knows about its list of the batch the warp is working on (or about to)
 struct SlList {
     int64_t beg, n64; // first value (index into vals), length
@@ -2613,6 +2671,8 @@ struct TileEncArgs {
     int64_t *tile_words;  // [nbatches] size pass: words of the tile; after the scan: first word of the tile in the output
     int hdr_mode;         // word in front of a list's bytes: 0 none, 1 IntCompressor's n, 2 Composition's 0 marker (non-empty lists)
     int page;             // FastPFOR block size: a list this long is not all VariableByte (0: no limit)
+    int *defer_cnt;       // tiles that hold such a list are left to k_vb4_pages (null: flag 2, the host takes other kernels)
+    int *defer_tiles;
 };
 
 template <int THREADS, int VPT, bool DELTA, bool EMIT>
@@ -2916,6 +2976,7 @@ __global__ void __launch_bounds__(THREADS) k_vb4_tile(const TileEncArgs ta)
     uint32_t *stage = s_out + 64 * warp;
     int64_t *s_w64 = reinterpret_cast<int64_t *>(s_vals); // (the staging tile is scratch here: the lists' sizes in words)
     if (has_page) {
+        if (ta.defer_cnt) return; // k_vb4_pages writes this tile
         if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
     } else {
         for (int j = warp; j < nl; j += C::WARPS) {
@@ -3096,6 +3157,10 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_size(const TileEncArgs ta)
     __shared__ uint32_t s_stage[C::WARPS][64];
     long long mine = 0;
     if (has_page) {
+        if (ta.defer_cnt) { // k_vb4_pages sizes this tile (before the scan)
+            if (tid == 0) ta.defer_tiles[atomicAdd(ta.defer_cnt, 1)] = (int)tile;
+            return;
+        }
         if (tid == 0) atomicMax(a.err, 2); // a FastPFOR page: the host takes the batched kernels
     } else {
         for (int j = warp; j < nl; j += C::WARPS) {
@@ -3111,6 +3176,76 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_size(const TileEncArgs ta)
 #pragma unroll
         for (int w = 0; w < C::WARPS; ++w) T += s_red[w];
         ta.tile_words[tile] = T;
+    }
+}
+
+// The tiles the two kernels above left aside (a list of at least one FastPFOR block among lists that are otherwise all
+// VariableByte -- FastPFOR128 on ~100-value lists meets one every few hundred lists): sized (EMIT = false, before the scan)
+// and written (EMIT = true, after it) by the warp-per-list routines, a CTA per tile of the worklist.  Kept out of the
+// kernels above on purpose: inlined there, the FastPFOR page encoder costs them 8-24 registers and 4 KB of shared memory.
+template <bool EMIT>
+__global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
+{
+    constexpr int WARPS = VB4_THREADS / 32;
+    const FastEncArgs &a = ta.f;
+    __shared__ uint32_t s_stage[WARPS][64];
+    __shared__ int s_fq[WARPS][68];
+    __shared__ long long s_w64[VB4_THREADS];
+    __shared__ long long s_red[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    auto list_off = [&](int64_t l) -> int64_t { return a.list_off ? a.list_off[l] : l * a.uniform_len; };
+    const int ndefer = *ta.defer_cnt;
+    if (EMIT && *a.total > a.cap) return;
+    for (int d = blockIdx.x; d < ndefer; d += gridDim.x) {
+        const long long tile = ta.defer_tiles[d];
+        const int64_t l0 = tile * a.lists_per_batch;
+        const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+        bool multi = false;
+        for (int j = warp; j < nl; j += WARPS) {
+            const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
+            const int64_t w = warp_any_list_encode<false>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp],
+                                                          s_fq[warp], lane, &multi);
+            if (lane == 0) s_w64[j] = w;
+            __syncwarp();
+        }
+        if (__syncthreads_or(multi)) { // a multi-page list: the host takes the warp-per-list kernels (stale-buffer emulation)
+            if (tid == 0) { atomicMax(a.err, 2); if (!EMIT) ta.tile_words[tile] = 0; }
+            continue;
+        }
+        const long long wj = tid < nl ? s_w64[tid] : 0;
+        long long incl = wj;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const long long t = __shfl_up_sync(kFull, incl, dd);
+            if (lane >= dd) incl += t;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        __syncthreads();
+        long long wo = 0, T = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const long long x = s_red[w];
+            if (w < warp) wo += x;
+            T += x;
+        }
+        if (!EMIT) {
+            if (tid == 0) ta.tile_words[tile] = T;
+        } else {
+            const long long gbase = ta.tile_words[tile], wbase = wo + incl - wj;
+            if (tid < nl) a.out_off[l0 + tid] = 4 * (gbase + wbase);
+            __syncthreads();
+            if (tid < nl) s_w64[tid] = wbase;
+            __syncthreads();
+            uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
+            for (int j = warp; j < nl; j += WARPS) {
+                const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
+                warp_any_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_w64[j], a.app}, a.app, s_stage[warp],
+                                           s_fq[warp], lane, &multi);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -3199,7 +3334,7 @@ constexpr int D4_MAXL = D4_THREADS - 1;
 __device__ __forceinline__ int d4_slot(int i) { return i ^ ((i >> 3) & 0x1c); }
 
 template <bool DELTA>
-__global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, int hdr_mode, int page)
+__global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, int hdr_mode, int page, int *defer_cnt, int *defer_tiles)
 {
     __shared__ __align__(16) uint32_t s_words[D4_WCAP];
     __shared__ __align__(1024) uint32_t s_val[D4_VSPAN]; // (1 KB aligned: the swizzle can be applied to the shared address itself)
@@ -3243,7 +3378,13 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
     int tile_st = 0; // (__syncthreads_or returns a truth value, not the OR of the arguments)
     if (__syncthreads_or(st)) tile_st = (__syncthreads_or(st & 1) ? 1 : 0) | (__syncthreads_or(st & 2) ? 2 : 0) | (__syncthreads_or(st & 4) ? 4 : 0);
     if (tile_st & 1) { if (tid == 0) atomicMax(a.err, 3); return; }
-    if (tile_st & 2) { if (tid == 0) atomicMax(a.err, 2); return; }
+    if (tile_st & 2) {
+        if (tid == 0) {
+            if (defer_cnt) defer_tiles[atomicAdd(defer_cnt, 1)] = (int)blockIdx.x; // k_vb4_decode_pages takes this tile
+            else atomicMax(a.err, 2);
+        }
+        return;
+    }
     if (tile_st & 4) {
         const CodecTraits tr = codec_traits(a.codec);
         for (int j = warp; j < nl; j += D4_WARPS) {
@@ -3438,6 +3579,31 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode(const FastDecArgs a, 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 
+// The tiles k_vb4_decode left aside (a list with a FastPFOR page): warp-per-list routines, a CTA per tile of the worklist.
+constexpr int D4P_SCR = 1280; // words a warp may un-swap a big-endian-framed page into (a list beyond it: flag 2)
+__global__ void __launch_bounds__(D4_THREADS) k_vb4_decode_pages(const FastDecArgs a, const int *defer_cnt, const int *defer_tiles)
+{
+    __shared__ uint32_t s_scr[D4_WARPS][D4P_SCR];
+    __shared__ int s_fq[D4_WARPS][68];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const CodecTraits tr = codec_traits(a.codec);
+    const int ndefer = *defer_cnt;
+    for (int d = blockIdx.x; d < ndefer; d += gridDim.x) {
+        const int64_t l0 = (int64_t)defer_tiles[d] * a.lists_per_batch;
+        const int nl = (int)min((int64_t)a.lists_per_batch, a.nlists - l0);
+        const int64_t *gin = a.in_off + l0, *goo = a.out_off + l0;
+        for (int j = warp; j < nl; j += D4_WARPS) {
+            const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + gin[j]), a.app};
+            bool multi = false;
+            const bool ok = warp_any_list_decode(tr, src, (gin[j + 1] - gin[j]) >> 2, goo[j + 1] - goo[j], a.out + goo[j], a.delta, s_scr[warp],
+                                                 D4P_SCR, s_fq[warp], lane, &multi);
+            if (lane == 0 && multi) atomicMax(a.err, 2); // the host takes the batched / warp-per-list kernels
+            else if (!ok && lane == 0) atomicMax(a.err, 4);
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void k_scan_partials(const int64_t *in, int64_t n, int64_t *partials)
 {
     __shared__ int64_t s[kScanThreads / 32];
@@ -3596,6 +3762,20 @@ int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists)
     return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64);
 }
 
+// flat kernels on a FastPFOR codec: is a list of a full block something to plan for (average length within a third of
+// the block) or an outlier (then the flat call fails over to the batched kernels as a whole)?
+static bool flat_pages_likely(const CodecTraits &tr, int64_t total_vals, int64_t nlists)
+{
+    return tr.fastpfor && nlists > 0 && 1.5 * (double)total_vals >= (double)tr.fp_block * (double)nlists;
+}
+
+// ... or the rule (average length at the block size or beyond: the thread-per-list / flat kernels are not tried at all)
+static bool flat_pages_common(int codec, int64_t total_vals, int64_t nlists)
+{
+    const CodecTraits tr = codec_traits(codec);
+    return tr.fastpfor && batched_applicable(codec, false, total_vals, nlists) && (double)total_vals >= 0.95 * (double)tr.fp_block * (double)nlists;
+}
+
 // Single-pass encode of nlists lists; writes d_out_off[0..nlists] (bytes) and the stream.  *total_out = bytes needed;
 // MCP_E_CAP when that exceeds cap (nothing useful is written then); MCP_E_UNSUPPORTED when a batch did not fit the
 // FastPFOR kernel's staging areas (the caller then takes the warp-per-list kernels).
@@ -3620,7 +3800,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.out = d_out;
     a.cap = d_out ? cap : 0;
     const bool batched = batched_applicable(a.codec, a.delta, total_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists, true);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists, true) && !flat_pages_common(a.codec, total_vals, nlists);
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
     // pass 0: thread-per-list kernel (short lists); pass 1: thread-per-block kernels
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
@@ -3631,8 +3811,8 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
                                       : fast_lists_per_batch(a.codec, total_vals, nlists);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
-        // scratch: [ticket u64][total i64][err i32 + pad][state u64 x nbatches]
-        const size_t sbytes = 32 + (size_t)a.nbatches * sizeof(uint64_t);
+        // scratch: [ticket u64][total i64][err i32][pad][deferred tiles i32][pad][state u64 x nbatches][deferred tile ids i32 x nbatches]
+        const size_t sbytes = 32 + (size_t)a.nbatches * (sizeof(uint64_t) + sizeof(int));
         MCP_CUDA(ctx, ctx->dScanTmp.reserve(sbytes));
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dScanTmp.p, 0, sbytes, ctx->stream));
         unsigned char *sp = ctx->dScanTmp.as<unsigned char>();
@@ -3645,12 +3825,22 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
                 // size pass, scan of the tiles' word counts (in place, in the state words), emit pass
-                TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (tr.fastpfor ? 2 : 0), tr.fastpfor ? tr.fp_block : 0};
+                // lists that reach a FastPFOR block are possible but rare at this average length (FastPFOR128 on ~100-value
+                // lists): their tiles go to k_vb4_pages, two more launches; when they cannot occur short of an outlier
+                // (FastPFOR on the same lists) the launches are saved and an outlier costs the rerun below
+                const bool pages = flat_pages_likely(tr, total_vals, nlists);
+                int *defer_cnt = pages ? reinterpret_cast<int *>(sp + 24) : nullptr;
+                int *defer_tiles = pages ? reinterpret_cast<int *>(sp + 32 + (size_t)a.nbatches * sizeof(uint64_t)) : nullptr;
+                TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (tr.fastpfor ? 2 : 0), tr.fastpfor ? tr.fp_block : 0,
+                               defer_cnt, defer_tiles};
+                const unsigned pgrid = (unsigned)std::min<int64_t>(a.nbatches, (int64_t)ctx->prop.multiProcessorCount * 8);
                 if (a.delta) k_vb4_size<true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 else k_vb4_size<false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                if (pages) k_vb4_pages<false><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
                 k_vb4_scan<<<1, 1024, 0, ctx->stream>>>(ta.tile_words, a.nbatches, a.total, a.out_off + a.nlists, a.cap, a.err);
                 if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 else k_vb4_tile<VB4_THREADS, VB4_VPT, false, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
+                if (pages) k_vb4_pages<true><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
             } else if (pass == 0) {
                 const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
                 k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);
@@ -3690,7 +3880,7 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     a.out = reinterpret_cast<uint32_t *>(d_out);
     a.out_off = d_out_off;
     const bool batched = batched_applicable(a.codec, a.delta, total_out_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists, false);
+    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists, false) && !flat_pages_common(a.codec, total_out_vals, nlists);
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
     MCP_CUDA(ctx, ctx->dErr.reserve(64));
     a.err = ctx->dErr.as<int>();
@@ -3706,8 +3896,18 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
                 const int hdr_mode = tr.sk ? 1 : (tr.fastpfor ? 2 : 0), page = tr.fastpfor ? tr.fp_block : 0;
-                if (a.delta) k_vb4_decode<true><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page);
-                else k_vb4_decode<false><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page);
+                int *defer_cnt = nullptr, *defer_tiles = nullptr;
+                if (flat_pages_likely(tr, total_out_vals, nlists)) { // (see codec_fast_encode)
+                    MCP_CUDA(ctx, ctx->dScanTmp.reserve(16 + (size_t)nbatches * sizeof(int)));
+                    MCP_CUDA(ctx, cudaMemsetAsync(ctx->dScanTmp.p, 0, 16, ctx->stream));
+                    defer_cnt = ctx->dScanTmp.as<int>();
+                    defer_tiles = defer_cnt + 4;
+                }
+                if (a.delta) k_vb4_decode<true><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page, defer_cnt, defer_tiles);
+                else k_vb4_decode<false><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page, defer_cnt, defer_tiles);
+                if (defer_cnt)
+                    k_vb4_decode_pages<<<(unsigned)std::min<int64_t>(nbatches, (int64_t)ctx->prop.multiProcessorCount * 8), D4_THREADS, 0,
+                                         ctx->stream>>>(a, defer_cnt, defer_tiles);
             } else if (pass == 0) {
                 const int64_t res = (int64_t)ctx->prop.multiProcessorCount * SL_DCTAS;
                 k_sl_decode<<<(unsigned)(nbatches < res ? nbatches : res), 32, 0, ctx->stream>>>(a, nbatches);

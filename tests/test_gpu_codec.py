@@ -396,17 +396,19 @@ def test_short_list_kernels_bit_exact(shortlist_everywhere, codec, delta, framin
         off = np.zeros(len(lists) + 1, np.int64)
         np.cumsum([len(v) for v in lists], out=off[1:])
         assert vals.size <= 144 * len(lists)
+        # (lists that average a FastPFOR block or more are not offered to these kernels at all: flat_pages_common)
+        tried = 0 if codec in (N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB) and vals.size >= 0.95 * 128 * len(lists) else 1
         before = ctx.codec_stats()
         out_off, out = ctx.codec_encode(cid, framing, vals, off, cap=int(8 * vals.size + 64 * len(lists)))
         mid = ctx.codec_stats()
-        assert mid["short_calls"] + mid["short_fallbacks"] == before["short_calls"] + before["short_fallbacks"] + 1
+        assert mid["short_calls"] + mid["short_fallbacks"] == before["short_calls"] + before["short_fallbacks"] + tried
         assert out_off[0] == 0 and out_off[-1] == out.size
         for i, v in enumerate(lists):
             ref = cref.get_compressed_instruments(cid, v) if framing == N.FRAME_APP else cref.compress(cid, v).tobytes()
             assert bytes(out[out_off[i]: out_off[i + 1]]) == ref, (i, len(v))
         assert np.array_equal(ctx.codec_decode(cid, framing, out, out_off, off), vals)
         after = ctx.codec_stats()
-        assert after["short_calls"] + after["short_fallbacks"] == mid["short_calls"] + mid["short_fallbacks"] + 1
+        assert after["short_calls"] + after["short_fallbacks"] == mid["short_calls"] + mid["short_fallbacks"] + tried
 
 
 @pytest.mark.parametrize("cid", [N.CODEC_BP32_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA,
@@ -424,8 +426,9 @@ def test_short_list_kernels_serve_c4(shortlist_everywhere, cid):
     out_off, out = ctx.codec_encode(cid, N.FRAME_APP, vals, off, cap=int(8 * vals.size + 64 * nl))
     back = ctx.codec_decode(cid, N.FRAME_APP, out, out_off, off)
     after = ctx.codec_stats()
-    if (cid & 0xff) == N.CODEC_FASTPFOR128_VB and np.max(np.diff(off)) >= 128:
-        # a list of a whole FastPFOR128 block is not theirs: the call moves on to the batched kernels
+    if (cid & 0xff) == N.CODEC_FASTPFOR128_VB and np.max(np.diff(off)) >= 128 and not FLAT_DEFAULT:
+        # a list of a whole FastPFOR128 block is not the thread-per-list kernels': the call moves on to the batched kernels
+        # (the flat kernels, the default, leave the tiles that hold such a list to k_vb4_pages and serve the call)
         assert after["short_calls"] == before["short_calls"] and after["short_fallbacks"] == before["short_fallbacks"] + 2
     else:
         assert after["short_calls"] == before["short_calls"] + 2 and after["short_fallbacks"] == before["short_fallbacks"]
@@ -648,6 +651,8 @@ def _awkward(kind, rng):
         lens = rng.integers(0, 120, 1500)
     elif kind == "long":      # lists longer than a tile next to short ones (VariableByte alone: no block limit)
         lens = np.concatenate([rng.integers(0, 60, 300), [5000, 0, 4096, 4095, 1, 9000], rng.integers(0, 60, 100)])
+    elif kind == "near128":   # FastPFOR128: a third of the lists reach one block (a page + a VariableByte tail), the rest are all tail
+        lens = np.concatenate([rng.integers(60, 160, 900), [128, 127, 129, 255, 256, 257, 0, 1]])
     elif kind == "exact":     # lists of exactly 32 / 64 / 128 values: list starts fall on thread boundaries
         lens = rng.choice([32, 64, 128, 0, 96], 700)
     off = np.zeros(lens.size + 1, np.int64)
@@ -659,7 +664,7 @@ def _awkward(kind, rng):
     return vals, off
 
 
-@pytest.mark.parametrize("kind", ["breach", "tiny", "mixed", "wide", "long", "exact"])
+@pytest.mark.parametrize("kind", ["breach", "tiny", "mixed", "wide", "long", "exact", "near128"])
 @pytest.mark.parametrize("shift", [0, 1, 3], ids=["aligned", "shift1", "shift3"])
 def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
     """The flat VariableByte kernels (size pass + tile scan + emit pass; tile-per-CTA decoder) against the oracle, list by
@@ -671,11 +676,14 @@ def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
     codecs = [N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB]
     if kind not in ("long",):
         codecs += [N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_SK_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB]
+    if kind in ("breach", "near128"):  # tiles with a FastPFOR128 page among all-VariableByte lists: the k_vb4_pages kernels
+        codecs += [N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB]
     guard = np.full(256, 0x5AC3A55A, np.uint32)
     ctx.set_option("short_list_codec", 2)
     ctx.set_option("flat_codec", 1)
     try:
         for cid in codecs:
+            before = ctx.codec_stats()
             for fr in (N.FRAME_APP, N.FRAME_WORDS):
                 want = [cref.get_compressed_instruments(cid, vals[off[i]:off[i + 1]]) if fr == N.FRAME_APP
                         else cref.compress(cid, vals[off[i]:off[i + 1]]).tobytes() for i in range(nl)]
@@ -712,6 +720,9 @@ def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
                 finally:
                     for q in bufs.values():
                         ctx.dev_free(q)
+            if kind in ("breach", "near128") and (cid & 0xff) in (N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB):
+                after = ctx.codec_stats()  # ... and nothing was handed on to the batched / warp-per-list kernels
+                assert after["short_fallbacks"] == before["short_fallbacks"], (hex(cid), before, after)
     finally:
         ctx.set_option("short_list_codec", 1)
         ctx.set_option("flat_codec", FLAT_DEFAULT)
