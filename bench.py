@@ -466,6 +466,9 @@ def e2e_leg(job, name, P_local, row0):
     import mcp_b200
     depth = 2
     ctx2 = mcp_b200.Context(job.local_rank)
+    if getattr(args, "simulate_turns", -1) >= 0:  # experiments: the library decides by upload size otherwise
+        ctx.set_option("simulate_turns", args.simulate_turns)
+        ctx2.set_option("simulate_turns", args.simulate_turns)
     outs2 = {k: pinned_array(L, v.shape, v.dtype) for k, v in outs.items()}
     n_enc2 = ctypes.c_int64(0)
     lanes = [(ctx, outs, n_enc), (ctx2, outs2, n_enc2)]
@@ -754,6 +757,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true")
+    ap.add_argument("--simulate-turns", type=int, default=-1, help="experiments: force mcp_set_option('simulate_turns') in the e2e leg")
     ap.add_argument("--no-extras", action="store_true", help="only the headline leg (profiling runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check after the timed region")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin the rank to its GPU's NUMA node")

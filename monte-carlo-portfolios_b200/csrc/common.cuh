@@ -127,6 +127,7 @@ struct mcp_ctx {
     int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     int selSlack = 0;              // extra entries of the sparse steps' staging area (experiment knob)
+    int simulateTurns = -1;        // mcp_simulate calls in flight on one GPU take turns on the SMs: 0 no, 1 yes, -1 by upload size
     bool warpSelect = true;        // small rows (dense samples of <= 1 024 values, <= 512 staged candidates): one warp per row
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)

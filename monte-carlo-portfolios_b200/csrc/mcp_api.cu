@@ -7,6 +7,8 @@
 
 #include "common.cuh"
 
+#include <mutex>
+
 using namespace mcp;
 
 namespace {
@@ -170,6 +172,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "warp_select")) ctx->warpSelect = value != 0;
     else if (!strcmp(key, "sel_slack")) ctx->selSlack = (int)value;
+    else if (!strcmp(key, "simulate_turns")) ctx->simulateTurns = (int)(value < 0 ? -1 : value > 0 ? 1 : 0);
     else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);
@@ -708,6 +711,19 @@ int mcp_fetch(mcp_ctx *ctx, double *mean, double *variance, double *var_loss, in
 
 static bool mma_factor_count(int32_t F) { return F == 16 || F == 32 || F == 48 || F == 64; }
 
+// Calls in flight on one GPU (one context and one host thread each, so that a step's copies ride under another step's
+// kernels) drift into step when their kernels are allowed to interleave: both then compute at half speed, finish together
+// and copy together with the SMs idle.  With turns, a call enqueues its uploads, then waits for the device's token, holds
+// it from its first kernel to the host sync that ends its last one, and downloads after handing it on.
+static std::mutex g_simulate_turn[64];
+static constexpr double kSimulateTurnBytes = 48e6; // uploads per call from which turns pay (measured: profiles/r2/optimization_log.md)
+
+static bool simulate_takes_turns(const mcp_ctx *ctx, int64_t P, int64_t N, int32_t F)
+{
+    if (ctx->simulateTurns >= 0) return ctx->simulateTurns != 0;
+    return (double)(P + N) * F * sizeof(double) >= kSimulateTurnBytes;
+}
+
 int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int64_t N, int32_t F, double alpha,
                  int codec_id, int framing, double *mean, double *variance, double *var_loss, int32_t *var_trial,
                  double *cvar, int32_t *breach_idx, int64_t *enc_off, uint8_t *enc, int64_t enc_cap, int64_t *enc_len)
@@ -724,7 +740,11 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
         // plain sequence: upload, run, fetch
         MCP_TRY(mcp_upload_exposures(ctx, E, P, F));
         MCP_TRY(mcp_upload_scenarios(ctx, S, N, F));
-        MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+        {
+            std::unique_lock<std::mutex> turn;
+            if (simulate_takes_turns(ctx, P, N, F)) turn = std::unique_lock<std::mutex>(g_simulate_turn[ctx->device & 63]);
+            MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+        }
         if (enc_len) *enc_len = ctx->runEncBytes;
         return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
     }
@@ -753,7 +773,12 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     ctx->sTailPending = true; ctx->sHeadRows = head; ctx->sMidRows = mid;
     ctx->earlyBreachDst = breach_idx;
     ctx->earlyMean = mean; ctx->earlyVar = variance; ctx->earlyVarLoss = var_loss; ctx->earlyVarTrial = var_trial; ctx->earlyCvar = cvar;
-    const int rc = mcp_run(ctx, alpha, codec_id, framing);
+    int rc;
+    {
+        std::unique_lock<std::mutex> turn;
+        if (simulate_takes_turns(ctx, P, N, F)) turn = std::unique_lock<std::mutex>(g_simulate_turn[ctx->device & 63]);
+        rc = mcp_run(ctx, alpha, codec_id, framing);
+    }
     ctx->earlyBreachDst = nullptr;
     ctx->earlyMean = ctx->earlyVar = ctx->earlyVarLoss = ctx->earlyCvar = nullptr;
     ctx->earlyVarTrial = nullptr;

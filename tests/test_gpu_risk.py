@@ -338,11 +338,15 @@ def test_simulate_one_call(ctx):
         assert bytes(r["enc"][r["enc_off"][p]: r["enc_off"][p + 1]]) == cref.get_compressed_instruments(cid, o["breach"][p])
 
 
-def test_simulate_pipeline_two_calls_in_flight():
+@pytest.mark.parametrize("turns", [-1, 0, 1], ids=["by-size", "free", "turns"])
+def test_simulate_pipeline_two_calls_in_flight(turns):
     """SimulatePipeline: two contexts on one GPU, one host thread each -- steps submitted back to back come back as the
-    steps run one at a time would have (and as the oracle says), whatever the interleaving of their copies and kernels."""
+    steps run one at a time would have (and as the oracle says), whatever the interleaving of their copies and kernels:
+    left free, or with the calls taking turns on the SMs (option simulate_turns; by upload size unless set)."""
     steps = [riskcases.synthetic(20 + i, 40000, 32, 100 + i) for i in range(5)]
     with mcp_b200.SimulatePipeline(device=0, depth=2) as pipe:
+        for c in pipe.contexts():
+            c.set_option("simulate_turns", turns)
         futures = [pipe.submit(E, S, 0.99) for E, S in steps]
         results = [f.result() for f in futures]
     cid = N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA
