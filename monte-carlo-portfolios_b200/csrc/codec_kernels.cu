@@ -332,32 +332,18 @@ __device__ __constant__ unsigned char kS16Bits[16][28] = {
     {4, 3, 3, 3, 3, 3, 3, 3, 3}, {3, 4, 4, 4, 4, 3, 3, 3}, {4, 4, 4, 4, 4, 4, 4}, {5, 5, 5, 5, 4, 4}, {4, 4, 5, 5, 5, 5},
     {6, 6, 6, 5, 5}, {5, 5, 6, 6, 6}, {7, 7, 7, 7}, {10, 9, 9}, {14, 14}, {28}};
 
-// The exception sequence of a block at width `w` without materialising it: entry e < c is the e-th exception's high part
-// (block order), entry c + e its position.  `blk` = the block's 128 values (shared memory), `mask` = exception bits.
-struct OptSeq {
-    const uint32_t *blk;
-    uint32_t mask[4];
-    int c, w;
-    __device__ __forceinline__ int position(int e) const
-    {
-        int wi = 0;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int cnt = __popc(mask[wi]);
-            if (e >= cnt && wi == q) { e -= cnt; ++wi; }
-        }
-        return 32 * wi + (int)__fns(mask[wi], 0, e + 1);
-    }
-    __device__ __forceinline__ int32_t operator()(int e) const // as a Java int (S16 compares signed)
-    {
-        if (e >= c) return position(e - c);
-        return (int32_t)(blk[position(e)] >> (w & 31));
-    }
+// The exception sequence of a block at width `w`: entry e < c is the e-th exception's high part (block order), entry c + e
+// its position -- as a Java int (S16 compares signed).  Written out in shared memory by opt_materialise.
+struct MemSeq {
+    const int32_t *s;
+    int c;
+    __device__ __forceinline__ int32_t operator()(int e) const { return s[e]; }
 };
 
 // S16.compressblock (S16.java:80-100): the first of the 16 layouts that holds the next min(num, n) entries; returns
 // how many it took (0 = "Too big a number": cannot happen, high parts are < 2^28) and the word
-__device__ __forceinline__ int s16_block(const OptSeq &q, int first, int n, uint32_t *word)
+template <typename SEQ>
+__device__ __forceinline__ int s16_block(const SEQ &q, int first, int n, uint32_t *word)
 {
     for (int idx = 0; idx < 16; ++idx) {
         uint32_t wv = (uint32_t)idx << 28;
@@ -378,7 +364,8 @@ __device__ __forceinline__ int s16_block(const OptSeq &q, int first, int n, uint
 }
 
 // words S16.compress spends on the block's exception sequence (S16.estimatecompress, S16.java:57-72)
-__device__ __forceinline__ int s16_words(const OptSeq &q)
+template <typename SEQ>
+__device__ __forceinline__ int s16_words(const SEQ &q)
 {
     int pos = 0, words = 0;
     const int n = 2 * q.c;
@@ -399,53 +386,69 @@ __device__ __forceinline__ void opt_mask(const uint32_t (&v)[4], int w, uint32_t
     for (int j = 0; j < 4; ++j) mask[j] = __ballot_sync(kFull, w < 32 && (v[j] >> (w & 31)) != 0u);
 }
 
+// the block's exception sequence at width w, written out by the warp: seq[e] = e-th exception's high part (block order),
+// seq[c + e] = its position; returns c
+__device__ __forceinline__ int opt_materialise(const uint32_t (&v)[4], int w, int32_t *seq, int lane)
+{
+    uint32_t mk[4];
+    opt_mask(v, w, mk);
+    const int c = __popc(mk[0]) + __popc(mk[1]) + __popc(mk[2]) + __popc(mk[3]);
+    if (c == 0 || c >= 128) return c; // (128 exceptions: the candidate is not priced, OptPFD.java:77)
+    int before = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if ((mk[j] >> lane) & 1u) {
+            const int e = before + __popc(mk[j] & ((1u << lane) - 1u));
+            seq[e] = (int32_t)(v[j] >> (w & 31));
+            seq[c + e] = 32 * j + lane;
+        }
+        before += __popc(mk[j]);
+    }
+    return c;
+}
+
 template <bool WRITE>
-__device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, uint32_t *blk /* 128 words */, int lane)
+__device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, int32_t *seq /* 2 x 256 words */, int lane)
 {
     const int64_t pos0 = pos;
     for (int64_t s = 0; s < m; s += 128) {
         uint32_t v[4];
         uint32_t orv = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = x(s + 32 * j + lane); blk[32 * j + lane] = v[j]; orv |= v[j]; }
-        __syncwarp();
-        // ---- getBestBFromData (OptPFD.java:61-98): lane i - mini prices candidate i; `mini` is computed from bit WIDTHS but
-        // used as the first INDEX, as the reference does; ties go to the later candidate (<=)
+        for (int j = 0; j < 4; ++j) { v[j] = x(s + 32 * j + lane); orv |= v[j]; }
+        // ---- getBestBFromData (OptPFD.java:61-98): candidates mini .. 15; `mini` is computed from bit WIDTHS but used as the
+        // first INDEX, as the reference does; ties go to the later candidate (<=).  Two candidates per round: the warp writes
+        // their exception sequences out (Simple16's greedy layout search reads every entry many times), lanes 0 and 1 price them.
         const int mb = bits32(__reduce_or_sync(kFull, orv));
         int mini = 0;
         if (mini + 28 < kOptBits[kOptInvBits[mb]]) mini = kOptBits[kOptInvBits[mb]] - 28;
-        const int cand = mini + lane;
         unsigned key = 0xffffffffu; // (cost << 5) | (31 - candidate): the minimum is the cheapest, latest candidate
-        {
-            // every lane needs the exception bits of ITS candidate: 16 rounds of ballots, round r serves candidate mini + r
-            OptSeq q{blk, {0, 0, 0, 0}, 0, 0};
-            for (int r = 0; mini + r < 16; ++r) {
-                uint32_t mk[4];
-                opt_mask(v, kOptBits[mini + r], mk);
-                if (lane == r) { q.mask[0] = mk[0]; q.mask[1] = mk[1]; q.mask[2] = mk[2]; q.mask[3] = mk[3]; }
-            }
-            if (cand < 16) {
-                q.w = kOptBits[cand];
-                q.c = __popc(q.mask[0]) + __popc(q.mask[1]) + __popc(q.mask[2]) + __popc(q.mask[3]);
-                if (q.c < 128) {
-                    const int cost = 4 * q.w + s16_words(q);
-                    if (cost <= 4 * 32) key = ((unsigned)cost << 5) | (unsigned)(31 - cand);
+        for (int r0 = mini; r0 < 16; r0 += 2) {
+            int cs[2] = {128, 128};
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (r0 + t < 16) cs[t] = opt_materialise(v, kOptBits[r0 + t], seq + 256 * t, lane);
+            __syncwarp();
+            if (lane < 2 && r0 + lane < 16) {
+                const int cand = r0 + lane, c = cs[lane];
+                if (c < 128) {
+                    const int cost = 4 * kOptBits[cand] + (c > 0 ? s16_words(MemSeq{seq + 256 * lane, c}) : 0);
+                    if (cost <= 4 * 32) key = min(key, ((unsigned)cost << 5) | (unsigned)(31 - cand));
                 }
             }
+            __syncwarp();
         }
         key = __reduce_min_sync(kFull, key);
         const int b = key == 0xffffffffu ? 16 : 31 - (int)(key & 31u);
         const int w = kOptBits[b];
-        OptSeq q{blk, {0, 0, 0, 0}, 0, w};
-        if (b < 16) {
-            opt_mask(v, w, q.mask);
-            q.c = __popc(q.mask[0]) + __popc(q.mask[1]) + __popc(q.mask[2]) + __popc(q.mask[3]);
-        }
+        const int c = b < 16 ? opt_materialise(v, w, seq, lane) : 0;
+        __syncwarp();
         // ---- header, S16 words (serial by nature: one lane), packed groups (fastpack masks to w bits)
         int sw = 0;
-        if (lane == 0 && q.c > 0) {
+        if (lane == 0 && c > 0) {
+            const MemSeq q{seq, c};
             int at = 0;
-            const int n = 2 * q.c;
+            const int n = 2 * c;
             while (at < n) {
                 uint32_t word;
                 const int took = s16_block(q, at, n - at, &word);
@@ -456,7 +459,7 @@ __device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink
             }
         }
         sw = __shfl_sync(kFull, sw, 0);
-        if (WRITE && lane == 0) sink.put(pos, (uint32_t)b | ((uint32_t)q.c << 8) | ((uint32_t)sw << 16));
+        if (WRITE && lane == 0) sink.put(pos, (uint32_t)b | ((uint32_t)c << 8) | ((uint32_t)sw << 16));
         pos += 1 + sw;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -466,7 +469,7 @@ __device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink
             }
             pos += w;
         }
-        __syncwarp(); // the staged block has been read: the next one may overwrite it
+        __syncwarp(); // the sequences have been read: the next block may overwrite them
     }
     return pos - pos0;
 }
@@ -787,11 +790,11 @@ __device__ int64_t warp_fp_decode_page(const uint32_t *inw, int64_t avail, int n
 }
 
 // ------------------------------------------------------------------- kernels
-template <bool WRITE>
-__global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
+template <bool WRITE, bool OPT> // OPT: the OptPFD instantiation (16 KB of shared memory the other codecs should not pay for)
+__global__ void __launch_bounds__(kEncWarps * 32, 3) k_encode(const EncArgs a)
 {
     __shared__ uint32_t s_stage[kEncWarps][48];
-    __shared__ uint32_t s_blk[kEncWarps][128]; // OptPFD: the block being priced
+    __shared__ int32_t s_blk[kEncWarps][OPT ? 512 : 1]; // OptPFD: the exception sequences of the two candidates being priced
     __shared__ int s_freq[kEncWarps][34];
     __shared__ int s_cnt[kEncWarps][34];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -851,7 +854,7 @@ __global__ void __launch_bounds__(kEncWarps * 32) k_encode(const EncArgs a)
                 if (WRITE && lane == 0) sink.put(pos, (uint32_t)m); // F1's count word, or Composition's 0 marker
                 ++pos;
                 if (tr.xorbp) pos += warp_xor128_encode<WRITE>(x, m, sink, pos, lane);
-                else pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, s_blk[wib], lane);
+                else if (OPT) pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, s_blk[wib], lane);
             }
             const int64_t r = n - m;
             if (r > 0) {
@@ -3977,7 +3980,8 @@ int codec_encode_plan(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.flags = ctx->dErr.as<int>();
     {
         KScope ks(ctx, MCP_K_ENCODE);
-        k_encode<false><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
+        if (codec_traits(a.codec).optpfd) k_encode<false, true><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
+        else k_encode<false, false><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
         MCP_TRY(check_launch(ctx, "k_encode<size>"));
     }
     MCP_TRY(exclusive_scan_i64(ctx, a.sizes, nlists, d_out_off));
@@ -4008,7 +4012,8 @@ int codec_encode_emit(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         a.shadow = ctx->dShadow.as<uint32_t>();
     }
     KScope ks(ctx, MCP_K_ENCODE);
-    k_encode<true><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
+    if (codec_traits(a.codec).optpfd) k_encode<true, true><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
+    else k_encode<true, false><<<grid_for_lists(ctx, nlists), kEncWarps * 32, 0, ctx->stream>>>(a);
     return check_launch(ctx, "k_encode<emit>");
 }
 
