@@ -2134,7 +2134,7 @@ __device__ __forceinline__ int64_t warp_short_list_encode(const CodecTraits tr, 
     int64_t pos = 0;
     if (tr.sk) { if (WRITE && lane == 0) sink.put(0, (uint32_t)n); pos = 1; } // IntCompressor: compressed[0] = n
     if (n > 0) {
-        if (tr.fastpfor && !tr.sk) { if (WRITE && lane == 0) sink.put(0, 0u); pos = 1; }
+        if ((tr.fastpfor || tr.xorbp || tr.optpfd) && !tr.sk) { if (WRITE && lane == 0) sink.put(0, 0u); pos = 1; } // Composition's 0 marker
         auto getv = [&](int64_t i) -> uint32_t { return x(i); };
         pos += warp_vb_encode<WRITE>(getv, n, sink, pos, stage, lane);
     }
@@ -2149,63 +2149,92 @@ __device__ __forceinline__ bool warp_short_list_decode(const CodecTraits tr, con
     int64_t p = 0;
     if (tr.sk) { if (avail < 1 || (int64_t)src.get(0) != n) return false; p = 1; }
     if (n == 0) return true;
-    if (tr.fastpfor && !tr.sk) { if (avail < 1 || src.get(0) != 0u) return false; p = 1; }
+    if ((tr.fastpfor || tr.xorbp || tr.optpfd) && !tr.sk) { if (avail < 1 || src.get(0) != 0u) return false; p = 1; }
     if (!warp_vb_decode<false>(src, p, avail, n, out, 0u, lane)) return false;
     if (delta) { __syncwarp(); warp_inverse_delta(out, n, lane); }
     return true;
 }
 
-// Any list of a flat-kernel call by one warp, FastPFOR pages included (a list of at least one block among lists that are
-// otherwise all VariableByte: FastPFOR128 on ~100-value lists meets one every few hundred lists).  Same steps as k_encode.
-// fq: 68 ints of scratch.  *unsupported is raised for a multi-page list (the stale-buffer emulation lives in k_encode).
-template <bool WRITE>
+// Any list of a flat-kernel call by one warp, first-stage blocks included (a list of at least one FastPFOR / XorBinaryPacking /
+// OptPFD block among lists that are otherwise all VariableByte: the 128-int codecs on ~100-value lists meet one every few
+// hundred lists).  Same steps as k_encode.  `x` is the sequence the flat kernels code (gaps for XorBinaryPacking's integrated
+// tail); fq: 68 ints of scratch; blk: OptPFD's 512 words.  *unsupported is raised for a multi-page FastPFOR list (the
+// stale-buffer emulation lives in k_encode).
+template <bool WRITE, bool OPT>
 __device__ __forceinline__ int64_t warp_any_list_encode(const CodecTraits tr, const ValSeq x, int64_t n, const WordSink sink, bool app,
-                                                        uint32_t *stage, int *fq, int lane, bool *unsupported)
+                                                        uint32_t *stage, int *fq, int32_t *blk, int lane, bool *unsupported)
 {
-    if (!(tr.fastpfor && n >= tr.fp_block)) return warp_short_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
-    const int64_t m = n - n % tr.fp_block;
-    if (m > kFpPage) { *unsupported = true; return 0; }
-    if (WRITE && lane == 0) sink.put(0, (uint32_t)(tr.sk ? n : m)); // IntCompressor's n, or FastPFOR.compress's count word
+    const int64_t blkn = tr.fastpfor ? tr.fp_block : 128;
+    if (!(tr.fastpfor || tr.xorbp || tr.optpfd) || n < blkn) return warp_short_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
+    const int64_t m = n - n % blkn;
+    if (tr.fastpfor && m > kFpPage) { *unsupported = true; return 0; }
+    if (WRITE && lane == 0) sink.put(0, (uint32_t)(tr.sk ? n : m)); // IntCompressor's n, or the first stage's count word
     int64_t pos = 1;
-    const int64_t w = tr.fp_block == 256 ? warp_fastpfor_encode<WRITE, 8>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane)
-                                         : warp_fastpfor_encode<WRITE, 4>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane);
-    if (WRITE && app) { // pages are written as native words (byte-granular metadata): swapped afterwards
-        __syncwarp();
-        for (int64_t j = pos + lane; j < pos + w; j += 32) sink.w[j] = bswap32(sink.w[j]);
+    if (tr.fastpfor) {
+        const int64_t w = tr.fp_block == 256 ? warp_fastpfor_encode<WRITE, 8>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane)
+                                             : warp_fastpfor_encode<WRITE, 4>(x, m, WRITE ? sink.w + pos : nullptr, fq, fq + 34, nullptr, lane);
+        if (WRITE && app) { // pages are written as native words (byte-granular metadata): swapped afterwards
+            __syncwarp();
+            for (int64_t j = pos + lane; j < pos + w; j += 32) sink.w[j] = bswap32(sink.w[j]);
+        }
+        pos += w;
+    } else if (tr.xorbp) {
+        pos += warp_xor128_encode<WRITE>(ValSeq{x.in, false}, m, sink, pos, lane); // the blocks XOR the values themselves
+    } else if (OPT) {
+        pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, blk, lane);
     }
-    pos += w;
     if (n > m) {
-        auto getv = [&](int64_t i) -> uint32_t { return x(m + i); };
-        pos += warp_vb_encode<WRITE>(getv, n - m, sink, pos, stage, lane);
+        if (tr.xorbp) { // IntegratedVariableByte restarts at 0 behind the blocks (IntegratedVariableByte.java:40)
+            const uint32_t *v = x.in;
+            auto getv = [&](int64_t i) -> uint32_t { return i > 0 ? __ldg(v + m + i) - __ldg(v + m + i - 1) : __ldg(v + m); };
+            pos += warp_vb_encode<WRITE>(getv, n - m, sink, pos, stage, lane);
+        } else {
+            auto getv = [&](int64_t i) -> uint32_t { return x(m + i); };
+            pos += warp_vb_encode<WRITE>(getv, n - m, sink, pos, stage, lane);
+        }
     }
     if (app) { if (WRITE && lane == 0) sink.put(pos, 0u); ++pos; }
     return pos;
 }
 
-// scr: cap words of shared memory (a big-endian-framed page is un-swapped into it); fq: 68 ints
+// scr: cap words of shared memory (a big-endian-framed FastPFOR page is un-swapped into it); fq: 68 ints; ex: OptPFD's 284 words.
+// `delta`: what the flat decoder undoes (true for XorBinaryPacking: its all-tail lists are gap-coded).
+template <bool OPT>
 __device__ __forceinline__ bool warp_any_list_decode(const CodecTraits tr, const WordSrc src, int64_t avail, int64_t n, uint32_t *out,
-                                                     bool delta, uint32_t *scr, int cap, int *fq, int lane, bool *unsupported)
+                                                     bool delta, uint32_t *scr, int cap, int *fq, uint32_t *ex, int lane, bool *unsupported)
 {
-    if (!(tr.fastpfor && n >= tr.fp_block)) return warp_short_list_decode(tr, src, avail, n, out, delta, lane);
-    const int64_t m = n - n % tr.fp_block;
-    if (m > kFpPage) { *unsupported = true; return true; }
+    const int64_t blkn = tr.fastpfor ? tr.fp_block : 128;
+    if (!(tr.fastpfor || tr.xorbp || tr.optpfd) || n < blkn) return warp_short_list_decode(tr, src, avail, n, out, delta, lane);
+    const int64_t m = n - n % blkn;
+    if (tr.fastpfor && m > kFpPage) { *unsupported = true; return true; }
     if (avail < 1 || (int64_t)src.get(0) != (tr.sk ? n : m)) return false;
-    int64_t p = 1, used;
-    if (src.swap) {
-        const int64_t take = avail - p;
-        if (take > cap) { *unsupported = true; return true; }
-        for (int64_t j = lane; j < take; j += 32) scr[j] = src.get(p + j);
-        __syncwarp();
-        used = tr.fp_block == 256 ? warp_fp_decode_page<8, false>(scr, take, (int)m, out, fq, fq + 34, lane)
-                                  : warp_fp_decode_page<4, false>(scr, take, (int)m, out, fq, fq + 34, lane);
-    } else
-        used = tr.fp_block == 256 ? warp_fp_decode_page<8, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane)
-                                  : warp_fp_decode_page<4, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane);
+    int64_t p = 1, used = -1;
+    uint32_t carry = 0;
+    if (tr.fastpfor) {
+        if (src.swap) {
+            const int64_t take = avail - p;
+            if (take > cap) { *unsupported = true; return true; }
+            for (int64_t j = lane; j < take; j += 32) scr[j] = src.get(p + j);
+            __syncwarp();
+            used = tr.fp_block == 256 ? warp_fp_decode_page<8, false>(scr, take, (int)m, out, fq, fq + 34, lane)
+                                      : warp_fp_decode_page<4, false>(scr, take, (int)m, out, fq, fq + 34, lane);
+        } else
+            used = tr.fp_block == 256 ? warp_fp_decode_page<8, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane)
+                                      : warp_fp_decode_page<4, true>(src.w + p, avail - p, (int)m, out, fq, fq + 34, lane);
+    } else if (tr.xorbp) {
+        used = warp_xor128_decode(src, p, avail, m, out, carry, lane);
+    } else if (OPT) {
+        used = warp_optpfd_decode(src, p, avail, m, out, ex, lane);
+    }
     __syncwarp();
     if (used < 0) return false;
     p += used;
-    if (n > m && !warp_vb_decode<false>(src, p, avail, n - m, out + m, 0u, lane)) return false;
-    if (delta) { __syncwarp(); warp_inverse_delta(out, n, lane); }
+    if (n > m) {
+        const bool ok = tr.xorbp ? warp_vb_decode<true>(src, p, avail, n - m, out + m, 0u, lane) // restarts at 0 (see the encoder)
+                                 : warp_vb_decode<false>(src, p, avail, n - m, out + m, 0u, lane);
+        if (!ok) return false;
+    }
+    if (delta && !tr.xorbp) { __syncwarp(); warp_inverse_delta(out, n, lane); }
     return true;
 }
 
@@ -3186,13 +3215,14 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_size(const TileEncArgs ta)
 // VariableByte -- FastPFOR128 on ~100-value lists meets one every few hundred lists): sized (EMIT = false, before the scan)
 // and written (EMIT = true, after it) by the warp-per-list routines, a CTA per tile of the worklist.  Kept out of the
 // kernels above on purpose: inlined there, the FastPFOR page encoder costs them 8-24 registers and 4 KB of shared memory.
-template <bool EMIT>
+template <bool EMIT, bool OPT> // OPT: OptPFD (its pricing scratch)
 __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
 {
     constexpr int WARPS = VB4_THREADS / 32;
     const FastEncArgs &a = ta.f;
     __shared__ uint32_t s_stage[WARPS][64];
     __shared__ int s_fq[WARPS][68];
+    __shared__ int32_t s_blk[WARPS][OPT ? 512 : 1];
     __shared__ long long s_w64[VB4_THREADS];
     __shared__ long long s_red[WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -3207,8 +3237,8 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
         bool multi = false;
         for (int j = warp; j < nl; j += WARPS) {
             const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
-            const int64_t w = warp_any_list_encode<false>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp],
-                                                          s_fq[warp], lane, &multi);
+            const int64_t w = warp_any_list_encode<false, OPT>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp],
+                                                               s_fq[warp], s_blk[warp], lane, &multi);
             if (lane == 0) s_w64[j] = w;
             __syncwarp();
         }
@@ -3243,8 +3273,8 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
             uint32_t *gout = reinterpret_cast<uint32_t *>(a.out) + gbase;
             for (int j = warp; j < nl; j += WARPS) {
                 const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
-                warp_any_list_encode<true>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_w64[j], a.app}, a.app, s_stage[warp],
-                                           s_fq[warp], lane, &multi);
+                warp_any_list_encode<true, OPT>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_w64[j], a.app}, a.app, s_stage[warp],
+                                                s_fq[warp], s_blk[warp], lane, &multi);
                 __syncwarp();
             }
         }
@@ -3584,10 +3614,12 @@ constexpr int kScanItems = 8;
 
 // The tiles k_vb4_decode left aside (a list with a FastPFOR page): warp-per-list routines, a CTA per tile of the worklist.
 constexpr int D4P_SCR = 1280; // words a warp may un-swap a big-endian-framed page into (a list beyond it: flag 2)
+template <bool OPT>
 __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode_pages(const FastDecArgs a, const int *defer_cnt, const int *defer_tiles)
 {
     __shared__ uint32_t s_scr[D4_WARPS][D4P_SCR];
     __shared__ int s_fq[D4_WARPS][68];
+    __shared__ uint32_t s_ex[D4_WARPS][OPT ? 2 * 128 + 28 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const CodecTraits tr = codec_traits(a.codec);
     const int ndefer = *defer_cnt;
@@ -3598,8 +3630,8 @@ __global__ void __launch_bounds__(D4_THREADS) k_vb4_decode_pages(const FastDecAr
         for (int j = warp; j < nl; j += D4_WARPS) {
             const WordSrc src{reinterpret_cast<const uint32_t *>(a.in + gin[j]), a.app};
             bool multi = false;
-            const bool ok = warp_any_list_decode(tr, src, (gin[j + 1] - gin[j]) >> 2, goo[j + 1] - goo[j], a.out + goo[j], a.delta, s_scr[warp],
-                                                 D4P_SCR, s_fq[warp], lane, &multi);
+            const bool ok = warp_any_list_decode<OPT>(tr, src, (gin[j + 1] - gin[j]) >> 2, goo[j + 1] - goo[j], a.out + goo[j], a.delta, s_scr[warp],
+                                                      D4P_SCR, s_fq[warp], s_ex[warp], lane, &multi);
             if (lane == 0 && multi) atomicMax(a.err, 2); // the host takes the batched / warp-per-list kernels
             else if (!ok && lane == 0) atomicMax(a.err, 4);
             __syncwarp();
@@ -3751,6 +3783,8 @@ bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, boo
     const int codec = codec_id & MCP_CODEC_MASK;
     const bool delta = (codec_id & MCP_FLAG_DELTA) != 0;
     (void)encode; // both directions
+    const CodecTraits tr = codec_traits(codec);
+    if ((tr.optpfd || (tr.xorbp && !delta)) && nlists > 0 && (double)total_vals < 0.95 * 128.0 * (double)nlists) return true; // flat_only_codec
     return batched_applicable(codec, delta, total_vals, nlists) || shortlist_applicable(nullptr, codec, delta, total_vals, nlists, encode);
 }
 
@@ -3761,15 +3795,27 @@ int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists)
 {
     const CodecTraits tr = codec_traits(codec_id & MCP_CODEC_MASK);
     if (tr.fastpfor) return 4 * (total_vals + total_vals / 8 + 384 * nlists + 64);
+    if (tr.optpfd) return 4 * (3 * total_vals + total_vals / 4 + 8 * nlists + 64); // a block: header + up to 254 S16 words + 4 x 20 packed (codec_max_words)
     if (!tr.blocks) return 4 * (total_vals + total_vals / 4 + 4 * nlists + 64); // VariableByte alone: 5 bytes per value at worst
     return 4 * (total_vals + total_vals / 32 + 44 * nlists + 64);
+}
+
+// XorBinaryPacking / OptPFD (128-int blocks) on short lists: no thread-per-list or batched kernel takes them, but lists below one
+// block are Composition's 0 marker + VariableByte (of gaps, for XorBinaryPacking's integrated tail) like FastPFOR128's: the flat
+// kernels serve the call, k_vb4_pages the tiles that hold a block.  (Delta before the integrated codec is not a combination anyone uses.)
+static bool flat_only_codec(const mcp_ctx *ctx, int codec, bool delta, int64_t total_vals, int64_t nlists)
+{
+    const CodecTraits tr = codec_traits(codec);
+    if (!(tr.xorbp || tr.optpfd) || (tr.xorbp && delta)) return false;
+    return ctx->shortListCodec && ctx->flatCodec && nlists > 0 && (double)total_vals < 0.95 * 128.0 * (double)nlists;
 }
 
 // flat kernels on a FastPFOR codec: is a list of a full block something to plan for (average length within a third of
 // the block) or an outlier (then the flat call fails over to the batched kernels as a whole)?
 static bool flat_pages_likely(const CodecTraits &tr, int64_t total_vals, int64_t nlists)
 {
-    return tr.fastpfor && nlists > 0 && 1.5 * (double)total_vals >= (double)tr.fp_block * (double)nlists;
+    const int64_t blk = tr.fastpfor ? tr.fp_block : ((tr.xorbp || tr.optpfd) ? 128 : 0);
+    return blk > 0 && nlists > 0 && 1.5 * (double)total_vals >= (double)blk * (double)nlists;
 }
 
 // ... or the rule (average length at the block size or beyond: the thread-per-list / flat kernels are not tried at all)
@@ -3803,13 +3849,16 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
     a.out = d_out;
     a.cap = d_out ? cap : 0;
     const bool batched = batched_applicable(a.codec, a.delta, total_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists, true) && !flat_pages_common(a.codec, total_vals, nlists);
+    const bool flat_only = flat_only_codec(ctx, a.codec, a.delta, total_vals, nlists);
+    const bool shortl = flat_only || (shortlist_applicable(ctx, a.codec, a.delta, total_vals, nlists, true) && !flat_pages_common(a.codec, total_vals, nlists));
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
+    if (codec_traits(a.codec).xorbp) a.delta = true; // what the flat kernels code: the integrated tail's gaps
     // pass 0: thread-per-list kernel (short lists); pass 1: thread-per-block kernels
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1 && !batched) { ++ctx->fastEncodeFallbacks; return MCP_E_UNSUPPORTED; }
         // lists that are all VariableByte (FastPFOR / FastPFOR128 below one block, VariableByte alone) take the flat kernel
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
+        if (pass == 0 && flat_only && !flat) return MCP_E_UNSUPPORTED;
         a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.93 * VB4::SPAN, VB4::MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_vals, nlists);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
@@ -3834,16 +3883,19 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
                 const bool pages = flat_pages_likely(tr, total_vals, nlists);
                 int *defer_cnt = pages ? reinterpret_cast<int *>(sp + 24) : nullptr;
                 int *defer_tiles = pages ? reinterpret_cast<int *>(sp + 32 + (size_t)a.nbatches * sizeof(uint64_t)) : nullptr;
-                TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (tr.fastpfor ? 2 : 0), tr.fastpfor ? tr.fp_block : 0,
+                const bool marker = tr.fastpfor || tr.xorbp || tr.optpfd; // a first stage that took nothing: Composition's 0 marker
+                TileEncArgs ta{a, reinterpret_cast<int64_t *>(a.state), tr.sk ? 1 : (marker ? 2 : 0), tr.fastpfor ? tr.fp_block : (marker ? 128 : 0),
                                defer_cnt, defer_tiles};
                 const unsigned pgrid = (unsigned)std::min<int64_t>(a.nbatches, (int64_t)ctx->prop.multiProcessorCount * 8);
                 if (a.delta) k_vb4_size<true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 else k_vb4_size<false><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
-                if (pages) k_vb4_pages<false><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
+                if (pages && tr.optpfd) k_vb4_pages<false, true><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
+                else if (pages) k_vb4_pages<false, false><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
                 k_vb4_scan<<<1, 1024, 0, ctx->stream>>>(ta.tile_words, a.nbatches, a.total, a.out_off + a.nlists, a.cap, a.err);
                 if (a.delta) k_vb4_tile<VB4_THREADS, VB4_VPT, true, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
                 else k_vb4_tile<VB4_THREADS, VB4_VPT, false, true><<<(unsigned)a.nbatches, VB4_THREADS, 0, ctx->stream>>>(ta);
-                if (pages) k_vb4_pages<true><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
+                if (pages && tr.optpfd) k_vb4_pages<true, true><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
+                else if (pages) k_vb4_pages<true, false><<<pgrid, VB4_THREADS, 0, ctx->stream>>>(ta);
             } else if (pass == 0) {
                 const int64_t want = (a.nbatches + SL_WARPS - 1) / SL_WARPS, res = (int64_t)ctx->prop.multiProcessorCount * SL_CTAS;
                 k_sl_encode<<<(unsigned)(want < res ? want : res), SL_WARPS * 32, 0, ctx->stream>>>(a);
@@ -3883,14 +3935,17 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
     a.out = reinterpret_cast<uint32_t *>(d_out);
     a.out_off = d_out_off;
     const bool batched = batched_applicable(a.codec, a.delta, total_out_vals, nlists);
-    const bool shortl = shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists, false) && !flat_pages_common(a.codec, total_out_vals, nlists);
+    const bool flat_only = flat_only_codec(ctx, a.codec, a.delta, total_out_vals, nlists);
+    const bool shortl = flat_only || (shortlist_applicable(ctx, a.codec, a.delta, total_out_vals, nlists, false) && !flat_pages_common(a.codec, total_out_vals, nlists));
     if (!batched && !shortl) return MCP_E_UNSUPPORTED;
+    if (codec_traits(a.codec).xorbp) a.delta = true; // (see codec_fast_encode)
     MCP_CUDA(ctx, ctx->dErr.reserve(64));
     a.err = ctx->dErr.as<int>();
     for (int pass = shortl ? 0 : 1; pass < 2; ++pass) {
         if (pass == 1 && !batched) return MCP_E_UNSUPPORTED;
         MCP_CUDA(ctx, cudaMemsetAsync(ctx->dErr.p, 0, sizeof(int), ctx->stream));
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
+        if (pass == 0 && flat_only && !flat) return MCP_E_UNSUPPORTED;
         a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_out_vals, nlists, 0.88 * D4_VSPAN, D4_MAXL) : 32)
                                       : fast_lists_per_batch(a.codec, total_out_vals, nlists);
         const int64_t nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
@@ -3898,7 +3953,8 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
             KScope ks(ctx, MCP_K_DECODE);
             const CodecTraits tr = codec_traits(a.codec);
             if (pass == 0 && flat) {
-                const int hdr_mode = tr.sk ? 1 : (tr.fastpfor ? 2 : 0), page = tr.fastpfor ? tr.fp_block : 0;
+                const bool marker = tr.fastpfor || tr.xorbp || tr.optpfd;
+                const int hdr_mode = tr.sk ? 1 : (marker ? 2 : 0), page = tr.fastpfor ? tr.fp_block : (marker ? 128 : 0);
                 int *defer_cnt = nullptr, *defer_tiles = nullptr;
                 if (flat_pages_likely(tr, total_out_vals, nlists)) { // (see codec_fast_encode)
                     MCP_CUDA(ctx, ctx->dScanTmp.reserve(16 + (size_t)nbatches * sizeof(int)));
@@ -3908,9 +3964,9 @@ int codec_fast_decode(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_
                 }
                 if (a.delta) k_vb4_decode<true><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page, defer_cnt, defer_tiles);
                 else k_vb4_decode<false><<<(unsigned)nbatches, D4_THREADS, 0, ctx->stream>>>(a, hdr_mode, page, defer_cnt, defer_tiles);
-                if (defer_cnt)
-                    k_vb4_decode_pages<<<(unsigned)std::min<int64_t>(nbatches, (int64_t)ctx->prop.multiProcessorCount * 8), D4_THREADS, 0,
-                                         ctx->stream>>>(a, defer_cnt, defer_tiles);
+                const unsigned pgrid = (unsigned)std::min<int64_t>(nbatches, (int64_t)ctx->prop.multiProcessorCount * 8);
+                if (defer_cnt && tr.optpfd) k_vb4_decode_pages<true><<<pgrid, D4_THREADS, 0, ctx->stream>>>(a, defer_cnt, defer_tiles);
+                else if (defer_cnt) k_vb4_decode_pages<false><<<pgrid, D4_THREADS, 0, ctx->stream>>>(a, defer_cnt, defer_tiles);
             } else if (pass == 0) {
                 const int64_t res = (int64_t)ctx->prop.multiProcessorCount * SL_DCTAS;
                 k_sl_decode<<<(unsigned)(nbatches < res ? nbatches : res), 32, 0, ctx->stream>>>(a, nbatches);

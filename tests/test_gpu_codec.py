@@ -676,8 +676,11 @@ def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
     codecs = [N.CODEC_VB | N.FLAG_DELTA, N.CODEC_VB]
     if kind not in ("long",):
         codecs += [N.CODEC_FASTPFOR256_VB | N.FLAG_DELTA, N.CODEC_SK_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR256_VB]
-    if kind in ("breach", "near128"):  # tiles with a FastPFOR128 page among all-VariableByte lists: the k_vb4_pages kernels
-        codecs += [N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB]
+    if kind in ("breach", "near128"):  # tiles with a 128-int block among all-VariableByte lists: the k_vb4_pages kernels
+        codecs += [N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB,
+                   N.CODEC_XOR128_IVB, N.CODEC_OPTPFD_VB | N.FLAG_DELTA, N.CODEC_OPTPFD_VB]
+    if kind in ("tiny", "wide"):       # (no list reaches a block: the flat kernels alone; `wide` sends tiles to the warp-per-list routines)
+        codecs += [N.CODEC_XOR128_IVB, N.CODEC_OPTPFD_VB | N.FLAG_DELTA]
     guard = np.full(256, 0x5AC3A55A, np.uint32)
     ctx.set_option("short_list_codec", 2)
     ctx.set_option("flat_codec", 1)
@@ -720,9 +723,11 @@ def test_flat_kernels_on_awkward_shapes(ctx, kind, shift):
                 finally:
                     for q in bufs.values():
                         ctx.dev_free(q)
-            if kind in ("breach", "near128") and (cid & 0xff) in (N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB):
+            if kind in ("breach", "near128") and (cid & 0xff) in (N.CODEC_FASTPFOR128_VB, N.CODEC_SK_FASTPFOR128_VB, N.CODEC_XOR128_IVB,
+                                                                  N.CODEC_OPTPFD_VB):
                 after = ctx.codec_stats()  # ... and nothing was handed on to the batched / warp-per-list kernels
                 assert after["short_fallbacks"] == before["short_fallbacks"], (hex(cid), before, after)
+                assert after["short_calls"] == before["short_calls"] + 4, (hex(cid), before, after)  # 2 framings x (encode + decode)
     finally:
         ctx.set_option("short_list_codec", 1)
         ctx.set_option("flat_codec", FLAT_DEFAULT)
