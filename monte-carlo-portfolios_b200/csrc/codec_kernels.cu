@@ -334,49 +334,51 @@ __device__ __constant__ unsigned char kS16Bits[16][28] = {
 
 // The exception sequence of a block at width `w`: entry e < c is the e-th exception's high part (block order), entry c + e
 // its position -- as a Java int (S16 compares signed).  Written out in shared memory by opt_materialise.
-struct MemSeq {
-    const int32_t *s;
-    int c;
-    __device__ __forceinline__ int32_t operator()(int e) const { return s[e]; }
-};
+//
+// S16.compressblock (S16.java:80-100): the first of the 16 layouts that holds the next min(num, n) entries; returns how many
+// it took (0 = "Too big a number": cannot happen, high parts are < 2^28) and the word.  S16.estimatecompress (:57-72) counts
+// the words of a sequence by the same steps.
+// By the whole warp: lane j holds entry first + j.  Layout idx fits when every one of its first `num` entries is below
+// 2^bits[idx][j] as a Java int (a negative int fits anything, S16.java:86); all 16 layouts are tested at once: `tab` holds, per
+// lane j and per bit length d of an entry, the 16-bit set of layouts that take such an entry at place j (all of them beyond a
+// layout's last place), so a word is one table read, one AND across the warp and a find-first-set.  Behind the sets: the
+// shift of entry j in the word of layout idx (s16_tables builds both, in shared memory).
+constexpr int kS16TabBytes = 32 * 32 * 2 + 16 * 32;
 
-// S16.compressblock (S16.java:80-100): the first of the 16 layouts that holds the next min(num, n) entries; returns
-// how many it took (0 = "Too big a number": cannot happen, high parts are < 2^28) and the word
-template <typename SEQ>
-__device__ __forceinline__ int s16_block(const SEQ &q, int first, int n, uint32_t *word)
+__device__ __forceinline__ void s16_tables(uint8_t *tab, int tid, int nthreads)
 {
-    for (int idx = 0; idx < 16; ++idx) {
-        uint32_t wv = (uint32_t)idx << 28;
-        const int num = kS16Num[idx] < n ? kS16Num[idx] : n;
-        int j = 0, bits = 0;
-        while (j < num) {
-            const int32_t v = q(first + j);
-            const int bw = kS16Bits[idx][j];
-            if (!(v < (int32_t)(1u << bw))) break;
-            wv |= (uint32_t)v << bits;
-            bits += bw;
-            ++j;
-        }
-        if (j == num) { *word = wv; return num; }
+    uint16_t *sets = reinterpret_cast<uint16_t *>(tab);
+    for (int i = tid; i < 1024; i += nthreads) {
+        const int j = i >> 5, d = i & 31;
+        unsigned set = 0;
+        for (int idx = 0; idx < 16; ++idx)
+            if (j >= kS16Num[idx] || d <= (int)kS16Bits[idx][j < 28 ? j : 0]) set |= 1u << idx;
+        sets[i] = (uint16_t)set;
     }
-    *word = 0;
-    return 0;
+    for (int i = tid; i < 512; i += nthreads) {
+        const int idx = i >> 5, j = i & 31;
+        int sh = 0;
+        for (int q = 0; q < j && q < kS16Num[idx]; ++q) sh += kS16Bits[idx][q];
+        tab[2048 + i] = (uint8_t)(sh > 31 ? 31 : sh);
+    }
 }
 
-// words S16.compress spends on the block's exception sequence (S16.estimatecompress, S16.java:57-72)
-template <typename SEQ>
-__device__ __forceinline__ int s16_words(const SEQ &q)
+template <bool WORD>
+__device__ __forceinline__ int warp_s16_block(const int32_t *seq, int first, int n, const uint8_t *tab, int lane, uint32_t *word)
 {
-    int pos = 0, words = 0;
-    const int n = 2 * q.c;
-    while (pos < n) {
-        uint32_t w;
-        const int took = s16_block(q, pos, n - pos, &w);
-        if (took <= 0) return 1 << 20;
-        pos += took;
-        ++words;
+    const bool mine = lane < n && lane < 28;
+    const int32_t v = mine ? seq[first + lane] : 0;
+    const int need = v < 0 ? 0 : 32 - __clz(v);
+    unsigned set = mine ? reinterpret_cast<const uint16_t *>(tab)[32 * lane + need] : 0xffffu;
+    set = __reduce_and_sync(kFull, set);
+    if (set == 0) { if (WORD) *word = 0; return 0; }
+    const int idx = __ffs(set) - 1;
+    const int num = kS16Num[idx] < n ? kS16Num[idx] : n;
+    if (WORD) {
+        const uint32_t part = lane < num ? (uint32_t)v << tab[2048 + 32 * idx + lane] : 0u;
+        *word = ((uint32_t)idx << 28) | __reduce_or_sync(kFull, part);
     }
-    return words;
+    return num;
 }
 
 // exception bits of the staged block at width w (all lanes compute the same four words)
@@ -408,7 +410,8 @@ __device__ __forceinline__ int opt_materialise(const uint32_t (&v)[4], int w, in
 }
 
 template <bool WRITE>
-__device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, int32_t *seq /* 2 x 256 words */, int lane)
+__device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink &sink, int64_t pos, int32_t *seq /* 256 words */,
+                                      const uint8_t *tab /* s16_tables */, int lane)
 {
     const int64_t pos0 = pos;
     for (int64_t s = 0; s < m; s += 128) {
@@ -417,48 +420,41 @@ __device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink
 #pragma unroll
         for (int j = 0; j < 4; ++j) { v[j] = x(s + 32 * j + lane); orv |= v[j]; }
         // ---- getBestBFromData (OptPFD.java:61-98): candidates mini .. 15; `mini` is computed from bit WIDTHS but used as the
-        // first INDEX, as the reference does; ties go to the later candidate (<=).  Two candidates per round: the warp writes
-        // their exception sequences out (Simple16's greedy layout search reads every entry many times), lanes 0 and 1 price them.
+        // first INDEX, as the reference does; ties go to the later candidate (<=).  Per candidate the warp writes the exception
+        // sequence out (Simple16's greedy layout search reads every entry many times) and prices it together, a word per step.
         const int mb = bits32(__reduce_or_sync(kFull, orv));
         int mini = 0;
         if (mini + 28 < kOptBits[kOptInvBits[mb]]) mini = kOptBits[kOptInvBits[mb]] - 28;
         unsigned key = 0xffffffffu; // (cost << 5) | (31 - candidate): the minimum is the cheapest, latest candidate
-        for (int r0 = mini; r0 < 16; r0 += 2) {
-            int cs[2] = {128, 128};
-#pragma unroll
-            for (int t = 0; t < 2; ++t)
-                if (r0 + t < 16) cs[t] = opt_materialise(v, kOptBits[r0 + t], seq + 256 * t, lane);
+        for (int cand = mini; cand < 16; ++cand) {
+            const int c = opt_materialise(v, kOptBits[cand], seq, lane);
             __syncwarp();
-            if (lane < 2 && r0 + lane < 16) {
-                const int cand = r0 + lane, c = cs[lane];
-                if (c < 128) {
-                    const int cost = 4 * kOptBits[cand] + (c > 0 ? s16_words(MemSeq{seq + 256 * lane, c}) : 0);
-                    if (cost <= 4 * 32) key = min(key, ((unsigned)cost << 5) | (unsigned)(31 - cand));
+            if (c < 128) {
+                int words = 0;
+                for (int at = 0, n = 2 * c; at < n; ++words) {
+                    uint32_t word;
+                    const int took = warp_s16_block<false>(seq, at, n - at, tab, lane, &word);
+                    if (took <= 0) { words = 1 << 20; break; }
+                    at += took;
                 }
+                const int cost = 4 * kOptBits[cand] + words;
+                if (cost <= 4 * 32) key = min(key, ((unsigned)cost << 5) | (unsigned)(31 - cand));
             }
             __syncwarp();
         }
-        key = __reduce_min_sync(kFull, key);
         const int b = key == 0xffffffffu ? 16 : 31 - (int)(key & 31u);
         const int w = kOptBits[b];
         const int c = b < 16 ? opt_materialise(v, w, seq, lane) : 0;
         __syncwarp();
-        // ---- header, S16 words (serial by nature: one lane), packed groups (fastpack masks to w bits)
+        // ---- header, S16 words, packed groups (fastpack masks to w bits)
         int sw = 0;
-        if (lane == 0 && c > 0) {
-            const MemSeq q{seq, c};
-            int at = 0;
-            const int n = 2 * c;
-            while (at < n) {
-                uint32_t word;
-                const int took = s16_block(q, at, n - at, &word);
-                if (took <= 0) break;
-                if (WRITE) sink.put(pos + 1 + sw, word);
-                at += took;
-                ++sw;
-            }
+        for (int at = 0, n = 2 * c; at < n; ++sw) {
+            uint32_t word;
+            const int took = warp_s16_block<true>(seq, at, n - at, tab, lane, &word);
+            if (took <= 0) break;
+            if (WRITE && lane == 0) sink.put(pos + 1 + sw, word);
+            at += took;
         }
-        sw = __shfl_sync(kFull, sw, 0);
         if (WRITE && lane == 0) sink.put(pos, (uint32_t)b | ((uint32_t)c << 8) | ((uint32_t)sw << 16));
         pos += 1 + sw;
 #pragma unroll
@@ -469,7 +465,7 @@ __device__ int64_t warp_optpfd_encode(const ValSeq &x, int64_t m, const WordSink
             }
             pos += w;
         }
-        __syncwarp(); // the sequences have been read: the next block may overwrite them
+        __syncwarp(); // the sequence has been read: the next block may overwrite it
     }
     return pos - pos0;
 }
@@ -794,7 +790,9 @@ template <bool WRITE, bool OPT> // OPT: the OptPFD instantiation (16 KB of share
 __global__ void __launch_bounds__(kEncWarps * 32, 3) k_encode(const EncArgs a)
 {
     __shared__ uint32_t s_stage[kEncWarps][48];
-    __shared__ int32_t s_blk[kEncWarps][OPT ? 512 : 1]; // OptPFD: the exception sequences of the two candidates being priced
+    __shared__ int32_t s_blk[kEncWarps][OPT ? 256 : 1]; // OptPFD: the exception sequence of the candidate being priced
+    __shared__ __align__(4) uint8_t s_s16[OPT ? kS16TabBytes : 4];
+    if (OPT) { s16_tables(s_s16, threadIdx.x, kEncWarps * 32); __syncthreads(); }
     __shared__ int s_freq[kEncWarps][34];
     __shared__ int s_cnt[kEncWarps][34];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -854,7 +852,7 @@ __global__ void __launch_bounds__(kEncWarps * 32, 3) k_encode(const EncArgs a)
                 if (WRITE && lane == 0) sink.put(pos, (uint32_t)m); // F1's count word, or Composition's 0 marker
                 ++pos;
                 if (tr.xorbp) pos += warp_xor128_encode<WRITE>(x, m, sink, pos, lane);
-                else if (OPT) pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, s_blk[wib], lane);
+                else if (OPT) pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, s_blk[wib], s_s16, lane);
             }
             const int64_t r = n - m;
             if (r > 0) {
@@ -2158,11 +2156,11 @@ __device__ __forceinline__ bool warp_short_list_decode(const CodecTraits tr, con
 // Any list of a flat-kernel call by one warp, first-stage blocks included (a list of at least one FastPFOR / XorBinaryPacking /
 // OptPFD block among lists that are otherwise all VariableByte: the 128-int codecs on ~100-value lists meet one every few
 // hundred lists).  Same steps as k_encode.  `x` is the sequence the flat kernels code (gaps for XorBinaryPacking's integrated
-// tail); fq: 68 ints of scratch; blk: OptPFD's 512 words.  *unsupported is raised for a multi-page FastPFOR list (the
+// tail); fq: 68 ints of scratch; blk / tab: OptPFD's 256 words and its Simple16 tables.  *unsupported is raised for a multi-page FastPFOR list (the
 // stale-buffer emulation lives in k_encode).
 template <bool WRITE, bool OPT>
 __device__ __forceinline__ int64_t warp_any_list_encode(const CodecTraits tr, const ValSeq x, int64_t n, const WordSink sink, bool app,
-                                                        uint32_t *stage, int *fq, int32_t *blk, int lane, bool *unsupported)
+                                                        uint32_t *stage, int *fq, int32_t *blk, const uint8_t *tab, int lane, bool *unsupported)
 {
     const int64_t blkn = tr.fastpfor ? tr.fp_block : 128;
     if (!(tr.fastpfor || tr.xorbp || tr.optpfd) || n < blkn) return warp_short_list_encode<WRITE>(tr, x, n, sink, app, stage, lane);
@@ -2181,7 +2179,7 @@ __device__ __forceinline__ int64_t warp_any_list_encode(const CodecTraits tr, co
     } else if (tr.xorbp) {
         pos += warp_xor128_encode<WRITE>(ValSeq{x.in, false}, m, sink, pos, lane); // the blocks XOR the values themselves
     } else if (OPT) {
-        pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, blk, lane);
+        pos += warp_optpfd_encode<WRITE>(x, m, sink, pos, blk, tab, lane);
     }
     if (n > m) {
         if (tr.xorbp) { // IntegratedVariableByte restarts at 0 behind the blocks (IntegratedVariableByte.java:40)
@@ -3222,7 +3220,9 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
     const FastEncArgs &a = ta.f;
     __shared__ uint32_t s_stage[WARPS][64];
     __shared__ int s_fq[WARPS][68];
-    __shared__ int32_t s_blk[WARPS][OPT ? 512 : 1];
+    __shared__ int32_t s_blk[WARPS][OPT ? 256 : 1];
+    __shared__ __align__(4) uint8_t s_s16[OPT ? kS16TabBytes : 4];
+    if (OPT) { s16_tables(s_s16, threadIdx.x, VB4_THREADS); __syncthreads(); }
     __shared__ long long s_w64[VB4_THREADS];
     __shared__ long long s_red[WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -3238,7 +3238,7 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
         for (int j = warp; j < nl; j += WARPS) {
             const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
             const int64_t w = warp_any_list_encode<false, OPT>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{nullptr, a.app}, a.app, s_stage[warp],
-                                                               s_fq[warp], s_blk[warp], lane, &multi);
+                                                               s_fq[warp], s_blk[warp], s_s16, lane, &multi);
             if (lane == 0) s_w64[j] = w;
             __syncwarp();
         }
@@ -3274,7 +3274,7 @@ __global__ void __launch_bounds__(VB4_THREADS) k_vb4_pages(const TileEncArgs ta)
             for (int j = warp; j < nl; j += WARPS) {
                 const int64_t beg = list_off(l0 + j), n = list_off(l0 + j + 1) - beg;
                 warp_any_list_encode<true, OPT>(tr, ValSeq{a.vals + beg, a.delta}, n, WordSink{gout + s_w64[j], a.app}, a.app, s_stage[warp],
-                                                s_fq[warp], s_blk[warp], lane, &multi);
+                                                s_fq[warp], s_blk[warp], s_s16, lane, &multi);
                 __syncwarp();
             }
         }
