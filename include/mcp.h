@@ -109,10 +109,11 @@ int  mcp_sync(mcp_ctx *ctx);
  * (smallest dense sample in trials, default 1024; process-wide), "overlap_tiles" (> 1 = portfolio tiles alternate between
  * two streams), "item_trials" (trials per valuation work item), "upload_split" (0 = mcp_simulate uploads the scenario
  * tail in one part), "simulate_turns" (mcp_simulate calls in flight on one GPU -- one context and host thread each -- take
- * turns on the SMs: a call enqueues its uploads, waits for the device's token, holds it from its first kernel to the end
- * of its last and downloads after handing it on; 1 / 0 = always / never, -1 (default) = when a call uploads 48 MB or
- * more: without turns the kernels of two long calls interleave, the calls fall into step and copy together with the SMs
- * idle), "ts_slack" (trial-sharded test hook).  Trial indices, breach lists and byte streams are identical
+ * turns on the SMs: a call enqueues its uploads, takes the device's token, makes its kernels wait for the event behind the
+ * previous call's last kernel, enqueues them, records its own event and hands the token on -- before its first host sync,
+ * so the next call's kernels are queued when this call's finish; downloads happen outside; 1 / 0 = always / never,
+ * -1 (default) = when a call uploads 48 MB or more: without turns the kernels of two long calls interleave, the calls
+ * fall into step and copy together with the SMs idle), "ts_slack" (trial-sharded test hook).  Trial indices, breach lists and byte streams are identical
  * either way, moments agree to 1e-9; only the kernels differ. */
 int  mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value);
 

@@ -3904,6 +3904,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
             else k_fp_encode_fast<4><<<(unsigned)a.nbatches, FE_THREADS, 0, ctx->stream>>>(a);
             MCP_TRY(check_launch(ctx, "k_encode_fast"));
         }
+        simulate_turn_end(ctx); // mcp_simulate with calls in flight: this call's last kernel is queued, the next call's may follow
         MCP_CUDA(ctx, cudaMemcpyAsync(ctx->hPinned, sp + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
         MCP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *total_out = *reinterpret_cast<int64_t *>(ctx->hPinned);

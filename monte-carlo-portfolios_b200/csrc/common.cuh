@@ -128,6 +128,8 @@ struct mcp_ctx {
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     int selSlack = 0;              // extra entries of the sparse steps' staging area (experiment knob)
     int simulateTurns = -1;        // mcp_simulate calls in flight on one GPU take turns on the SMs: 0 no, 1 yes, -1 by upload size
+    cudaEvent_t evTurn = nullptr;  // ... "this call's kernels are done", what the next call's kernels wait for
+    bool turnHeld = false;         // this context holds the device's turn token (between simulate_turn_begin and _end)
     bool warpSelect = true;        // small rows (dense samples of <= 1 024 values, <= 512 staged candidates): one warp per row
     bool regSelect = true;         // dense-step selection from registers when the row fits (risk_kernels.cu)
     bool fastCodec = true;         // batched single-pass kernels for the BinaryPacking family (codec_kernels.cu)
@@ -221,6 +223,7 @@ int codec_decode_counts(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *
 int codec_decode_device(mcp_ctx *ctx, int codec_id, int framing, const uint8_t *d_in, const int64_t *d_in_off,
                         int64_t nlists, int32_t *d_out, const int64_t *d_out_off);
 bool codec_fast_applicable(int codec_id, int64_t total_vals, int64_t nlists, bool encode);
+void simulate_turn_end(mcp_ctx *ctx); // (mcp_api.cu) called before the first host sync behind a call's last kernel
 int64_t codec_fast_max_bytes(int codec_id, int64_t total_vals, int64_t nlists);
 int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_vals, const int64_t *d_list_off,
                       int64_t uniform_len, int64_t nlists, int64_t total_vals, int64_t *d_out_off, uint8_t *d_out, int64_t cap,

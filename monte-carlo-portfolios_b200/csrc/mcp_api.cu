@@ -9,6 +9,13 @@
 
 #include <mutex>
 
+// (see simulate_turn_begin)
+struct TurnSlot {
+    std::mutex m;
+    cudaEvent_t last = nullptr; // recorded behind the last kernel of the latest call that took a turn on this device
+};
+static TurnSlot g_turn[64];
+
 using namespace mcp;
 
 namespace {
@@ -59,6 +66,28 @@ void resolve_profile(mcp_ctx *ctx)
 }
 
 } // namespace
+
+static int simulate_turn_begin(mcp_ctx *ctx)
+{
+    TurnSlot &slot = g_turn[ctx->device & 63];
+    slot.m.lock();
+    ctx->turnHeld = true;
+    if (!ctx->evTurn) MCP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evTurn, cudaEventDisableTiming));
+    if (slot.last && slot.last != ctx->evTurn) MCP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, slot.last, 0));
+    return MCP_OK;
+}
+
+namespace mcp {
+void simulate_turn_end(mcp_ctx *ctx)
+{
+    if (!ctx->turnHeld) return;
+    TurnSlot &slot = g_turn[ctx->device & 63];
+    if (ctx->evTurn && cudaEventRecord(ctx->evTurn, ctx->stream) == cudaSuccess) slot.last = ctx->evTurn;
+    ctx->turnHeld = false;
+    slot.m.unlock();
+}
+} // namespace mcp
+
 
 extern "C" {
 
@@ -135,6 +164,12 @@ void mcp_destroy(mcp_ctx *ctx)
     if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
     if (ctx->tA) cudaEventDestroy(ctx->tA);
     if (ctx->tB) cudaEventDestroy(ctx->tB);
+    if (ctx->evTurn) { // nobody may wait for an event that is about to go
+        TurnSlot &slot = g_turn[ctx->device & 63];
+        std::lock_guard<std::mutex> g(slot.m);
+        if (slot.last == ctx->evTurn) slot.last = nullptr;
+        cudaEventDestroy(ctx->evTurn);
+    }
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     if (ctx->evTail) cudaEventDestroy(ctx->evTail);
@@ -713,9 +748,11 @@ static bool mma_factor_count(int32_t F) { return F == 16 || F == 32 || F == 48 |
 
 // Calls in flight on one GPU (one context and one host thread each, so that a step's copies ride under another step's
 // kernels) drift into step when their kernels are allowed to interleave: both then compute at half speed, finish together
-// and copy together with the SMs idle.  With turns, a call enqueues its uploads, then waits for the device's token, holds
-// it from its first kernel to the host sync that ends its last one, and downloads after handing it on.
-static std::mutex g_simulate_turn[64];
+// and copy together with the SMs idle.  With turns the kernels of the calls run one call after the other ON THE GPU: a call
+// enqueues its uploads, takes the device's token, makes its stream wait for the event the previous holder recorded behind
+// its last kernel, enqueues its own kernels, records its own event and hands the token on -- all before its first host
+// sync, so the token is held for the ~0.1 ms of enqueueing, not for the milliseconds the kernels take, and the next
+// call's kernels are already queued when this call's finish.  Downloads happen outside.
 static constexpr double kSimulateTurnBytes = 48e6; // uploads per call from which turns pay (measured: profiles/r2/optimization_log.md)
 
 static bool simulate_takes_turns(const mcp_ctx *ctx, int64_t P, int64_t N, int32_t F)
@@ -741,9 +778,10 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
         MCP_TRY(mcp_upload_exposures(ctx, E, P, F));
         MCP_TRY(mcp_upload_scenarios(ctx, S, N, F));
         {
-            std::unique_lock<std::mutex> turn;
-            if (simulate_takes_turns(ctx, P, N, F)) turn = std::unique_lock<std::mutex>(g_simulate_turn[ctx->device & 63]);
-            MCP_TRY(mcp_run(ctx, alpha, codec_id, framing));
+            int rc = simulate_takes_turns(ctx, P, N, F) ? simulate_turn_begin(ctx) : MCP_OK;
+            if (rc == MCP_OK) rc = mcp_run(ctx, alpha, codec_id, framing);
+            simulate_turn_end(ctx); // (if the run did not get as far as its own hand-over)
+            if (rc != MCP_OK) return rc;
         }
         if (enc_len) *enc_len = ctx->runEncBytes;
         return mcp_fetch(ctx, mean, variance, var_loss, var_trial, cvar, breach_idx, enc_off, enc, enc_cap);
@@ -773,12 +811,9 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
     ctx->sTailPending = true; ctx->sHeadRows = head; ctx->sMidRows = mid;
     ctx->earlyBreachDst = breach_idx;
     ctx->earlyMean = mean; ctx->earlyVar = variance; ctx->earlyVarLoss = var_loss; ctx->earlyVarTrial = var_trial; ctx->earlyCvar = cvar;
-    int rc;
-    {
-        std::unique_lock<std::mutex> turn;
-        if (simulate_takes_turns(ctx, P, N, F)) turn = std::unique_lock<std::mutex>(g_simulate_turn[ctx->device & 63]);
-        rc = mcp_run(ctx, alpha, codec_id, framing);
-    }
+    int rc = simulate_takes_turns(ctx, P, N, F) ? simulate_turn_begin(ctx) : MCP_OK;
+    if (rc == MCP_OK) rc = mcp_run(ctx, alpha, codec_id, framing);
+    simulate_turn_end(ctx); // (if the run did not get as far as its own hand-over)
     ctx->earlyBreachDst = nullptr;
     ctx->earlyMean = ctx->earlyVar = ctx->earlyVarLoss = ctx->earlyCvar = nullptr;
     ctx->earlyVarTrial = nullptr;
