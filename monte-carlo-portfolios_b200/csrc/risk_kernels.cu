@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(256) k_value_generic(const double *__restrict_
 // shared-memory operand fetch per 256 fma instead of one per 64: the scalar DFMA version of this kernel
 // (git history) was shared-memory-bandwidth bound at 48 % of the FP64 peak.  (tcgen05 has no FP64 kind.)
 //
-// "E-stationary": a warp keeps the A fragments of VM_G = 2 portfolio groups (16 portfolios x all F factors) in
-// registers and streams trials past them; a CTA = 8 warps = 128 portfolios x one trial sub-chunk.  The scenario rows of
-// the sub-chunk arrive in B-FRAGMENT ORDER (k_repack_scenarios), so a stage of 32 trials is ONE contiguous block: a
-// single cp.async.bulk (TMA bulk copy, SASS UBLKCP) by one elected thread, completing on mbarriers, 4 stages deep, and
+// "E-stationary": a warp keeps the A fragments of VM_G portfolio groups (two up to F = 48: 16 portfolios x all F factors; four
+// at F = 64) in registers and streams trials past them; a CTA = 8 warps = 128 (256) portfolios x one trial sub-chunk.  The
+// scenario rows of the sub-chunk arrive in B-FRAGMENT ORDER (k_repack_scenarios), so a stage of 128 trials is ONE contiguous
+// block: a single cp.async.bulk (TMA bulk copy, SASS UBLKCP) by one elected thread, completing on mbarriers, 2 stages deep, and
 // every B-fragment load reads 32 consecutive doubles -- bank-conflict free without padding.  Fused on each value while
 // it is still in a register:
 //   * moments (MOMENTS variant only): d = V - c_p (c_p = V[p][trial 0]), s1 += d, s2 = fma(d,d,s2)
@@ -2243,9 +2243,8 @@ static int risk_stream_core(mcp_ctx *ctx, StreamIO &io, int64_t t, bool optimist
     size_t budget = ctx->prop.totalGlobalMem / 4;
     if (budget > ((size_t)40 << 30)) budget = (size_t)40 << 30;
     int64_t Pt = P;
-    // Portfolio tiles alternate between two streams: the selection / compaction kernels of one tile (latency-bound,
-    // small CTAs) then run under the valuation kernel of the next (DMMA-bound, one 512-thread CTA per SM that leaves
-    // registers and shared memory for them) instead of after it.
+    // overlap_tiles > 1 (off by default): portfolio tiles alternate between two streams, so that the selection / compaction
+    // kernels of one tile (latency-bound, small CTAs) run under the valuation kernel of the next instead of after it.
     const int VM_PG = vm_pg(ctx->F);
     const int64_t groups = (P + VM_PG - 1) / VM_PG;
     const int64_t want_tiles = ctx->overlapTiles > 1 && groups >= 2 * ctx->overlapTiles ? ctx->overlapTiles : 1;
