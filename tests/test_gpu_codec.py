@@ -216,6 +216,39 @@ def test_fastpfor_fast_decode_rejects_malformed_pages(ctx):
         assert e.value.code == N.MCP_E_FORMAT, what
 
 
+@pytest.mark.parametrize("framing", [N.FRAME_WORDS, N.FRAME_APP], ids=["words", "app"])
+@pytest.mark.parametrize("codec", [N.CODEC_FASTPFOR128_VB | N.FLAG_DELTA, N.CODEC_XOR128_IVB, N.CODEC_OPTPFD_VB | N.FLAG_DELTA],
+                         ids=["fastpfor128", "xor128", "optpfd"])
+def test_flat_decoder_rejects_malformed_blocks_in_page_tiles(ctx, codec, framing):
+    """Lists of ~110 values under the 128-int codecs: the flat decoder leaves the tiles that hold a block to
+    k_vb4_decode_pages; a damaged block there must end in MCP_E_FORMAT (never in a read or write outside the buffers),
+    and the undamaged stream must still decode."""
+    rng = np.random.default_rng(31)
+    vals, off = _awkward("near128", rng)
+    out_off, out = ctx.codec_encode(codec, framing, vals, off)
+    assert np.array_equal(ctx.codec_decode(codec, framing, out, out_off, off), vals)
+    lens = np.diff(off)
+    victims = [int(i) for i in np.flatnonzero(lens >= 128)[:6]]
+    assert victims
+    swap = (lambda x: int(np.uint32(x).byteswap())) if framing == N.FRAME_APP else (lambda x: int(x))
+    for i in victims:
+        for what in ("count word", "first block word", "truncated"):
+            bad, boff = out.copy(), out_off.copy()
+            w = bad.view(np.uint32)
+            p0 = int(out_off[i] // 4)
+            if what == "count word":
+                w[p0] = swap(128 * 5)                      # the first stage claims more blocks than the list has
+            elif what == "first block word":
+                w[p0 + 1] = swap(0x7fffff4d)               # FastPFOR: where_meta outside the list; Xor / OptPFD: widths > 32 / S16 words beyond it
+            else:
+                boff = out_off.copy()
+                boff[i + 1:] -= 16                         # the list loses its last four words
+                bad = np.concatenate([out[: out_off[i + 1] - 16], out[out_off[i + 1]:]])
+            with pytest.raises(mcp_b200.McpError) as e:
+                ctx.codec_decode(codec, framing, bad, boff, off)
+            assert e.value.code == N.MCP_E_FORMAT, (i, what)
+
+
 def test_multipage_fastpfor(ctx):
     """> 65 536 ints: FastPFOR pages (FastPFOR.java:98-102), including the stale exception-buffer padding that a
     Java instance carries from page to page (FastPFOR.java:143): bytes identical to the oracle's emulation."""
