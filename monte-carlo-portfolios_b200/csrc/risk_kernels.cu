@@ -1075,11 +1075,23 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
             __syncthreads();
             const int4 *R = reinterpret_cast<const int4 *>(rowp);
             const int total = segoff[a.nsub];
-#pragma unroll 4
-            for (int i = tid; i < total; i += THREADS) {
-                const int g = (int)sidx[kn + i];
-                const int4 rec = __ldg(R + (int64_t)g * a.sub_len + (i - segoff[g]));
-                put(kn + i, fkey(0.0 - __hiloint2double(rec.y, rec.x)), (uint32_t)rec.z);
+            // four records per thread and round: all four labels are read and all four loads issued before the first slot is
+            // rewritten (labels and results share `sidx`: left to the compiler, every load waited for the store before it)
+            for (int i0 = tid; i0 < total; i0 += 4 * THREADS) {
+                int4 rec[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * THREADS;
+                    if (i < total) {
+                        const int g = (int)sidx[kn + i];
+                        rec[u] = __ldg(R + (int64_t)g * a.sub_len + (i - segoff[g]));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * THREADS;
+                    if (i < total) put(kn + i, fkey(0.0 - __hiloint2double(rec[u].y, rec[u].x)), (uint32_t)rec[u].z);
+                }
             }
         } else {
             const double *V = reinterpret_cast<const double *>(rowp);
@@ -1767,13 +1779,26 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsel_sparse(const SelArgs a, 
     for (int j = 0; j < c1; ++j) W.idx[kn + tot0 + i1 - c1 + j] = (uint32_t)(lane + 32);
     __syncwarp();
     const int4 *R = reinterpret_cast<const int4 *>(reinterpret_cast<const unsigned char *>(a.cand) + row * a.pitch);
-    for (int i = lane; i < total; i += 32) {
-        const int g = (int)W.idx[kn + i];
-        const int4 rec = __ldg(R + (int64_t)g * a.sub_len + (i - W.segoff[g]));
-        const uint64_t k = fkey(0.0 - __hiloint2double(rec.y, rec.x));
-        W.key[kn + i] = k;
-        W.idx[kn + i] = (uint32_t)rec.z;
-        mn = k < mn ? k : mn; mx = k > mx ? k : mx;
+    for (int i0 = lane; i0 < total; i0 += 128) { // four records per lane and round: four loads in flight (see k_select_t)
+        int4 rec[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < total) {
+                const int g = (int)W.idx[kn + i];
+                rec[u] = __ldg(R + (int64_t)g * a.sub_len + (i - W.segoff[g]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i < total) {
+                const uint64_t k = fkey(0.0 - __hiloint2double(rec[u].y, rec[u].x));
+                W.key[kn + i] = k;
+                W.idx[kn + i] = (uint32_t)rec[u].z;
+                mn = k < mn ? k : mn; mx = k > mx ? k : mx;
+            }
+        }
     }
     __syncwarp();
     ws_select(W, M, t, 0, mn, mx, kk, ki, a, row, lane);
@@ -1827,12 +1852,32 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap_t(const uint64_
     int *pre = reinterpret_cast<int *>(bm + nwords);                 // [nwords] kept trials before this word
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (kept_idx[row * t] < 0) return; // row failed its optimistic bound: redone separately (k_select)
+    // the kept tail is read ONCE, up front (up to FIN_PER entries per thread in registers; all loads in flight while the
+    // bitmap is zeroed): read where it is used, the kernel paid three dependent global round trips per row
+    constexpr int FIN_PER = 4;
+    const bool inreg = t <= (int64_t)FIN_PER * FIN_THREADS;
+    int32_t rid[FIN_PER];
+    uint64_t rkey[FIN_PER];
+    if (inreg) {
+#pragma unroll
+        for (int u = 0; u < FIN_PER; ++u) {
+            const int i = tid + u * FIN_THREADS;
+            rid[u] = i < t ? __ldg(kept_idx + row * t + i) : 0;
+            rkey[u] = i < t ? __ldg(kept_key + row * t + i) : 0ull;
+        }
+    }
     for (int i = tid; i < nwords; i += FIN_THREADS) bm[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < t; i += FIN_THREADS) {
-        const int32_t id = kept_idx[row * t + i] - trial_base;
-        atomicOr(&bm[id >> 5], 1u << (id & 31));
+    const int failed = tid == 0 && (inreg ? rid[0] : kept_idx[row * t]) < 0;
+    if (__syncthreads_or(failed)) return; // row failed its optimistic bound: redone separately (k_select)
+    if (inreg) {
+#pragma unroll
+        for (int u = 0; u < FIN_PER; ++u)
+            if (tid + u * FIN_THREADS < t) { const int32_t id = rid[u] - trial_base; atomicOr(&bm[id >> 5], 1u << (id & 31)); }
+    } else {
+        for (int i = tid; i < t; i += FIN_THREADS) {
+            const int32_t id = kept_idx[row * t + i] - trial_base;
+            atomicOr(&bm[id >> 5], 1u << (id & 31));
+        }
     }
     __syncthreads();
     // exclusive prefix of the word popcounts: each thread owns a contiguous run of words
@@ -1853,12 +1898,23 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_bitmap_t(const uint64_
     __syncthreads();
     // every kept trial knows its rank in the ascending list: emit the trial and park its loss at that rank
     int32_t *dst = breach + row * t;
-    for (int i = tid; i < t; i += FIN_THREADS) {
-        const int32_t gid = kept_idx[row * t + i];
-        const int32_t id = gid - trial_base;
-        const int rank = pre[id >> 5] + __popc(bm[id >> 5] & ((1u << (id & 31)) - 1u));
-        dst[rank] = gid;
-        sl[rank] = fkey_inv(kept_key[row * t + i]);
+    if (inreg) {
+#pragma unroll
+        for (int u = 0; u < FIN_PER; ++u)
+            if (tid + u * FIN_THREADS < t) {
+                const int32_t id = rid[u] - trial_base;
+                const int rank = pre[id >> 5] + __popc(bm[id >> 5] & ((1u << (id & 31)) - 1u));
+                dst[rank] = rid[u];
+                sl[rank] = fkey_inv(rkey[u]);
+            }
+    } else {
+        for (int i = tid; i < t; i += FIN_THREADS) {
+            const int32_t gid = kept_idx[row * t + i];
+            const int32_t id = gid - trial_base;
+            const int rank = pre[id >> 5] + __popc(bm[id >> 5] & ((1u << (id & 31)) - 1u));
+            dst[rank] = gid;
+            sl[rank] = fkey_inv(kept_key[row * t + i]);
+        }
     }
     __syncthreads();
     // CVaR = mean tail loss, summed in list order with a fixed tree: bit-reproducible whatever order the
