@@ -984,8 +984,18 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
     int32_t *ki = a.kept_idx_out + row * t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // what the row needs first -- the "lost" mark, this thread's entry of the kept tail, its segment count -- is requested
+    // before anything is waited for (one global round trip instead of three)
+    const bool kflat = a.kept_n > 0 && a.kept_segs <= 1;
+    int32_t first = 0, pcnt = 0;
+    uint64_t pk = 0;
+    uint32_t pi = 0;
+    if (kflat) first = a.kept_idx_in[row * a.kept_n];
+    const bool have_pk = tid < a.kept_n;
+    if (have_pk) kept_at(a, row, tid, pk, pi);
+    if (a.cnt && tid < a.nsub) pcnt = a.cnt[row * a.nsub + tid];
     // a row that already lost its optimistic bet at an earlier step stays lost (it is redone separately)
-    if (a.kept_n > 0 && a.kept_segs <= 1 && a.kept_idx_in[row * a.kept_n] < 0) {
+    if (kflat && first < 0) {
         if (tid == 0) ki[0] = -1;
         return;
     }
@@ -1013,7 +1023,8 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
     int64_t M;
     if (a.cnt) {
         // exclusive prefix of the segment counts: coalesced load, every thread scans a contiguous run, block scan
-        for (int sgi = tid; sgi < a.nsub; sgi += THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
+        if (tid < a.nsub) segoff[tid + 1] = pcnt;
+        for (int sgi = tid + THREADS; sgi < a.nsub; sgi += THREADS) segoff[sgi + 1] = a.cnt[row * a.nsub + sgi];
         if (tid == 0) segoff[0] = 0;
         __syncthreads();
         const int per = (a.nsub + THREADS - 1) / THREADS;
@@ -1058,7 +1069,8 @@ __device__ void select_t_row(const SelArgs &a, const int64_t row)
             mn = k < mn ? k : mn; mx = k > mx ? k : mx;
         };
         const int kn = (int)a.kept_n;
-        for (int i = tid; i < kn; i += THREADS) {
+        if (have_pk) put(tid, pk, pi);
+        for (int i = tid + THREADS; i < kn; i += THREADS) {
             uint64_t k; uint32_t id;
             kept_at(a, row, i, k, id);
             put(i, k, id);
@@ -1736,14 +1748,22 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsel_sparse(const SelArgs a, 
     uint64_t *kk = a.kept_key_out + row * a.tail;
     int32_t *ki = a.kept_idx_out + row * a.tail;
     const int kn = (int)a.kept_n;
+    // everything the row needs first -- the kept tail (two entries per lane), the segment counts -- is requested before
+    // anything is waited for: one global round trip instead of three
+    const uint64_t *kin = a.kept_key_in + row * a.kept_n;
+    const int32_t *iin = a.kept_idx_in + row * a.kept_n;
+    uint64_t pk0 = 0, pk1 = 0;
+    int32_t pi0 = 0, pi1 = 0;
+    if (lane < kn) { pk0 = kin[lane]; pi0 = iin[lane]; }
+    if (lane + 32 < kn) { pk1 = kin[lane + 32]; pi1 = iin[lane + 32]; }
+    int c0 = lane < a.nsub ? a.cnt[row * a.nsub + lane] : 0;
+    int c1 = lane + 32 < a.nsub ? a.cnt[row * a.nsub + lane + 32] : 0;
     // a row that already lost its optimistic bet at an earlier step stays lost (it is redone separately)
-    if (kn > 0 && a.kept_idx_in[row * a.kept_n] < 0) {
+    if (kn > 0 && __shfl_sync(kFullMask, pi0, 0) < 0) {
         if (lane == 0) ki[0] = -1;
         return;
     }
     // ---- segment books: exclusive prefix of the counts (two segments per lane)
-    int c0 = lane < a.nsub ? a.cnt[row * a.nsub + lane] : 0;
-    int c1 = lane + 32 < a.nsub ? a.cnt[row * a.nsub + lane + 32] : 0;
     int i0 = c0, i1 = c1;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1770,9 +1790,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32) k_wsel_sparse(const SelArgs a, 
     if (lane == 0) W.segoff[WS_MAXSEG] = total;
     // ---- stage: the kept tail, then the records (every lane labels the slots of its segments, a flat loop loads them)
     uint64_t mn = ~0ull, mx = 0;
-    for (int i = lane; i < kn; i += 32) {
-        const uint64_t k = a.kept_key_in[row * a.kept_n + i];
-        W.key[i] = k; W.idx[i] = (uint32_t)a.kept_idx_in[row * a.kept_n + i];
+    if (lane < kn) { W.key[lane] = pk0; W.idx[lane] = (uint32_t)pi0; mn = pk0; mx = pk0; }
+    if (lane + 32 < kn) { W.key[lane + 32] = pk1; W.idx[lane + 32] = (uint32_t)pi1; mn = pk1 < mn ? pk1 : mn; mx = pk1 > mx ? pk1 : mx; }
+    for (int i = lane + 64; i < kn; i += 32) {
+        const uint64_t k = kin[i];
+        W.key[i] = k; W.idx[i] = (uint32_t)iin[i];
         mn = k < mn ? k : mn; mx = k > mx ? k : mx;
     }
     for (int j = 0; j < c0; ++j) W.idx[kn + i0 - c0 + j] = (uint32_t)lane;
