@@ -247,6 +247,7 @@ int gen_breach_lists(mcp_ctx *ctx, int64_t nlists, int32_t n_trials, double rate
                      int64_t *total);
 int64_t risk_first_step_len(int64_t N, int64_t t);
 void risk_set_dense_floor(int64_t v);
+void risk_set_dense_mult(int64_t v);
 int build_exposures(mcp_ctx *ctx, const int32_t *d_inst, const double *d_w, const int64_t *d_off, int64_t P, const double *d_B,
                     int64_t n_inst, int32_t F, double *d_E);
 int fp64_peak(mcp_ctx *ctx, double *tflops);

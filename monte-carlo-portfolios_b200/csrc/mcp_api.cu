@@ -211,6 +211,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);
+    else if (!strcmp(key, "dense_mult")) risk_set_dense_mult(value);
     else if (!strcmp(key, "overlap_tiles")) ctx->overlapTiles = value < 1 ? 1 : value;
     else if (!strcmp(key, "ts_slack")) ctx->tsSlackOverride = value; // trial-sharded test hook: m = ceil(t / world) + value (-1 = automatic)
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;

@@ -1998,11 +1998,13 @@ constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail siz
 // length of the dense first step: ~4 tail sizes, at least kDenseFloor trials, a multiple of 8 (tensor-core trial blocks)
 static int64_t g_dense_floor = 1024; // process-wide tuning knob (mcp_set_option "dense_floor"); 1 024: C3 6.93 ms vs 7.17 at 2 048
 void risk_set_dense_floor(int64_t v) { g_dense_floor = v < 64 ? 64 : v; }
+static int64_t g_dense_mult = 4;     // tail sizes in the dense first step (mcp_set_option "dense_mult")
+void risk_set_dense_mult(int64_t v) { g_dense_mult = v < 1 ? 1 : (v > 16 ? 16 : v); }
 // `two_step` (optimistic schedule): the sample only has to pin down a quantile, so it is capped at the 4 096 values the
 // register-resident selection handles -- for large tails the bound gets relatively tighter, not looser (r ~ t n0 / N).
 static int64_t first_step_len(int64_t N, int64_t t, bool two_step = false)
 {
-    int64_t c0 = 4 * t;
+    int64_t c0 = (two_step ? g_dense_mult : 4) * t;
     if (c0 < g_dense_floor) c0 = g_dense_floor;
     if (two_step && c0 > 16 * SEL_THREADS) c0 = 16 * SEL_THREADS;
     c0 = (c0 + 7) & ~(int64_t)7;
