@@ -3729,12 +3729,22 @@ int exclusive_scan_i64(mcp_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_
 // ---- fast-path launchers -------------------------------------------------------------------------------------
 // lists per batch: fill ~92 % of the value staging area on average (a batch that overflows is still handled, by the
 // per-warp routines); 0 = the fast path is not worth it (long lists: the per-warp kernels are the better fit)
-static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists)
+static int fast_lists_per_batch(int codec, int64_t total_vals, int64_t nlists, int64_t uniform_len = 0)
 {
     if (nlists <= 0) return 0;
     const CodecTraits tr = codec_traits(codec);
     const double avg = (double)total_vals / (double)nlists;
     if (avg > (tr.fastpfor ? 4000.0 : 1024.0)) return 0; // (a FastPFOR batch may be a single list of up to FE_VCAP values)
+    if (uniform_len > 0 && tr.fastpfor) {
+        // lists of one known length (the risk step's breach lists): the staging areas can be filled exactly -- 1 001-int lists
+        // go four to a batch (96 of 128 threads hold a 32-value group) instead of three
+        const int64_t tail = uniform_len % tr.fp_block;
+        int64_t g = FE_VCAP / uniform_len;
+        if (tail > 0 && FE_TCAP / tail < g) g = FE_TCAP / tail;
+        const int64_t nb = uniform_len / tr.fp_block;
+        if (nb > 0 && g * nb > FP_MAXBLK) g = FP_MAXBLK / nb;
+        return (int)(g < 1 ? 1 : (g > FP_MAXL ? FP_MAXL : g));
+    }
     int64_t g = (int64_t)(0.92 * FE_VCAP / (avg > 1.0 ? avg : 1.0));
     int64_t gmax = FE_MAXL;
     if (tr.fastpfor) { // VariableByte tails of up to block-1 values per list share the tail table
@@ -3860,7 +3870,7 @@ int codec_fast_encode(mcp_ctx *ctx, int codec_id, int framing, const int32_t *d_
         const bool flat = pass == 0 && !codec_traits(a.codec).blocks && ctx->flatCodec;
         if (pass == 0 && flat_only && !flat) return MCP_E_UNSUPPORTED;
         a.lists_per_batch = pass == 0 ? (flat ? vbf_lists_per_tile(total_vals, nlists, 0.93 * VB4::SPAN, VB4::MAXL) : 32)
-                                      : fast_lists_per_batch(a.codec, total_vals, nlists);
+                                      : fast_lists_per_batch(a.codec, total_vals, nlists, uniform_len);
         a.nbatches = (nlists + a.lists_per_batch - 1) / a.lists_per_batch;
         if (a.nbatches > 0x7fffffff) return fail(ctx, MCP_E_ARG, "encode: too many lists for one call");
         // scratch: [ticket u64][total i64][err i32][pad][deferred tiles i32][pad][state u64 x nbatches][deferred tile ids i32 x nbatches]
