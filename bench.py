@@ -542,6 +542,7 @@ def c5_leg(job, steps, warmup):
     if world > 1:
         job.dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(uid[0], rank, world)
+    ctx.set_option("ts_exchange", 0 if args.c5_allgather else 1)
     n_global, base = Nl * world, rank * Nl
     ctx.generate_exposures(P, F, seed, E_SCALE, 0.0)
     ctx.generate_scenarios(Nl, F, seed, 1.0, S_DRIFT, row0=base)
@@ -580,6 +581,10 @@ def c5_leg(job, steps, warmup):
             if n_global * F * 8 <= (3 << 30) else 0
     if rank == 0:
         gathered = block * world
+        # a rank merges only its own portfolio slice, so it is sent only that slice of every other rank's block (grouped
+        # ncclSend / ncclRecv, option ts_exchange = 1, the default); ts_exchange = 0 is the all-gather of whole blocks
+        slices = not args.c5_allgather
+        moved = (block - 64) * (world - 1) // world + 64 * (world - 1) if slices else gathered - block
         out = {"metric": METRIC, "value": P * n_global / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                "ms_per_step": ms_per_step, "scaling": "weak (trials per GPU fixed)",
                "config": {"workload": workload_string("c5", world) if not args.c5_portfolios else f"c5 with {P} portfolios",
@@ -587,9 +592,13 @@ def c5_leg(job, steps, warmup):
                           "inputs": "Philox4x32-10 synthetic E and S generated on device (S rows by global trial index), resident in HBM",
                           "l2": "L2 flushed before every timed step; CUDA events on the library's stream, max over ranks",
                           "second_round_rows": stats["fallback_rows"]},
-               "collective": {"name": "ncclAllGather (one per step; + one byte per portfolio of exactness flags)", "bytes_sent_per_rank": block,
-                              "bytes_received_per_rank": gathered - block, "ms_per_step": comm_ms,
-                              "achieved_gbs_received": (gathered - block) / (comm_ms * 1e-3) / 1e9 if comm_ms > 0 else None,
+               "collective": {"name": ("slice exchange: one group of ncclSend / ncclRecv per step -- every rank receives its own portfolio slice of "
+                                       "every other rank's candidate block (1 / world of what an all-gather of the blocks moves; --c5-allgather "
+                                       "runs that instead)" if slices else "ncclAllGather of the ranks' candidate blocks (one per step)")
+                                      + "; + an ncclAllGather of one byte per portfolio of exactness flags",
+                              "bytes_sent_per_rank": moved if slices else block, "bytes_received_per_rank": moved, "ms_per_step": comm_ms,
+                              "all_gather_bytes_received_per_rank": gathered - block,
+                              "achieved_gbs_received": moved / (comm_ms * 1e-3) / 1e9 if comm_ms > 0 else None,
                               "peer_copy_peak_gbs": 770.0, "peak_source": "SURVEY.md 8(e): measured peer-copy bandwidth per direction"},
                "roofline": {"bound": "tensor", "kernel": "k_value_mma", "achieved": flops / (v_ms * 1e-3) / 1e12, "peak": pk, "unit": "TFLOP/s",
                             "frac": flops / (v_ms * 1e-3) / 1e12 / pk, "traffic": job.traffic("c5"), "peak_source": job.peak_source,
@@ -757,6 +766,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-codec", action="store_true")
+    ap.add_argument("--c5-allgather", action="store_true", help="c5: exchange whole candidate blocks by ncclAllGather (ts_exchange = 0)")
     ap.add_argument("--simulate-turns", type=int, default=-1, help="experiments: force mcp_set_option('simulate_turns') in the e2e leg")
     ap.add_argument("--no-extras", action="store_true", help="only the headline leg (profiling runs under ncu)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check after the timed region")

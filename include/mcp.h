@@ -276,7 +276,10 @@ int mcp_simulate(mcp_ctx *ctx, const double *E, int64_t P, const double *S, int6
 /* ------------------------------------------------- trial-sharded mode (optional)
  * BASELINE config C5: every rank holds ALL exposure rows and a contiguous shard of the scenario rows (trials
  * [trial_base, trial_base + N_local) of n_global, balanced: N_local <= ceil(n_global / world)).  Per portfolio the
- * global tail is found from the ranks' local top-m candidates (m ~ tail/world + 6 sigma) exchanged by ONE all-gather
+ * global tail is found from the ranks' local top-m candidates (m ~ tail/world + 6 sigma), exchanged ONCE: a rank merges its
+ * own portfolio slice, so mcp_run_trial_sharded sends it only that slice of every other rank's candidate block (one group
+ * of ncclSend / ncclRecv; option "ts_exchange" 0 = ncclAllGather of the whole blocks, world times the bytes; the phase
+ * calls below leave the transport to the caller and work with whole gathered blocks or with the slices in place)
  * (plus one byte per portfolio saying whether that was provably enough); rows for which it was not (adversarial
  * trial orders) go through a second round with the full local tails, so results are exact for any input.  After the run, rank g holds the results of its portfolio slice
  * [P g / world, P (g+1) / world) (same split as portfolio sharding): mcp_run_sizes / mcp_fetch return that slice.
@@ -319,7 +322,7 @@ enum {
     MCP_K_SCAN = 4,    /* prefix sums / bookkeeping                     */
     MCP_K_GEN = 5,     /* generators, FP64 peak probe                   */
     MCP_K_MOMENTS = 6, /* mean / variance (on a side stream: overlaps the valuation) */
-    MCP_K_COMM = 7,    /* NCCL all-gather of the trial-sharded mode             */
+    MCP_K_COMM = 7,    /* NCCL exchange of the trial-sharded mode               */
     MCP_K_COUNT = 8
 };
 int mcp_profile_enable(mcp_ctx *ctx, int on);

@@ -97,6 +97,7 @@ struct mcp_ctx {
     int64_t runFallbackRows = 0;   // rows the last run had to redo with the guaranteed schedule
     // trial-sharded mode (risk_kernels.cu): state between the phase calls
     int64_t tsT = 0, tsM = 0, tsNGlobal = 0, tsTrialBase = 0, tsNFlag = 0, tsSlackOverride = -1;
+    bool tsSliceExchange = true;   // trial-sharded: ranks exchange portfolio SLICES of their blocks (grouped send / recv), not whole blocks
     int tsWorld = 0, tsRank = -1;
     const unsigned char *tsGath = nullptr; // first-round gathered blocks (caller- or library-owned), needed until ts_finish
     std::vector<int32_t> tsFlagRows;
@@ -265,6 +266,13 @@ int nccl_unique_id(unsigned char id[128], std::string *err);
 int nccl_comm_init(mcp_ctx *ctx, const unsigned char id[128], int rank, int world);
 void nccl_comm_destroy(mcp_ctx *ctx);
 int nccl_all_gather(mcp_ctx *ctx, const void *send, void *recv, size_t bytes);
+bool nccl_has_send_recv();
+// One region of the ranks' exchange blocks: `head` bytes at `off` that every peer gets as they are, or rows of `row_bytes`
+// bytes from `off` on, of which peer d gets rows [p0[d], p0[d + 1]).
+struct ExchRegion { size_t off, row_bytes, head; };
+int nccl_slice_exchange(mcp_ctx *ctx, const unsigned char *send_block, unsigned char *recv_base, size_t block_bytes,
+                        const ExchRegion *regions, int nregions, const int64_t *p0 /* [world + 1] */);
+int risk_ts_exchange_regions(mcp_ctx *ctx, int world, ExchRegion regions[5], int64_t *p0 /* [world + 1] */);
 int nccl_rank_world(mcp_ctx *ctx, int *rank, int *world);
 
 } // namespace mcp

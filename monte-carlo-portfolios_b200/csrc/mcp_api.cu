@@ -213,6 +213,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "dense_floor")) risk_set_dense_floor(value);
     else if (!strcmp(key, "dense_mult")) risk_set_dense_mult(value);
     else if (!strcmp(key, "overlap_tiles")) ctx->overlapTiles = value < 1 ? 1 : value;
+    else if (!strcmp(key, "ts_exchange")) ctx->tsSliceExchange = value != 0;
     else if (!strcmp(key, "ts_slack")) ctx->tsSlackOverride = value; // trial-sharded test hook: m = ceil(t / world) + value (-1 = automatic)
     else if (!strcmp(key, "item_trials")) ctx->itemTrials = value < 64 ? 64 : value;
     else return fail(ctx, MCP_E_ARG, "set_option: unknown key");
@@ -921,8 +922,17 @@ int mcp_run_trial_sharded(mcp_ctx *ctx, double alpha, int codec_id, int framing,
     MCP_TRY(risk_ts_local(ctx, alpha, n_global, trial_base, world, &blk, &bytes));
     MCP_CUDA(ctx, ctx->dTsRecv.reserve((size_t)bytes * world));
     {
+        // the one exchange of the common case.  A rank merges only ITS portfolio slice, so it needs only that slice of every
+        // other rank's block: a grouped send / recv of slices (1/world of the all-gather's bytes, same addresses) unless the
+        // option or the NCCL at hand says otherwise
         KScope ks(ctx, MCP_K_COMM);
-        MCP_TRY(nccl_all_gather(ctx, blk, ctx->dTsRecv.p, (size_t)bytes)); // the one exchange of the common case
+        if (ctx->tsSliceExchange && world > 1 && world <= 64 && nccl_has_send_recv()) {
+            ExchRegion regions[5];
+            int64_t p0[65];
+            MCP_TRY(risk_ts_exchange_regions(ctx, world, regions, p0));
+            MCP_TRY(nccl_slice_exchange(ctx, reinterpret_cast<const unsigned char *>(blk), ctx->dTsRecv.as<unsigned char>(), (size_t)bytes, regions, 5, p0));
+        } else
+            MCP_TRY(nccl_all_gather(ctx, blk, ctx->dTsRecv.p, (size_t)bytes));
     }
     void *flags = nullptr;
     int64_t fbytes = 0;

@@ -2877,6 +2877,25 @@ static void ts_slice(int64_t P, int rank, int world, int64_t &p0, int64_t &p1)
     p1 = p0 + base + (rank < extra ? 1 : 0);
 }
 
+// What the merge below (and the pooled moments) read of the ranks' first-round blocks: the header, and the keys / trial
+// indices / mean / variance of the reader's own portfolio slice -- an eighth of each block on eight GPUs.
+int risk_ts_exchange_regions(mcp_ctx *ctx, int world, ExchRegion regions[5], int64_t *p0)
+{
+    if (ctx->tsWorld != world || world < 1) return fail(ctx, MCP_E_STATE, "ts exchange: call ts_local first (same world)");
+    const TsLayout L = ts_layout(ctx->P, ctx->tsM);
+    regions[0] = ExchRegion{0, 0, 64};
+    regions[1] = ExchRegion{(size_t)L.off_keys, (size_t)L.m * 8, 0};
+    regions[2] = ExchRegion{(size_t)L.off_mean, 8, 0};
+    regions[3] = ExchRegion{(size_t)L.off_var, 8, 0};
+    regions[4] = ExchRegion{(size_t)L.off_idx, (size_t)L.m * 4, 0};
+    for (int g = 0; g < world; ++g) {
+        int64_t a, b;
+        ts_slice(ctx->P, g, world, a, b);
+        p0[g] = a; p0[g + 1] = b;
+    }
+    return MCP_OK;
+}
+
 // Merge THIS RANK'S portfolio slice from the gathered blocks and test it; the slice's flags (one byte per row, padded to
 // ceil(P / world) bytes so that every rank's block has the same size) are what the ranks exchange next.
 int risk_ts_merge(mcp_ctx *ctx, const void *d_gathered, int rank, void **d_flags, int64_t *flag_bytes)

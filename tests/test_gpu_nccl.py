@@ -1,4 +1,5 @@
-"""Trial-sharded mode over NCCL (the real all-gather inside libmcp.so): two processes, one GPU each.
+"""Trial-sharded mode over NCCL (the real exchange inside libmcp.so -- slices by grouped send / recv, or the all-gather of
+whole blocks): two processes, one GPU each.
 Needs a box with >= 2 GPUs (`gpurun --gpus 2`); on a 1-GPU box the exchange kernels are still covered by
 tests/test_gpu_trial_sharded.py, which emulates the ranks."""
 import numpy as np
@@ -28,9 +29,10 @@ def _gpu_count() -> int:
 
 def _worker(rank, world, uid_q, out_q, case):
     import mcp_b200
-    E, S, alpha = case
+    E, S, alpha, exchange = case
     try:
         ctx = mcp_b200.Context(rank)
+        ctx.set_option("ts_exchange", exchange)
         if rank == 0:
             uid = ctx.comm_unique_id()
             for _ in range(world - 1):
@@ -61,14 +63,17 @@ def _run(world, case):
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_nccl_allgather_trial_sharded_two_gpus():
-    E, S = riskcases.synthetic(130, 60000, 32, 71)
-    got, fb = _run(2, (E, S, 0.99))
+@pytest.mark.parametrize("exchange", [1, 0], ids=["slices", "allgather"])
+def test_nccl_allgather_trial_sharded_two_gpus(exchange):
+    """ts_exchange = 1 (default): a rank receives only its portfolio slice of the other ranks' blocks (131 rows: slices of
+    66 and 65); 0: the all-gather of whole blocks.  Same results, and the oracle's."""
+    E, S = riskcases.synthetic(131, 60000, 32, 71)
+    got, fb = _run(2, (E, S, 0.99, exchange))
     o = cref.risk(E, S, 0.99)
     assert fb == [0, 0]
     assert np.array_equal(got["var_trial"], o["var_trial"]) and np.array_equal(got["var_loss"], o["var_loss"])
     assert np.array_equal(got["breach"], o["breach"])
-    for p in (0, 64, 65, 129):
+    for p in (0, 64, 65, 66, 130):
         assert bytes(got["enc"][got["enc_off"][p]: got["enc_off"][p + 1]]) == cref.get_compressed_instruments(CID, o["breach"][p])
     np.testing.assert_allclose(got["variance"], o["variance"], rtol=1e-9, atol=0)
     np.testing.assert_allclose(got["cvar"], o["cvar"], rtol=1e-9, atol=0)
@@ -78,7 +83,7 @@ def test_nccl_allgather_trial_sharded_two_gpus():
     S2[:, 0] = -np.linspace(0.0, 1.0, Nn)
     S2[:, 1] = 1e-3 * np.cos(np.arange(Nn))
     E2 = np.abs(riskcases.synthetic(P, 1, F, 3)[0]) + 1.0
-    got, fb = _run(2, (E2, S2, 0.99))
+    got, fb = _run(2, (E2, S2, 0.99, exchange))
     o = cref.risk(E2, S2, 0.99)
     assert fb == [P, P]
     assert np.array_equal(got["breach"], o["breach"]) and np.array_equal(got["var_trial"], o["var_trial"])
