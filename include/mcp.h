@@ -107,7 +107,9 @@ int  mcp_sync(mcp_ctx *ctx);
  * "warp_select" (0 = dense-step selection staged in shared memory / 256-thread selection CTAs for small tails / no warp-per-row
  * selection of the sparse step for rows of <= 512 candidates), "dense_floor"
  * (smallest dense sample in trials, default 1024; process-wide), "dense_mult" (tail sizes in the dense sample of the
- * optimistic schedule, default 4; process-wide), "overlap_tiles" (> 1 = portfolio tiles alternate between
+ * optimistic schedule, default 4; process-wide), "radix_finalize" (0 = tails of >= 1 024 trials over a trial range too long
+ * for the bitmap are put in order by the bitonic sort instead of the counting kernel), "ts_exchange" (see
+ * mcp_run_trial_sharded), "overlap_tiles" (> 1 = portfolio tiles alternate between
  * two streams), "item_trials" (trials per valuation work item), "upload_split" (0 = mcp_simulate uploads the scenario
  * tail in one part), "simulate_turns" (mcp_simulate calls in flight on one GPU -- one context and host thread each -- take
  * turns on the SMs: a call enqueues its uploads, takes the device's token, makes its kernels wait for the event behind the

@@ -128,6 +128,7 @@ struct mcp_ctx {
     int64_t fastEncodeCalls = 0, fastEncodeFallbacks = 0; // encodes served by the batched kernels / handed back to the warp-per-list ones
     bool smallSelect = true;       // 64-thread selection / compaction CTAs for small tails
     int selSlack = 0;              // extra entries of the sparse steps' staging area (experiment knob)
+    bool radixFinalize = true;     // large tails over long trial ranges: counting finalize (k_finalize_radix) instead of the bitonic sort
     int simulateTurns = -1;        // mcp_simulate calls in flight on one GPU take turns on the SMs: 0 no, 1 yes, -1 by upload size
     cudaEvent_t evTurn = nullptr;  // ... "this call's kernels are done", what the next call's kernels wait for
     bool turnHeld = false;         // this context holds the device's turn token (between simulate_turn_begin and _end)

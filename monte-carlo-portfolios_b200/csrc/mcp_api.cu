@@ -207,6 +207,7 @@ int mcp_set_option(mcp_ctx *ctx, const char *key, int64_t value)
     else if (!strcmp(key, "reg_select")) ctx->regSelect = value != 0;
     else if (!strcmp(key, "warp_select")) ctx->warpSelect = value != 0;
     else if (!strcmp(key, "sel_slack")) ctx->selSlack = (int)value;
+    else if (!strcmp(key, "radix_finalize")) ctx->radixFinalize = value != 0;
     else if (!strcmp(key, "simulate_turns")) ctx->simulateTurns = (int)(value < 0 ? -1 : value > 0 ? 1 : 0);
     else if (!strcmp(key, "upload_split")) ctx->uploadSplit = value != 0;
     else if (!strcmp(key, "small_select")) ctx->smallSelect = value != 0;

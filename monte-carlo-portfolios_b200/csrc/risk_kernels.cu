@@ -1991,6 +1991,115 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize_t(const uint64_t *kept
     if (tid == 0) cvar[row] = s / (double)t;
 }
 
+// Finalize for LARGE tails over a trial range too long for the bitmap (C5: 10 001 of 10 M trials per row): the bitonic sort above
+// is 105 barrier-separated stages over 16 384 padded entries (350 us per row: 29 of C5's 299 ms).  Trial indices are distinct, so
+// an ascending list is two counting steps: (1) bucket = trial >> shift (<= 4 096 buckets of <= 4 096 trials): histogram,
+// exclusive scan, scatter -- the buckets are then in place, their contents in any order; (2) a warp per bucket ranks its
+// entries: up to 32 by comparing one another through shuffles (the common case: ~2.4 entries per bucket), more through a
+// warp-private 4 096-bit bitmap of the bucket's trial range.  The losses land in list order in shared memory and are summed
+// exactly like k_finalize_t does (same thread count, same tree): bit-identical CVaR.
+constexpr int FR_THREADS = 1024, FR_MAXB = 4096, FR_BMW = 128; // buckets; bitmap words per warp (4 096 bits)
+static size_t fin_radix_smem(int64_t t) { return (size_t)(FR_MAXB + 4 + FR_MAXB) * 4 + (size_t)t * 4 + (((size_t)t * 2 + 15) & ~(size_t)15) + (size_t)t * 8 + (size_t)(FR_THREADS / 32) * FR_BMW * 4 + 64; }
+
+__global__ void __launch_bounds__(FR_THREADS, 1) k_finalize_radix(const uint64_t *kept_key, const int32_t *kept_idx, int64_t t64, int shift, int nb,
+                                                                  int32_t *breach, double *cvar)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int s_wsum[FR_THREADS / 32];
+    const int t = (int)t64;
+    double *sl = reinterpret_cast<double *>(smem_raw);                       // [t] losses in ascending-trial order
+    int *off = reinterpret_cast<int *>(sl + t);                              // [FR_MAXB + 4] counts, then exclusive offsets
+    int *cur = off + FR_MAXB + 4;                                            // [FR_MAXB] scatter cursors
+    int32_t *bidx = cur + FR_MAXB;                                           // [t] trial indices, bucket by bucket
+    uint16_t *bsrc = reinterpret_cast<uint16_t *>(bidx + t);                 // [t] where the entry came from
+    uint32_t *bmall = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bsrc) + (((size_t)t * 2 + 15) & ~(size_t)15));
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *ki = kept_idx + row * t64;
+    const uint64_t *kk = kept_key + row * t64;
+    if (ki[0] < 0) return; // row failed its optimistic bound: redone separately (k_select)
+    for (int b = tid; b < FR_MAXB + 4; b += FR_THREADS) off[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < t; i += FR_THREADS) atomicAdd(&off[ki[i] >> shift], 1);
+    __syncthreads();
+    { // exclusive scan of the bucket counts: four buckets per thread
+        const int b0 = 4 * tid;
+        const int c0 = off[b0], c1 = off[b0 + 1], c2 = off[b0 + 2], c3 = off[b0 + 3];
+        const int c = c0 + c1 + c2 + c3;
+        int incl = c;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int run = incl - c;
+        for (int w = 0; w < warp; ++w) run += s_wsum[w];
+        off[b0] = run; cur[b0] = run; run += c0;
+        off[b0 + 1] = run; cur[b0 + 1] = run; run += c1;
+        off[b0 + 2] = run; cur[b0 + 2] = run; run += c2;
+        off[b0 + 3] = run; cur[b0 + 3] = run;
+        if (tid == 0) off[FR_MAXB] = t;
+    }
+    __syncthreads();
+    for (int i = tid; i < t; i += FR_THREADS) {
+        const int32_t id = ki[i];
+        const int pos = atomicAdd(&cur[id >> shift], 1);
+        bidx[pos] = id;
+        bsrc[pos] = (uint16_t)i;
+    }
+    __syncthreads();
+    int32_t *dst = breach + row * t64;
+    uint32_t *bm = bmall + warp * FR_BMW;
+    const uint32_t low = (1u << shift) - 1u;
+    for (int b = warp; b < nb; b += FR_THREADS / 32) {
+        const int o = off[b], c = off[b + 1] - o;
+        if (c == 0) continue;
+        if (c <= 32) {
+            const int32_t id = lane < c ? bidx[o + lane] : 0x7fffffff;
+            int rank = 0;
+            for (int j = 0; j < c; ++j) rank += __shfl_sync(kFullMask, id, j) < id;
+            if (lane < c) {
+                dst[o + rank] = id;
+                sl[o + rank] = fkey_inv(kk[bsrc[o + lane]]);
+            }
+        } else { // a crowded bucket (clustered tail trials): rank through a bitmap of the bucket's trial range
+            for (int w = lane; w < FR_BMW; w += 32) bm[w] = 0;
+            __syncwarp();
+            for (int e = lane; e < c; e += 32) { const uint32_t r = (uint32_t)bidx[o + e] & low; atomicOr(&bm[r >> 5], 1u << (r & 31)); }
+            __syncwarp();
+            const uint32_t w0 = bm[4 * lane], w1 = bm[4 * lane + 1], w2 = bm[4 * lane + 2], w3 = bm[4 * lane + 3];
+            const int mine = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
+            int incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(kFullMask, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const int excl = incl - mine;
+            for (int e0 = 0; e0 < c; e0 += 32) {
+                const int e = e0 + lane;
+                const bool have = e < c;
+                const int32_t id = have ? bidx[o + e] : 0;
+                const uint32_t r = (uint32_t)id & low, wi = r >> 5;
+                int rank = __shfl_sync(kFullMask, excl, (int)(wi >> 2));
+                for (uint32_t q = wi & ~3u; q < wi; ++q) rank += __popc(bm[q]);
+                rank += __popc(bm[wi] & ((1u << (r & 31)) - 1u));
+                if (have) {
+                    dst[o + rank] = id;
+                    sl[o + rank] = fkey_inv(kk[bsrc[o + e]]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double s = 0.0;
+    for (int i = tid; i < t; i += FR_THREADS) s += sl[i];
+    s = block_sum(s, red);
+    if (tid == 0) cvar[row] = s / (double)t;
+}
+
 // ============================================================ host orchestration
 struct Step { int64_t begin, end; int nsub; int sub_len; };
 constexpr int64_t kStepRatio = 3;   // trials seen grow 3x per step: ~2 tail sizes of new candidates per selection pass
@@ -2084,6 +2193,18 @@ static int run_finalize(mcp_ctx *ctx, int64_t rows, int64_t t, const uint64_t *k
         else if (bm_smem > 72 * 1024) k_finalize_bitmap_t<1024><<<(unsigned)rows, 1024, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         else k_finalize_bitmap_t<256><<<(unsigned)rows, 256, bm_smem, cur_stream(ctx)>>>(kk, ki, t, n_trials, 0, breach, cvar);
         return check_launch(ctx, "k_finalize_bitmap");
+    }
+    { // large tails over a trial range of up to 2^24: two counting steps instead of a bitonic sort (k_finalize_radix)
+        int bits = 1;
+        while (bits < 31 && ((int64_t)1 << bits) < n_trials) ++bits;
+        const int shift = bits > 12 ? bits - 12 : 0;
+        if (t >= 1024 && t <= 65535 && shift <= 12 && fin_radix_smem(t) <= 200 * 1024 && ctx->radixFinalize) {
+            const int nb = (int)(((n_trials - 1) >> shift) + 1);
+            MCP_CUDA(ctx, cudaFuncSetAttribute(k_finalize_radix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_radix_smem(t)));
+            KScope ks(ctx, MCP_K_SELECT);
+            k_finalize_radix<<<(unsigned)rows, FR_THREADS, fin_radix_smem(t), cur_stream(ctx)>>>(kk, ki, t, shift, nb, breach, cvar);
+            return check_launch(ctx, "k_finalize_radix");
+        }
     }
     int m = 1;
     while (m < t) m <<= 1;

@@ -150,11 +150,45 @@ def test_large_tails_take_the_wide_selection_kernels(ctx):
     for alpha in (0.95, 0.9, 0.6):
         check_against_oracle(ctx, E, S, alpha, rows=[0, 11, 23])
         assert ctx.run_stats()["fallback_rows"] == 0
-    ctx.set_option("force_sort_finalize", 1)        # the sort-based breach list with 1 024-thread CTAs (tails >= 4 097)
+    ctx.set_option("force_sort_finalize", 1)        # no bitmap over the trial range: the counting finalize (tails >= 1 024) ...
     try:
-        check_against_oracle(ctx, E, S, 0.93, rows=[0, 11, 23])
+        r1 = check_against_oracle(ctx, E, S, 0.93, rows=[0, 11, 23])
+        ctx.set_option("radix_finalize", 0)         # ... and the bitonic sort with 1 024-thread CTAs (tails >= 4 097)
+        r0 = check_against_oracle(ctx, E, S, 0.93, rows=[0, 11, 23])
+        for k in ("breach", "cvar", "enc"):
+            assert np.array_equal(r0[k], r1[k]), k   # (CVaR bit for bit: same summation order)
     finally:
         ctx.set_option("force_sort_finalize", 0)
+        ctx.set_option("radix_finalize", 1)
+
+
+def test_counting_finalize_on_clustered_tails(ctx):
+    """k_finalize_radix: buckets of trial >> shift, then a rank inside each bucket -- by shuffles up to 32 entries, through a
+    warp-private bitmap beyond.  Losses that grow with the trial index put a row's whole tail into consecutive trials, i.e.
+    into a few FULL buckets (300 000 trials: buckets of 128); a second shape has the tail in clusters of ~40."""
+    Nn, F, P = 300_000, 32, 6
+    S = np.zeros((Nn, F))
+    S[:, 0] = -np.linspace(0.0, 1.0, Nn)                       # loss ascending in the trial index: the tail is the last t trials
+    S[:, 1] = 1e-4 * np.cos(np.arange(Nn))
+    E = np.abs(riskcases.synthetic(P, 1, F, 5)[0]) + 1.0
+    rng = np.random.default_rng(17)
+    S2 = rng.standard_normal((Nn, F)) * 0.01
+    centres = rng.choice(Nn - 64, 200, replace=False)
+    for c in centres:                                           # 200 clusters of 40 consecutive bad trials
+        S2[c:c + 40, 0] -= 5.0 + rng.random(40)
+    ctx.set_option("force_sort_finalize", 1)
+    try:
+        for SS, alpha in ((S, 0.99), (S2, 0.975), (S, 0.95)):   # tails of 3 000, 7 500 and 15 000 (the last one: shared memory for 15 000
+            r1 = check_against_oracle(ctx, E, SS, alpha)        #  entries exceeds the kernel's budget -> bitonic sort in global memory)
+            ctx.set_option("radix_finalize", 0)
+            r0 = check_against_oracle(ctx, E, SS, alpha, rows=[0, P - 1])
+            ctx.set_option("radix_finalize", 1)
+            for k in ("breach", "enc"):
+                assert np.array_equal(r0[k], r1[k]), (k, alpha)
+            np.testing.assert_allclose(r0["cvar"], r1["cvar"], rtol=1e-13, atol=0)  # (the 256-thread sort kernel sums in another tree)
+    finally:
+        ctx.set_option("force_sort_finalize", 0)
+        ctx.set_option("radix_finalize", 1)
 
 
 def test_thin_samples_take_a_middle_step(ctx):
