@@ -2021,7 +2021,9 @@ __global__ void __launch_bounds__(FR_THREADS, 1) k_finalize_radix(const uint64_t
     if (ki[0] < 0) return; // row failed its optimistic bound: redone separately (k_select)
     for (int b = tid; b < FR_MAXB + 4; b += FR_THREADS) off[b] = 0;
     __syncthreads();
-    for (int i = tid; i < t; i += FR_THREADS) atomicAdd(&off[ki[i] >> shift], 1);
+    // (trial indices lie in [0, n_trials) by construction; the clamp keeps anything else inside the bucket array)
+    auto bucket_of = [&](int32_t id) -> int { const unsigned b = (unsigned)id >> shift; return (int)(b < (unsigned)nb ? b : (unsigned)nb - 1u); };
+    for (int i = tid; i < t; i += FR_THREADS) atomicAdd(&off[bucket_of(ki[i])], 1);
     __syncthreads();
     { // exclusive scan of the bucket counts: four buckets per thread
         const int b0 = 4 * tid;
@@ -2045,7 +2047,7 @@ __global__ void __launch_bounds__(FR_THREADS, 1) k_finalize_radix(const uint64_t
     __syncthreads();
     for (int i = tid; i < t; i += FR_THREADS) {
         const int32_t id = ki[i];
-        const int pos = atomicAdd(&cur[id >> shift], 1);
+        const int pos = atomicAdd(&cur[bucket_of(id)], 1);
         bidx[pos] = id;
         bsrc[pos] = (uint16_t)i;
     }
